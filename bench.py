@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""Headline benchmark: SR train images/s (forward + loss + backward + Adam) on synthetic
+Food101-shaped crops, BASELINE.json config C2 (ResNet-SR 16 blocks x 64 ch, x4, 64->256, batch 64 per
+GPU, NLPD loss), one process per GPU, weak scaling.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl srk|reference] [--dtype bf16|fp32]
+
+Prints ONE JSON line on rank 0 (see DESIGN.md "Measurement").  `--impl reference` times the CPU port of
+the reference path (oracle/sr_oracle.py: the same ATen calls the reference modules make) on the host
+cores with all threads, on a bounded sample of the same workload."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "food101-super-resolution_b200"))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+ARCH = "RESNET"
+LOSS = "nlpd"
+LR_HW = 64
+SCALE = 4
+BATCH_PER_GPU = 64
+FWD_BWD_GFLOP_PER_IMG = 54.39  # 2*MAC over convs, fwd + dgrad + wgrad (no input dgrad)
+WORKLOAD = "C2: ResNet-SR 16x64ch x4, 64->256 synthetic crops, batch %d/GPU, NLPD loss, fwd+bwd+Adam" % BATCH_PER_GPU
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"],
+                "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, reasons, mx, pw = [], set(), None, []
+        for r in rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                pw.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(pw) if pw else None)
+        return out
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# --------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """CPU port of the reference path on the host cores (rank 0 only)."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    from oracle import sr_oracle as O
+    torch.manual_seed(0)
+    threads = torch.get_num_threads()
+    sample_batch = args.cpu_batch
+    sd = cpu_state_dict()
+    lr, hr = O.synthetic_pair(sample_batch, LR_HW, LR_HW, SCALE)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()
+              if v.is_floating_point() and "running_" not in k}
+    work = dict(sd)
+    work.update(params)
+    opt = torch.optim.Adam(list(params.values()), lr=4e-4, betas=(0.5, 0.999))
+
+    def step():
+        opt.zero_grad()
+        out = O.model_forward(ARCH, work, lr, training=True)
+        loss = O.loss_fn(LOSS)(out, hr)
+        loss.backward()
+        opt.step()
+        return loss.item()
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    v = sample_batch / dt
+    sample = "batch %d of the C2 workload per step (fp32, torch CPU ATen ops, %d threads)" % (sample_batch, threads)
+    line = {"impl": "reference", "metric": "sr_train_images_per_sec", "value": round(v, 3), "unit": "images/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": round(v, 3), "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": round(v, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_state_dict():
+    """Seeded ResNet-SR weights built on the CPU through the drop-in constructors (no compute)."""
+    from src.models import get_model
+    torch.manual_seed(0)
+    return {k: v.clone() for k, v in get_model(ARCH, SCALE, "cpu").state_dict().items()}
+
+
+def cpu_baseline(budget_s=20.0, batch=2):
+    from oracle import sr_oracle as O
+    sd = cpu_state_dict()
+    lr, hr = O.synthetic_pair(batch, LR_HW, LR_HW, SCALE)
+    threads = torch.get_num_threads()
+    times = []
+    t_begin = time.perf_counter()
+    while len(times) < 4 and (time.perf_counter() - t_begin) < budget_s:
+        t0 = time.perf_counter()
+        O.train_step_grads(ARCH, sd, lr, hr, LOSS)
+        times.append(time.perf_counter() - t0)
+    best = min(times[1:]) if len(times) > 1 else times[0]
+    return {"value": round(batch / best, 3), "unit": "images/s", "cores": threads, "kind": "port",
+            "sample": "%d x (fwd+loss+bwd of batch %d, C2 shapes, fp32), best step after 1 warm-up" % (len(times), batch)}
+
+
+# --------------------------------------------------------------------------------------------------
+def run_srk(args):
+    import srk
+    from srk import dp, ops
+    from srk import _lib as L
+    from src.loss import get_loss_function
+    from src.models import get_model
+    import torch.distributed as dist
+
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    srk.set_compute_dtype(args.dtype)
+    torch.manual_seed(0)
+    model = get_model(ARCH, SCALE, dev)
+    dp.broadcast_parameters(model)
+    model.train()
+    crit = get_loss_function(LOSS, dev)
+    opt = srk.optim.Adam(model.parameters(), lr=4e-4, betas=(0.5, 0.999))
+    averager = dp.GradAverager(model.parameters()) if world > 1 else None
+
+    from src.dataset import synthetic_pair
+    B = args.batch
+    lr_h, hr_h = synthetic_pair(B, LR_HW, LR_HW, SCALE, seed=1234 + rank)
+    lr_pin, hr_pin = lr_h.pin_memory(), hr_h.pin_memory()
+    lr_d, hr_d = lr_pin.to(dev), hr_pin.to(dev)
+
+    def step(lr, hr):
+        opt.zero_grad()
+        loss = crit(model(lr), hr)
+        loss.backward()
+        if averager is not None:
+            averager.average()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, e2e):
+        barrier()
+        c0 = L.launch_calls
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(nsteps):
+            if e2e:
+                lr = lr_pin.to(dev, non_blocking=True)
+                hr = hr_pin.to(dev, non_blocking=True)
+                loss = step(lr, hr)
+                loss.item()
+            else:
+                step(lr_d, hr_d)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / nsteps, (L.launch_calls - c0) // max(nsteps, 1)
+
+    for _ in range(args.warmup):
+        step(lr_d, hr_d)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_step, launches = timed(args.steps, e2e=False)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e, _ = timed(max(2, args.steps // 2), e2e=True)
+
+    # dominant kernel, timed live with CUDA events on the launching stream: 3x3 64->64 conv fprop
+    ops.kernel_timer = ops.KernelTimer(lambda k: k[0] == "conv_fprop" and k[1:5] == (64, 64, 3, 0))
+    step(lr_d, hr_d)
+    torch.cuda.synchronize()
+    kt = ops.kernel_timer.summary()
+    ops.kernel_timer = None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    value = world * B / (ms_step * 1e-3)
+    roof = None
+    if kt:
+        key, (avg_ms, count) = max(kt.items(), key=lambda kv: kv[1][0] * kv[1][1])
+        n, h, w = key[5:8]
+        flops = 2.0 * n * h * w * 64 * 64 * 9
+        ach = flops / (avg_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "conv3x3_c64_fprop(%s)" % ("tcgen05" if key[8] else "cuda-core"),
+                "achieved": round(ach, 2), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                "frac": round(ach / pk["tf_sustained"], 4), "traffic": None, "avg_ms": round(avg_ms, 4),
+                "launches_per_step": count, "peak_source": pk["src"] + " bf16 sustained"}
+    step_tf = world * B * FWD_BWD_GFLOP_PER_IMG / (ms_step * 1e-3) / 1e3
+    line = {"metric": "sr_train_images_per_sec", "value": round(value, 2), "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.dtype == "bf16" else "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": "dp%d" % world,
+                       "l2": "working set (>2 GB of activations per step) exceeds the 126 MB L2; no explicit flush",
+                       "step_tflops": round(step_tf, 2),
+                       "step_frac_of_bf16_sustained": round(step_tf / (world * pk["tf_sustained"]), 4)},
+            "e2e": {"value": round(world * B / (ms_e2e * 1e-3), 2), "unit": "images/s",
+                    "h2d_bytes_per_step": int(lr_pin.numel() * 4 + hr_pin.numel() * 4), "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="srk", choices=["srk", "reference"])
+    ap.add_argument("--dtype", default=os.environ.get("SRK_BENCH_DTYPE", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="images per GPU per step")
+    ap.add_argument("--cpu-batch", type=int, default=4, help="--impl reference: images per CPU step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if not torch.cuda.is_available():
+        sys.exit("bench.py: no CUDA device; the SR hot path has no CPU fallback (use --impl reference for the CPU port)")
+    _, _, world = dist_env()
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29511"] + sys.argv
+        sys.exit(subprocess.call(cmd))
+    run_srk(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,115 @@
+// C-ABI front door of libsrk: error channel, conv dispatch (CUDA-core fp32 path vs tcgen05 path),
+// version / capability queries.  Declarations: include/srk.h.
+#include "srk_common.cuh"
+
+#include <cstring>
+
+namespace srk {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// srk_conv_simt.cu
+int conv_fprop_simt_launch(const srk_tensor* x, const srk_tensor* y, const float* w, int cout, int r,
+                           int s, const float* bias, int act, const float* alpha,
+                           const srk_tensor* residual, int shuffle, cudaStream_t st);
+int conv_wgrad_simt_launch(const srk_tensor* x, const srk_tensor* dy, float* dw, float* db, int r,
+                           int s, cudaStream_t st);
+// srk_conv_tc.cu
+bool conv_tc_shape_ok(int cin, int cout, int r, int s, int dtype, int shuffle);
+int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout,
+                         int r, int s, const float* bias, int act, const float* alpha,
+                         const srk_tensor* residual, int shuffle, cudaStream_t st);
+bool conv_wgrad_tc_shape_ok(const srk_tensor* x, const srk_tensor* dy, int r, int s);
+int64_t conv_wgrad_tc_workspace(const srk_tensor* x, const srk_tensor* dy, int r, int s);
+int conv_wgrad_tc_launch(const srk_tensor* x, const srk_tensor* dy, float* dw, float* db, int r, int s,
+                         void* workspace, cudaStream_t st);
+
+static bool tensor_ok(const srk_tensor* t) {
+  if (t == nullptr || t->data == nullptr) return false;
+  if (t->n <= 0 || t->c <= 0 || t->h <= 0 || t->w <= 0) return false;
+  if (t->layout == SRK_LAYOUT_IMAGE) return t->dtype == SRK_F32;
+  if (t->layout == SRK_LAYOUT_ACT) return t->dtype == SRK_F32 || t->dtype == SRK_BF16;
+  return false;
+}
+
+}  // namespace srk
+
+using namespace srk;
+
+extern "C" const char* srk_last_error(void) { return g_err; }
+extern "C" int srk_version(void) { return 100; }
+
+extern "C" int srk_conv_tc_supported(int cin, int cout, int r, int s, int dtype, int pixel_shuffle) {
+  return conv_tc_shape_ok(cin, cout, r, s, dtype, pixel_shuffle) ? 1 : 0;
+}
+
+extern "C" int srk_conv_fprop(const srk_tensor* x, const srk_tensor* y, const void* w_packed,
+                              int pack_kind, int cout, int r, int s, const float* bias, int act,
+                              const float* alpha, const srk_tensor* residual, int pixel_shuffle,
+                              int impl, void* stream) {
+  SRK_REQUIRE(tensor_ok(x) && tensor_ok(y), "srk_conv_fprop: bad x / y tensor");
+  SRK_REQUIRE(w_packed != nullptr, "srk_conv_fprop: null weights");
+  SRK_REQUIRE(r == s && (r & 1) == 1 && r >= 1 && r <= 11, "srk_conv_fprop: odd square kernels only (got %dx%d)", r, s);
+  SRK_REQUIRE(act == SRK_ACT_NONE || act == SRK_ACT_RELU || act == SRK_ACT_PRELU, "srk_conv_fprop: bad act %d", act);
+  SRK_REQUIRE(act != SRK_ACT_PRELU || alpha != nullptr, "srk_conv_fprop: PReLU needs alpha");
+  SRK_REQUIRE(pixel_shuffle == 0 || pixel_shuffle == 2, "srk_conv_fprop: pixel_shuffle must be 0 or 2");
+  if (pixel_shuffle == 2) {
+    SRK_REQUIRE(cout % 4 == 0 && y->c == cout / 4 && y->h == 2 * x->h && y->w == 2 * x->w && y->n == x->n,
+                "srk_conv_fprop: pixel-shuffle output geometry mismatch");
+  } else {
+    SRK_REQUIRE(y->c == cout && y->h == x->h && y->w == x->w && y->n == x->n,
+                "srk_conv_fprop: output geometry mismatch");
+  }
+  if (residual) {
+    SRK_REQUIRE(tensor_ok(residual) && same_geometry(residual, y) && residual->layout == y->layout,
+                "srk_conv_fprop: residual must match the output geometry and layout");
+  }
+  const bool tc_kind = pack_kind == SRK_PACK_FPROP_TC || pack_kind == SRK_PACK_DGRAD_TC;
+  const bool simt_kind = pack_kind == SRK_PACK_FPROP_SIMT || pack_kind == SRK_PACK_DGRAD_SIMT;
+  SRK_REQUIRE(tc_kind || simt_kind, "srk_conv_fprop: bad pack kind %d", pack_kind);
+  if (impl == SRK_IMPL_AUTO) impl = tc_kind ? SRK_IMPL_TC : SRK_IMPL_SIMT;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (impl == SRK_IMPL_TC) {
+    SRK_REQUIRE(tc_kind, "srk_conv_fprop: tcgen05 path needs SRK_PACK_*_TC weights");
+    SRK_REQUIRE(x->layout == SRK_LAYOUT_ACT && y->layout == SRK_LAYOUT_ACT && x->dtype == SRK_BF16 &&
+                    y->dtype == SRK_BF16,
+                "srk_conv_fprop: tcgen05 path needs bf16 ACT tensors");
+    SRK_REQUIRE(conv_tc_shape_ok(x->c, cout, r, s, SRK_BF16, pixel_shuffle),
+                "srk_conv_fprop: shape Cin=%d Cout=%d %dx%d not supported by the tcgen05 path", x->c, cout, r, s);
+    return conv_fprop_tc_launch(x, y, w_packed, cout, r, s, bias, act, alpha, residual, pixel_shuffle, st);
+  }
+  SRK_REQUIRE(impl == SRK_IMPL_SIMT && simt_kind, "srk_conv_fprop: CUDA-core path needs SRK_PACK_*_SIMT weights");
+  return conv_fprop_simt_launch(x, y, (const float*)w_packed, cout, r, s, bias, act, alpha, residual,
+                                pixel_shuffle, st);
+}
+
+extern "C" int64_t srk_conv_wgrad_workspace_bytes(const srk_tensor* x, const srk_tensor* dy, int r, int s,
+                                                  int impl) {
+  if (x == nullptr || dy == nullptr) return -1;
+  if (impl == SRK_IMPL_TC || (impl == SRK_IMPL_AUTO && conv_wgrad_tc_shape_ok(x, dy, r, s)))
+    return conv_wgrad_tc_workspace(x, dy, r, s);
+  return 0;
+}
+
+extern "C" int srk_conv_wgrad(const srk_tensor* x, const srk_tensor* dy, float* dw, float* db, int r, int s,
+                              int impl, void* workspace, void* stream) {
+  SRK_REQUIRE(tensor_ok(x) && tensor_ok(dy), "srk_conv_wgrad: bad x / dy tensor");
+  SRK_REQUIRE(dw != nullptr, "srk_conv_wgrad: null dw");
+  SRK_REQUIRE(r == s && (r & 1) == 1 && r >= 1 && r <= 11, "srk_conv_wgrad: odd square kernels only");
+  SRK_REQUIRE(x->n == dy->n && x->h == dy->h && x->w == dy->w, "srk_conv_wgrad: x / dy geometry mismatch");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (impl == SRK_IMPL_AUTO) impl = conv_wgrad_tc_shape_ok(x, dy, r, s) ? SRK_IMPL_TC : SRK_IMPL_SIMT;
+  if (impl == SRK_IMPL_TC) {
+    SRK_REQUIRE(conv_wgrad_tc_shape_ok(x, dy, r, s), "srk_conv_wgrad: shape not supported by the tcgen05 path");
+    SRK_REQUIRE(workspace != nullptr || conv_wgrad_tc_workspace(x, dy, r, s) == 0, "srk_conv_wgrad: workspace required");
+    return conv_wgrad_tc_launch(x, dy, dw, db, r, s, workspace, st);
+  }
+  return conv_wgrad_simt_launch(x, dy, dw, db, r, s, st);
+}

@@ -1,0 +1,826 @@
+// HBM-bound kernels on the zero-bordered channels-last activation layout: BatchNorm (training and
+// eval), PReLU/ReLU backward (+ pixel-unshuffle), squeeze-excite gate, layout conversion, residual
+// add, bicubic upsampling.  All are coalesced along the channel dimension with 16-byte vectors when
+// C % 8 == 0; reductions go warp-shuffle -> shared memory -> one atomic per block and channel.
+#include "srk_common.cuh"
+
+namespace srk {
+
+// ---- vector helpers: VEC contiguous channels -------------------------------------------------
+template <typename T, int VEC> struct Vec;
+template <> struct Vec<float, 1> {
+  static __device__ __forceinline__ void ld(const float* p, float* o) { o[0] = p[0]; }
+  static __device__ __forceinline__ void st(float* p, const float* v) { p[0] = v[0]; }
+};
+template <> struct Vec<__nv_bfloat16, 1> {
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float* o) { o[0] = __bfloat162float(p[0]); }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, const float* v) { p[0] = __float2bfloat16_rn(v[0]); }
+};
+template <> struct Vec<float, 8> {
+  static __device__ __forceinline__ void ld(const float* p, float* o) {
+    float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <> struct Vec<__nv_bfloat16, 8> {
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float* o) {
+    uint4 r = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); o[2 * i] = f.x; o[2 * i + 1] = f.y; }
+  }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, const float* v) {
+    uint4 r;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = r;
+  }
+};
+
+struct Geo {
+  int N, Hp, Wp, C;
+  long long pixels;  // N*Hp*Wp
+};
+inline Geo geo_of(const srk_tensor* t) {
+  Geo g; g.N = t->n; g.Hp = t->h + 2; g.Wp = t->w + 2; g.C = t->c;
+  g.pixels = (long long)g.N * g.Hp * g.Wp;
+  return g;
+}
+__device__ __forceinline__ bool is_border(const Geo& g, long long q) {
+  int xx = (int)(q % g.Wp);
+  int yy = (int)((q / g.Wp) % g.Hp);
+  return xx == 0 || xx == g.Wp - 1 || yy == 0 || yy == g.Hp - 1;
+}
+
+// Pixel-tiled iteration: a block owns `ppb` consecutive padded pixels; thread t handles channel
+// vector cv = t % CV for pixel rows t / CV, t / CV + rows, ...
+#define SRK_PIXEL_LOOP(g, VEC)                                                      \
+  const int CV = (g).C / (VEC);                                                     \
+  const int rows = blockDim.x / CV;                                                 \
+  const int cv = threadIdx.x % CV;                                                  \
+  const int prow = threadIdx.x / CV;                                                \
+  const long long q_begin = (long long)blockIdx.x * ppb;                            \
+  long long q_end = q_begin + ppb;                                                  \
+  if (q_end > (g).pixels) q_end = (g).pixels;                                       \
+  if (prow < rows)                                                                  \
+    for (long long q = q_begin + prow; q < q_end; q += rows)
+
+inline void pixel_grid(const Geo& g, int& blocks, int& ppb) {
+  // ~4 blocks per SM worth of work, at least 64 pixels per block
+  long long target = 148LL * 8;
+  long long p = (g.pixels + target - 1) / target;
+  if (p < 64) p = 64;
+  ppb = (int)p;
+  blocks = (int)((g.pixels + ppb - 1) / ppb);
+}
+
+// Reduce per-thread VEC partials across the rows of a block, then one atomic per channel.
+template <int VEC>
+__device__ __forceinline__ void block_channel_atomic(float* part, float* smem, int CV, int rows,
+                                                     int cv, int prow, float* gdst) {
+  // smem: [rows][CV*VEC]
+  __syncthreads();
+  if (prow < rows) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) smem[prow * CV * VEC + cv * VEC + j] = part[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < CV * VEC; c += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += smem[r * CV * VEC + c];
+    atomicAdd(&gdst[c], s);
+  }
+}
+
+// ---- BatchNorm ---------------------------------------------------------------------------------
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ y, Geo g, int ppb,
+                                                       float* __restrict__ sum, float* __restrict__ sumsq) {
+  extern __shared__ float smem[];
+  float s1[VEC], s2[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  SRK_PIXEL_LOOP(g, VEC) {
+    if (is_border(g, q)) continue;
+    float v[VEC];
+    Vec<T, VEC>::ld(y + q * g.C + cv * VEC, v);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { s1[j] += v[j]; s2[j] = fmaf(v[j], v[j], s2[j]); }
+  }
+  block_channel_atomic<VEC>(s1, smem, CV, rows, cv, prow, sum);
+  block_channel_atomic<VEC>(s2, smem, CV, rows, cv, prow, sumsq);
+}
+
+__global__ void bn_finalize_kernel(const float* sum, const float* sumsq, int C, double count, float eps,
+                                   float momentum, float* running_mean, float* running_var,
+                                   long long* nbt, float* mean, float* invstd) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    double m = (double)sum[c] / count;
+    double var = (double)sumsq[c] / count - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[c] = (float)m;
+    invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean != nullptr) {
+      double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+  }
+  if (c == 0 && nbt != nullptr) nbt[0] += 1;
+}
+
+__global__ void bn_eval_params_kernel(const float* rm, const float* rv, int C, float eps, float* mean,
+                                      float* invstd) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) { mean[c] = rm[c]; invstd[c] = rsqrtf(rv[c] + eps); }
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ y, Geo g, int ppb,
+    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+    const float* __restrict__ beta, const float* __restrict__ alpha_p, const T* __restrict__ res,
+    T* __restrict__ out) {
+  const float alpha = alpha_p ? alpha_p[0] : 1.f;
+  SRK_PIXEL_LOOP(g, VEC) {
+    float o[VEC];
+    const long long e = q * g.C + cv * VEC;
+    if (is_border(g, q)) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) o[j] = 0.f;
+    } else {
+      float v[VEC];
+      Vec<T, VEC>::ld(y + e, v);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        int c = cv * VEC + j;
+        float sc = gamma[c] * invstd[c];
+        float b = (v[j] - mean[c]) * sc + beta[c];
+        o[j] = (alpha_p && b < 0.f) ? alpha * b : b;
+      }
+      if (res) {
+        float r[VEC];
+        Vec<T, VEC>::ld(res + e, r);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) o[j] += r[j];
+      }
+    }
+    Vec<T, VEC>::st(out + e, o);
+  }
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict__ dout,
+    const T* __restrict__ y, Geo g, int ppb, const float* __restrict__ mean,
+    const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+    const float* __restrict__ alpha_p, float* __restrict__ dgamma, float* __restrict__ dbeta,
+    float* __restrict__ dalpha) {
+  extern __shared__ float smem[];
+  const float alpha = alpha_p ? alpha_p[0] : 1.f;
+  float dg[VEC], db[VEC];
+  float da = 0.f;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) { dg[j] = 0.f; db[j] = 0.f; }
+  SRK_PIXEL_LOOP(g, VEC) {
+    if (is_border(g, q)) continue;
+    const long long e = q * g.C + cv * VEC;
+    float v[VEC], d[VEC];
+    Vec<T, VEC>::ld(y + e, v);
+    Vec<T, VEC>::ld(dout + e, d);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      int c = cv * VEC + j;
+      float xh = (v[j] - mean[c]) * invstd[c];
+      float gd = d[j];
+      if (alpha_p) {
+        float b = xh * gamma[c] + beta[c];
+        if (b < 0.f) { da = fmaf(gd, b, da); gd *= alpha; }
+      }
+      dg[j] = fmaf(gd, xh, dg[j]);
+      db[j] += gd;
+    }
+  }
+  block_channel_atomic<VEC>(dg, smem, CV, rows, cv, prow, dgamma);
+  block_channel_atomic<VEC>(db, smem, CV, rows, cv, prow, dbeta);
+  if (alpha_p && dalpha) {
+    __shared__ float red[32];
+    float t = block_sum(da, red);
+    if (threadIdx.x == 0) atomicAdd(dalpha, t);
+  }
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ dout,
+    const T* __restrict__ y, Geo g, int ppb, const float* __restrict__ mean,
+    const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+    const float* __restrict__ alpha_p, const float* __restrict__ dgamma, const float* __restrict__ dbeta,
+    float inv_count, int batch_stats, T* __restrict__ dy) {
+  const float alpha = alpha_p ? alpha_p[0] : 1.f;
+  SRK_PIXEL_LOOP(g, VEC) {
+    float o[VEC];
+    const long long e = q * g.C + cv * VEC;
+    if (is_border(g, q)) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) o[j] = 0.f;
+    } else {
+      float v[VEC], d[VEC];
+      Vec<T, VEC>::ld(y + e, v);
+      Vec<T, VEC>::ld(dout + e, d);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        int c = cv * VEC + j;
+        float xh = (v[j] - mean[c]) * invstd[c];
+        float gd = d[j];
+        if (alpha_p) {
+          float b = xh * gamma[c] + beta[c];
+          if (b < 0.f) gd *= alpha;
+        }
+        float sc = gamma[c] * invstd[c];
+        o[j] = batch_stats ? sc * (gd - dbeta[c] * inv_count - xh * dgamma[c] * inv_count) : sc * gd;
+      }
+    }
+    Vec<T, VEC>::st(dy + e, o);
+  }
+}
+
+// ---- activation backward -------------------------------------------------------------------------
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) act_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ out,
+    Geo g, int ppb, int act, const float* __restrict__ alpha_p, float* __restrict__ dalpha,
+    T* __restrict__ dz) {
+  const float alpha = (act == SRK_ACT_PRELU) ? alpha_p[0] : 0.f;
+  const float inv_alpha = (act == SRK_ACT_PRELU && alpha != 0.f) ? 1.f / alpha : 0.f;
+  float da = 0.f;
+  SRK_PIXEL_LOOP(g, VEC) {
+    float o[VEC];
+    const long long e = q * g.C + cv * VEC;
+    if (is_border(g, q)) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) o[j] = 0.f;
+    } else {
+      float v[VEC], d[VEC];
+      Vec<T, VEC>::ld(out + e, v);
+      Vec<T, VEC>::ld(dout + e, d);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        if (v[j] > 0.f) o[j] = d[j];
+        else { o[j] = alpha * d[j]; da = fmaf(d[j], v[j] * inv_alpha, da); }
+      }
+    }
+    Vec<T, VEC>::st(dz + e, o);
+  }
+  if (act == SRK_ACT_PRELU && dalpha) {
+    __shared__ float red[32];
+    float t = block_sum(da, red);
+    if (threadIdx.x == 0) atomicAdd(dalpha, t);
+  }
+}
+
+// dout/out: [N][2H+2][2W+2][C]; dz: [N][H+2][W+2][4C].  Iterates over dz.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) act_bwd_unshuffle_kernel(const T* __restrict__ dout,
+    const T* __restrict__ out, Geo gz, int ppb, int C, int act, const float* __restrict__ alpha_p,
+    float* __restrict__ dalpha, int perm_tc, T* __restrict__ dz) {
+  const float alpha = (act == SRK_ACT_PRELU) ? alpha_p[0] : 0.f;
+  const float inv_alpha = (act == SRK_ACT_PRELU && alpha != 0.f) ? 1.f / alpha : 0.f;
+  const int Wp2 = 2 * (gz.Wp - 2) + 2, Hp2 = 2 * (gz.Hp - 2) + 2;
+  float da = 0.f;
+  SRK_PIXEL_LOOP(gz, VEC) {
+    float o[VEC];
+    const long long e = q * gz.C + cv * VEC;
+    if (is_border(gz, q)) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) o[j] = 0.f;
+    } else {
+      int xx = (int)(q % gz.Wp) - 1;
+      long long t = q / gz.Wp;
+      int yy = (int)(t % gz.Hp) - 1;
+      int n = (int)(t / gz.Hp);
+      float v[VEC], d[VEC];
+      if (perm_tc && VEC == 8) {
+        int cop = cv * VEC, sub = cop / C, c = cop - sub * C;
+        long long src = (((long long)n * Hp2 + (2 * yy + (sub >> 1) + 1)) * Wp2 + (2 * xx + (sub & 1) + 1)) * C + c;
+        Vec<T, VEC>::ld(out + src, v);
+        Vec<T, VEC>::ld(dout + src, d);
+      } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          int cop = cv * VEC + j, sub, c;
+          if (perm_tc) { sub = cop / C; c = cop - sub * C; } else { c = cop >> 2; sub = cop & 3; }
+          long long src = (((long long)n * Hp2 + (2 * yy + (sub >> 1) + 1)) * Wp2 + (2 * xx + (sub & 1) + 1)) * C + c;
+          v[j] = to_f<T>(out[src]);
+          d[j] = to_f<T>(dout[src]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        if (act == SRK_ACT_NONE || v[j] > 0.f) o[j] = d[j];
+        else { o[j] = alpha * d[j]; da = fmaf(d[j], v[j] * inv_alpha, da); }
+      }
+    }
+    Vec<T, VEC>::st(dz + e, o);
+  }
+  if (act == SRK_ACT_PRELU && dalpha) {
+    __shared__ float red[32];
+    float t = block_sum(da, red);
+    if (threadIdx.x == 0) atomicAdd(dalpha, t);
+  }
+}
+
+// ---- squeeze-excite ------------------------------------------------------------------------------
+// per-image channel sums of a (optionally times b): grid = (blocks_per_image, N)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) image_channel_sum_kernel(const T* __restrict__ a,
+    const T* __restrict__ b, Geo g, int ppb, float scale, float* __restrict__ out) {
+  extern __shared__ float smem[];
+  const int n = blockIdx.y;
+  const long long img_pixels = (long long)g.Hp * g.Wp;
+  const int CV = g.C / VEC, rows = blockDim.x / CV, cv = threadIdx.x % CV, prow = threadIdx.x / CV;
+  long long q_begin = (long long)blockIdx.x * ppb, q_end = q_begin + ppb;
+  if (q_end > img_pixels) q_end = img_pixels;
+  float s[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) s[j] = 0.f;
+  if (prow < rows)
+    for (long long ql = q_begin + prow; ql < q_end; ql += rows) {
+      long long q = n * img_pixels + ql;
+      if (is_border(g, q)) continue;
+      float v[VEC];
+      Vec<T, VEC>::ld(a + q * g.C + cv * VEC, v);
+      if (b) {
+        float w[VEC];
+        Vec<T, VEC>::ld(b + q * g.C + cv * VEC, w);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) s[j] = fmaf(v[j], w[j], s[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) s[j] += v[j];
+      }
+    }
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) s[j] *= scale;
+  block_channel_atomic<VEC>(s, smem, CV, rows, cv, prow, out + (long long)n * g.C);
+}
+
+__global__ void se_fc_kernel(const float* __restrict__ pool, const float* __restrict__ w1,
+                             const float* __restrict__ w2, int C, int Cr, float* __restrict__ hidden,
+                             float* __restrict__ gate) {
+  extern __shared__ float sh[];  // pool[C] + hidden[Cr]
+  float* sp = sh; float* hd = sh + C;
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) sp[c] = pool[(long long)n * C + c];
+  __syncthreads();
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int j = warp; j < Cr; j += nw) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(w1[j * C + c], sp[c], s);
+    s = warp_sum(s);
+    if (lane == 0) { s = fmaxf(s, 0.f); hd[j] = s; hidden[(long long)n * Cr + j] = s; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int j = 0; j < Cr; ++j) s = fmaf(w2[c * Cr + j], hd[j], s);
+    gate[(long long)n * C + c] = 1.f / (1.f + expf(-s));
+  }
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) se_apply_kernel(const T* __restrict__ x, const T* __restrict__ r,
+    Geo g, int ppb, const float* __restrict__ gate, float scale, T* __restrict__ out) {
+  const long long img_pixels = (long long)g.Hp * g.Wp;
+  SRK_PIXEL_LOOP(g, VEC) {
+    float o[VEC];
+    const long long e = q * g.C + cv * VEC;
+    if (is_border(g, q)) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) o[j] = 0.f;
+    } else {
+      int n = (int)(q / img_pixels);
+      float v[VEC];
+      Vec<T, VEC>::ld(r + e, v);
+      if (x) Vec<T, VEC>::ld(x + e, o);
+      else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) o[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) o[j] = fmaf(scale * gate[(long long)n * g.C + cv * VEC + j], v[j], o[j]);
+    }
+    Vec<T, VEC>::st(out + e, o);
+  }
+}
+
+// single block; accumulates dw1/dw2 over the batch and writes dpool
+__global__ void se_fc_bwd_kernel(const float* __restrict__ dgate_raw, const float* __restrict__ gate,
+    const float* __restrict__ hidden, const float* __restrict__ pool, const float* __restrict__ w1,
+    const float* __restrict__ w2, int N, int C, int Cr, float scale, float* __restrict__ dw1,
+    float* __restrict__ dw2, float* __restrict__ dpool, float* __restrict__ dz2_ws /* [N][C] */,
+    float* __restrict__ dh_ws /* [N][Cr] */) {
+  // dz2[n][c] = scale * dgate_raw * gate * (1-gate)
+  for (int i = threadIdx.x; i < N * C; i += blockDim.x) {
+    float s = gate[i];
+    dz2_ws[i] = scale * dgate_raw[i] * s * (1.f - s);
+  }
+  __syncthreads();
+  // dh[n][j] = [hidden>0] * sum_c w2[c][j] dz2[n][c]
+  for (int i = threadIdx.x; i < N * Cr; i += blockDim.x) {
+    int n = i / Cr, j = i - n * Cr;
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s = fmaf(w2[c * Cr + j], dz2_ws[n * C + c], s);
+    dh_ws[i] = hidden[i] > 0.f ? s : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * Cr; i += blockDim.x) {
+    int c = i / Cr, j = i - c * Cr;
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s = fmaf(dz2_ws[n * C + c], hidden[n * Cr + j], s);
+    dw2[i] += s;
+  }
+  for (int i = threadIdx.x; i < Cr * C; i += blockDim.x) {
+    int j = i / C, c = i - j * C;
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s = fmaf(dh_ws[n * Cr + j], pool[n * C + c], s);
+    dw1[i] += s;
+  }
+  for (int i = threadIdx.x; i < N * C; i += blockDim.x) {
+    int n = i / C, c = i - n * C;
+    float s = 0.f;
+    for (int j = 0; j < Cr; ++j) s = fmaf(w1[j * C + c], dh_ws[n * Cr + j], s);
+    dpool[i] = s;
+  }
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) se_bwd_apply_kernel(const T* __restrict__ dout, Geo g, int ppb,
+    const float* __restrict__ gate, const float* __restrict__ dpool, float scale, float inv_hw,
+    T* __restrict__ dr) {
+  const long long img_pixels = (long long)g.Hp * g.Wp;
+  SRK_PIXEL_LOOP(g, VEC) {
+    float o[VEC];
+    const long long e = q * g.C + cv * VEC;
+    if (is_border(g, q)) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) o[j] = 0.f;
+    } else {
+      int n = (int)(q / img_pixels);
+      float d[VEC];
+      Vec<T, VEC>::ld(dout + e, d);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        long long gi = (long long)n * g.C + cv * VEC + j;
+        o[j] = scale * gate[gi] * d[j] + dpool[gi] * inv_hw;
+      }
+    }
+    Vec<T, VEC>::st(dr + e, o);
+  }
+}
+
+// ---- layout / misc ---------------------------------------------------------------------------------
+template <typename T>
+__global__ void image_to_act_kernel(const float* __restrict__ img, T* __restrict__ act, int N, int C,
+                                    int H, int W) {
+  const int Hp = H + 2, Wp = W + 2;
+  long long total = (long long)N * Hp * Wp * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C); long long t = i / C;
+    int xx = (int)(t % Wp); t /= Wp;
+    int yy = (int)(t % Hp); int n = (int)(t / Hp);
+    float v = 0.f;
+    if (xx > 0 && xx < Wp - 1 && yy > 0 && yy < Hp - 1)
+      v = img[(((long long)n * C + c) * H + (yy - 1)) * W + (xx - 1)];
+    act[i] = from_f<T>(v);
+  }
+}
+template <typename T>
+__global__ void act_to_image_kernel(const T* __restrict__ act, float* __restrict__ img, int N, int C,
+                                    int H, int W) {
+  const int Hp = H + 2, Wp = W + 2;
+  long long total = (long long)N * C * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int x = (int)(i % W); long long t = i / W;
+    int y = (int)(t % H); t /= H;
+    int c = (int)(t % C); int n = (int)(t / C);
+    img[i] = to_f<T>(act[(((long long)n * Hp + y + 1) * Wp + x + 1) * C + c]);
+  }
+}
+template <typename T>
+__global__ void act_add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o,
+                               long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    o[i] = from_f<T>(to_f<T>(a[i]) + to_f<T>(b[i]));
+}
+
+// F.interpolate bicubic, align_corners=False, A=-0.75, border taps clamped (ATen upsample_bicubic2d)
+__device__ __forceinline__ void cubic_coeffs(float t, float* w) {
+  const float A = -0.75f;
+  float x;
+  x = t + 1.f; w[0] = ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A;
+  x = t;       w[1] = ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f;
+  x = 1.f - t; w[2] = ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f;
+  x = 2.f - t; w[3] = ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A;
+}
+__global__ void bicubic_kernel(const float* __restrict__ in, float* __restrict__ out, int NC, int H,
+                               int W, int OH, int OW, float sh, float sw) {
+  long long total = (long long)NC * OH * OW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int ox = (int)(i % OW); long long t = i / OW;
+    int oy = (int)(t % OH); int nc = (int)(t / OH);
+    float fy = sh * (oy + 0.5f) - 0.5f, fx = sw * (ox + 0.5f) - 0.5f;
+    int iy = (int)floorf(fy), ix = (int)floorf(fx);
+    float wy[4], wx[4];
+    cubic_coeffs(fy - iy, wy);
+    cubic_coeffs(fx - ix, wx);
+    const float* p = in + (long long)nc * H * W;
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      int yy = min(max(iy - 1 + a, 0), H - 1);
+      float row = 0.f;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        int xx = min(max(ix - 1 + b, 0), W - 1);
+        row = fmaf(wx[b], p[(long long)yy * W + xx], row);
+      }
+      acc = fmaf(wy[a], row, acc);
+    }
+    out[i] = acc;
+  }
+}
+
+}  // namespace srk
+
+using namespace srk;
+
+#define ACT_CHECK(t, name)                                                                  \
+  SRK_REQUIRE((t) && (t)->layout == SRK_LAYOUT_ACT && ((t)->dtype == SRK_F32 || (t)->dtype == SRK_BF16), \
+              "%s: expected ACT tensor", name)
+
+// dispatch on dtype and vector width
+#define DISPATCH_T_VEC(t, ...)                                            \
+  do {                                                                    \
+    const bool vec8__ = ((t)->c % 8 == 0) && ((t)->c / 8 <= 256);         \
+    if ((t)->dtype == SRK_BF16) {                                         \
+      using T = __nv_bfloat16;                                            \
+      if (vec8__) { constexpr int VEC = 8; __VA_ARGS__; }                 \
+      else { constexpr int VEC = 1; __VA_ARGS__; }                        \
+    } else {                                                              \
+      using T = float;                                                    \
+      if (vec8__) { constexpr int VEC = 8; __VA_ARGS__; }                 \
+      else { constexpr int VEC = 1; __VA_ARGS__; }                        \
+    }                                                                     \
+  } while (0)
+
+static inline size_t red_smem(const srk_tensor* t) {
+  // [rows][C] floats with rows <= 256
+  int vec = (t->c % 8 == 0 && t->c / 8 <= 256) ? 8 : 1;
+  int cv = t->c / vec;
+  int rows = 256 / cv; if (rows < 1) rows = 1;
+  return (size_t)rows * t->c * sizeof(float);
+}
+static inline bool c_ok(const srk_tensor* t) {
+  int vec = (t->c % 8 == 0 && t->c / 8 <= 256) ? 8 : 1;
+  return t->c / vec <= 256 && red_smem(t) <= 48 * 1024;
+}
+
+extern "C" int srk_bn_stats(const srk_tensor* y, float* sum, float* sumsq, void* stream) {
+  ACT_CHECK(y, "srk_bn_stats");
+  SRK_REQUIRE(c_ok(y), "srk_bn_stats: unsupported channel count %d", y->c);
+  Geo g = geo_of(y); int blocks, ppb; pixel_grid(g, blocks, ppb);
+  DISPATCH_T_VEC(y, (bn_stats_kernel<T, VEC><<<blocks, 256, red_smem(y), (cudaStream_t)stream>>>(
+                        (const T*)y->data, g, ppb, sum, sumsq)));
+  SRK_CUDA_LAUNCH_CHECK("bn_stats");
+  return 0;
+}
+
+extern "C" int srk_bn_finalize(const float* sum, const float* sumsq, int c, int64_t count, float eps,
+                               float momentum, float* running_mean, float* running_var,
+                               int64_t* num_batches_tracked, float* mean, float* invstd, void* stream) {
+  SRK_REQUIRE(count > 0, "srk_bn_finalize: empty batch");
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      sum, sumsq, c, (double)count, eps, momentum, running_mean, running_var,
+      (long long*)num_batches_tracked, mean, invstd);
+  SRK_CUDA_LAUNCH_CHECK("bn_finalize");
+  return 0;
+}
+
+extern "C" int srk_bn_eval_params(const float* running_mean, const float* running_var, int c, float eps,
+                                  float* mean, float* invstd, void* stream) {
+  bn_eval_params_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(running_mean, running_var, c, eps, mean, invstd);
+  SRK_CUDA_LAUNCH_CHECK("bn_eval_params");
+  return 0;
+}
+
+extern "C" int srk_bn_apply(const srk_tensor* y, const float* mean, const float* invstd,
+                            const float* gamma, const float* beta, const float* alpha,
+                            const srk_tensor* residual, const srk_tensor* out, void* stream) {
+  ACT_CHECK(y, "srk_bn_apply"); ACT_CHECK(out, "srk_bn_apply");
+  SRK_REQUIRE(same_geometry(y, out) && y->dtype == out->dtype, "srk_bn_apply: geometry mismatch");
+  if (residual) SRK_REQUIRE(same_geometry(y, residual) && residual->dtype == y->dtype && residual->layout == SRK_LAYOUT_ACT, "srk_bn_apply: residual mismatch");
+  SRK_REQUIRE(c_ok(y), "srk_bn_apply: unsupported channel count %d", y->c);
+  Geo g = geo_of(y); int blocks, ppb; pixel_grid(g, blocks, ppb);
+  DISPATCH_T_VEC(y, (bn_apply_kernel<T, VEC><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)y->data, g, ppb, mean, invstd, gamma, beta, alpha,
+                        residual ? (const T*)residual->data : nullptr, (T*)out->data)));
+  SRK_CUDA_LAUNCH_CHECK("bn_apply");
+  return 0;
+}
+
+extern "C" int srk_bn_bwd_reduce(const srk_tensor* dout, const srk_tensor* y, const float* mean,
+                                 const float* invstd, const float* gamma, const float* beta,
+                                 const float* alpha, float* dgamma, float* dbeta, float* dalpha,
+                                 void* stream) {
+  ACT_CHECK(y, "srk_bn_bwd_reduce"); ACT_CHECK(dout, "srk_bn_bwd_reduce");
+  SRK_REQUIRE(same_geometry(y, dout) && y->dtype == dout->dtype, "srk_bn_bwd_reduce: geometry mismatch");
+  SRK_REQUIRE(c_ok(y), "srk_bn_bwd_reduce: unsupported channel count %d", y->c);
+  Geo g = geo_of(y); int blocks, ppb; pixel_grid(g, blocks, ppb);
+  DISPATCH_T_VEC(y, (bn_bwd_reduce_kernel<T, VEC><<<blocks, 256, red_smem(y), (cudaStream_t)stream>>>(
+                        (const T*)dout->data, (const T*)y->data, g, ppb, mean, invstd, gamma, beta,
+                        alpha, dgamma, dbeta, dalpha)));
+  SRK_CUDA_LAUNCH_CHECK("bn_bwd_reduce");
+  return 0;
+}
+
+extern "C" int srk_bn_bwd_apply(const srk_tensor* dout, const srk_tensor* y, const float* mean,
+                                const float* invstd, const float* gamma, const float* beta,
+                                const float* alpha, const float* dgamma_b, const float* dbeta_b,
+                                int batch_stats, const srk_tensor* dy, void* stream) {
+  ACT_CHECK(y, "srk_bn_bwd_apply"); ACT_CHECK(dout, "srk_bn_bwd_apply"); ACT_CHECK(dy, "srk_bn_bwd_apply");
+  SRK_REQUIRE(same_geometry(y, dout) && same_geometry(y, dy) && y->dtype == dout->dtype && y->dtype == dy->dtype,
+              "srk_bn_bwd_apply: geometry mismatch");
+  SRK_REQUIRE(c_ok(y), "srk_bn_bwd_apply: unsupported channel count %d", y->c);
+  Geo g = geo_of(y); int blocks, ppb; pixel_grid(g, blocks, ppb);
+  float inv_count = 1.f / ((float)y->n * y->h * y->w);
+  DISPATCH_T_VEC(y, (bn_bwd_apply_kernel<T, VEC><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)dout->data, (const T*)y->data, g, ppb, mean, invstd, gamma, beta,
+                        alpha, dgamma_b, dbeta_b, inv_count, batch_stats, (T*)dy->data)));
+  SRK_CUDA_LAUNCH_CHECK("bn_bwd_apply");
+  return 0;
+}
+
+extern "C" int srk_act_bwd(const srk_tensor* dout, const srk_tensor* out, const srk_tensor* dz, int act,
+                           const float* alpha, float* dalpha, int pixel_unshuffle, int perm_tc,
+                           void* stream) {
+  ACT_CHECK(dout, "srk_act_bwd"); ACT_CHECK(out, "srk_act_bwd"); ACT_CHECK(dz, "srk_act_bwd");
+  SRK_REQUIRE(same_geometry(dout, out) && dout->dtype == out->dtype && dz->dtype == out->dtype, "srk_act_bwd: geometry mismatch");
+  SRK_REQUIRE(act != SRK_ACT_PRELU || alpha != nullptr, "srk_act_bwd: PReLU needs alpha");
+  SRK_REQUIRE(c_ok(dz), "srk_act_bwd: unsupported channel count %d", dz->c);
+  Geo g = geo_of(dz); int blocks, ppb; pixel_grid(g, blocks, ppb);
+  if (pixel_unshuffle == 2) {
+    SRK_REQUIRE(dz->c == 4 * out->c && out->h == 2 * dz->h && out->w == 2 * dz->w && dz->n == out->n,
+                "srk_act_bwd: unshuffle geometry mismatch");
+    SRK_REQUIRE(!perm_tc || out->c % 8 == 0, "srk_act_bwd: perm_tc needs C %% 8 == 0");
+    DISPATCH_T_VEC(dz, (act_bwd_unshuffle_kernel<T, VEC><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+                           (const T*)dout->data, (const T*)out->data, g, ppb, out->c, act, alpha, dalpha,
+                           perm_tc, (T*)dz->data)));
+  } else {
+    SRK_REQUIRE(pixel_unshuffle == 0 && same_geometry(dz, out), "srk_act_bwd: geometry mismatch");
+    DISPATCH_T_VEC(dz, (act_bwd_kernel<T, VEC><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+                           (const T*)dout->data, (const T*)out->data, g, ppb, act, alpha, dalpha,
+                           (T*)dz->data)));
+  }
+  SRK_CUDA_LAUNCH_CHECK("act_bwd");
+  return 0;
+}
+
+static int image_sum_launch(const srk_tensor* a, const srk_tensor* b, float scale, float* out,
+                            cudaStream_t st, const char* name) {
+  Geo g = geo_of(a);
+  long long img_pixels = (long long)g.Hp * g.Wp;
+  int bpi = (int)((148LL * 4 + g.N - 1) / g.N);
+  long long maxb = (img_pixels + 63) / 64;
+  if (bpi > maxb) bpi = (int)maxb;
+  if (bpi < 1) bpi = 1;
+  int ppb = (int)((img_pixels + bpi - 1) / bpi);
+  bpi = (int)((img_pixels + ppb - 1) / ppb);
+  dim3 grid(bpi, g.N);
+  DISPATCH_T_VEC(a, (image_channel_sum_kernel<T, VEC><<<grid, 256, red_smem(a), st>>>(
+                        (const T*)a->data, b ? (const T*)b->data : nullptr, g, ppb, scale, out)));
+  SRK_CUDA_LAUNCH_CHECK(name);
+  return 0;
+}
+
+extern "C" int srk_se_pool(const srk_tensor* r, float* pool, void* stream) {
+  ACT_CHECK(r, "srk_se_pool");
+  SRK_REQUIRE(c_ok(r), "srk_se_pool: unsupported channel count %d", r->c);
+  cudaMemsetAsync(pool, 0, sizeof(float) * (size_t)r->n * r->c, (cudaStream_t)stream);
+  return image_sum_launch(r, nullptr, 1.f / ((float)r->h * r->w), pool, (cudaStream_t)stream, "se_pool");
+}
+
+extern "C" int srk_se_fc(const float* pool, const float* w1, const float* w2, int n, int c, int cr,
+                         float* hidden, float* gate, void* stream) {
+  SRK_REQUIRE(cr >= 1 && c >= 1, "srk_se_fc: bad sizes");
+  se_fc_kernel<<<n, 128, sizeof(float) * (c + cr), (cudaStream_t)stream>>>(pool, w1, w2, c, cr, hidden, gate);
+  SRK_CUDA_LAUNCH_CHECK("se_fc");
+  return 0;
+}
+
+extern "C" int srk_se_apply(const srk_tensor* x, const srk_tensor* r, const float* gate, float scale,
+                            const srk_tensor* out, void* stream) {
+  ACT_CHECK(r, "srk_se_apply"); ACT_CHECK(out, "srk_se_apply");
+  SRK_REQUIRE(same_geometry(r, out) && r->dtype == out->dtype, "srk_se_apply: geometry mismatch");
+  if (x) SRK_REQUIRE(same_geometry(r, x) && x->dtype == r->dtype && x->layout == SRK_LAYOUT_ACT, "srk_se_apply: x mismatch");
+  SRK_REQUIRE(c_ok(r), "srk_se_apply: unsupported channel count %d", r->c);
+  Geo g = geo_of(r); int blocks, ppb; pixel_grid(g, blocks, ppb);
+  DISPATCH_T_VEC(r, (se_apply_kernel<T, VEC><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+                        x ? (const T*)x->data : nullptr, (const T*)r->data, g, ppb, gate, scale, (T*)out->data)));
+  SRK_CUDA_LAUNCH_CHECK("se_apply");
+  return 0;
+}
+
+extern "C" int srk_se_bwd_reduce(const srk_tensor* dout, const srk_tensor* r, float* dgate_raw, void* stream) {
+  ACT_CHECK(r, "srk_se_bwd_reduce"); ACT_CHECK(dout, "srk_se_bwd_reduce");
+  SRK_REQUIRE(same_geometry(r, dout) && r->dtype == dout->dtype, "srk_se_bwd_reduce: geometry mismatch");
+  SRK_REQUIRE(c_ok(r), "srk_se_bwd_reduce: unsupported channel count %d", r->c);
+  return image_sum_launch(dout, r, 1.f, dgate_raw, (cudaStream_t)stream, "se_bwd_reduce");
+}
+
+extern "C" int srk_se_fc_bwd(const float* dgate_raw, const float* gate, const float* hidden,
+                             const float* pool, const float* w1, const float* w2, int n, int c, int cr,
+                             float scale, float* dw1, float* dw2, float* dpool, void* stream) {
+  // scratch: dz2 [n][c] + dh [n][cr]; borrowed from dpool's tail is not possible -> use a static
+  // per-call device allocation-free trick: dpool is [n][c]; we need n*c + n*cr more floats.  The
+  // caller provides dpool with room for 2*n*c + n*cr floats (documented in the Python binding).
+  float* dz2 = dpool + (size_t)n * c;
+  float* dh = dz2 + (size_t)n * c;
+  se_fc_bwd_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(dgate_raw, gate, hidden, pool, w1, w2, n, c, cr,
+                                                         scale, dw1, dw2, dpool, dz2, dh);
+  SRK_CUDA_LAUNCH_CHECK("se_fc_bwd");
+  return 0;
+}
+
+extern "C" int srk_se_bwd_apply(const srk_tensor* dout, const float* gate, const float* dpool,
+                                float scale, const srk_tensor* dr, void* stream) {
+  ACT_CHECK(dr, "srk_se_bwd_apply"); ACT_CHECK(dout, "srk_se_bwd_apply");
+  SRK_REQUIRE(same_geometry(dr, dout) && dr->dtype == dout->dtype, "srk_se_bwd_apply: geometry mismatch");
+  SRK_REQUIRE(c_ok(dr), "srk_se_bwd_apply: unsupported channel count %d", dr->c);
+  Geo g = geo_of(dr); int blocks, ppb; pixel_grid(g, blocks, ppb);
+  float inv_hw = 1.f / ((float)dr->h * dr->w);
+  DISPATCH_T_VEC(dr, (se_bwd_apply_kernel<T, VEC><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+                         (const T*)dout->data, g, ppb, gate, dpool, scale, inv_hw, (T*)dr->data)));
+  SRK_CUDA_LAUNCH_CHECK("se_bwd_apply");
+  return 0;
+}
+
+static inline int ew_blocks(long long n) {
+  long long b = (n + 255) / 256;
+  if (b > 148 * 16) b = 148 * 16;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+extern "C" int srk_image_to_act(const srk_tensor* img, const srk_tensor* act, void* stream) {
+  ACT_CHECK(act, "srk_image_to_act");
+  SRK_REQUIRE(img && img->layout == SRK_LAYOUT_IMAGE && same_geometry(img, act), "srk_image_to_act: geometry mismatch");
+  long long total = act_elems(act);
+  if (act->dtype == SRK_BF16)
+    image_to_act_kernel<__nv_bfloat16><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((const float*)img->data, (__nv_bfloat16*)act->data, act->n, act->c, act->h, act->w);
+  else
+    image_to_act_kernel<float><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((const float*)img->data, (float*)act->data, act->n, act->c, act->h, act->w);
+  SRK_CUDA_LAUNCH_CHECK("image_to_act");
+  return 0;
+}
+
+extern "C" int srk_act_to_image(const srk_tensor* act, const srk_tensor* img, void* stream) {
+  ACT_CHECK(act, "srk_act_to_image");
+  SRK_REQUIRE(img && img->layout == SRK_LAYOUT_IMAGE && same_geometry(img, act), "srk_act_to_image: geometry mismatch");
+  long long total = (long long)act->n * act->c * act->h * act->w;
+  if (act->dtype == SRK_BF16)
+    act_to_image_kernel<__nv_bfloat16><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)act->data, (float*)img->data, act->n, act->c, act->h, act->w);
+  else
+    act_to_image_kernel<float><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((const float*)act->data, (float*)img->data, act->n, act->c, act->h, act->w);
+  SRK_CUDA_LAUNCH_CHECK("act_to_image");
+  return 0;
+}
+
+extern "C" int srk_act_add(const srk_tensor* a, const srk_tensor* b, const srk_tensor* out, void* stream) {
+  ACT_CHECK(a, "srk_act_add"); ACT_CHECK(b, "srk_act_add"); ACT_CHECK(out, "srk_act_add");
+  SRK_REQUIRE(same_geometry(a, b) && same_geometry(a, out) && a->dtype == b->dtype && a->dtype == out->dtype, "srk_act_add: geometry mismatch");
+  long long total = act_elems(a);
+  if (a->dtype == SRK_BF16)
+    act_add_kernel<__nv_bfloat16><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a->data, (const __nv_bfloat16*)b->data, (__nv_bfloat16*)out->data, total);
+  else
+    act_add_kernel<float><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((const float*)a->data, (const float*)b->data, (float*)out->data, total);
+  SRK_CUDA_LAUNCH_CHECK("act_add");
+  return 0;
+}
+
+extern "C" int srk_bicubic_upsample(const srk_tensor* in, const srk_tensor* out, void* stream) {
+  SRK_REQUIRE(in && out && in->layout == SRK_LAYOUT_IMAGE && out->layout == SRK_LAYOUT_IMAGE, "srk_bicubic_upsample: IMAGE tensors expected");
+  SRK_REQUIRE(in->n == out->n && in->c == out->c && out->h >= 1 && out->w >= 1, "srk_bicubic_upsample: geometry mismatch");
+  // F.interpolate(scale_factor=s) with recompute_scale_factor=None uses 1/s as the coordinate scale
+  float sh = (float)((double)in->h / (double)out->h), sw = (float)((double)in->w / (double)out->w);
+  long long total = (long long)out->n * out->c * out->h * out->w;
+  bicubic_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((const float*)in->data, (float*)out->data, in->n * in->c, in->h, in->w, out->h, out->w, sh, sw);
+  SRK_CUDA_LAUNCH_CHECK("bicubic");
+  return 0;
+}

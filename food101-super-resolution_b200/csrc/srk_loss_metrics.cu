@@ -1,0 +1,474 @@
+// Pixel losses (nn.L1Loss / nn.MSELoss, loss.py:81-86), NLPD loss (loss.py:31-79) forward+backward,
+// PSNR / SSIM reductions (metrics.py:14-31 via torchmetrics 1.8.2) and a flat Adam step
+// (train.py:55,120).  All inputs are NCHW fp32 images; kernels are coalesced along W, vectorised
+// where alignment allows, and reduce with warp shuffles -> one atomic per block.
+#include "srk_common.cuh"
+
+namespace srk {
+
+// ---- L1 / MSE -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pixel_loss_fwd_kernel(const float* __restrict__ a,
+    const float* __restrict__ b, long long n, int mode, double* __restrict__ acc) {
+  __shared__ double red[32];
+  float s = 0.f;
+  long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4;
+  long long stride = (long long)gridDim.x * blockDim.x * 4;
+  const bool aligned = ((((uintptr_t)a) | ((uintptr_t)b)) & 15) == 0;
+  for (; i < n; i += stride) {
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+    if (aligned && i + 3 < n) {
+      float4 x = *reinterpret_cast<const float4*>(a + i), y = *reinterpret_cast<const float4*>(b + i);
+      d[0] = x.x - y.x; d[1] = x.y - y.y; d[2] = x.z - y.z; d[3] = x.w - y.w;
+    } else {
+      for (int j = 0; j < 4 && i + j < n; ++j) d[j] = a[i + j] - b[i + j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s += mode == 0 ? fabsf(d[j]) : d[j] * d[j];
+  }
+  double t = block_sum_d((double)s, red);
+  if (threadIdx.x == 0) atomicAdd(acc, t);
+}
+__global__ void scale_to_float_kernel(const double* acc, double scale, float* out) { out[0] = (float)(acc[0] * scale); }
+
+__global__ void __launch_bounds__(256) pixel_loss_bwd_kernel(const float* __restrict__ a,
+    const float* __restrict__ b, long long n, int mode, const float* __restrict__ gout,
+    float* __restrict__ g) {
+  const float go = gout[0] / (float)n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float d = a[i] - b[i];
+    g[i] = mode == 0 ? (d > 0.f ? go : (d < 0.f ? -go : 0.f)) : 2.f * d * go;
+  }
+}
+
+// ---- NLPD ------------------------------------------------------------------------------------------
+// The Laplacian pyramid is linear, so Lap_l(sr) - Lap_l(hr) = Lap_l(sr - hr): one pyramid of the
+// difference image d is built (half the reference's work, same value up to fp32 rounding).
+// Workspace layout (floats): for l in 0..L: cur_l [NC*h_l*w_l] (cur_0 = d); then per level l<L a
+// sign map s_l [NC*h_l*w_l] (int8), and two ping-pong gradient buffers of the level-0/level-1 size.
+struct NlpdPlan {
+  int L;
+  int h[8], w[8];
+  long long cur_off[8];   // float offsets
+  long long sign_off[8];  // byte offsets from sign base
+  long long g_off[2];     // float offsets
+  long long floats, sign_bytes, total_bytes;
+  long long acc_off;      // byte offset of double acc[8]
+};
+static NlpdPlan nlpd_plan(int n, int c, int h, int w, int L) {
+  NlpdPlan p; p.L = L;
+  long long nc = (long long)n * c, off = 0;
+  p.h[0] = h; p.w[0] = w;
+  for (int l = 0; l <= L; ++l) {
+    if (l > 0) { p.h[l] = (p.h[l - 1] + 1) / 2; p.w[l] = (p.w[l - 1] + 1) / 2; }
+    p.cur_off[l] = off; off += nc * p.h[l] * p.w[l];
+  }
+  p.g_off[0] = off; off += nc * p.h[0] * p.w[0];
+  p.g_off[1] = off; off += nc * p.h[1] * p.w[1];
+  p.floats = off;
+  long long sb = 0;
+  for (int l = 0; l < L; ++l) { p.sign_off[l] = sb; sb += (nc * p.h[l] * p.w[l] + 15) / 16 * 16; }
+  p.sign_bytes = sb;
+  p.acc_off = (p.floats * 4 + 15) / 16 * 16 + sb;
+  p.total_bytes = p.acc_off + 8 * sizeof(double);
+  return p;
+}
+
+__global__ void __launch_bounds__(256) nlpd_diff_kernel(const float* __restrict__ a,
+    const float* __restrict__ b, long long n, int clamp01, float* __restrict__ d, double* __restrict__ acc) {
+  __shared__ double red[32];
+  float s = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float x = a[i], y = b[i];
+    if (clamp01) { x = fminf(fmaxf(x, 0.f), 1.f); y = fminf(fmaxf(y, 0.f), 1.f); }
+    float v = x - y;
+    d[i] = v; s += fabsf(v);
+  }
+  double t = block_sum_d((double)s, red);
+  if (threadIdx.x == 0) atomicAdd(acc, t);
+}
+
+// down[y][x] = sum_{ky,kx} k[ky][kx] * cur[2y+ky-2][2x+kx-2] (zero padded)   (loss.py:61-62)
+__global__ void __launch_bounds__(256) nlpd_blur_down_kernel(const float* __restrict__ cur, int NC, int H,
+    int W, int h2, int w2, const float* __restrict__ k25, float* __restrict__ down) {
+  __shared__ float k[25];
+  if (threadIdx.x < 25) k[threadIdx.x] = k25[threadIdx.x];
+  __syncthreads();
+  long long total = (long long)NC * h2 * w2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int x = (int)(i % w2); long long t = i / w2;
+    int y = (int)(t % h2); int nc = (int)(t / h2);
+    const float* p = cur + (long long)nc * H * W;
+    float acc = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky) {
+      int yy = 2 * y + ky - 2;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 5; ++kx) {
+        int xx = 2 * x + kx - 2;
+        if (xx < 0 || xx >= W) continue;
+        acc = fmaf(k[ky * 5 + kx], p[(long long)yy * W + xx], acc);
+      }
+    }
+    down[i] = acc;
+  }
+}
+
+// bilinear, align_corners=False, explicit output size (loss.py:63): src = max(scale*(o+.5)-.5, 0)
+__device__ __forceinline__ void bilin_src(int o, float scale, int in, int& i0, int& i1, float& lam) {
+  float src = fmaxf(scale * (o + 0.5f) - 0.5f, 0.f);
+  i0 = (int)src; if (i0 > in - 1) i0 = in - 1;
+  i1 = i0 + (i0 < in - 1 ? 1 : 0);
+  lam = src - (float)i0;
+  lam = fminf(fmaxf(lam, 0.f), 1.f);
+}
+
+// diff = cur - up(down); accumulates sum|diff|; optionally stores sign(diff) as int8
+__global__ void __launch_bounds__(256) nlpd_lap_abs_kernel(const float* __restrict__ cur,
+    const float* __restrict__ down, int NC, int H, int W, int h2, int w2, float sy, float sx,
+    signed char* __restrict__ sign, double* __restrict__ acc) {
+  __shared__ double red[32];
+  long long total = (long long)NC * H * W;
+  float s = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int x = (int)(i % W); long long t = i / W;
+    int y = (int)(t % H); int nc = (int)(t / H);
+    int y0, y1, x0, x1; float ly, lx;
+    bilin_src(y, sy, h2, y0, y1, ly);
+    bilin_src(x, sx, w2, x0, x1, lx);
+    const float* p = down + (long long)nc * h2 * w2;
+    float up = (1.f - ly) * ((1.f - lx) * p[y0 * w2 + x0] + lx * p[y0 * w2 + x1]) +
+               ly * ((1.f - lx) * p[y1 * w2 + x0] + lx * p[y1 * w2 + x1]);
+    float d = cur[i] - up;
+    s += fabsf(d);
+    if (sign) sign[i] = d > 0.f ? 1 : (d < 0.f ? -1 : 0);
+  }
+  double t = block_sum_d((double)s, red);
+  if (threadIdx.x == 0) atomicAdd(acc, t);
+}
+
+struct NlpdWeights { double w[8]; };
+__global__ void nlpd_combine_kernel(const double* acc, NlpdWeights wt, float* loss) {
+  double v = 0.0;
+  for (int i = 0; i < 8; ++i) v += acc[i] * wt.w[i];
+  loss[0] = (float)v;
+}
+
+// g_down[y][x] = G_next[y][x] - c_l * sum_{Y,X} Uy[Y][y] Ux[X][x] sign_l[Y][X]    (bilinear^T)
+__global__ void __launch_bounds__(256) nlpd_bwd_down_kernel(const signed char* __restrict__ sign,
+    const float* __restrict__ g_next, int NC, int H, int W, int h2, int w2, float sy, float sx, float c_l,
+    float* __restrict__ g_down) {
+  long long total = (long long)NC * h2 * w2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int x = (int)(i % w2); long long t = i / w2;
+    int y = (int)(t % h2); int nc = (int)(t / h2);
+    const signed char* sp = sign + (long long)nc * H * W;
+    float acc = 0.f;
+    for (int Y = max(2 * y - 3, 0); Y <= min(2 * y + 4, H - 1); ++Y) {
+      int y0, y1; float ly;
+      bilin_src(Y, sy, h2, y0, y1, ly);
+      float wy = (y0 == y ? 1.f - ly : 0.f) + (y1 == y ? ly : 0.f);
+      if (wy == 0.f) continue;
+      for (int X = max(2 * x - 3, 0); X <= min(2 * x + 4, W - 1); ++X) {
+        int x0, x1; float lx;
+        bilin_src(X, sx, w2, x0, x1, lx);
+        float wx = (x0 == x ? 1.f - lx : 0.f) + (x1 == x ? lx : 0.f);
+        if (wx == 0.f) continue;
+        acc = fmaf(wy * wx, (float)sp[(long long)Y * W + X], acc);
+      }
+    }
+    g_down[i] = (g_next ? g_next[i] : 0.f) - c_l * acc;
+  }
+}
+
+// G_l[Y][X] = c_l*sign_l[Y][X] + sum_{ky,kx: (Y+2-ky),(X+2-kx) even} k[ky][kx] g_down[(Y+2-ky)/2][(X+2-kx)/2]
+// level 0 additionally adds alpha*sign(d)/numel, multiplies by gout and writes grad_sr.
+__global__ void __launch_bounds__(256) nlpd_bwd_up_kernel(const signed char* __restrict__ sign,
+    const float* __restrict__ g_down, int NC, int H, int W, int h2, int w2, const float* __restrict__ k25,
+    float c_l, const float* __restrict__ d0, float c_mae, const float* __restrict__ gout,
+    float* __restrict__ G) {
+  __shared__ float k[25];
+  if (threadIdx.x < 25) k[threadIdx.x] = k25[threadIdx.x];
+  __syncthreads();
+  const float go = gout ? gout[0] : 1.f;
+  long long total = (long long)NC * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int X = (int)(i % W); long long t = i / W;
+    int Y = (int)(t % H); int nc = (int)(t / H);
+    const float* gp = g_down + (long long)nc * h2 * w2;
+    float acc = c_l * (float)sign[i];
+    // blurred[yy][xx] reads cur[yy+ky-2][xx+kx-2]; only even (yy,xx) are kept as down[yy/2][xx/2]
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky) {
+      int yy = Y + 2 - ky;
+      if (yy < 0 || (yy & 1) || (yy >> 1) >= h2) continue;
+#pragma unroll
+      for (int kx = 0; kx < 5; ++kx) {
+        int xx = X + 2 - kx;
+        if (xx < 0 || (xx & 1) || (xx >> 1) >= w2) continue;
+        acc = fmaf(k[ky * 5 + kx], gp[(long long)(yy >> 1) * w2 + (xx >> 1)], acc);
+      }
+    }
+    if (d0) {
+      float d = d0[i];
+      acc += d > 0.f ? c_mae : (d < 0.f ? -c_mae : 0.f);
+      acc *= go;
+    }
+    G[i] = acc;
+  }
+}
+
+// ---- PSNR / SSIM ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) psnr_sse_kernel(const float* __restrict__ a, const float* __restrict__ b,
+    long long per_image, int clamp01, double* __restrict__ sse) {
+  __shared__ double red[32];
+  const int n = blockIdx.y;
+  const float* pa = a + (long long)n * per_image;
+  const float* pb = b + (long long)n * per_image;
+  float s = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_image;
+       i += (long long)gridDim.x * blockDim.x) {
+    float x = pa[i], y = pb[i];
+    if (clamp01) { x = fminf(fmaxf(x, 0.f), 1.f); y = fminf(fmaxf(y, 0.f), 1.f); }
+    float d = x - y;
+    s = fmaf(d, d, s);
+  }
+  double t = block_sum_d((double)s, red);
+  if (threadIdx.x == 0) atomicAdd(&sse[n], t);
+}
+
+// SSIM (gaussian 11x11, sigma 1.5, k1=.01, k2=.03, data_range 1): the reflect padding of
+// torchmetrics is cropped away again, so only the (H-10)x(W-10) valid windows contribute.
+// Tile: 32x16 outputs from a 42x26 input patch; separable: horizontal pass of the 5 maps into shared
+// memory, vertical pass per output.
+constexpr int ST_W = 32, ST_H = 16, SK = 11;
+__global__ void __launch_bounds__(ST_W * ST_H) ssim_kernel(const float* __restrict__ a, const float* __restrict__ b,
+    int C, int H, int W, int clamp01, double* __restrict__ out) {
+  __shared__ float pa[ST_H + SK - 1][ST_W + SK - 1 + 1];
+  __shared__ float pb[ST_H + SK - 1][ST_W + SK - 1 + 1];
+  __shared__ float hm[5][ST_H + SK - 1][ST_W + 1];
+  __shared__ float g[SK];
+  __shared__ double red[32];
+  const int tid = threadIdx.y * ST_W + threadIdx.x;
+  if (tid == 0) {
+    double s = 0.0, t[SK];
+    for (int i = 0; i < SK; ++i) { double d = (i - 5) / 1.5; t[i] = exp(-d * d / 2.0); s += t[i]; }
+    for (int i = 0; i < SK; ++i) g[i] = (float)(t[i] / s);
+  }
+  const int nc = blockIdx.z, n = nc / C;
+  const int OH = H - (SK - 1), OW = W - (SK - 1);
+  const int ox0 = blockIdx.x * ST_W, oy0 = blockIdx.y * ST_H;
+  const float* A = a + (long long)nc * H * W;
+  const float* B = b + (long long)nc * H * W;
+  for (int i = tid; i < (ST_H + SK - 1) * (ST_W + SK - 1); i += ST_W * ST_H) {
+    int r = i / (ST_W + SK - 1), cc = i - r * (ST_W + SK - 1);
+    int y = oy0 + r, x = ox0 + cc;
+    float va = 0.f, vb = 0.f;
+    if (y < H && x < W) {
+      va = A[(long long)y * W + x]; vb = B[(long long)y * W + x];
+      if (clamp01) { va = fminf(fmaxf(va, 0.f), 1.f); vb = fminf(fmaxf(vb, 0.f), 1.f); }
+    }
+    pa[r][cc] = va; pb[r][cc] = vb;
+  }
+  __syncthreads();
+  for (int i = tid; i < (ST_H + SK - 1) * ST_W; i += ST_W * ST_H) {
+    int r = i / ST_W, cc = i - r * ST_W;
+    float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, m4 = 0.f;
+#pragma unroll
+    for (int k = 0; k < SK; ++k) {
+      float w = g[k], x = pa[r][cc + k], y = pb[r][cc + k];
+      m0 = fmaf(w, x, m0); m1 = fmaf(w, y, m1);
+      m2 = fmaf(w, x * x, m2); m3 = fmaf(w, y * y, m3); m4 = fmaf(w, x * y, m4);
+    }
+    hm[0][r][cc] = m0; hm[1][r][cc] = m1; hm[2][r][cc] = m2; hm[3][r][cc] = m3; hm[4][r][cc] = m4;
+  }
+  __syncthreads();
+  float val = 0.f;
+  {
+    int oy = oy0 + threadIdx.y, ox = ox0 + threadIdx.x;
+    if (oy < OH && ox < OW) {
+      float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, m4 = 0.f;
+#pragma unroll
+      for (int k = 0; k < SK; ++k) {
+        float w = g[k];
+        m0 = fmaf(w, hm[0][threadIdx.y + k][threadIdx.x], m0);
+        m1 = fmaf(w, hm[1][threadIdx.y + k][threadIdx.x], m1);
+        m2 = fmaf(w, hm[2][threadIdx.y + k][threadIdx.x], m2);
+        m3 = fmaf(w, hm[3][threadIdx.y + k][threadIdx.x], m3);
+        m4 = fmaf(w, hm[4][threadIdx.y + k][threadIdx.x], m4);
+      }
+      const float c1 = 1e-4f, c2 = 9e-4f;
+      float mu_pp = m0 * m0, mu_tt = m1 * m1, mu_pt = m0 * m1;
+      float s_pp = fmaxf(m2 - mu_pp, 0.f), s_tt = fmaxf(m3 - mu_tt, 0.f), s_pt = m4 - mu_pt;
+      val = ((2.f * mu_pt + c1) * (2.f * s_pt + c2)) / ((mu_pp + mu_tt + c1) * (s_pp + s_tt + c2));
+    }
+  }
+  // block reduce (2-D block -> linear tid)
+  double v = warp_sum_d((double)val);
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  __syncthreads();
+  if (tid < 32) {
+    double r = tid < (ST_W * ST_H / 32) ? red[tid] : 0.0;
+    r = warp_sum_d(r);
+    if (tid == 0) atomicAdd(&out[n], r);
+  }
+}
+
+// ---- Adam -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+    float* __restrict__ m, float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
+    const long long* __restrict__ step, float grad_scale) {
+  const double t = (double)step[0];
+  const float bc1 = (float)(1.0 - pow((double)b1, t));
+  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
+  const float step_size = lr / bc1;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float gi = g[i] * grad_scale;
+    float mi = m[i] + (1.f - b1) * (gi - m[i]);      // torch: exp_avg.lerp_(grad, 1-beta1)
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= step_size * (mi / denom);
+  }
+}
+
+}  // namespace srk
+
+using namespace srk;
+
+static inline int red_blocks(long long n, int per_thread) {
+  long long b = (n + 256LL * per_thread - 1) / (256LL * per_thread);
+  if (b > 148 * 8) b = 148 * 8;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+extern "C" int srk_pixel_loss_fwd(const float* sr, const float* hr, int64_t numel, int mode, float* loss,
+                                  double* scratch, void* stream) {
+  SRK_REQUIRE(numel > 0 && (mode == 0 || mode == 1), "srk_pixel_loss_fwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(scratch, 0, sizeof(double), st);
+  pixel_loss_fwd_kernel<<<red_blocks(numel, 16), 256, 0, st>>>(sr, hr, numel, mode, scratch);
+  scale_to_float_kernel<<<1, 1, 0, st>>>(scratch, 1.0 / (double)numel, loss);
+  SRK_CUDA_LAUNCH_CHECK("pixel_loss_fwd");
+  return 0;
+}
+
+extern "C" int srk_pixel_loss_bwd(const float* sr, const float* hr, int64_t numel, int mode,
+                                  const float* gout, float* grad_sr, void* stream) {
+  SRK_REQUIRE(numel > 0 && (mode == 0 || mode == 1), "srk_pixel_loss_bwd: bad arguments");
+  pixel_loss_bwd_kernel<<<red_blocks(numel, 4), 256, 0, (cudaStream_t)stream>>>(sr, hr, numel, mode, gout, grad_sr);
+  SRK_CUDA_LAUNCH_CHECK("pixel_loss_bwd");
+  return 0;
+}
+
+extern "C" int64_t srk_nlpd_workspace_bytes(int n, int c, int h, int w, int levels) {
+  if (levels < 1 || levels > 6) return -1;
+  return nlpd_plan(n, c, h, w, levels).total_bytes;
+}
+
+extern "C" int srk_nlpd_fwd(const float* sr, const float* hr, int n, int c, int h, int w, int levels,
+                            float alpha, const float* kernel25, int clamp01, void* workspace, float* loss,
+                            void* stream) {
+  SRK_REQUIRE(levels >= 1 && levels <= 6, "srk_nlpd_fwd: levels must be in [1,6]");
+  SRK_REQUIRE(((uintptr_t)workspace & 15) == 0, "srk_nlpd_fwd: workspace must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  NlpdPlan p = nlpd_plan(n, c, h, w, levels);
+  float* wsf = (float*)workspace;
+  signed char* sbase = (signed char*)workspace + (p.floats * 4 + 15) / 16 * 16;
+  double* acc = (double*)((char*)workspace + p.acc_off);
+  const int NC = n * c;
+  cudaMemsetAsync(acc, 0, 8 * sizeof(double), st);
+  long long n0 = (long long)NC * h * w;
+  nlpd_diff_kernel<<<red_blocks(n0, 8), 256, 0, st>>>(sr, hr, n0, clamp01, wsf + p.cur_off[0], acc);
+  NlpdWeights wt;
+  for (int i = 0; i < 8; ++i) wt.w[i] = 0.0;
+  wt.w[0] = (double)alpha / (double)n0;
+  for (int l = 0; l < levels; ++l) {
+    int H = p.h[l], W = p.w[l], h2 = p.h[l + 1], w2 = p.w[l + 1];
+    long long nd = (long long)NC * h2 * w2, nu = (long long)NC * H * W;
+    nlpd_blur_down_kernel<<<red_blocks(nd, 2), 256, 0, st>>>(wsf + p.cur_off[l], NC, H, W, h2, w2, kernel25, wsf + p.cur_off[l + 1]);
+    float sy = (float)((double)h2 / H), sx = (float)((double)w2 / W);
+    nlpd_lap_abs_kernel<<<red_blocks(nu, 4), 256, 0, st>>>(wsf + p.cur_off[l], wsf + p.cur_off[l + 1], NC, H, W, h2, w2, sy, sx, sbase + p.sign_off[l], acc + 1 + l);
+    wt.w[1 + l] = (1.0 - (double)alpha) / (double)nu;
+  }
+  nlpd_combine_kernel<<<1, 1, 0, st>>>(acc, wt, loss);
+  SRK_CUDA_LAUNCH_CHECK("nlpd_fwd");
+  return 0;
+}
+
+extern "C" int srk_nlpd_bwd(int n, int c, int h, int w, int levels, float alpha, const float* kernel25,
+                            void* workspace, const float* gout, float* grad_sr, void* stream) {
+  SRK_REQUIRE(levels >= 1 && levels <= 6, "srk_nlpd_bwd: levels must be in [1,6]");
+  cudaStream_t st = (cudaStream_t)stream;
+  NlpdPlan p = nlpd_plan(n, c, h, w, levels);
+  float* wsf = (float*)workspace;
+  signed char* sbase = (signed char*)workspace + (p.floats * 4 + 15) / 16 * 16;
+  const int NC = n * c;
+  // coarse -> fine.  G_{l+1} (gradient w.r.t. cur_{l+1}) lives in g buffer (l+1)&1 ... sizes shrink
+  // with l, so buffer 0 (level-0 sized) and buffer 1 (level-1 sized) alternate safely: G_l for odd l
+  // in buffer 1, even l >= 2 in buffer 0; g_down_l reuses the cur_{l+1} slot (no longer needed).
+  const float* g_next = nullptr;  // G_{L} = 0 : nothing consumes cur_L except the top-level upsample
+  for (int l = levels - 1; l >= 0; --l) {
+    int H = p.h[l], W = p.w[l], h2 = p.h[l + 1], w2 = p.w[l + 1];
+    long long nd = (long long)NC * h2 * w2, nu = (long long)NC * H * W;
+    float c_l = (float)((1.0 - (double)alpha) / (double)nu);
+    float sy = (float)((double)h2 / H), sx = (float)((double)w2 / W);
+    float* g_down = wsf + p.cur_off[l + 1];
+    nlpd_bwd_down_kernel<<<red_blocks(nd, 1), 256, 0, st>>>(sbase + p.sign_off[l], g_next, NC, H, W, h2, w2, sy, sx, c_l, g_down);
+    if (l == 0) {
+      float c_mae = (float)((double)alpha / (double)nu);
+      nlpd_bwd_up_kernel<<<red_blocks(nu, 2), 256, 0, st>>>(sbase + p.sign_off[0], g_down, NC, H, W, h2, w2, kernel25, c_l, wsf + p.cur_off[0], c_mae, gout, grad_sr);
+    } else {
+      float* G = wsf + p.g_off[l & 1];
+      nlpd_bwd_up_kernel<<<red_blocks(nu, 2), 256, 0, st>>>(sbase + p.sign_off[l], g_down, NC, H, W, h2, w2, kernel25, c_l, nullptr, 0.f, nullptr, G);
+      g_next = G;
+    }
+  }
+  SRK_CUDA_LAUNCH_CHECK("nlpd_bwd");
+  return 0;
+}
+
+extern "C" int srk_psnr_sse(const float* sr, const float* hr, int n, int64_t per_image, int clamp01,
+                            double* sse, void* stream) {
+  SRK_REQUIRE(n > 0 && per_image > 0, "srk_psnr_sse: empty input");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(sse, 0, sizeof(double) * n, st);
+  int bx = red_blocks(per_image, 8);
+  int cap = (148 * 8 + n - 1) / n; if (cap < 1) cap = 1;
+  if (bx > cap) bx = cap;
+  psnr_sse_kernel<<<dim3(bx, n), 256, 0, st>>>(sr, hr, per_image, clamp01, sse);
+  SRK_CUDA_LAUNCH_CHECK("psnr_sse");
+  return 0;
+}
+
+extern "C" int srk_ssim(const float* sr, const float* hr, int n, int c, int h, int w, int clamp01,
+                        double* ssim_sum, void* stream) {
+  SRK_REQUIRE(n > 0 && c > 0, "srk_ssim: empty input");
+  SRK_REQUIRE(h > 10 && w > 10, "srk_ssim: image smaller than the 11x11 window");
+  SRK_REQUIRE((long long)n * c <= 65535, "srk_ssim: too many planes in one call");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(ssim_sum, 0, sizeof(double) * n, st);
+  int OH = h - 10, OW = w - 10;
+  dim3 grid((OW + ST_W - 1) / ST_W, (OH + ST_H - 1) / ST_H, n * c);
+  ssim_kernel<<<grid, dim3(ST_W, ST_H), 0, st>>>(sr, hr, c, h, w, clamp01, ssim_sum);
+  SRK_CUDA_LAUNCH_CHECK("ssim");
+  return 0;
+}
+
+extern "C" int srk_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                             int64_t numel, float lr, float beta1, float beta2, float eps,
+                             const int64_t* step_count, float grad_scale, void* stream) {
+  SRK_REQUIRE(numel > 0, "srk_adam_step: empty parameter buffer");
+  adam_kernel<<<red_blocks(numel, 4), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps, (const long long*)step_count, grad_scale);
+  SRK_CUDA_LAUNCH_CHECK("adam");
+  return 0;
+}

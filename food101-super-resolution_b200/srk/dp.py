@@ -1,0 +1,83 @@
+"""Data-parallel glue: one process per GPU, weights replicated, the global batch sharded over ranks,
+gradients averaged with one all-reduce per flat bucket (NCCL over NVLink on GPUs; any
+torch.distributed backend works - the gloo backend is what the CPU tests use).
+
+The reference has no distributed path at all; semantics follow SURVEY 8e: losses are
+batch means, so equal shards + gradient averaging reproduce the single-process gradient for
+AttentionSR / SRCNN exactly, and ResNet-SR BatchNorm keeps per-rank batch statistics (DDP semantics)."""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(total, rank, world):
+    """Contiguous, balanced [begin, end) slice of `total` items for `rank` (ragged tails go to low ranks)."""
+    base, rem = divmod(total, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def make_buckets(params, bucket_bytes=8 << 20):
+    """Groups parameters in reverse registration order (the order backward produces gradients) into
+    buckets of about `bucket_bytes`."""
+    buckets, cur, size = [], [], 0
+    for p in reversed([p for p in params if p.requires_grad]):
+        cur.append(p)
+        size += p.numel() * p.element_size()
+        if size >= bucket_bytes:
+            buckets.append(cur)
+            cur, size = [], 0
+    if cur:
+        buckets.append(cur)
+    return buckets
+
+
+class GradAverager:
+    """Averages .grad of `params` across the process group through flat fp32 buckets."""
+
+    def __init__(self, params, bucket_bytes=8 << 20, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.buckets = make_buckets(list(params), bucket_bytes)
+        self.flat = [None] * len(self.buckets)
+
+    def _flat(self, i, like):
+        n = sum(p.numel() for p in self.buckets[i])
+        if self.flat[i] is None or self.flat[i].device != like.device:
+            self.flat[i] = torch.empty((n,), dtype=torch.float32, device=like.device)
+        return self.flat[i]
+
+    @torch.no_grad()
+    def average(self, async_op=False):
+        if self.world == 1:
+            return []
+        works = []
+        for i, bucket in enumerate(self.buckets):
+            grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in bucket]
+            flat = self._flat(i, grads[0])
+            views = list(flat.split([g.numel() for g in grads]))
+            torch._foreach_copy_(views, [g.reshape(-1) for g in grads])
+            flat.div_(self.world)
+            w = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            works.append((w, bucket, views))
+        if async_op:
+            return works
+        self.finish(works)
+        return []
+
+    @torch.no_grad()
+    def finish(self, works):
+        for w, bucket, views in works:
+            w.wait()
+            for p, v in zip(bucket, views):
+                if p.grad is None:
+                    p.grad = v.view_as(p).clone()
+                else:
+                    p.grad.copy_(v.view_as(p))
+
+
+def broadcast_parameters(module, src=0, group=None):
+    """Makes every rank start from rank `src`'s weights and buffers."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src=src, group=group)

@@ -1,0 +1,225 @@
+"""Autograd nodes of the SR hot path.  Each node is one fused stage of the reference graph
+(/root/reference/src/models.py) whose forward and backward are libsrk kernels:
+
+  ConvAct      conv + bias + ReLU/PReLU + PixelShuffle(2) [+ residual]         models.py:84-87,107-108,116-125
+  ConvBN       conv + bias + BatchNorm2d [+ PReLU] [+ residual]                 models.py:55-60,113-114,140-141
+  AttnBlock    conv + PReLU + conv + squeeze-excite gate + scaled skip          models.py:62-78
+  ImageToAct / ActToImage                                                       layout boundary
+
+Gradients w.r.t. parameters are returned as ordinary fp32 tensors in the state_dict layout (OIHW),
+so torch.optim / utils.py (train.py:55,122-133) see what they see with the reference."""
+import torch
+
+from . import _lib as L
+from . import ops
+
+
+def _needs(ctx, i):
+    return ctx.needs_input_grad[i]
+
+
+class ImageToAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, dtype):
+        ops.require_cuda(img, "image_to_act")
+        return ops.image_to_act(img.contiguous().float(), dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.act_to_image(g.contiguous()), None
+
+
+class ActToImage(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a):
+        ctx.dtype = a.dtype
+        return ops.act_to_image(a)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.image_to_act(g.contiguous().float(), ctx.dtype)
+
+
+class ConvAct(torch.autograd.Function):
+    """y = [PixelShuffle2](act(conv(x) + b)) (+ residual).  act in {none, relu, prelu(single alpha)}."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, alpha, residual, act, shuffle, x_img, out_img, out_dtype):
+        ops.require_cuda(x, "conv")
+        x = x.contiguous()
+        if x_img:
+            x = x.float()
+        assert not (shuffle and residual is not None)
+        assert not (act != L.ACT_NONE and residual is not None), "residual is added to un-activated outputs only"
+        assert not (out_img and act != L.ACT_NONE), "activated outputs are kept in the act layout"
+        # with pixel-shuffle the activation is applied by the conv epilogue before the store remap
+        # (a single-alpha PReLU / ReLU commutes with the permutation, models.py:117-119)
+        y, used_tc = ops.conv_fprop(x, x_img, weight, bias, act, alpha, residual, shuffle, out_img, out_dtype)
+        ctx.save_for_backward(x, weight, alpha, y if act != L.ACT_NONE else None)
+        ctx.cfg = (act, shuffle, x_img, out_img, bias is not None, residual is not None, used_tc)
+        return y
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, weight, alpha, y = ctx.saved_tensors
+        act, shuffle, x_img, out_img, has_bias, has_res, used_tc = ctx.cfg
+        dout = dout.contiguous()
+        dalpha = None
+        perm = bool(used_tc and shuffle == 2)
+        if act != L.ACT_NONE or shuffle == 2:
+            dz, dalpha = ops.act_bwd(dout, y if y is not None else dout, act, alpha, shuffle, perm)
+            dz_img = False
+        else:
+            dz, dz_img = dout, out_img
+        dw = db = dx = None
+        if _needs(ctx, 1) or (has_bias and _needs(ctx, 2)):
+            dw, db = ops.conv_wgrad(x, x_img, dz, dz_img, weight, has_bias, perm)
+        if _needs(ctx, 0):
+            dx = ops.conv_dgrad(dz, dz_img, weight, None, x.dtype if not x_img else torch.float32, perm)
+            if x_img:
+                dx = ops.act_to_image(dx)
+        dres = dout if (has_res and _needs(ctx, 4)) else None
+        return dx, dw, db, (dalpha if _needs(ctx, 3) else None), dres, None, None, None, None, None
+
+
+def conv_act(x, conv, act=L.ACT_NONE, alpha=None, residual=None, shuffle=0, x_img=False, out_img=False,
+             out_dtype=None):
+    if out_dtype is None:
+        out_dtype = torch.float32 if out_img else (x.dtype if not x_img else ops.cfg.compute_dtype)
+    return ConvAct.apply(x, conv.weight, conv.bias, alpha, residual, act, shuffle, x_img, out_img, out_dtype)
+
+
+def _conv_bn_forward(x, w, b, bn_params, bn_buffers, training, eps, momentum, alpha, residual):
+    gamma, beta = bn_params
+    rm, rv, nbt = bn_buffers
+    y, used_tc = ops.conv_fprop(x, False, w, b, L.ACT_NONE, None, None, 0, False, x.dtype)
+    out, stats = ops.bn_forward(y, gamma, beta, rm, rv, nbt, training, eps, momentum, alpha, residual)
+    return y, out, stats
+
+
+def _conv_bn_backward(dout, x, y, stats, w, has_bias, gamma, beta, alpha, batch_stats, dgrad_residual, need_dx):
+    dy, dgamma, dbeta, dalpha = ops.bn_backward(dout, y, stats, gamma, beta, alpha, batch_stats)
+    dw, db = ops.conv_wgrad(x, False, dy, False, w, has_bias)
+    dx = ops.conv_dgrad(dy, False, w, dgrad_residual, x.dtype) if need_dx else None
+    return dx, dw, db, dgamma, dbeta, dalpha
+
+
+class ConvBN(torch.autograd.Function):
+    """out = [PReLU](BN(conv(x) + b)) [+ residual]   (mid_conv + bn_mid + skip, models.py:140-141)"""
+
+    @staticmethod
+    def forward(ctx, x, w, b, gamma, beta, alpha, residual, rm, rv, nbt, training, eps, momentum):
+        ops.require_cuda(x, "conv_bn")
+        x = x.contiguous()
+        y, out, stats = _conv_bn_forward(x, w, b, (gamma, beta), (rm, rv, nbt), training, eps, momentum,
+                                         alpha, residual)
+        ctx.save_for_backward(x, y, stats, w, gamma, beta, alpha)
+        ctx.cfg = (b is not None, residual is not None, training or rm is None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, y, stats, w, gamma, beta, alpha = ctx.saved_tensors
+        has_bias, has_res, batch_stats = ctx.cfg
+        dout = dout.contiguous()
+        dx, dw, db, dgamma, dbeta, dalpha = _conv_bn_backward(
+            dout, x, y, stats, w, has_bias, gamma, beta, alpha, batch_stats, None, _needs(ctx, 0))
+        return (dx, dw, db, dgamma, dbeta, dalpha, dout if has_res else None,
+                None, None, None, None, None, None)
+
+
+class ResBlockBN(torch.autograd.Function):
+    """out = x + BN2(conv2(PReLU(BN1(conv1(x)))))   (ResidualBlock.forward, models.py:55-60, use_se=False)"""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, g1, be1, alpha, w2, b2, g2, be2, buf1, buf2, training, eps1, mom1, eps2, mom2):
+        ops.require_cuda(x, "residual block")
+        x = x.contiguous()
+        y1, a1, st1 = _conv_bn_forward(x, w1, b1, (g1, be1), buf1, training, eps1, mom1, alpha, None)
+        y2, out, st2 = _conv_bn_forward(a1, w2, b2, (g2, be2), buf2, training, eps2, mom2, None, x)
+        ctx.save_for_backward(x, y1, st1, a1, y2, st2, w1, g1, be1, alpha, w2, g2, be2)
+        ctx.cfg = (b1 is not None, b2 is not None, training or buf1[0] is None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, y1, st1, a1, y2, st2, w1, g1, be1, alpha, w2, g2, be2 = ctx.saved_tensors
+        hb1, hb2, batch_stats = ctx.cfg
+        dout = dout.contiguous()
+        da1, dw2, db2, dg2, dbe2, _ = _conv_bn_backward(dout, a1, y2, st2, w2, hb2, g2, be2, None,
+                                                        batch_stats, None, True)
+        # the skip connection's gradient rides in the dgrad epilogue: dx = dgrad(dy1) + dout
+        dx, dw1, db1, dg1, dbe1, dalpha = _conv_bn_backward(da1, x, y1, st1, w1, hb1, g1, be1, alpha,
+                                                            batch_stats, dout, True)
+        return (dx, dw1, db1, dg1, dbe1, dalpha, dw2, db2, dg2, dbe2,
+                None, None, None, None, None, None, None)
+
+
+class AttnBlock(torch.autograd.Function):
+    """out = x + scale * SE(conv2(PReLU(conv1(x))))   (AttentionResidualBlock.forward, models.py:73-78)"""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, alpha, w2, b2, fc1, fc2, scale):
+        ops.require_cuda(x, "attention residual block")
+        x = x.contiguous()
+        a, _ = ops.conv_fprop(x, False, w1, b1, L.ACT_PRELU, alpha, None, 0, False, x.dtype)
+        r, _ = ops.conv_fprop(a, False, w2, b2, L.ACT_NONE, None, None, 0, False, x.dtype)
+        out, pool, hidden, gate = ops.se_forward(x, r, fc1, fc2, scale)
+        ctx.save_for_backward(x, a, r, pool, hidden, gate, w1, alpha, w2, fc1, fc2)
+        ctx.cfg = (b1 is not None, b2 is not None, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, a, r, pool, hidden, gate, w1, alpha, w2, fc1, fc2 = ctx.saved_tensors
+        hb1, hb2, scale = ctx.cfg
+        dout = dout.contiguous()
+        dr, dfc1, dfc2 = ops.se_backward(dout, r, pool, hidden, gate, fc1, fc2, scale)
+        dw2, db2 = ops.conv_wgrad(a, False, dr, False, w2, hb2)
+        da = ops.conv_dgrad(dr, False, w2, None, a.dtype)
+        dz1, dalpha = ops.act_bwd(da, a, L.ACT_PRELU, alpha, 0)
+        dw1, db1 = ops.conv_wgrad(x, False, dz1, False, w1, hb1)
+        dx = ops.conv_dgrad(dz1, False, w1, dout, x.dtype)
+        return dx, dw1, db1, dalpha, dw2, db2, dfc1, dfc2, None
+
+
+class SEGate(torch.autograd.Function):
+    """out = r * sigmoid(fc2(relu(fc1(mean_hw(r)))))   (SEBlock.forward, models.py:37-41)"""
+
+    @staticmethod
+    def forward(ctx, r, fc1, fc2):
+        ops.require_cuda(r, "SE block")
+        r = r.contiguous()
+        out, pool, hidden, gate = ops.se_forward(None, r, fc1, fc2, 1.0)
+        ctx.save_for_backward(r, pool, hidden, gate, fc1, fc2)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        r, pool, hidden, gate, fc1, fc2 = ctx.saved_tensors
+        dr, dfc1, dfc2 = ops.se_backward(dout.contiguous(), r, pool, hidden, gate, fc1, fc2, 1.0)
+        return dr, dfc1, dfc2
+
+
+class ActAdd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        return ops.act_add(a.contiguous(), b.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+class Bicubic(torch.autograd.Function):
+    """F.interpolate(mode='bicubic', align_corners=False) on the GPU (models.py:98 does it on the CPU).
+    The SRCNN input carries no gradient, so no backward is provided."""
+
+    @staticmethod
+    def forward(ctx, img, oh, ow):
+        ops.require_cuda(img, "bicubic upsample")
+        return ops.bicubic_upsample(img.contiguous().float(), oh, ow)
+
+    @staticmethod
+    def backward(ctx, g):
+        raise RuntimeError("bicubic upsample: gradient w.r.t. the low-resolution input is not implemented")

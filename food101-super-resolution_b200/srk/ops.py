@@ -1,0 +1,361 @@
+"""Thin, non-differentiable wrappers over the libsrk C ABI: descriptor construction, weight-pack
+cache and one Python function per kernel family.  torch is used for device memory and the
+current stream only; every arithmetic operation happens inside libsrk.
+
+Tensor conventions
+  image : NCHW fp32 contiguous (what the reference modules take / return)
+  act   : zero-bordered channels-last [N, H+2, W+2, C], fp32 or bf16 (internal activations)
+"""
+import weakref
+
+import torch
+
+from . import _lib as L
+
+
+class _Config:
+    # storage / arithmetic type of internal activations: torch.float32 (CUDA-core fp32 convs,
+    # reference-exact) or torch.bfloat16 (tcgen05 convs where the shape is supported)
+    compute_dtype = torch.float32
+    # "auto": tcgen05 when supported and activations are bf16, else CUDA cores; "simt": never tcgen05
+    conv_impl = "auto"
+
+
+cfg = _Config()
+
+
+def set_compute_dtype(dtype):
+    if isinstance(dtype, str):
+        dtype = {"fp32": torch.float32, "float32": torch.float32, "bf16": torch.bfloat16,
+                 "bfloat16": torch.bfloat16}[dtype.lower()]
+    if dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("compute dtype must be float32 or bfloat16")
+    cfg.compute_dtype = dtype
+
+
+def set_conv_impl(impl):
+    if impl not in ("auto", "simt"):
+        raise ValueError("conv impl must be 'auto' or 'simt'")
+    cfg.conv_impl = impl
+
+
+def require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(
+            "%s: libsrk runs on CUDA (sm_100a) tensors only; got a %s tensor. There is no CPU fallback."
+            % (what, t.device))
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dt(t):
+    if t.dtype == torch.bfloat16:
+        return L.BF16
+    if t.dtype == torch.float32:
+        return L.F32
+    raise TypeError("unsupported dtype %s" % t.dtype)
+
+
+def act_desc(t):
+    assert t.dim() == 4 and t.is_contiguous(), "act tensors are contiguous [N,H+2,W+2,C]"
+    n, hp, wp, c = t.shape
+    return L.SrkTensor(t.data_ptr(), L.LAYOUT_ACT, _dt(t), n, c, hp - 2, wp - 2)
+
+
+def img_desc(t):
+    assert t.dim() == 4 and t.is_contiguous() and t.dtype == torch.float32, "images are contiguous NCHW fp32"
+    n, c, h, w = t.shape
+    return L.SrkTensor(t.data_ptr(), L.LAYOUT_IMAGE, L.F32, n, c, h, w)
+
+
+def desc(t, is_image):
+    return img_desc(t) if is_image else act_desc(t)
+
+
+def geometry(t, is_image):
+    """-> (N, C, H, W) logical sizes"""
+    if is_image:
+        n, c, h, w = t.shape
+    else:
+        n, hp, wp, c = t.shape
+        h, w = hp - 2, wp - 2
+    return n, c, h, w
+
+
+def new_act(n, c, h, w, dtype, device):
+    return torch.empty((n, h + 2, w + 2, c), dtype=dtype, device=device)
+
+
+def new_image(n, c, h, w, device):
+    return torch.empty((n, c, h, w), dtype=torch.float32, device=device)
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+# ---- weight packing ------------------------------------------------------------------------------
+_pack_cache = {}
+_weights_epoch = 0
+
+
+def bump_weights_epoch():
+    """Call after parameters were modified behind torch's back (raw-pointer optimizer kernels)."""
+    global _weights_epoch
+    _weights_epoch += 1
+
+
+def _drop(key):
+    _pack_cache.pop(key, None)
+
+
+def packed_weight(weight, kind, shuffle):
+    """OIHW fp32 master weight -> kernel operand layout, cached until the weight is modified in place
+    (optimizer step bumps Tensor._version) or collected."""
+    key = id(weight)
+    ent = _pack_cache.get(key)
+    ver = (weight._version, _weights_epoch)
+    if ent is None or ent["ver"] != ver or ent["ptr"] != weight.data_ptr():
+        ent = {"ver": ver, "ptr": weight.data_ptr(), "packs": {}}
+        if key not in _pack_cache:
+            try:
+                ent["ref"] = weakref.ref(weight, lambda _r, k=key: _drop(k))
+            except TypeError:
+                pass
+        else:
+            ent["ref"] = _pack_cache[key].get("ref")
+        _pack_cache[key] = ent
+    pk = ent["packs"].get((kind, shuffle))
+    if pk is None:
+        cout, cin, r, s = weight.shape
+        w = weight.detach()
+        if not w.is_contiguous():
+            w = w.contiguous()
+        nbytes = L.cdll.srk_weight_pack_bytes(cout, cin, r, s, kind)
+        pk = torch.empty((nbytes,), dtype=torch.uint8, device=weight.device)
+        L.call("srk_weight_pack", w.data_ptr(), pk.data_ptr(), cout, cin, r, s, kind, shuffle, stream_ptr())
+        ent["packs"][(kind, shuffle)] = pk
+    return pk
+
+
+def tc_supported(cin, cout, r, s, dtype, shuffle):
+    if cfg.conv_impl == "simt" or dtype != torch.bfloat16:
+        return False
+    return bool(L.cdll.srk_conv_tc_supported(cin, cout, r, s, L.BF16, shuffle))
+
+
+# ---- optional per-kernel timing (bench.py roofline) -------------------------------------------------
+class KernelTimer:
+    """Brackets selected libsrk launches with CUDA events on the launching (current) stream."""
+
+    def __init__(self, select):
+        self.select, self.events = select, []
+
+    def wrap(self, key, launch):
+        if not self.select(key):
+            return launch()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = launch()
+        e1.record()
+        self.events.append((key, e0, e1))
+        return out
+
+    def summary(self):
+        """-> {key: (average ms, launches)}; synchronises."""
+        torch.cuda.synchronize()
+        acc = {}
+        for key, e0, e1 in self.events:
+            t, n = acc.get(key, (0.0, 0))
+            acc[key] = (t + e0.elapsed_time(e1), n + 1)
+        return {k: (t / n, n) for k, (t, n) in acc.items()}
+
+
+kernel_timer = None
+
+
+def _timed(key, launch):
+    if kernel_timer is None:
+        return launch()
+    return kernel_timer.wrap(key, launch)
+
+
+# ---- convolution -----------------------------------------------------------------------------------
+def conv_fprop(x, x_img, weight, bias, act, alpha, residual, shuffle, out_img, out_dtype):
+    """y = [shuffle](act(conv(x, weight) + bias)) [+ residual]; stride 1, pad R//2."""
+    n, cin, h, w = geometry(x, x_img)
+    cout, wcin, r, s = weight.shape
+    assert wcin == cin, "conv: input has %d channels, weight expects %d" % (cin, wcin)
+    use_tc = (not x_img) and (not out_img) and tc_supported(cin, cout, r, s, x.dtype, shuffle) \
+        and out_dtype == torch.bfloat16
+    kind = L.PACK_FPROP_TC if use_tc else L.PACK_FPROP_SIMT
+    pk = packed_weight(weight, kind, shuffle if use_tc else 0)
+    if shuffle == 2:
+        oc, oh, ow = cout // 4, 2 * h, 2 * w
+    else:
+        oc, oh, ow = cout, h, w
+    y = new_image(n, oc, oh, ow, x.device) if out_img else new_act(n, oc, oh, ow, out_dtype, x.device)
+    xd, yd = desc(x, x_img), desc(y, out_img)
+    rd = desc(residual, out_img) if residual is not None else None
+    _timed(("conv_fprop", cin, cout, r, shuffle, n, h, w, use_tc),
+           lambda: L.call("srk_conv_fprop", xd, yd, pk.data_ptr(), kind, cout, r, s, _ptr(bias), act,
+                          _ptr(alpha), rd, shuffle, L.IMPL_AUTO, stream_ptr()))
+    return y, use_tc
+
+
+def conv_dgrad(dz, dz_img, weight, residual, out_dtype, perm_tc=False):
+    """dx = conv_transpose(dz, weight) [+ residual]  (fprop over dz with rotated, transposed taps)."""
+    n, c, h, w = geometry(dz, dz_img)
+    cout, cin, r, s = weight.shape
+    assert c == cout
+    use_tc = (not dz_img) and tc_supported(cout, cin, r, s, dz.dtype, 0) and out_dtype == torch.bfloat16
+    if perm_tc and not use_tc:
+        raise RuntimeError("conv_dgrad: permuted dz requires the tcgen05 path")
+    kind = L.PACK_DGRAD_TC if use_tc else L.PACK_DGRAD_SIMT
+    pk = packed_weight(weight, kind, 2 if perm_tc else 0)
+    dx = new_act(n, cin, h, w, out_dtype, dz.device)
+    rd = act_desc(residual) if residual is not None else None
+    _timed(("conv_dgrad", cout, cin, r, 0, n, h, w, use_tc),
+           lambda: L.call("srk_conv_fprop", desc(dz, dz_img), act_desc(dx), pk.data_ptr(), kind, cin, r, s,
+                          None, L.ACT_NONE, None, rd, 0, L.IMPL_AUTO, stream_ptr()))
+    return dx
+
+
+def conv_wgrad(x, x_img, dz, dz_img, weight, need_bias, perm_tc=False):
+    """-> (dW fp32 OIHW, db fp32 [Cout] or None)"""
+    if perm_tc:
+        raise RuntimeError("conv_wgrad: sub-pixel-major dz is not supported yet")
+    cout, cin, r, s = weight.shape
+    dw = torch.zeros_like(weight, memory_format=torch.contiguous_format)
+    db = torch.zeros((cout,), dtype=torch.float32, device=weight.device) if need_bias else None
+    xd, dd = desc(x, x_img), desc(dz, dz_img)
+    impl = L.IMPL_SIMT if cfg.conv_impl == "simt" else L.IMPL_AUTO
+    nbytes = L.cdll.srk_conv_wgrad_workspace_bytes(xd, dd, r, s, impl)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=weight.device) if nbytes > 0 else None
+    n, _, h, w = geometry(x, x_img)
+    _timed(("conv_wgrad", cin, cout, r, 0, n, h, w, nbytes > 0),
+           lambda: L.call("srk_conv_wgrad", xd, dd, dw.data_ptr(), _ptr(db), r, s, impl, _ptr(ws), stream_ptr()))
+    return dw, db
+
+
+def act_bwd(dout, out, act, alpha, unshuffle, perm_tc=False):
+    """gradient of the pre-activation (conv-output geometry) from the saved post-activation tensor"""
+    n, c, h, w = geometry(out, False)
+    if unshuffle == 2:
+        dz = new_act(n, 4 * c, h // 2, w // 2, out.dtype, out.device)
+    else:
+        dz = torch.empty_like(out)
+    dalpha = torch.zeros((1,), dtype=torch.float32, device=out.device) if act == L.ACT_PRELU else None
+    L.call("srk_act_bwd", act_desc(dout), act_desc(out), act_desc(dz), act, _ptr(alpha), _ptr(dalpha),
+           unshuffle, 1 if perm_tc else 0, stream_ptr())
+    return dz, dalpha
+
+
+# ---- batch norm ------------------------------------------------------------------------------------
+def bn_forward(y, gamma, beta, running_mean, running_var, nbt, training, eps, momentum, alpha, residual):
+    """out = [PReLU](BN(y)) [+ residual]; returns (out, mean, invstd)."""
+    n, c, h, w = geometry(y, False)
+    dev = y.device
+    stats = torch.empty((2, c), dtype=torch.float32, device=dev)
+    mean, invstd = stats[0], stats[1]
+    st = stream_ptr()
+    if training or running_mean is None:
+        sums = torch.zeros((2, c), dtype=torch.float32, device=dev)
+        L.call("srk_bn_stats", act_desc(y), sums[0].data_ptr(), sums[1].data_ptr(), st)
+        upd = training and running_mean is not None
+        L.call("srk_bn_finalize", sums[0].data_ptr(), sums[1].data_ptr(), c, n * h * w, eps, momentum,
+               _ptr(running_mean) if upd else None, _ptr(running_var) if upd else None,
+               _ptr(nbt) if upd else None, mean.data_ptr(), invstd.data_ptr(), st)
+    else:
+        L.call("srk_bn_eval_params", running_mean.data_ptr(), running_var.data_ptr(), c, eps,
+               mean.data_ptr(), invstd.data_ptr(), st)
+    out = torch.empty_like(y)
+    L.call("srk_bn_apply", act_desc(y), mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+           _ptr(alpha), act_desc(residual) if residual is not None else None, act_desc(out), st)
+    return out, stats
+
+
+def bn_backward(dout, y, stats, gamma, beta, alpha, batch_stats):
+    """-> (dy, dgamma, dbeta, dalpha or None)"""
+    c = y.shape[3]
+    dev = y.device
+    red = torch.zeros((2 * c + 1,), dtype=torch.float32, device=dev)
+    dgamma, dbeta, dalpha = red[:c], red[c:2 * c], red[2 * c:]
+    mean, invstd = stats[0], stats[1]
+    st = stream_ptr()
+    L.call("srk_bn_bwd_reduce", act_desc(dout), act_desc(y), mean.data_ptr(), invstd.data_ptr(),
+           gamma.data_ptr(), beta.data_ptr(), _ptr(alpha), dgamma.data_ptr(), dbeta.data_ptr(),
+           dalpha.data_ptr() if alpha is not None else None, st)
+    dy = torch.empty_like(y)
+    L.call("srk_bn_bwd_apply", act_desc(dout), act_desc(y), mean.data_ptr(), invstd.data_ptr(),
+           gamma.data_ptr(), beta.data_ptr(), _ptr(alpha), dgamma.data_ptr(), dbeta.data_ptr(),
+           1 if batch_stats else 0, act_desc(dy), st)
+    return dy, dgamma, dbeta, (dalpha if alpha is not None else None)
+
+
+# ---- squeeze-excite --------------------------------------------------------------------------------
+def se_forward(x, r, w1, w2, scale):
+    """out = x + scale * r * sigmoid(relu(mean_hw(r) @ w1^T) @ w2^T); returns (out, pool, hidden, gate)."""
+    n, c, h, w = geometry(r, False)
+    cr = w1.shape[0]
+    dev = r.device
+    pool = torch.empty((n, c), dtype=torch.float32, device=dev)
+    hidden = torch.empty((n, cr), dtype=torch.float32, device=dev)
+    gate = torch.empty((n, c), dtype=torch.float32, device=dev)
+    st = stream_ptr()
+    L.call("srk_se_pool", act_desc(r), pool.data_ptr(), st)
+    L.call("srk_se_fc", pool.data_ptr(), w1.data_ptr(), w2.data_ptr(), n, c, cr, hidden.data_ptr(),
+           gate.data_ptr(), st)
+    out = torch.empty_like(r)
+    L.call("srk_se_apply", act_desc(x) if x is not None else None, act_desc(r), gate.data_ptr(), scale,
+           act_desc(out), st)
+    return out, pool, hidden, gate
+
+
+def se_backward(dout, r, pool, hidden, gate, w1, w2, scale):
+    """-> (dr, dw1, dw2)   (the skip path's gradient is dout itself)"""
+    n, c, h, w = geometry(r, False)
+    cr = w1.shape[0]
+    dev = r.device
+    st = stream_ptr()
+    dgate_raw = torch.zeros((n, c), dtype=torch.float32, device=dev)
+    L.call("srk_se_bwd_reduce", act_desc(dout), act_desc(r), dgate_raw.data_ptr(), st)
+    dw1 = torch.zeros_like(w1, memory_format=torch.contiguous_format)
+    dw2 = torch.zeros_like(w2, memory_format=torch.contiguous_format)
+    # dpool [n][c] followed by the kernel's scratch (dz2 [n][c], dh [n][cr])
+    dpool = torch.empty((2 * n * c + n * cr,), dtype=torch.float32, device=dev)
+    L.call("srk_se_fc_bwd", dgate_raw.data_ptr(), gate.data_ptr(), hidden.data_ptr(), pool.data_ptr(),
+           w1.data_ptr(), w2.data_ptr(), n, c, cr, scale, dw1.data_ptr(), dw2.data_ptr(), dpool.data_ptr(), st)
+    dr = torch.empty_like(r)
+    L.call("srk_se_bwd_apply", act_desc(dout), gate.data_ptr(), dpool.data_ptr(), scale, act_desc(dr), st)
+    return dr, dw1, dw2
+
+
+# ---- layout / misc ---------------------------------------------------------------------------------
+def image_to_act(img, dtype):
+    n, c, h, w = img.shape
+    a = new_act(n, c, h, w, dtype, img.device)
+    L.call("srk_image_to_act", img_desc(img), act_desc(a), stream_ptr())
+    return a
+
+
+def act_to_image(a):
+    n, c, h, w = geometry(a, False)
+    img = new_image(n, c, h, w, a.device)
+    L.call("srk_act_to_image", act_desc(a), img_desc(img), stream_ptr())
+    return img
+
+
+def act_add(a, b):
+    out = torch.empty_like(a)
+    L.call("srk_act_add", act_desc(a), act_desc(b), act_desc(out), stream_ptr())
+    return out
+
+
+def bicubic_upsample(img, oh, ow):
+    n, c, h, w = img.shape
+    out = new_image(n, c, oh, ow, img.device)
+    L.call("srk_bicubic_upsample", img_desc(img), img_desc(out), stream_ptr())
+    return out

@@ -1,0 +1,188 @@
+/*
+ * srk.h — C ABI of libsrk.so: the B200 (sm_100a) super-resolution hot-path kernels.
+ *
+ * The reference (Jaskieeeer/food101-super-resolution) has no FFI: its hot path is the set of
+ * ATen ops dispatched from src/models.py, src/loss.py and src/metrics.py.  Every entry point
+ * below replaces one such op family; the reference call sites are cited per function
+ * (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise;
+ *   - the caller owns every buffer, including workspaces (sizes via srk_*_workspace_bytes);
+ *   - `stream` is a cudaStream_t passed as void*; no entry point synchronises the host;
+ *   - return value 0 = ok; non-zero = error, message via srk_last_error() (thread local);
+ *   - re-entrant: may be called concurrently from the autograd thread and the main thread.
+ *
+ * Tensor layouts
+ *   SRK_LAYOUT_IMAGE : NCHW fp32, contiguous — what the reference modules take and return.
+ *   SRK_LAYOUT_ACT   : zero-bordered channels-last [N][H+2][W+2][C], dtype fp32 or bf16 — the
+ *                      internal activation layout.  The 1-pixel border is always zero so a 3x3
+ *                      tap is a constant offset in the flat pixel index.
+ */
+#ifndef SRK_H_
+#define SRK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRK_F32 0
+#define SRK_BF16 1
+
+#define SRK_LAYOUT_IMAGE 0
+#define SRK_LAYOUT_ACT 1
+
+#define SRK_ACT_NONE 0
+#define SRK_ACT_RELU 1
+#define SRK_ACT_PRELU 2
+
+#define SRK_IMPL_AUTO 0
+#define SRK_IMPL_SIMT 1 /* fp32-accurate CUDA-core implicit GEMM */
+#define SRK_IMPL_TC 2   /* tcgen05/TMEM/TMA implicit GEMM (bf16 in, fp32 accumulate) */
+
+/* weight pack kinds (srk_weight_pack) */
+#define SRK_PACK_FPROP_SIMT 0 /* fp32 [R][S][Cin][Cout] */
+#define SRK_PACK_DGRAD_SIMT 1 /* fp32 [R][S][Cout][Cin], taps rotated by 180 degrees */
+#define SRK_PACK_FPROP_TC 2   /* bf16 [R*S][Cout'][Cin]  (Cout' permuted when pixel_shuffle) */
+#define SRK_PACK_DGRAD_TC 3   /* bf16 [R*S rot180][Cin][Cout'] */
+
+typedef struct srk_tensor {
+  void* data;
+  int32_t layout; /* SRK_LAYOUT_* */
+  int32_t dtype;  /* SRK_F32 / SRK_BF16 (IMAGE is always fp32) */
+  int32_t n, c, h, w; /* logical (un-padded) sizes */
+} srk_tensor;
+
+const char* srk_last_error(void);
+int srk_version(void);
+/* 1 if the tcgen05 path can take this conv shape (used by the host to pick pack kinds). */
+int srk_conv_tc_supported(int cin, int cout, int r, int s, int dtype, int pixel_shuffle);
+
+/* ---- convolution family: F.conv2d / convolution_backward -------------------------------------
+ * replaces nn.Conv2d forward at models.py:46,49,65,67,84-86,107,113,117,120,125,150,156,159,162,167
+ * and its autograd backward (dgrad = fprop with SRK_PACK_DGRAD_* weights).
+ * Fused epilogue: +bias, ReLU (models.py:99-100) / single-alpha PReLU (models.py:108,119,122,151,161,164),
+ * +residual (models.py:185), PixelShuffle(2) store remap (models.py:118,121,160,163).
+ * stride 1, "same" padding (pad = R/2), as every conv on the path.
+ * `y` holds the output geometry; with pixel_shuffle=2, y is [N][Cout/4][2H][2W].
+ */
+int srk_conv_fprop(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int pack_kind,
+                   int cout, int r, int s, const float* bias, int act, const float* alpha,
+                   const srk_tensor* residual, int pixel_shuffle, int impl, void* stream);
+
+/* dW (fp32, OIHW, ACCUMULATED into dw: caller zero-fills) and db (fp32 [Cout], accumulated, may be NULL).
+ * x: conv input, dy: gradient w.r.t. the conv output (pre-activation, conv-output geometry).
+ * workspace: srk_conv_wgrad_workspace_bytes() bytes (may be NULL when that returns 0). */
+int srk_conv_wgrad(const srk_tensor* x, const srk_tensor* dy, float* dw, float* db, int r, int s,
+                   int impl, void* workspace, void* stream);
+int64_t srk_conv_wgrad_workspace_bytes(const srk_tensor* x, const srk_tensor* dy, int r, int s, int impl);
+
+/* OIHW fp32 master weights -> kernel operand layouts (see SRK_PACK_*). */
+int srk_weight_pack(const float* w_oihw, void* out, int cout, int cin, int r, int s, int kind,
+                    int pixel_shuffle, void* stream);
+int64_t srk_weight_pack_bytes(int cout, int cin, int r, int s, int kind);
+
+/* ---- activation backward: _prelu_kernel_backward / threshold_backward (+ pixel_unshuffle) ----
+ * out: saved post-activation tensor; dout: its gradient; dz: gradient of the pre-activation in
+ * conv-output geometry ([N][4C][H/2][W/2] when pixel_unshuffle=2; channel order matches `perm_tc`:
+ * 0 = reference order co=4c+2i+j, 1 = sub-pixel-major co'=(2i+j)*C+c used by the TC conv path).
+ * dalpha (fp32[1], accumulated) only for PReLU.  PReLU backward reconstructs the pre-activation
+ * from `out`, exact for alpha > 0 (reference init 0.25, models.py:48). */
+int srk_act_bwd(const srk_tensor* dout, const srk_tensor* out, const srk_tensor* dz, int act,
+                const float* alpha, float* dalpha, int pixel_unshuffle, int perm_tc, void* stream);
+
+/* ---- BatchNorm2d (models.py:47,50,56-57,114,140): native_batch_norm / _backward ----------------*/
+/* per-channel sum and sum of squares over interior pixels (fp32[C] each, accumulated) */
+int srk_bn_stats(const srk_tensor* y, float* sum, float* sumsq, void* stream);
+/* training: batch mean / invstd from (sum,sumsq); updates running stats (momentum, unbiased var)
+ * and num_batches_tracked (int64) when those pointers are non-NULL. */
+int srk_bn_finalize(const float* sum, const float* sumsq, int c, int64_t count, float eps,
+                    float momentum, float* running_mean, float* running_var,
+                    int64_t* num_batches_tracked, float* mean, float* invstd, void* stream);
+/* eval: mean = running_mean, invstd = rsqrt(running_var + eps) */
+int srk_bn_eval_params(const float* running_mean, const float* running_var, int c, float eps,
+                       float* mean, float* invstd, void* stream);
+/* out = [PReLU_alpha](gamma*(y-mean)*invstd+beta) [+ residual]   (alpha/residual may be NULL) */
+int srk_bn_apply(const srk_tensor* y, const float* mean, const float* invstd, const float* gamma,
+                 const float* beta, const float* alpha, const srk_tensor* residual,
+                 const srk_tensor* out, void* stream);
+/* backward pass 1: dgamma[C], dbeta[C], dalpha[1] (all fp32, accumulated) */
+int srk_bn_bwd_reduce(const srk_tensor* dout, const srk_tensor* y, const float* mean,
+                      const float* invstd, const float* gamma, const float* beta,
+                      const float* alpha, float* dgamma, float* dbeta, float* dalpha, void* stream);
+/* backward pass 2: dy.  dgamma_b/dbeta_b are THIS batch's reductions (pass-1 outputs into zeroed
+ * buffers); batch_stats=0 gives the eval-mode backward (dy = gamma*invstd*g). */
+int srk_bn_bwd_apply(const srk_tensor* dout, const srk_tensor* y, const float* mean,
+                     const float* invstd, const float* gamma, const float* beta, const float* alpha,
+                     const float* dgamma_b, const float* dbeta_b, int batch_stats,
+                     const srk_tensor* dy, void* stream);
+
+/* ---- squeeze-excite gate (models.py:26-41,76-78): mean / mm / sigmoid / mul / add ------------- */
+/* pool[N][C] = mean over H,W of r */
+int srk_se_pool(const srk_tensor* r, float* pool, void* stream);
+/* hidden[N][Cr] = relu(pool @ w1^T), gate[N][C] = sigmoid(hidden @ w2^T); w1 [Cr][C], w2 [C][Cr] */
+int srk_se_fc(const float* pool, const float* w1, const float* w2, int n, int c, int cr,
+              float* hidden, float* gate, void* stream);
+/* out = (x ? x : 0) + scale * r * gate[n][c] */
+int srk_se_apply(const srk_tensor* x, const srk_tensor* r, const float* gate, float scale,
+                 const srk_tensor* out, void* stream);
+/* dgate_raw[N][C] = sum_hw dout * r   (accumulated) */
+int srk_se_bwd_reduce(const srk_tensor* dout, const srk_tensor* r, float* dgate_raw, void* stream);
+/* tiny FC backward: dw1 [Cr][C], dw2 [C][Cr] (accumulated), dpool [N][C] (overwritten) */
+int srk_se_fc_bwd(const float* dgate_raw, const float* gate, const float* hidden, const float* pool,
+                  const float* w1, const float* w2, int n, int c, int cr, float scale, float* dw1,
+                  float* dw2, float* dpool, void* stream);
+/* dr = scale * gate * dout + dpool / (H*W) */
+int srk_se_bwd_apply(const srk_tensor* dout, const float* gate, const float* dpool, float scale,
+                     const srk_tensor* dr, void* stream);
+
+/* ---- layout / elementwise helpers --------------------------------------------------------------*/
+int srk_image_to_act(const srk_tensor* img, const srk_tensor* act, void* stream);
+int srk_act_to_image(const srk_tensor* act, const srk_tensor* img, void* stream);
+/* out = a + b on ACT tensors (residual sums models.py:60,141) ; out may alias a */
+int srk_act_add(const srk_tensor* a, const srk_tensor* b, const srk_tensor* out, void* stream);
+/* F.interpolate(mode='bicubic', align_corners=False) models.py:98 (A=-0.75, clamped taps) */
+int srk_bicubic_upsample(const srk_tensor* in, const srk_tensor* out, void* stream);
+
+/* ---- losses (loss.py:81-86 nn.L1Loss / nn.MSELoss; loss.py:31-79 NLPDLoss) --------------------- */
+/* mode 0 = L1, 1 = MSE.  loss[1] fp32 overwritten. */
+int srk_pixel_loss_fwd(const float* sr, const float* hr, int64_t numel, int mode, float* loss,
+                       double* scratch, void* stream);
+/* grad_sr = gout[0] * dLoss/dsr */
+int srk_pixel_loss_bwd(const float* sr, const float* hr, int64_t numel, int mode, const float* gout,
+                       float* grad_sr, void* stream);
+int64_t srk_nlpd_workspace_bytes(int n, int c, int h, int w, int levels);
+/* loss = alpha*L1 + (1-alpha)*sum_l mean|Lap_l(sr)-Lap_l(hr)|; kernel25 = the 5x5 blur taps (device).
+ * clamp01 != 0 clamps both inputs to [0,1] first (metrics.py:16-17; forward only).
+ * The workspace keeps the pyramid for the backward. */
+int srk_nlpd_fwd(const float* sr, const float* hr, int n, int c, int h, int w, int levels,
+                 float alpha, const float* kernel25, int clamp01, void* workspace, float* loss,
+                 void* stream);
+int srk_nlpd_bwd(int n, int c, int h, int w, int levels, float alpha, const float* kernel25,
+                 void* workspace, const float* gout, float* grad_sr, void* stream);
+
+/* ---- metrics (metrics.py:14-31 via torchmetrics 1.8.2 PSNR / SSIM) ----------------------------- */
+/* per-image sum of squared error of clamp(sr,0,1) vs clamp(hr,0,1) (clamp01 != 0): sse[N] double */
+int srk_psnr_sse(const float* sr, const float* hr, int n, int64_t per_image, int clamp01,
+                 double* sse, void* stream);
+/* per-image SSIM sums over the (H-10)x(W-10) valid windows x C: ssim_sum[N] double (overwritten) */
+int srk_ssim(const float* sr, const float* hr, int n, int c, int h, int w, int clamp01,
+             double* ssim_sum, void* stream);
+
+/* ---- optimizer (train.py:55,120 optim.Adam(betas=(0.5,0.999))) --------------------------------- */
+/* single flat fp32 buffer Adam step (torch.optim.Adam semantics, no amsgrad/weight decay);
+ * step_count is the 1-based step number held on the device (int64[1]) so the call is graph-safe. */
+int srk_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel,
+                  float lr, float beta1, float beta2, float eps, const int64_t* step_count,
+                  float grad_scale, void* stream);
+
+/* ---- bring-up / self-test hooks (tests only) --------------------------------------------------- */
+/* Runs the tcgen05 descriptor probe (see csrc/srk_probe.cu); results into out[] (host memory). */
+int srk_tc_probe(int variant, float* out_host, int out_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRK_H_ */

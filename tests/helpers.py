@@ -1,0 +1,32 @@
+"""Shared helpers for the parity tests (test infrastructure)."""
+import os
+
+import numpy as np
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return {k: z[k] for k in z.files}
+
+
+def golden_state_dict(fix, prefix="sd/"):
+    sd = {}
+    for k, v in fix.items():
+        if k.startswith(prefix):
+            t = torch.from_numpy(np.array(v))
+            sd[k[len(prefix):]] = t
+    return sd
+
+
+def rel_err(a, b):
+    """max |a-b| / max(|b|) - the 'relative' tolerance of BASELINE.json's north_star."""
+    a, b = a.double().flatten(), b.double().flatten()
+    denom = b.abs().max().item()
+    return (a - b).abs().max().item() / (denom if denom > 0 else 1.0)
+
+
+def max_abs(a, b):
+    return (a.double() - b.double()).abs().max().item()

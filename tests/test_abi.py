@@ -1,0 +1,99 @@
+"""CPU-side checks of the drop-in boundary: libsrk.so loads and exports every symbol include/srk.h
+declares, the ctypes table mirrors the header, the nn.Modules keep the reference's state_dict layout,
+and nothing silently runs on the CPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "srk.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(srk_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from srk import _lib
+    syms = _header_symbols()
+    assert len(syms) >= 30
+    lib = ctypes.CDLL(os.path.abspath(_lib.LIB_PATH))
+    for s in syms:
+        assert hasattr(lib, s), "libsrk.so does not export %s" % s
+    assert sorted(_lib.SIGNATURES) == syms, "ctypes table and include/srk.h disagree"
+    assert _lib.cdll.srk_version() >= 100
+
+
+def test_ctypes_arity_matches_header():
+    from srk import _lib
+    text = open(os.path.join(ROOT, "include", "srk.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    for name, args in re.findall(r"\b(srk_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+        args = args.strip()
+        n = 0 if args in ("", "void") else args.count(",") + 1
+        assert len(_lib.SIGNATURES[name][1]) == n, name
+
+
+@pytest.mark.parametrize("arch", ["SRCNN", "RESNET", "AttentionSR"])
+def test_state_dict_layout_and_seeded_init_match_reference(arch):
+    from src.models import get_model
+    fix = load_golden("state_dicts")
+    torch.manual_seed(0)
+    sd = get_model(arch, scale_factor=4).state_dict()
+    assert list(sd.keys()) == [str(k) for k in fix[arch + "/keys"]]
+    assert [str(tuple(v.shape)) for v in sd.values()] == [str(s) for s in fix[arch + "/shapes"]]
+    assert [str(v.dtype) for v in sd.values()] == [str(s) for s in fix[arch + "/dtypes"]]
+    # same RNG consumption as the reference constructors -> identical seeded weights
+    got = np.array([float(v.double().sum()) for v in sd.values()])
+    np.testing.assert_allclose(got, fix[arch + "/checksum"], rtol=0, atol=1e-9)
+
+
+def test_get_model_and_loss_factory_errors():
+    from src.loss import get_loss_function
+    from src.models import get_model
+    with pytest.raises(ValueError, match="Unknown architecture"):
+        get_model("VDSR")
+    with pytest.raises(ValueError, match="Unknown loss function"):
+        get_loss_function("huber", "cpu")
+    assert get_loss_function("NLPD", "cpu").kernel.shape == (3, 1, 5, 5)
+    assert "kernel" in get_loss_function("nlpd", "cpu").state_dict()
+
+
+def test_cpu_tensors_are_rejected_not_silently_computed():
+    from src.loss import get_loss_function
+    from src.metrics import MetricsCalculator
+    from src.models import get_model
+    x = torch.rand(1, 3, 8, 8)
+    for arch in ("SRCNN", "RESNET"):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            get_model(arch)(x)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        get_loss_function("mae", "cpu")(x, x)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        get_loss_function("nlpd", "cpu")(x, x)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        MetricsCalculator("cpu").compute(torch.rand(1, 3, 16, 16), torch.rand(1, 3, 16, 16))
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    import subprocess
+    import sys
+    env = dict(os.environ, SRK_LIB=str(tmp_path / "nope.so"), PYTHONPATH=os.path.join(ROOT, "food101-super-resolution_b200"))
+    r = subprocess.run([sys.executable, "-c", "import srk"], env=env, capture_output=True, text=True)
+    assert r.returncode != 0 and "libsrk.so not found" in r.stderr
+
+
+def test_product_code_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "food101-super-resolution_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "sr_oracle" not in src and "import oracle" not in src and "from oracle" not in src, f

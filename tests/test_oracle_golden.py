@@ -1,0 +1,96 @@
+"""Pins oracle/sr_oracle.py (the CPU restatement) against fixtures produced by the reference modules
+themselves (oracle/make_golden.py).  CPU only."""
+import math
+
+import pytest
+import torch
+
+from helpers import golden_state_dict, load_golden, max_abs, rel_err
+from oracle import sr_oracle as O
+
+CASES = [("srcnn_x2", 1e-5), ("resnet_c32_b2", 1e-4), ("attn_c32_b2", 1e-5)]
+
+
+@pytest.mark.parametrize("name,tol", CASES)
+def test_model_forward_backward_matches_reference(name, tol):
+    fix = load_golden(name)
+    arch, loss_name, scale = [str(x) for x in fix["meta"]]
+    sd = golden_state_dict(fix)
+    lr, hr = torch.from_numpy(fix["lr"]), torch.from_numpy(fix["hr"])
+    out, loss, grads, work = O.train_step_grads(arch, sd, lr, hr, loss_name, scale_factor=int(scale))
+    assert max_abs(out, torch.from_numpy(fix["out_train"])) <= tol
+    assert abs(loss.item() - float(fix["loss"])) <= 1e-5
+    n_checked = 0
+    for k, v in fix.items():
+        if k.startswith("grad/"):
+            assert rel_err(grads[k[5:]], torch.from_numpy(v)) <= 1e-3, k
+            n_checked += 1
+    assert n_checked == len(grads)
+    for k, v in fix.items():
+        if k.startswith("after/"):
+            assert max_abs(work[k[6:]].detach(), torch.from_numpy(v)) <= 1e-5, k
+    with torch.no_grad():
+        out_eval = O.model_forward(arch, sd, lr, training=False, scale_factor=int(scale))
+    assert max_abs(out_eval, torch.from_numpy(fix["out_eval"])) <= tol
+
+
+@pytest.mark.parametrize("tag", ["even", "odd", "native"])
+@pytest.mark.parametrize("lname", ["mae", "mse", "nlpd"])
+def test_losses_match_reference(tag, lname):
+    fix = load_golden("losses")
+    sr = torch.from_numpy(fix[tag + "/sr"]).requires_grad_(True)
+    hr = torch.from_numpy(fix[tag + "/hr"])
+    loss = O.loss_fn(lname)(sr, hr)
+    loss.backward()
+    assert abs(loss.item() - float(fix["%s/%s/loss" % (tag, lname)])) <= 1e-6
+    if tag != "native":
+        assert max_abs(sr.grad, torch.from_numpy(fix["%s/%s/grad" % (tag, lname)])) <= 1e-8
+    else:
+        assert abs(sr.grad.abs().sum().item() - float(fix["%s/%s/grad_sum_abs" % (tag, lname)])) <= 1e-4
+
+
+def test_gaussian_kernel_matches_reference_buffer():
+    fix = load_golden("losses")
+    assert max_abs(O.gaussian_kernel_5x5(3), torch.from_numpy(fix["kernel"])) <= 1e-8
+
+
+# ---- metrics: torchmetrics restatement, analytic known answers (parity unpinned) ----------
+def test_psnr_known_answers():
+    x = torch.rand(2, 3, 16, 16) * 0.8
+    assert abs(O.psnr(x, x + 0.1) - 20.0) < 1e-5
+    assert O.psnr(x, x) == float("inf")
+
+
+def test_ssim_known_answers():
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(2, 3, 24, 20, generator=g)
+    assert abs(O.ssim(x, x) - 1.0) < 1e-12
+    a, b = torch.full((1, 3, 16, 16), 0.5), torch.full((1, 3, 16, 16), 0.6)
+    expect = (2 * 0.5 * 0.6 + 1e-4) / (0.25 + 0.36 + 1e-4)
+    assert abs(O.ssim(a, b) - expect) < 1e-6
+    assert abs(expect - 0.983609) < 1e-6
+
+
+def test_ssim_equals_valid_window_mean():
+    """The reflect padding is cropped away again: SSIM == mean over the (H-10)x(W-10) valid windows."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(4)
+    p, t = torch.rand(1, 1, 20, 22, generator=g).double(), torch.rand(1, 1, 20, 22, generator=g).double()
+    d = torch.arange(-5, 6, dtype=torch.float64)
+    k = torch.exp(-((d / 1.5) ** 2) / 2)
+    k = (k / k.sum())
+    k2 = (k[:, None] * k[None, :]).view(1, 1, 11, 11)
+    mu_p, mu_t = F.conv2d(p, k2), F.conv2d(t, k2)
+    s_pp = (F.conv2d(p * p, k2) - mu_p ** 2).clamp(min=0)
+    s_tt = (F.conv2d(t * t, k2) - mu_t ** 2).clamp(min=0)
+    s_pt = F.conv2d(p * t, k2) - mu_p * mu_t
+    m = ((2 * mu_p * mu_t + 1e-4) * (2 * s_pt + 9e-4)) / ((mu_p ** 2 + mu_t ** 2 + 1e-4) * (s_pp + s_tt + 9e-4))
+    assert abs(m.mean().item() - O.ssim(p, t)) < 1e-12
+
+
+def test_metrics_compute_clamps_first():
+    x = torch.full((1, 3, 16, 16), 1.5)
+    y = torch.full((1, 3, 16, 16), 1.0)
+    m = O.metrics_compute(x, y)
+    assert m["psnr"] == float("inf") and abs(m["ssim"] - 1.0) < 1e-9 and m["nlpd"] == 0.0
+    assert math.isfinite(O.metrics_compute(x * 0.3, y * 0.5)["psnr"])
