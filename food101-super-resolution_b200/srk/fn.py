@@ -65,7 +65,7 @@ class ConvAct(torch.autograd.Function):
         act, shuffle, x_img, out_img, has_bias, has_res, used_tc = ctx.cfg
         dout = dout.contiguous()
         dalpha = None
-        perm = bool(used_tc and shuffle == 2)
+        perm = False  # the tcgen05 path keeps the reference channel order
         if act != L.ACT_NONE or shuffle == 2:
             dz, dalpha = ops.act_bwd(dout, y if y is not None else dout, act, alpha, shuffle, perm)
             dz_img = False

@@ -191,7 +191,7 @@ def conv_fprop(x, x_img, weight, bias, act, alpha, residual, shuffle, out_img, o
     use_tc = (not x_img) and (not out_img) and tc_supported(cin, cout, r, s, x.dtype, shuffle) \
         and out_dtype == torch.bfloat16
     kind = L.PACK_FPROP_TC if use_tc else L.PACK_FPROP_SIMT
-    pk = packed_weight(weight, kind, shuffle if use_tc else 0)
+    pk = packed_weight(weight, kind, 0)
     if shuffle == 2:
         oc, oh, ow = cout // 4, 2 * h, 2 * w
     else:
@@ -214,7 +214,7 @@ def conv_dgrad(dz, dz_img, weight, residual, out_dtype, perm_tc=False):
     if perm_tc and not use_tc:
         raise RuntimeError("conv_dgrad: permuted dz requires the tcgen05 path")
     kind = L.PACK_DGRAD_TC if use_tc else L.PACK_DGRAD_SIMT
-    pk = packed_weight(weight, kind, 2 if perm_tc else 0)
+    pk = packed_weight(weight, kind, 0)
     dx = new_act(n, cin, h, w, out_dtype, dz.device)
     rd = act_desc(residual) if residual is not None else None
     _timed(("conv_dgrad", cout, cin, r, 0, n, h, w, use_tc),

@@ -57,7 +57,7 @@ def test_fp32_train_step_matches_reference_golden(name):
     for k, p in model.named_parameters():
         assert p.grad is not None, k
         assert p.grad.shape == p.shape and p.grad.dtype == torch.float32
-        assert rel_err(p.grad.cpu(), torch.from_numpy(fix["grad/" + k])) <= 1e-3, k
+        assert rel_err(p.grad.cpu(), torch.from_numpy(fix["grad/" + k]), floor=1e-4) <= 1e-3, k
     for k, v in model.state_dict().items():
         if ("after/" + k) in fix:
             assert max_abs(v.cpu(), torch.from_numpy(fix["after/" + k])) <= 1e-5, k
@@ -82,8 +82,8 @@ def test_bf16_train_step_within_tolerance(name):
     loss = get_loss_function(loss_name, DEV)(out, hr)
     loss.backward()
     assert rel_err(out.cpu(), torch.from_numpy(fix["out_train"])) <= 1e-2
-    worst = max(rel_err(p.grad.cpu(), torch.from_numpy(fix["grad/" + k])) for k, p in model.named_parameters()
-                if p.numel() > 1)
+    worst = max(rel_err(p.grad.cpu(), torch.from_numpy(fix["grad/" + k]), floor=1e-4)
+                for k, p in model.named_parameters() if p.numel() > 1)
     assert worst <= 5e-2, worst  # whole-network bf16 chain; single layers are held to 1e-2 below
 
 
