@@ -26,6 +26,9 @@ bool conv_tc_shape_ok(int cin, int cout, int r, int s, int dtype, int shuffle);
 int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout,
                          int r, int s, const float* bias, int act, const float* alpha,
                          const srk_tensor* residual, int shuffle, cudaStream_t st);
+bool conv_smalln_tc_ok(const srk_tensor* x, const srk_tensor* y, int cout, int r, int s);
+int conv_smalln_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout, int r,
+                          const float* bias, cudaStream_t st);
 bool conv_wgrad_tc_shape_ok(const srk_tensor* x, const srk_tensor* dy, int r, int s);
 int64_t conv_wgrad_tc_workspace(const srk_tensor* x, const srk_tensor* dy, int r, int s);
 int conv_wgrad_tc_launch(const srk_tensor* x, const srk_tensor* dy, float* dw, float* db, int r, int s,
@@ -47,6 +50,8 @@ extern "C" const char* srk_last_error(void) { return g_err; }
 extern "C" int srk_version(void) { return 100; }
 
 extern "C" int srk_conv_tc_supported(int cin, int cout, int r, int s, int dtype, int pixel_shuffle) {
+  /* 2 = the RGB-output variant (bf16 ACT in, IMAGE out, SRK_PACK_FPROP_TC_N8 weights) */
+  if (dtype == SRK_BF16 && cin == 64 && cout <= 4 && r == s && (r == 5 || r == 9) && pixel_shuffle == 0) return 2;
   return conv_tc_shape_ok(cin, cout, r, s, dtype, pixel_shuffle) ? 1 : 0;
 }
 
@@ -70,6 +75,12 @@ extern "C" int srk_conv_fprop(const srk_tensor* x, const srk_tensor* y, const vo
   if (residual) {
     SRK_REQUIRE(tensor_ok(residual) && same_geometry(residual, y) && residual->layout == y->layout,
                 "srk_conv_fprop: residual must match the output geometry and layout");
+  }
+  if (pack_kind == SRK_PACK_FPROP_TC_N8) {
+    SRK_REQUIRE(conv_smalln_tc_ok(x, y, cout, r, s) && act == SRK_ACT_NONE && residual == nullptr && pixel_shuffle == 0,
+                "srk_conv_fprop: the RGB-output tcgen05 path takes bf16 ACT input with 64 channels, an IMAGE "
+                "output with <= 4 channels and no activation / residual");
+    return conv_smalln_tc_launch(x, y, w_packed, cout, r, bias, (cudaStream_t)stream);
   }
   const bool tc_kind = pack_kind == SRK_PACK_FPROP_TC || pack_kind == SRK_PACK_DGRAD_TC;
   const bool simt_kind = pack_kind == SRK_PACK_FPROP_SIMT || pack_kind == SRK_PACK_DGRAD_SIMT;

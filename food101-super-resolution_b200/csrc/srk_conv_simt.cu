@@ -317,10 +317,17 @@ int conv_wgrad_simt_launch(const srk_tensor* x, const srk_tensor* dy, float* dw,
 __global__ void pack_weights_kernel(const float* __restrict__ w, void* __restrict__ out, int Cout,
                                     int Cin, int R, int S, int kind, int shuffle) {
   long long total = (long long)Cout * Cin * R * S;
+  if (kind == SRK_PACK_FPROP_TC_N8) total = (long long)8 * Cin * R * S;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     // i indexes the OUTPUT linearly
-    if (kind == SRK_PACK_FPROP_SIMT) {  // [R][S][Cin][Cout]
+    if (kind == SRK_PACK_FPROP_TC_N8) {  // bf16 [tap][8][Cin]
+      int ci = (int)(i % Cin); long long t = i / Cin;
+      int co = (int)(t % 8); int tap = (int)(t / 8);
+      int r = tap / S, s = tap - r * S;
+      float v = co < Cout ? w[(((long long)co * Cin + ci) * R + r) * S + s] : 0.f;
+      ((__nv_bfloat16*)out)[i] = __float2bfloat16_rn(v);
+    } else if (kind == SRK_PACK_FPROP_SIMT) {  // [R][S][Cin][Cout]
       int co = (int)(i % Cout); long long t = i / Cout;
       int ci = (int)(t % Cin); t /= Cin;
       int s = (int)(t % S); int r = (int)(t / S);
@@ -355,16 +362,20 @@ using namespace srk;
 
 extern "C" int64_t srk_weight_pack_bytes(int cout, int cin, int r, int s, int kind) {
   int64_t n = (int64_t)cout * cin * r * s;
+  if (kind == SRK_PACK_FPROP_TC_N8) return (int64_t)8 * cin * r * s * 2 + 8 * 128;
   return (kind == SRK_PACK_FPROP_SIMT || kind == SRK_PACK_DGRAD_SIMT) ? n * 4 : n * 2;
 }
 
 extern "C" int srk_weight_pack(const float* w_oihw, void* out, int cout, int cin, int r, int s,
                                int kind, int pixel_shuffle, void* stream) {
-  SRK_REQUIRE(kind >= 0 && kind <= 3, "srk_weight_pack: bad kind %d", kind);
+  SRK_REQUIRE(kind >= 0 && kind <= 4, "srk_weight_pack: bad kind %d", kind);
+  SRK_REQUIRE(kind != SRK_PACK_FPROP_TC_N8 || cout <= 8, "srk_weight_pack: N8 pack needs Cout <= 8");
   SRK_REQUIRE(pixel_shuffle == 0 || (pixel_shuffle == 2 && cout % 4 == 0), "srk_weight_pack: bad pixel_shuffle");
-  long long total = (long long)cout * cin * r * s;
+  long long total = (long long)(kind == SRK_PACK_FPROP_TC_N8 ? 8 : cout) * cin * r * s;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
+  if (kind == SRK_PACK_FPROP_TC_N8)  // zero the slack tap read by the last N=16 MMA
+    cudaMemsetAsync((char*)out + total * 2, 0, 8 * 128, (cudaStream_t)stream);
   pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, out, cout, cin, r, s, kind, pixel_shuffle);
   SRK_CUDA_LAUNCH_CHECK("pack_weights");
   return 0;

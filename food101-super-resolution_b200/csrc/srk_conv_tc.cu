@@ -426,12 +426,6 @@ int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w
   return 0;
 }
 
-bool conv_wgrad_tc_shape_ok(const srk_tensor*, const srk_tensor*, int, int) { return false; }
-int64_t conv_wgrad_tc_workspace(const srk_tensor*, const srk_tensor*, int, int) { return 0; }
-int conv_wgrad_tc_launch(const srk_tensor*, const srk_tensor*, float*, float*, int, int, void*, cudaStream_t) {
-  SRK_FAIL("tcgen05 wgrad path not built");
-}
-
 }  // namespace srk
 
 // Test / bring-up hook: variant 0..2 selects the A-staging mode of the tcgen05 conv (see the header

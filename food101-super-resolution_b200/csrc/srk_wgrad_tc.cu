@@ -1,0 +1,258 @@
+// tcgen05 weight-gradient of the 3x3 convolutions on the zero-bordered channels-last bf16 layout.
+//
+//   dW[tap][ci][co] = sum_p  X[p + d(tap)][ci] * dZ[p][co]        (reference: convolution_backward of
+//   models.py:46,49,65,67,113,117,120; p over all padded pixels - dZ is zero on the border)
+//
+// GEMM view per 16-pixel K step: D[(tap pair, ci) = 128][co = 64] += A^T B with BOTH operands "MN-major"
+// (pixels are the contraction dimension and the slow axis of the NHWC tiles TMA delivers):
+//   A = halo slab of X  [pixels][64 ci], SWIZZLE_128B; the two 64-row halves of M are two taps of the same
+//       slab, separated by the descriptor's leading-byte-offset (d(t2) - d(t1)) * 128 B
+//   B = dZ tile         [128 pixels][64 co], SWIZZLE_128B
+// Five accumulators (tap pairs (0,1)(2,3)(4,5)(6,7)(8,-)) live in TMEM for the CTA's whole pixel range
+// (split-K over persistent CTAs); they are flushed once with vector fp32 reductions into a
+// [9][64 ci][64 co] workspace, which a small kernel folds into the OIHW fp32 gradient.  The bias gradient
+// (column sums of dZ) is accumulated from the staged dZ tiles by the otherwise idle epilogue warps.
+#include "srk_common.cuh"
+#include "srk_tc_common.cuh"
+
+namespace srk {
+
+using namespace tc;
+
+int* tc_err_flag();
+
+constexpr int TM = 128, KC = 64, NT = 64, TAPS = 9, NACC = 5;
+constexpr int SLAB_BOX_ROWS = 32;
+constexpr int DZ_TILE_BYTES = TM * NT * 2;
+constexpr int kThreads = 192;
+constexpr int MAX_STAGES = 6;
+
+struct WgradTcParams {
+  int P, Wp, num_tiles;
+  int x_col0, dz_col0;     // channel offsets of this (ci chunk, co chunk) pass
+  int slab_rows, stages, stage_bytes;
+  float* ws;               // [9][64][64] fp32, zero-filled by the caller
+  float* db;               // [64] slice of the bias gradient (accumulated) or null
+  int* err;
+};
+
+struct __align__(8) WgradBarriers {
+  uint64_t full[MAX_STAGES], empty[MAX_STAGES], done;
+  uint32_t tmem_base;
+  float red[16][NT];
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDz,
+                   const WgradTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  WgradBarriers* bars = reinterpret_cast<WgradBarriers*>(smem_al + p.stages * p.stage_bytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.stages;
+  const int slab_bytes = p.slab_rows * KC * 2;   // dZ tile sits behind the slab inside a stage
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(smem_u32(&bars->full[i]), 1);
+      mbar_init(smem_u32(&bars->empty[i]), p.db ? 5 : 1);
+    }
+    mbar_init(smem_u32(&bars->done), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&bars->tmem_base), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  const int my_tiles = blockIdx.x < p.num_tiles ? (p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      prefetch_tmap(&tmX);
+      prefetch_tmap(&tmDz);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int m0 = (blockIdx.x + i * gridDim.x) * TM;
+        if (!mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1, p.err, 11)) break;
+        const uint32_t fb = smem_u32(&bars->full[s]);
+        const uint32_t st0 = smem_base + s * p.stage_bytes;
+        mbar_arrive_expect_tx(fb, slab_bytes + DZ_TILE_BYTES);
+        const int row0 = m0 - p.Wp - 1;
+        for (int j = 0; j < p.slab_rows / SLAB_BOX_ROWS; ++j)
+          tma_load_2d(st0 + j * SLAB_BOX_ROWS * KC * 2, &tmX, fb, p.x_col0, row0 + j * SLAB_BOX_ROWS);
+        tma_load_2d(st0 + slab_bytes, &tmDz, fb, p.dz_col0, m0);
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, NT, 1, 1);
+      int s = 0;
+      uint32_t ph = 0;
+      bool ok = true;
+      for (int i = 0; i < my_tiles && ok; ++i) {
+        ok = mbar_wait(smem_u32(&bars->full[s]), ph, p.err, 12);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t slab = smem_base + s * p.stage_bytes, dz = slab + slab_bytes;
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) {
+          const int t1 = 2 * a, t2 = a == NACC - 1 ? 2 * a : 2 * a + 1;
+          const int d1 = (t1 / 3) * p.Wp + t1 % 3, d2 = (t2 / 3) * p.Wp + t2 % 3;
+          const uint32_t lbo = (uint32_t)(d2 - d1) * (KC * 2);
+#pragma unroll
+          for (int ks = 0; ks < TM / 16; ++ks) {
+            const uint64_t adesc = make_smem_desc(slab + (d1 + ks * 16) * (KC * 2), lbo, 1024, kLayoutSW128, 0);
+            const uint64_t bdesc = make_smem_desc(dz + ks * 16 * (NT * 2), 0, 1024, kLayoutSW128, 0);
+            umma_bf16(tmem_base + a * NT, adesc, bdesc, idesc, (i | ks) != 0);
+          }
+        }
+        umma_commit(smem_u32(&bars->empty[s]));
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+      umma_commit(smem_u32(&bars->done));
+    }
+    __syncwarp();
+  } else {
+    // ---- epilogue warps: bias-gradient partial sums while the MMAs run, then the accumulator flush ----
+    const int et = threadIdx.x - 64;          // 0..127
+    if (p.db) {
+      const int c8 = et & 7, r0 = et >> 3;    // 16-byte channel chunk, first row
+      float acc[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        if (!mbar_wait(smem_u32(&bars->full[s]), ph, p.err, 13)) break;
+        const uint8_t* dz = smem_al + s * p.stage_bytes + slab_bytes;
+#pragma unroll
+        for (int rr = 0; rr < TM / 16; ++rr) {
+          const int r = r0 + rr * 16;
+          const uint4 q = *reinterpret_cast<const uint4*>(dz + r * 128 + ((c8 ^ (r & 7)) << 4));
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { float2 t = __bfloat1622float2(h[e]); acc[2 * e] += t.x; acc[2 * e + 1] += t.y; }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->empty[s]));
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) bars->red[r0][c8 * 8 + e] = acc[e];
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et < NT) {
+        float t = 0.f;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) t += bars->red[r][et];
+        atomicAdd(&p.db[et], t);
+      }
+    }
+    if (my_tiles > 0 && mbar_wait(smem_u32(&bars->done), 0, p.err, 14)) {
+      tc_fence_after();
+      const int lg = warp & 3;
+      const int row = lg * 32 + lane;          // accumulator lane = (half, ci)
+      const int half = row >> 6, ci = row & 63;
+#pragma unroll 1
+      for (int a = 0; a < NACC; ++a) {
+        uint32_t v[NT];
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + a * NT;
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_32x32(taddr + 32, v + 32);
+        tmem_ld_wait();
+        if (a == NACC - 1 && half == 1) continue;
+        const int tap = 2 * a + half;
+        float* dst = p.ws + ((size_t)tap * KC + ci) * NT;
+#pragma unroll
+        for (int j = 0; j < NT / 4; ++j)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j),
+                       "f"(__uint_as_float(v[4 * j])), "f"(__uint_as_float(v[4 * j + 1])),
+                       "f"(__uint_as_float(v[4 * j + 2])), "f"(__uint_as_float(v[4 * j + 3]))
+                       : "memory");
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// dw[co0+co][ci0+ci][tap] += ws[tap][ci][co]
+__global__ void wgrad_fold_kernel(const float* __restrict__ ws, float* __restrict__ dw, int cin_total, int ci0,
+                                  int co0) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;  // over [co][ci][tap] of the 64x64 block
+  if (i >= NT * KC * TAPS) return;
+  int tap = i % TAPS, t = i / TAPS;
+  int ci = t % KC, co = t / KC;
+  dw[((size_t)(co0 + co) * cin_total + (ci0 + ci)) * TAPS + tap] += ws[((size_t)tap * KC + ci) * NT + co];
+}
+
+bool conv_wgrad_tc_shape_ok(const srk_tensor* x, const srk_tensor* dy, int r, int s) {
+  if (r != 3 || s != 3) return false;
+  if (x->layout != SRK_LAYOUT_ACT || dy->layout != SRK_LAYOUT_ACT) return false;
+  if (x->dtype != SRK_BF16 || dy->dtype != SRK_BF16) return false;
+  if (x->c % KC != 0 || dy->c % NT != 0) return false;
+  const int Wp = x->w + 2;
+  const int slab_rows = ((TM + 2 * Wp + 2) + SLAB_BOX_ROWS - 1) / SLAB_BOX_ROWS * SLAB_BOX_ROWS;
+  return 2 * (slab_rows * KC * 2 + DZ_TILE_BYTES) + 4096 <= 227 * 1024;
+}
+
+int64_t conv_wgrad_tc_workspace(const srk_tensor* x, const srk_tensor* dy, int, int) {
+  return (int64_t)(x->c / KC) * (dy->c / NT) * TAPS * KC * NT * sizeof(float);
+}
+
+int conv_wgrad_tc_launch(const srk_tensor* x, const srk_tensor* dy, float* dw, float* db, int r, int s,
+                         void* workspace, cudaStream_t st) {
+  const int Hp = x->h + 2, Wp = x->w + 2;
+  const long long P = (long long)x->n * Hp * Wp;
+  SRK_REQUIRE(P < (1LL << 31) - 4096, "wgrad_tc: too many pixels");
+  static int smem_max = 0;
+  if (!smem_max) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaFuncSetAttribute(wgrad3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+  }
+  WgradTcParams p;
+  p.P = (int)P; p.Wp = Wp;
+  p.num_tiles = (int)((P + TM - 1) / TM);
+  p.slab_rows = ((TM + 2 * Wp + 2) + SLAB_BOX_ROWS - 1) / SLAB_BOX_ROWS * SLAB_BOX_ROWS;
+  p.stage_bytes = p.slab_rows * KC * 2 + DZ_TILE_BYTES;
+  const int fixed = 1024 + (int)sizeof(WgradBarriers);
+  p.stages = (smem_max - fixed) / p.stage_bytes;
+  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  SRK_REQUIRE(p.stages >= 2, "wgrad_tc: image too wide for the shared-memory slab");
+  p.err = tc_err_flag();
+  const int smem_bytes = fixed + p.stages * p.stage_bytes;
+  CUtensorMap tmX, tmDz;
+  if (make_tmap_2d_bf16(&tmX, x->data, (uint64_t)P, (uint64_t)x->c, (uint64_t)x->c, SLAB_BOX_ROWS, KC, 128)) return 1;
+  if (make_tmap_2d_bf16(&tmDz, dy->data, (uint64_t)P, (uint64_t)dy->c, (uint64_t)dy->c, TM, NT, 128)) return 1;
+  const int kchunks = x->c / KC, nchunks = dy->c / NT;
+  const size_t ws_block = (size_t)TAPS * KC * NT;
+  cudaMemsetAsync(workspace, 0, ws_block * sizeof(float) * kchunks * nchunks, st);
+  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  for (int nc = 0; nc < nchunks; ++nc)
+    for (int kc = 0; kc < kchunks; ++kc) {
+      p.x_col0 = kc * KC;
+      p.dz_col0 = nc * NT;
+      p.ws = (float*)workspace + ws_block * (nc * kchunks + kc);
+      p.db = (db != nullptr && kc == 0) ? db + nc * NT : nullptr;
+      wgrad3x3_tc_kernel<<<grid, kThreads, smem_bytes, st>>>(tmX, tmDz, p);
+      SRK_CUDA_LAUNCH_CHECK("wgrad3x3_tc");
+      wgrad_fold_kernel<<<(NT * KC * TAPS + 255) / 256, 256, 0, st>>>(p.ws, dw, x->c, kc * KC, nc * NT);
+      SRK_CUDA_LAUNCH_CHECK("wgrad_fold");
+    }
+  return 0;
+}
+
+}  // namespace srk

@@ -15,7 +15,7 @@ F32, BF16 = 0, 1
 LAYOUT_IMAGE, LAYOUT_ACT = 0, 1
 ACT_NONE, ACT_RELU, ACT_PRELU = 0, 1, 2
 IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
-PACK_FPROP_SIMT, PACK_DGRAD_SIMT, PACK_FPROP_TC, PACK_DGRAD_TC = 0, 1, 2, 3
+PACK_FPROP_SIMT, PACK_DGRAD_SIMT, PACK_FPROP_TC, PACK_DGRAD_TC, PACK_FPROP_TC_N8 = 0, 1, 2, 3, 4
 
 
 class SrkTensor(ctypes.Structure):

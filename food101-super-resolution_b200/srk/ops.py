@@ -141,9 +141,10 @@ def packed_weight(weight, kind, shuffle):
 
 
 def tc_supported(cin, cout, r, s, dtype, shuffle):
+    """0 = CUDA cores, 1 = tcgen05 ACT->ACT conv, 2 = tcgen05 RGB-output conv (ACT -> IMAGE)"""
     if cfg.conv_impl == "simt" or dtype != torch.bfloat16:
-        return False
-    return bool(L.cdll.srk_conv_tc_supported(cin, cout, r, s, L.BF16, shuffle))
+        return 0
+    return int(L.cdll.srk_conv_tc_supported(cin, cout, r, s, L.BF16, shuffle))
 
 
 # ---- optional per-kernel timing (bench.py roofline) -------------------------------------------------
@@ -188,9 +189,10 @@ def conv_fprop(x, x_img, weight, bias, act, alpha, residual, shuffle, out_img, o
     n, cin, h, w = geometry(x, x_img)
     cout, wcin, r, s = weight.shape
     assert wcin == cin, "conv: input has %d channels, weight expects %d" % (cin, wcin)
-    use_tc = (not x_img) and (not out_img) and tc_supported(cin, cout, r, s, x.dtype, shuffle) \
-        and out_dtype == torch.bfloat16
-    kind = L.PACK_FPROP_TC if use_tc else L.PACK_FPROP_SIMT
+    tc = 0 if x_img else tc_supported(cin, cout, r, s, x.dtype, shuffle)
+    rgb_tc = tc == 2 and out_img and act == L.ACT_NONE and residual is None
+    use_tc = rgb_tc or (tc == 1 and (not out_img) and out_dtype == torch.bfloat16)
+    kind = L.PACK_FPROP_TC_N8 if rgb_tc else (L.PACK_FPROP_TC if use_tc else L.PACK_FPROP_SIMT)
     pk = packed_weight(weight, kind, 0)
     if shuffle == 2:
         oc, oh, ow = cout // 4, 2 * h, 2 * w
@@ -210,7 +212,7 @@ def conv_dgrad(dz, dz_img, weight, residual, out_dtype, perm_tc=False):
     n, c, h, w = geometry(dz, dz_img)
     cout, cin, r, s = weight.shape
     assert c == cout
-    use_tc = (not dz_img) and tc_supported(cout, cin, r, s, dz.dtype, 0) and out_dtype == torch.bfloat16
+    use_tc = (not dz_img) and tc_supported(cout, cin, r, s, dz.dtype, 0) == 1 and out_dtype == torch.bfloat16
     if perm_tc and not use_tc:
         raise RuntimeError("conv_dgrad: permuted dz requires the tcgen05 path")
     kind = L.PACK_DGRAD_TC if use_tc else L.PACK_DGRAD_SIMT

@@ -47,6 +47,7 @@ extern "C" {
 #define SRK_PACK_DGRAD_SIMT 1 /* fp32 [R][S][Cout][Cin], taps rotated by 180 degrees */
 #define SRK_PACK_FPROP_TC 2   /* bf16 [R*S][Cout'][Cin]  (Cout' permuted when pixel_shuffle) */
 #define SRK_PACK_DGRAD_TC 3   /* bf16 [R*S rot180][Cin][Cout'] */
+#define SRK_PACK_FPROP_TC_N8 4 /* bf16 [R*S][8][Cin], rows >= Cout zero: RGB-output convs on tcgen05 */
 
 typedef struct srk_tensor {
   void* data;

@@ -294,3 +294,32 @@ def test_full_size_properties_resnet_step():
     with torch.no_grad():
         a, b = model(lr), model(lr)
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("k,n,h,w", [(9, 2, 16, 8), (9, 1, 37, 21), (5, 2, 19, 30), (9, 2, 64, 64)])
+def test_rgb_output_conv_tcgen05_vs_oracle(k, n, h, w):
+    """output_conv 9x9 64->3 / SRCNN conv3 5x5 64->3: bf16 ACT in, NCHW fp32 out, on tensor cores."""
+    import srk
+    from srk import fn
+    srk.set_compute_dtype("bf16")
+    g = torch.Generator().manual_seed(k * 100 + h)
+    x = torch.randn(n, 64, h, w, generator=g).bfloat16().float()
+    conv = torch.nn.Conv2d(64, 3, k, padding=k // 2)
+    with torch.no_grad():
+        conv.weight.copy_(conv.weight.bfloat16().float())
+    xo = x.clone().requires_grad_(True)
+    yo = conv(xo)
+    go = torch.randn(yo.shape, generator=g)
+    yo.backward(go)
+    ref_w, ref_b = conv.weight.grad.clone(), conv.bias.grad.clone()
+    conv.weight.grad = conv.bias.grad = None
+    conv = conv.to(DEV)
+    xg = x.to(DEV).requires_grad_(True)
+    y = fn.conv_act(fn.ImageToAct.apply(xg, torch.bfloat16), conv, out_img=True)
+    assert y.dtype == torch.float32 and y.shape == yo.shape
+    y.backward(go.to(DEV))
+    assert rel_err(y.cpu(), yo) <= 1e-2
+    assert max_abs(y.cpu(), yo) <= 2e-2 * float(yo.abs().max())
+    assert rel_err(conv.weight.grad.cpu(), ref_w) <= 1e-2
+    assert rel_err(conv.bias.grad.cpu(), ref_b) <= 1e-2
+    assert rel_err(xg.grad.cpu(), xo.grad) <= 1e-2
