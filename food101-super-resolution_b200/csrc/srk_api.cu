@@ -34,6 +34,11 @@ int64_t conv_wgrad_tc_workspace(const srk_tensor* x, const srk_tensor* dy, int r
 int conv_wgrad_tc_launch(const srk_tensor* x, const srk_tensor* dy, float* dw, float* db, int r, int s,
                          void* workspace, cudaStream_t st);
 
+int64_t conv_rgb_workspace_bytes(int k);
+int conv_rgb_tc_run(const srk_tensor* t3, const srk_tensor* y, const void* w_packed, const float* bias, int act,
+                    const float* alpha, const srk_tensor* t64, float* dw, float* db, float* db3, int rgb_out, int k,
+                    void* workspace, cudaStream_t st);
+
 static bool tensor_ok(const srk_tensor* t) {
   if (t == nullptr || t->data == nullptr) return false;
   if (t->n <= 0 || t->c <= 0 || t->h <= 0 || t->w <= 0) return false;
@@ -123,4 +128,24 @@ extern "C" int srk_conv_wgrad(const srk_tensor* x, const srk_tensor* dy, float* 
     return conv_wgrad_tc_launch(x, dy, dw, db, r, s, workspace, st);
   }
   return conv_wgrad_simt_launch(x, dy, dw, db, r, s, st);
+}
+
+extern "C" int64_t srk_conv_rgb_workspace_bytes(int k) { return (k == 9 || k == 5) ? conv_rgb_workspace_bytes(k) : -1; }
+
+extern "C" int srk_conv_rgb_fprop(const srk_tensor* img3, const srk_tensor* y, const void* w_packed, int k,
+                                  const float* bias, int act, const float* alpha, void* stream) {
+  SRK_REQUIRE(tensor_ok(img3) && tensor_ok(y) && w_packed != nullptr, "srk_conv_rgb_fprop: bad arguments");
+  SRK_REQUIRE(act != SRK_ACT_PRELU || alpha != nullptr, "srk_conv_rgb_fprop: PReLU needs alpha");
+  return conv_rgb_tc_run(img3, y, w_packed, bias, act, alpha, nullptr, nullptr, nullptr, nullptr, 0, k, nullptr,
+                         (cudaStream_t)stream);
+}
+
+extern "C" int srk_conv_rgb_bwd(const srk_tensor* img3, const srk_tensor* t64, const void* w_packed,
+                                const srk_tensor* dx, float* dw, float* db, int k, int rgb_out, void* workspace,
+                                void* stream) {
+  SRK_REQUIRE(tensor_ok(img3) && tensor_ok(t64) && dw != nullptr && workspace != nullptr, "srk_conv_rgb_bwd: bad arguments");
+  SRK_REQUIRE(dx == nullptr || (tensor_ok(dx) && w_packed != nullptr && rgb_out == 1),
+              "srk_conv_rgb_bwd: dx needs rgb_out = 1 and SRK_PACK_RGBOUT_DGRAD_TC weights");
+  return conv_rgb_tc_run(img3, dx, w_packed, nullptr, SRK_ACT_NONE, nullptr, t64, dw, rgb_out ? nullptr : db,
+                         rgb_out ? db : nullptr, rgb_out, k, workspace, (cudaStream_t)stream);
 }

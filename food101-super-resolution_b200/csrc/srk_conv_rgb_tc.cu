@@ -1,0 +1,407 @@
+// tcgen05 kernels for the convolutions whose OTHER side has only 3 (RGB) channels:
+//   input_conv 9x9 3->64 (models.py:107,150), SRCNN conv1 9x9 3->64 (models.py:84)       : forward + wgrad
+//   output_conv 9x9 64->3 (models.py:125,167), SRCNN conv3 5x5 64->3 (models.py:86)       : dgrad + wgrad
+//
+// All of them contract over k = (tap, rgb channel): KK = K*K*3 (243 / 75), padded to KP = 256 / 128.  The
+// kernel materialises, per 16x8-pixel tile, the im2col matrix A[128 pixels][KP] of the 3-channel fp32
+// NCHW image T3 in shared memory (bf16, four/two [128 x 128 B] SWIZZLE_128B sub-tiles) and feeds it to the
+// tensor cores twice:
+//   (y)  Y[pixel][n]  = sum_k A[pixel][k] * Wk[n][k]          A K-major,  Wk K-major  -> ACT bf16 output
+//   (g)  G[k][n]     += sum_pixel A[pixel][k] * T64[pixel][n] A MN-major, T64 MN-major -> fp32 weight gradient
+// with T64 the 64-channel activation-layout tensor at the same pixels (TMA 4-D box, zero outside the image).
+// Column k = KK of A is 1 for in-image pixels, so row KK of G is the column sum of T64 (a bias gradient for
+// free).  G stays in TMEM for the CTA's whole tile range and is flushed once with vector fp32 reductions.
+//
+// 10 warps: 0 TMA, 1 MMA issue, 2-5 im2col builders, 6-9 epilogue.
+#include "srk_common.cuh"
+#include "srk_tc_common.cuh"
+
+namespace srk {
+
+using namespace tc;
+int* tc_err_flag();
+int zero_border(const srk_tensor* t, cudaStream_t st);
+
+namespace rgb {
+
+constexpr int TY = 16, TX = 8, TM = 128, NT = 64;
+constexpr int kThreads = 320;
+constexpr int SUB_BYTES = TM * 128;  // one [128 x 64 k] sub-tile of A
+
+struct Params {
+  int N, H, W, tiles_x, tiles_y, num_tiles;
+  int do_y, do_g, act;
+  const float* t3;       // [N][3][H][W]
+  const float* bias;     // [64] or null (y)
+  const float* alpha;
+  __nv_bfloat16* y;      // ACT [N][H+2][W+2][64]
+  float* ws;             // [KP][64] fp32 (g), zero-filled by the caller
+  float* db3;            // [3]: sum over pixels of T3 (accumulated) or null
+  int* err;
+};
+
+struct __align__(8) Barriers {
+  uint64_t wfull, afull[2], aempty[2], tfull[2], tempty[2], yfull[2], yempty[2], done;
+  uint32_t tmem_base;
+  float red3[4][3];
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+template <int K>
+struct Geo {
+  static constexpr int KK = K * K * 3;
+  static constexpr int KP = (KK + 1 + 63) / 64 * 64;   // + the ones column
+  static constexpr int KCH = KP / 64;
+  static constexpr int HH = TY + K - 1, HW = TX + K - 1;
+  static constexpr int HALO = 3 * HH * HW;              // bf16 elements
+  static constexpr int HALO_BYTES = (HALO * 2 + 1023) / 1024 * 1024;
+  static constexpr int A_BYTES = KCH * SUB_BYTES;
+  static constexpr int W_BYTES = KCH * NT * 128;
+  static constexpr int T_BYTES = TM * 128;
+  // smem: [A x2][W][T64 x2][halo][barriers]
+  static constexpr int SMEM = 1024 + 2 * A_BYTES + W_BYTES + 2 * T_BYTES + HALO_BYTES + (int)sizeof(Barriers);
+};
+
+template <int K>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmT, const Params p) {
+  using G = Geo<K>;
+  constexpr int PAD = K / 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t a_sm = smem_base, w_sm = a_sm + 2 * G::A_BYTES, t_sm = w_sm + G::W_BYTES;
+  uint8_t* a_ptr = smem_al;
+  __nv_bfloat16* halo = reinterpret_cast<__nv_bfloat16*>(smem_al + 2 * G::A_BYTES + G::W_BYTES + 2 * G::T_BYTES);
+  Barriers* bars = reinterpret_cast<Barriers*>(smem_al + 2 * G::A_BYTES + G::W_BYTES + 2 * G::T_BYTES + G::HALO_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NG = G::KP / 128;        // G accumulators (M = 128 each)
+  constexpr int TMEM_COLS = 256;         // Y: 2 x 64, G: up to 2 x 64
+
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bars->wfull), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bars->afull[i]), 128);
+      mbar_init(smem_u32(&bars->aempty[i]), 1);
+      mbar_init(smem_u32(&bars->tfull[i]), 1);
+      mbar_init(smem_u32(&bars->tempty[i]), 1);
+      mbar_init(smem_u32(&bars->yfull[i]), 1);
+      mbar_init(smem_u32(&bars->yempty[i]), 128);
+    }
+    mbar_init(smem_u32(&bars->done), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&bars->tmem_base), TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int my_tiles = blockIdx.x < p.num_tiles ? (p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp == 0) {
+    // ================= TMA: weights once, T64 tiles =================
+    if (lane == 0) {
+      if (p.do_y) {
+        prefetch_tmap(&tmW);
+        const uint32_t wb = smem_u32(&bars->wfull);
+        mbar_arrive_expect_tx(wb, G::W_BYTES);
+        for (int q = 0; q < G::KCH; ++q) tma_load_2d(w_sm + q * NT * 128, &tmW, wb, q * 64, 0);
+      }
+      if (p.do_g) {
+        prefetch_tmap(&tmT);
+        for (int i = 0; i < my_tiles; ++i) {
+          const int tile = blockIdx.x + i * gridDim.x;
+          const int n = tile / tiles_per_img, t2 = tile - n * tiles_per_img;
+          const int y0 = (t2 / p.tiles_x) * TY, x0 = (t2 % p.tiles_x) * TX;
+          const int s = i & 1;
+          if (!mbar_wait(smem_u32(&bars->tempty[s]), ((i >> 1) & 1) ^ 1, p.err, 31)) break;
+          const uint32_t fb = smem_u32(&bars->tfull[s]);
+          mbar_arrive_expect_tx(fb, G::T_BYTES);
+          tma_load_4d(t_sm + s * G::T_BYTES, &tmT, fb, 0, x0, y0, n);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc_y = make_idesc_bf16(128, NT, 0, 0);
+      constexpr uint32_t idesc_g = make_idesc_bf16(128, NT, 1, 1);
+      bool ok = true;
+      if (p.do_y) ok = mbar_wait(smem_u32(&bars->wfull), 0, p.err, 32);
+      for (int i = 0; i < my_tiles && ok; ++i) {
+        const int buf = i & 1;
+        const uint32_t par = (i >> 1) & 1;
+        ok = mbar_wait(smem_u32(&bars->afull[buf]), par, p.err, 33);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t a0 = a_sm + buf * G::A_BYTES;
+        if (p.do_y) {
+          ok = mbar_wait(smem_u32(&bars->yempty[buf]), par ^ 1, p.err, 34);
+          if (!ok) break;
+          tc_fence_after();
+          const uint32_t d = tmem_base + buf * NT;
+#pragma unroll
+          for (int q = 0; q < G::KCH; ++q)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_bf16(d, make_smem_desc(a0 + q * SUB_BYTES + ks * 32, 16, 1024, kLayoutSW128, 0),
+                        make_smem_desc(w_sm + q * NT * 128 + ks * 32, 16, 1024, kLayoutSW128, 0), idesc_y,
+                        (q | ks) != 0);
+          umma_commit(smem_u32(&bars->yfull[buf]));
+        }
+        if (p.do_g) {
+          ok = mbar_wait(smem_u32(&bars->tfull[buf]), par, p.err, 35);
+          if (!ok) break;
+          tc_fence_after();
+          const uint32_t t0 = t_sm + buf * G::T_BYTES;
+#pragma unroll
+          for (int mh = 0; mh < NG; ++mh)
+#pragma unroll
+            for (int ks = 0; ks < TM / 16; ++ks)
+              umma_bf16(tmem_base + 2 * NT + mh * NT,
+                        make_smem_desc(a0 + (2 * mh) * SUB_BYTES + ks * 16 * 128, SUB_BYTES, 1024, kLayoutSW128, 0),
+                        make_smem_desc(t0 + ks * 16 * 128, 0, 1024, kLayoutSW128, 0), idesc_g, (i | ks) != 0);
+          umma_commit(smem_u32(&bars->tempty[buf]));
+        }
+        umma_commit(smem_u32(&bars->aempty[buf]));
+      }
+      umma_commit(smem_u32(&bars->done));
+    }
+    __syncwarp();
+  } else if (warp < 6) {
+    // ================= im2col builders =================
+    const int bi = threadIdx.x - 64, ty = bi >> 3, tx = bi & 7;
+    const __nv_bfloat16* hb = halo + ty * G::HW + tx;
+    float s3[3] = {0.f, 0.f, 0.f};
+    const __nv_bfloat16 one = __float2bfloat16_rn(1.f), zero = __float2bfloat16_rn(0.f);
+    for (int i = 0; i < my_tiles; ++i) {
+      const int tile = blockIdx.x + i * gridDim.x;
+      const int n = tile / tiles_per_img, t2 = tile - n * tiles_per_img;
+      const int y0 = (t2 / p.tiles_x) * TY, x0 = (t2 % p.tiles_x) * TX;
+      const int buf = i & 1;
+      asm volatile("bar.sync 2, 128;" ::: "memory");  // everyone is done reading the previous halo
+      const float* src = p.t3 + (size_t)n * 3 * p.H * p.W;
+      for (int idx = bi; idx < G::HALO; idx += 128) {
+        const int c = idx / (G::HH * G::HW), rem = idx - c * (G::HH * G::HW);
+        const int hy = rem / G::HW, hx = rem - hy * G::HW;
+        const int gy = y0 + hy - PAD, gx = x0 + hx - PAD;
+        float v = 0.f;
+        if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) v = __ldg(src + ((size_t)c * p.H + gy) * p.W + gx);
+        halo[idx] = __float2bfloat16_rn(v);
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (!mbar_wait(smem_u32(&bars->aempty[buf]), ((i >> 1) & 1) ^ 1, p.err, 36)) break;
+      const bool inside = (y0 + ty < p.H) && (x0 + tx < p.W);
+      uint8_t* arow = a_ptr + buf * G::A_BYTES + bi * 128;
+#pragma unroll
+      for (int j = 0; j < G::KP / 8; ++j) {
+        __nv_bfloat16 e[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          constexpr int dummy = 0;
+          (void)dummy;
+          const int k = j * 8 + t;
+          if (k < G::KK) {
+            const int tap = k / 3, c = k - tap * 3, r = tap / K, s = tap - r * K;
+            e[t] = hb[(c * G::HH + r) * G::HW + s];
+          } else if (k == G::KK) {
+            e[t] = inside ? one : zero;
+          } else {
+            e[t] = zero;
+          }
+        }
+        uint4 q;
+        q.x = (uint32_t)__bfloat16_as_ushort(e[0]) | ((uint32_t)__bfloat16_as_ushort(e[1]) << 16);
+        q.y = (uint32_t)__bfloat16_as_ushort(e[2]) | ((uint32_t)__bfloat16_as_ushort(e[3]) << 16);
+        q.z = (uint32_t)__bfloat16_as_ushort(e[4]) | ((uint32_t)__bfloat16_as_ushort(e[5]) << 16);
+        q.w = (uint32_t)__bfloat16_as_ushort(e[6]) | ((uint32_t)__bfloat16_as_ushort(e[7]) << 16);
+        const int sub = j >> 3, jj = j & 7;
+        *reinterpret_cast<uint4*>(arow + sub * SUB_BYTES + ((jj ^ (bi & 7)) << 4)) = q;
+      }
+      if (p.db3 && inside) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) s3[c] += __bfloat162float(hb[(c * G::HH + PAD) * G::HW + PAD]);
+      }
+      fence_proxy_async();
+      mbar_arrive(smem_u32(&bars->afull[buf]));
+    }
+    if (p.db3) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float t = warp_sum(s3[c]);
+        if (lane == 0) bars->red3[warp - 2][c] = t;
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (bi < 3) atomicAdd(&p.db3[bi], bars->red3[0][bi] + bars->red3[1][bi] + bars->red3[2][bi] + bars->red3[3][bi]);
+    }
+  } else {
+    // ================= epilogue =================
+    const int lg = warp & 3, ei = lg * 32 + lane, ty = ei >> 3, tx = ei & 7;
+    if (p.do_y) {
+      const float alpha = (p.act == SRK_ACT_PRELU) ? p.alpha[0] : 0.f;
+      const int Hp = p.H + 2, Wp = p.W + 2;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int buf = i & 1;
+        if (!mbar_wait(smem_u32(&bars->yfull[buf]), (i >> 1) & 1, p.err, 37)) break;
+        tc_fence_after();
+        uint32_t v[NT];
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + buf * NT;
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_32x32(taddr + 32, v + 32);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(smem_u32(&bars->yempty[buf]));
+        const int tile = blockIdx.x + i * gridDim.x;
+        const int n = tile / tiles_per_img, t2 = tile - n * tiles_per_img;
+        const int y = (t2 / p.tiles_x) * TY + ty, x = (t2 % p.tiles_x) * TX + tx;
+        if (y >= p.H || x >= p.W) continue;
+        uint4* dst = reinterpret_cast<uint4*>(p.y + (((size_t)n * Hp + y + 1) * Wp + x + 1) * NT);
+#pragma unroll
+        for (int j = 0; j < NT / 8; ++j) {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float a = __uint_as_float(v[j * 8 + e]) + (p.bias ? __ldg(p.bias + j * 8 + e) : 0.f);
+            if (p.act == SRK_ACT_RELU) a = fmaxf(a, 0.f);
+            else if (p.act == SRK_ACT_PRELU) a = a > 0.f ? a : alpha * a;
+            f[e] = a;
+          }
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
+          dst[j] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                              *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+        }
+      }
+    }
+    if (p.do_g && my_tiles > 0 && mbar_wait(smem_u32(&bars->done), 0, p.err, 38)) {
+      tc_fence_after();
+#pragma unroll 1
+      for (int mh = 0; mh < NG; ++mh) {
+        uint32_t v[NT];
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + 2 * NT + mh * NT;
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_32x32(taddr + 32, v + 32);
+        tmem_ld_wait();
+        float* dst = p.ws + (size_t)(mh * 128 + ei) * NT;
+#pragma unroll
+        for (int j = 0; j < NT / 4; ++j)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j),
+                       "f"(__uint_as_float(v[4 * j])), "f"(__uint_as_float(v[4 * j + 1])),
+                       "f"(__uint_as_float(v[4 * j + 2])), "f"(__uint_as_float(v[4 * j + 3]))
+                       : "memory");
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ws[k][n] -> OIHW gradient.  rgb_out = 0: dW[n][c][tap] (3 -> 64 conv), db[n] = ws[KK][n]
+//                               rgb_out = 1: dW[c][n][taps-1-tap] (64 -> 3 conv; im2col was taken over dY)
+__global__ void fold_kernel(const float* __restrict__ ws, float* __restrict__ dw, float* __restrict__ db, int K,
+                            int rgb_out) {
+  const int taps = K * K, KK = taps * 3;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < KK * NT) {
+    const int n = i % NT, k = i / NT, tap = k / 3, c = k - tap * 3;
+    const float v = ws[i];
+    if (!rgb_out) dw[((size_t)n * 3 + c) * taps + tap] += v;
+    else dw[((size_t)c * NT + n) * taps + (taps - 1 - tap)] += v;
+  } else if (i < (KK + 1) * NT && db != nullptr && !rgb_out) {
+    db[i - KK * NT] += ws[i];
+  }
+}
+
+static int make_tmap_act_4d_tile(CUtensorMap* out, const srk_tensor* x) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  SRK_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  const uint64_t C = x->c, Wp = x->w + 2, Hp = x->h + 2;
+  cuuint64_t dims[4] = {C, (cuuint64_t)x->w, (cuuint64_t)x->h, (cuuint64_t)x->n};
+  cuuint64_t strides[3] = {C * 2, Wp * C * 2, Hp * Wp * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)C, TX, TY, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  void* base = (char*)x->data + (Wp + 1) * C * 2;
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SRK_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(4d tile) failed (%d)", (int)r);
+  return 0;
+}
+
+template <int K>
+static int launch(const CUtensorMap& tmW, const CUtensorMap& tmT, const Params& p, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(conv_rgb_tc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<K>::SMEM);
+    attr = true;
+  }
+  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  conv_rgb_tc_kernel<K><<<grid, kThreads, Geo<K>::SMEM, st>>>(tmW, tmT, p);
+  SRK_CUDA_LAUNCH_CHECK("conv_rgb_tc");
+  return 0;
+}
+
+}  // namespace rgb
+
+int64_t conv_rgb_workspace_bytes(int k) { return (int64_t)(k == 9 ? rgb::Geo<9>::KP : rgb::Geo<5>::KP) * 64 * 4; }
+
+// t3: IMAGE [N,3,H,W]; y (optional): ACT bf16 [N,64,H,W] = act(conv + bias) with Wk = w_packed (bf16 [64][KP]);
+// t64 (optional): ACT bf16 [N,64,H,W] -> dw (OIHW fp32, accumulated), db / db3 (accumulated).
+int conv_rgb_tc_run(const srk_tensor* t3, const srk_tensor* y, const void* w_packed, const float* bias, int act,
+                    const float* alpha, const srk_tensor* t64, float* dw, float* db, float* db3, int rgb_out, int k,
+                    void* workspace, cudaStream_t st) {
+  SRK_REQUIRE(k == 9 || k == 5, "conv_rgb: kernel size must be 9 or 5");
+  SRK_REQUIRE(t3 && t3->layout == SRK_LAYOUT_IMAGE && t3->c == 3, "conv_rgb: needs a 3-channel IMAGE tensor");
+  rgb::Params p;
+  p.N = t3->n; p.H = t3->h; p.W = t3->w;
+  p.tiles_x = (p.W + rgb::TX - 1) / rgb::TX; p.tiles_y = (p.H + rgb::TY - 1) / rgb::TY;
+  const long long nt = (long long)p.N * p.tiles_x * p.tiles_y;
+  SRK_REQUIRE(nt < (1LL << 31), "conv_rgb: too many tiles");
+  p.num_tiles = (int)nt;
+  p.do_y = y != nullptr; p.do_g = t64 != nullptr; p.act = act;
+  p.t3 = (const float*)t3->data; p.bias = bias; p.alpha = alpha;
+  p.y = y ? (__nv_bfloat16*)y->data : nullptr;
+  p.ws = (float*)workspace; p.db3 = db3; p.err = tc_err_flag();
+  const int KP = k == 9 ? rgb::Geo<9>::KP : rgb::Geo<5>::KP;
+  CUtensorMap tmW, tmT;
+  memset(&tmW, 0, sizeof(tmW)); memset(&tmT, 0, sizeof(tmT));
+  if (p.do_y) {
+    SRK_REQUIRE(y->layout == SRK_LAYOUT_ACT && y->dtype == SRK_BF16 && y->c == 64 && y->n == p.N && y->h == p.H && y->w == p.W,
+                "conv_rgb: y must be a bf16 ACT tensor with 64 channels");
+    if (make_tmap_2d_bf16(&tmW, w_packed, 64, (uint64_t)KP, (uint64_t)KP, 64, 64, 128)) return 1;
+  }
+  if (p.do_g) {
+    SRK_REQUIRE(t64->layout == SRK_LAYOUT_ACT && t64->dtype == SRK_BF16 && t64->c == 64 && t64->n == p.N && t64->h == p.H && t64->w == p.W,
+                "conv_rgb: t64 must be a bf16 ACT tensor with 64 channels");
+    SRK_REQUIRE(workspace != nullptr && dw != nullptr, "conv_rgb: workspace / dw required");
+    if (rgb::make_tmap_act_4d_tile(&tmT, t64)) return 1;
+    cudaMemsetAsync(workspace, 0, (size_t)KP * 64 * 4, st);
+  }
+  int rc = k == 9 ? rgb::launch<9>(tmW, tmT, p, st) : rgb::launch<5>(tmW, tmT, p, st);
+  if (rc) return rc;
+  if (p.do_g) {
+    const int total = (k * k * 3 + 1) * 64;
+    rgb::fold_kernel<<<(total + 255) / 256, 256, 0, st>>>((const float*)workspace, dw, db, k, rgb_out);
+    SRK_CUDA_LAUNCH_CHECK("conv_rgb_fold");
+  }
+  if (p.do_y) return zero_border(y, st);
+  return 0;
+}
+
+}  // namespace srk

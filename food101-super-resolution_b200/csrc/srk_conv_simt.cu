@@ -318,10 +318,24 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, void* __restric
                                     int Cin, int R, int S, int kind, int shuffle) {
   long long total = (long long)Cout * Cin * R * S;
   if (kind == SRK_PACK_FPROP_TC_N8) total = (long long)8 * Cin * R * S;
+  const int KPr = (R * S * 3 + 1 + 63) / 64 * 64;
+  if (kind == SRK_PACK_RGBIN_TC || kind == SRK_PACK_RGBOUT_DGRAD_TC) total = 64LL * KPr;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     // i indexes the OUTPUT linearly
-    if (kind == SRK_PACK_FPROP_TC_N8) {  // bf16 [tap][8][Cin]
+    if (kind == SRK_PACK_RGBIN_TC || kind == SRK_PACK_RGBOUT_DGRAD_TC) {  // bf16 [64][KP]
+      int k = (int)(i % KPr), n = (int)(i / KPr);
+      float v = 0.f;
+      if (k < R * S * 3) {
+        int tap = k / 3, c = k - tap * 3, r = tap / S, s = tap - r * S;
+        if (kind == SRK_PACK_RGBIN_TC) {            // n = co (Cout == 64), c = ci (Cin == 3)
+          if (n < Cout && c < Cin) v = w[(((long long)n * Cin + c) * R + r) * S + s];
+        } else {                                      // n = ci (Cin == 64), c = co (Cout <= 3), rot180
+          if (n < Cin && c < Cout) v = w[(((long long)c * Cin + n) * R + (R - 1 - r)) * S + (S - 1 - s)];
+        }
+      }
+      ((__nv_bfloat16*)out)[i] = __float2bfloat16_rn(v);
+    } else if (kind == SRK_PACK_FPROP_TC_N8) {  // bf16 [tap][8][Cin]
       int ci = (int)(i % Cin); long long t = i / Cin;
       int co = (int)(t % 8); int tap = (int)(t / 8);
       int r = tap / S, s = tap - r * S;
@@ -363,15 +377,19 @@ using namespace srk;
 extern "C" int64_t srk_weight_pack_bytes(int cout, int cin, int r, int s, int kind) {
   int64_t n = (int64_t)cout * cin * r * s;
   if (kind == SRK_PACK_FPROP_TC_N8) return (int64_t)8 * cin * r * s * 2 + 8 * 128;
+  if (kind == SRK_PACK_RGBIN_TC || kind == SRK_PACK_RGBOUT_DGRAD_TC) return 64LL * ((r * s * 3 + 1 + 63) / 64 * 64) * 2;
   return (kind == SRK_PACK_FPROP_SIMT || kind == SRK_PACK_DGRAD_SIMT) ? n * 4 : n * 2;
 }
 
 extern "C" int srk_weight_pack(const float* w_oihw, void* out, int cout, int cin, int r, int s,
                                int kind, int pixel_shuffle, void* stream) {
-  SRK_REQUIRE(kind >= 0 && kind <= 4, "srk_weight_pack: bad kind %d", kind);
+  SRK_REQUIRE(kind >= 0 && kind <= 6, "srk_weight_pack: bad kind %d", kind);
+  SRK_REQUIRE(kind != SRK_PACK_RGBIN_TC || (cin == 3 && cout == 64), "srk_weight_pack: RGBIN pack needs a 3 -> 64 conv");
+  SRK_REQUIRE(kind != SRK_PACK_RGBOUT_DGRAD_TC || (cin == 64 && cout <= 3), "srk_weight_pack: RGBOUT pack needs a 64 -> 3 conv");
   SRK_REQUIRE(kind != SRK_PACK_FPROP_TC_N8 || cout <= 8, "srk_weight_pack: N8 pack needs Cout <= 8");
   SRK_REQUIRE(pixel_shuffle == 0 || (pixel_shuffle == 2 && cout % 4 == 0), "srk_weight_pack: bad pixel_shuffle");
   long long total = (long long)(kind == SRK_PACK_FPROP_TC_N8 ? 8 : cout) * cin * r * s;
+  if (kind == SRK_PACK_RGBIN_TC || kind == SRK_PACK_RGBOUT_DGRAD_TC) total = 64LL * ((r * s * 3 + 1 + 63) / 64 * 64);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (kind == SRK_PACK_FPROP_TC_N8)  // zero the slack tap read by the last N=16 MMA

@@ -16,6 +16,7 @@ LAYOUT_IMAGE, LAYOUT_ACT = 0, 1
 ACT_NONE, ACT_RELU, ACT_PRELU = 0, 1, 2
 IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
 PACK_FPROP_SIMT, PACK_DGRAD_SIMT, PACK_FPROP_TC, PACK_DGRAD_TC, PACK_FPROP_TC_N8 = 0, 1, 2, 3, 4
+PACK_RGBIN_TC, PACK_RGBOUT_DGRAD_TC = 5, 6
 
 
 class SrkTensor(ctypes.Structure):
@@ -34,6 +35,9 @@ SIGNATURES = {
     "srk_conv_fprop": (c_int, [_T, _T, _P, c_int, c_int, c_int, c_int, _P, c_int, _P, _T, c_int, c_int, _P]),
     "srk_conv_wgrad": (c_int, [_T, _T, _P, _P, c_int, c_int, c_int, _P, _P]),
     "srk_conv_wgrad_workspace_bytes": (c_int64, [_T, _T, c_int, c_int, c_int]),
+    "srk_conv_rgb_workspace_bytes": (c_int64, [c_int]),
+    "srk_conv_rgb_fprop": (c_int, [_T, _T, _P, c_int, _P, c_int, _P, _P]),
+    "srk_conv_rgb_bwd": (c_int, [_T, _T, _P, _T, _P, _P, c_int, c_int, _P, _P]),
     "srk_weight_pack": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "srk_weight_pack_bytes": (c_int64, [c_int] * 5),
     "srk_act_bwd": (c_int, [_T, _T, _T, c_int, _P, _P, c_int, c_int, _P]),
@@ -78,7 +82,7 @@ for _name, (_res, _args) in SIGNATURES.items():
 # number of libsrk kernel-launching calls made by this process (bench.py reports it)
 launch_calls = 0
 _NO_COUNT = {"srk_last_error", "srk_version", "srk_conv_tc_supported", "srk_weight_pack_bytes",
-             "srk_conv_wgrad_workspace_bytes", "srk_nlpd_workspace_bytes"}
+             "srk_conv_wgrad_workspace_bytes", "srk_nlpd_workspace_bytes", "srk_conv_rgb_workspace_bytes"}
 
 
 def last_error():

@@ -72,6 +72,9 @@ class ConvAct(torch.autograd.Function):
         else:
             dz, dz_img = dout, out_img
         dw = db = dx = None
+        if ops.rgbout_bwd_supported(x, x_img, dz_img, weight):
+            dx, dw, db = ops.conv_rgbout_bwd(x, dz, weight, _needs(ctx, 0), has_bias)
+            return dx, dw, db, None, None, None, None, None, None, None
         if _needs(ctx, 1) or (has_bias and _needs(ctx, 2)):
             dw, db = ops.conv_wgrad(x, x_img, dz, dz_img, weight, has_bias, perm)
         if _needs(ctx, 0):

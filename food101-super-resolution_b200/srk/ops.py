@@ -184,11 +184,49 @@ def _timed(key, launch):
 
 
 # ---- convolution -----------------------------------------------------------------------------------
+def _rgb_tc_ok(r, s):
+    return cfg.conv_impl != "simt" and cfg.compute_dtype == torch.bfloat16 and r == s and r in (5, 9)
+
+
+def _rgb_workspace(k, device):
+    return torch.empty((L.cdll.srk_conv_rgb_workspace_bytes(k),), dtype=torch.uint8, device=device)
+
+
+def conv_rgbout_bwd(x, dout, weight, need_dx, need_bias):
+    """Backward of a 64 -> 3 conv whose output gradient is an NCHW fp32 image (output_conv, SRCNN conv3):
+    one tcgen05 kernel produces dx (bf16 act), dW and db.  -> (dx or None, dw, db or None)"""
+    cout, cin, r, s = weight.shape
+    n, _, h, w = geometry(x, False)
+    dw = torch.zeros_like(weight, memory_format=torch.contiguous_format)
+    db = torch.zeros((cout,), dtype=torch.float32, device=weight.device)
+    dx = new_act(n, cin, h, w, torch.bfloat16, x.device) if need_dx else None
+    pk = packed_weight(weight, L.PACK_RGBOUT_DGRAD_TC, 0) if need_dx else None
+    ws = _rgb_workspace(r, x.device)
+    _timed(("conv_rgbout_bwd", cin, cout, r, 0, n, h, w, True),
+           lambda: L.call("srk_conv_rgb_bwd", img_desc(dout), act_desc(x), _ptr(pk),
+                          act_desc(dx) if need_dx else None, dw.data_ptr(), db.data_ptr(), r, 1, ws.data_ptr(),
+                          stream_ptr()))
+    return dx, dw, (db if need_bias else None)
+
+
+def rgbout_bwd_supported(x, x_img, dz_img, weight):
+    cout, cin, r, s = weight.shape
+    return (not x_img) and dz_img and cin == 64 and cout == 3 and x.dtype == torch.bfloat16 and _rgb_tc_ok(r, s)
+
+
 def conv_fprop(x, x_img, weight, bias, act, alpha, residual, shuffle, out_img, out_dtype):
     """y = [shuffle](act(conv(x, weight) + bias)) [+ residual]; stride 1, pad R//2."""
     n, cin, h, w = geometry(x, x_img)
     cout, wcin, r, s = weight.shape
     assert wcin == cin, "conv: input has %d channels, weight expects %d" % (cin, wcin)
+    if (x_img and cin == 3 and cout == 64 and not out_img and out_dtype == torch.bfloat16 and residual is None
+            and shuffle == 0 and _rgb_tc_ok(r, s)):
+        pk = packed_weight(weight, L.PACK_RGBIN_TC, 0)
+        y = new_act(n, cout, h, w, out_dtype, x.device)
+        _timed(("conv_rgbin_fprop", cin, cout, r, 0, n, h, w, True),
+               lambda: L.call("srk_conv_rgb_fprop", img_desc(x), act_desc(y), pk.data_ptr(), r, _ptr(bias), act,
+                              _ptr(alpha), stream_ptr()))
+        return y, True
     tc = 0 if x_img else tc_supported(cin, cout, r, s, x.dtype, shuffle)
     rgb_tc = tc == 2 and out_img and act == L.ACT_NONE and residual is None
     use_tc = rgb_tc or (tc == 1 and (not out_img) and out_dtype == torch.bfloat16)
@@ -232,6 +270,13 @@ def conv_wgrad(x, x_img, dz, dz_img, weight, need_bias, perm_tc=False):
     cout, cin, r, s = weight.shape
     dw = torch.zeros_like(weight, memory_format=torch.contiguous_format)
     db = torch.zeros((cout,), dtype=torch.float32, device=weight.device) if need_bias else None
+    if x_img and (not dz_img) and cin == 3 and cout == 64 and dz.dtype == torch.bfloat16 and _rgb_tc_ok(r, s):
+        n, _, h, w = geometry(x, True)
+        ws = _rgb_workspace(r, x.device)
+        _timed(("conv_rgbin_wgrad", cin, cout, r, 0, n, h, w, True),
+               lambda: L.call("srk_conv_rgb_bwd", img_desc(x), act_desc(dz), None, None, dw.data_ptr(), _ptr(db),
+                              r, 0, ws.data_ptr(), stream_ptr()))
+        return dw, db
     xd, dd = desc(x, x_img), desc(dz, dz_img)
     impl = L.IMPL_SIMT if cfg.conv_impl == "simt" else L.IMPL_AUTO
     nbytes = L.cdll.srk_conv_wgrad_workspace_bytes(xd, dd, r, s, impl)

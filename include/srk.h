@@ -48,6 +48,8 @@ extern "C" {
 #define SRK_PACK_FPROP_TC 2   /* bf16 [R*S][Cout'][Cin]  (Cout' permuted when pixel_shuffle) */
 #define SRK_PACK_DGRAD_TC 3   /* bf16 [R*S rot180][Cin][Cout'] */
 #define SRK_PACK_FPROP_TC_N8 4 /* bf16 [R*S][8][Cin], rows >= Cout zero: RGB-output convs on tcgen05 */
+#define SRK_PACK_RGBIN_TC 5    /* bf16 [64][KP], k = (r*S+s)*3 + c, zero padded: 3 -> 64 conv forward */
+#define SRK_PACK_RGBOUT_DGRAD_TC 6 /* bf16 [64 ci][KP], k = (r'*S+s')*3 + co, taps rotated: 64 -> 3 conv dgrad */
 
 typedef struct srk_tensor {
   void* data;
@@ -79,6 +81,21 @@ int srk_conv_fprop(const srk_tensor* x, const srk_tensor* y, const void* w_packe
 int srk_conv_wgrad(const srk_tensor* x, const srk_tensor* dy, float* dw, float* db, int r, int s,
                    int impl, void* workspace, void* stream);
 int64_t srk_conv_wgrad_workspace_bytes(const srk_tensor* x, const srk_tensor* dy, int r, int s, int impl);
+
+/* ---- convolutions with an RGB side on tcgen05 (K = 9 or 5; im2col built in shared memory) ---------
+ * input_conv / SRCNN conv1 (3 -> 64, models.py:84,107,150) and the backward of output_conv / SRCNN conv3
+ * (64 -> 3, models.py:86,125,167).  img3: IMAGE fp32 [N,3,H,W]; y, t64, dx: bf16 ACT [N,64,H,W].
+ *   fprop:  y = act(conv(img3, W) + bias), W packed SRK_PACK_RGBIN_TC.
+ *   bwd, rgb_out = 0 (3 -> 64 conv): img3 = the conv input, t64 = dZ; dw [64][3][K][K], db [64] accumulated.
+ *   bwd, rgb_out = 1 (64 -> 3 conv): img3 = dY, t64 = the conv input; dw [3][64][K][K], db [3] accumulated;
+ *        when dx != NULL also dx = dgrad(dY) with w_packed = SRK_PACK_RGBOUT_DGRAD_TC weights.
+ * workspace: srk_conv_rgb_workspace_bytes(k) bytes. */
+int64_t srk_conv_rgb_workspace_bytes(int k);
+int srk_conv_rgb_fprop(const srk_tensor* img3, const srk_tensor* y, const void* w_packed, int k,
+                       const float* bias, int act, const float* alpha, void* stream);
+int srk_conv_rgb_bwd(const srk_tensor* img3, const srk_tensor* t64, const void* w_packed,
+                     const srk_tensor* dx, float* dw, float* db, int k, int rgb_out, void* workspace,
+                     void* stream);
 
 /* OIHW fp32 master weights -> kernel operand layouts (see SRK_PACK_*). */
 int srk_weight_pack(const float* w_oihw, void* out, int cout, int cin, int r, int s, int kind,

@@ -323,3 +323,38 @@ def test_rgb_output_conv_tcgen05_vs_oracle(k, n, h, w):
     assert rel_err(conv.weight.grad.cpu(), ref_w) <= 1e-2
     assert rel_err(conv.bias.grad.cpu(), ref_b) <= 1e-2
     assert rel_err(xg.grad.cpu(), xo.grad) <= 1e-2
+
+
+@pytest.mark.parametrize("k,n,h,w,act", [(9, 2, 16, 8, "prelu"), (9, 1, 37, 21, "relu"), (5, 2, 19, 30, "none"),
+                                         (9, 3, 64, 64, "prelu")])
+def test_rgb_input_conv_tcgen05_vs_oracle(k, n, h, w, act):
+    """input_conv / SRCNN conv1 (3 -> 64): NCHW fp32 in, bf16 ACT out, im2col built in shared memory."""
+    import srk
+    from srk import _lib as L
+    from srk import fn
+    srk.set_compute_dtype("bf16")
+    g = torch.Generator().manual_seed(k * 10 + h)
+    x = torch.rand(n, 3, h, w, generator=g).bfloat16().float()
+    conv = torch.nn.Conv2d(3, 64, k, padding=k // 2)
+    with torch.no_grad():
+        conv.weight.copy_(conv.weight.bfloat16().float())
+    alpha = torch.tensor([0.25])
+    ao = alpha.clone().requires_grad_(True)
+    yo = conv(x)
+    yo = F.prelu(yo, ao) if act == "prelu" else (F.relu(yo) if act == "relu" else yo)
+    go = torch.randn(yo.shape, generator=g).bfloat16().float()
+    yo.backward(go)
+    ref_w, ref_b = conv.weight.grad.clone(), conv.bias.grad.clone()
+    conv.weight.grad = conv.bias.grad = None
+    conv = conv.to(DEV)
+    al = alpha.to(DEV).requires_grad_(True)
+    code = {"none": L.ACT_NONE, "relu": L.ACT_RELU, "prelu": L.ACT_PRELU}[act]
+    ya = fn.conv_act(x.to(DEV), conv, act=code, alpha=al if act == "prelu" else None, x_img=True)
+    y = fn.ActToImage.apply(ya)
+    y.backward(go.to(DEV))
+    assert rel_err(y.cpu(), yo) <= 1e-2
+    assert rel_err(conv.weight.grad.cpu(), ref_w) <= 1e-2
+    assert rel_err(conv.bias.grad.cpu(), ref_b) <= 1e-2
+    if act == "prelu":
+        assert rel_err(al.grad.cpu(), ao.grad) <= 1e-2
+    assert float(ya[:, 0].abs().max()) == 0 and float(ya[:, :, -1].abs().max()) == 0
