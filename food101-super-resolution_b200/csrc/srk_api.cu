@@ -25,7 +25,8 @@ int conv_wgrad_simt_launch(const srk_tensor* x, const srk_tensor* dy, float* dw,
 bool conv_tc_shape_ok(int cin, int cout, int r, int s, int dtype, int shuffle);
 int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout,
                          int r, int s, const float* bias, int act, const float* alpha,
-                         const srk_tensor* residual, int shuffle, cudaStream_t st);
+                         const srk_tensor* residual, int shuffle, float* stats_sum, float* stats_sumsq,
+                         cudaStream_t st);
 bool conv_smalln_tc_ok(const srk_tensor* x, const srk_tensor* y, int cout, int r, int s);
 int conv_smalln_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout, int r,
                           const float* bias, cudaStream_t st);
@@ -63,7 +64,11 @@ extern "C" int srk_conv_tc_supported(int cin, int cout, int r, int s, int dtype,
 extern "C" int srk_conv_fprop(const srk_tensor* x, const srk_tensor* y, const void* w_packed,
                               int pack_kind, int cout, int r, int s, const float* bias, int act,
                               const float* alpha, const srk_tensor* residual, int pixel_shuffle,
-                              int impl, void* stream) {
+                              int impl, float* bn_sum, float* bn_sumsq, void* stream) {
+  SRK_REQUIRE((bn_sum == nullptr) == (bn_sumsq == nullptr), "srk_conv_fprop: bn_sum and bn_sumsq go together");
+  SRK_REQUIRE(bn_sum == nullptr || (act == SRK_ACT_NONE && residual == nullptr && pixel_shuffle == 0 &&
+                                    y->layout == SRK_LAYOUT_ACT),
+              "srk_conv_fprop: BN statistics are taken of a plain conv output in the ACT layout");
   SRK_REQUIRE(tensor_ok(x) && tensor_ok(y), "srk_conv_fprop: bad x / y tensor");
   SRK_REQUIRE(w_packed != nullptr, "srk_conv_fprop: null weights");
   SRK_REQUIRE(r == s && (r & 1) == 1 && r >= 1 && r <= 11, "srk_conv_fprop: odd square kernels only (got %dx%d)", r, s);
@@ -82,7 +87,8 @@ extern "C" int srk_conv_fprop(const srk_tensor* x, const srk_tensor* y, const vo
                 "srk_conv_fprop: residual must match the output geometry and layout");
   }
   if (pack_kind == SRK_PACK_FPROP_TC_N8) {
-    SRK_REQUIRE(conv_smalln_tc_ok(x, y, cout, r, s) && act == SRK_ACT_NONE && residual == nullptr && pixel_shuffle == 0,
+    SRK_REQUIRE(conv_smalln_tc_ok(x, y, cout, r, s) && act == SRK_ACT_NONE && residual == nullptr && pixel_shuffle == 0 &&
+                    bn_sum == nullptr,
                 "srk_conv_fprop: the RGB-output tcgen05 path takes bf16 ACT input with 64 channels, an IMAGE "
                 "output with <= 4 channels and no activation / residual");
     return conv_smalln_tc_launch(x, y, w_packed, cout, r, bias, (cudaStream_t)stream);
@@ -99,11 +105,20 @@ extern "C" int srk_conv_fprop(const srk_tensor* x, const srk_tensor* y, const vo
                 "srk_conv_fprop: tcgen05 path needs bf16 ACT tensors");
     SRK_REQUIRE(conv_tc_shape_ok(x->c, cout, r, s, SRK_BF16, pixel_shuffle),
                 "srk_conv_fprop: shape Cin=%d Cout=%d %dx%d not supported by the tcgen05 path", x->c, cout, r, s);
-    return conv_fprop_tc_launch(x, y, w_packed, cout, r, s, bias, act, alpha, residual, pixel_shuffle, st);
+    if (bn_sum != nullptr && x->c != 64) {  // the fused statistics cover single-pass convs only
+      if (conv_fprop_tc_launch(x, y, w_packed, cout, r, s, bias, act, alpha, residual, pixel_shuffle, nullptr,
+                               nullptr, st))
+        return 1;
+      return srk_bn_stats(y, bn_sum, bn_sumsq, stream);
+    }
+    return conv_fprop_tc_launch(x, y, w_packed, cout, r, s, bias, act, alpha, residual, pixel_shuffle, bn_sum,
+                                bn_sumsq, st);
   }
   SRK_REQUIRE(impl == SRK_IMPL_SIMT && simt_kind, "srk_conv_fprop: CUDA-core path needs SRK_PACK_*_SIMT weights");
-  return conv_fprop_simt_launch(x, y, (const float*)w_packed, cout, r, s, bias, act, alpha, residual,
-                                pixel_shuffle, st);
+  if (conv_fprop_simt_launch(x, y, (const float*)w_packed, cout, r, s, bias, act, alpha, residual,
+                             pixel_shuffle, st))
+    return 1;
+  return bn_sum ? srk_bn_stats(y, bn_sum, bn_sumsq, stream) : 0;
 }
 
 extern "C" int64_t srk_conv_wgrad_workspace_bytes(const srk_tensor* x, const srk_tensor* dy, int r, int s,

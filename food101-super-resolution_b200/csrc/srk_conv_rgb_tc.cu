@@ -110,75 +110,87 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   const int my_tiles = blockIdx.x < p.num_tiles ? (p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (warp == 0) {
-    // ================= TMA: weights once, T64 tiles =================
-    if (lane == 0) {
-      if (p.do_y) {
+    // ================= TMA: weights once, T64 tiles (whole warp, one elected lane issues) =================
+    if (p.do_y) {
+      if (elect_one()) {
         prefetch_tmap(&tmW);
         const uint32_t wb = smem_u32(&bars->wfull);
         mbar_arrive_expect_tx(wb, G::W_BYTES);
         for (int q = 0; q < G::KCH; ++q) tma_load_2d(w_sm + q * NT * 128, &tmW, wb, q * 64, 0);
       }
-      if (p.do_g) {
-        prefetch_tmap(&tmT);
-        for (int i = 0; i < my_tiles; ++i) {
-          const int tile = blockIdx.x + i * gridDim.x;
-          const int n = tile / tiles_per_img, t2 = tile - n * tiles_per_img;
-          const int y0 = (t2 / p.tiles_x) * TY, x0 = (t2 % p.tiles_x) * TX;
-          const int s = i & 1;
-          if (!mbar_wait(smem_u32(&bars->tempty[s]), ((i >> 1) & 1) ^ 1, p.err, 31)) break;
+      __syncwarp();
+    }
+    if (p.do_g) {
+      if (elect_one()) prefetch_tmap(&tmT);
+      __syncwarp();
+      for (int i = 0; i < my_tiles; ++i) {
+        const int tile = blockIdx.x + i * gridDim.x;
+        const int n = tile / tiles_per_img, t2 = tile - n * tiles_per_img;
+        const int y0 = (t2 / p.tiles_x) * TY, x0 = (t2 % p.tiles_x) * TX;
+        const int s = i & 1;
+        if (!mbar_wait(smem_u32(&bars->tempty[s]), ((i >> 1) & 1) ^ 1, p.err, 31)) break;
+        if (elect_one()) {
           const uint32_t fb = smem_u32(&bars->tfull[s]);
           mbar_arrive_expect_tx(fb, G::T_BYTES);
           tma_load_4d(t_sm + s * G::T_BYTES, &tmT, fb, 0, x0, y0, n);
         }
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc_y = make_idesc_bf16(128, NT, 0, 0);
-      constexpr uint32_t idesc_g = make_idesc_bf16(128, NT, 1, 1);
-      bool ok = true;
-      if (p.do_y) ok = mbar_wait(smem_u32(&bars->wfull), 0, p.err, 32);
-      for (int i = 0; i < my_tiles && ok; ++i) {
-        const int buf = i & 1;
-        const uint32_t par = (i >> 1) & 1;
-        ok = mbar_wait(smem_u32(&bars->afull[buf]), par, p.err, 33);
+    // ================= MMA issuer (whole warp, one elected lane issues) =================
+    constexpr uint32_t idesc_y = make_idesc_bf16(128, NT, 0, 0);
+    constexpr uint32_t idesc_g = make_idesc_bf16(128, NT, 1, 1);
+    const uint64_t hi_k = make_smem_desc(0, 16, 1024, kLayoutSW128, 0) & 0xFFFFFFFF00000000ull;
+    const uint32_t lo_k = (uint32_t)(make_smem_desc(0, 16, 1024, kLayoutSW128, 0) & 0xFFFFFFFFull);
+    const uint32_t lo_ga = (uint32_t)(make_smem_desc(0, SUB_BYTES, 1024, kLayoutSW128, 0) & 0xFFFFFFFFull);
+    const uint32_t lo_gb = (uint32_t)(make_smem_desc(0, 0, 1024, kLayoutSW128, 0) & 0xFFFFFFFFull);
+    bool ok = true;
+    if (p.do_y) ok = mbar_wait(smem_u32(&bars->wfull), 0, p.err, 32);
+    for (int i = 0; i < my_tiles && ok; ++i) {
+      const int buf = i & 1;
+      const uint32_t par = (i >> 1) & 1;
+      ok = mbar_wait(smem_u32(&bars->afull[buf]), par, p.err, 33);
+      if (!ok) break;
+      tc_fence_after();
+      const uint32_t a0 = (a_sm + buf * G::A_BYTES) >> 4;
+      if (p.do_y) {
+        ok = mbar_wait(smem_u32(&bars->yempty[buf]), par ^ 1, p.err, 34);
         if (!ok) break;
         tc_fence_after();
-        const uint32_t a0 = a_sm + buf * G::A_BYTES;
-        if (p.do_y) {
-          ok = mbar_wait(smem_u32(&bars->yempty[buf]), par ^ 1, p.err, 34);
-          if (!ok) break;
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t d = tmem_base + buf * NT;
 #pragma unroll
           for (int q = 0; q < G::KCH; ++q)
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              umma_bf16(d, make_smem_desc(a0 + q * SUB_BYTES + ks * 32, 16, 1024, kLayoutSW128, 0),
-                        make_smem_desc(w_sm + q * NT * 128 + ks * 32, 16, 1024, kLayoutSW128, 0), idesc_y,
-                        (q | ks) != 0);
+              umma_bf16(d, hi_k | (lo_k + a0 + q * (SUB_BYTES / 16) + 2 * ks),
+                        hi_k | (lo_k + (w_sm >> 4) + q * (NT * 128 / 16) + 2 * ks), idesc_y, (q | ks) != 0);
           umma_commit(smem_u32(&bars->yfull[buf]));
         }
-        if (p.do_g) {
-          ok = mbar_wait(smem_u32(&bars->tfull[buf]), par, p.err, 35);
-          if (!ok) break;
-          tc_fence_after();
-          const uint32_t t0 = t_sm + buf * G::T_BYTES;
+        __syncwarp();
+      }
+      if (p.do_g) {
+        ok = mbar_wait(smem_u32(&bars->tfull[buf]), par, p.err, 35);
+        if (!ok) break;
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t t0 = (t_sm + buf * G::T_BYTES) >> 4;
 #pragma unroll
           for (int mh = 0; mh < NG; ++mh)
 #pragma unroll
             for (int ks = 0; ks < TM / 16; ++ks)
               umma_bf16(tmem_base + 2 * NT + mh * NT,
-                        make_smem_desc(a0 + (2 * mh) * SUB_BYTES + ks * 16 * 128, SUB_BYTES, 1024, kLayoutSW128, 0),
-                        make_smem_desc(t0 + ks * 16 * 128, 0, 1024, kLayoutSW128, 0), idesc_g, (i | ks) != 0);
+                        hi_k | (lo_ga + a0 + (2 * mh) * (SUB_BYTES / 16) + ks * (16 * 128 / 16)),
+                        hi_k | (lo_gb + t0 + ks * (16 * 128 / 16)), idesc_g, (i | ks) != 0);
           umma_commit(smem_u32(&bars->tempty[buf]));
         }
-        umma_commit(smem_u32(&bars->aempty[buf]));
+        __syncwarp();
       }
-      umma_commit(smem_u32(&bars->done));
+      if (elect_one()) umma_commit(smem_u32(&bars->aempty[buf]));
+      __syncwarp();
     }
+    if (elect_one()) umma_commit(smem_u32(&bars->done));
     __syncwarp();
   } else if (warp < 6) {
     // ================= im2col builders =================

@@ -79,57 +79,65 @@ conv_smalln_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   const int tiles_per_img = p.tiles_x * p.tiles_y;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // TMA producer: whole warp, one elected lane issues
+    if (elect_one()) {
       prefetch_tmap(&tmX);
       prefetch_tmap(&tmW);
       const uint32_t wbar = smem_u32(&bars->wfull);
-      // weights: rows of 128 B, loaded in boxes of up to 128 rows
       const int wrows = taps * NPAD;
       mbar_arrive_expect_tx(wbar, wrows * 128);
       for (int r0 = 0; r0 < wrows; r0 += NPAD) tma_load_2d(wsm + r0 * 128, &tmW, wbar, 0, r0);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int n = tile / tiles_per_img, t2 = tile - n * tiles_per_img;
-        const int y0 = (t2 / p.tiles_x) * TY, x0 = (t2 % p.tiles_x) * TX;
-        if (!mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1, p.err, 21)) break;
+    }
+    __syncwarp();
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int n = tile / tiles_per_img, t2 = tile - n * tiles_per_img;
+      const int y0 = (t2 / p.tiles_x) * TY, x0 = (t2 % p.tiles_x) * TX;
+      if (!mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1, p.err, 21)) break;
+      if (elect_one()) {
         const uint32_t fb = smem_u32(&bars->full[s]);
         mbar_arrive_expect_tx(fb, p.box_w * p.box_h * 128);
         tma_load_4d(hsm + s * p.stage_bytes, &tmX, fb, 0, x0 - p.pad, y0 - p.pad, n);
-        if (++s == S) { s = 0; ph ^= 1; }
       }
+      __syncwarp();
+      if (++s == S) { s = 0; ph ^= 1; }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, 16, 0, 0);
-      bool ok = mbar_wait(smem_u32(&bars->wfull), 0, p.err, 22);
-      int s = 0, it = 0;
-      uint32_t ph = 0;
-      const uint32_t sbo = p.box_w * 128;
-      for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        ok = mbar_wait(smem_u32(&bars->tempty[acc]), ((it >> 1) & 1) ^ 1, p.err, 23);
-        if (!ok) break;
-        ok = mbar_wait(smem_u32(&bars->full[s]), ph, p.err, 24);
-        if (!ok) break;
-        tc_fence_after();
-        const uint32_t halo = hsm + s * p.stage_bytes, d_tmem = tmem_base + acc * 16;
-        int tap = 0;
-        for (int r = 0; r < p.K; ++r)
-          for (int c = 0; c < p.K; ++c, ++tap) {
-            const uint32_t a0 = halo + (r * p.box_w + c) * 128, b0 = wsm + tap * (NPAD * 128);
+    // MMA issuer: whole warp, one elected lane issues
+    constexpr uint32_t idesc = make_idesc_bf16(128, 16, 0, 0);
+    const uint32_t sbo = p.box_w * 128;
+    const uint64_t a_hi = make_smem_desc(0, 16, sbo, kLayoutSW128, 0) & 0xFFFFFFFF00000000ull;
+    const uint64_t b_hi = make_smem_desc(0, 16, 1024, kLayoutSW128, 0) & 0xFFFFFFFF00000000ull;
+    const uint32_t lo_base = (uint32_t)(make_smem_desc(0, 16, 1024, kLayoutSW128, 0) & 0xFFFFFFFFull);
+    const uint32_t w_lo = lo_base + (wsm >> 4);
+    bool ok = mbar_wait(smem_u32(&bars->wfull), 0, p.err, 22);
+    int s = 0, it = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      ok = mbar_wait(smem_u32(&bars->tempty[acc]), ((it >> 1) & 1) ^ 1, p.err, 23);
+      if (!ok) break;
+      ok = mbar_wait(smem_u32(&bars->full[s]), ph, p.err, 24);
+      if (!ok) break;
+      tc_fence_after();
+      const uint32_t halo_lo = lo_base + ((hsm + s * p.stage_bytes) >> 4), d_tmem = tmem_base + acc * 16;
+      if (elect_one()) {
+        uint32_t row_lo = halo_lo, b_lo = w_lo;
+        for (int r = 0; r < p.K; ++r, row_lo += p.box_w * 8) {
+          uint32_t a_lo = row_lo;
+          for (int c = 0; c < p.K; ++c, a_lo += 8, b_lo += NPAD * 128 / 16) {
 #pragma unroll
             for (int ks = 0; ks < KC / 16; ++ks)
-              umma_bf16(d_tmem, make_smem_desc(a0 + ks * 32, 16, sbo, kLayoutSW128, 0),
-                        make_smem_desc(b0 + ks * 32, 16, 1024, kLayoutSW128, 0), idesc, (tap | ks) != 0);
+              umma_bf16(d_tmem, a_hi | (a_lo + 2 * ks), b_hi | (b_lo + 2 * ks), idesc, (r | c | ks) != 0);
           }
+        }
         umma_commit(smem_u32(&bars->empty[s]));
         umma_commit(smem_u32(&bars->tfull[acc]));
-        if (++s == S) { s = 0; ph ^= 1; }
       }
+      __syncwarp();
+      if (++s == S) { s = 0; ph ^= 1; }
     }
-    __syncwarp();
   } else {
     const int lg = warp & 3;
     const int i = lg * 32 + lane, ty = i >> 3, tx = i & 7;

@@ -8,10 +8,11 @@
 // of a tap is the same [rows][64ch] matrix shifted by d(tap) rows.  Border pixels compute garbage that the
 // epilogue replaces by zeros (which keeps the zero-border invariant without a second pass).
 //
-// One persistent CTA per SM, 192 threads:
+// One persistent CTA per SM, 320 threads:
 //   warp 0   TMA producer  (A tiles / halo slabs -> smem ring, weights once)
 //   warp 1   MMA issuer    (one thread: tcgen05.mma M128 N64 K16, fp32 accumulators in TMEM, double buffered)
-//   warps 2-5 epilogue     (tcgen05.ld -> +bias, ReLU/PReLU, +residual, bf16 -> global, PixelShuffle remap)
+//   warps 2-9 epilogue     (tcgen05.ld -> +bias, ReLU/PReLU, BN statistics, +residual, bf16 -> global,
+//                           PixelShuffle remap); two warps share a TMEM lane group and split the 64 columns
 //
 // A-operand staging modes (runtime `mode`):
 //   0  one TMA load of [128 x 64ch] per tap (9 loads per tile; every MMA operand 1024-B aligned)
@@ -68,7 +69,7 @@ constexpr int TAPS = 9;
 constexpr int W_TILE_BYTES = NT * KC * 2;       // 8 KB per tap
 constexpr int A_TILE_BYTES = TM * KC * 2;       // 16 KB
 constexpr int SLAB_BOX_ROWS = 32;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;
 constexpr int MAX_STAGES = 8;
 
 struct TcConvParams {
@@ -86,13 +87,16 @@ struct TcConvParams {
   const __nv_bfloat16* residual;
   __nv_bfloat16* y;
   int Hp2, Wp2;        // padded sizes of the shuffled output
+  float* stats_sum;    // fused BatchNorm statistics: per-channel sum / sum of squares of the fp32
+  float* stats_sumsq;  // outputs over interior pixels (accumulated), or null
   int* err;
+  int dbg;             // bring-up knobs: 1 skip stores, 2 skip MMAs, 4 skip A loads
+  long long* trace;    // bring-up: per-tile clock64 stamps of CTA 0 ([6][32]) or null
 };
 
 struct __align__(8) TcBarriers {
   uint64_t full[MAX_STAGES], empty[MAX_STAGES], wfull, tfull[2], tempty[2];
   uint32_t tmem_base;
-  float bias[NT];
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -117,16 +121,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
     mbar_init(smem_u32(&bars->wfull), 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->tfull[i]), 1); mbar_init(smem_u32(&bars->tempty[i]), 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->tfull[i]), 1); mbar_init(smem_u32(&bars->tempty[i]), 256); }
     fence_barrier_init();
   }
   if (warp == 1) {
     tmem_alloc(smem_u32(&bars->tmem_base), 128);
     tmem_relinquish();
-  }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + NT) {
-    int c = threadIdx.x - 64;
-    bars->bias[c] = p.bias ? p.bias[p.bias_off + c * p.bias_stride] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -135,168 +135,228 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
+    // The whole warp runs the loop (warp-uniform control flow keeps addresses / coordinates in uniform
+    // registers); one elected lane issues the TMA instructions.
+    if (elect_one()) {
       prefetch_tmap(&tmA);
       prefetch_tmap(&tmW);
       const uint32_t wbar = smem_u32(&bars->wfull);
       mbar_arrive_expect_tx(wbar, TAPS * W_TILE_BYTES);
       for (int t = 0; t < TAPS; ++t)
         tma_load_2d(wsm + t * W_TILE_BYTES, &tmW, wbar, p.k_col0, t * p.w_row_per_tap + p.w_row0);
-      int s = 0;
-      uint32_t ph = 0;
-      bool ok = true;
-      for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
-        const int m0 = tile * TM;
-        if (p.mode == 0) {
-          for (int t = 0; t < TAPS && ok; ++t) {
-            ok = mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1, p.err, 1);
-            if (!ok) break;
+    }
+    __syncwarp();
+    int s = 0;
+    uint32_t ph = 0;
+    bool ok = true;
+    for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
+      const int m0 = tile * TM;
+      if (p.mode == 0) {
+        for (int t = 0; t < TAPS && ok; ++t) {
+          ok = mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1, p.err, 1);
+          if (!ok) break;
+          if (elect_one()) {
             const uint32_t fb = smem_u32(&bars->full[s]);
             mbar_arrive_expect_tx(fb, A_TILE_BYTES);
             const int d = (t / 3 - 1) * p.Wp + (t % 3 - 1);
             tma_load_2d(asm0 + s * p.stage_bytes, &tmA, fb, p.k_col0, m0 + d);
-            if (++s == S) { s = 0; ph ^= 1; }
           }
-        } else {
-          ok = mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1, p.err, 1);
-          if (!ok) break;
-          const uint32_t fb = smem_u32(&bars->full[s]);
-          mbar_arrive_expect_tx(fb, p.slab_rows * KC * 2);
-          const int row0 = m0 - p.Wp - 1;
-          for (int j = 0; j < p.slab_rows / SLAB_BOX_ROWS; ++j)
-            tma_load_2d(asm0 + s * p.stage_bytes + j * SLAB_BOX_ROWS * KC * 2, &tmA, fb, p.k_col0,
-                        row0 + j * SLAB_BOX_ROWS);
+          __syncwarp();
           if (++s == S) { s = 0; ph ^= 1; }
         }
+      } else {
+        ok = mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1, p.err, 1);
+        if (!ok) break;
+        if (elect_one()) {
+          const uint32_t fb = smem_u32(&bars->full[s]);
+          if (p.dbg & 4) {
+            mbar_arrive(fb);
+          } else {
+            mbar_arrive_expect_tx(fb, p.slab_rows * KC * 2);
+            const int row0 = m0 - p.Wp - 1;
+            for (int j = 0; j < p.slab_rows / SLAB_BOX_ROWS; ++j)
+              tma_load_2d(asm0 + s * p.stage_bytes + j * SLAB_BOX_ROWS * KC * 2, &tmA, fb, p.k_col0,
+                          row0 + j * SLAB_BOX_ROWS);
+          }
+          if (p.trace && blockIdx.x == 0 && tile / (int)gridDim.x < 32) p.trace[0 * 32 + tile / gridDim.x] = clock64();
+        }
+        __syncwarp();
+        if (++s == S) { s = 0; ph ^= 1; }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(TM, NT, 0, 0);
-      bool ok = mbar_wait(smem_u32(&bars->wfull), 0, p.err, 2);
-      int s = 0, it = 0;
-      uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        ok = mbar_wait(smem_u32(&bars->tempty[acc]), ((it >> 1) & 1) ^ 1, p.err, 3);
-        if (!ok) break;
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * NT;
-        if (p.mode == 0) {
-          for (int t = 0; t < TAPS && ok; ++t) {
-            ok = mbar_wait(smem_u32(&bars->full[s]), ph, p.err, 4);
-            if (!ok) break;
-            tc_fence_after();
-            const uint32_t a0 = asm0 + s * p.stage_bytes, b0 = wsm + t * W_TILE_BYTES;
-#pragma unroll
-            for (int ks = 0; ks < KC / 16; ++ks)
-              umma_bf16(d_tmem, make_smem_desc(a0 + ks * 32, 16, 1024, kLayoutSW128, 0),
-                        make_smem_desc(b0 + ks * 32, 16, 1024, kLayoutSW128, 0), idesc, (t | ks) != 0);
-            umma_commit(smem_u32(&bars->empty[s]));
-            if (++s == S) { s = 0; ph ^= 1; }
-          }
-        } else {
+    // Whole warp, warp-uniform; tcgen05.mma / commit are issued by one elected lane.  Descriptors are built
+    // once: the upper word (SBO 1024 B, version, SWIZZLE_128B) is constant, the lower word is
+    // (address >> 4) | (LBO >> 4) << 16, so stepping K by 16 elements (32 B) or moving to another tap / stage
+    // is a 32-bit add on the lower word.
+    constexpr uint32_t idesc = make_idesc_bf16(TM, NT, 0, 0);
+    const uint64_t desc_hi = make_smem_desc(0, 16, 1024, kLayoutSW128, 0) & 0xFFFFFFFF00000000ull;
+    const uint32_t lo_base = (uint32_t)(make_smem_desc(0, 16, 1024, kLayoutSW128, 0) & 0xFFFFFFFFull);
+    const uint32_t w_lo = lo_base + (wsm >> 4), a_lo0 = lo_base + (asm0 >> 4);
+    const uint32_t row_units = (uint32_t)p.Wp * (KC * 2 / 16);   // one image row of the slab, in 16-byte units
+    const uint32_t stage_units = (uint32_t)p.stage_bytes >> 4;
+    bool ok = mbar_wait(smem_u32(&bars->wfull), 0, p.err, 2);
+    int s = 0, it = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      ok = mbar_wait(smem_u32(&bars->tempty[acc]), ((it >> 1) & 1) ^ 1, p.err, 3);
+      if (!ok) break;
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * NT;
+      if (p.mode == 0) {
+#pragma unroll 1
+        for (int t = 0; t < TAPS; ++t) {
           ok = mbar_wait(smem_u32(&bars->full[s]), ph, p.err, 4);
           if (!ok) break;
           tc_fence_after();
-          const uint32_t slab = asm0 + s * p.stage_bytes;
-          for (int t = 0; t < TAPS; ++t) {
-            const uint32_t a0 = slab + ((t / 3) * p.Wp + (t % 3)) * (KC * 2), b0 = wsm + t * W_TILE_BYTES;
-            const uint32_t bo = p.mode == 2 ? ((a0 >> 7) & 7) : 0;
+          const uint32_t a_lo = a_lo0 + s * stage_units, b_lo = w_lo + t * (W_TILE_BYTES / 16);
+          if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < KC / 16; ++ks)
-              umma_bf16(d_tmem, make_smem_desc(a0 + ks * 32, 16, 1024, kLayoutSW128, bo),
-                        make_smem_desc(b0 + ks * 32, 16, 1024, kLayoutSW128, 0), idesc, (t | ks) != 0);
+              umma_bf16(d_tmem, desc_hi | (a_lo + 2 * ks), desc_hi | (b_lo + 2 * ks), idesc, (t | ks) != 0);
+            umma_commit(smem_u32(&bars->empty[s]));
           }
-          umma_commit(smem_u32(&bars->empty[s]));
+          __syncwarp();
           if (++s == S) { s = 0; ph ^= 1; }
         }
-        if (ok) umma_commit(smem_u32(&bars->tfull[acc]));
+        if (!ok) break;
+      } else {
+        ok = mbar_wait(smem_u32(&bars->full[s]), ph, p.err, 4);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t a_lo = a_lo0 + s * stage_units;
+        if (elect_one()) {
+          if (p.trace && blockIdx.x == 0 && it < 32) p.trace[1 * 32 + it] = clock64();
+          if (!(p.dbg & 2)) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+              for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int ks = 0; ks < KC / 16; ++ks)
+                  umma_bf16(d_tmem, desc_hi | (a_lo + r * row_units + c * (KC * 2 / 16) + 2 * ks),
+                            desc_hi | (w_lo + (r * 3 + c) * (W_TILE_BYTES / 16) + 2 * ks), idesc, (r | c | ks) != 0);
+          }
+          umma_commit(smem_u32(&bars->empty[s]));
+        }
+        __syncwarp();
+        if (++s == S) { s = 0; ph ^= 1; }
       }
+      if (elect_one()) {
+        umma_commit(smem_u32(&bars->tfull[acc]));
+        if (p.trace && blockIdx.x == 0 && it < 32) p.trace[2 * 32 + it] = clock64();
+      }
+      __syncwarp();
     }
-    __syncwarp();
   } else {
-    // ================= epilogue =================
-    const int lg = warp & 3;  // TMEM lane group this warp may access
-    const float alpha = (p.act == SRK_ACT_PRELU) ? p.alpha[0] : 0.f;
+    // ================= epilogue: 8 warps, warp e owns TMEM lanes 32*(e&3).. and 32 of the 64 columns ====
+    const int e = warp - 2, lg = warp & 3, ch = e >> 2;   // warps 2..9 -> lane groups 2,3,0,1,2,3,0,1
+    const int c0 = ch * 32;                                // first accumulator column of this thread
+    const float alpha = (p.act == SRK_ACT_PRELU) ? __ldg(p.alpha) : 0.f;
     const int img = p.Hp * p.Wp;
+    float bias[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) bias[j] = p.bias ? __ldg(p.bias + p.bias_off + c0 + j) : 0.f;
+    float s1[32], s2[32];
+    if (p.stats_sum) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+    }
     bool ok = true;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++it) {
       const int acc = it & 1;
+      const int pix = tile * TM + lg * 32 + lane;
+      const int pc = pix < p.P ? pix : 0;
+      const int n = pc / img, q = pc - n * img;
+      const int yy = q / p.Wp, xx = q - yy * p.Wp;
+      const bool interior = pix < p.P && yy >= 1 && yy <= p.Hp - 2 && xx >= 1 && xx <= p.Wp - 2;
+      // the residual does not depend on the accumulator: fetch it while the MMAs of this tile still run
+      uint4 rr[4];
+      if (p.residual && interior) {
+        const uint4* res = reinterpret_cast<const uint4*>(p.residual + (long long)pix * p.cout_total + p.cout_off + c0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rr[j] = __ldg(res + j);
+      }
       ok = mbar_wait(smem_u32(&bars->tfull[acc]), (it >> 1) & 1, p.err, 5);
       if (!ok) break;
       tc_fence_after();
-      uint32_t v[NT];
-      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * NT;
-      tmem_ld_32x32(taddr, v);
-      tmem_ld_32x32(taddr + 32, v + 32);
+      const bool tr = p.trace && blockIdx.x == 0 && it < 32 && threadIdx.x == 64;
+      if (tr) p.trace[3 * 32 + it] = clock64();
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * NT + c0, v);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(smem_u32(&bars->tempty[acc]));
-
-      const int pix = tile * TM + lg * 32 + lane;
+      if (tr) p.trace[4 * 32 + it] = clock64();
       if (pix >= p.P) continue;
-      const int n = pix / img, q = pix - n * img;
-      const int yy = q / p.Wp, xx = q - yy * p.Wp;
-      const bool interior = yy >= 1 && yy <= p.Hp - 2 && xx >= 1 && xx <= p.Wp - 2;
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float a = __uint_as_float(v[j]) + bias[j];
+        if (p.act == SRK_ACT_RELU) a = fmaxf(a, 0.f);
+        else if (p.act == SRK_ACT_PRELU) a = a > 0.f ? a : alpha * a;
+        f[j] = a;
+      }
       if (p.shuffle == 2) {
         // PixelShuffle(2) as a store remap (models.py:118,121): column j of this pass is reference channel
-        // co = cout_off + j = 4c + sub  ->  output pixel (2y + sub/2, 2x + sub%2), channel c.
+        // co = cout_off + c0 + j = 4c + sub  ->  output pixel (2y + sub/2, 2x + sub%2), channel c.
         if (!interior) continue;
-#pragma unroll
-        for (int j = 0; j < NT; ++j) {
-          float a = __uint_as_float(v[j]) + bars->bias[j];
-          if (p.act == SRK_ACT_RELU) a = fmaxf(a, 0.f);
-          else if (p.act == SRK_ACT_PRELU) a = a > 0.f ? a : alpha * a;
-          v[j] = __float_as_uint(a);
-        }
 #pragma unroll
         for (int sub = 0; sub < 4; ++sub) {
           const long long orow =
               ((long long)n * p.Hp2 + (2 * (yy - 1) + (sub >> 1) + 1)) * p.Wp2 + (2 * (xx - 1) + (sub & 1) + 1);
-          uint4* dst = reinterpret_cast<uint4*>(p.y + orow * p.cout_total + p.cout_off / 4);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int c0 = h * 8;
-            dst[h] = make_uint4(
-                pack_bf16x2(__uint_as_float(v[4 * (c0 + 0) + sub]), __uint_as_float(v[4 * (c0 + 1) + sub])),
-                pack_bf16x2(__uint_as_float(v[4 * (c0 + 2) + sub]), __uint_as_float(v[4 * (c0 + 3) + sub])),
-                pack_bf16x2(__uint_as_float(v[4 * (c0 + 4) + sub]), __uint_as_float(v[4 * (c0 + 5) + sub])),
-                pack_bf16x2(__uint_as_float(v[4 * (c0 + 6) + sub]), __uint_as_float(v[4 * (c0 + 7) + sub])));
-          }
+          uint4* dst = reinterpret_cast<uint4*>(p.y + orow * p.cout_total + (p.cout_off + c0) / 4);
+          dst[0] = make_uint4(pack_bf16x2(f[sub], f[4 + sub]), pack_bf16x2(f[8 + sub], f[12 + sub]),
+                              pack_bf16x2(f[16 + sub], f[20 + sub]), pack_bf16x2(f[24 + sub], f[28 + sub]));
         }
         continue;
       }
-      uint4* dst = reinterpret_cast<uint4*>(p.y + (long long)pix * p.cout_total + p.cout_off);
+      uint4* dst = reinterpret_cast<uint4*>(p.y + (long long)pix * p.cout_total + p.cout_off + c0);
+      if ((p.dbg & 1) && f[0] != 12345.f) continue;
       if (!interior) {
 #pragma unroll
-        for (int j = 0; j < NT / 8; ++j) dst[j] = make_uint4(0, 0, 0, 0);
+        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(0, 0, 0, 0);
         continue;
       }
-      const uint4* res =
-          p.residual ? reinterpret_cast<const uint4*>(p.residual + (long long)pix * p.cout_total + p.cout_off) : nullptr;
+      if (p.stats_sum) {
 #pragma unroll
-      for (int j = 0; j < NT / 8; ++j) {
-        float f[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float a = __uint_as_float(v[j * 8 + e]) + bars->bias[j * 8 + e];
-          if (p.act == SRK_ACT_RELU) a = fmaxf(a, 0.f);
-          else if (p.act == SRK_ACT_PRELU) a = a > 0.f ? a : alpha * a;
-          f[e] = a;
-        }
-        if (res) {
-          uint4 r = res[j];
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) { float2 t = __bfloat1622float2(h[e]); f[2 * e] += t.x; f[2 * e + 1] += t.y; }
-        }
-        dst[j] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                            pack_bf16x2(f[6], f[7]));
+        for (int j = 0; j < 32; ++j) { s1[j] += f[j]; s2[j] = fmaf(f[j], f[j], s2[j]); }
       }
+      if (p.residual) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) { float2 u = __bfloat1622float2(h[t]); f[8 * j + 2 * t] += u.x; f[8 * j + 2 * t + 1] += u.y; }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        dst[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                            pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+      if (tr) p.trace[5 * 32 + it] = clock64();
+    }
+    if (p.stats_sum) {
+      // per-thread partial sums over this CTA's pixels -> per-channel totals: transposed butterfly (lane l
+      // ends up owning column l), then one atomic per lane
+#pragma unroll
+      for (int half = 16; half >= 1; half >>= 1) {
+        const bool up = (lane & half) != 0;
+#pragma unroll
+        for (int j = 0; j < half; ++j) {
+          // keep column block [j] if !up, [j + half] if up; send the other one to the partner lane
+          float k1 = up ? s1[j + half] : s1[j], o1 = up ? s1[j] : s1[j + half];
+          float k2 = up ? s2[j + half] : s2[j], o2 = up ? s2[j] : s2[j + half];
+          s1[j] = k1 + __shfl_xor_sync(0xffffffffu, o1, half);
+          s2[j] = k2 + __shfl_xor_sync(0xffffffffu, o2, half);
+        }
+      }
+      // after the butterfly lane l holds the total of column bitrev-free index: col = sum over steps of (lane & half)
+      atomicAdd(p.stats_sum + p.cout_off + c0 + lane, s1[0]);
+      atomicAdd(p.stats_sumsq + p.cout_off + c0 + lane, s2[0]);
     }
   }
   tc_fence_before();
@@ -309,6 +369,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 // ---- host launcher ---------------------------------------------------------------------------------------
 static int g_tc_mode = -1;
+static long long* g_tc_trace = nullptr;
+void tc_set_trace(long long* t) { g_tc_trace = t; }
 int tc_mode() {
   if (g_tc_mode < 0) {
     const char* e = getenv("SRK_TC_MODE");
@@ -353,7 +415,7 @@ bool conv_tc_shape_ok(int cin, int cout, int r, int s, int dtype, int shuffle) {
 
 int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout, int r, int s,
                          const float* bias, int act, const float* alpha, const srk_tensor* residual, int shuffle,
-                         cudaStream_t st) {
+                         float* stats_sum, float* stats_sumsq, cudaStream_t st) {
   const int cin = x->c;
   const int Hp = x->h + 2, Wp = x->w + 2;
   const long long P = (long long)x->n * Hp * Wp;
@@ -398,7 +460,12 @@ int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w
   p.shuffle = shuffle;
   p.Hp2 = y->h + 2; p.Wp2 = y->w + 2;
   p.err = tc_err_flag();
+  { const char* e = getenv("SRK_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
+  p.trace = g_tc_trace;
+  p.stats_sum = stats_sum; p.stats_sumsq = stats_sumsq;
   const int nchunks = cout / NT, kchunks = cin / KC;
+  SRK_REQUIRE(stats_sum == nullptr || (kchunks == 1 && shuffle == 0 && act == SRK_ACT_NONE && residual == nullptr),
+              "conv_tc: fused BN statistics need a plain Cin == 64 conv");
   int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
   for (int nc = 0; nc < nchunks; ++nc) {
     for (int kc = 0; kc < kchunks; ++kc) {
@@ -428,11 +495,34 @@ int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w
 
 }  // namespace srk
 
+namespace srk { int probe_mma_rate(int n, int a_row_off, int mn_major, float* out_host); }
+
 // Test / bring-up hook: variant 0..2 selects the A-staging mode of the tcgen05 conv (see the header
 // comment); any other value leaves it unchanged.  out_host[0] = the device-side protocol-error flag
 // (0 = none; it is cleared by the call), out_host[1] = the mode now in effect.  Synchronises the device.
 extern "C" int srk_tc_probe(int variant, float* out_host, int out_len) {
   if (variant >= 0 && variant <= 2) srk::tc_set_mode(variant);
+  if (variant >= 1000 && out_host && out_len >= 2) {
+    // 1000 + n/8 + 100 * a_row_off + 10000 * mn_major: sustained MMA rate microbenchmark
+    int v = variant - 1000;
+    return srk::probe_mma_rate((v % 100) * 8, (v / 100) % 100, v / 10000, out_host);
+  }
+  static long long* trace = nullptr;
+  if (variant == 100) {
+    if (!trace) cudaMalloc(&trace, 6 * 32 * sizeof(long long));
+    cudaMemset(trace, 0, 6 * 32 * sizeof(long long));
+    srk::tc_set_trace(trace);
+  }
+  if (variant == 101 && trace && out_host && out_len >= 6 * 32) {
+    long long h[6 * 32];
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost);
+    long long mn = 0;
+    for (int i = 0; i < 6 * 32; ++i) if (h[i] && (mn == 0 || h[i] < mn)) mn = h[i];
+    for (int i = 0; i < 6 * 32; ++i) out_host[i] = h[i] ? (float)(h[i] - mn) : -1.f;
+    srk::tc_set_trace(nullptr);
+    return 0;
+  }
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) SRK_FAIL("srk_tc_probe: device error: %s", cudaGetErrorString(e));
   int flag = srk::tc_read_err_flag();

@@ -340,6 +340,43 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 
+// Multi-tensor Adam: one launch updates up to ADAM_MT tensors; the pointer table travels by value in the
+// kernel parameters (so the launch is CUDA-graph capturable without a host-side table upload).
+constexpr int ADAM_MT = 48;
+struct AdamTable {
+  float* p[ADAM_MT];
+  const float* g[ADAM_MT];
+  float* m[ADAM_MT];
+  float* v[ADAM_MT];
+  int n[ADAM_MT];
+};
+__global__ void __launch_bounds__(256) adam_multi_kernel(const AdamTable tb, float lr, float b1, float b2, float eps,
+    const long long* __restrict__ step, float grad_scale) {
+  const int t = blockIdx.y;
+  const int n = tb.n[t];
+  const int i0 = blockIdx.x * 1024;
+  if (i0 >= n) return;
+  const double tt = (double)step[0];
+  const float bc1 = (float)(1.0 - pow((double)b1, tt));
+  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, tt));
+  const float step_size = lr / bc1;
+  float* __restrict__ p = tb.p[t];
+  const float* __restrict__ g = tb.g[t];
+  float* __restrict__ m = tb.m[t];
+  float* __restrict__ v = tb.v[t];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = i0 + k * 256 + threadIdx.x;
+    if (i < n) {
+      float gi = g[i] * grad_scale;
+      float mi = m[i] + (1.f - b1) * (gi - m[i]);
+      float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+      m[i] = mi; v[i] = vi;
+      p[i] -= step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+    }
+  }
+}
+
 }  // namespace srk
 
 using namespace srk;
@@ -470,5 +507,31 @@ extern "C" int srk_adam_step(float* param, const float* grad, float* exp_avg, fl
   SRK_REQUIRE(numel > 0, "srk_adam_step: empty parameter buffer");
   adam_kernel<<<red_blocks(numel, 4), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps, (const long long*)step_count, grad_scale);
   SRK_CUDA_LAUNCH_CHECK("adam");
+  return 0;
+}
+
+extern "C" int srk_adam_multi(int count, float* const* params, const float* const* grads, float* const* exp_avg,
+                              float* const* exp_avg_sq, const int64_t* numel, float lr, float beta1, float beta2,
+                              float eps, const int64_t* step_count, float grad_scale, void* stream) {
+  SRK_REQUIRE(count >= 0, "srk_adam_multi: negative count");
+  for (int base = 0; base < count; base += ADAM_MT) {
+    AdamTable tb;
+    const int c = count - base < ADAM_MT ? count - base : ADAM_MT;
+    int64_t mx = 0;
+    for (int i = 0; i < ADAM_MT; ++i) {
+      if (i < c) {
+        SRK_REQUIRE(numel[base + i] > 0 && numel[base + i] < (1LL << 31), "srk_adam_multi: bad tensor size");
+        tb.p[i] = params[base + i]; tb.g[i] = grads[base + i]; tb.m[i] = exp_avg[base + i];
+        tb.v[i] = exp_avg_sq[base + i]; tb.n[i] = (int)numel[base + i];
+        if (numel[base + i] > mx) mx = numel[base + i];
+      } else {
+        tb.p[i] = nullptr; tb.g[i] = nullptr; tb.m[i] = nullptr; tb.v[i] = nullptr; tb.n[i] = 0;
+      }
+    }
+    dim3 grid((unsigned)((mx + 1023) / 1024), (unsigned)c);
+    adam_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tb, lr, beta1, beta2, eps, (const long long*)step_count,
+                                                              grad_scale);
+    SRK_CUDA_LAUNCH_CHECK("adam_multi");
+  }
   return 0;
 }

@@ -72,14 +72,15 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   const int my_tiles = blockIdx.x < p.num_tiles ? (p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (warp == 0) {
-    if (lane == 0) {
-      prefetch_tmap(&tmX);
-      prefetch_tmap(&tmDz);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int i = 0; i < my_tiles; ++i) {
-        const int m0 = (blockIdx.x + i * gridDim.x) * TM;
-        if (!mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1, p.err, 11)) break;
+    // TMA producer: whole warp (warp-uniform control flow), one elected lane issues
+    if (elect_one()) { prefetch_tmap(&tmX); prefetch_tmap(&tmDz); }
+    __syncwarp();
+    int s = 0;
+    uint32_t ph = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int m0 = (blockIdx.x + i * gridDim.x) * TM;
+      if (!mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1, p.err, 11)) break;
+      if (elect_one()) {
         const uint32_t fb = smem_u32(&bars->full[s]);
         const uint32_t st0 = smem_base + s * p.stage_bytes;
         mbar_arrive_expect_tx(fb, slab_bytes + DZ_TILE_BYTES);
@@ -87,38 +88,43 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         for (int j = 0; j < p.slab_rows / SLAB_BOX_ROWS; ++j)
           tma_load_2d(st0 + j * SLAB_BOX_ROWS * KC * 2, &tmX, fb, p.x_col0, row0 + j * SLAB_BOX_ROWS);
         tma_load_2d(st0 + slab_bytes, &tmDz, fb, p.dz_col0, m0);
-        if (++s == S) { s = 0; ph ^= 1; }
       }
+      __syncwarp();
+      if (++s == S) { s = 0; ph ^= 1; }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, NT, 1, 1);
-      int s = 0;
-      uint32_t ph = 0;
-      bool ok = true;
-      for (int i = 0; i < my_tiles && ok; ++i) {
-        ok = mbar_wait(smem_u32(&bars->full[s]), ph, p.err, 12);
-        if (!ok) break;
-        tc_fence_after();
-        const uint32_t slab = smem_base + s * p.stage_bytes, dz = slab + slab_bytes;
+    // MMA issuer: whole warp, one elected lane issues tcgen05.mma / commit
+    constexpr uint32_t idesc = make_idesc_bf16(128, NT, 1, 1);
+    // constant descriptor halves (see srk_conv_tc.cu): per MMA only the lower words are advanced
+    const uint64_t hi = make_smem_desc(0, 0, 1024, kLayoutSW128, 0) & 0xFFFFFFFF00000000ull;
+    const uint32_t lo_base = (uint32_t)(make_smem_desc(0, 0, 1024, kLayoutSW128, 0) & 0xFFFFFFFFull);
+    const uint32_t wp_u = (uint32_t)p.Wp * (KC * 2 / 16), px_u = KC * 2 / 16;  // image row / pixel in 16-B units
+    // tap pairs (0,1) (2,3) (4,5) (6,7) (8,8): start offset of the first tap | (distance to the second) << 16
+    const uint32_t a_off[NACC] = {0u + (px_u << 16), 2 * px_u + ((wp_u - 2 * px_u) << 16),
+                                  wp_u + px_u + (px_u << 16), 2 * wp_u + (px_u << 16), 2 * wp_u + 2 * px_u};
+    int s = 0;
+    uint32_t ph = 0;
+    bool ok = true;
+    for (int i = 0; i < my_tiles && ok; ++i) {
+      ok = mbar_wait(smem_u32(&bars->full[s]), ph, p.err, 12);
+      if (!ok) break;
+      tc_fence_after();
+      const uint32_t slab_lo = lo_base + ((smem_base + s * p.stage_bytes) >> 4);
+      const uint32_t dz_lo = slab_lo + (slab_bytes >> 4);
+      if (elect_one()) {
 #pragma unroll
         for (int a = 0; a < NACC; ++a) {
-          const int t1 = 2 * a, t2 = a == NACC - 1 ? 2 * a : 2 * a + 1;
-          const int d1 = (t1 / 3) * p.Wp + t1 % 3, d2 = (t2 / 3) * p.Wp + t2 % 3;
-          const uint32_t lbo = (uint32_t)(d2 - d1) * (KC * 2);
 #pragma unroll
-          for (int ks = 0; ks < TM / 16; ++ks) {
-            const uint64_t adesc = make_smem_desc(slab + (d1 + ks * 16) * (KC * 2), lbo, 1024, kLayoutSW128, 0);
-            const uint64_t bdesc = make_smem_desc(dz + ks * 16 * (NT * 2), 0, 1024, kLayoutSW128, 0);
-            umma_bf16(tmem_base + a * NT, adesc, bdesc, idesc, (i | ks) != 0);
-          }
+          for (int ks = 0; ks < TM / 16; ++ks)
+            umma_bf16(tmem_base + a * NT, hi | (slab_lo + a_off[a] + ks * (16 * KC * 2 / 16)),
+                      hi | (dz_lo + ks * (16 * NT * 2 / 16)), idesc, (i | ks) != 0);
         }
         umma_commit(smem_u32(&bars->empty[s]));
-        if (++s == S) { s = 0; ph ^= 1; }
       }
-      umma_commit(smem_u32(&bars->done));
+      __syncwarp();
+      if (++s == S) { s = 0; ph ^= 1; }
     }
+    if (elect_one()) umma_commit(smem_u32(&bars->done));
     __syncwarp();
   } else {
     // ---- epilogue warps: bias-gradient partial sums while the MMAs run, then the accumulator flush ----

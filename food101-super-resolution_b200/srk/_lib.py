@@ -32,7 +32,7 @@ SIGNATURES = {
     "srk_last_error": (c_char_p, []),
     "srk_version": (c_int, []),
     "srk_conv_tc_supported": (c_int, [c_int] * 6),
-    "srk_conv_fprop": (c_int, [_T, _T, _P, c_int, c_int, c_int, c_int, _P, c_int, _P, _T, c_int, c_int, _P]),
+    "srk_conv_fprop": (c_int, [_T, _T, _P, c_int, c_int, c_int, c_int, _P, c_int, _P, _T, c_int, c_int, _P, _P, _P]),
     "srk_conv_wgrad": (c_int, [_T, _T, _P, _P, c_int, c_int, c_int, _P, _P]),
     "srk_conv_wgrad_workspace_bytes": (c_int64, [_T, _T, c_int, c_int, c_int]),
     "srk_conv_rgb_workspace_bytes": (c_int64, [c_int]),
@@ -65,6 +65,7 @@ SIGNATURES = {
     "srk_psnr_sse": (c_int, [_P, _P, c_int, c_int64, c_int, _P, _P]),
     "srk_ssim": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "srk_adam_step": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, _P, c_float, _P]),
+    "srk_adam_multi": (c_int, [c_int, _P, _P, _P, _P, _P, c_float, c_float, c_float, c_float, _P, c_float, _P]),
     "srk_tc_probe": (c_int, [c_int, POINTER(c_float), c_int]),
 }
 

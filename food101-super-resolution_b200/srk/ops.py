@@ -214,8 +214,9 @@ def rgbout_bwd_supported(x, x_img, dz_img, weight):
     return (not x_img) and dz_img and cin == 64 and cout == 3 and x.dtype == torch.bfloat16 and _rgb_tc_ok(r, s)
 
 
-def conv_fprop(x, x_img, weight, bias, act, alpha, residual, shuffle, out_img, out_dtype):
-    """y = [shuffle](act(conv(x, weight) + bias)) [+ residual]; stride 1, pad R//2."""
+def conv_fprop(x, x_img, weight, bias, act, alpha, residual, shuffle, out_img, out_dtype, bn_sums=None):
+    """y = [shuffle](act(conv(x, weight) + bias)) [+ residual]; stride 1, pad R//2.
+    bn_sums: optional zero-filled fp32 [2, Cout] that receives the per-channel sum / sum of squares of y."""
     n, cin, h, w = geometry(x, x_img)
     cout, wcin, r, s = weight.shape
     assert wcin == cin, "conv: input has %d channels, weight expects %d" % (cin, wcin)
@@ -241,7 +242,9 @@ def conv_fprop(x, x_img, weight, bias, act, alpha, residual, shuffle, out_img, o
     rd = desc(residual, out_img) if residual is not None else None
     _timed(("conv_fprop", cin, cout, r, shuffle, n, h, w, use_tc),
            lambda: L.call("srk_conv_fprop", xd, yd, pk.data_ptr(), kind, cout, r, s, _ptr(bias), act,
-                          _ptr(alpha), rd, shuffle, L.IMPL_AUTO, stream_ptr()))
+                          _ptr(alpha), rd, shuffle, L.IMPL_AUTO,
+                          bn_sums[0].data_ptr() if bn_sums is not None else None,
+                          bn_sums[1].data_ptr() if bn_sums is not None else None, stream_ptr()))
     return y, use_tc
 
 
@@ -259,7 +262,7 @@ def conv_dgrad(dz, dz_img, weight, residual, out_dtype, perm_tc=False):
     rd = act_desc(residual) if residual is not None else None
     _timed(("conv_dgrad", cout, cin, r, 0, n, h, w, use_tc),
            lambda: L.call("srk_conv_fprop", desc(dz, dz_img), act_desc(dx), pk.data_ptr(), kind, cin, r, s,
-                          None, L.ACT_NONE, None, rd, 0, L.IMPL_AUTO, stream_ptr()))
+                          None, L.ACT_NONE, None, rd, 0, L.IMPL_AUTO, None, None, stream_ptr()))
     return dx
 
 
@@ -301,16 +304,22 @@ def act_bwd(dout, out, act, alpha, unshuffle, perm_tc=False):
 
 
 # ---- batch norm ------------------------------------------------------------------------------------
-def bn_forward(y, gamma, beta, running_mean, running_var, nbt, training, eps, momentum, alpha, residual):
-    """out = [PReLU](BN(y)) [+ residual]; returns (out, mean, invstd)."""
+def bn_needs_batch_stats(running_mean, training):
+    return training or running_mean is None
+
+
+def bn_forward(y, gamma, beta, running_mean, running_var, nbt, training, eps, momentum, alpha, residual, sums=None):
+    """out = [PReLU](BN(y)) [+ residual]; returns (out, stats[2, C] = mean, invstd).
+    sums: per-channel (sum, sum of squares) of y when the producing conv already accumulated them."""
     n, c, h, w = geometry(y, False)
     dev = y.device
     stats = torch.empty((2, c), dtype=torch.float32, device=dev)
     mean, invstd = stats[0], stats[1]
     st = stream_ptr()
     if training or running_mean is None:
-        sums = torch.zeros((2, c), dtype=torch.float32, device=dev)
-        L.call("srk_bn_stats", act_desc(y), sums[0].data_ptr(), sums[1].data_ptr(), st)
+        if sums is None:
+            sums = torch.zeros((2, c), dtype=torch.float32, device=dev)
+            L.call("srk_bn_stats", act_desc(y), sums[0].data_ptr(), sums[1].data_ptr(), st)
         upd = training and running_mean is not None
         L.call("srk_bn_finalize", sums[0].data_ptr(), sums[1].data_ptr(), c, n * h * w, eps, momentum,
                _ptr(running_mean) if upd else None, _ptr(running_var) if upd else None,

@@ -32,14 +32,20 @@ class Adam:
 
     @torch.no_grad()
     def step(self, grad_scale=1.0):
+        import ctypes
         self.step_count += 1
         lr = float(self.param_groups[0]["lr"])
-        st = ops.stream_ptr()
-        for p, (m, v) in zip(self.params, self.state):
-            if p.grad is None:
-                continue
-            g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-            L.call("srk_adam_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr,
-                   self.betas[0], self.betas[1], self.eps, self.step_count.data_ptr(), float(grad_scale), st)
+        live = [(p, p.grad if p.grad.is_contiguous() else p.grad.contiguous(), m, v)
+                for p, (m, v) in zip(self.params, self.state) if p.grad is not None]
+        if not live:
+            return
+        n = len(live)
+        arr = lambda vals: (ctypes.c_void_p * n)(*vals)
+        self._keep = [g for _, g, _, _ in live]  # contiguous copies must outlive the launch
+        L.call("srk_adam_multi", n, arr([p.data_ptr() for p, _, _, _ in live]),
+               arr([g.data_ptr() for _, g, _, _ in live]), arr([m.data_ptr() for _, _, m, _ in live]),
+               arr([v.data_ptr() for _, _, _, v in live]), (ctypes.c_int64 * n)(*[p.numel() for p, _, _, _ in live]),
+               lr, self.betas[0], self.betas[1], self.eps, self.step_count.data_ptr(), float(grad_scale),
+               ops.stream_ptr())
         # the kernels wrote through raw pointers: invalidate the packed-weight cache
         ops.bump_weights_epoch()

@@ -70,10 +70,14 @@ int srk_conv_tc_supported(int cin, int cout, int r, int s, int dtype, int pixel_
  * +residual (models.py:185), PixelShuffle(2) store remap (models.py:118,121,160,163).
  * stride 1, "same" padding (pad = R/2), as every conv on the path.
  * `y` holds the output geometry; with pixel_shuffle=2, y is [N][Cout/4][2H][2W].
+ * bn_sum / bn_sumsq (fp32 [Cout], accumulated, both NULL or both set): per-channel sum and sum of squares of
+ * the conv output over interior pixels - the statistics native_batch_norm needs (models.py:47,50,114) -
+ * produced by the conv epilogue from the fp32 accumulators on the tcgen05 path.
  */
 int srk_conv_fprop(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int pack_kind,
                    int cout, int r, int s, const float* bias, int act, const float* alpha,
-                   const srk_tensor* residual, int pixel_shuffle, int impl, void* stream);
+                   const srk_tensor* residual, int pixel_shuffle, int impl, float* bn_sum,
+                   float* bn_sumsq, void* stream);
 
 /* dW (fp32, OIHW, ACCUMULATED into dw: caller zero-fills) and db (fp32 [Cout], accumulated, may be NULL).
  * x: conv input, dy: gradient w.r.t. the conv output (pre-activation, conv-output geometry).
@@ -195,6 +199,11 @@ int srk_ssim(const float* sr, const float* hr, int n, int c, int h, int w, int c
 int srk_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel,
                   float lr, float beta1, float beta2, float eps, const int64_t* step_count,
                   float grad_scale, void* stream);
+
+/* the same update for `count` tensors in ceil(count / 48) launches (host arrays of device pointers) */
+int srk_adam_multi(int count, float* const* params, const float* const* grads, float* const* exp_avg,
+                   float* const* exp_avg_sq, const int64_t* numel, float lr, float beta1, float beta2,
+                   float eps, const int64_t* step_count, float grad_scale, void* stream);
 
 /* ---- bring-up / self-test hooks (tests only) --------------------------------------------------- */
 /* Runs the tcgen05 descriptor probe (see csrc/srk_probe.cu); results into out[] (host memory). */

@@ -32,3 +32,9 @@ def rel_err(a, b, floor=0.0):
 
 def max_abs(a, b):
     return (a.double() - b.double()).abs().max().item()
+
+
+def rms_rel_err(a, b):
+    """||a-b||_2 / ||b||_2"""
+    a, b = a.detach().double().flatten(), b.detach().double().flatten()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
