@@ -185,31 +185,46 @@ def run_srk(args):
     lr_pin, hr_pin = lr_h.pin_memory(), hr_h.pin_memory()
     lr_d, hr_d = lr_pin.to(dev), hr_pin.to(dev)
 
-    def step(lr, hr):
+    def fwd_bwd(lr, hr):
         opt.zero_grad()
         loss = crit(model(lr), hr)
         loss.backward()
         if averager is not None:
-            averager.average()
-        opt.step()
+            averager.pack()          # gradients -> flat fp32 buckets / world
         return loss
 
-    # The whole step (forward, loss, backward, [all-reduce], Adam, weight re-pack) is captured once into a
-    # CUDA graph and replayed: same kernels, same work, no per-launch host overhead.
+    def finish():
+        if averager is not None:
+            averager.unpack()
+        opt.step()
+
+    def step(lr, hr):
+        loss = fwd_bwd(lr, hr)
+        if averager is not None:
+            averager.all_reduce()    # NCCL over NVLink, one collective per bucket
+        finish()
+        return loss
+
+    # The step is captured once into two CUDA graphs (forward + loss + backward + weight re-pack | Adam) and
+    # replayed: same kernels, same work, no per-launch host overhead.  The NCCL all-reduce between them is
+    # launched eagerly.
     use_graph = not args.no_graph
     lr_s, hr_s = lr_d.clone(), hr_d.clone()
-    graph, loss_s = None, None
+    g1 = g2 = loss_s = None
+
+    def run_step():
+        if g1 is None:
+            return step(lr_s, hr_s)
+        g1.replay()
+        if averager is not None:
+            averager.all_reduce()
+        g2.replay()
+        return loss_s
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-
-    def run_step():
-        if graph is not None:
-            graph.replay()
-            return loss_s
-        return step(lr_s, hr_s)
 
     def timed(nsteps, e2e):
         barrier()
@@ -237,18 +252,19 @@ def run_srk(args):
     for _ in range(max(args.warmup - 1, 2)):
         step(lr_s, hr_s)
     if use_graph:
-        torch.cuda.synchronize()
+        barrier()
         ops.bump_weights_epoch()          # every weight pack is re-done inside the captured step
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            step(lr_s, hr_s)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=side):
-                loss_s = step(lr_s, hr_s)
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1, stream=side, capture_error_mode="thread_local"):
+                loss_s = fwd_bwd(lr_s, hr_s)
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2, stream=side, pool=g1.pool(), capture_error_mode="thread_local"):
+                finish()
         torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
+        barrier()
         run_step()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms_step = timed(args.steps, e2e=False)
@@ -310,7 +326,7 @@ def run_srk(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": "dp%d" % world,
                        "l2": "working set (>2 GB of activations per step) exceeds the 126 MB L2; no explicit flush",
-                       "cuda_graph": bool(graph is not None), "final_loss": round(loss_value, 5),
+                       "cuda_graph": bool(g1 is not None), "final_loss": round(loss_value, 5),
                        "step_tflops": round(step_tf, 2),
                        "step_frac_of_bf16_sustained": round(step_tf / (world * pk["tf_sustained"]), 4)},
             "e2e": {"value": round(world * B / (ms_e2e * 1e-3), 2), "unit": "images/s",

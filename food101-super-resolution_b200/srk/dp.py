@@ -46,33 +46,47 @@ class GradAverager:
             self.flat[i] = torch.empty((n,), dtype=torch.float32, device=like.device)
         return self.flat[i]
 
+    # The three phases are separate so that a trainer can capture pack() and unpack() in CUDA graphs (with the
+    # backward and the optimizer step respectively) and launch only the collective itself eagerly.
     @torch.no_grad()
-    def average(self, async_op=False):
+    def pack(self):
+        """gradients -> flat buckets, pre-divided by the world size"""
         if self.world == 1:
-            return []
-        works = []
+            return
+        self._views = []
         for i, bucket in enumerate(self.buckets):
             grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in bucket]
             flat = self._flat(i, grads[0])
             views = list(flat.split([g.numel() for g in grads]))
             torch._foreach_copy_(views, [g.reshape(-1) for g in grads])
             flat.div_(self.world)
-            w = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-            works.append((w, bucket, views))
-        if async_op:
-            return works
-        self.finish(works)
-        return []
+            self._views.append(views)
 
     @torch.no_grad()
-    def finish(self, works):
-        for w, bucket, views in works:
+    def all_reduce(self):
+        if self.world == 1:
+            return
+        works = [dist.all_reduce(f, op=dist.ReduceOp.SUM, group=self.group, async_op=True) for f in self.flat
+                 if f is not None]
+        for w in works:
             w.wait()
+
+    @torch.no_grad()
+    def unpack(self):
+        """flat buckets -> .grad"""
+        if self.world == 1:
+            return
+        for bucket, views in zip(self.buckets, self._views):
             for p, v in zip(bucket, views):
                 if p.grad is None:
                     p.grad = v.view_as(p).clone()
                 else:
                     p.grad.copy_(v.view_as(p))
+
+    def average(self):
+        self.pack()
+        self.all_reduce()
+        self.unpack()
 
 
 def broadcast_parameters(module, src=0, group=None):
