@@ -58,17 +58,45 @@ __device__ __forceinline__ bool is_border(const Geo& g, long long q) {
 }
 
 // Pixel-tiled iteration: a block owns `ppb` consecutive padded pixels; thread t handles channel
-// vector cv = t % CV for pixel rows t / CV, t / CV + rows, ...
+// vector cv = t % CV for pixel rows t / CV, t / CV + rows, ...  The walker tracks the padded (x, y) of its
+// pixel incrementally: one 64-bit division per thread instead of two per pixel.
+struct PixWalk {
+  long long q, q_end;
+  int xx, yy, rows, Wp, Hp;
+  __device__ __forceinline__ PixWalk(const Geo& g, int ppb, int rows_, int prow) {
+    const long long q_begin = (long long)blockIdx.x * ppb;
+    q_end = q_begin + ppb;
+    if (q_end > g.pixels) q_end = g.pixels;
+    q = q_begin + prow;
+    rows = rows_; Wp = g.Wp; Hp = g.Hp;
+    xx = (int)(q % g.Wp);
+    yy = (int)((q / g.Wp) % g.Hp);
+  }
+  __device__ __forceinline__ bool valid() const { return q < q_end; }
+  __device__ __forceinline__ bool border() const { return xx == 0 || xx == Wp - 1 || yy == 0 || yy == Hp - 1; }
+  __device__ __forceinline__ void next() {
+    q += rows; xx += rows;
+    while (xx >= Wp) { xx -= Wp; if (++yy == Hp) yy = 0; }
+  }
+};
 #define SRK_PIXEL_LOOP(g, VEC)                                                      \
   const int CV = (g).C / (VEC);                                                     \
   const int rows = blockDim.x / CV;                                                 \
   const int cv = threadIdx.x % CV;                                                  \
   const int prow = threadIdx.x / CV;                                                \
-  const long long q_begin = (long long)blockIdx.x * ppb;                            \
-  long long q_end = q_begin + ppb;                                                  \
-  if (q_end > (g).pixels) q_end = (g).pixels;                                       \
-  if (prow < rows)                                                                  \
-    for (long long q = q_begin + prow; q < q_end; q += rows)
+  _Pragma("unroll 4")                                                               \
+  for (PixWalk pw((g), ppb, rows, prow); prow < rows && pw.valid(); pw.next())
+
+// Same ownership without the (x, y) bookkeeping, for reductions whose border terms vanish.
+#define SRK_FLAT_LOOP(g, VEC)                                                       \
+  const int CV = (g).C / (VEC);                                                     \
+  const int rows = blockDim.x / CV;                                                 \
+  const int cv = threadIdx.x % CV;                                                  \
+  const int prow = threadIdx.x / CV;                                                \
+  const long long q_begin__ = (long long)blockIdx.x * ppb;                          \
+  const long long q_end__ = q_begin__ + ppb < (g).pixels ? q_begin__ + ppb : (g).pixels; \
+  _Pragma("unroll 4")                                                               \
+  for (long long q = q_begin__ + prow; prow < rows && q < q_end__; q += rows)
 
 inline void pixel_grid(const Geo& g, int& blocks, int& ppb) {
   // ~4 blocks per SM worth of work, at least 64 pixels per block
@@ -80,19 +108,40 @@ inline void pixel_grid(const Geo& g, int& blocks, int& ppb) {
 }
 
 // Reduce per-thread VEC partials across the rows of a block, then one atomic per channel.
+// When the channel-vector count divides the warp size the lanes that share a channel vector are first folded
+// with shuffles, so only one row per warp goes through shared memory.
 template <int VEC>
 __device__ __forceinline__ void block_channel_atomic(float* part, float* smem, int CV, int rows,
                                                      int cv, int prow, float* gdst) {
-  // smem: [rows][CV*VEC]
+  const int C = CV * VEC;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   __syncthreads();
+  if ((32 % CV) == 0 && (blockDim.x % CV) == 0) {
+    for (int o = CV; o < 32; o <<= 1) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) part[j] += __shfl_xor_sync(0xffffffffu, part[j], o);
+    }
+    if (lane < CV) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) smem[warp * C + cv * VEC + j] = part[j];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float s = 0.f;
+      for (int r = 0; r < nwarps; ++r) s += smem[r * C + c];
+      atomicAdd(&gdst[c], s);
+    }
+    return;
+  }
+  // smem: [rows][CV*VEC]
   if (prow < rows) {
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) smem[prow * CV * VEC + cv * VEC + j] = part[j];
+    for (int j = 0; j < VEC; ++j) smem[prow * C + cv * VEC + j] = part[j];
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < CV * VEC; c += blockDim.x) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = 0.f;
-    for (int r = 0; r < rows; ++r) s += smem[r * CV * VEC + c];
+    for (int r = 0; r < rows; ++r) s += smem[r * C + c];
     atomicAdd(&gdst[c], s);
   }
 }
@@ -105,8 +154,8 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ y, 
   float s1[VEC], s2[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-  SRK_PIXEL_LOOP(g, VEC) {
-    if (is_border(g, q)) continue;
+  // the border is zero by invariant, so it contributes nothing: plain strided walk over all padded pixels
+  SRK_FLAT_LOOP(g, VEC) {
     float v[VEC];
     Vec<T, VEC>::ld(y + q * g.C + cv * VEC, v);
 #pragma unroll
@@ -147,25 +196,34 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ y, 
     const float* __restrict__ beta, const float* __restrict__ alpha_p, const T* __restrict__ res,
     T* __restrict__ out) {
   const float alpha = alpha_p ? alpha_p[0] : 1.f;
+  // per-channel scale / shift of this thread's channel vector, hoisted out of the pixel loop
+  float sc[VEC], sh[VEC];
+  {
+    const int c0 = (threadIdx.x % (g.C / VEC)) * VEC;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      sc[j] = gamma[c0 + j] * invstd[c0 + j];
+      sh[j] = beta[c0 + j] - mean[c0 + j] * sc[j];
+    }
+  }
   SRK_PIXEL_LOOP(g, VEC) {
+    const long long q = pw.q;
     float o[VEC];
     const long long e = q * g.C + cv * VEC;
-    if (is_border(g, q)) {
+    if (pw.border()) {
 #pragma unroll
       for (int j = 0; j < VEC; ++j) o[j] = 0.f;
     } else {
       float v[VEC];
       Vec<T, VEC>::ld(y + e, v);
+      float r[VEC];
+      if (res) Vec<T, VEC>::ld(res + e, r);
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
-        int c = cv * VEC + j;
-        float sc = gamma[c] * invstd[c];
-        float b = (v[j] - mean[c]) * sc + beta[c];
+        float b = fmaf(v[j], sc[j], sh[j]);
         o[j] = (alpha_p && b < 0.f) ? alpha * b : b;
       }
       if (res) {
-        float r[VEC];
-        Vec<T, VEC>::ld(res + e, r);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) o[j] += r[j];
       }
@@ -184,21 +242,29 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const T* __restrict_
   const float alpha = alpha_p ? alpha_p[0] : 1.f;
   float dg[VEC], db[VEC];
   float da = 0.f;
+  // xhat = v * is - mi,  bn output b = v * sc + sh   (4 constants per channel)
+  float is[VEC], mi[VEC], sc[VEC], sh[VEC];
+  {
+    const int c0 = (threadIdx.x % (g.C / VEC)) * VEC;
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) { dg[j] = 0.f; db[j] = 0.f; }
-  SRK_PIXEL_LOOP(g, VEC) {
-    if (is_border(g, q)) continue;
+    for (int j = 0; j < VEC; ++j) {
+      dg[j] = 0.f; db[j] = 0.f;
+      is[j] = invstd[c0 + j]; mi[j] = mean[c0 + j] * is[j];
+      sc[j] = gamma[c0 + j] * is[j]; sh[j] = beta[c0 + j] - mean[c0 + j] * sc[j];
+    }
+  }
+  // dout is zero on the border (layout invariant), so border pixels add exactly zero to every sum
+  SRK_FLAT_LOOP(g, VEC) {
     const long long e = q * g.C + cv * VEC;
     float v[VEC], d[VEC];
     Vec<T, VEC>::ld(y + e, v);
     Vec<T, VEC>::ld(dout + e, d);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      int c = cv * VEC + j;
-      float xh = (v[j] - mean[c]) * invstd[c];
+      float xh = fmaf(v[j], is[j], -mi[j]);
       float gd = d[j];
       if (alpha_p) {
-        float b = xh * gamma[c] + beta[c];
+        float b = fmaf(v[j], sc[j], sh[j]);
         if (b < 0.f) { da = fmaf(gd, b, da); gd *= alpha; }
       }
       dg[j] = fmaf(gd, xh, dg[j]);
@@ -221,28 +287,34 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
     const float* __restrict__ alpha_p, const float* __restrict__ dgamma, const float* __restrict__ dbeta,
     float inv_count, int batch_stats, T* __restrict__ dy) {
   const float alpha = alpha_p ? alpha_p[0] : 1.f;
+  // dy = a1 * g' + a2 * v + a3 with g' = PReLU-masked dout; mask from b = v * a1 + sh   (4 constants / channel)
+  float a1[VEC], a2[VEC], a3[VEC], sh[VEC];
+  {
+    const int c0 = (threadIdx.x % (g.C / VEC)) * VEC;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float is = invstd[c0 + j], mu = mean[c0 + j], ga = gamma[c0 + j];
+      const float k1 = batch_stats ? dbeta[c0 + j] * inv_count : 0.f;
+      const float k2 = batch_stats ? dgamma[c0 + j] * inv_count : 0.f;
+      a1[j] = ga * is;
+      a2[j] = -a1[j] * is * k2;
+      a3[j] = -a1[j] * k1 - a2[j] * mu;
+      sh[j] = beta[c0 + j] - mu * a1[j];
+    }
+  }
   SRK_PIXEL_LOOP(g, VEC) {
+    const long long q = pw.q;
     float o[VEC];
     const long long e = q * g.C + cv * VEC;
-    if (is_border(g, q)) {
+    float v[VEC], d[VEC];
+    Vec<T, VEC>::ld(y + e, v);
+    Vec<T, VEC>::ld(dout + e, d);
+    const bool border = pw.border();
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) o[j] = 0.f;
-    } else {
-      float v[VEC], d[VEC];
-      Vec<T, VEC>::ld(y + e, v);
-      Vec<T, VEC>::ld(dout + e, d);
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        int c = cv * VEC + j;
-        float xh = (v[j] - mean[c]) * invstd[c];
-        float gd = d[j];
-        if (alpha_p) {
-          float b = xh * gamma[c] + beta[c];
-          if (b < 0.f) gd *= alpha;
-        }
-        float sc = gamma[c] * invstd[c];
-        o[j] = batch_stats ? sc * (gd - dbeta[c] * inv_count - xh * dgamma[c] * inv_count) : sc * gd;
-      }
+    for (int j = 0; j < VEC; ++j) {
+      float gd = d[j];
+      if (alpha_p && fmaf(v[j], a1[j], sh[j]) < 0.f) gd *= alpha;
+      o[j] = border ? 0.f : fmaf(a1[j], gd, fmaf(a2[j], v[j], a3[j]));
     }
     Vec<T, VEC>::st(dy + e, o);
   }
@@ -257,9 +329,10 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const T* __restrict__ dout
   const float inv_alpha = (act == SRK_ACT_PRELU && alpha != 0.f) ? 1.f / alpha : 0.f;
   float da = 0.f;
   SRK_PIXEL_LOOP(g, VEC) {
+    const long long q = pw.q;
     float o[VEC];
     const long long e = q * g.C + cv * VEC;
-    if (is_border(g, q)) {
+    if (pw.border()) {
 #pragma unroll
       for (int j = 0; j < VEC; ++j) o[j] = 0.f;
     } else {
@@ -291,9 +364,10 @@ __global__ void __launch_bounds__(256) act_bwd_unshuffle_kernel(const T* __restr
   const int Wp2 = 2 * (gz.Wp - 2) + 2, Hp2 = 2 * (gz.Hp - 2) + 2;
   float da = 0.f;
   SRK_PIXEL_LOOP(gz, VEC) {
+    const long long q = pw.q;
     float o[VEC];
     const long long e = q * gz.C + cv * VEC;
-    if (is_border(gz, q)) {
+    if (pw.border()) {
 #pragma unroll
       for (int j = 0; j < VEC; ++j) o[j] = 0.f;
     } else {
@@ -307,6 +381,19 @@ __global__ void __launch_bounds__(256) act_bwd_unshuffle_kernel(const T* __restr
         long long src = (((long long)n * Hp2 + (2 * yy + (sub >> 1) + 1)) * Wp2 + (2 * xx + (sub & 1) + 1)) * C + c;
         Vec<T, VEC>::ld(out + src, v);
         Vec<T, VEC>::ld(dout + src, d);
+      } else if (!perm_tc && VEC == 8 && sizeof(T) == 2) {
+        // reference channel order co = 4c + sub: this thread's 8 channels are c = 2cv, 2cv+1 for the four
+        // sub-pixels -> one 32-bit load (two adjacent bf16 channels) per sub-pixel and tensor; across the
+        // warp each sub-pixel's 64 channels are one contiguous 128-byte row
+#pragma unroll
+        for (int sub = 0; sub < 4; ++sub) {
+          long long src = (((long long)n * Hp2 + (2 * yy + (sub >> 1) + 1)) * Wp2 + (2 * xx + (sub & 1) + 1)) * C + 2 * cv;
+          const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(out + src);
+          const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(dout + src);
+          const float2 af = __bfloat1622float2(a), bf = __bfloat1622float2(b);
+          v[sub] = af.x; v[4 + sub] = af.y;
+          d[sub] = bf.x; d[4 + sub] = bf.y;
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
@@ -395,9 +482,10 @@ __global__ void __launch_bounds__(256) se_apply_kernel(const T* __restrict__ x, 
     Geo g, int ppb, const float* __restrict__ gate, float scale, T* __restrict__ out) {
   const long long img_pixels = (long long)g.Hp * g.Wp;
   SRK_PIXEL_LOOP(g, VEC) {
+    const long long q = pw.q;
     float o[VEC];
     const long long e = q * g.C + cv * VEC;
-    if (is_border(g, q)) {
+    if (pw.border()) {
 #pragma unroll
       for (int j = 0; j < VEC; ++j) o[j] = 0.f;
     } else {
@@ -462,9 +550,10 @@ __global__ void __launch_bounds__(256) se_bwd_apply_kernel(const T* __restrict__
     T* __restrict__ dr) {
   const long long img_pixels = (long long)g.Hp * g.Wp;
   SRK_PIXEL_LOOP(g, VEC) {
+    const long long q = pw.q;
     float o[VEC];
     const long long e = q * g.C + cv * VEC;
-    if (is_border(g, q)) {
+    if (pw.border()) {
 #pragma unroll
       for (int j = 0; j < VEC; ++j) o[j] = 0.f;
     } else {
