@@ -33,7 +33,7 @@ int conv_smalln_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* 
 bool conv_wgrad_tc_shape_ok(const srk_tensor* x, const srk_tensor* dy, int r, int s);
 int64_t conv_wgrad_tc_workspace(const srk_tensor* x, const srk_tensor* dy, int r, int s);
 int conv_wgrad_tc_launch(const srk_tensor* x, const srk_tensor* dy, float* dw, float* db, int r, int s,
-                         void* workspace, cudaStream_t st);
+                         void* workspace, int accumulate, cudaStream_t st);
 
 int64_t conv_rgb_workspace_bytes(int k);
 int conv_rgb_tc_run(const srk_tensor* t3, const srk_tensor* y, const void* w_packed, const float* bias, int act,
@@ -130,7 +130,7 @@ extern "C" int64_t srk_conv_wgrad_workspace_bytes(const srk_tensor* x, const srk
 }
 
 extern "C" int srk_conv_wgrad(const srk_tensor* x, const srk_tensor* dy, float* dw, float* db, int r, int s,
-                              int impl, void* workspace, void* stream) {
+                              int impl, int accumulate, void* workspace, void* stream) {
   SRK_REQUIRE(tensor_ok(x) && tensor_ok(dy), "srk_conv_wgrad: bad x / dy tensor");
   SRK_REQUIRE(dw != nullptr, "srk_conv_wgrad: null dw");
   SRK_REQUIRE(r == s && (r & 1) == 1 && r >= 1 && r <= 11, "srk_conv_wgrad: odd square kernels only");
@@ -140,7 +140,11 @@ extern "C" int srk_conv_wgrad(const srk_tensor* x, const srk_tensor* dy, float* 
   if (impl == SRK_IMPL_TC) {
     SRK_REQUIRE(conv_wgrad_tc_shape_ok(x, dy, r, s), "srk_conv_wgrad: shape not supported by the tcgen05 path");
     SRK_REQUIRE(workspace != nullptr || conv_wgrad_tc_workspace(x, dy, r, s) == 0, "srk_conv_wgrad: workspace required");
-    return conv_wgrad_tc_launch(x, dy, dw, db, r, s, workspace, st);
+    return conv_wgrad_tc_launch(x, dy, dw, db, r, s, workspace, accumulate, st);
+  }
+  if (!accumulate) {  // the CUDA-core kernel adds with atomics
+    cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)dy->c * x->c * r * s, st);
+    if (db) cudaMemsetAsync(db, 0, sizeof(float) * (size_t)dy->c, st);
   }
   return conv_wgrad_simt_launch(x, dy, dw, db, r, s, st);
 }

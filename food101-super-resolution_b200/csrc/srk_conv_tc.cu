@@ -69,7 +69,8 @@ constexpr int TAPS = 9;
 constexpr int W_TILE_BYTES = NT * KC * 2;       // 8 KB per tap
 constexpr int A_TILE_BYTES = TM * KC * 2;       // 16 KB
 constexpr int SLAB_BOX_ROWS = 32;
-constexpr int kThreads = 320;
+constexpr int kThreads = 352;           // warps: 0 TMA, 1 MMA, 2-9 epilogue, 10 output store / residual load
+constexpr int O_TILE_BYTES = TM * NT * 2;  // bf16 output tile staged for the TMA store
 constexpr int MAX_STAGES = 8;
 
 struct TcConvParams {
@@ -96,6 +97,7 @@ struct TcConvParams {
 
 struct __align__(8) TcBarriers {
   uint64_t full[MAX_STAGES], empty[MAX_STAGES], wfull, tfull[2], tempty[2];
+  uint64_t oready[2], ofree[2], rfull[2];   // output staging tiles: written / drained / residual landed
   uint32_t tmem_base;
 };
 
@@ -106,14 +108,17 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
                   const TcConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // dynamic smem: [weights 9 x 8 KB][A ring stages x stage_bytes][barriers]
+  // dynamic smem: [weights 9 x 8 KB][A ring stages x stage_bytes][2 output tiles x 16 KB][barriers]
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t wsm = smem_base;
   const uint32_t asm0 = smem_base + TAPS * W_TILE_BYTES;
-  TcBarriers* bars = reinterpret_cast<TcBarriers*>(smem_al + TAPS * W_TILE_BYTES + p.stages * p.stage_bytes);
+  const uint32_t osm = asm0 + p.stages * p.stage_bytes;
+  uint8_t* optr = smem_al + TAPS * W_TILE_BYTES + p.stages * p.stage_bytes;
+  TcBarriers* bars = reinterpret_cast<TcBarriers*>(optr + 2 * O_TILE_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
@@ -121,7 +126,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
     mbar_init(smem_u32(&bars->wfull), 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->tfull[i]), 1); mbar_init(smem_u32(&bars->tempty[i]), 256); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bars->tfull[i]), 1); mbar_init(smem_u32(&bars->tempty[i]), 256);
+      mbar_init(smem_u32(&bars->oready[i]), 256); mbar_init(smem_u32(&bars->ofree[i]), 1);
+      mbar_init(smem_u32(&bars->rfull[i]), 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -250,6 +259,39 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       __syncwarp();
     }
+  } else if (warp == 10) {
+    // ================= output store / residual load warp (plain, non-PixelShuffle outputs) =================
+    // tile `it` uses staging buffer b = it & 1: [residual TMA load ->] epilogue writes -> TMA store -> free
+    if (p.shuffle == 0) {
+      const int my_tiles = blockIdx.x < p.num_tiles ? (p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+      if (p.residual && elect_one()) {
+        prefetch_tmap(&tmR);
+        for (int it = 0; it < 2 && it < my_tiles; ++it) {
+          const uint32_t rb = smem_u32(&bars->rfull[it]);
+          mbar_arrive_expect_tx(rb, O_TILE_BYTES);
+          tma_load_2d(osm + it * O_TILE_BYTES, &tmR, rb, p.cout_off, (blockIdx.x + it * gridDim.x) * TM);
+        }
+      }
+      __syncwarp();
+      for (int it = 0; it < my_tiles; ++it) {
+        const int b = it & 1;
+        if (!mbar_wait(smem_u32(&bars->oready[b]), (it >> 1) & 1, p.err, 6)) break;
+        if (elect_one()) {
+          tma_store_2d(&tmY, osm + b * O_TILE_BYTES, p.cout_off, (blockIdx.x + it * gridDim.x) * TM);
+          tma_store_commit();
+          tma_store_wait_read0();               // the staging tile has been read out: it may be refilled
+          if (p.residual && it + 2 < my_tiles) {
+            const uint32_t rb = smem_u32(&bars->rfull[b]);
+            mbar_arrive_expect_tx(rb, O_TILE_BYTES);
+            tma_load_2d(osm + b * O_TILE_BYTES, &tmR, rb, p.cout_off, (blockIdx.x + (it + 2) * gridDim.x) * TM);
+          }
+          mbar_arrive(smem_u32(&bars->ofree[b]));
+        }
+        __syncwarp();
+      }
+      if (elect_one()) tma_store_wait_all();
+      __syncwarp();
+    }
   } else {
     // ================= epilogue: 8 warps, warp e owns TMEM lanes 32*(e&3).. and 32 of the 64 columns ====
     const int e = warp - 2, lg = warp & 3, ch = e >> 2;   // warps 2..9 -> lane groups 2,3,0,1,2,3,0,1
@@ -273,13 +315,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int n = pc / img, q = pc - n * img;
       const int yy = q / p.Wp, xx = q - yy * p.Wp;
       const bool interior = pix < p.P && yy >= 1 && yy <= p.Hp - 2 && xx >= 1 && xx <= p.Wp - 2;
-      // the residual does not depend on the accumulator: fetch it while the MMAs of this tile still run
-      uint4 rr[4];
-      if (p.residual && interior) {
-        const uint4* res = reinterpret_cast<const uint4*>(p.residual + (long long)pix * p.cout_total + p.cout_off + c0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) rr[j] = __ldg(res + j);
-      }
       ok = mbar_wait(smem_u32(&bars->tfull[acc]), (it >> 1) & 1, p.err, 5);
       if (!ok) break;
       tc_fence_after();
@@ -291,7 +326,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_before();
       mbar_arrive(smem_u32(&bars->tempty[acc]));
       if (tr) p.trace[4 * 32 + it] = clock64();
-      if (pix >= p.P) continue;
       float f[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -314,29 +348,35 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         continue;
       }
-      uint4* dst = reinterpret_cast<uint4*>(p.y + (long long)pix * p.cout_total + p.cout_off + c0);
-      if ((p.dbg & 1) && f[0] != 12345.f) continue;
-      if (!interior) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(0, 0, 0, 0);
-        continue;
-      }
-      if (p.stats_sum) {
+      // stage the bf16 tile in shared memory ([128 rows][128 B], SWIZZLE_128B) for one coalesced TMA store;
+      // border pixels are stored as zeros (layout invariant), rows past the tensor are clipped by TMA
+      const int row = lg * 32 + lane;
+      uint8_t* orow = optr + acc * O_TILE_BYTES + row * 128;
+      if (!mbar_wait(smem_u32(&bars->ofree[acc]), ((it >> 1) & 1) ^ 1, p.err, 7)) break;
+      if (interior && p.stats_sum) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) { s1[j] += f[j]; s2[j] = fmaf(f[j], f[j], s2[j]); }
       }
       if (p.residual) {
+        if (!mbar_wait(smem_u32(&bars->rfull[acc]), (it >> 1) & 1, p.err, 8)) break;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
+          const uint4 rr = *reinterpret_cast<const uint4*>(orow + (((ch * 4 + j) ^ (row & 7)) << 4));
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rr);
 #pragma unroll
           for (int t = 0; t < 4; ++t) { float2 u = __bfloat1622float2(h[t]); f[8 * j + 2 * t] += u.x; f[8 * j + 2 * t + 1] += u.y; }
         }
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        dst[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                            pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+      for (int j = 0; j < 4; ++j) {
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (interior)
+          o = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                         pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+        *reinterpret_cast<uint4*>(orow + (((ch * 4 + j) ^ (row & 7)) << 4)) = o;
+      }
+      fence_proxy_async();
+      mbar_arrive(smem_u32(&bars->oready[acc]));
       if (tr) p.trace[5 * 32 + it] = clock64();
     }
     if (p.stats_sum) {
@@ -429,7 +469,7 @@ int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w
   }
   int mode = tc_mode();
   int slab_rows = ((TM + 2 * Wp + 2) + SLAB_BOX_ROWS - 1) / SLAB_BOX_ROWS * SLAB_BOX_ROWS;
-  const int fixed = 1024 + TAPS * W_TILE_BYTES + (int)sizeof(TcBarriers);
+  const int fixed = 1024 + TAPS * W_TILE_BYTES + 2 * O_TILE_BYTES + (int)sizeof(TcBarriers);
   int stage_bytes, stages;
   if (mode != 0) {
     stage_bytes = slab_rows * KC * 2;
@@ -449,6 +489,13 @@ int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w
   if (make_tmap_2d_bf16(&tmA, x->data, (uint64_t)P, (uint64_t)cin, (uint64_t)cin, mode == 0 ? TM : SLAB_BOX_ROWS, KC, 128))
     return 1;
   if (make_tmap_2d_bf16(&tmW, w_packed, (uint64_t)TAPS * cout, (uint64_t)cin, (uint64_t)cin, NT, KC, 128)) return 1;
+  CUtensorMap tmY = tmA, tmR = tmA;  // output store / residual load maps (plain outputs only)
+  if (shuffle == 0) {
+    if (make_tmap_2d_bf16(&tmY, y->data, (uint64_t)P, (uint64_t)cout, (uint64_t)cout, TM, NT, 128)) return 1;
+    tmR = tmY;
+    if (residual && make_tmap_2d_bf16(&tmR, residual->data, (uint64_t)P, (uint64_t)cout, (uint64_t)cout, TM, NT, 128))
+      return 1;
+  }
 
   TcConvParams p;
   p.P = (int)P; p.Hp = Hp; p.Wp = Wp;
@@ -482,7 +529,8 @@ int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w
       p.residual = first ? (residual ? (const __nv_bfloat16*)residual->data : nullptr) : p.y;
       SRK_REQUIRE(kchunks == 1 || (act == SRK_ACT_NONE && shuffle == 0),
                   "conv_tc: activation / pixel-shuffle epilogues need Cin == 64");
-      conv3x3_tc_kernel<<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, p);
+      // partial sums of a multi-chunk contraction are re-read from y itself
+      conv3x3_tc_kernel<<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, first ? tmR : tmY, p);
       SRK_CUDA_LAUNCH_CHECK("conv3x3_tc");
     }
   }

@@ -9,8 +9,8 @@
 //       slab, separated by the descriptor's leading-byte-offset (d(t2) - d(t1)) * 128 B
 //   B = dZ tile         [128 pixels][64 co], SWIZZLE_128B
 // Five accumulators (tap pairs (0,1)(2,3)(4,5)(6,7)(8,-)) live in TMEM for the CTA's whole pixel range
-// (split-K over persistent CTAs); they are flushed once with vector fp32 reductions into a
-// [9][64 ci][64 co] workspace, which a small kernel folds into the OIHW fp32 gradient.  The bias gradient
+// (split-K over persistent CTAs); each CTA stores its partial [9][64 ci][64 co] block once and a small
+// kernel adds the partials into the OIHW fp32 gradient.  The bias gradient
 // (column sums of dZ) is accumulated from the staged dZ tiles by the otherwise idle epilogue warps.
 #include "srk_common.cuh"
 #include "srk_tc_common.cuh"
@@ -31,7 +31,7 @@ struct WgradTcParams {
   int P, Wp, num_tiles;
   int x_col0, dz_col0;     // channel offsets of this (ci chunk, co chunk) pass
   int slab_rows, stages, stage_bytes;
-  float* ws;               // [9][64][64] fp32, zero-filled by the caller
+  float* ws;               // [gridDim.x][9][64][64] fp32 per-CTA partial sums
   float* db;               // [64] slice of the bias gradient (accumulated) or null
   int* err;
 };
@@ -158,7 +158,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         float t = 0.f;
 #pragma unroll
         for (int r = 0; r < 16; ++r) t += bars->red[r][et];
-        atomicAdd(&p.db[et], t);
+        p.ws[(size_t)gridDim.x * (TAPS * KC * NT) + (size_t)blockIdx.x * NT + et] = t;  // per-CTA partial
       }
     }
     if (my_tiles > 0 && mbar_wait(smem_u32(&bars->done), 0, p.err, 14)) {
@@ -175,13 +175,13 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         tmem_ld_wait();
         if (a == NACC - 1 && half == 1) continue;
         const int tap = 2 * a + half;
-        float* dst = p.ws + ((size_t)tap * KC + ci) * NT;
+        // this CTA's partial sum, stored plainly (148 CTAs hammering the same 147 KB with atomics cost ~20 us);
+        // wgrad_fold_kernel adds the partials up
+        float4* dst = reinterpret_cast<float4*>(p.ws + ((size_t)blockIdx.x * TAPS + tap) * KC * NT + (size_t)ci * NT);
 #pragma unroll
         for (int j = 0; j < NT / 4; ++j)
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j),
-                       "f"(__uint_as_float(v[4 * j])), "f"(__uint_as_float(v[4 * j + 1])),
-                       "f"(__uint_as_float(v[4 * j + 2])), "f"(__uint_as_float(v[4 * j + 3]))
-                       : "memory");
+          dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                               __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
       }
     }
   }
@@ -193,14 +193,29 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   }
 }
 
-// dw[co0+co][ci0+ci][tap] += ws[tap][ci][co]
-__global__ void wgrad_fold_kernel(const float* __restrict__ ws, float* __restrict__ dw, int cin_total, int ci0,
-                                  int co0) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;  // over [co][ci][tap] of the 64x64 block
-  if (i >= NT * KC * TAPS) return;
-  int tap = i % TAPS, t = i / TAPS;
-  int ci = t % KC, co = t / KC;
-  dw[((size_t)(co0 + co) * cin_total + (ci0 + ci)) * TAPS + tap] += ws[((size_t)tap * KC + ci) * NT + co];
+// dw[co0+co][ci0+ci][tap] += sum over CTAs of ws[cta][tap][ci][co];  db[co0+co] += sum over CTAs of the tail
+__global__ void wgrad_fold_kernel(const float* __restrict__ ws, int parts, float* __restrict__ dw, int cin_total,
+                                  int ci0, int co0, float* __restrict__ db, int accumulate) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;  // over [tap][ci][co]: coalesced reads of every partial
+  if (i >= NT * KC * TAPS) {
+    const int c = i - NT * KC * TAPS;
+    if (db != nullptr && c < NT) {
+      float s = 0.f;
+      for (int k = 0; k < parts; ++k) s += ws[(size_t)parts * (TAPS * KC * NT) + (size_t)k * NT + c];
+      db[co0 + c] = accumulate ? db[co0 + c] + s : s;
+    }
+    return;
+  }
+  float s0 = 0.f, s1 = 0.f;
+  int k = 0;
+  for (; k + 1 < parts; k += 2) {
+    s0 += ws[(size_t)k * (TAPS * KC * NT) + i];
+    s1 += ws[(size_t)(k + 1) * (TAPS * KC * NT) + i];
+  }
+  if (k < parts) s0 += ws[(size_t)k * (TAPS * KC * NT) + i];
+  const int co = i % NT, t = i / NT, ci = t % KC, tap = t / KC;
+  float* o = &dw[((size_t)(co0 + co) * cin_total + (ci0 + ci)) * TAPS + tap];
+  *o = accumulate ? *o + s0 + s1 : s0 + s1;
 }
 
 bool conv_wgrad_tc_shape_ok(const srk_tensor* x, const srk_tensor* dy, int r, int s) {
@@ -214,11 +229,12 @@ bool conv_wgrad_tc_shape_ok(const srk_tensor* x, const srk_tensor* dy, int r, in
 }
 
 int64_t conv_wgrad_tc_workspace(const srk_tensor* x, const srk_tensor* dy, int, int) {
-  return (int64_t)(x->c / KC) * (dy->c / NT) * TAPS * KC * NT * sizeof(float);
+  (void)x; (void)dy;
+  return (int64_t)kNumSMs * (TAPS * KC * NT + NT) * sizeof(float);  // one partial (+ bias partial) per CTA
 }
 
 int conv_wgrad_tc_launch(const srk_tensor* x, const srk_tensor* dy, float* dw, float* db, int r, int s,
-                         void* workspace, cudaStream_t st) {
+                         void* workspace, int accumulate, cudaStream_t st) {
   const int Hp = x->h + 2, Wp = x->w + 2;
   const long long P = (long long)x->n * Hp * Wp;
   SRK_REQUIRE(P < (1LL << 31) - 4096, "wgrad_tc: too many pixels");
@@ -244,18 +260,17 @@ int conv_wgrad_tc_launch(const srk_tensor* x, const srk_tensor* dy, float* dw, f
   if (make_tmap_2d_bf16(&tmX, x->data, (uint64_t)P, (uint64_t)x->c, (uint64_t)x->c, SLAB_BOX_ROWS, KC, 128)) return 1;
   if (make_tmap_2d_bf16(&tmDz, dy->data, (uint64_t)P, (uint64_t)dy->c, (uint64_t)dy->c, TM, NT, 128)) return 1;
   const int kchunks = x->c / KC, nchunks = dy->c / NT;
-  const size_t ws_block = (size_t)TAPS * KC * NT;
-  cudaMemsetAsync(workspace, 0, ws_block * sizeof(float) * kchunks * nchunks, st);
   const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
   for (int nc = 0; nc < nchunks; ++nc)
     for (int kc = 0; kc < kchunks; ++kc) {
       p.x_col0 = kc * KC;
       p.dz_col0 = nc * NT;
-      p.ws = (float*)workspace + ws_block * (nc * kchunks + kc);
+      p.ws = (float*)workspace;  // reused by every (ci, co) chunk pass: the fold runs right behind on the stream
       p.db = (db != nullptr && kc == 0) ? db + nc * NT : nullptr;
       wgrad3x3_tc_kernel<<<grid, kThreads, smem_bytes, st>>>(tmX, tmDz, p);
       SRK_CUDA_LAUNCH_CHECK("wgrad3x3_tc");
-      wgrad_fold_kernel<<<(NT * KC * TAPS + 255) / 256, 256, 0, st>>>(p.ws, dw, x->c, kc * KC, nc * NT);
+      wgrad_fold_kernel<<<(NT * KC * TAPS + NT + 127) / 128, 128, 0, st>>>(p.ws, grid, dw, x->c, kc * KC, nc * NT,
+                                                                           p.db ? db : nullptr, accumulate);
       SRK_CUDA_LAUNCH_CHECK("wgrad_fold");
     }
   return 0;

@@ -271,6 +271,19 @@ def conv_wgrad(x, x_img, dz, dz_img, weight, need_bias, perm_tc=False):
     if perm_tc:
         raise RuntimeError("conv_wgrad: sub-pixel-major dz is not supported yet")
     cout, cin, r, s = weight.shape
+    if not (x_img and (not dz_img) and cin == 3 and cout == 64 and dz.dtype == torch.bfloat16 and _rgb_tc_ok(r, s)):
+        # general path: the kernels write (accumulate = 0), so no zero-fill launches are needed
+        dw = torch.empty_like(weight, memory_format=torch.contiguous_format)
+        db = torch.empty((cout,), dtype=torch.float32, device=weight.device) if need_bias else None
+        xd, dd = desc(x, x_img), desc(dz, dz_img)
+        impl = L.IMPL_SIMT if cfg.conv_impl == "simt" else L.IMPL_AUTO
+        nbytes = L.cdll.srk_conv_wgrad_workspace_bytes(xd, dd, r, s, impl)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=weight.device) if nbytes > 0 else None
+        n, _, h, w = geometry(x, x_img)
+        _timed(("conv_wgrad", cin, cout, r, 0, n, h, w, nbytes > 0),
+               lambda: L.call("srk_conv_wgrad", xd, dd, dw.data_ptr(), _ptr(db), r, s, impl, 0, _ptr(ws),
+                              stream_ptr()))
+        return dw, db
     dw = torch.zeros_like(weight, memory_format=torch.contiguous_format)
     db = torch.zeros((cout,), dtype=torch.float32, device=weight.device) if need_bias else None
     if x_img and (not dz_img) and cin == 3 and cout == 64 and dz.dtype == torch.bfloat16 and _rgb_tc_ok(r, s):
@@ -280,14 +293,7 @@ def conv_wgrad(x, x_img, dz, dz_img, weight, need_bias, perm_tc=False):
                lambda: L.call("srk_conv_rgb_bwd", img_desc(x), act_desc(dz), None, None, dw.data_ptr(), _ptr(db),
                               r, 0, ws.data_ptr(), stream_ptr()))
         return dw, db
-    xd, dd = desc(x, x_img), desc(dz, dz_img)
-    impl = L.IMPL_SIMT if cfg.conv_impl == "simt" else L.IMPL_AUTO
-    nbytes = L.cdll.srk_conv_wgrad_workspace_bytes(xd, dd, r, s, impl)
-    ws = torch.empty((nbytes,), dtype=torch.uint8, device=weight.device) if nbytes > 0 else None
-    n, _, h, w = geometry(x, x_img)
-    _timed(("conv_wgrad", cin, cout, r, 0, n, h, w, nbytes > 0),
-           lambda: L.call("srk_conv_wgrad", xd, dd, dw.data_ptr(), _ptr(db), r, s, impl, _ptr(ws), stream_ptr()))
-    return dw, db
+    raise AssertionError("unreachable")
 
 
 def act_bwd(dout, out, act, alpha, unshuffle, perm_tc=False):

@@ -79,11 +79,11 @@ int srk_conv_fprop(const srk_tensor* x, const srk_tensor* y, const void* w_packe
                    const srk_tensor* residual, int pixel_shuffle, int impl, float* bn_sum,
                    float* bn_sumsq, void* stream);
 
-/* dW (fp32, OIHW, ACCUMULATED into dw: caller zero-fills) and db (fp32 [Cout], accumulated, may be NULL).
+/* dW (fp32, OIHW) and db (fp32 [Cout], may be NULL): added into dw / db when accumulate != 0, written otherwise.
  * x: conv input, dy: gradient w.r.t. the conv output (pre-activation, conv-output geometry).
  * workspace: srk_conv_wgrad_workspace_bytes() bytes (may be NULL when that returns 0). */
 int srk_conv_wgrad(const srk_tensor* x, const srk_tensor* dy, float* dw, float* db, int r, int s,
-                   int impl, void* workspace, void* stream);
+                   int impl, int accumulate, void* workspace, void* stream);
 int64_t srk_conv_wgrad_workspace_bytes(const srk_tensor* x, const srk_tensor* dy, int r, int s, int impl);
 
 /* ---- convolutions with an RGB side on tcgen05 (K = 9 or 5; im2col built in shared memory) ---------

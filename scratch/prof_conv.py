@@ -17,6 +17,7 @@ fns = {
     'fprop+stats': lambda: ops.conv_fprop(x, False, wt, b, 0, None, None, 0, False, torch.bfloat16, bn_sums=sums),
     'dgrad+res': lambda: ops.conv_dgrad(dz, False, wt, x, torch.bfloat16),
     'wgrad': lambda: ops.conv_wgrad(x, False, dz, False, wt, True),
+    'wgrad_nobias': lambda: ops.conv_wgrad(x, False, dz, False, wt, False),
 }
 for f in fns.values():
     for _ in range(2): f()
