@@ -82,6 +82,7 @@ struct TcConvParams {
   int cout_off;        // channel offset inside a y row
   int act, shuffle, sub;
   int mode, slab_rows, stages, stage_bytes;
+  int taps;            // 9 (3x3) or 1 (1x1, staged like mode 0)
   const float* bias;   // indexed [bias_off + c] or null
   int bias_off, bias_stride;   // bias index of column c = bias_off + c * bias_stride
   const float* alpha;
@@ -150,8 +151,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       prefetch_tmap(&tmA);
       prefetch_tmap(&tmW);
       const uint32_t wbar = smem_u32(&bars->wfull);
-      mbar_arrive_expect_tx(wbar, TAPS * W_TILE_BYTES);
-      for (int t = 0; t < TAPS; ++t)
+      mbar_arrive_expect_tx(wbar, p.taps * W_TILE_BYTES);
+      for (int t = 0; t < p.taps; ++t)
         tma_load_2d(wsm + t * W_TILE_BYTES, &tmW, wbar, p.k_col0, t * p.w_row_per_tap + p.w_row0);
     }
     __syncwarp();
@@ -161,13 +162,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
       const int m0 = tile * TM;
       if (p.mode == 0) {
-        for (int t = 0; t < TAPS && ok; ++t) {
+        for (int t = 0; t < p.taps && ok; ++t) {
           ok = mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1, p.err, 1);
           if (!ok) break;
           if (elect_one()) {
             const uint32_t fb = smem_u32(&bars->full[s]);
             mbar_arrive_expect_tx(fb, A_TILE_BYTES);
-            const int d = (t / 3 - 1) * p.Wp + (t % 3 - 1);
+            const int d = p.taps == 1 ? 0 : (t / 3 - 1) * p.Wp + (t % 3 - 1);
             tma_load_2d(asm0 + s * p.stage_bytes, &tmA, fb, p.k_col0, m0 + d);
           }
           __syncwarp();
@@ -216,7 +217,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t d_tmem = tmem_base + acc * NT;
       if (p.mode == 0) {
 #pragma unroll 1
-        for (int t = 0; t < TAPS; ++t) {
+        for (int t = 0; t < p.taps; ++t) {
           ok = mbar_wait(smem_u32(&bars->full[s]), ph, p.err, 4);
           if (!ok) break;
           tc_fence_after();
@@ -447,7 +448,7 @@ int tc_read_err_flag() {
 }
 
 bool conv_tc_shape_ok(int cin, int cout, int r, int s, int dtype, int shuffle) {
-  if (dtype != SRK_BF16 || r != 3 || s != 3) return false;
+  if (dtype != SRK_BF16 || r != s || (r != 3 && r != 1)) return false;
   if (cin % KC != 0 || cout % NT != 0) return false;
   if (shuffle != 0 && !(shuffle == 2 && cout % NT == 0 && cin == KC)) return false;
   return true;
@@ -467,7 +468,7 @@ int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
   }
-  int mode = tc_mode();
+  int mode = r == 1 ? 0 : tc_mode();
   int slab_rows = ((TM + 2 * Wp + 2) + SLAB_BOX_ROWS - 1) / SLAB_BOX_ROWS * SLAB_BOX_ROWS;
   const int fixed = 1024 + TAPS * W_TILE_BYTES + 2 * O_TILE_BYTES + (int)sizeof(TcBarriers);
   int stage_bytes, stages;
@@ -488,7 +489,7 @@ int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w
   CUtensorMap tmA, tmW;
   if (make_tmap_2d_bf16(&tmA, x->data, (uint64_t)P, (uint64_t)cin, (uint64_t)cin, mode == 0 ? TM : SLAB_BOX_ROWS, KC, 128))
     return 1;
-  if (make_tmap_2d_bf16(&tmW, w_packed, (uint64_t)TAPS * cout, (uint64_t)cin, (uint64_t)cin, NT, KC, 128)) return 1;
+  if (make_tmap_2d_bf16(&tmW, w_packed, (uint64_t)(r * s) * cout, (uint64_t)cin, (uint64_t)cin, NT, KC, 128)) return 1;
   CUtensorMap tmY = tmA, tmR = tmA;  // output store / residual load maps (plain outputs only)
   if (shuffle == 0) {
     if (make_tmap_2d_bf16(&tmY, y->data, (uint64_t)P, (uint64_t)cout, (uint64_t)cout, TM, NT, 128)) return 1;
@@ -501,6 +502,7 @@ int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w
   p.P = (int)P; p.Hp = Hp; p.Wp = Wp;
   p.num_tiles = (int)((P + TM - 1) / TM);
   p.w_row_per_tap = cout;
+  p.taps = r * s;
   p.mode = mode; p.slab_rows = slab_rows; p.stages = stages; p.stage_bytes = stage_bytes;
   p.alpha = alpha;
   p.y = (__nv_bfloat16*)y->data;

@@ -6,3 +6,4 @@ from .ops import cfg, set_compute_dtype, set_conv_impl  # noqa: F401
 
 __all__ = ["fn", "ops", "cfg", "set_compute_dtype", "set_conv_impl"]
 from . import optim  # noqa: F401,E402
+from . import dp, evaluate  # noqa: F401,E402

@@ -57,3 +57,31 @@ def test_shard_range_covers_everything_once():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             sizes = [e - b for b, e in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _eval_worker(rank, world, port, out):
+    sys.path.insert(0, os.path.join(ROOT, "food101-super-resolution_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from srk import evaluate as ev
+    torch.manual_seed(0)
+    batches = [(torch.rand(4 if i < 6 else 3, 3, 8, 8), torch.rand(4 if i < 6 else 3, 3, 8, 8)) for i in range(7)]
+    fake_model = lambda x: x * 2.0
+    def metrics(sr, hr):  # stand-in for MetricsCalculator.compute: any per-batch function
+        return {"psnr": float((sr - hr).abs().mean()), "ssim": float(sr.mean()), "nlpd": float(hr.std()), "lpips": float("nan")}
+    got = ev.evaluate(fake_model, batches, "cpu", rank, world, metrics_fn=metrics)
+    want = {k: sum(metrics(fake_model(a), b)[k] for a, b in batches) / len(batches) for k in ("psnr", "ssim", "nlpd")}
+    out[rank] = (got["batches"], max(abs(got[k] - want[k]) for k in want), got["lpips"] != got["lpips"])
+    dist.destroy_process_group()
+
+
+def test_sharded_evaluation_reproduces_batch_mean_semantics():
+    """7 batches (ragged last one) over 2 ranks == the single-process mean over batches (train.py:161,193-195)."""
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_eval_worker, args=(world, 29541, out), nprocs=world, join=True)
+        assert len(out) == world
+        for nb, err, lp_nan in out.values():
+            assert nb == 7 and err < 1e-12 and lp_nan

@@ -103,7 +103,7 @@ def test_bf16_resnet_step_realistic_size():
         if _zero_grad_by_construction(k):
             continue
         # a shared PReLU slope's gradient is one number summed over positive and negative contributions
-        tol = 1.5e-1 if k.endswith("prelu.weight") or k in ("upsample.2.weight", "upsample.5.weight") else 4e-2
+        tol = 2.5e-1 if k.endswith("prelu.weight") or k in ("upsample.2.weight", "upsample.5.weight") else 4e-2
         assert e <= tol, (k, e)
 
 
@@ -115,7 +115,7 @@ def test_bf16_attention_step_realistic_size():
     (e_max, e_rms), errs = _bf16_vs_oracle("AttentionSR", model, lr, hr, "mae")
     assert e_rms <= 2e-2 and e_max <= 2e-2, (e_max, e_rms)
     for k, e in errs.items():
-        tol = 1.5e-1 if "prelu" in k or k in ("upsample.2.weight", "upsample.5.weight") else 4e-2
+        tol = 2.5e-1 if "prelu" in k or k in ("upsample.2.weight", "upsample.5.weight") else 4e-2
         assert e <= tol, (k, e)
 
 
@@ -424,3 +424,47 @@ def test_adam_matches_torch_optim():
         o_mine.step()
     for r, m in zip(ref, mine):
         assert max_abs(m.detach().cpu(), r.detach()) <= 2e-6
+
+
+def test_sharded_evaluate_matches_oracle_metrics():
+    """srk.evaluate (config C4 path, one rank): ResNet-SR inference + PSNR/SSIM/NLPD per batch, mean over batches,
+    against the CPU oracle run on the same weights and batches (ragged last batch kept as its own batch)."""
+    from srk import evaluate as ev
+    from src import models as M
+    torch.manual_seed(4)
+    model = M.ResNetSR(num_channels=64, num_residuals=1)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    batches = []
+    for i, n in enumerate((3, 3, 2)):
+        lr, hr = O.synthetic_pair(n, 12, 16, 4, seed=50 + i)
+        batches.append((lr, hr))
+    got = ev.evaluate(model.to(DEV), batches, DEV)
+    want = {"psnr": 0.0, "ssim": 0.0, "nlpd": 0.0}
+    with torch.no_grad():
+        for lr, hr in batches:
+            m = O.metrics_compute(O.model_forward("RESNET", sd, lr, training=False), hr)
+            for k in want:
+                want[k] += m[k] / len(batches)
+    assert got["batches"] == 3
+    assert abs(got["psnr"] - want["psnr"]) <= 0.01
+    assert abs(got["ssim"] - want["ssim"]) <= 1e-4
+    assert abs(got["nlpd"] - want["nlpd"]) <= 1e-5
+
+
+def test_srcnn_bf16_step_all_tensor_core_shapes():
+    """SRCNN (config C1 shapes, reduced batch) in bf16: 9x9 3->64, 1x1 64->64 and 5x5 64->3 all take tcgen05 paths."""
+    import srk
+    from src import models as M
+    from src.loss import get_loss_function
+    torch.manual_seed(6)
+    model = M.SRCNN(scale_factor=2, hidden_dim=64)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    lr, hr = O.synthetic_pair(2, 32, 32, 2, seed=12)
+    out_ref, _, grads_ref, _ = O.train_step_grads("SRCNN", sd, lr, hr, "nlpd", scale_factor=2)
+    srk.set_compute_dtype("bf16")
+    model = model.to(DEV).train()
+    out = model(lr.to(DEV))
+    get_loss_function("nlpd", DEV)(out, hr.to(DEV)).backward()
+    assert rel_err(out.cpu(), out_ref) <= 1e-2
+    for k, p in model.named_parameters():
+        assert rel_err(p.grad.cpu(), grads_ref[k], floor=1e-4) <= 3e-2, k
