@@ -22,13 +22,29 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
+# headline workload = BASELINE config C2; C1 / C3 are selectable for secondary measurements (--config)
+CONFIGS = {
+    "C2": dict(arch="RESNET", loss="nlpd", lr_hw=64, scale=4, batch=64, gflop=54.39,
+               name="C2: ResNet-SR 16x64ch x4, 64->256 synthetic crops, batch 64/GPU, NLPD loss, fwd+bwd+Adam"),
+    "C3": dict(arch="AttentionSR", loss="mae", lr_hw=64, scale=4, batch=32, gflop=158.9,
+               name="C3: AttentionSR 32x96ch x4, 64->256 synthetic crops, batch 32/GPU, MAE loss, fwd+bwd+Adam"),
+    "C1": dict(arch="SRCNN", loss="nlpd", lr_hw=128, scale=2, batch=16, gflop=7.57,
+               name="C1: SRCNN 9-1-5 x2, 128->256 synthetic crops, batch 16/GPU, NLPD loss, fwd+bwd+Adam"),
+}
 ARCH = "RESNET"
 LOSS = "nlpd"
 LR_HW = 64
 SCALE = 4
 BATCH_PER_GPU = 64
 FWD_BWD_GFLOP_PER_IMG = 54.39  # 2*MAC over convs, fwd + dgrad + wgrad (no input dgrad)
-WORKLOAD = "C2: ResNet-SR 16x64ch x4, 64->256 synthetic crops, batch %d/GPU, NLPD loss, fwd+bwd+Adam" % BATCH_PER_GPU
+WORKLOAD = CONFIGS["C2"]["name"]
+
+
+def select_config(name):
+    global ARCH, LOSS, LR_HW, SCALE, BATCH_PER_GPU, FWD_BWD_GFLOP_PER_IMG, WORKLOAD
+    c = CONFIGS[name]
+    ARCH, LOSS, LR_HW, SCALE, BATCH_PER_GPU = c["arch"], c["loss"], c["lr_hw"], c["scale"], c["batch"]
+    FWD_BWD_GFLOP_PER_IMG, WORKLOAD = c["gflop"], c["name"]
 
 
 def peaks():
@@ -110,7 +126,7 @@ def run_reference(args):
 
     def step():
         opt.zero_grad()
-        out = O.model_forward(ARCH, work, lr, training=True)
+        out = O.model_forward(ARCH, work, lr, training=True, scale_factor=SCALE)
         loss = O.loss_fn(LOSS)(out, hr)
         loss.backward()
         opt.step()
@@ -149,7 +165,7 @@ def cpu_baseline(budget_s=20.0, batch=2):
     t_begin = time.perf_counter()
     while len(times) < 4 and (time.perf_counter() - t_begin) < budget_s:
         t0 = time.perf_counter()
-        O.train_step_grads(ARCH, sd, lr, hr, LOSS)
+        O.train_step_grads(ARCH, sd, lr, hr, LOSS, scale_factor=SCALE)
         times.append(time.perf_counter() - t0)
     best = min(times[1:]) if len(times) > 1 else times[0]
     return {"value": round(batch / best, 3), "unit": "images/s", "cores": threads, "kind": "port",
@@ -281,7 +297,7 @@ def run_srk(args):
     kt = ops.kernel_timer.summary()
     ops.kernel_timer = None
     kern_ms = None
-    if kt:
+    if kt and ARCH == "RESNET":
         blk = model.res_blocks[0]
         xa = torch.zeros((B, LR_HW + 2, LR_HW + 2, 64), dtype=ops.cfg.compute_dtype, device=dev)
         one = lambda: ops.conv_fprop(xa, False, blk.conv1.weight, blk.conv1.bias, 0, None, None, 0, False, xa.dtype)
@@ -309,7 +325,7 @@ def run_srk(args):
     pk = peaks()
     value = world * B / (ms_step * 1e-3)
     roof = None
-    if kt:
+    if kt and kern_ms is not None:
         key, (_, count) = max(kt.items(), key=lambda kv: kv[1][0] * kv[1][1])
         avg_ms = kern_ms
         n, h, w = key[5:8]
@@ -346,11 +362,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="srk", choices=["srk", "reference"])
     ap.add_argument("--dtype", default=os.environ.get("SRK_BENCH_DTYPE", "bf16"), choices=["bf16", "fp32"])
-    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the config's)")
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS), help="BASELINE.json config (headline: C2)")
     ap.add_argument("--cpu-batch", type=int, default=4, help="--impl reference: images per CPU step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
+    select_config(args.config)
+    if args.batch <= 0:
+        args.batch = BATCH_PER_GPU
     if args.impl == "reference":
         run_reference(args)
         return

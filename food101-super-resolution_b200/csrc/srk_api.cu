@@ -26,7 +26,8 @@ bool conv_tc_shape_ok(int cin, int cout, int r, int s, int dtype, int shuffle);
 int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout,
                          int r, int s, const float* bias, int act, const float* alpha,
                          const srk_tensor* residual, int shuffle, float* stats_sum, float* stats_sumsq,
-                         cudaStream_t st);
+                         void* workspace, cudaStream_t st);
+int64_t conv_fprop_tc_workspace(const srk_tensor* x);
 bool conv_smalln_tc_ok(const srk_tensor* x, const srk_tensor* y, int cout, int r, int s);
 int conv_smalln_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout, int r,
                           const float* bias, cudaStream_t st);
@@ -61,10 +62,16 @@ extern "C" int srk_conv_tc_supported(int cin, int cout, int r, int s, int dtype,
   return conv_tc_shape_ok(cin, cout, r, s, dtype, pixel_shuffle) ? 1 : 0;
 }
 
+extern "C" int64_t srk_conv_fprop_workspace_bytes(const srk_tensor* x, int pack_kind) {
+  if (x == nullptr) return -1;
+  const bool tc_kind = pack_kind == SRK_PACK_FPROP_TC || pack_kind == SRK_PACK_DGRAD_TC;
+  return (tc_kind && x->layout == SRK_LAYOUT_ACT) ? conv_fprop_tc_workspace(x) : 0;
+}
+
 extern "C" int srk_conv_fprop(const srk_tensor* x, const srk_tensor* y, const void* w_packed,
                               int pack_kind, int cout, int r, int s, const float* bias, int act,
                               const float* alpha, const srk_tensor* residual, int pixel_shuffle,
-                              int impl, float* bn_sum, float* bn_sumsq, void* stream) {
+                              int impl, float* bn_sum, float* bn_sumsq, void* workspace, void* stream) {
   SRK_REQUIRE((bn_sum == nullptr) == (bn_sumsq == nullptr), "srk_conv_fprop: bn_sum and bn_sumsq go together");
   SRK_REQUIRE(bn_sum == nullptr || (act == SRK_ACT_NONE && residual == nullptr && pixel_shuffle == 0 &&
                                     y->layout == SRK_LAYOUT_ACT),
@@ -107,12 +114,12 @@ extern "C" int srk_conv_fprop(const srk_tensor* x, const srk_tensor* y, const vo
                 "srk_conv_fprop: shape Cin=%d Cout=%d %dx%d not supported by the tcgen05 path", x->c, cout, r, s);
     if (bn_sum != nullptr && x->c != 64) {  // the fused statistics cover single-pass convs only
       if (conv_fprop_tc_launch(x, y, w_packed, cout, r, s, bias, act, alpha, residual, pixel_shuffle, nullptr,
-                               nullptr, st))
+                               nullptr, workspace, st))
         return 1;
       return srk_bn_stats(y, bn_sum, bn_sumsq, stream);
     }
     return conv_fprop_tc_launch(x, y, w_packed, cout, r, s, bias, act, alpha, residual, pixel_shuffle, bn_sum,
-                                bn_sumsq, st);
+                                bn_sumsq, workspace, st);
   }
   SRK_REQUIRE(impl == SRK_IMPL_SIMT && simt_kind, "srk_conv_fprop: CUDA-core path needs SRK_PACK_*_SIMT weights");
   if (conv_fprop_simt_launch(x, y, (const float*)w_packed, cout, r, s, bias, act, alpha, residual,

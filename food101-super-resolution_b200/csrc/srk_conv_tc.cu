@@ -83,6 +83,11 @@ struct TcConvParams {
   int act, shuffle, sub;
   int mode, slab_rows, stages, stage_bytes;
   int taps;            // 9 (3x3) or 1 (1x1, staged like mode 0)
+  int n_cols;          // output channels of this pass: 64 or 32 (UMMA N)
+  int ksteps;          // 16-channel K steps of this pass: 4 (64 channels) or 2 (32 channels)
+  int res_first;       // (unused) 
+  float* partial_out;  // chunked contraction (Cin > 64): fp32 partial sums [P][64] written instead of y ...
+  const float* partial_in;  // ... and added back (before the activation) by the next contraction chunk
   const float* bias;   // indexed [bias_off + c] or null
   int bias_off, bias_stride;   // bias index of column c = bias_off + c * bias_stride
   const float* alpha;
@@ -107,10 +112,23 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// kFast: the common single-chunk 64 -> 64 pass (no partial sums, N = 64, four K steps) with those choices
+// compiled in; the general instantiation covers 32-wide tails and chunked contractions.
+template <bool kFast, bool kStats>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
-                  const TcConvParams p) {
+                  const TcConvParams pp) {
+  // in the fast instantiation the chunking parameters are compile-time constants
+  const TcConvParams& p = pp;
+  const int n_cols = kFast ? NT : pp.n_cols;
+  const int ksteps = kFast ? KC / 16 : pp.ksteps;
+  float* const partial_out = kFast ? nullptr : pp.partial_out;
+  const float* const partial_in = kFast ? nullptr : pp.partial_in;
+  const int dbg = kFast ? 0 : pp.dbg;
+  long long* const trace = kFast ? nullptr : pp.trace;
+  float* const stats_sum = kStats ? pp.stats_sum : nullptr;
+  float* const stats_sumsq = kStats ? pp.stats_sumsq : nullptr;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem: [weights 9 x 8 KB][A ring stages x stage_bytes][2 output tiles x 16 KB][barriers]
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -179,7 +197,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (!ok) break;
         if (elect_one()) {
           const uint32_t fb = smem_u32(&bars->full[s]);
-          if (p.dbg & 4) {
+          if (dbg & 4) {
             mbar_arrive(fb);
           } else {
             mbar_arrive_expect_tx(fb, p.slab_rows * KC * 2);
@@ -188,7 +206,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               tma_load_2d(asm0 + s * p.stage_bytes + j * SLAB_BOX_ROWS * KC * 2, &tmA, fb, p.k_col0,
                           row0 + j * SLAB_BOX_ROWS);
           }
-          if (p.trace && blockIdx.x == 0 && tile / (int)gridDim.x < 32) p.trace[0 * 32 + tile / gridDim.x] = clock64();
+          if (trace && blockIdx.x == 0 && tile / (int)gridDim.x < 32) trace[0 * 32 + tile / gridDim.x] = clock64();
         }
         __syncwarp();
         if (++s == S) { s = 0; ph ^= 1; }
@@ -200,7 +218,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // once: the upper word (SBO 1024 B, version, SWIZZLE_128B) is constant, the lower word is
     // (address >> 4) | (LBO >> 4) << 16, so stepping K by 16 elements (32 B) or moving to another tap / stage
     // is a 32-bit add on the lower word.
-    constexpr uint32_t idesc = make_idesc_bf16(TM, NT, 0, 0);
+    const uint32_t idesc = make_idesc_bf16(TM, n_cols, 0, 0);
     const uint64_t desc_hi = make_smem_desc(0, 16, 1024, kLayoutSW128, 0) & 0xFFFFFFFF00000000ull;
     const uint32_t lo_base = (uint32_t)(make_smem_desc(0, 16, 1024, kLayoutSW128, 0) & 0xFFFFFFFFull);
     const uint32_t w_lo = lo_base + (wsm >> 4), a_lo0 = lo_base + (asm0 >> 4);
@@ -225,7 +243,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < KC / 16; ++ks)
-              umma_bf16(d_tmem, desc_hi | (a_lo + 2 * ks), desc_hi | (b_lo + 2 * ks), idesc, (t | ks) != 0);
+              if (ks < ksteps)
+                umma_bf16(d_tmem, desc_hi | (a_lo + 2 * ks), desc_hi | (b_lo + 2 * ks), idesc, (t | ks) != 0);
             umma_commit(smem_u32(&bars->empty[s]));
           }
           __syncwarp();
@@ -238,16 +257,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc_fence_after();
         const uint32_t a_lo = a_lo0 + s * stage_units;
         if (elect_one()) {
-          if (p.trace && blockIdx.x == 0 && it < 32) p.trace[1 * 32 + it] = clock64();
-          if (!(p.dbg & 2)) {
+          if (trace && blockIdx.x == 0 && it < 32) trace[1 * 32 + it] = clock64();
+          if (!(dbg & 2)) {
 #pragma unroll
             for (int r = 0; r < 3; ++r)
 #pragma unroll
               for (int c = 0; c < 3; ++c)
 #pragma unroll
                 for (int ks = 0; ks < KC / 16; ++ks)
-                  umma_bf16(d_tmem, desc_hi | (a_lo + r * row_units + c * (KC * 2 / 16) + 2 * ks),
-                            desc_hi | (w_lo + (r * 3 + c) * (W_TILE_BYTES / 16) + 2 * ks), idesc, (r | c | ks) != 0);
+                  if (ks < ksteps)
+                    umma_bf16(d_tmem, desc_hi | (a_lo + r * row_units + c * (KC * 2 / 16) + 2 * ks),
+                              desc_hi | (w_lo + (r * 3 + c) * (W_TILE_BYTES / 16) + 2 * ks), idesc, (r | c | ks) != 0);
           }
           umma_commit(smem_u32(&bars->empty[s]));
         }
@@ -256,14 +276,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       if (elect_one()) {
         umma_commit(smem_u32(&bars->tfull[acc]));
-        if (p.trace && blockIdx.x == 0 && it < 32) p.trace[2 * 32 + it] = clock64();
+        if (trace && blockIdx.x == 0 && it < 32) trace[2 * 32 + it] = clock64();
       }
       __syncwarp();
     }
   } else if (warp == 10) {
     // ================= output store / residual load warp (plain, non-PixelShuffle outputs) =================
     // tile `it` uses staging buffer b = it & 1: [residual TMA load ->] epilogue writes -> TMA store -> free
-    if (p.shuffle == 0) {
+    if (p.shuffle == 0 && partial_out == nullptr) {
       const int my_tiles = blockIdx.x < p.num_tiles ? (p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
       if (p.residual && elect_one()) {
         prefetch_tmap(&tmR);
@@ -299,11 +319,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int c0 = ch * 32;                                // first accumulator column of this thread
     const float alpha = (p.act == SRK_ACT_PRELU) ? __ldg(p.alpha) : 0.f;
     const int img = p.Hp * p.Wp;
+    const bool active = c0 < n_cols;   // a 32-column pass leaves the second column half idle (it still signals)
     float bias[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) bias[j] = p.bias ? __ldg(p.bias + p.bias_off + c0 + j) : 0.f;
+    for (int j = 0; j < 32; ++j) bias[j] = (p.bias && active) ? __ldg(p.bias + p.bias_off + c0 + j) : 0.f;
     float s1[32], s2[32];
-    if (p.stats_sum) {
+    if (stats_sum) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
     }
@@ -319,18 +340,50 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       ok = mbar_wait(smem_u32(&bars->tfull[acc]), (it >> 1) & 1, p.err, 5);
       if (!ok) break;
       tc_fence_after();
-      const bool tr = p.trace && blockIdx.x == 0 && it < 32 && threadIdx.x == 64;
-      if (tr) p.trace[3 * 32 + it] = clock64();
+      const bool tr = trace && blockIdx.x == 0 && it < 32 && threadIdx.x == 64;
+      if (tr) trace[3 * 32 + it] = clock64();
       uint32_t v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * NT + c0, v);
-      tmem_ld_wait();
+      if (active) {
+        tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * NT + c0, v);
+        tmem_ld_wait();
+      }
       tc_fence_before();
       mbar_arrive(smem_u32(&bars->tempty[acc]));
-      if (tr) p.trace[4 * 32 + it] = clock64();
+      if (tr) trace[4 * 32 + it] = clock64();
+      const int row = lg * 32 + lane;
+      uint8_t* orow = optr + acc * O_TILE_BYTES + row * 128;
+      if (!active) {
+        // nothing to compute or store; keep the staging-buffer handshake going
+        if (p.shuffle == 0 && partial_out == nullptr) {
+          if (!mbar_wait(smem_u32(&bars->ofree[acc]), ((it >> 1) & 1) ^ 1, p.err, 7)) break;
+          if (p.residual && !mbar_wait(smem_u32(&bars->rfull[acc]), (it >> 1) & 1, p.err, 8)) break;
+          mbar_arrive(smem_u32(&bars->oready[acc]));
+        }
+        continue;
+      }
       float f[32];
 #pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bias[j];
+      if (partial_in && pix < p.P) {   // fp32 partial sums of the earlier contraction chunks
+        const float4* pin = reinterpret_cast<const float4*>(partial_in + (long long)pix * NT + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 q4 = __ldg(pin + j);
+          f[4 * j] += q4.x; f[4 * j + 1] += q4.y; f[4 * j + 2] += q4.z; f[4 * j + 3] += q4.w;
+        }
+      }
+      if (partial_out) {              // not the last chunk: keep fp32, no activation, nothing goes to y
+        if (pix < p.P) {
+          float4* po = reinterpret_cast<float4*>(partial_out + (long long)pix * NT + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) po[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        }
+        continue;
+      }
+      if (p.shuffle == 0 && !mbar_wait(smem_u32(&bars->ofree[acc]), ((it >> 1) & 1) ^ 1, p.err, 7)) break;
+#pragma unroll
       for (int j = 0; j < 32; ++j) {
-        float a = __uint_as_float(v[j]) + bias[j];
+        float a = f[j];
         if (p.act == SRK_ACT_RELU) a = fmaxf(a, 0.f);
         else if (p.act == SRK_ACT_PRELU) a = a > 0.f ? a : alpha * a;
         f[j] = a;
@@ -351,10 +404,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       // stage the bf16 tile in shared memory ([128 rows][128 B], SWIZZLE_128B) for one coalesced TMA store;
       // border pixels are stored as zeros (layout invariant), rows past the tensor are clipped by TMA
-      const int row = lg * 32 + lane;
-      uint8_t* orow = optr + acc * O_TILE_BYTES + row * 128;
-      if (!mbar_wait(smem_u32(&bars->ofree[acc]), ((it >> 1) & 1) ^ 1, p.err, 7)) break;
-      if (interior && p.stats_sum) {
+      if (interior && stats_sum) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) { s1[j] += f[j]; s2[j] = fmaf(f[j], f[j], s2[j]); }
       }
@@ -378,9 +428,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       fence_proxy_async();
       mbar_arrive(smem_u32(&bars->oready[acc]));
-      if (tr) p.trace[5 * 32 + it] = clock64();
+      if (tr) trace[5 * 32 + it] = clock64();
     }
-    if (p.stats_sum) {
+    if (stats_sum) {
       // per-thread partial sums over this CTA's pixels -> per-channel totals: transposed butterfly (lane l
       // ends up owning column l), then one atomic per lane
 #pragma unroll
@@ -396,8 +446,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
       // after the butterfly lane l holds the total of column bitrev-free index: col = sum over steps of (lane & half)
-      atomicAdd(p.stats_sum + p.cout_off + c0 + lane, s1[0]);
-      atomicAdd(p.stats_sumsq + p.cout_off + c0 + lane, s2[0]);
+      if (active && p.cout_off + c0 + lane < p.cout_total) {
+        atomicAdd(stats_sum + p.cout_off + c0 + lane, s1[0]);
+        atomicAdd(stats_sumsq + p.cout_off + c0 + lane, s2[0]);
+      }
     }
   }
   tc_fence_before();
@@ -447,16 +499,22 @@ int tc_read_err_flag() {
   return v;
 }
 
+int64_t conv_fprop_tc_workspace(const srk_tensor* x) {
+  if (x->c <= KC) return 0;
+  return (int64_t)x->n * (x->h + 2) * (x->w + 2) * NT * (int64_t)sizeof(float);
+}
+
 bool conv_tc_shape_ok(int cin, int cout, int r, int s, int dtype, int shuffle) {
   if (dtype != SRK_BF16 || r != s || (r != 3 && r != 1)) return false;
-  if (cin % KC != 0 || cout % NT != 0) return false;
+  // channels are processed in chunks of 64 with a 32-wide tail (96 = 64 + 32 for AttentionSR)
+  if (cin % 32 != 0 || cout % 32 != 0 || cin < 64 || cout < 64) return false;
   if (shuffle != 0 && !(shuffle == 2 && cout % NT == 0 && cin == KC)) return false;
   return true;
 }
 
 int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout, int r, int s,
                          const float* bias, int act, const float* alpha, const srk_tensor* residual, int shuffle,
-                         float* stats_sum, float* stats_sumsq, cudaStream_t st) {
+                         float* stats_sum, float* stats_sumsq, void* workspace, cudaStream_t st) {
   const int cin = x->c;
   const int Hp = x->h + 2, Wp = x->w + 2;
   const long long P = (long long)x->n * Hp * Wp;
@@ -466,7 +524,9 @@ int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    cudaFuncSetAttribute(conv3x3_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    cudaFuncSetAttribute(conv3x3_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    cudaFuncSetAttribute(conv3x3_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
   }
   int mode = r == 1 ? 0 : tc_mode();
   int slab_rows = ((TM + 2 * Wp + 2) + SLAB_BOX_ROWS - 1) / SLAB_BOX_ROWS * SLAB_BOX_ROWS;
@@ -512,7 +572,7 @@ int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w
   { const char* e = getenv("SRK_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.trace = g_tc_trace;
   p.stats_sum = stats_sum; p.stats_sumsq = stats_sumsq;
-  const int nchunks = cout / NT, kchunks = cin / KC;
+  const int nchunks = (cout + NT - 1) / NT, kchunks = (cin + KC - 1) / KC;
   SRK_REQUIRE(stats_sum == nullptr || (kchunks == 1 && shuffle == 0 && act == SRK_ACT_NONE && residual == nullptr),
               "conv_tc: fused BN statistics need a plain Cin == 64 conv");
   int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
@@ -525,14 +585,34 @@ int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w
       p.cout_total = y->c;     // channels per output pixel (Cout, or Cout/4 after PixelShuffle)
       p.cout_off = nc * NT;    // first conv output channel of this pass (reference order)
       p.bias_off = nc * NT; p.bias_stride = 1;
+      p.n_cols = cout - nc * NT < NT ? cout - nc * NT : NT;
+      p.ksteps = (cin - kc * KC < KC ? cin - kc * KC : KC) / 16;
       p.bias = first ? bias : nullptr;
       p.act = last ? act : SRK_ACT_NONE;
-      // partial sums over contraction chunks ride through y itself (bf16) when Cin > 64
-      p.residual = first ? (residual ? (const __nv_bfloat16*)residual->data : nullptr) : p.y;
-      SRK_REQUIRE(kchunks == 1 || (act == SRK_ACT_NONE && shuffle == 0),
-                  "conv_tc: activation / pixel-shuffle epilogues need Cin == 64");
-      // partial sums of a multi-chunk contraction are re-read from y itself
-      conv3x3_tc_kernel<<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, first ? tmR : tmY, p);
+      // A contraction over more than 64 channels runs as one pass per chunk.  Without an activation the partial
+      // sums ride through y itself in bf16 (TMA store, then re-read as the residual of the next pass; a caller
+      // residual is added by the first pass).  With an activation the sign of the pre-activation matters for the
+      // backward, so the partial sums travel in fp32 through the caller's workspace ([P][64] floats) and only the
+      // last pass activates, adds the residual and stores.
+      const bool fp32_partials = kchunks > 1 && act != SRK_ACT_NONE;
+      if (fp32_partials) {
+        p.residual = (last && residual) ? (const __nv_bfloat16*)residual->data : nullptr;
+        p.partial_out = last ? nullptr : (float*)workspace;
+        p.partial_in = first ? nullptr : (const float*)workspace;
+        SRK_REQUIRE(workspace != nullptr, "conv_tc: Cin > 64 with an activation needs the fprop workspace");
+      } else {
+        p.residual = first ? (residual ? (const __nv_bfloat16*)residual->data : nullptr) : p.y;
+        p.partial_out = nullptr;
+        p.partial_in = nullptr;
+      }
+      p.res_first = 0;
+      SRK_REQUIRE(kchunks == 1 || shuffle == 0, "conv_tc: the pixel-shuffle epilogue needs Cin == 64");
+      const CUtensorMap& tmRes = (fp32_partials || first) ? tmR : tmY;
+      const bool fast = kchunks == 1 && p.n_cols == NT && p.ksteps == KC / 16 && p.dbg == 0 && p.trace == nullptr;
+      SRK_REQUIRE(fast || stats_sum == nullptr, "conv_tc: fused BN statistics need the single-chunk 64 -> 64 pass");
+      if (fast && stats_sum) conv3x3_tc_kernel<true, true><<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, tmRes, p);
+      else if (fast) conv3x3_tc_kernel<true, false><<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, tmRes, p);
+      else conv3x3_tc_kernel<false, false><<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, tmRes, p);
       SRK_CUDA_LAUNCH_CHECK("conv3x3_tc");
     }
   }

@@ -195,11 +195,11 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 
 // dw[co0+co][ci0+ci][tap] += sum over CTAs of ws[cta][tap][ci][co];  db[co0+co] += sum over CTAs of the tail
 __global__ void wgrad_fold_kernel(const float* __restrict__ ws, int parts, float* __restrict__ dw, int cin_total,
-                                  int ci0, int co0, float* __restrict__ db, int accumulate) {
+                                  int cout_total, int ci0, int co0, float* __restrict__ db, int accumulate) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;  // over [tap][ci][co]: coalesced reads of every partial
   if (i >= NT * KC * TAPS) {
     const int c = i - NT * KC * TAPS;
-    if (db != nullptr && c < NT) {
+    if (db != nullptr && c < NT && co0 + c < cout_total) {
       float s = 0.f;
       for (int k = 0; k < parts; ++k) s += ws[(size_t)parts * (TAPS * KC * NT) + (size_t)k * NT + c];
       db[co0 + c] = accumulate ? db[co0 + c] + s : s;
@@ -214,6 +214,7 @@ __global__ void wgrad_fold_kernel(const float* __restrict__ ws, int parts, float
   }
   if (k < parts) s0 += ws[(size_t)k * (TAPS * KC * NT) + i];
   const int co = i % NT, t = i / NT, ci = t % KC, tap = t / KC;
+  if (ci0 + ci >= cin_total || co0 + co >= cout_total) return;  // zero-filled tail of a 96-channel tensor
   float* o = &dw[((size_t)(co0 + co) * cin_total + (ci0 + ci)) * TAPS + tap];
   *o = accumulate ? *o + s0 + s1 : s0 + s1;
 }
@@ -222,7 +223,8 @@ bool conv_wgrad_tc_shape_ok(const srk_tensor* x, const srk_tensor* dy, int r, in
   if (r != 3 || s != 3) return false;
   if (x->layout != SRK_LAYOUT_ACT || dy->layout != SRK_LAYOUT_ACT) return false;
   if (x->dtype != SRK_BF16 || dy->dtype != SRK_BF16) return false;
-  if (x->c % KC != 0 || dy->c % NT != 0) return false;
+  // channel counts that are not multiples of 64 (96) are covered by zero-filled TMA boxes; the fold drops the tail
+  if (x->c % 32 != 0 || dy->c % 32 != 0 || x->c < 64 || dy->c < 64) return false;
   const int Wp = x->w + 2;
   const int slab_rows = ((TM + 2 * Wp + 2) + SLAB_BOX_ROWS - 1) / SLAB_BOX_ROWS * SLAB_BOX_ROWS;
   return 2 * (slab_rows * KC * 2 + DZ_TILE_BYTES) + 4096 <= 227 * 1024;
@@ -259,7 +261,7 @@ int conv_wgrad_tc_launch(const srk_tensor* x, const srk_tensor* dy, float* dw, f
   CUtensorMap tmX, tmDz;
   if (make_tmap_2d_bf16(&tmX, x->data, (uint64_t)P, (uint64_t)x->c, (uint64_t)x->c, SLAB_BOX_ROWS, KC, 128)) return 1;
   if (make_tmap_2d_bf16(&tmDz, dy->data, (uint64_t)P, (uint64_t)dy->c, (uint64_t)dy->c, TM, NT, 128)) return 1;
-  const int kchunks = x->c / KC, nchunks = dy->c / NT;
+  const int kchunks = (x->c + KC - 1) / KC, nchunks = (dy->c + NT - 1) / NT;
   const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
   for (int nc = 0; nc < nchunks; ++nc)
     for (int kc = 0; kc < kchunks; ++kc) {
@@ -269,7 +271,7 @@ int conv_wgrad_tc_launch(const srk_tensor* x, const srk_tensor* dy, float* dw, f
       p.db = (db != nullptr && kc == 0) ? db + nc * NT : nullptr;
       wgrad3x3_tc_kernel<<<grid, kThreads, smem_bytes, st>>>(tmX, tmDz, p);
       SRK_CUDA_LAUNCH_CHECK("wgrad3x3_tc");
-      wgrad_fold_kernel<<<(NT * KC * TAPS + NT + 127) / 128, 128, 0, st>>>(p.ws, grid, dw, x->c, kc * KC, nc * NT,
+      wgrad_fold_kernel<<<(NT * KC * TAPS + NT + 127) / 128, 128, 0, st>>>(p.ws, grid, dw, x->c, dy->c, kc * KC, nc * NT,
                                                                            p.db ? db : nullptr, accumulate);
       SRK_CUDA_LAUNCH_CHECK("wgrad_fold");
     }

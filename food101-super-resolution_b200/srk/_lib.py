@@ -32,7 +32,8 @@ SIGNATURES = {
     "srk_last_error": (c_char_p, []),
     "srk_version": (c_int, []),
     "srk_conv_tc_supported": (c_int, [c_int] * 6),
-    "srk_conv_fprop": (c_int, [_T, _T, _P, c_int, c_int, c_int, c_int, _P, c_int, _P, _T, c_int, c_int, _P, _P, _P]),
+    "srk_conv_fprop": (c_int, [_T, _T, _P, c_int, c_int, c_int, c_int, _P, c_int, _P, _T, c_int, c_int, _P, _P, _P, _P]),
+    "srk_conv_fprop_workspace_bytes": (c_int64, [_T, c_int]),
     "srk_conv_wgrad": (c_int, [_T, _T, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "srk_conv_wgrad_workspace_bytes": (c_int64, [_T, _T, c_int, c_int, c_int]),
     "srk_conv_rgb_workspace_bytes": (c_int64, [c_int]),
@@ -83,7 +84,8 @@ for _name, (_res, _args) in SIGNATURES.items():
 # number of libsrk kernel-launching calls made by this process (bench.py reports it)
 launch_calls = 0
 _NO_COUNT = {"srk_last_error", "srk_version", "srk_conv_tc_supported", "srk_weight_pack_bytes",
-             "srk_conv_wgrad_workspace_bytes", "srk_nlpd_workspace_bytes", "srk_conv_rgb_workspace_bytes"}
+             "srk_conv_wgrad_workspace_bytes", "srk_nlpd_workspace_bytes", "srk_conv_rgb_workspace_bytes",
+             "srk_conv_fprop_workspace_bytes"}
 
 
 def last_error():

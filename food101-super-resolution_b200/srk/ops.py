@@ -214,6 +214,11 @@ def rgbout_bwd_supported(x, x_img, dz_img, weight):
     return (not x_img) and dz_img and cin == 64 and cout == 3 and x.dtype == torch.bfloat16 and _rgb_tc_ok(r, s)
 
 
+def _fprop_workspace(xd, kind, device):
+    nbytes = L.cdll.srk_conv_fprop_workspace_bytes(xd, kind)
+    return torch.empty((nbytes,), dtype=torch.uint8, device=device) if nbytes > 0 else None
+
+
 def conv_fprop(x, x_img, weight, bias, act, alpha, residual, shuffle, out_img, out_dtype, bn_sums=None):
     """y = [shuffle](act(conv(x, weight) + bias)) [+ residual]; stride 1, pad R//2.
     bn_sums: optional zero-filled fp32 [2, Cout] that receives the per-channel sum / sum of squares of y."""
@@ -240,11 +245,12 @@ def conv_fprop(x, x_img, weight, bias, act, alpha, residual, shuffle, out_img, o
     y = new_image(n, oc, oh, ow, x.device) if out_img else new_act(n, oc, oh, ow, out_dtype, x.device)
     xd, yd = desc(x, x_img), desc(y, out_img)
     rd = desc(residual, out_img) if residual is not None else None
+    ws = _fprop_workspace(xd, kind, x.device)
     _timed(("conv_fprop", cin, cout, r, shuffle, n, h, w, use_tc),
            lambda: L.call("srk_conv_fprop", xd, yd, pk.data_ptr(), kind, cout, r, s, _ptr(bias), act,
                           _ptr(alpha), rd, shuffle, L.IMPL_AUTO,
                           bn_sums[0].data_ptr() if bn_sums is not None else None,
-                          bn_sums[1].data_ptr() if bn_sums is not None else None, stream_ptr()))
+                          bn_sums[1].data_ptr() if bn_sums is not None else None, _ptr(ws), stream_ptr()))
     return y, use_tc
 
 
@@ -260,9 +266,11 @@ def conv_dgrad(dz, dz_img, weight, residual, out_dtype, perm_tc=False):
     pk = packed_weight(weight, kind, 0)
     dx = new_act(n, cin, h, w, out_dtype, dz.device)
     rd = act_desc(residual) if residual is not None else None
+    dzd = desc(dz, dz_img)
+    ws = _fprop_workspace(dzd, kind, dz.device)
     _timed(("conv_dgrad", cout, cin, r, 0, n, h, w, use_tc),
-           lambda: L.call("srk_conv_fprop", desc(dz, dz_img), act_desc(dx), pk.data_ptr(), kind, cin, r, s,
-                          None, L.ACT_NONE, None, rd, 0, L.IMPL_AUTO, None, None, stream_ptr()))
+           lambda: L.call("srk_conv_fprop", dzd, act_desc(dx), pk.data_ptr(), kind, cin, r, s,
+                          None, L.ACT_NONE, None, rd, 0, L.IMPL_AUTO, None, None, _ptr(ws), stream_ptr()))
     return dx
 
 

@@ -77,7 +77,10 @@ int srk_conv_tc_supported(int cin, int cout, int r, int s, int dtype, int pixel_
 int srk_conv_fprop(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int pack_kind,
                    int cout, int r, int s, const float* bias, int act, const float* alpha,
                    const srk_tensor* residual, int pixel_shuffle, int impl, float* bn_sum,
-                   float* bn_sumsq, void* stream);
+                   float* bn_sumsq, void* workspace, void* stream);
+/* bytes of `workspace` srk_conv_fprop needs for this input and pack kind (0 = may pass NULL): the tcgen05 path
+ * carries the fp32 partial sums of a contraction over more than 64 input channels through it. */
+int64_t srk_conv_fprop_workspace_bytes(const srk_tensor* x, int pack_kind);
 
 /* dW (fp32, OIHW) and db (fp32 [Cout], may be NULL): added into dw / db when accumulate != 0, written otherwise.
  * x: conv input, dy: gradient w.r.t. the conv output (pre-activation, conv-output geometry).
