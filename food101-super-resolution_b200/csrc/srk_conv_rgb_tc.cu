@@ -31,6 +31,8 @@ constexpr int SUB_BYTES = TM * 128;  // one [128 x 64 k] sub-tile of A
 struct Params {
   int N, H, W, tiles_x, tiles_y, num_tiles;
   int do_y, do_g, act;
+  int y_stride, y_col0, n_valid;   // y row pitch in channels, first channel and channel count of this pass
+  int w_row0, t_col0;              // first packed-weight row / first T64 channel of this pass
   const float* t3;       // [N][3][H][W]
   const float* bias;     // [64] or null (y)
   const float* alpha;
@@ -116,7 +118,7 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         prefetch_tmap(&tmW);
         const uint32_t wb = smem_u32(&bars->wfull);
         mbar_arrive_expect_tx(wb, G::W_BYTES);
-        for (int q = 0; q < G::KCH; ++q) tma_load_2d(w_sm + q * NT * 128, &tmW, wb, q * 64, 0);
+        for (int q = 0; q < G::KCH; ++q) tma_load_2d(w_sm + q * NT * 128, &tmW, wb, q * 64, p.w_row0);
       }
       __syncwarp();
     }
@@ -132,7 +134,7 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         if (elect_one()) {
           const uint32_t fb = smem_u32(&bars->tfull[s]);
           mbar_arrive_expect_tx(fb, G::T_BYTES);
-          tma_load_4d(t_sm + s * G::T_BYTES, &tmT, fb, 0, x0, y0, n);
+          tma_load_4d(t_sm + s * G::T_BYTES, &tmT, fb, p.t_col0, x0, y0, n);
         }
         __syncwarp();
       }
@@ -279,13 +281,14 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         const int n = tile / tiles_per_img, t2 = tile - n * tiles_per_img;
         const int y = (t2 / p.tiles_x) * TY + ty, x = (t2 % p.tiles_x) * TX + tx;
         if (y >= p.H || x >= p.W) continue;
-        uint4* dst = reinterpret_cast<uint4*>(p.y + (((size_t)n * Hp + y + 1) * Wp + x + 1) * NT);
+        uint4* dst = reinterpret_cast<uint4*>(p.y + (((size_t)n * Hp + y + 1) * Wp + x + 1) * p.y_stride + p.y_col0);
 #pragma unroll
         for (int j = 0; j < NT / 8; ++j) {
+          if (j * 8 >= p.n_valid) break;
           float f[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            float a = __uint_as_float(v[j * 8 + e]) + (p.bias ? __ldg(p.bias + j * 8 + e) : 0.f);
+            float a = __uint_as_float(v[j * 8 + e]) + (p.bias ? __ldg(p.bias + p.y_col0 + j * 8 + e) : 0.f);
             if (p.act == SRK_ACT_RELU) a = fmaxf(a, 0.f);
             else if (p.act == SRK_ACT_PRELU) a = a > 0.f ? a : alpha * a;
             f[e] = a;
@@ -327,16 +330,18 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 // ws[k][n] -> OIHW gradient.  rgb_out = 0: dW[n][c][tap] (3 -> 64 conv), db[n] = ws[KK][n]
 //                               rgb_out = 1: dW[c][n][taps-1-tap] (64 -> 3 conv; im2col was taken over dY)
 __global__ void fold_kernel(const float* __restrict__ ws, float* __restrict__ dw, float* __restrict__ db, int K,
-                            int rgb_out) {
+                            int rgb_out, int n0, int n_total) {
   const int taps = K * K, KK = taps * 3;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < KK * NT) {
     const int n = i % NT, k = i / NT, tap = k / 3, c = k - tap * 3;
+    if (n0 + n >= n_total) return;
     const float v = ws[i];
-    if (!rgb_out) dw[((size_t)n * 3 + c) * taps + tap] += v;
-    else dw[((size_t)c * NT + n) * taps + (taps - 1 - tap)] += v;
+    if (!rgb_out) dw[((size_t)(n0 + n) * 3 + c) * taps + tap] += v;
+    else dw[((size_t)c * n_total + n0 + n) * taps + (taps - 1 - tap)] += v;
   } else if (i < (KK + 1) * NT && db != nullptr && !rgb_out) {
-    db[i - KK * NT] += ws[i];
+    const int n = i - KK * NT;
+    if (n0 + n < n_total) db[n0 + n] += ws[i];
   }
 }
 
@@ -346,7 +351,7 @@ static int make_tmap_act_4d_tile(CUtensorMap* out, const srk_tensor* x) {
   const uint64_t C = x->c, Wp = x->w + 2, Hp = x->h + 2;
   cuuint64_t dims[4] = {C, (cuuint64_t)x->w, (cuuint64_t)x->h, (cuuint64_t)x->n};
   cuuint64_t strides[3] = {C * 2, Wp * C * 2, Hp * Wp * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)C, TX, TY, 1};
+  cuuint32_t box[4] = {64, TX, TY, 1};  // 64 channels per pass; a 96-channel tensor's tail is zero-filled
   cuuint32_t estr[4] = {1, 1, 1, 1};
   void* base = (char*)x->data + (Wp + 1) * C * 2;
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr,
@@ -393,24 +398,38 @@ int conv_rgb_tc_run(const srk_tensor* t3, const srk_tensor* y, const void* w_pac
   const int KP = k == 9 ? rgb::Geo<9>::KP : rgb::Geo<5>::KP;
   CUtensorMap tmW, tmT;
   memset(&tmW, 0, sizeof(tmW)); memset(&tmT, 0, sizeof(tmT));
+  // the 64-channel side may have 64 or 96 channels: one pass per 64-channel chunk (tails are zero-filled by TMA)
+  const int c64 = p.do_y ? y->c : t64->c;
   if (p.do_y) {
-    SRK_REQUIRE(y->layout == SRK_LAYOUT_ACT && y->dtype == SRK_BF16 && y->c == 64 && y->n == p.N && y->h == p.H && y->w == p.W,
-                "conv_rgb: y must be a bf16 ACT tensor with 64 channels");
-    if (make_tmap_2d_bf16(&tmW, w_packed, 64, (uint64_t)KP, (uint64_t)KP, 64, 64, 128)) return 1;
+    SRK_REQUIRE(y->layout == SRK_LAYOUT_ACT && y->dtype == SRK_BF16 && y->c % 32 == 0 && y->c >= 64 && y->n == p.N &&
+                    y->h == p.H && y->w == p.W,
+                "conv_rgb: y must be a bf16 ACT tensor with 64 or 96 channels");
+    if (make_tmap_2d_bf16(&tmW, w_packed, (uint64_t)(rgb_out ? 64 : y->c), (uint64_t)KP, (uint64_t)KP, 64, 64, 128)) return 1;
   }
   if (p.do_g) {
-    SRK_REQUIRE(t64->layout == SRK_LAYOUT_ACT && t64->dtype == SRK_BF16 && t64->c == 64 && t64->n == p.N && t64->h == p.H && t64->w == p.W,
-                "conv_rgb: t64 must be a bf16 ACT tensor with 64 channels");
+    SRK_REQUIRE(t64->layout == SRK_LAYOUT_ACT && t64->dtype == SRK_BF16 && t64->c % 32 == 0 && t64->c >= 64 &&
+                    t64->n == p.N && t64->h == p.H && t64->w == p.W,
+                "conv_rgb: t64 must be a bf16 ACT tensor with 64 or 96 channels");
     SRK_REQUIRE(workspace != nullptr && dw != nullptr, "conv_rgb: workspace / dw required");
+    SRK_REQUIRE(!(p.do_y && t64->c != y->c), "conv_rgb: y and t64 channel counts differ");
     if (rgb::make_tmap_act_4d_tile(&tmT, t64)) return 1;
-    cudaMemsetAsync(workspace, 0, (size_t)KP * 64 * 4, st);
   }
-  int rc = k == 9 ? rgb::launch<9>(tmW, tmT, p, st) : rgb::launch<5>(tmW, tmT, p, st);
-  if (rc) return rc;
-  if (p.do_g) {
-    const int total = (k * k * 3 + 1) * 64;
-    rgb::fold_kernel<<<(total + 255) / 256, 256, 0, st>>>((const float*)workspace, dw, db, k, rgb_out);
-    SRK_CUDA_LAUNCH_CHECK("conv_rgb_fold");
+  SRK_REQUIRE(!rgb_out || c64 == 64, "conv_rgb: the 64 -> 3 backward takes a 64-channel input");
+  for (int n0 = 0; n0 < c64; n0 += 64) {
+    p.y_stride = p.do_y ? y->c : 64;
+    p.y_col0 = n0;
+    p.n_valid = c64 - n0 < 64 ? c64 - n0 : 64;
+    p.w_row0 = rgb_out ? 0 : n0;
+    p.t_col0 = n0;
+    p.db3 = n0 == 0 ? db3 : nullptr;
+    if (p.do_g) cudaMemsetAsync(workspace, 0, (size_t)KP * 64 * 4, st);
+    int rc = k == 9 ? rgb::launch<9>(tmW, tmT, p, st) : rgb::launch<5>(tmW, tmT, p, st);
+    if (rc) return rc;
+    if (p.do_g) {
+      const int total = (k * k * 3 + 1) * 64;
+      rgb::fold_kernel<<<(total + 255) / 256, 256, 0, st>>>((const float*)workspace, dw, db, k, rgb_out, n0, c64);
+      SRK_CUDA_LAUNCH_CHECK("conv_rgb_fold");
+    }
   }
   if (p.do_y) return zero_border(y, st);
   return 0;

@@ -319,7 +319,8 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, void* __restric
   long long total = (long long)Cout * Cin * R * S;
   if (kind == SRK_PACK_FPROP_TC_N8) total = (long long)8 * Cin * R * S;
   const int KPr = (R * S * 3 + 1 + 63) / 64 * 64;
-  if (kind == SRK_PACK_RGBIN_TC || kind == SRK_PACK_RGBOUT_DGRAD_TC) total = 64LL * KPr;
+  if (kind == SRK_PACK_RGBOUT_DGRAD_TC) total = 64LL * KPr;
+  if (kind == SRK_PACK_RGBIN_TC) total = (long long)Cout * KPr;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     // i indexes the OUTPUT linearly
@@ -377,19 +378,22 @@ using namespace srk;
 extern "C" int64_t srk_weight_pack_bytes(int cout, int cin, int r, int s, int kind) {
   int64_t n = (int64_t)cout * cin * r * s;
   if (kind == SRK_PACK_FPROP_TC_N8) return (int64_t)8 * cin * r * s * 2 + 8 * 128;
-  if (kind == SRK_PACK_RGBIN_TC || kind == SRK_PACK_RGBOUT_DGRAD_TC) return 64LL * ((r * s * 3 + 1 + 63) / 64 * 64) * 2;
+  if (kind == SRK_PACK_RGBOUT_DGRAD_TC) return 64LL * ((r * s * 3 + 1 + 63) / 64 * 64) * 2;
+  if (kind == SRK_PACK_RGBIN_TC) return (int64_t)cout * ((r * s * 3 + 1 + 63) / 64 * 64) * 2;
   return (kind == SRK_PACK_FPROP_SIMT || kind == SRK_PACK_DGRAD_SIMT) ? n * 4 : n * 2;
 }
 
 extern "C" int srk_weight_pack(const float* w_oihw, void* out, int cout, int cin, int r, int s,
                                int kind, int pixel_shuffle, void* stream) {
   SRK_REQUIRE(kind >= 0 && kind <= 6, "srk_weight_pack: bad kind %d", kind);
-  SRK_REQUIRE(kind != SRK_PACK_RGBIN_TC || (cin == 3 && cout == 64), "srk_weight_pack: RGBIN pack needs a 3 -> 64 conv");
+  SRK_REQUIRE(kind != SRK_PACK_RGBIN_TC || (cin == 3 && cout % 32 == 0 && cout >= 64),
+              "srk_weight_pack: RGBIN pack needs a 3 -> 64 / 96 conv");
   SRK_REQUIRE(kind != SRK_PACK_RGBOUT_DGRAD_TC || (cin == 64 && cout <= 3), "srk_weight_pack: RGBOUT pack needs a 64 -> 3 conv");
   SRK_REQUIRE(kind != SRK_PACK_FPROP_TC_N8 || cout <= 8, "srk_weight_pack: N8 pack needs Cout <= 8");
   SRK_REQUIRE(pixel_shuffle == 0 || (pixel_shuffle == 2 && cout % 4 == 0), "srk_weight_pack: bad pixel_shuffle");
   long long total = (long long)(kind == SRK_PACK_FPROP_TC_N8 ? 8 : cout) * cin * r * s;
-  if (kind == SRK_PACK_RGBIN_TC || kind == SRK_PACK_RGBOUT_DGRAD_TC) total = 64LL * ((r * s * 3 + 1 + 63) / 64 * 64);
+  if (kind == SRK_PACK_RGBOUT_DGRAD_TC) total = 64LL * ((r * s * 3 + 1 + 63) / 64 * 64);
+  if (kind == SRK_PACK_RGBIN_TC) total = (long long)cout * ((r * s * 3 + 1 + 63) / 64 * 64);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (kind == SRK_PACK_FPROP_TC_N8)  // zero the slack tap read by the last N=16 MMA

@@ -500,7 +500,7 @@ int tc_read_err_flag() {
 }
 
 int64_t conv_fprop_tc_workspace(const srk_tensor* x) {
-  if (x->c <= KC) return 0;
+  if (x->c <= KC) return 0;  // (needed when an activation or PixelShuffle follows a chunked contraction)
   return (int64_t)x->n * (x->h + 2) * (x->w + 2) * NT * (int64_t)sizeof(float);
 }
 
@@ -508,7 +508,7 @@ bool conv_tc_shape_ok(int cin, int cout, int r, int s, int dtype, int shuffle) {
   if (dtype != SRK_BF16 || r != s || (r != 3 && r != 1)) return false;
   // channels are processed in chunks of 64 with a 32-wide tail (96 = 64 + 32 for AttentionSR)
   if (cin % 32 != 0 || cout % 32 != 0 || cin < 64 || cout < 64) return false;
-  if (shuffle != 0 && !(shuffle == 2 && cout % NT == 0 && cin == KC)) return false;
+  if (shuffle != 0 && !(shuffle == 2 && cout % NT == 0)) return false;
   return true;
 }
 
@@ -594,7 +594,7 @@ int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w
       // residual is added by the first pass).  With an activation the sign of the pre-activation matters for the
       // backward, so the partial sums travel in fp32 through the caller's workspace ([P][64] floats) and only the
       // last pass activates, adds the residual and stores.
-      const bool fp32_partials = kchunks > 1 && act != SRK_ACT_NONE;
+      const bool fp32_partials = kchunks > 1 && (act != SRK_ACT_NONE || shuffle != 0);
       if (fp32_partials) {
         p.residual = (last && residual) ? (const __nv_bfloat16*)residual->data : nullptr;
         p.partial_out = last ? nullptr : (float*)workspace;
@@ -606,7 +606,6 @@ int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w
         p.partial_in = nullptr;
       }
       p.res_first = 0;
-      SRK_REQUIRE(kchunks == 1 || shuffle == 0, "conv_tc: the pixel-shuffle epilogue needs Cin == 64");
       const CUtensorMap& tmRes = (fp32_partials || first) ? tmR : tmY;
       const bool fast = kchunks == 1 && p.n_cols == NT && p.ksteps == KC / 16 && p.dbg == 0 && p.trace == nullptr;
       SRK_REQUIRE(fast || stats_sum == nullptr, "conv_tc: fused BN statistics need the single-chunk 64 -> 64 pass");

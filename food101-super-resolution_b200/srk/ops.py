@@ -225,7 +225,7 @@ def conv_fprop(x, x_img, weight, bias, act, alpha, residual, shuffle, out_img, o
     n, cin, h, w = geometry(x, x_img)
     cout, wcin, r, s = weight.shape
     assert wcin == cin, "conv: input has %d channels, weight expects %d" % (cin, wcin)
-    if (x_img and cin == 3 and cout == 64 and not out_img and out_dtype == torch.bfloat16 and residual is None
+    if (x_img and cin == 3 and cout in (64, 96) and not out_img and out_dtype == torch.bfloat16 and residual is None
             and shuffle == 0 and _rgb_tc_ok(r, s)):
         pk = packed_weight(weight, L.PACK_RGBIN_TC, 0)
         y = new_act(n, cout, h, w, out_dtype, x.device)
@@ -279,7 +279,7 @@ def conv_wgrad(x, x_img, dz, dz_img, weight, need_bias, perm_tc=False):
     if perm_tc:
         raise RuntimeError("conv_wgrad: sub-pixel-major dz is not supported yet")
     cout, cin, r, s = weight.shape
-    if not (x_img and (not dz_img) and cin == 3 and cout == 64 and dz.dtype == torch.bfloat16 and _rgb_tc_ok(r, s)):
+    if not (x_img and (not dz_img) and cin == 3 and cout in (64, 96) and dz.dtype == torch.bfloat16 and _rgb_tc_ok(r, s)):
         # general path: the kernels write (accumulate = 0), so no zero-fill launches are needed
         dw = torch.empty_like(weight, memory_format=torch.contiguous_format)
         db = torch.empty((cout,), dtype=torch.float32, device=weight.device) if need_bias else None
@@ -294,7 +294,7 @@ def conv_wgrad(x, x_img, dz, dz_img, weight, need_bias, perm_tc=False):
         return dw, db
     dw = torch.zeros_like(weight, memory_format=torch.contiguous_format)
     db = torch.zeros((cout,), dtype=torch.float32, device=weight.device) if need_bias else None
-    if x_img and (not dz_img) and cin == 3 and cout == 64 and dz.dtype == torch.bfloat16 and _rgb_tc_ok(r, s):
+    if x_img and (not dz_img) and cin == 3 and cout in (64, 96) and dz.dtype == torch.bfloat16 and _rgb_tc_ok(r, s):
         n, _, h, w = geometry(x, True)
         ws = _rgb_workspace(r, x.device)
         _timed(("conv_rgbin_wgrad", cin, cout, r, 0, n, h, w, True),

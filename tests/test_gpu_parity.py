@@ -371,9 +371,10 @@ def test_rgb_output_conv_tcgen05_vs_oracle(k, n, h, w):
     assert rel_err(xg.grad.cpu(), xo.grad) <= 1e-2
 
 
+@pytest.mark.parametrize("cout", [64, 96])
 @pytest.mark.parametrize("k,n,h,w,act", [(9, 2, 16, 8, "prelu"), (9, 1, 37, 21, "relu"), (5, 2, 19, 30, "none"),
                                          (9, 3, 64, 64, "prelu")])
-def test_rgb_input_conv_tcgen05_vs_oracle(k, n, h, w, act):
+def test_rgb_input_conv_tcgen05_vs_oracle(k, n, h, w, act, cout):
     """input_conv / SRCNN conv1 (3 -> 64): NCHW fp32 in, bf16 ACT out, im2col built in shared memory."""
     import srk
     from srk import _lib as L
@@ -381,7 +382,7 @@ def test_rgb_input_conv_tcgen05_vs_oracle(k, n, h, w, act):
     srk.set_compute_dtype("bf16")
     g = torch.Generator().manual_seed(k * 10 + h)
     x = torch.rand(n, 3, h, w, generator=g).bfloat16().float()
-    conv = torch.nn.Conv2d(3, 64, k, padding=k // 2)
+    conv = torch.nn.Conv2d(3, cout, k, padding=k // 2)
     with torch.no_grad():
         conv.weight.copy_(conv.weight.bfloat16().float())
     alpha = torch.tensor([0.25])
