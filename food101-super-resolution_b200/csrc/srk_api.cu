@@ -58,7 +58,7 @@ extern "C" int srk_version(void) { return 100; }
 
 extern "C" int srk_conv_tc_supported(int cin, int cout, int r, int s, int dtype, int pixel_shuffle) {
   /* 2 = the RGB-output variant (bf16 ACT in, IMAGE out, SRK_PACK_FPROP_TC_N8 weights) */
-  if (dtype == SRK_BF16 && cin == 64 && cout <= 4 && r == s && (r == 5 || r == 9) && pixel_shuffle == 0) return 2;
+  if (dtype == SRK_BF16 && cin == 64 && cout <= 3 && r == s && (r == 5 || r == 9) && pixel_shuffle == 0) return 2;
   return conv_tc_shape_ok(cin, cout, r, s, dtype, pixel_shuffle) ? 1 : 0;
 }
 

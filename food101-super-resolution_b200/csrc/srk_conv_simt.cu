@@ -317,7 +317,8 @@ int conv_wgrad_simt_launch(const srk_tensor* x, const srk_tensor* dy, float* dw,
 __global__ void pack_weights_kernel(const float* __restrict__ w, void* __restrict__ out, int Cout,
                                     int Cin, int R, int S, int kind, int shuffle) {
   long long total = (long long)Cout * Cin * R * S;
-  if (kind == SRK_PACK_FPROP_TC_N8) total = (long long)8 * Cin * R * S;
+  const int NPn8 = S * 3 > 16 ? 32 : 16;
+  if (kind == SRK_PACK_FPROP_TC_N8) total = (long long)R * NPn8 * Cin;
   const int KPr = (R * S * 3 + 1 + 63) / 64 * 64;
   if (kind == SRK_PACK_RGBOUT_DGRAD_TC) total = 64LL * KPr;
   if (kind == SRK_PACK_RGBIN_TC) total = (long long)Cout * KPr;
@@ -336,11 +337,11 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, void* __restric
         }
       }
       ((__nv_bfloat16*)out)[i] = __float2bfloat16_rn(v);
-    } else if (kind == SRK_PACK_FPROP_TC_N8) {  // bf16 [tap][8][Cin]
+    } else if (kind == SRK_PACK_FPROP_TC_N8) {  // bf16 [R][NP][Cin], row n = s * 3 + co
       int ci = (int)(i % Cin); long long t = i / Cin;
-      int co = (int)(t % 8); int tap = (int)(t / 8);
-      int r = tap / S, s = tap - r * S;
-      float v = co < Cout ? w[(((long long)co * Cin + ci) * R + r) * S + s] : 0.f;
+      int n = (int)(t % NPn8); int r = (int)(t / NPn8);
+      int s = n / 3, co = n - s * 3;
+      float v = (s < S && co < Cout) ? w[(((long long)co * Cin + ci) * R + r) * S + s] : 0.f;
       ((__nv_bfloat16*)out)[i] = __float2bfloat16_rn(v);
     } else if (kind == SRK_PACK_FPROP_SIMT) {  // [R][S][Cin][Cout]
       int co = (int)(i % Cout); long long t = i / Cout;
@@ -377,7 +378,7 @@ using namespace srk;
 
 extern "C" int64_t srk_weight_pack_bytes(int cout, int cin, int r, int s, int kind) {
   int64_t n = (int64_t)cout * cin * r * s;
-  if (kind == SRK_PACK_FPROP_TC_N8) return (int64_t)8 * cin * r * s * 2 + 8 * 128;
+  if (kind == SRK_PACK_FPROP_TC_N8) return (int64_t)r * (s * 3 > 16 ? 32 : 16) * cin * 2;
   if (kind == SRK_PACK_RGBOUT_DGRAD_TC) return 64LL * ((r * s * 3 + 1 + 63) / 64 * 64) * 2;
   if (kind == SRK_PACK_RGBIN_TC) return (int64_t)cout * ((r * s * 3 + 1 + 63) / 64 * 64) * 2;
   return (kind == SRK_PACK_FPROP_SIMT || kind == SRK_PACK_DGRAD_SIMT) ? n * 4 : n * 2;
@@ -389,15 +390,14 @@ extern "C" int srk_weight_pack(const float* w_oihw, void* out, int cout, int cin
   SRK_REQUIRE(kind != SRK_PACK_RGBIN_TC || (cin == 3 && cout % 32 == 0 && cout >= 64),
               "srk_weight_pack: RGBIN pack needs a 3 -> 64 / 96 conv");
   SRK_REQUIRE(kind != SRK_PACK_RGBOUT_DGRAD_TC || (cin == 64 && cout <= 3), "srk_weight_pack: RGBOUT pack needs a 64 -> 3 conv");
-  SRK_REQUIRE(kind != SRK_PACK_FPROP_TC_N8 || cout <= 8, "srk_weight_pack: N8 pack needs Cout <= 8");
+  SRK_REQUIRE(kind != SRK_PACK_FPROP_TC_N8 || cout <= 3, "srk_weight_pack: the RGB-output pack needs Cout <= 3");
   SRK_REQUIRE(pixel_shuffle == 0 || (pixel_shuffle == 2 && cout % 4 == 0), "srk_weight_pack: bad pixel_shuffle");
-  long long total = (long long)(kind == SRK_PACK_FPROP_TC_N8 ? 8 : cout) * cin * r * s;
+  long long total = (long long)cout * cin * r * s;
+  if (kind == SRK_PACK_FPROP_TC_N8) total = (long long)r * (s * 3 > 16 ? 32 : 16) * cin;
   if (kind == SRK_PACK_RGBOUT_DGRAD_TC) total = 64LL * ((r * s * 3 + 1 + 63) / 64 * 64);
   if (kind == SRK_PACK_RGBIN_TC) total = (long long)cout * ((r * s * 3 + 1 + 63) / 64 * 64);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  if (kind == SRK_PACK_FPROP_TC_N8)  // zero the slack tap read by the last N=16 MMA
-    cudaMemsetAsync((char*)out + total * 2, 0, 8 * 128, (cudaStream_t)stream);
   pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, out, cout, cin, r, s, kind, pixel_shuffle);
   SRK_CUDA_LAUNCH_CHECK("pack_weights");
   return 0;

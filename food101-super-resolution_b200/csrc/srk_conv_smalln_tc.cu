@@ -1,15 +1,20 @@
 // tcgen05 convolution for the "many channels in, RGB out" layers: output_conv 9x9 64->3 (models.py:125,167)
-// and SRCNN conv3 5x5 64->3 (models.py:86).  Direct (no im2col) implicit GEMM:
+// and SRCNN conv3 5x5 64->3 (models.py:86).
 //
 //   out[n][co][y][x] = b[co] + sum_{r,s,ci} X[n][y+r-pad][x+s-pad][ci] * W[co][ci][r][s]
 //
-// M tile = 16 rows x 8 columns of output pixels.  One 4-D TMA box brings the (16+K-1) x (8+K-1) halo of
-// 64-channel pixels (zero-filled outside the image by TMA bounds checking, so the 1-pixel activation border
-// is irrelevant here) into shared memory as [halo_y][halo_x][128 B] SWIZZLE_128B.  The A operand of tap
-// (r, s) is that same buffer viewed through a descriptor that starts at pixel (r, s) with
-// stride-byte-offset = halo row pitch: eight consecutive x pixels are the 8 rows of a core matrix, the 16
-// tile rows are the 16 row groups.  N is padded to the minimum UMMA N=16; weights are packed
-// [tap][8 co][64 ci] so the upper 8 columns read the next tap's rows and are simply never stored.
+// With only 3 output channels a direct implicit GEMM wastes the MMA's N dimension and re-reads the A operand
+// from shared memory once per tap (81 times).  Here the horizontal taps are folded into N instead:
+//
+//   Z[p][(s, co)] = sum_r sum_ci X[p + (r - pad, 0)][ci] * W[co][ci][r][s]        N = 3K (27 -> 32, 15 -> 16)
+//   out[q][co]    = b[co] + sum_s Z[q + (0, s - pad)][(s, co)]
+//
+// i.e. the vertical tap shift is applied to the INPUT (a row-shifted UMMA descriptor into the halo tile, K
+// descriptors instead of K*K), the horizontal tap shift to the OUTPUT (a shifted sum across neighbouring
+// pixels = neighbouring TMEM lanes, done with warp shuffles in the epilogue).  M tile = 8 rows x 16 pixels;
+// the 16 - (K-1) centre columns of a tile are complete, tiles overlap horizontally by K-1 pixels.
+// One 4-D TMA box brings the (8 + K-1) x 16 pixel halo (zero outside the image) as [rows][16 px][128 B]
+// SWIZZLE_128B, so every row shift is a whole number of 1024-byte swizzle atoms.
 #include "srk_common.cuh"
 #include "srk_tc_common.cuh"
 
@@ -18,14 +23,14 @@ namespace srk {
 using namespace tc;
 int* tc_err_flag();
 
-constexpr int TY = 16, TX = 8, KC = 64, NPAD = 8;
+constexpr int TY = 8, TXW = 16, KC = 64;
 constexpr int kThreads = 192;
 constexpr int MAX_STAGES = 4;
 
 struct SmallNParams {
-  int N, H, W, K, pad, cout;
+  int N, H, W, K, pad, cout, npad, xv;   // xv = valid output columns per tile
   int tiles_x, tiles_y, num_tiles;
-  int box_w, box_h, stage_bytes, stages, w_bytes;
+  int halo_rows, stage_bytes, stages, w_bytes;
   const float* bias;
   float* out;  // NCHW fp32
   int* err;
@@ -43,24 +48,29 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint
       ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld_32x4(uint32_t taddr, uint32_t* v) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
-               : "r"(taddr)
-               : "memory");
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
 }
 
+template <int K>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_smalln_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                       const SmallNParams p) {
+  constexpr int PAD = K / 2, NP = (K * 3 > 16) ? 32 : 16;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t hsm = smem_base;                                  // halo ring
-  const uint32_t wsm = smem_base + p.stages * p.stage_bytes;       // weights [taps][8][64] (+ slack)
+  const uint32_t wsm = smem_base + p.stages * p.stage_bytes;       // weights [K][NP][64]
   SmallNBarriers* bars = reinterpret_cast<SmallNBarriers*>(smem_al + p.stages * p.stage_bytes + p.w_bytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int S = p.stages, taps = p.K * p.K;
+  const int S = p.stages;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
@@ -69,7 +79,7 @@ conv_smalln_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(&bars->tmem_base), 32);
+    tmem_alloc(smem_u32(&bars->tmem_base), 64);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -84,31 +94,28 @@ conv_smalln_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       prefetch_tmap(&tmX);
       prefetch_tmap(&tmW);
       const uint32_t wbar = smem_u32(&bars->wfull);
-      const int wrows = taps * NPAD;
-      mbar_arrive_expect_tx(wbar, wrows * 128);
-      for (int r0 = 0; r0 < wrows; r0 += NPAD) tma_load_2d(wsm + r0 * 128, &tmW, wbar, 0, r0);
+      mbar_arrive_expect_tx(wbar, K * NP * 128);
+      for (int r = 0; r < K; ++r) tma_load_2d(wsm + r * NP * 128, &tmW, wbar, 0, r * NP);
     }
     __syncwarp();
     int s = 0;
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int n = tile / tiles_per_img, t2 = tile - n * tiles_per_img;
-      const int y0 = (t2 / p.tiles_x) * TY, x0 = (t2 % p.tiles_x) * TX;
+      const int y0 = (t2 / p.tiles_x) * TY, x0 = (t2 % p.tiles_x) * p.xv;
       if (!mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1, p.err, 21)) break;
       if (elect_one()) {
         const uint32_t fb = smem_u32(&bars->full[s]);
-        mbar_arrive_expect_tx(fb, p.box_w * p.box_h * 128);
-        tma_load_4d(hsm + s * p.stage_bytes, &tmX, fb, 0, x0 - p.pad, y0 - p.pad, n);
+        mbar_arrive_expect_tx(fb, p.halo_rows * TXW * 128);
+        tma_load_4d(hsm + s * p.stage_bytes, &tmX, fb, 0, x0 - PAD, y0 - PAD, n);
       }
       __syncwarp();
       if (++s == S) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    // MMA issuer: whole warp, one elected lane issues
-    constexpr uint32_t idesc = make_idesc_bf16(128, 16, 0, 0);
-    const uint32_t sbo = p.box_w * 128;
-    const uint64_t a_hi = make_smem_desc(0, 16, sbo, kLayoutSW128, 0) & 0xFFFFFFFF00000000ull;
-    const uint64_t b_hi = make_smem_desc(0, 16, 1024, kLayoutSW128, 0) & 0xFFFFFFFF00000000ull;
+    // MMA issuer: whole warp, one elected lane issues.  A(r) = halo + r * (16 px * 128 B): 1024-byte aligned.
+    constexpr uint32_t idesc = make_idesc_bf16(128, NP, 0, 0);
+    const uint64_t hi = make_smem_desc(0, 16, 1024, kLayoutSW128, 0) & 0xFFFFFFFF00000000ull;
     const uint32_t lo_base = (uint32_t)(make_smem_desc(0, 16, 1024, kLayoutSW128, 0) & 0xFFFFFFFFull);
     const uint32_t w_lo = lo_base + (wsm >> 4);
     bool ok = mbar_wait(smem_u32(&bars->wfull), 0, p.err, 22);
@@ -121,17 +128,14 @@ conv_smalln_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       ok = mbar_wait(smem_u32(&bars->full[s]), ph, p.err, 24);
       if (!ok) break;
       tc_fence_after();
-      const uint32_t halo_lo = lo_base + ((hsm + s * p.stage_bytes) >> 4), d_tmem = tmem_base + acc * 16;
+      const uint32_t halo_lo = lo_base + ((hsm + s * p.stage_bytes) >> 4), d_tmem = tmem_base + acc * 32;
       if (elect_one()) {
-        uint32_t row_lo = halo_lo, b_lo = w_lo;
-        for (int r = 0; r < p.K; ++r, row_lo += p.box_w * 8) {
-          uint32_t a_lo = row_lo;
-          for (int c = 0; c < p.K; ++c, a_lo += 8, b_lo += NPAD * 128 / 16) {
 #pragma unroll
-            for (int ks = 0; ks < KC / 16; ++ks)
-              umma_bf16(d_tmem, a_hi | (a_lo + 2 * ks), b_hi | (b_lo + 2 * ks), idesc, (r | c | ks) != 0);
-          }
-        }
+        for (int r = 0; r < K; ++r)
+#pragma unroll
+          for (int ks = 0; ks < KC / 16; ++ks)
+            umma_bf16(d_tmem, hi | (halo_lo + r * (TXW * 128 / 16) + 2 * ks), hi | (w_lo + r * (NP * 128 / 16) + 2 * ks),
+                      idesc, (r | ks) != 0);
         umma_commit(smem_u32(&bars->empty[s]));
         umma_commit(smem_u32(&bars->tfull[acc]));
       }
@@ -139,27 +143,40 @@ conv_smalln_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       if (++s == S) { s = 0; ph ^= 1; }
     }
   } else {
+    // epilogue: warp lg owns TMEM lanes 32 lg .. = tile rows 2 lg, 2 lg + 1 (16 pixels each)
     const int lg = warp & 3;
-    const int i = lg * 32 + lane, ty = i >> 3, tx = i & 7;
-    float b[4];
+    const int tyl = lane >> 4, tx = lane & 15, ty = lg * 2 + tyl;
+    float b[3];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) b[c] = (p.bias && c < p.cout) ? p.bias[c] : 0.f;
+    for (int c = 0; c < 3; ++c) b[c] = (p.bias && c < p.cout) ? p.bias[c] : 0.f;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       if (!mbar_wait(smem_u32(&bars->tfull[acc]), (it >> 1) & 1, p.err, 25)) break;
       tc_fence_after();
-      uint32_t v[4];
-      tmem_ld_32x4(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * 16, v);
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * 32;
+      tmem_ld_32x16(taddr, v);
+      if (NP == 32) tmem_ld_32x16(taddr + 16, v + 16);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(smem_u32(&bars->tempty[acc]));
-      const int n = tile / tiles_per_img, t2 = tile - n * tiles_per_img;
-      const int y = (t2 / p.tiles_x) * TY + ty, x = (t2 % p.tiles_x) * TX + tx;
-      if (y < p.H && x < p.W) {
+      // out[q][co] = sum_s Z[q + (s - PAD)][(s, co)]: the neighbour's value comes by shuffle
+      float o[3] = {b[0], b[1], b[2]};
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (c < p.cout) p.out[(((size_t)n * p.cout + c) * p.H + y) * p.W + x] = __uint_as_float(v[c]) + b[c];
+      for (int s = 0; s < K; ++s) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float z = __shfl_sync(0xffffffffu, __uint_as_float(v[s * 3 + c]), (lane + s - PAD) & 31);
+          o[c] += z;
+        }
+      }
+      const int n = tile / tiles_per_img, t2 = tile - n * tiles_per_img;
+      const int y = (t2 / p.tiles_x) * TY + ty, x = (t2 % p.tiles_x) * p.xv + tx - PAD;
+      if (tx >= PAD && tx < TXW - PAD && y < p.H && x < p.W) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          if (c < p.cout) p.out[(((size_t)n * p.cout + c) * p.H + y) * p.W + x] = o[c];
       }
     }
   }
@@ -167,14 +184,14 @@ conv_smalln_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 32);
+    tmem_dealloc(tmem_base, 64);
   }
 }
 
 bool conv_smalln_tc_ok(const srk_tensor* x, const srk_tensor* y, int cout, int r, int s) {
-  if (r != s || (r != 5 && r != 9 && r != 3 && r != 7)) return false;
+  if (r != s || (r != 5 && r != 9)) return false;
   if (x->layout != SRK_LAYOUT_ACT || x->dtype != SRK_BF16 || x->c != KC) return false;
-  if (y->layout != SRK_LAYOUT_IMAGE || cout > 4) return false;
+  if (y->layout != SRK_LAYOUT_IMAGE || cout > 3) return false;
   return true;
 }
 
@@ -194,7 +211,7 @@ static int make_tmap_act_4d(CUtensorMap* out, const srk_tensor* x, int box_w, in
   return 0;
 }
 
-// w_packed: SRK_PACK_FPROP_TC_N8 = bf16 [tap][8][64]
+// w_packed: SRK_PACK_FPROP_TC_N8 = bf16 [R][NP][64], row n = s * 3 + co, NP = 32 (9x9) or 16 (5x5)
 int conv_smalln_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout, int r,
                           const float* bias, cudaStream_t st) {
   static int smem_max = 0;
@@ -202,27 +219,32 @@ int conv_smalln_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* 
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    cudaFuncSetAttribute(conv_smalln_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    cudaFuncSetAttribute(conv_smalln_tc_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    cudaFuncSetAttribute(conv_smalln_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
   }
   SmallNParams p;
   p.N = x->n; p.H = x->h; p.W = x->w; p.K = r; p.pad = r / 2; p.cout = cout;
-  p.tiles_x = (p.W + TX - 1) / TX; p.tiles_y = (p.H + TY - 1) / TY;
+  p.npad = r * 3 > 16 ? 32 : 16;
+  p.xv = TXW - (r - 1);
+  p.tiles_x = (p.W + p.xv - 1) / p.xv; p.tiles_y = (p.H + TY - 1) / TY;
   const long long nt = (long long)p.N * p.tiles_x * p.tiles_y;
   SRK_REQUIRE(nt < (1LL << 31), "conv_smalln: too many tiles");
   p.num_tiles = (int)nt;
-  p.box_w = TX + r - 1; p.box_h = TY + r - 1;
-  p.stage_bytes = (p.box_w * p.box_h * 128 + 1023) / 1024 * 1024;
-  p.w_bytes = (r * r * NPAD * 128 + NPAD * 128 + 1023) / 1024 * 1024;  // + one tap of slack for the N=16 read
+  p.halo_rows = TY + r - 1;
+  p.stage_bytes = p.halo_rows * TXW * 128;                 // multiple of 2048
+  p.w_bytes = (r * p.npad * 128 + 1023) / 1024 * 1024;
   const int fixed = 1024 + p.w_bytes + (int)sizeof(SmallNBarriers);
   p.stages = (smem_max - fixed) / p.stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   SRK_REQUIRE(p.stages >= 1, "conv_smalln: not enough shared memory");
   p.bias = bias; p.out = (float*)y->data; p.err = tc_err_flag();
   CUtensorMap tmX, tmW;
-  if (make_tmap_act_4d(&tmX, x, p.box_w, p.box_h)) return 1;
-  if (make_tmap_2d_bf16(&tmW, w_packed, (uint64_t)r * r * NPAD, KC, KC, NPAD, KC, 128)) return 1;
+  if (make_tmap_act_4d(&tmX, x, TXW, p.halo_rows)) return 1;
+  if (make_tmap_2d_bf16(&tmW, w_packed, (uint64_t)r * p.npad, KC, KC, p.npad, KC, 128)) return 1;
   const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
-  conv_smalln_tc_kernel<<<grid, kThreads, fixed + p.stages * p.stage_bytes, st>>>(tmX, tmW, p);
+  const int smem = fixed + p.stages * p.stage_bytes;
+  if (r == 9) conv_smalln_tc_kernel<9><<<grid, kThreads, smem, st>>>(tmX, tmW, p);
+  else conv_smalln_tc_kernel<5><<<grid, kThreads, smem, st>>>(tmX, tmW, p);
   SRK_CUDA_LAUNCH_CHECK("conv_smalln_tc");
   return 0;
 }

@@ -206,13 +206,17 @@ __global__ void wgrad_fold_kernel(const float* __restrict__ ws, int parts, float
     }
     return;
   }
-  float s0 = 0.f, s1 = 0.f;
+  // 8 independent loads in flight per thread: the partials are L2 resident, the loop is latency bound
+  float acc[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) acc[u] = 0.f;
   int k = 0;
-  for (; k + 1 < parts; k += 2) {
-    s0 += ws[(size_t)k * (TAPS * KC * NT) + i];
-    s1 += ws[(size_t)(k + 1) * (TAPS * KC * NT) + i];
+  for (; k + 8 <= parts; k += 8) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] += ws[(size_t)(k + u) * (TAPS * KC * NT) + i];
   }
-  if (k < parts) s0 += ws[(size_t)k * (TAPS * KC * NT) + i];
+  for (; k < parts; ++k) acc[0] += ws[(size_t)k * (TAPS * KC * NT) + i];
+  const float s0 = (acc[0] + acc[1]) + (acc[2] + acc[3]), s1 = (acc[4] + acc[5]) + (acc[6] + acc[7]);
   const int co = i % NT, t = i / NT, ci = t % KC, tap = t / KC;
   if (ci0 + ci >= cin_total || co0 + co >= cout_total) return;  // zero-filled tail of a 96-channel tensor
   float* o = &dw[((size_t)(co0 + co) * cin_total + (ci0 + ci)) * TAPS + tap];
