@@ -202,6 +202,7 @@ def run_srk(args):
     lr_d, hr_d = lr_pin.to(dev), hr_pin.to(dev)
 
     def fwd_bwd(lr, hr):
+        ops.begin_step(device=dev)   # one memset serves every zero-initialised scratch tensor of the step
         opt.zero_grad()
         loss = crit(model(lr), hr)
         loss.backward()

@@ -12,7 +12,7 @@
 // Column k = KK of A is 1 for in-image pixels, so row KK of G is the column sum of T64 (a bias gradient for
 // free).  G stays in TMEM for the CTA's whole tile range and is flushed once with vector fp32 reductions.
 //
-// 10 warps: 0 TMA, 1 MMA issue, 2-5 im2col builders, 6-9 epilogue.
+// 14 warps: 0 TMA, 1 MMA issue, 2-9 im2col builders (two threads per pixel row), 10-13 epilogue.
 #include "srk_common.cuh"
 #include "srk_tc_common.cuh"
 
@@ -25,7 +25,8 @@ int zero_border(const srk_tensor* t, cudaStream_t st);
 namespace rgb {
 
 constexpr int TY = 16, TX = 8, TM = 128, NT = 64;
-constexpr int kThreads = 320;
+constexpr int kThreads = 448;   // warps: 0 TMA, 1 MMA, 2-9 im2col builders, 10-13 epilogue
+constexpr int kBuilders = 256;
 constexpr int SUB_BYTES = TM * 128;  // one [128 x 64 k] sub-tile of A
 
 struct Params {
@@ -45,7 +46,7 @@ struct Params {
 struct __align__(8) Barriers {
   uint64_t wfull, afull[2], aempty[2], tfull[2], tempty[2], yfull[2], yempty[2], done;
   uint32_t tmem_base;
-  float red3[4][3];
+  float red3[8][3];
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2,
@@ -63,7 +64,7 @@ struct Geo {
   static constexpr int KCH = KP / 64;
   static constexpr int HH = TY + K - 1, HW = TX + K - 1;
   static constexpr int HALO = 3 * HH * HW;              // bf16 elements
-  static constexpr int HALO_BYTES = (HALO * 2 + 1023) / 1024 * 1024;
+  static constexpr int HALO_BYTES = (2 * HALO * 2 + 1023) / 1024 * 1024;   // double buffered
   static constexpr int A_BYTES = KCH * SUB_BYTES;
   static constexpr int W_BYTES = KCH * NT * 128;
   static constexpr int T_BYTES = TM * 128;
@@ -90,7 +91,7 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&bars->wfull), 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&bars->afull[i]), 128);
+      mbar_init(smem_u32(&bars->afull[i]), kBuilders);
       mbar_init(smem_u32(&bars->aempty[i]), 1);
       mbar_init(smem_u32(&bars->tfull[i]), 1);
       mbar_init(smem_u32(&bars->tempty[i]), 1);
@@ -194,57 +195,80 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     }
     if (elect_one()) umma_commit(smem_u32(&bars->done));
     __syncwarp();
-  } else if (warp < 6) {
-    // ================= im2col builders =================
-    const int bi = threadIdx.x - 64, ty = bi >> 3, tx = bi & 7;
-    const __nv_bfloat16* hb = halo + ty * G::HW + tx;
+  } else if (warp < 10) {
+    // ================= im2col builders: thread (row, half) builds half of the K range of one pixel row ===========
+    const int bt = threadIdx.x - 64, bi = bt & 127, half = bt >> 7, ty = bi >> 3, tx = bi & 7;
+    constexpr int PER = (G::HALO + kBuilders - 1) / kBuilders;   // halo elements staged per thread
     float s3[3] = {0.f, 0.f, 0.f};
     const __nv_bfloat16 one = __float2bfloat16_rn(1.f), zero = __float2bfloat16_rn(0.f);
+    float pre[PER];
+    auto fetch = [&](int i) {   // global -> registers for tile i (issued one tile ahead of its use)
+      const int tile = blockIdx.x + i * gridDim.x;
+      const int n = tile / tiles_per_img, t2 = tile - n * tiles_per_img;
+      const int y0 = (t2 / p.tiles_x) * TY, x0 = (t2 % p.tiles_x) * TX;
+      const float* src = p.t3 + (size_t)n * 3 * p.H * p.W;
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        const int idx = bt + u * kBuilders;
+        float v = 0.f;
+        if (idx < G::HALO) {
+          const int c = idx / (G::HH * G::HW), rem = idx - c * (G::HH * G::HW);
+          const int hy = rem / G::HW, hx = rem - hy * G::HW;
+          const int gy = y0 + hy - PAD, gx = x0 + hx - PAD;
+          if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) v = __ldg(src + ((size_t)c * p.H + gy) * p.W + gx);
+        }
+        pre[u] = v;
+      }
+    };
+    if (my_tiles > 0) fetch(0);
     for (int i = 0; i < my_tiles; ++i) {
       const int tile = blockIdx.x + i * gridDim.x;
       const int n = tile / tiles_per_img, t2 = tile - n * tiles_per_img;
       const int y0 = (t2 / p.tiles_x) * TY, x0 = (t2 % p.tiles_x) * TX;
+      (void)n;
       const int buf = i & 1;
-      asm volatile("bar.sync 2, 128;" ::: "memory");  // everyone is done reading the previous halo
-      const float* src = p.t3 + (size_t)n * 3 * p.H * p.W;
-      for (int idx = bi; idx < G::HALO; idx += 128) {
-        const int c = idx / (G::HH * G::HW), rem = idx - c * (G::HH * G::HW);
-        const int hy = rem / G::HW, hx = rem - hy * G::HW;
-        const int gy = y0 + hy - PAD, gx = x0 + hx - PAD;
-        float v = 0.f;
-        if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) v = __ldg(src + ((size_t)c * p.H + gy) * p.W + gx);
-        halo[idx] = __float2bfloat16_rn(v);
+      __nv_bfloat16* hbuf = halo + buf * G::HALO;
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        const int idx = bt + u * kBuilders;
+        if (idx < G::HALO) hbuf[idx] = __float2bfloat16_rn(pre[u]);
       }
-      asm volatile("bar.sync 2, 128;" ::: "memory");
+      // one barrier per tile: the other halo buffer is only rewritten after everybody passed this point again
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (i + 1 < my_tiles) fetch(i + 1);
       if (!mbar_wait(smem_u32(&bars->aempty[buf]), ((i >> 1) & 1) ^ 1, p.err, 36)) break;
       const bool inside = (y0 + ty < p.H) && (x0 + tx < p.W);
+      const __nv_bfloat16* hb = hbuf + ty * G::HW + tx;
       uint8_t* arow = a_ptr + buf * G::A_BYTES + bi * 128;
 #pragma unroll
-      for (int j = 0; j < G::KP / 8; ++j) {
-        __nv_bfloat16 e[8];
+      for (int jh = 0; jh < G::KP / 16; ++jh) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          constexpr int dummy = 0;
-          (void)dummy;
-          const int k = j * 8 + t;
-          if (k < G::KK) {
-            const int tap = k / 3, c = k - tap * 3, r = tap / K, s = tap - r * K;
-            e[t] = hb[(c * G::HH + r) * G::HW + s];
-          } else if (k == G::KK) {
-            e[t] = inside ? one : zero;
-          } else {
-            e[t] = zero;
+        for (int hsel = 0; hsel < 2; ++hsel) {
+          if (hsel != half) continue;
+          const int j = hsel * (G::KP / 16) + jh;
+          __nv_bfloat16 e[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int k = j * 8 + t;
+            if (k < G::KK) {
+              const int tap = k / 3, c = k - tap * 3, r = tap / K, s = tap - r * K;
+              e[t] = hb[(c * G::HH + r) * G::HW + s];
+            } else if (k == G::KK) {
+              e[t] = inside ? one : zero;
+            } else {
+              e[t] = zero;
+            }
           }
+          uint4 q;
+          q.x = (uint32_t)__bfloat16_as_ushort(e[0]) | ((uint32_t)__bfloat16_as_ushort(e[1]) << 16);
+          q.y = (uint32_t)__bfloat16_as_ushort(e[2]) | ((uint32_t)__bfloat16_as_ushort(e[3]) << 16);
+          q.z = (uint32_t)__bfloat16_as_ushort(e[4]) | ((uint32_t)__bfloat16_as_ushort(e[5]) << 16);
+          q.w = (uint32_t)__bfloat16_as_ushort(e[6]) | ((uint32_t)__bfloat16_as_ushort(e[7]) << 16);
+          const int sub = j >> 3, jj = j & 7;
+          *reinterpret_cast<uint4*>(arow + sub * SUB_BYTES + ((jj ^ (bi & 7)) << 4)) = q;
         }
-        uint4 q;
-        q.x = (uint32_t)__bfloat16_as_ushort(e[0]) | ((uint32_t)__bfloat16_as_ushort(e[1]) << 16);
-        q.y = (uint32_t)__bfloat16_as_ushort(e[2]) | ((uint32_t)__bfloat16_as_ushort(e[3]) << 16);
-        q.z = (uint32_t)__bfloat16_as_ushort(e[4]) | ((uint32_t)__bfloat16_as_ushort(e[5]) << 16);
-        q.w = (uint32_t)__bfloat16_as_ushort(e[6]) | ((uint32_t)__bfloat16_as_ushort(e[7]) << 16);
-        const int sub = j >> 3, jj = j & 7;
-        *reinterpret_cast<uint4*>(arow + sub * SUB_BYTES + ((jj ^ (bi & 7)) << 4)) = q;
       }
-      if (p.db3 && inside) {
+      if (p.db3 && inside && half == 0) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) s3[c] += __bfloat162float(hb[(c * G::HH + PAD) * G::HW + PAD]);
       }
@@ -257,8 +281,13 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         float t = warp_sum(s3[c]);
         if (lane == 0) bars->red3[warp - 2][c] = t;
       }
-      asm volatile("bar.sync 2, 128;" ::: "memory");
-      if (bi < 3) atomicAdd(&p.db3[bi], bars->red3[0][bi] + bars->red3[1][bi] + bars->red3[2][bi] + bars->red3[3][bi]);
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (bt < 3) {
+        float t = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) t += bars->red3[w8][bt];
+        atomicAdd(&p.db3[bt], t);
+      }
     }
   } else {
     // ================= epilogue =================

@@ -97,7 +97,7 @@ def _conv_bn_forward(x, w, b, bn_params, bn_buffers, training, eps, momentum, al
     rm, rv, nbt = bn_buffers
     sums = None
     if ops.bn_needs_batch_stats(rm, training):  # the conv epilogue accumulates the batch statistics
-        sums = torch.zeros((2, w.shape[0]), dtype=torch.float32, device=x.device)
+        sums = ops.zeros((2, w.shape[0]), x.device)
     y, used_tc = ops.conv_fprop(x, False, w, b, L.ACT_NONE, None, None, 0, False, x.dtype, bn_sums=sums)
     out, stats = ops.bn_forward(y, gamma, beta, rm, rv, nbt, training, eps, momentum, alpha, residual, sums=sums)
     return y, out, stats

@@ -96,6 +96,44 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+# ---- zero-initialised scratch ------------------------------------------------------------------------
+# Many kernels accumulate small results with atomics (BN sums, PReLU-slope gradients, SE reductions) and need
+# zero-filled outputs.  Opt-in: a trainer calls begin_step() once per step; zeros() then hands out slices of one
+# buffer cleared by a single memset instead of launching a fill kernel per tensor.  Tensors obtained this way are
+# only valid until the next begin_step() (gradients must have been consumed by the optimizer by then).
+class _ZeroArena:
+    buf = None
+    off = 0
+    active = False
+
+
+def begin_step(nbytes=8 << 20, device=None):
+    if _ZeroArena.buf is None or _ZeroArena.buf.numel() < nbytes or (device is not None and _ZeroArena.buf.device != torch.device(device)):
+        _ZeroArena.buf = torch.empty((nbytes,), dtype=torch.uint8, device=device or "cuda")
+    _ZeroArena.buf.zero_()
+    _ZeroArena.off = 0
+    _ZeroArena.active = True
+
+
+def end_arena():
+    _ZeroArena.active = False
+
+
+def zeros(shape, device, dtype=torch.float32):
+    if isinstance(shape, int):
+        shape = (shape,)
+    n = 1
+    for d in shape:
+        n *= d
+    nbytes = n * torch.empty((), dtype=dtype).element_size()
+    a = _ZeroArena
+    if a.active and a.buf is not None and a.buf.device == torch.device(device) and a.off + nbytes + 256 <= a.buf.numel():
+        start = (a.off + 255) // 256 * 256
+        a.off = start + nbytes
+        return a.buf[start:start + nbytes].view(dtype).view(shape)
+    return torch.zeros(shape, dtype=dtype, device=device)
+
+
 # ---- weight packing ------------------------------------------------------------------------------
 _pack_cache = {}
 _weights_epoch = 0
@@ -198,7 +236,7 @@ def conv_rgbout_bwd(x, dout, weight, need_dx, need_bias):
     cout, cin, r, s = weight.shape
     n, _, h, w = geometry(x, False)
     dw = torch.zeros_like(weight, memory_format=torch.contiguous_format)
-    db = torch.zeros((cout,), dtype=torch.float32, device=weight.device)
+    db = zeros((cout,), weight.device)
     dx = new_act(n, cin, h, w, torch.bfloat16, x.device) if need_dx else None
     pk = packed_weight(weight, L.PACK_RGBOUT_DGRAD_TC, 0) if need_dx else None
     ws = _rgb_workspace(r, x.device)
@@ -311,7 +349,7 @@ def act_bwd(dout, out, act, alpha, unshuffle, perm_tc=False):
         dz = new_act(n, 4 * c, h // 2, w // 2, out.dtype, out.device)
     else:
         dz = torch.empty_like(out)
-    dalpha = torch.zeros((1,), dtype=torch.float32, device=out.device) if act == L.ACT_PRELU else None
+    dalpha = zeros((1,), out.device) if act == L.ACT_PRELU else None
     L.call("srk_act_bwd", act_desc(dout), act_desc(out), act_desc(dz), act, _ptr(alpha), _ptr(dalpha),
            unshuffle, 1 if perm_tc else 0, stream_ptr())
     return dz, dalpha
@@ -332,7 +370,7 @@ def bn_forward(y, gamma, beta, running_mean, running_var, nbt, training, eps, mo
     st = stream_ptr()
     if training or running_mean is None:
         if sums is None:
-            sums = torch.zeros((2, c), dtype=torch.float32, device=dev)
+            sums = zeros((2, c), dev)
             L.call("srk_bn_stats", act_desc(y), sums[0].data_ptr(), sums[1].data_ptr(), st)
         upd = training and running_mean is not None
         L.call("srk_bn_finalize", sums[0].data_ptr(), sums[1].data_ptr(), c, n * h * w, eps, momentum,
@@ -351,7 +389,7 @@ def bn_backward(dout, y, stats, gamma, beta, alpha, batch_stats):
     """-> (dy, dgamma, dbeta, dalpha or None)"""
     c = y.shape[3]
     dev = y.device
-    red = torch.zeros((2 * c + 1,), dtype=torch.float32, device=dev)
+    red = zeros((2 * c + 1,), dev)
     dgamma, dbeta, dalpha = red[:c], red[c:2 * c], red[2 * c:]
     mean, invstd = stats[0], stats[1]
     st = stream_ptr()
@@ -390,7 +428,7 @@ def se_backward(dout, r, pool, hidden, gate, w1, w2, scale):
     cr = w1.shape[0]
     dev = r.device
     st = stream_ptr()
-    dgate_raw = torch.zeros((n, c), dtype=torch.float32, device=dev)
+    dgate_raw = zeros((n, c), dev)
     L.call("srk_se_bwd_reduce", act_desc(dout), act_desc(r), dgate_raw.data_ptr(), st)
     dw1 = torch.zeros_like(w1, memory_format=torch.contiguous_format)
     dw2 = torch.zeros_like(w2, memory_format=torch.contiguous_format)
