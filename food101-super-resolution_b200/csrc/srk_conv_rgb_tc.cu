@@ -12,7 +12,7 @@
 // Column k = KK of A is 1 for in-image pixels, so row KK of G is the column sum of T64 (a bias gradient for
 // free).  G stays in TMEM for the CTA's whole tile range and is flushed once with vector fp32 reductions.
 //
-// 14 warps: 0 TMA, 1 MMA issue, 2-9 im2col builders (two threads per pixel row), 10-13 epilogue.
+// 18 warps: 0 TMA, 1 MMA issue, 2-9 im2col builders (two threads per pixel row), 10-17 epilogue.
 #include "srk_common.cuh"
 #include "srk_tc_common.cuh"
 
@@ -25,7 +25,7 @@ int zero_border(const srk_tensor* t, cudaStream_t st);
 namespace rgb {
 
 constexpr int TY = 16, TX = 8, TM = 128, NT = 64;
-constexpr int kThreads = 448;   // warps: 0 TMA, 1 MMA, 2-9 im2col builders, 10-13 epilogue
+constexpr int kThreads = 576;   // warps: 0 TMA, 1 MMA, 2-9 im2col builders, 10-17 epilogue
 constexpr int kBuilders = 256;
 constexpr int SUB_BYTES = TM * 128;  // one [128 x 64 k] sub-tile of A
 
@@ -96,7 +96,7 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       mbar_init(smem_u32(&bars->tfull[i]), 1);
       mbar_init(smem_u32(&bars->tempty[i]), 1);
       mbar_init(smem_u32(&bars->yfull[i]), 1);
-      mbar_init(smem_u32(&bars->yempty[i]), 128);
+      mbar_init(smem_u32(&bars->yempty[i]), 256);
     }
     mbar_init(smem_u32(&bars->done), 1);
     fence_barrier_init();
@@ -290,57 +290,60 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       }
     }
   } else {
-    // ================= epilogue =================
-    const int lg = warp & 3, ei = lg * 32 + lane, ty = ei >> 3, tx = ei & 7;
+    // ================= epilogue: 8 warps; two warps share a TMEM lane group and split the 64 columns ==========
+    const int lg = warp & 3, ch = (warp - 10) >> 2, c0 = ch * 32;
+    const int ei = lg * 32 + lane, ty = ei >> 3, tx = ei & 7;
     if (p.do_y) {
       const float alpha = (p.act == SRK_ACT_PRELU) ? p.alpha[0] : 0.f;
       const int Hp = p.H + 2, Wp = p.W + 2;
+      float bias[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) bias[j] = (p.bias && c0 + j < p.n_valid) ? __ldg(p.bias + p.y_col0 + c0 + j) : 0.f;
       for (int i = 0; i < my_tiles; ++i) {
         const int buf = i & 1;
         if (!mbar_wait(smem_u32(&bars->yfull[buf]), (i >> 1) & 1, p.err, 37)) break;
         tc_fence_after();
-        uint32_t v[NT];
-        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + buf * NT;
-        tmem_ld_32x32(taddr, v);
-        tmem_ld_32x32(taddr + 32, v + 32);
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + buf * NT + c0, v);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(smem_u32(&bars->yempty[buf]));
         const int tile = blockIdx.x + i * gridDim.x;
         const int n = tile / tiles_per_img, t2 = tile - n * tiles_per_img;
         const int y = (t2 / p.tiles_x) * TY + ty, x = (t2 % p.tiles_x) * TX + tx;
-        if (y >= p.H || x >= p.W) continue;
-        uint4* dst = reinterpret_cast<uint4*>(p.y + (((size_t)n * Hp + y + 1) * Wp + x + 1) * p.y_stride + p.y_col0);
+        if (y >= p.H || x >= p.W || c0 >= p.n_valid) continue;
+        uint4* dst = reinterpret_cast<uint4*>(p.y + (((size_t)n * Hp + y + 1) * Wp + x + 1) * p.y_stride + p.y_col0 + c0);
+        uint4 o[4];
 #pragma unroll
-        for (int j = 0; j < NT / 8; ++j) {
-          if (j * 8 >= p.n_valid) break;
+        for (int j = 0; j < 4; ++j) {
           float f[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            float a = __uint_as_float(v[j * 8 + e]) + (p.bias ? __ldg(p.bias + p.y_col0 + j * 8 + e) : 0.f);
+            float a = __uint_as_float(v[j * 8 + e]) + bias[j * 8 + e];
             if (p.act == SRK_ACT_RELU) a = fmaxf(a, 0.f);
             else if (p.act == SRK_ACT_PRELU) a = a > 0.f ? a : alpha * a;
             f[e] = a;
           }
           __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
           __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
-          dst[j] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
-                              *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+          o[j] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                            *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (c0 + j * 8 < p.n_valid) dst[j] = o[j];
       }
     }
     if (p.do_g && my_tiles > 0 && mbar_wait(smem_u32(&bars->done), 0, p.err, 38)) {
       tc_fence_after();
 #pragma unroll 1
       for (int mh = 0; mh < NG; ++mh) {
-        uint32_t v[NT];
-        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + 2 * NT + mh * NT;
-        tmem_ld_32x32(taddr, v);
-        tmem_ld_32x32(taddr + 32, v + 32);
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + 2 * NT + mh * NT + c0, v);
         tmem_ld_wait();
-        float* dst = p.ws + (size_t)(mh * 128 + ei) * NT;
+        float* dst = p.ws + (size_t)(mh * 128 + ei) * NT + c0;
 #pragma unroll
-        for (int j = 0; j < NT / 4; ++j)
+        for (int j = 0; j < 8; ++j)
           asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j),
                        "f"(__uint_as_float(v[4 * j])), "f"(__uint_as_float(v[4 * j + 1])),
                        "f"(__uint_as_float(v[4 * j + 2])), "f"(__uint_as_float(v[4 * j + 3]))

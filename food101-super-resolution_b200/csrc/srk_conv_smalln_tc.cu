@@ -13,7 +13,7 @@
 // descriptors instead of K*K), the horizontal tap shift to the OUTPUT (a shifted sum across neighbouring
 // pixels = neighbouring TMEM lanes, done with warp shuffles in the epilogue).  M tile = 8 rows x 16 pixels;
 // the 16 - (K-1) centre columns of a tile are complete, tiles overlap horizontally by K-1 pixels.
-// One 4-D TMA box brings the (8 + K-1) x 16 pixel halo (zero outside the image) as [rows][16 px][128 B]
+// One 4-D TMA box brings the (4 + K-1) x 32 pixel halo (zero outside the image) as [rows][32 px][128 B]
 // SWIZZLE_128B, so every row shift is a whole number of 1024-byte swizzle atoms.
 #include "srk_common.cuh"
 #include "srk_tc_common.cuh"
@@ -23,7 +23,7 @@ namespace srk {
 using namespace tc;
 int* tc_err_flag();
 
-constexpr int TY = 8, TXW = 16, KC = 64;
+constexpr int TY = 4, TXW = 32, KC = 64;   // M tile = 4 rows x 32 pixels: 32 - (K-1) of 32 columns are complete
 constexpr int kThreads = 192;
 constexpr int MAX_STAGES = 4;
 
@@ -113,7 +113,7 @@ conv_smalln_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       if (++s == S) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    // MMA issuer: whole warp, one elected lane issues.  A(r) = halo + r * (16 px * 128 B): 1024-byte aligned.
+    // MMA issuer: whole warp, one elected lane issues.  A(r) = halo + r * (32 px * 128 B): 1024-byte aligned.
     constexpr uint32_t idesc = make_idesc_bf16(128, NP, 0, 0);
     const uint64_t hi = make_smem_desc(0, 16, 1024, kLayoutSW128, 0) & 0xFFFFFFFF00000000ull;
     const uint32_t lo_base = (uint32_t)(make_smem_desc(0, 16, 1024, kLayoutSW128, 0) & 0xFFFFFFFFull);
@@ -143,9 +143,9 @@ conv_smalln_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       if (++s == S) { s = 0; ph ^= 1; }
     }
   } else {
-    // epilogue: warp lg owns TMEM lanes 32 lg .. = tile rows 2 lg, 2 lg + 1 (16 pixels each)
+    // epilogue: warp lg owns TMEM lanes 32 lg .. = tile row lg (32 pixels)
     const int lg = warp & 3;
-    const int tyl = lane >> 4, tx = lane & 15, ty = lg * 2 + tyl;
+    const int tx = lane, ty = lg;
     float b[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) b[c] = (p.bias && c < p.cout) ? p.bias[c] : 0.f;
