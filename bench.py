@@ -56,6 +56,17 @@ def peaks():
     return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/r1_conv3x3_ncu.json); None when the summary is missing."""
+    p = os.path.join(ROOT, "profiles", "r1_conv3x3_ncu.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return {"bytes": d["dram_bytes_read"] + d["dram_bytes_write"], "algorithmic_bytes": d["algorithmic_bytes"],
+            "tensor_pipe_active_pct": d["tensor_pipe_active_pct"], "source": "profiles/r1_conv3x3_ncu.json"}
+
+
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -334,7 +345,7 @@ def run_srk(args):
         ach = flops / (avg_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "conv3x3_c64_fprop(%s)" % ("tcgen05" if key[8] else "cuda-core"),
                 "achieved": round(ach, 2), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": round(ach / pk["tf_sustained"], 4), "traffic": None, "avg_ms": round(avg_ms, 4),
+                "frac": round(ach / pk["tf_sustained"], 4), "traffic": ncu_traffic(), "avg_ms": round(avg_ms, 4),
                 "launches_per_step": count, "peak_source": pk["src"] + " bf16 sustained"}
     step_tf = world * B * FWD_BWD_GFLOP_PER_IMG / (ms_step * 1e-3) / 1e3
     line = {"metric": "sr_train_images_per_sec", "value": round(value, 2), "unit": "images/s", "n_gpus": world,
