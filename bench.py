@@ -225,6 +225,7 @@ def run_srk(args):
         if averager is not None:
             averager.unpack()
         opt.step()
+        ops.repack_all()             # all weight packs of the next step in one launch
 
     def step(lr, hr):
         loss = fwd_bwd(lr, hr)
@@ -281,7 +282,7 @@ def run_srk(args):
         step(lr_s, hr_s)
     if use_graph:
         barrier()
-        ops.bump_weights_epoch()          # every weight pack is re-done inside the captured step
+        ops.repack_all()                  # packs are current; inside the graphs only finish() refreshes them
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):

@@ -314,16 +314,16 @@ int conv_wgrad_simt_launch(const srk_tensor* x, const srk_tensor* dy, float* dw,
 
 // ---------------------------------------------------------------------------------------------
 // weight packing from OIHW fp32 master weights
-__global__ void pack_weights_kernel(const float* __restrict__ w, void* __restrict__ out, int Cout,
-                                    int Cin, int R, int S, int kind, int shuffle) {
+__device__ __forceinline__ void pack_weights_body(const float* __restrict__ w, void* __restrict__ out, int Cout,
+                                                  int Cin, int R, int S, int kind, int shuffle, long long bx,
+                                                  long long gx) {
   long long total = (long long)Cout * Cin * R * S;
   const int NPn8 = S * 3 > 16 ? 32 : 16;
   if (kind == SRK_PACK_FPROP_TC_N8) total = (long long)R * NPn8 * Cin;
   const int KPr = (R * S * 3 + 1 + 63) / 64 * 64;
   if (kind == SRK_PACK_RGBOUT_DGRAD_TC) total = 64LL * KPr;
   if (kind == SRK_PACK_RGBIN_TC) total = (long long)Cout * KPr;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  for (long long i = bx * (long long)blockDim.x + threadIdx.x; i < total; i += gx * blockDim.x) {
     // i indexes the OUTPUT linearly
     if (kind == SRK_PACK_RGBIN_TC || kind == SRK_PACK_RGBOUT_DGRAD_TC) {  // bf16 [64][KP]
       int k = (int)(i % KPr), n = (int)(i / KPr);
@@ -372,6 +372,24 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, void* __restric
   }
 }
 
+__global__ void pack_weights_kernel(const float* __restrict__ w, void* __restrict__ out, int Cout, int Cin, int R,
+                                    int S, int kind, int shuffle) {
+  pack_weights_body(w, out, Cout, Cin, R, S, kind, shuffle, blockIdx.x, gridDim.x);
+}
+
+// Many packs in one launch: the table travels by value (CUDA-graph capturable); blockIdx.y selects the entry.
+constexpr int PACK_MT = 64;
+struct PackTable {
+  const float* w[PACK_MT];
+  void* out[PACK_MT];
+  short cout[PACK_MT], cin[PACK_MT];
+  signed char r[PACK_MT], kind[PACK_MT];
+};
+__global__ void pack_weights_multi_kernel(const PackTable tb) {
+  const int t = blockIdx.y;
+  pack_weights_body(tb.w[t], tb.out[t], tb.cout[t], tb.cin[t], tb.r[t], tb.r[t], tb.kind[t], 0, blockIdx.x, gridDim.x);
+}
+
 }  // namespace srk
 
 using namespace srk;
@@ -400,5 +418,25 @@ extern "C" int srk_weight_pack(const float* w_oihw, void* out, int cout, int cin
   if (blocks > 148 * 8) blocks = 148 * 8;
   pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, out, cout, cin, r, s, kind, pixel_shuffle);
   SRK_CUDA_LAUNCH_CHECK("pack_weights");
+  return 0;
+}
+
+extern "C" int srk_weight_pack_multi(int count, const float* const* w_oihw, void* const* out, const int32_t* cout,
+                                     const int32_t* cin, const int32_t* r, const int32_t* kind, void* stream) {
+  SRK_REQUIRE(count >= 0, "srk_weight_pack_multi: negative count");
+  for (int base = 0; base < count; base += PACK_MT) {
+    PackTable tb;
+    const int c = count - base < PACK_MT ? count - base : PACK_MT;
+    for (int i = 0; i < PACK_MT; ++i) {
+      const int j = base + (i < c ? i : 0);
+      SRK_REQUIRE(kind[j] >= 0 && kind[j] <= 6 && cout[j] > 0 && cout[j] < 32768 && cin[j] > 0 && cin[j] < 32768 &&
+                      r[j] >= 1 && r[j] <= 11,
+                  "srk_weight_pack_multi: bad entry %d", j);
+      tb.w[i] = w_oihw[j]; tb.out[i] = out[j];
+      tb.cout[i] = (short)cout[j]; tb.cin[i] = (short)cin[j]; tb.r[i] = (signed char)r[j]; tb.kind[i] = (signed char)kind[j];
+    }
+    pack_weights_multi_kernel<<<dim3(64, c), 256, 0, (cudaStream_t)stream>>>(tb);
+    SRK_CUDA_LAUNCH_CHECK("pack_weights_multi");
+  }
   return 0;
 }

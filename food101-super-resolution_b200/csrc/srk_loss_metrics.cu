@@ -169,12 +169,14 @@ __global__ void __launch_bounds__(256) nlpd_bwd_down_kernel(const signed char* _
     int y = (int)(t % h2); int nc = (int)(t / h2);
     const signed char* sp = sign + (long long)nc * H * W;
     float acc = 0.f;
-    for (int Y = max(2 * y - 3, 0); Y <= min(2 * y + 4, H - 1); ++Y) {
+    // an exact 2x level touches fine rows / columns 2y-1 .. 2y+2 only; other ratios get the wider safe window
+    const int ry = (H == 2 * h2) ? 1 : 3, rx = (W == 2 * w2) ? 1 : 3;
+    for (int Y = max(2 * y - ry, 0); Y <= min(2 * y + ry + 1, H - 1); ++Y) {
       int y0, y1; float ly;
       bilin_src(Y, sy, h2, y0, y1, ly);
       float wy = (y0 == y ? 1.f - ly : 0.f) + (y1 == y ? ly : 0.f);
       if (wy == 0.f) continue;
-      for (int X = max(2 * x - 3, 0); X <= min(2 * x + 4, W - 1); ++X) {
+      for (int X = max(2 * x - rx, 0); X <= min(2 * x + rx + 1, W - 1); ++X) {
         int x0, x1; float lx;
         bilin_src(X, sx, w2, x0, x1, lx);
         float wx = (x0 == x ? 1.f - lx : 0.f) + (x1 == x ? lx : 0.f);
@@ -204,14 +206,13 @@ __global__ void __launch_bounds__(256) nlpd_bwd_up_kernel(const signed char* __r
     const float* gp = g_down + (long long)nc * h2 * w2;
     float acc = c_l * (float)sign[i];
     // blurred[yy][xx] reads cur[yy+ky-2][xx+kx-2]; only even (yy,xx) are kept as down[yy/2][xx/2]
-#pragma unroll
-    for (int ky = 0; ky < 5; ++ky) {
+    // only taps with Y + 2 - ky even (and likewise in x) land on a kept sample: step the taps by 2
+    for (int ky = Y & 1; ky < 5; ky += 2) {
       int yy = Y + 2 - ky;
-      if (yy < 0 || (yy & 1) || (yy >> 1) >= h2) continue;
-#pragma unroll
-      for (int kx = 0; kx < 5; ++kx) {
+      if (yy < 0 || (yy >> 1) >= h2) continue;
+      for (int kx = X & 1; kx < 5; kx += 2) {
         int xx = X + 2 - kx;
-        if (xx < 0 || (xx & 1) || (xx >> 1) >= w2) continue;
+        if (xx < 0 || (xx >> 1) >= w2) continue;
         acc = fmaf(k[ky * 5 + kx], gp[(long long)(yy >> 1) * w2 + (xx >> 1)], acc);
       }
     }

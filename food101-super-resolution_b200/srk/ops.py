@@ -178,6 +178,37 @@ def packed_weight(weight, kind, shuffle):
     return pk
 
 
+def repack_all():
+    """Refreshes every cached weight pack in one multi-tensor launch and marks it current.  Call right after an
+    optimizer step (srk.optim.Adam bumps the epoch): the next forward / backward then finds all packs ready
+    instead of launching ~70 small pack kernels on first use."""
+    import ctypes
+    srcs, dsts, couts, cins, rs, kinds, ents = [], [], [], [], [], [], []
+    for ent in list(_pack_cache.values()):
+        ref = ent.get("ref")
+        w = ref() if ref is not None else None
+        if w is None or w.data_ptr() != ent["ptr"]:
+            continue
+        cout, cin, r, s = w.shape
+        if r != s:
+            continue
+        for (kind, shuffle), pk in ent["packs"].items():
+            if shuffle != 0:
+                continue
+            srcs.append(w.data_ptr()); dsts.append(pk.data_ptr())
+            couts.append(cout); cins.append(cin); rs.append(r); kinds.append(kind)
+        ents.append((ent, w))
+    n = len(srcs)
+    if n == 0:
+        return 0
+    vp = lambda v: (ctypes.c_void_p * n)(*v)
+    ip = lambda v: (ctypes.c_int32 * n)(*v)
+    L.call("srk_weight_pack_multi", n, vp(srcs), vp(dsts), ip(couts), ip(cins), ip(rs), ip(kinds), stream_ptr())
+    for ent, w in ents:
+        ent["ver"] = (w._version, _weights_epoch)
+    return n
+
+
 def tc_supported(cin, cout, r, s, dtype, shuffle):
     """0 = CUDA cores, 1 = tcgen05 ACT->ACT conv, 2 = tcgen05 RGB-output conv (ACT -> IMAGE)"""
     if cfg.conv_impl == "simt" or dtype != torch.bfloat16:

@@ -108,6 +108,9 @@ int srk_conv_rgb_bwd(const srk_tensor* img3, const srk_tensor* t64, const void* 
 int srk_weight_pack(const float* w_oihw, void* out, int cout, int cin, int r, int s, int kind,
                     int pixel_shuffle, void* stream);
 int64_t srk_weight_pack_bytes(int cout, int cin, int r, int s, int kind);
+/* `count` packs (square kernels, pixel_shuffle = 0) in ceil(count / 64) launches; host arrays of device pointers */
+int srk_weight_pack_multi(int count, const float* const* w_oihw, void* const* out, const int32_t* cout,
+                          const int32_t* cin, const int32_t* r, const int32_t* kind, void* stream);
 
 /* ---- activation backward: _prelu_kernel_backward / threshold_backward (+ pixel_unshuffle) ----
  * out: saved post-activation tensor; dout: its gradient; dz: gradient of the pre-activation in

@@ -469,3 +469,59 @@ def test_srcnn_bf16_step_all_tensor_core_shapes():
     assert rel_err(out.cpu(), out_ref) <= 1e-2
     for k, p in model.named_parameters():
         assert rel_err(p.grad.cpu(), grads_ref[k], floor=1e-4) <= 3e-2, k
+
+
+def test_full_size_conv_adjoint_identities():
+    """BASELINE config C2 layer size ([64, 64, 64, 64], 3x3 64->64, too big for the CPU oracle): size-independent
+    properties of the tensor-core kernels.  With y = conv(x, W) (no bias):  <g, y> = <dgrad(g), x> = <wgrad(x, g), W>,
+    conv is linear in x, and the bias gradient is the plain sum of g."""
+    import srk
+    from srk import ops
+    srk.set_compute_dtype("bf16")
+    g_ = torch.Generator(device=DEV).manual_seed(11)
+
+    def act(scale):
+        t = (torch.randn(64, 66, 66, 64, generator=g_, device=DEV) * scale).bfloat16()
+        t[:, 0] = 0; t[:, -1] = 0; t[:, :, 0] = 0; t[:, :, -1] = 0
+        return t
+
+    x, x2, g = act(1.0), act(1.0), act(1.0)
+    w = (torch.randn(64, 64, 3, 3, generator=g_, device=DEV) / 24).bfloat16().float()
+    y, used_tc = ops.conv_fprop(x, False, w, None, 0, None, None, 0, False, torch.bfloat16)
+    assert used_tc
+    dx = ops.conv_dgrad(g, False, w, None, torch.bfloat16)
+    dw, db = ops.conv_wgrad(x, False, g, False, w, True)
+    a = (g.float() * y.float()).sum().item()
+    b = (dx.float() * x.float()).sum().item()
+    c = (dw * w).sum().item()
+    scale = (g.float().norm() * y.float().norm()).item()
+    assert abs(a - b) <= 2e-3 * scale and abs(a - c) <= 2e-3 * scale, (a, b, c, scale)
+    # bias gradient = per-channel sum of g (fp32 accumulation of bf16 values)
+    want_db = g.float().sum(dim=(0, 1, 2))
+    assert rel_err(db.cpu(), want_db.cpu()) <= 1e-4
+    # linearity: conv(x + x2) == conv(x) + conv(x2) up to bf16 rounding of the three outputs
+    xs = (x.float() + x2.float()).bfloat16()
+    y2, _ = ops.conv_fprop(x2, False, w, None, 0, None, None, 0, False, torch.bfloat16)
+    ys, _ = ops.conv_fprop(xs, False, w, None, 0, None, None, 0, False, torch.bfloat16)
+    lin = (ys.float() - y.float() - y2.float()).abs().max().item()
+    assert lin <= 3e-2 * ys.float().abs().max().item(), lin
+    # zero border invariant at full size
+    assert float(y[:, 0].abs().max()) == 0 and float(y[:, :, -1].abs().max()) == 0
+    assert float(dx[:, -1].abs().max()) == 0 and float(dx[:, :, 0].abs().max()) == 0
+
+
+def test_full_size_psnr_ssim_properties():
+    """512x512 images (config C4 size): PSNR(x, x + c) analytic, SSIM symmetric and 1 on identical inputs."""
+    from src.metrics import psnr_from_sse, psnr_ssim_sums
+    g_ = torch.Generator(device=DEV).manual_seed(12)
+    x = torch.rand(8, 3, 512, 512, generator=g_, device=DEV) * 0.8
+    y = (x + 0.05 * torch.randn(x.shape, generator=g_, device=DEV)).clamp(0, 1)
+    sse, ss = psnr_ssim_sums(x + 0.1, x, clamp=False)
+    assert abs(psnr_from_sse(float(sse.sum()), x.numel()) - 20.0) <= 0.01
+    _, s_xy = psnr_ssim_sums(x, y)
+    _, s_yx = psnr_ssim_sums(y, x)
+    _, s_xx = psnr_ssim_sums(x, x)
+    n_win = 3 * 502 * 502
+    assert max_abs(s_xy.cpu(), s_yx.cpu()) <= 1e-6 * n_win
+    assert max_abs(s_xx.cpu() / n_win, torch.ones(8, dtype=torch.float64)) <= 1e-6
+    assert float((s_xy / n_win).max()) < 1.0
