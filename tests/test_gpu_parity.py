@@ -107,10 +107,12 @@ def test_bf16_resnet_step_realistic_size():
         assert e <= tol, (k, e)
 
 
-def test_bf16_attention_step_realistic_size():
+@pytest.mark.parametrize("channels", [64, 96])
+def test_bf16_attention_step_realistic_size(channels):
+    """AttentionSR at 64 channels and at the reference width of 96 (64 + 32 channel chunks on the tensor cores)."""
     from src import models as M
     torch.manual_seed(2)
-    model = M.AttentionSR(num_channels=64, num_residuals=2)
+    model = M.AttentionSR(num_channels=channels, num_residuals=2)
     lr, hr = O.synthetic_pair(4, 24, 24, 4, seed=9)
     (e_max, e_rms), errs = _bf16_vs_oracle("AttentionSR", model, lr, hr, "mae")
     assert e_rms <= 2e-2 and e_max <= 2e-2, (e_max, e_rms)
