@@ -1,0 +1,549 @@
+// tcgen05 / TMEM / TMA implicit-GEMM 3x3 convolution with the three HORIZONTAL taps folded into the MMA N
+// dimension (fprop, and dgrad through rotated weights) on the zero-bordered channels-last bf16 layout.
+//
+// Why: with N = 64 a tcgen05.mma M128 K16 is bound by shared-memory operand delivery (A 4 KB + B 2 KB per MMA at
+// 128 B/cycle = 48 cycles against a 32-cycle tensor floor, measured, scratch/ldtm_rate.py).  Folding the taps
+// s = 0,1,2 of one kernel row into N (N = 3 x 64 = 192) reads the A operand once per kernel ROW instead of once
+// per tap: 12 MMAs of 96 cycles per tile (measured 96 = floor) instead of 36 of 48.
+//
+// GEMM view (reference: nn.Conv2d 3x3 s1 p1 at models.py:46,49,65,67,113,117,120):
+//   D_s[q, co] = sum_{r, ci} X[q + (r-1)*(W+2), ci] * W[r][s][co][ci]          (accumulator slot s, TMEM columns)
+//   Y[p, co]   = D_0[p-1, co] + D_1[p, co] + D_2[p+1, co]                      (epilogue: shift across TMEM lanes)
+// q runs over ALL padded pixels (a vertical tap is a constant shift of the flat pixel index because the border is
+// zero).  A tile is 128 consecutive padded pixels q0..q0+127 and produces the 126 outputs q0+1..q0+126, so
+// consecutive tiles overlap by two pixels.  The +-1 lane shift is two warp shuffles per output value; the two
+// values per warp that cross a warp boundary go through a 4 KB shared-memory exchange buffer.
+//
+// One persistent CTA per SM, 352 threads: warp 0 TMA producer (halo slab [128 + 2(W+2) rows][64 ch] per tile,
+// weights once), warp 1 MMA issuer, warps 2-9 epilogue (two per TMEM lane group, 32 output channels each),
+// warp 10 output TMA store / residual TMA load.  Accumulators are double buffered in TMEM (2 x 192 columns).
+#include "srk_common.cuh"
+#include "srk_tc_common.cuh"
+
+#include <cstdlib>
+
+namespace srk {
+
+int* tc_err_flag();
+extern long long* g_tc_trace;
+int zero_border(const srk_tensor* t, cudaStream_t st);
+
+namespace fold {
+
+using namespace tc;
+
+constexpr int TM = 128;              // pixels per tile (UMMA M)
+constexpr int TMO = 126;             // output pixels per tile
+constexpr int NT = 64;               // output channels per pass (one accumulator slot)
+constexpr int KC = 64;               // contraction channels per pass: one 128-byte swizzle row
+constexpr int W_BYTES = 9 * NT * KC * 2;   // 72 KB: [r][s][co][ci]
+constexpr int SLAB_BOX_ROWS = 32;
+constexpr int kThreads = 352;
+constexpr int O_TILE_BYTES = TM * NT * 2;  // bf16 output tile staged for the TMA store (126 rows used)
+constexpr int XCH_BYTES = 2 * 2 * 4 * 2 * 32 * 4;  // [acc][column half][lane group][slot 0 / slot 2][32 floats]
+constexpr int BIAS_BYTES = 256;
+constexpr int MAX_STAGES = 4;
+constexpr int ACC_COLS = 256;        // TMEM column stride between the two accumulator buffers
+
+struct Params {
+  int P, Hp, Wp, num_tiles;
+  int k_col0;          // first contraction channel of this pass
+  int w_row_per_tap;   // rows per tap in the packed weight matrix (= total output channels)
+  int w_row0;          // first weight row of this pass
+  int cout_total;      // channels per pixel of y
+  int cout_off;        // channel offset inside a y row
+  int act, shuffle;
+  int slab_rows, stages, stage_bytes;
+  int n_cols;          // output channels of this pass: 64 or 32
+  int ksteps;          // 16-channel K steps of this pass: 4 or 2
+  float* partial_out;  // chunked contraction: fp32 partial sums [P][64] written instead of y ...
+  const float* partial_in;  // ... and added back (before the activation) by the next chunk
+  const float* bias;
+  int bias_off;
+  const float* alpha;
+  int has_residual;
+  __nv_bfloat16* y;
+  int Hp2, Wp2;        // padded sizes of the pixel-shuffled output
+  float* stats_sum;
+  float* stats_sumsq;
+  int* err;
+  long long* trace;    // bring-up: per-tile clock64 stamps of CTA 0 ([16][32]) or null (general instantiation)
+  int dbg;             // bring-up knobs (general instantiation only): 1 no stores, 2 no MMAs, 4 no A loads,
+                       // 8 no lane shifts / exchange, 16 centre slot only
+};
+
+struct __align__(8) Barriers {
+  uint64_t full[MAX_STAGES], empty[MAX_STAGES], wfull, tfull[2], tempty[2];
+  uint64_t oready[2], ofree[2], rfull[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <bool kFast, bool kStats>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                       const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
+                       const Params p) {
+  const int n_cols = kFast ? NT : p.n_cols;
+  const int ksteps = kFast ? KC / 16 : p.ksteps;
+  float* const partial_out = kFast ? nullptr : p.partial_out;
+  const float* const partial_in = kFast ? nullptr : p.partial_in;
+  float* const stats_sum = kStats ? p.stats_sum : nullptr;
+  float* const stats_sumsq = kStats ? p.stats_sumsq : nullptr;
+  const int dbg = kFast ? 0 : p.dbg;
+  long long* const trace = kFast ? nullptr : p.trace;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic smem: [weights 72 KB][A ring][2 output tiles][exchange][bias][barriers]
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t wsm = smem_base;
+  const uint32_t asm0 = smem_base + W_BYTES;
+  const uint32_t osm = asm0 + p.stages * p.stage_bytes;
+  uint8_t* optr = smem_al + W_BYTES + p.stages * p.stage_bytes;
+  float* xch = reinterpret_cast<float*>(optr + 2 * O_TILE_BYTES);
+  float* bias_s = reinterpret_cast<float*>(optr + 2 * O_TILE_BYTES + XCH_BYTES);
+  Barriers* bars = reinterpret_cast<Barriers*>(optr + 2 * O_TILE_BYTES + XCH_BYTES + BIAS_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.stages;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
+    mbar_init(smem_u32(&bars->wfull), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bars->tfull[i]), 1); mbar_init(smem_u32(&bars->tempty[i]), 256);
+      mbar_init(smem_u32(&bars->oready[i]), 256); mbar_init(smem_u32(&bars->ofree[i]), 1);
+      mbar_init(smem_u32(&bars->rfull[i]), 1);
+    }
+    fence_barrier_init();
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 128) {
+    const int c = threadIdx.x - 64;
+    bias_s[c] = (p.bias && c < n_cols) ? __ldg(p.bias + p.bias_off + c) : 0.f;
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&bars->tmem_base), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (elect_one()) {
+      prefetch_tmap(&tmA);
+      prefetch_tmap(&tmW);
+      const uint32_t wbar = smem_u32(&bars->wfull);
+      mbar_arrive_expect_tx(wbar, 9 * n_cols * KC * 2);
+      for (int t = 0; t < 9; ++t)   // smem order [r][s][n_cols rows]: the three s of a row are one N = 3 n_cols tile
+        tma_load_2d(wsm + t * n_cols * KC * 2, &tmW, wbar, p.k_col0, t * p.w_row_per_tap + p.w_row0);
+    }
+    __syncwarp();
+    int s = 0;
+    uint32_t ph = 0;
+    bool ok = true;
+    for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
+      ok = mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1, p.err, 1);
+      if (!ok) break;
+      if (elect_one()) {
+        const uint32_t fb = smem_u32(&bars->full[s]);
+        if (dbg & 4) {
+          mbar_arrive(fb);
+        } else {
+          mbar_arrive_expect_tx(fb, p.slab_rows * KC * 2);
+          const int row0 = tile * TMO - 1 - p.Wp;
+          for (int j = 0; j < p.slab_rows / SLAB_BOX_ROWS; ++j)
+            tma_load_2d(asm0 + s * p.stage_bytes + j * SLAB_BOX_ROWS * KC * 2, &tmA, fb, p.k_col0,
+                        row0 + j * SLAB_BOX_ROWS);
+        }
+        if (trace && blockIdx.x == 0 && tile / (int)gridDim.x < 32) trace[0 * 32 + tile / gridDim.x] = clock64();
+      }
+      __syncwarp();
+      if (++s == S) { s = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    const uint32_t idesc = make_idesc_bf16(TM, 3 * n_cols, 0, 0);
+    const uint64_t desc_hi = make_smem_desc(0, 16, 1024, kLayoutSW128, 0) & 0xFFFFFFFF00000000ull;
+    const uint32_t lo_base = (uint32_t)(make_smem_desc(0, 16, 1024, kLayoutSW128, 0) & 0xFFFFFFFFull);
+    const uint32_t w_lo = lo_base + (wsm >> 4), a_lo0 = lo_base + (asm0 >> 4);
+    const uint32_t row_units = (uint32_t)p.Wp * (KC * 2 / 16);   // one image row of the slab, in 16-byte units
+    const uint32_t wrow_units = (uint32_t)(3 * n_cols) * (KC * 2 / 16);   // one kernel row of weights
+    const uint32_t stage_units = (uint32_t)p.stage_bytes >> 4;
+    bool ok = mbar_wait(smem_u32(&bars->wfull), 0, p.err, 2);
+    int s = 0, it = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      ok = mbar_wait(smem_u32(&bars->tempty[acc]), ((it >> 1) & 1) ^ 1, p.err, 3);
+      if (!ok) break;
+      ok = mbar_wait(smem_u32(&bars->full[s]), ph, p.err, 4);
+      if (!ok) break;
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+      const uint32_t a_lo = a_lo0 + s * stage_units;
+      if (elect_one()) {
+        if (trace && blockIdx.x == 0 && it < 32) trace[1 * 32 + it] = clock64();
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int ks = 0; ks < KC / 16; ++ks)
+            if (ks < ksteps && !(dbg & 2))
+              umma_bf16(d_tmem, desc_hi | (a_lo + r * row_units + 2 * ks), desc_hi | (w_lo + r * wrow_units + 2 * ks),
+                        idesc, (r | ks) != 0);
+        umma_commit(smem_u32(&bars->empty[s]));
+        umma_commit(smem_u32(&bars->tfull[acc]));
+        if (trace && blockIdx.x == 0 && it < 32) trace[2 * 32 + it] = clock64();
+      }
+      __syncwarp();
+      if (++s == S) { s = 0; ph ^= 1; }
+    }
+  } else if (warp == 10) {
+    // ================= output store / residual load warp (plain, non-PixelShuffle outputs) =================
+    if (p.shuffle == 0 && partial_out == nullptr && !(dbg & 1)) {
+      const int my_tiles = blockIdx.x < p.num_tiles ? (p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+      if (p.has_residual && elect_one()) {
+        prefetch_tmap(&tmR);
+        for (int it = 0; it < 2 && it < my_tiles; ++it) {
+          const uint32_t rb = smem_u32(&bars->rfull[it]);
+          mbar_arrive_expect_tx(rb, TMO * NT * 2);
+          tma_load_2d(osm + it * O_TILE_BYTES, &tmR, rb, p.cout_off, (blockIdx.x + it * gridDim.x) * TMO);
+        }
+      }
+      __syncwarp();
+      for (int it = 0; it < my_tiles; ++it) {
+        const int b = it & 1;
+        if (!mbar_wait(smem_u32(&bars->oready[b]), (it >> 1) & 1, p.err, 6)) break;
+        if (elect_one()) {
+          if (trace && blockIdx.x == 0 && it < 32) trace[12 * 32 + it] = clock64();
+          tma_store_2d(&tmY, osm + b * O_TILE_BYTES, p.cout_off, (blockIdx.x + it * gridDim.x) * TMO);
+          tma_store_commit();
+          tma_store_wait_read0();
+          if (trace && blockIdx.x == 0 && it < 32) trace[13 * 32 + it] = clock64();
+          if (p.has_residual && it + 2 < my_tiles) {
+            const uint32_t rb = smem_u32(&bars->rfull[b]);
+            mbar_arrive_expect_tx(rb, TMO * NT * 2);
+            tma_load_2d(osm + b * O_TILE_BYTES, &tmR, rb, p.cout_off, (blockIdx.x + (it + 2) * gridDim.x) * TMO);
+          }
+          mbar_arrive(smem_u32(&bars->ofree[b]));
+        }
+        __syncwarp();
+      }
+      if (elect_one()) tma_store_wait_all();
+      __syncwarp();
+    }
+  } else {
+    // ================= epilogue: 8 warps, warp e owns TMEM lanes 32*(warp&3).. and 32 of the 64 channels ====
+    const int e = warp - 2, lg = warp & 3, ch = e >> 2;
+    const int c0 = ch * 32;
+    const float alpha = (p.act == SRK_ACT_PRELU) ? __ldg(p.alpha) : 0.f;
+    const int img = p.Hp * p.Wp;
+    const bool active = c0 < n_cols;
+    const bool staged = p.shuffle == 0 && partial_out == nullptr && !(dbg & 1);
+    float s1[32], s2[32];
+    if (stats_sum) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+    }
+    // after a protocol error every wait is skipped, but all warps keep running the same tile sequence so that
+    // the named barriers below stay matched (a hung bar.sync would hang the GPU)
+    bool ok = true;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int row = lg * 32 + lane;
+      const int pix = tile * TMO - 1 + row;
+      const bool is_out = row >= 1 && row <= TMO && pix < p.P;
+      const int pc = is_out ? pix : 0;
+      const int n = pc / img, q = pc - n * img;
+      const int yy = q / p.Wp, xx = q - yy * p.Wp;
+      const bool interior = is_out && yy >= 1 && yy <= p.Hp - 2 && xx >= 1 && xx <= p.Wp - 2;
+      const bool tr = trace && blockIdx.x == 0 && it < 32 && threadIdx.x == 64;
+      if (tr) trace[3 * 32 + it] = clock64();
+      if (ok) ok = mbar_wait(smem_u32(&bars->tfull[acc]), (it >> 1) & 1, p.err, 5);
+      tc_fence_after();
+      if (tr) trace[4 * 32 + it] = clock64();
+      uint8_t* orow = optr + acc * O_TILE_BYTES + (row - 1) * 128;
+      if (!active) {
+        tc_fence_before();
+        mbar_arrive(smem_u32(&bars->tempty[acc]));
+        if (staged) {
+          if (ok) ok = mbar_wait(smem_u32(&bars->ofree[acc]), ((it >> 1) & 1) ^ 1, p.err, 7);
+          if (ok && p.has_residual) ok = mbar_wait(smem_u32(&bars->rfull[acc]), (it >> 1) & 1, p.err, 8);
+          mbar_arrive(smem_u32(&bars->oready[acc]));
+        }
+        continue;
+      }
+      float f[32];
+      {
+        uint32_t v1[32], v0[32];
+        const uint32_t tbase = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * ACC_COLS + c0;
+        float* xw = xch + (((acc * 2 + ch) * 4 + lg) * 2) * 32;
+        tmem_ld_32x32(tbase + n_cols, v1);        // slot 1: this pixel
+        if (!(dbg & 16)) tmem_ld_32x32(tbase, v0);                 // slot 0: belongs to the pixel one lane up
+        tmem_ld_wait();
+        if (tr) trace[5 * 32 + it] = clock64();
+        if (lane == 31 && !(dbg & 8)) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            reinterpret_cast<uint4*>(xw)[j] = make_uint4(v0[4 * j], v0[4 * j + 1], v0[4 * j + 2], v0[4 * j + 3]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b4 = reinterpret_cast<const float4*>(bias_s + c0)[j];
+          f[4 * j] = __uint_as_float(v1[4 * j]) + b4.x; f[4 * j + 1] = __uint_as_float(v1[4 * j + 1]) + b4.y;
+          f[4 * j + 2] = __uint_as_float(v1[4 * j + 2]) + b4.z; f[4 * j + 3] = __uint_as_float(v1[4 * j + 3]) + b4.w;
+        }
+        if (!(dbg & 8)) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float t = __uint_as_float(__shfl_up_sync(0xffffffffu, v0[j], 1));
+            f[j] += lane > 0 ? t : 0.f;
+          }
+        }
+        if (!(dbg & 16)) {
+          tmem_ld_32x32(tbase + 2 * n_cols, v0);    // slot 2: belongs to the pixel one lane down
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        mbar_arrive(smem_u32(&bars->tempty[acc]));
+        if (tr) trace[6 * 32 + it] = clock64();
+        if (lane == 0 && !(dbg & 8)) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            reinterpret_cast<uint4*>(xw + 32)[j] = make_uint4(v0[4 * j], v0[4 * j + 1], v0[4 * j + 2], v0[4 * j + 3]);
+        }
+        if (!(dbg & 8)) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float t = __uint_as_float(__shfl_down_sync(0xffffffffu, v0[j], 1));
+            f[j] += lane < 31 ? t : 0.f;
+          }
+        }
+      }
+      if (tr) trace[7 * 32 + it] = clock64();
+      if (!(dbg & 8)) named_bar_sync(1 + ch, 128);   // the four warps of this column half have published their edge values
+      if (tr) trace[8 * 32 + it] = clock64();
+      if (dbg & 1) continue;
+      if (lane == 0 && lg > 0) {
+        const float4* src = reinterpret_cast<const float4*>(xch + (((acc * 2 + ch) * 4 + lg - 1) * 2) * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 t = src[j];
+          f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
+        }
+      }
+      if (lane == 31 && lg < 3) {
+        const float4* src = reinterpret_cast<const float4*>(xch + (((acc * 2 + ch) * 4 + lg + 1) * 2 + 1) * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 t = src[j];
+          f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
+        }
+      }
+      if (partial_in && is_out) {   // fp32 partial sums of the earlier contraction chunks
+        const float4* pin = reinterpret_cast<const float4*>(partial_in + (long long)pix * NT + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 q4 = __ldg(pin + j);
+          f[4 * j] += q4.x; f[4 * j + 1] += q4.y; f[4 * j + 2] += q4.z; f[4 * j + 3] += q4.w;
+        }
+      }
+      if (partial_out) {              // not the last chunk: keep fp32, no activation, nothing goes to y
+        if (is_out) {
+          float4* po = reinterpret_cast<float4*>(partial_out + (long long)pix * NT + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) po[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        }
+        continue;
+      }
+      if (staged && ok) ok = mbar_wait(smem_u32(&bars->ofree[acc]), ((it >> 1) & 1) ^ 1, p.err, 7);
+      if (tr) trace[9 * 32 + it] = clock64();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float a = f[j];
+        if (p.act == SRK_ACT_RELU) a = fmaxf(a, 0.f);
+        else if (p.act == SRK_ACT_PRELU) a = a > 0.f ? a : alpha * a;
+        f[j] = a;
+      }
+      if (p.shuffle == 2) {
+        // PixelShuffle(2) as a store remap (models.py:118,121): column j of this pass is reference channel
+        // co = cout_off + c0 + j = 4c + sub  ->  output pixel (2y + sub/2, 2x + sub%2), channel c.
+        if (!interior) continue;
+#pragma unroll
+        for (int sub = 0; sub < 4; ++sub) {
+          const long long o2 =
+              ((long long)n * p.Hp2 + (2 * (yy - 1) + (sub >> 1) + 1)) * p.Wp2 + (2 * (xx - 1) + (sub & 1) + 1);
+          uint4* dst = reinterpret_cast<uint4*>(p.y + o2 * p.cout_total + (p.cout_off + c0) / 4);
+          dst[0] = make_uint4(pack_bf16x2(f[sub], f[4 + sub]), pack_bf16x2(f[8 + sub], f[12 + sub]),
+                              pack_bf16x2(f[16 + sub], f[20 + sub]), pack_bf16x2(f[24 + sub], f[28 + sub]));
+        }
+        continue;
+      }
+      if (interior && stats_sum) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { s1[j] += f[j]; s2[j] = fmaf(f[j], f[j], s2[j]); }
+      }
+      const bool has_row = row >= 1 && row <= TMO;
+      if (p.has_residual) {
+        if (ok) ok = mbar_wait(smem_u32(&bars->rfull[acc]), (it >> 1) & 1, p.err, 8);
+        if (has_row) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 rr = *reinterpret_cast<const uint4*>(orow + (((ch * 4 + j) ^ ((row - 1) & 7)) << 4));
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { float2 u = __bfloat1622float2(h[t]); f[8 * j + 2 * t] += u.x; f[8 * j + 2 * t + 1] += u.y; }
+          }
+        }
+      }
+      if (has_row) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 o = make_uint4(0, 0, 0, 0);
+          if (interior)
+            o = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                           pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+          *reinterpret_cast<uint4*>(orow + (((ch * 4 + j) ^ ((row - 1) & 7)) << 4)) = o;
+        }
+      }
+      if (tr) trace[10 * 32 + it] = clock64();
+      fence_proxy_async();
+      mbar_arrive(smem_u32(&bars->oready[acc]));
+      if (tr) trace[11 * 32 + it] = clock64();
+    }
+    if (stats_sum) {
+      // per-thread partial sums over this CTA's pixels -> per-channel totals: transposed butterfly (lane l
+      // ends up owning column l), then one atomic per lane
+#pragma unroll
+      for (int half = 16; half >= 1; half >>= 1) {
+        const bool up = (lane & half) != 0;
+#pragma unroll
+        for (int j = 0; j < half; ++j) {
+          float k1 = up ? s1[j + half] : s1[j], o1 = up ? s1[j] : s1[j + half];
+          float k2 = up ? s2[j + half] : s2[j], o2 = up ? s2[j] : s2[j + half];
+          s1[j] = k1 + __shfl_xor_sync(0xffffffffu, o1, half);
+          s2[j] = k2 + __shfl_xor_sync(0xffffffffu, o2, half);
+        }
+      }
+      if (active && p.cout_off + c0 + lane < p.cout_total) {
+        atomicAdd(stats_sum + p.cout_off + c0 + lane, s1[0]);
+        atomicAdd(stats_sumsq + p.cout_off + c0 + lane, s2[0]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace fold
+
+// Returns 0 ok, 1 error, -1 "not applicable" (image too wide for two slab stages: the caller uses the
+// per-tap kernel of srk_conv_tc.cu).
+int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout,
+                           const float* bias, int act, const float* alpha, const srk_tensor* residual, int shuffle,
+                           float* stats_sum, float* stats_sumsq, void* workspace, cudaStream_t st) {
+  using namespace fold;
+  const int cin = x->c;
+  const int Hp = x->h + 2, Wp = x->w + 2;
+  const long long P = (long long)x->n * Hp * Wp;
+  SRK_REQUIRE(P < (1LL << 31) - 4096, "conv_fold: too many pixels");
+  static int smem_max = 0;
+  if (!smem_max) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaFuncSetAttribute(conv3x3_fold_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    cudaFuncSetAttribute(conv3x3_fold_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    cudaFuncSetAttribute(conv3x3_fold_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+  }
+  const int slab_rows = ((TM + 2 * Wp) + SLAB_BOX_ROWS - 1) / SLAB_BOX_ROWS * SLAB_BOX_ROWS;
+  const int fixed = 1024 + W_BYTES + 2 * O_TILE_BYTES + XCH_BYTES + BIAS_BYTES + (int)sizeof(Barriers);
+  const int stage_bytes = slab_rows * KC * 2;
+  int stages = (smem_max - fixed) / stage_bytes;
+  if (stages < 2) return -1;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  const int smem_bytes = fixed + stages * stage_bytes;
+
+  CUtensorMap tmA;
+  if (make_tmap_2d_bf16(&tmA, x->data, (uint64_t)P, (uint64_t)cin, (uint64_t)cin, SLAB_BOX_ROWS, KC, 128)) return 1;
+  CUtensorMap tmY = tmA, tmR = tmA;  // output store / residual load maps (plain outputs only)
+  if (shuffle == 0) {
+    if (make_tmap_2d_bf16(&tmY, y->data, (uint64_t)P, (uint64_t)cout, (uint64_t)cout, TMO, NT, 128)) return 1;
+    tmR = tmY;
+    if (residual && make_tmap_2d_bf16(&tmR, residual->data, (uint64_t)P, (uint64_t)cout, (uint64_t)cout, TMO, NT, 128))
+      return 1;
+  }
+
+  Params p;
+  p.P = (int)P; p.Hp = Hp; p.Wp = Wp;
+  p.num_tiles = (int)((P + TMO - 1) / TMO);
+  p.w_row_per_tap = cout;
+  p.slab_rows = slab_rows; p.stages = stages; p.stage_bytes = stage_bytes;
+  p.alpha = alpha;
+  p.y = (__nv_bfloat16*)y->data;
+  p.shuffle = shuffle;
+  p.Hp2 = y->h + 2; p.Wp2 = y->w + 2;
+  p.err = tc_err_flag();
+  { const char* e = getenv("SRK_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
+  p.trace = g_tc_trace;
+  p.stats_sum = stats_sum; p.stats_sumsq = stats_sumsq;
+  const int nchunks = (cout + NT - 1) / NT, kchunks = (cin + KC - 1) / KC;
+  SRK_REQUIRE(stats_sum == nullptr || (kchunks == 1 && shuffle == 0 && act == SRK_ACT_NONE && residual == nullptr),
+              "conv_fold: fused BN statistics need a plain Cin == 64 conv");
+  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  for (int nc = 0; nc < nchunks; ++nc) {
+    const int n_cols = cout - nc * NT < NT ? cout - nc * NT : NT;
+    CUtensorMap tmW;
+    if (make_tmap_2d_bf16(&tmW, w_packed, (uint64_t)9 * cout, (uint64_t)cin, (uint64_t)cin, n_cols, KC, 128)) return 1;
+    for (int kc = 0; kc < kchunks; ++kc) {
+      const bool first = kc == 0, last = kc == kchunks - 1;
+      p.k_col0 = kc * KC;
+      p.w_row0 = nc * NT;
+      p.cout_total = y->c;
+      p.cout_off = nc * NT;
+      p.bias_off = nc * NT;
+      p.n_cols = n_cols;
+      p.ksteps = (cin - kc * KC < KC ? cin - kc * KC : KC) / 16;
+      p.bias = first ? bias : nullptr;
+      p.act = last ? act : SRK_ACT_NONE;
+      // chunked contractions: see srk_conv_tc.cu (bf16 partial sums through y without an activation, fp32 partial
+      // sums through the workspace when an activation / PixelShuffle follows)
+      const bool fp32_partials = kchunks > 1 && (act != SRK_ACT_NONE || shuffle != 0);
+      if (fp32_partials) {
+        p.has_residual = (last && residual) ? 1 : 0;
+        p.partial_out = last ? nullptr : (float*)workspace;
+        p.partial_in = first ? nullptr : (const float*)workspace;
+        SRK_REQUIRE(workspace != nullptr, "conv_fold: Cin > 64 with an activation needs the fprop workspace");
+      } else {
+        p.has_residual = first ? (residual ? 1 : 0) : 1;
+        p.partial_out = nullptr;
+        p.partial_in = nullptr;
+      }
+      const CUtensorMap& tmRes = (fp32_partials || first) ? tmR : tmY;
+      const bool fast = kchunks == 1 && p.n_cols == NT && p.ksteps == KC / 16 && p.dbg == 0 && p.trace == nullptr;
+      SRK_REQUIRE(fast || stats_sum == nullptr, "conv_fold: fused BN statistics need the single-chunk 64 -> 64 pass");
+      if (fast && stats_sum) conv3x3_fold_tc_kernel<true, true><<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, tmRes, p);
+      else if (fast) conv3x3_fold_tc_kernel<true, false><<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, tmRes, p);
+      else conv3x3_fold_tc_kernel<false, false><<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, tmRes, p);
+      SRK_CUDA_LAUNCH_CHECK("conv3x3_fold_tc");
+    }
+  }
+  if (shuffle == 2) return zero_border(y, st);
+  return 0;
+}
+
+}  // namespace srk

@@ -462,7 +462,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 // ---- host launcher ---------------------------------------------------------------------------------------
 static int g_tc_mode = -1;
-static long long* g_tc_trace = nullptr;
+long long* g_tc_trace = nullptr;
 void tc_set_trace(long long* t) { g_tc_trace = t; }
 int tc_mode() {
   if (g_tc_mode < 0) {
@@ -499,6 +499,19 @@ int tc_read_err_flag() {
   return v;
 }
 
+// srk_conv_fold_tc.cu: 3x3 kernel with the horizontal taps folded into N (the default for 3x3)
+int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout,
+                           const float* bias, int act, const float* alpha, const srk_tensor* residual, int shuffle,
+                           float* stats_sum, float* stats_sumsq, void* workspace, cudaStream_t st);
+static int g_tc_fold = -1;
+int tc_fold() {
+  if (g_tc_fold < 0) {
+    const char* e = getenv("SRK_TC_FOLD");
+    g_tc_fold = e ? (atoi(e) != 0) : 0;   // off until its epilogue beats the per-tap kernel
+  }
+  return g_tc_fold;
+}
+
 int64_t conv_fprop_tc_workspace(const srk_tensor* x) {
   if (x->c <= KC) return 0;  // (needed when an activation or PixelShuffle follows a chunked contraction)
   return (int64_t)x->n * (x->h + 2) * (x->w + 2) * NT * (int64_t)sizeof(float);
@@ -515,6 +528,11 @@ bool conv_tc_shape_ok(int cin, int cout, int r, int s, int dtype, int shuffle) {
 int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout, int r, int s,
                          const float* bias, int act, const float* alpha, const srk_tensor* residual, int shuffle,
                          float* stats_sum, float* stats_sumsq, void* workspace, cudaStream_t st) {
+  if (r == 3 && tc_fold()) {
+    const int rc = conv_fprop_fold_launch(x, y, w_packed, cout, bias, act, alpha, residual, shuffle, stats_sum,
+                                          stats_sumsq, workspace, st);
+    if (rc >= 0) return rc;   // -1: slab does not fit (very wide images) -> per-tap kernel below
+  }
   const int cin = x->c;
   const int Hp = x->h + 2, Wp = x->w + 2;
   const long long P = (long long)x->n * Hp * Wp;
@@ -624,13 +642,24 @@ int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w
 
 }  // namespace srk
 
-namespace srk { int probe_mma_rate(int n, int a_row_off, int mn_major, float* out_host); }
+namespace srk {
+int probe_mma_rate(int n, int a_row_off, int mn_major, float* out_host);
+int probe_ldtm_rate(int nwarps, int batch, float* out_host);
+}
 
 // Test / bring-up hook: variant 0..2 selects the A-staging mode of the tcgen05 conv (see the header
 // comment); any other value leaves it unchanged.  out_host[0] = the device-side protocol-error flag
 // (0 = none; it is cleared by the call), out_host[1] = the mode now in effect.  Synchronises the device.
 extern "C" int srk_tc_probe(int variant, float* out_host, int out_len) {
   if (variant >= 0 && variant <= 2) srk::tc_set_mode(variant);
+  if (variant == 10 || variant == 11) { srk::tc_fold(); srk::g_tc_fold = variant - 10; }  // folded-tap 3x3 kernel off / on
+  if (variant == 20 && out_host && out_len >= 2) {   // query: out[1] = 1 when the folded-tap kernel is the default
+    out_host[0] = 0.f;
+    out_host[1] = (float)srk::tc_fold();
+    return 0;
+  }
+  if (variant >= 2000 && variant < 3000 && out_host && out_len >= 2)   // 2000 + nwarps + 100 * batch: TMEM read rate
+    return srk::probe_ldtm_rate((variant - 2000) % 100, (variant - 2000) / 100, out_host);
   if (variant >= 1000 && out_host && out_len >= 2) {
     // 1000 + n/8 + 100 * a_row_off + 10000 * mn_major: sustained MMA rate microbenchmark
     int v = variant - 1000;
@@ -638,9 +667,19 @@ extern "C" int srk_tc_probe(int variant, float* out_host, int out_len) {
   }
   static long long* trace = nullptr;
   if (variant == 100) {
-    if (!trace) cudaMalloc(&trace, 6 * 32 * sizeof(long long));
-    cudaMemset(trace, 0, 6 * 32 * sizeof(long long));
+    if (!trace) cudaMalloc(&trace, 16 * 32 * sizeof(long long));
+    cudaMemset(trace, 0, 16 * 32 * sizeof(long long));
     srk::tc_set_trace(trace);
+  }
+  if (variant == 102 && trace && out_host && out_len >= 16 * 32) {   // 16-row trace of the folded-tap kernel
+    long long h[16 * 32];
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost);
+    long long mn = 0;
+    for (int i = 0; i < 16 * 32; ++i) if (h[i] && (mn == 0 || h[i] < mn)) mn = h[i];
+    for (int i = 0; i < 16 * 32; ++i) out_host[i] = h[i] ? (float)(h[i] - mn) : -1.f;
+    srk::tc_set_trace(nullptr);
+    return 0;
   }
   if (variant == 101 && trace && out_host && out_len >= 6 * 32) {
     long long h[6 * 32];

@@ -69,4 +69,48 @@ int probe_mma_rate(int n, int a_row_off, int mn_major, float* out_host) {
   out_host[1] = (float)h[1] / (4.f * iters);
   return 0;
 }
+
+// TMEM read rate: `nwarps` warps (4 or 8; warp w reads lane group w & 3) loop tcgen05.ld.32x32b.x32 (4 KB per
+// instruction); `batch` loads are issued back to back before each tcgen05.wait::ld.
+__global__ void __launch_bounds__(256, 1) ldtm_rate_kernel(int iters, int batch, long long* out) {
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) { tmem_alloc(smem_u32(&tmem_slot), 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot + ((uint32_t)((warp & 3) * 32) << 16);
+  uint32_t v[32], acc = 0;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+    for (int b = 0; b < batch; ++b) {
+      tmem_ld_32x32(tmem + (((warp >> 2) * 8 + b) & 15) * 32, v);
+      if (b == batch - 1) tmem_ld_wait();
+    }
+    acc += v[0] ^ v[31];
+  }
+  const long long t1 = clock64();
+  if (acc == 0x12345678u) out[2] = acc;
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = t1 - t0;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_slot, 512); }
+}
+
+// out_host[0] = cycles per 4 KB tcgen05.ld per warp, out_host[1] = TMEM bytes read per cycle per SM
+int probe_ldtm_rate(int nwarps, int batch, float* out_host) {
+  long long* d = nullptr;
+  if (cudaMalloc(&d, 4 * sizeof(long long)) != cudaSuccess) SRK_FAIL("probe: cudaMalloc failed");
+  const int iters = 2000;
+  ldtm_rate_kernel<<<148, nwarps * 32>>>(iters, batch, d);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long h[2] = {0, 0};
+  cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) SRK_FAIL("probe: %s", cudaGetErrorString(e));
+  out_host[0] = (float)h[0] / ((float)iters * batch);
+  out_host[1] = 4096.f * nwarps * iters * batch / (float)h[0];
+  return 0;
+}
 }  // namespace srk

@@ -19,6 +19,9 @@ fns = {
     'wgrad': lambda: ops.conv_wgrad(x, False, dz, False, wt, True),
     'wgrad_nobias': lambda: ops.conv_wgrad(x, False, dz, False, wt, False),
 }
+only = os.environ.get('ONLY')
+if only:
+    fns = {k: f for k, f in fns.items() if k in only.split(',')}
 for f in fns.values():
     for _ in range(2): f()
 torch.cuda.synchronize()
@@ -35,5 +38,4 @@ def t(f, n=20):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
-only = os.environ.get('ONLY')
 print(' | '.join("%s %.2f us" % (k, 1e3 * t(f)) for k, f in fns.items() if not only or k in only.split(',')), flush=True)

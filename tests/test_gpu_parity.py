@@ -147,6 +147,10 @@ CONV_CASES = [
     (64, 64, 1, 7, 9, 2, "relu", 0),
     (64, 3, 5, 11, 9, 2, "none", 0),
     (32, 32, 3, 5, 5, 1, "none", 0),
+    (64, 64, 3, 33, 47, 2, "none", 0),      # many 126-pixel tiles, ragged last tile, two images
+    (96, 96, 3, 20, 17, 2, "prelu", 0),     # 64 + 32 channel chunks over several tiles
+    (64, 256, 3, 20, 20, 1, "prelu", 2),
+    (128, 64, 3, 12, 30, 2, "relu", 0),     # two full contraction chunks
 ]
 
 
@@ -208,6 +212,25 @@ def test_conv_forward_backward_vs_oracle(cin, cout, k, h, w, n, act, shuffle, dt
     # the zero border of the activation layout must survive every kernel
     assert float(ya[:, 0].abs().max()) == 0 and float(ya[:, -1].abs().max()) == 0
     assert float(ya[:, :, 0].abs().max()) == 0 and float(ya[:, :, -1].abs().max()) == 0
+
+
+@pytest.mark.parametrize("cin,cout,k,h,w,n,act,shuffle", [c for c in CONV_CASES if c[2] == 3 and c[0] >= 64])
+@pytest.mark.parametrize("fold", [0, 1])
+def test_conv3x3_both_tc_kernels_vs_oracle(cin, cout, k, h, w, n, act, shuffle, fold):
+    """Two tcgen05 kernels serve the 3x3 convs: the per-tap kernel (srk_conv_tc.cu) and the folded-tap kernel
+    (srk_conv_fold_tc.cu, three horizontal taps in the MMA N dimension).  Both must match the oracle whichever
+    one is the default."""
+    import ctypes
+    from srk import _lib as L
+    out = (ctypes.c_float * 2)()
+    L.call("srk_tc_probe", 20, out, 2)
+    default = int(out[1])
+    L.call("srk_tc_probe", 10 + fold, out, 2)
+    try:
+        test_conv_forward_backward_vs_oracle(cin, cout, k, h, w, n, act, shuffle, "bf16")
+    finally:
+        L.call("srk_tc_probe", 10 + default, out, 2)
+        assert out[0] == 0, "tcgen05 protocol error flag %r" % out[0]
 
 
 def test_image_in_image_out_convs_vs_oracle():
