@@ -11,12 +11,14 @@
 //   Y[p, co]   = D_0[p-1, co] + D_1[p, co] + D_2[p+1, co]                      (epilogue: shift across TMEM lanes)
 // q runs over ALL padded pixels (a vertical tap is a constant shift of the flat pixel index because the border is
 // zero).  A tile is 128 consecutive padded pixels q0..q0+127 and produces the 126 outputs q0+1..q0+126, so
-// consecutive tiles overlap by two pixels.  The +-1 lane shift is two warp shuffles per output value; the two
-// values per warp that cross a warp boundary go through a 4 KB shared-memory exchange buffer.
+// consecutive tiles overlap by two pixels.  The +-1 lane shift is a rotating warp shuffle per slot; the value that
+// crosses a warp boundary is first swapped in through a 4 KB shared-memory exchange buffer (lane 31 / lane 0 load
+// their neighbour warp's edge value before the rotation), so the shuffled sum needs no masking.
 //
-// One persistent CTA per SM, 352 threads: warp 0 TMA producer (halo slab [128 + 2(W+2) rows][64 ch] per tile,
-// weights once), warp 1 MMA issuer, warps 2-9 epilogue (two per TMEM lane group, 32 output channels each),
-// warp 10 output TMA store / residual TMA load.  Accumulators are double buffered in TMEM (2 x 192 columns).
+// One persistent CTA per SM, 608 threads: warp 0 TMA producer (halo slab [128 + 2(W+2) rows][64 ch] per tile,
+// weights once), warp 1 MMA issuer, warp 2 output TMA store / residual TMA load, warps 3-18 epilogue (four per
+// TMEM lane group, 16 output channels each: the epilogue is instruction-issue bound).
+// Accumulators are double buffered in TMEM (2 x 192 columns).
 #include "srk_common.cuh"
 #include "srk_tc_common.cuh"
 
@@ -38,12 +40,17 @@ constexpr int NT = 64;               // output channels per pass (one accumulato
 constexpr int KC = 64;               // contraction channels per pass: one 128-byte swizzle row
 constexpr int W_BYTES = 9 * NT * KC * 2;   // 72 KB: [r][s][co][ci]
 constexpr int SLAB_BOX_ROWS = 32;
-constexpr int kThreads = 352;
+constexpr int kEpiWarp0 = 3;         // first epilogue warp
+constexpr int kEpiWarps = 16;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;   // 608
+constexpr int CPT = 16;              // accumulator columns (output channels) per epilogue thread
 constexpr int O_TILE_BYTES = TM * NT * 2;  // bf16 output tile staged for the TMA store (126 rows used)
-constexpr int XCH_BYTES = 2 * 2 * 4 * 2 * 32 * 4;  // [acc][column half][lane group][slot 0 / slot 2][32 floats]
+constexpr int XCH_BYTES = 2 * 4 * 4 * 2 * CPT * 4;  // [acc][column quarter][lane group][slot 0 / slot 2][16 floats]
 constexpr int BIAS_BYTES = 256;
 constexpr int MAX_STAGES = 4;
 constexpr int ACC_COLS = 256;        // TMEM column stride between the two accumulator buffers
+constexpr int ACT_RUNTIME = -1;
 
 struct Params {
   int P, Hp, Wp, num_tiles;
@@ -56,6 +63,7 @@ struct Params {
   int slab_rows, stages, stage_bytes;
   int n_cols;          // output channels of this pass: 64 or 32
   int ksteps;          // 16-channel K steps of this pass: 4 or 2
+  int step_n, step_y, step_x;   // (gridDim.x * TMO) pixels decomposed as n * Hp*Wp + y * Wp + x: per-tile walker
   float* partial_out;  // chunked contraction: fp32 partial sums [P][64] written instead of y ...
   const float* partial_in;  // ... and added back (before the activation) by the next chunk
   const float* bias;
@@ -68,8 +76,7 @@ struct Params {
   float* stats_sumsq;
   int* err;
   long long* trace;    // bring-up: per-tile clock64 stamps of CTA 0 ([16][32]) or null (general instantiation)
-  int dbg;             // bring-up knobs (general instantiation only): 1 no stores, 2 no MMAs, 4 no A loads,
-                       // 8 no lane shifts / exchange, 16 centre slot only
+  int dbg;             // bring-up knobs (general instantiation only): 1 no stores, 2 no MMAs, 4 no A loads
 };
 
 struct __align__(8) Barriers {
@@ -86,13 +93,18 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <bool kFast, bool kStats>
+// kFast: the common single-chunk 64 -> 64 pass (no partial sums, N = 3 x 64, four K steps, no PixelShuffle) with
+// those choices and the activation (kAct) compiled in; the general instantiation (kFast = false, kAct = ACT_RUNTIME)
+// covers 32-wide tails, chunked contractions and the PixelShuffle store.
+template <bool kFast, bool kStats, int kAct>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                        const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
                        const Params p) {
   const int n_cols = kFast ? NT : p.n_cols;
   const int ksteps = kFast ? KC / 16 : p.ksteps;
+  const int shuffle = kFast ? 0 : p.shuffle;
+  const int act = kAct == ACT_RUNTIME ? p.act : kAct;
   float* const partial_out = kFast ? nullptr : p.partial_out;
   const float* const partial_in = kFast ? nullptr : p.partial_in;
   float* const stats_sum = kStats ? p.stats_sum : nullptr;
@@ -118,14 +130,14 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     for (int i = 0; i < S; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
     mbar_init(smem_u32(&bars->wfull), 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&bars->tfull[i]), 1); mbar_init(smem_u32(&bars->tempty[i]), 256);
-      mbar_init(smem_u32(&bars->oready[i]), 256); mbar_init(smem_u32(&bars->ofree[i]), 1);
+      mbar_init(smem_u32(&bars->tfull[i]), 1); mbar_init(smem_u32(&bars->tempty[i]), kEpiThreads);
+      mbar_init(smem_u32(&bars->oready[i]), kEpiThreads); mbar_init(smem_u32(&bars->ofree[i]), 1);
       mbar_init(smem_u32(&bars->rfull[i]), 1);
     }
     fence_barrier_init();
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 128) {
-    const int c = threadIdx.x - 64;
+  if (threadIdx.x >= 96 && threadIdx.x < 160) {
+    const int c = threadIdx.x - 96;
     bias_s[c] = (p.bias && c < n_cols) ? __ldg(p.bias + p.bias_off + c) : 0.f;
   }
   if (warp == 1) {
@@ -207,9 +219,9 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       __syncwarp();
       if (++s == S) { s = 0; ph ^= 1; }
     }
-  } else if (warp == 10) {
+  } else if (warp == 2) {
     // ================= output store / residual load warp (plain, non-PixelShuffle outputs) =================
-    if (p.shuffle == 0 && partial_out == nullptr && !(dbg & 1)) {
+    if (shuffle == 0 && partial_out == nullptr && !(dbg & 1)) {
       const int my_tiles = blockIdx.x < p.num_tiles ? (p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
       if (p.has_residual && elect_one()) {
         prefetch_tmap(&tmR);
@@ -242,17 +254,28 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       __syncwarp();
     }
   } else {
-    // ================= epilogue: 8 warps, warp e owns TMEM lanes 32*(warp&3).. and 32 of the 64 channels ====
-    const int e = warp - 2, lg = warp & 3, ch = e >> 2;
-    const int c0 = ch * 32;
-    const float alpha = (p.act == SRK_ACT_PRELU) ? __ldg(p.alpha) : 0.f;
-    const int img = p.Hp * p.Wp;
+    // ====== epilogue: 16 warps; a warp owns TMEM lanes 32*(warp&3).. and 16 of the 64 channels ======
+    const int lg = warp & 3, cq = (warp - kEpiWarp0) >> 2;
+    const int c0 = cq * CPT;
+    const float alpha = (act == SRK_ACT_PRELU) ? __ldg(p.alpha) : 0.f;
     const bool active = c0 < n_cols;
-    const bool staged = p.shuffle == 0 && partial_out == nullptr && !(dbg & 1);
-    float s1[32], s2[32];
+    const bool staged = shuffle == 0 && partial_out == nullptr && !(dbg & 1);
+    const int row = lg * 32 + lane;
+    const bool has_row = row >= 1 && row <= TMO;
+    const int src_up = (lane + 31) & 31, src_dn = (lane + 1) & 31;
+    // pixel walker: coordinates (wn, wy, wx) of padded pixel t = tile*TMO + row (= this thread's pixel + 1)
+    int wn, wy, wx;
+    {
+      const int t0 = blockIdx.x * TMO + row, img = p.Hp * p.Wp;
+      wn = t0 / img;
+      const int q = t0 - wn * img;
+      wy = q / p.Wp;
+      wx = q - wy * p.Wp;
+    }
+    float s1[CPT], s2[CPT];
     if (stats_sum) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+      for (int j = 0; j < CPT; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
     }
     // after a protocol error every wait is skipped, but all warps keep running the same tile sequence so that
     // the named barriers below stay matched (a hung bar.sync would hang the GPU)
@@ -260,14 +283,17 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
-      const int row = lg * 32 + lane;
       const int pix = tile * TMO - 1 + row;
-      const bool is_out = row >= 1 && row <= TMO && pix < p.P;
-      const int pc = is_out ? pix : 0;
-      const int n = pc / img, q = pc - n * img;
-      const int yy = q / p.Wp, xx = q - yy * p.Wp;
-      const bool interior = is_out && yy >= 1 && yy <= p.Hp - 2 && xx >= 1 && xx <= p.Wp - 2;
-      const bool tr = trace && blockIdx.x == 0 && it < 32 && threadIdx.x == 64;
+      // this thread's pixel is t - 1: same row of the image unless wx == 0 (then it is a right-border pixel)
+      const bool is_out = has_row && pix < p.P;
+      const bool interior = is_out && wx >= 2 && wx <= p.Wp - 1 && wy >= 1 && wy <= p.Hp - 2;
+      const int cn = wn, cy = wy, cx = wx - 1;
+      wx += p.step_x;
+      if (wx >= p.Wp) { wx -= p.Wp; ++wy; }
+      wy += p.step_y;
+      if (wy >= p.Hp) { wy -= p.Hp; ++wn; }
+      wn += p.step_n;
+      const bool tr = trace && blockIdx.x == 0 && it < 32 && threadIdx.x == kEpiWarp0 * 32;
       if (tr) trace[3 * 32 + it] = clock64();
       if (ok) ok = mbar_wait(smem_u32(&bars->tfull[acc]), (it >> 1) & 1, p.err, 5);
       tc_fence_after();
@@ -283,77 +309,66 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
         continue;
       }
-      float f[32];
+      float f[CPT];
       {
-        uint32_t v1[32], v0[32];
+        uint32_t v0[CPT], v1[CPT], v2[CPT];
         const uint32_t tbase = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * ACC_COLS + c0;
-        float* xw = xch + (((acc * 2 + ch) * 4 + lg) * 2) * 32;
-        tmem_ld_32x32(tbase + n_cols, v1);        // slot 1: this pixel
-        if (!(dbg & 16)) tmem_ld_32x32(tbase, v0);                 // slot 0: belongs to the pixel one lane up
+        float* xw = xch + (((acc * 4 + cq) * 4 + lg) * 2) * CPT;
+        tmem_ld_32x16(tbase + n_cols, v1);        // slot 1: this pixel
+        tmem_ld_32x16(tbase, v0);                 // slot 0: belongs to the pixel one lane up
+        tmem_ld_32x16(tbase + 2 * n_cols, v2);    // slot 2: belongs to the pixel one lane down
         tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(smem_u32(&bars->tempty[acc]));   // the accumulator is in registers: MMA may refill it
         if (tr) trace[5 * 32 + it] = clock64();
-        if (lane == 31 && !(dbg & 8)) {
+        if (lane == 31) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
+          for (int j = 0; j < CPT / 4; ++j)
             reinterpret_cast<uint4*>(xw)[j] = make_uint4(v0[4 * j], v0[4 * j + 1], v0[4 * j + 2], v0[4 * j + 3]);
         }
+        if (lane == 0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < CPT / 4; ++j)
+            reinterpret_cast<uint4*>(xw + CPT)[j] = make_uint4(v2[4 * j], v2[4 * j + 1], v2[4 * j + 2], v2[4 * j + 3]);
+        }
+        named_bar_sync(1 + cq, 128);   // the four warps of this column quarter have published their edge values
+        if (tr) trace[6 * 32 + it] = clock64();
+        // lane 31 / lane 0 swap in the neighbour warp's edge value, so that a ROTATING shuffle delivers the right
+        // value to every lane (rows 0 and 127 of the tile are halo rows: whatever they receive is never stored)
+        if (lane == 31 && lg > 0) {
+          const uint4* src = reinterpret_cast<const uint4*>(xch + (((acc * 4 + cq) * 4 + lg - 1) * 2) * CPT);
+#pragma unroll
+          for (int j = 0; j < CPT / 4; ++j) {
+            const uint4 t = src[j];
+            v0[4 * j] = t.x; v0[4 * j + 1] = t.y; v0[4 * j + 2] = t.z; v0[4 * j + 3] = t.w;
+          }
+        }
+        if (lane == 0 && lg < 3) {
+          const uint4* src = reinterpret_cast<const uint4*>(xch + (((acc * 4 + cq) * 4 + lg + 1) * 2 + 1) * CPT);
+#pragma unroll
+          for (int j = 0; j < CPT / 4; ++j) {
+            const uint4 t = src[j];
+            v2[4 * j] = t.x; v2[4 * j + 1] = t.y; v2[4 * j + 2] = t.z; v2[4 * j + 3] = t.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < CPT / 4; ++j) {
           const float4 b4 = reinterpret_cast<const float4*>(bias_s + c0)[j];
           f[4 * j] = __uint_as_float(v1[4 * j]) + b4.x; f[4 * j + 1] = __uint_as_float(v1[4 * j + 1]) + b4.y;
           f[4 * j + 2] = __uint_as_float(v1[4 * j + 2]) + b4.z; f[4 * j + 3] = __uint_as_float(v1[4 * j + 3]) + b4.w;
         }
-        if (!(dbg & 8)) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float t = __uint_as_float(__shfl_up_sync(0xffffffffu, v0[j], 1));
-            f[j] += lane > 0 ? t : 0.f;
-          }
-        }
-        if (!(dbg & 16)) {
-          tmem_ld_32x32(tbase + 2 * n_cols, v0);    // slot 2: belongs to the pixel one lane down
-          tmem_ld_wait();
-        }
-        tc_fence_before();
-        mbar_arrive(smem_u32(&bars->tempty[acc]));
-        if (tr) trace[6 * 32 + it] = clock64();
-        if (lane == 0 && !(dbg & 8)) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            reinterpret_cast<uint4*>(xw + 32)[j] = make_uint4(v0[4 * j], v0[4 * j + 1], v0[4 * j + 2], v0[4 * j + 3]);
-        }
-        if (!(dbg & 8)) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float t = __uint_as_float(__shfl_down_sync(0xffffffffu, v0[j], 1));
-            f[j] += lane < 31 ? t : 0.f;
-          }
+        for (int j = 0; j < CPT; ++j) {
+          f[j] += __uint_as_float(__shfl_sync(0xffffffffu, v0[j], src_up));
+          f[j] += __uint_as_float(__shfl_sync(0xffffffffu, v2[j], src_dn));
         }
       }
       if (tr) trace[7 * 32 + it] = clock64();
-      if (!(dbg & 8)) named_bar_sync(1 + ch, 128);   // the four warps of this column half have published their edge values
-      if (tr) trace[8 * 32 + it] = clock64();
       if (dbg & 1) continue;
-      if (lane == 0 && lg > 0) {
-        const float4* src = reinterpret_cast<const float4*>(xch + (((acc * 2 + ch) * 4 + lg - 1) * 2) * 32);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 t = src[j];
-          f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
-        }
-      }
-      if (lane == 31 && lg < 3) {
-        const float4* src = reinterpret_cast<const float4*>(xch + (((acc * 2 + ch) * 4 + lg + 1) * 2 + 1) * 32);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 t = src[j];
-          f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
-        }
-      }
       if (partial_in && is_out) {   // fp32 partial sums of the earlier contraction chunks
         const float4* pin = reinterpret_cast<const float4*>(partial_in + (long long)pix * NT + c0);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < CPT / 4; ++j) {
           const float4 q4 = __ldg(pin + j);
           f[4 * j] += q4.x; f[4 * j + 1] += q4.y; f[4 * j + 2] += q4.z; f[4 * j + 3] += q4.w;
         }
@@ -362,70 +377,74 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (is_out) {
           float4* po = reinterpret_cast<float4*>(partial_out + (long long)pix * NT + c0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) po[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          for (int j = 0; j < CPT / 4; ++j) po[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
         }
         continue;
       }
-      if (staged && ok) ok = mbar_wait(smem_u32(&bars->ofree[acc]), ((it >> 1) & 1) ^ 1, p.err, 7);
-      if (tr) trace[9 * 32 + it] = clock64();
+      if (act == SRK_ACT_RELU) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float a = f[j];
-        if (p.act == SRK_ACT_RELU) a = fmaxf(a, 0.f);
-        else if (p.act == SRK_ACT_PRELU) a = a > 0.f ? a : alpha * a;
-        f[j] = a;
+        for (int j = 0; j < CPT; ++j) f[j] = fmaxf(f[j], 0.f);
+      } else if (act == SRK_ACT_PRELU) {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) f[j] = fmaf(alpha, fminf(f[j], 0.f), fmaxf(f[j], 0.f));
       }
-      if (p.shuffle == 2) {
+      if (shuffle == 2) {
         // PixelShuffle(2) as a store remap (models.py:118,121): column j of this pass is reference channel
         // co = cout_off + c0 + j = 4c + sub  ->  output pixel (2y + sub/2, 2x + sub%2), channel c.
         if (!interior) continue;
 #pragma unroll
         for (int sub = 0; sub < 4; ++sub) {
           const long long o2 =
-              ((long long)n * p.Hp2 + (2 * (yy - 1) + (sub >> 1) + 1)) * p.Wp2 + (2 * (xx - 1) + (sub & 1) + 1);
-          uint4* dst = reinterpret_cast<uint4*>(p.y + o2 * p.cout_total + (p.cout_off + c0) / 4);
-          dst[0] = make_uint4(pack_bf16x2(f[sub], f[4 + sub]), pack_bf16x2(f[8 + sub], f[12 + sub]),
-                              pack_bf16x2(f[16 + sub], f[20 + sub]), pack_bf16x2(f[24 + sub], f[28 + sub]));
+              ((long long)cn * p.Hp2 + (2 * (cy - 1) + (sub >> 1) + 1)) * p.Wp2 + (2 * (cx - 1) + (sub & 1) + 1);
+          uint2* dst = reinterpret_cast<uint2*>(p.y + o2 * p.cout_total + (p.cout_off + c0) / 4);
+          dst[0] = make_uint2(pack_bf16x2(f[sub], f[4 + sub]), pack_bf16x2(f[8 + sub], f[12 + sub]));
         }
         continue;
       }
-      if (interior && stats_sum) {
+      if (stats_sum && interior) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { s1[j] += f[j]; s2[j] = fmaf(f[j], f[j], s2[j]); }
+        for (int j = 0; j < CPT; ++j) { s1[j] += f[j]; s2[j] = fmaf(f[j], f[j], s2[j]); }
       }
-      const bool has_row = row >= 1 && row <= TMO;
+      if (ok) ok = mbar_wait(smem_u32(&bars->ofree[acc]), ((it >> 1) & 1) ^ 1, p.err, 7);
       if (p.has_residual) {
         if (ok) ok = mbar_wait(smem_u32(&bars->rfull[acc]), (it >> 1) & 1, p.err, 8);
         if (has_row) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 rr = *reinterpret_cast<const uint4*>(orow + (((ch * 4 + j) ^ ((row - 1) & 7)) << 4));
+          for (int j = 0; j < CPT / 8; ++j) {
+            const uint4 rr = *reinterpret_cast<const uint4*>(orow + (((cq * (CPT / 8) + j) ^ ((row - 1) & 7)) << 4));
             const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rr);
 #pragma unroll
             for (int t = 0; t < 4; ++t) { float2 u = __bfloat1622float2(h[t]); f[8 * j + 2 * t] += u.x; f[8 * j + 2 * t + 1] += u.y; }
           }
         }
       }
+      if (tr) trace[9 * 32 + it] = clock64();
       if (has_row) {
+        // bf16 tile staged in shared memory ([126 rows][128 B], SWIZZLE_128B) for one TMA store; border pixels are
+        // stored as zeros (layout invariant), rows past the tensor are clipped by TMA
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < CPT / 8; ++j) {
           uint4 o = make_uint4(0, 0, 0, 0);
           if (interior)
             o = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
                            pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
-          *reinterpret_cast<uint4*>(orow + (((ch * 4 + j) ^ ((row - 1) & 7)) << 4)) = o;
+          *reinterpret_cast<uint4*>(orow + (((cq * (CPT / 8) + j) ^ ((row - 1) & 7)) << 4)) = o;
         }
       }
-      if (tr) trace[10 * 32 + it] = clock64();
       fence_proxy_async();
       mbar_arrive(smem_u32(&bars->oready[acc]));
       if (tr) trace[11 * 32 + it] = clock64();
     }
     if (stats_sum) {
-      // per-thread partial sums over this CTA's pixels -> per-channel totals: transposed butterfly (lane l
-      // ends up owning column l), then one atomic per lane
+      // per-thread partial sums over this CTA's pixels -> per-channel totals: fold the two half-warps, then a
+      // transposed butterfly (lane l ends up owning column l & 15), then one atomic per column
 #pragma unroll
-      for (int half = 16; half >= 1; half >>= 1) {
+      for (int j = 0; j < CPT; ++j) {
+        s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16);
+        s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
+      }
+#pragma unroll
+      for (int half = CPT / 2; half >= 1; half >>= 1) {
         const bool up = (lane & half) != 0;
 #pragma unroll
         for (int j = 0; j < half; ++j) {
@@ -435,7 +454,7 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           s2[j] = k2 + __shfl_xor_sync(0xffffffffu, o2, half);
         }
       }
-      if (active && p.cout_off + c0 + lane < p.cout_total) {
+      if (active && lane < CPT && p.cout_off + c0 + lane < p.cout_total) {
         atomicAdd(stats_sum + p.cout_off + c0 + lane, s1[0]);
         atomicAdd(stats_sumsq + p.cout_off + c0 + lane, s2[0]);
       }
@@ -447,6 +466,11 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+}
+
+template <bool kFast, bool kStats, int kAct>
+static void set_smem(int smem_max) {
+  cudaFuncSetAttribute(conv3x3_fold_tc_kernel<kFast, kStats, kAct>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
 }
 
 }  // namespace fold
@@ -466,9 +490,11 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    cudaFuncSetAttribute(conv3x3_fold_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
-    cudaFuncSetAttribute(conv3x3_fold_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
-    cudaFuncSetAttribute(conv3x3_fold_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    set_smem<true, false, SRK_ACT_NONE>(smem_max);
+    set_smem<true, true, SRK_ACT_NONE>(smem_max);
+    set_smem<true, false, SRK_ACT_RELU>(smem_max);
+    set_smem<true, false, SRK_ACT_PRELU>(smem_max);
+    set_smem<false, false, ACT_RUNTIME>(smem_max);
   }
   const int slab_rows = ((TM + 2 * Wp) + SLAB_BOX_ROWS - 1) / SLAB_BOX_ROWS * SLAB_BOX_ROWS;
   const int fixed = 1024 + W_BYTES + 2 * O_TILE_BYTES + XCH_BYTES + BIAS_BYTES + (int)sizeof(Barriers);
@@ -505,6 +531,12 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
   SRK_REQUIRE(stats_sum == nullptr || (kchunks == 1 && shuffle == 0 && act == SRK_ACT_NONE && residual == nullptr),
               "conv_fold: fused BN statistics need a plain Cin == 64 conv");
   const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  {
+    const long long step = (long long)grid * TMO, img = (long long)Hp * Wp;
+    p.step_n = (int)(step / img);
+    p.step_y = (int)((step % img) / Wp);
+    p.step_x = (int)((step % img) % Wp);
+  }
   for (int nc = 0; nc < nchunks; ++nc) {
     const int n_cols = cout - nc * NT < NT ? cout - nc * NT : NT;
     CUtensorMap tmW;
@@ -534,11 +566,19 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
         p.partial_in = nullptr;
       }
       const CUtensorMap& tmRes = (fp32_partials || first) ? tmR : tmY;
-      const bool fast = kchunks == 1 && p.n_cols == NT && p.ksteps == KC / 16 && p.dbg == 0 && p.trace == nullptr;
+      const bool fast = kchunks == 1 && p.n_cols == NT && p.ksteps == KC / 16 && shuffle == 0 && p.dbg == 0 &&
+                        p.trace == nullptr;
       SRK_REQUIRE(fast || stats_sum == nullptr, "conv_fold: fused BN statistics need the single-chunk 64 -> 64 pass");
-      if (fast && stats_sum) conv3x3_fold_tc_kernel<true, true><<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, tmRes, p);
-      else if (fast) conv3x3_fold_tc_kernel<true, false><<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, tmRes, p);
-      else conv3x3_fold_tc_kernel<false, false><<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, tmRes, p);
+      if (fast && stats_sum)
+        conv3x3_fold_tc_kernel<true, true, SRK_ACT_NONE><<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, tmRes, p);
+      else if (fast && p.act == SRK_ACT_NONE)
+        conv3x3_fold_tc_kernel<true, false, SRK_ACT_NONE><<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, tmRes, p);
+      else if (fast && p.act == SRK_ACT_RELU)
+        conv3x3_fold_tc_kernel<true, false, SRK_ACT_RELU><<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, tmRes, p);
+      else if (fast && p.act == SRK_ACT_PRELU)
+        conv3x3_fold_tc_kernel<true, false, SRK_ACT_PRELU><<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, tmRes, p);
+      else
+        conv3x3_fold_tc_kernel<false, false, ACT_RUNTIME><<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, tmRes, p);
       SRK_CUDA_LAUNCH_CHECK("conv3x3_fold_tc");
     }
   }

@@ -4,6 +4,8 @@
 // C % 8 == 0; reductions go warp-shuffle -> shared memory -> one atomic per block and channel.
 #include "srk_common.cuh"
 
+#include <cstdlib>
+
 namespace srk {
 
 // ---- vector helpers: VEC contiguous channels -------------------------------------------------
@@ -98,9 +100,23 @@ struct PixWalk {
   _Pragma("unroll 4")                                                               \
   for (long long q = q_begin__ + prow; prow < rows && q < q_end__; q += rows)
 
+// Reductions end in one atomic per block and channel: fewer, longer blocks win (measured on B200 at the C2 layer
+// shape: bn_bwd_reduce 17.0 us at 2 blocks / SM, 23.0 at 8, 31.5 at 16); the map kernels want 4-8 blocks / SM.
+inline void reduce_grid(const Geo& g, int& blocks, int& ppb) {
+  static int per_sm = 0;
+  if (!per_sm) { const char* e = getenv("SRK_EW_REDUCE_PER_SM"); per_sm = e ? atoi(e) : 2; if (per_sm < 1) per_sm = 2; }
+  long long target = 148LL * per_sm;
+  long long p = (g.pixels + target - 1) / target;
+  if (p < 64) p = 64;
+  ppb = (int)p;
+  blocks = (int)((g.pixels + ppb - 1) / ppb);
+}
+
 inline void pixel_grid(const Geo& g, int& blocks, int& ppb) {
   // ~4 blocks per SM worth of work, at least 64 pixels per block
-  long long target = 148LL * 8;
+  static int per_sm = 0;
+  if (!per_sm) { const char* e = getenv("SRK_EW_BLOCKS_PER_SM"); per_sm = e ? atoi(e) : 8; if (per_sm < 1) per_sm = 8; }
+  long long target = 148LL * per_sm;
   long long p = (g.pixels + target - 1) / target;
   if (p < 64) p = 64;
   ppb = (int)p;
@@ -684,7 +700,7 @@ static inline bool c_ok(const srk_tensor* t) {
 extern "C" int srk_bn_stats(const srk_tensor* y, float* sum, float* sumsq, void* stream) {
   ACT_CHECK(y, "srk_bn_stats");
   SRK_REQUIRE(c_ok(y), "srk_bn_stats: unsupported channel count %d", y->c);
-  Geo g = geo_of(y); int blocks, ppb; pixel_grid(g, blocks, ppb);
+  Geo g = geo_of(y); int blocks, ppb; reduce_grid(g, blocks, ppb);
   DISPATCH_T_VEC(y, (bn_stats_kernel<T, VEC><<<blocks, 256, red_smem(y), (cudaStream_t)stream>>>(
                         (const T*)y->data, g, ppb, sum, sumsq)));
   SRK_CUDA_LAUNCH_CHECK("bn_stats");
@@ -731,7 +747,7 @@ extern "C" int srk_bn_bwd_reduce(const srk_tensor* dout, const srk_tensor* y, co
   ACT_CHECK(y, "srk_bn_bwd_reduce"); ACT_CHECK(dout, "srk_bn_bwd_reduce");
   SRK_REQUIRE(same_geometry(y, dout) && y->dtype == dout->dtype, "srk_bn_bwd_reduce: geometry mismatch");
   SRK_REQUIRE(c_ok(y), "srk_bn_bwd_reduce: unsupported channel count %d", y->c);
-  Geo g = geo_of(y); int blocks, ppb; pixel_grid(g, blocks, ppb);
+  Geo g = geo_of(y); int blocks, ppb; reduce_grid(g, blocks, ppb);
   DISPATCH_T_VEC(y, (bn_bwd_reduce_kernel<T, VEC><<<blocks, 256, red_smem(y), (cudaStream_t)stream>>>(
                         (const T*)dout->data, (const T*)y->data, g, ppb, mean, invstd, gamma, beta,
                         alpha, dgamma, dbeta, dalpha)));

@@ -89,17 +89,30 @@ __global__ void __launch_bounds__(256) nlpd_diff_kernel(const float* __restrict_
   if (threadIdx.x == 0) atomicAdd(acc, t);
 }
 
+// Row-wise iteration over an [NC][H][W] image stack: a block walks whole rows (several per pass when W is
+// narrower than the block), so the (nc, y, x) of an element costs one 32-bit division per ROW instead of two
+// 64-bit divisions per element.
+#define NLPD_LOOP_BEGIN(NC_, H_, W_)                                                                   \
+  {                                                                                                    \
+    const bool wide__ = (W_) >= (int)blockDim.x;                                                       \
+    const int rpi__ = wide__ ? 1 : (int)blockDim.x / (W_);                                             \
+    const int tr__ = wide__ ? 0 : (int)threadIdx.x / (W_);                                             \
+    const int tx__ = wide__ ? (int)threadIdx.x : (int)threadIdx.x - tr__ * (W_);                       \
+    const int xs__ = wide__ ? (int)blockDim.x : (W_);                                                  \
+    const int rows__ = (NC_) * (H_);                                                                   \
+    for (int row = blockIdx.x * rpi__ + tr__; row < rows__ && tr__ < rpi__; row += gridDim.x * rpi__) { \
+      const int nc = row / (H_), y = row - nc * (H_);                                                  \
+      for (int x = tx__; x < (W_); x += xs__) {                                                        \
+        const long long i = (long long)row * (W_) + x;
+#define NLPD_LOOP_END }}}
+
 // down[y][x] = sum_{ky,kx} k[ky][kx] * cur[2y+ky-2][2x+kx-2] (zero padded)   (loss.py:61-62)
 __global__ void __launch_bounds__(256) nlpd_blur_down_kernel(const float* __restrict__ cur, int NC, int H,
     int W, int h2, int w2, const float* __restrict__ k25, float* __restrict__ down) {
   __shared__ float k[25];
   if (threadIdx.x < 25) k[threadIdx.x] = k25[threadIdx.x];
   __syncthreads();
-  long long total = (long long)NC * h2 * w2;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    int x = (int)(i % w2); long long t = i / w2;
-    int y = (int)(t % h2); int nc = (int)(t / h2);
+  NLPD_LOOP_BEGIN(NC, h2, w2)
     const float* p = cur + (long long)nc * H * W;
     float acc = 0.f;
 #pragma unroll
@@ -114,7 +127,7 @@ __global__ void __launch_bounds__(256) nlpd_blur_down_kernel(const float* __rest
       }
     }
     down[i] = acc;
-  }
+  NLPD_LOOP_END
 }
 
 // bilinear, align_corners=False, explicit output size (loss.py:63): src = max(scale*(o+.5)-.5, 0)
@@ -131,12 +144,8 @@ __global__ void __launch_bounds__(256) nlpd_lap_abs_kernel(const float* __restri
     const float* __restrict__ down, int NC, int H, int W, int h2, int w2, float sy, float sx,
     signed char* __restrict__ sign, double* __restrict__ acc) {
   __shared__ double red[32];
-  long long total = (long long)NC * H * W;
   float s = 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    int x = (int)(i % W); long long t = i / W;
-    int y = (int)(t % H); int nc = (int)(t / H);
+  NLPD_LOOP_BEGIN(NC, H, W)
     int y0, y1, x0, x1; float ly, lx;
     bilin_src(y, sy, h2, y0, y1, ly);
     bilin_src(x, sx, w2, x0, x1, lx);
@@ -146,7 +155,7 @@ __global__ void __launch_bounds__(256) nlpd_lap_abs_kernel(const float* __restri
     float d = cur[i] - up;
     s += fabsf(d);
     if (sign) sign[i] = d > 0.f ? 1 : (d < 0.f ? -1 : 0);
-  }
+  NLPD_LOOP_END
   double t = block_sum_d((double)s, red);
   if (threadIdx.x == 0) atomicAdd(acc, t);
 }
@@ -162,11 +171,7 @@ __global__ void nlpd_combine_kernel(const double* acc, NlpdWeights wt, float* lo
 __global__ void __launch_bounds__(256) nlpd_bwd_down_kernel(const signed char* __restrict__ sign,
     const float* __restrict__ g_next, int NC, int H, int W, int h2, int w2, float sy, float sx, float c_l,
     float* __restrict__ g_down) {
-  long long total = (long long)NC * h2 * w2;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    int x = (int)(i % w2); long long t = i / w2;
-    int y = (int)(t % h2); int nc = (int)(t / h2);
+  NLPD_LOOP_BEGIN(NC, h2, w2)
     const signed char* sp = sign + (long long)nc * H * W;
     float acc = 0.f;
     // an exact 2x level touches fine rows / columns 2y-1 .. 2y+2 only; other ratios get the wider safe window
@@ -185,7 +190,7 @@ __global__ void __launch_bounds__(256) nlpd_bwd_down_kernel(const signed char* _
       }
     }
     g_down[i] = (g_next ? g_next[i] : 0.f) - c_l * acc;
-  }
+  NLPD_LOOP_END
 }
 
 // G_l[Y][X] = c_l*sign_l[Y][X] + sum_{ky,kx: (Y+2-ky),(X+2-kx) even} k[ky][kx] g_down[(Y+2-ky)/2][(X+2-kx)/2]
@@ -198,11 +203,8 @@ __global__ void __launch_bounds__(256) nlpd_bwd_up_kernel(const signed char* __r
   if (threadIdx.x < 25) k[threadIdx.x] = k25[threadIdx.x];
   __syncthreads();
   const float go = gout ? gout[0] : 1.f;
-  long long total = (long long)NC * H * W;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    int X = (int)(i % W); long long t = i / W;
-    int Y = (int)(t % H); int nc = (int)(t / H);
+  NLPD_LOOP_BEGIN(NC, H, W)
+    const int X = x, Y = y;
     const float* gp = g_down + (long long)nc * h2 * w2;
     float acc = c_l * (float)sign[i];
     // blurred[yy][xx] reads cur[yy+ky-2][xx+kx-2]; only even (yy,xx) are kept as down[yy/2][xx/2]
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(256) nlpd_bwd_up_kernel(const signed char* __r
       acc *= go;
     }
     G[i] = acc;
-  }
+  NLPD_LOOP_END
 }
 
 // ---- PSNR / SSIM ------------------------------------------------------------------------------------

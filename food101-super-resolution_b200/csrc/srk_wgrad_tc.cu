@@ -193,34 +193,48 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   }
 }
 
-// dw[co0+co][ci0+ci][tap] += sum over CTAs of ws[cta][tap][ci][co];  db[co0+co] += sum over CTAs of the tail
-__global__ void wgrad_fold_kernel(const float* __restrict__ ws, int parts, float* __restrict__ dw, int cin_total,
-                                  int cout_total, int ci0, int co0, float* __restrict__ db, int accumulate) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;  // over [tap][ci][co]: coalesced reads of every partial
-  if (i >= NT * KC * TAPS) {
-    const int c = i - NT * KC * TAPS;
-    if (db != nullptr && c < NT && co0 + c < cout_total) {
-      float s = 0.f;
-      for (int k = 0; k < parts; ++k) s += ws[(size_t)parts * (TAPS * KC * NT) + (size_t)k * NT + c];
-      db[co0 + c] = accumulate ? db[co0 + c] + s : s;
+// dw[co0+co][ci0+ci][tap] += sum over CTAs of ws[cta][tap][ci][co];  db[co0+co] += sum over CTAs of the tail.
+// The partials are L2 resident and the sum is latency bound, so it is spread over the partials as well: a block
+// owns 32 consecutive outputs (one coalesced 128-byte row of every partial) and its 8 warps each sum every 8th
+// partial with all their loads in flight, then fold through shared memory.
+constexpr int FOLD_OUT = 32, FOLD_WARPS = 8, FOLD_MAX_PER_WARP = 24;   // up to 192 partials
+__global__ void __launch_bounds__(FOLD_OUT * FOLD_WARPS)
+wgrad_fold_kernel(const float* __restrict__ ws, int parts, float* __restrict__ dw, int cin_total,
+                  int cout_total, int ci0, int co0, float* __restrict__ db, int accumulate) {
+  __shared__ float red[FOLD_WARPS][FOLD_OUT];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.x * FOLD_OUT + lane;   // over [tap][ci][co], then the 64 bias columns
+  const bool bias_part = i >= NT * KC * TAPS;
+  const float* src = bias_part ? ws + (size_t)parts * (TAPS * KC * NT) + (i - NT * KC * TAPS) : ws + i;
+  const size_t stride = bias_part ? NT : (size_t)TAPS * KC * NT;
+  float v[FOLD_MAX_PER_WARP];
+  if (!bias_part || db != nullptr) {
+#pragma unroll
+    for (int u = 0; u < FOLD_MAX_PER_WARP; ++u) {
+      const int k = w + u * FOLD_WARPS;
+      v[u] = k < parts ? __ldg(src + (size_t)k * stride) : 0.f;
     }
+  } else {
+#pragma unroll
+    for (int u = 0; u < FOLD_MAX_PER_WARP; ++u) v[u] = 0.f;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int u = 0; u < FOLD_MAX_PER_WARP; ++u) s += v[u];
+  red[w][lane] = s;
+  __syncthreads();
+  if (w != 0) return;
+#pragma unroll
+  for (int r = 1; r < FOLD_WARPS; ++r) s += red[r][lane];
+  if (bias_part) {
+    const int c = i - NT * KC * TAPS;
+    if (db != nullptr && co0 + c < cout_total) db[co0 + c] = accumulate ? db[co0 + c] + s : s;
     return;
   }
-  // 8 independent loads in flight per thread: the partials are L2 resident, the loop is latency bound
-  float acc[8];
-#pragma unroll
-  for (int u = 0; u < 8; ++u) acc[u] = 0.f;
-  int k = 0;
-  for (; k + 8 <= parts; k += 8) {
-#pragma unroll
-    for (int u = 0; u < 8; ++u) acc[u] += ws[(size_t)(k + u) * (TAPS * KC * NT) + i];
-  }
-  for (; k < parts; ++k) acc[0] += ws[(size_t)k * (TAPS * KC * NT) + i];
-  const float s0 = (acc[0] + acc[1]) + (acc[2] + acc[3]), s1 = (acc[4] + acc[5]) + (acc[6] + acc[7]);
   const int co = i % NT, t = i / NT, ci = t % KC, tap = t / KC;
   if (ci0 + ci >= cin_total || co0 + co >= cout_total) return;  // zero-filled tail of a 96-channel tensor
   float* o = &dw[((size_t)(co0 + co) * cin_total + (ci0 + ci)) * TAPS + tap];
-  *o = accumulate ? *o + s0 + s1 : s0 + s1;
+  *o = accumulate ? *o + s : s;
 }
 
 bool conv_wgrad_tc_shape_ok(const srk_tensor* x, const srk_tensor* dy, int r, int s) {
@@ -275,7 +289,7 @@ int conv_wgrad_tc_launch(const srk_tensor* x, const srk_tensor* dy, float* dw, f
       p.db = (db != nullptr && kc == 0) ? db + nc * NT : nullptr;
       wgrad3x3_tc_kernel<<<grid, kThreads, smem_bytes, st>>>(tmX, tmDz, p);
       SRK_CUDA_LAUNCH_CHECK("wgrad3x3_tc");
-      wgrad_fold_kernel<<<(NT * KC * TAPS + NT + 127) / 128, 128, 0, st>>>(p.ws, grid, dw, x->c, dy->c, kc * KC, nc * NT,
+      wgrad_fold_kernel<<<(NT * KC * TAPS + NT) / FOLD_OUT, FOLD_OUT * FOLD_WARPS, 0, st>>>(p.ws, grid, dw, x->c, dy->c, kc * KC, nc * NT,
                                                                            p.db ? db : nullptr, accumulate);
       SRK_CUDA_LAUNCH_CHECK("wgrad_fold");
     }
