@@ -272,7 +272,10 @@ int conv_wgrad_tc_launch(const srk_tensor* x, const srk_tensor* dy, float* dw, f
   p.stage_bytes = p.slab_rows * KC * 2 + DZ_TILE_BYTES;
   const int fixed = 1024 + (int)sizeof(WgradBarriers);
   p.stages = (smem_max - fixed) / p.stage_bytes;
-  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  // Three stages hide the TMA latency (a stage is ~2000 cycles of MMA work) and leave ~60 KB of the SM's shared
+  // memory free: this kernel runs on the side stream NEXT TO the BatchNorm-backward reductions of the following
+  // layer (srk/ops.py run_on_side_stream), whose blocks need 8 KB each to become resident beside it.
+  if (p.stages > 3) p.stages = 3;
   SRK_REQUIRE(p.stages >= 2, "wgrad_tc: image too wide for the shared-memory slab");
   p.err = tc_err_flag();
   const int smem_bytes = fixed + p.stages * p.stage_bytes;

@@ -75,12 +75,14 @@ class ConvAct(torch.autograd.Function):
         if ops.rgbout_bwd_supported(x, x_img, dz_img, weight):
             dx, dw, db = ops.conv_rgbout_bwd(x, dz, weight, _needs(ctx, 0), has_bias)
             return dx, dw, db, None, None, None, None, None, None, None
-        if _needs(ctx, 1) or (has_bias and _needs(ctx, 2)):
-            dw, db = ops.conv_wgrad(x, x_img, dz, dz_img, weight, has_bias, perm)
+        # data gradient first, then the weight gradient on the side stream: it overlaps the HBM-bound backward
+        # passes of the next layer instead of competing with this layer's dgrad for the SMs
         if _needs(ctx, 0):
             dx = ops.conv_dgrad(dz, dz_img, weight, None, x.dtype if not x_img else torch.float32, perm)
             if x_img:
                 dx = ops.act_to_image(dx)
+        if _needs(ctx, 1) or (has_bias and _needs(ctx, 2)):
+            dw, db = ops.conv_wgrad(x, x_img, dz, dz_img, weight, has_bias, perm, side=True)
         dres = dout if (has_res and _needs(ctx, 4)) else None
         return dx, dw, db, (dalpha if _needs(ctx, 3) else None), dres, None, None, None, None, None
 
@@ -105,8 +107,8 @@ def _conv_bn_forward(x, w, b, bn_params, bn_buffers, training, eps, momentum, al
 
 def _conv_bn_backward(dout, x, y, stats, w, has_bias, gamma, beta, alpha, batch_stats, dgrad_residual, need_dx):
     dy, dgamma, dbeta, dalpha = ops.bn_backward(dout, y, stats, gamma, beta, alpha, batch_stats)
-    dw, db = ops.conv_wgrad(x, False, dy, False, w, has_bias)
     dx = ops.conv_dgrad(dy, False, w, dgrad_residual, x.dtype) if need_dx else None
+    dw, db = ops.conv_wgrad(x, False, dy, False, w, has_bias, side=True)   # overlaps the next BN backward
     return dx, dw, db, dgamma, dbeta, dalpha
 
 
@@ -181,11 +183,11 @@ class AttnBlock(torch.autograd.Function):
         hb1, hb2, scale = ctx.cfg
         dout = dout.contiguous()
         dr, dfc1, dfc2 = ops.se_backward(dout, r, pool, hidden, gate, fc1, fc2, scale)
-        dw2, db2 = ops.conv_wgrad(a, False, dr, False, w2, hb2)
         da = ops.conv_dgrad(dr, False, w2, None, a.dtype)
+        dw2, db2 = ops.conv_wgrad(a, False, dr, False, w2, hb2, side=True)
         dz1, dalpha = ops.act_bwd(da, a, L.ACT_PRELU, alpha, 0)
-        dw1, db1 = ops.conv_wgrad(x, False, dz1, False, w1, hb1)
         dx = ops.conv_dgrad(dz1, False, w1, dout, x.dtype)
+        dw1, db1 = ops.conv_wgrad(x, False, dz1, False, w1, hb1, side=True)
         return dx, dw1, db1, dalpha, dw2, db2, dfc1, dfc2, None
 
 

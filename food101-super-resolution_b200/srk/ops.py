@@ -6,6 +6,7 @@ Tensor conventions
   image : NCHW fp32 contiguous (what the reference modules take / return)
   act   : zero-bordered channels-last [N, H+2, W+2, C], fp32 or bf16 (internal activations)
 """
+import os
 import weakref
 
 import torch
@@ -19,6 +20,11 @@ class _Config:
     compute_dtype = torch.float32
     # "auto": tcgen05 when supported and activations are bf16, else CUDA cores; "simt": never tcgen05
     conv_impl = "auto"
+
+
+    # weight-gradient kernels (tensor-core / shared-memory bound) run on a side stream so that they overlap the
+    # HBM-bound BatchNorm / activation backward passes of the next layer (see run_on_side_stream)
+    overlap_wgrad = os.environ.get("SRK_OVERLAP_WGRAD", "1") != "0"
 
 
 cfg = _Config()
@@ -252,6 +258,53 @@ def _timed(key, launch):
     return kernel_timer.wrap(key, launch)
 
 
+# ---- side stream ------------------------------------------------------------------------------------
+class _Side:
+    streams = {}      # device index -> torch.cuda.Stream
+    pending = []      # tensors the side stream still uses (kept alive until the join is enqueued)
+
+
+def _side_stream(device):
+    idx = torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    st = _Side.streams.get(idx)
+    if st is None:
+        st = _Side.streams[idx] = torch.cuda.Stream(device=idx)
+    return st
+
+
+def join_side_stream():
+    """Make the current stream wait for everything launched through run_on_side_stream."""
+    if not _Side.pending:
+        return
+    main = torch.cuda.current_stream()
+    main.wait_stream(_side_stream(main.device))
+    _Side.pending.clear()   # frees happen after the join is enqueued: allocator reuse stays ordered
+
+
+def run_on_side_stream(launch, keep):
+    """Run `launch()` (libsrk launches that read the current stream through stream_ptr) on the side stream,
+    ordered after everything already enqueued on the current stream.  The current stream joins again at the end
+    of the autograd backward pass (engine callback), so results must only be consumed after backward() returns;
+    outside a backward pass the join happens immediately.  `keep` holds every tensor the launch touches: all of
+    them were allocated on the current stream and stay referenced until the join is enqueued, so the caching
+    allocator cannot hand their memory to later kernels of the current stream.  Works under CUDA-graph capture
+    (event record / wait become graph edges; the join closes the fork before the capture ends)."""
+    main = torch.cuda.current_stream()
+    side = _side_stream(main.device)
+    ev = torch.cuda.Event()
+    ev.record(main)
+    side.wait_event(ev)
+    with torch.cuda.stream(side):
+        launch()
+    _Side.pending.append(keep)
+    try:   # one callback per launch: after the first one has joined the others find nothing pending
+        torch.autograd.Variable._execution_engine.queue_callback(join_side_stream)
+    except RuntimeError:
+        join_side_stream()
+
+
 # ---- convolution -----------------------------------------------------------------------------------
 def _rgb_tc_ok(r, s):
     return cfg.conv_impl != "simt" and cfg.compute_dtype == torch.bfloat16 and r == s and r in (5, 9)
@@ -343,8 +396,14 @@ def conv_dgrad(dz, dz_img, weight, residual, out_dtype, perm_tc=False):
     return dx
 
 
-def conv_wgrad(x, x_img, dz, dz_img, weight, need_bias, perm_tc=False):
-    """-> (dW fp32 OIHW, db fp32 [Cout] or None)"""
+def conv_wgrad(x, x_img, dz, dz_img, weight, need_bias, perm_tc=False, side=False):
+    """-> (dW fp32 OIHW, db fp32 [Cout] or None).  side=True: launch on the side stream (run_on_side_stream);
+    the caller must not read the results before the backward pass has ended."""
+    # The results are handed to autograd before the side stream has produced them.  That is safe only when
+    # AccumulateGrad takes the tensors over without touching them (no existing .grad to add to, no hooks, no other
+    # reference to dw / db - which is why `keep` below must not hold them); otherwise stay on the current stream.
+    side = (side and cfg.overlap_wgrad and weight.grad is None and not weight._backward_hooks
+            and not getattr(weight, "_post_accumulate_grad_hooks", None))
     if perm_tc:
         raise RuntimeError("conv_wgrad: sub-pixel-major dz is not supported yet")
     cout, cin, r, s = weight.shape
@@ -357,18 +416,26 @@ def conv_wgrad(x, x_img, dz, dz_img, weight, need_bias, perm_tc=False):
         nbytes = L.cdll.srk_conv_wgrad_workspace_bytes(xd, dd, r, s, impl)
         ws = torch.empty((nbytes,), dtype=torch.uint8, device=weight.device) if nbytes > 0 else None
         n, _, h, w = geometry(x, x_img)
-        _timed(("conv_wgrad", cin, cout, r, 0, n, h, w, nbytes > 0),
-               lambda: L.call("srk_conv_wgrad", xd, dd, dw.data_ptr(), _ptr(db), r, s, impl, 0, _ptr(ws),
-                              stream_ptr()))
+        launch = lambda: _timed(("conv_wgrad", cin, cout, r, 0, n, h, w, nbytes > 0),
+                                lambda: L.call("srk_conv_wgrad", xd, dd, dw.data_ptr(), _ptr(db), r, s, impl, 0,
+                                               _ptr(ws), stream_ptr()))
+        if side:
+            run_on_side_stream(launch, (x, dz, ws))
+        else:
+            launch()
         return dw, db
     dw = torch.zeros_like(weight, memory_format=torch.contiguous_format)
     db = torch.zeros((cout,), dtype=torch.float32, device=weight.device) if need_bias else None
     if x_img and (not dz_img) and cin == 3 and cout in (64, 96) and dz.dtype == torch.bfloat16 and _rgb_tc_ok(r, s):
         n, _, h, w = geometry(x, True)
         ws = _rgb_workspace(r, x.device)
-        _timed(("conv_rgbin_wgrad", cin, cout, r, 0, n, h, w, True),
-               lambda: L.call("srk_conv_rgb_bwd", img_desc(x), act_desc(dz), None, None, dw.data_ptr(), _ptr(db),
-                              r, 0, ws.data_ptr(), stream_ptr()))
+        launch = lambda: _timed(("conv_rgbin_wgrad", cin, cout, r, 0, n, h, w, True),
+                                lambda: L.call("srk_conv_rgb_bwd", img_desc(x), act_desc(dz), None, None,
+                                               dw.data_ptr(), _ptr(db), r, 0, ws.data_ptr(), stream_ptr()))
+        if side:
+            run_on_side_stream(launch, (x, dz, ws))
+        else:
+            launch()
         return dw, db
     raise AssertionError("unreachable")
 
