@@ -713,6 +713,91 @@ using namespace srk;
               "%s: expected ACT tensor", name)
 
 // dispatch on dtype and vector width
+// ---- 2x2 max pooling, stride 2, floor mode (nn.MaxPool2d(2, 2) inside VGG19.features, loss.py:23-24) ----------
+// One thread per (padded output pixel, channel vector).  Forward: border pixels of `out` are written as zeros.
+// Backward: the gradient of an output pixel goes to the first maximum of its window in row-major scan order (the
+// index ATen's max_pool2d_with_indices records); every input pixel - including rows / columns the floor mode
+// leaves uncovered, and the border - is written exactly once (zero where no gradient arrives).
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const T* __restrict__ x, int N, int H, int W, int C,
+                                                           T* __restrict__ out) {
+  const int Ho = H / 2, Wo = W / 2, CV = C / VEC;
+  const long long total = (long long)N * (Ho + 2) * (Wo + 2) * CV;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    long long t = i / CV;
+    const int xo = (int)(t % (Wo + 2)); t /= (Wo + 2);
+    const int yo = (int)(t % (Ho + 2));
+    const int n = (int)(t / (Ho + 2));
+    float o[VEC];
+    if (xo == 0 || xo == Wo + 1 || yo == 0 || yo == Ho + 1) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) o[j] = 0.f;
+    } else {
+      const long long base = (((long long)n * (H + 2) + (2 * (yo - 1) + 1)) * (W + 2) + (2 * (xo - 1) + 1)) * C + cv * VEC;
+      float a[VEC], b[VEC], c[VEC], d[VEC];
+      Vec<T, VEC>::ld(x + base, a);
+      Vec<T, VEC>::ld(x + base + C, b);
+      Vec<T, VEC>::ld(x + base + (long long)(W + 2) * C, c);
+      Vec<T, VEC>::ld(x + base + (long long)(W + 2) * C + C, d);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) o[j] = fmaxf(fmaxf(a[j], b[j]), fmaxf(c[j], d[j]));
+    }
+    Vec<T, VEC>::st(out + i * VEC, o);
+  }
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dout,
+                                                           int N, int H, int W, int C, T* __restrict__ dx) {
+  const int Ho = H / 2, Wo = W / 2, CV = C / VEC;
+  // one thread per 2x2 block of the PADDED input grid, aligned to the pooling windows: block by covers padded rows
+  // 2by-1 and 2by, so rows 0 .. H+1 need by = 0 .. (H+2)/2; out-of-range quarters are skipped
+  const int By = (H + 4) / 2, Bx = (W + 4) / 2;
+  const long long total = (long long)N * By * Bx * CV;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    long long t = i / CV;
+    const int bx = (int)(t % Bx); t /= Bx;
+    const int by = (int)(t % By);
+    const int n = (int)(t / By);
+    // window (yo, xo) of the pooling covers padded input pixels (2yo-1 .. 2yo, 2xo-1 .. 2xo), yo in [1, Ho]; blocks
+    // are aligned to those windows: block (by, bx) = padded pixels (2by-1 .. 2by, 2bx-1 .. 2bx)
+    const bool win = by >= 1 && by <= Ho && bx >= 1 && bx <= Wo;
+    float g[VEC], v[4][VEC];
+    if (win) {
+      Vec<T, VEC>::ld(dout + ((((long long)n * (Ho + 2) + by) * (Wo + 2) + bx) * C + cv * VEC), g);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int py = 2 * by - 1 + (k >> 1), px = 2 * bx - 1 + (k & 1);
+        Vec<T, VEC>::ld(x + ((((long long)n * (H + 2) + py) * (W + 2) + px) * C + cv * VEC), v[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int py = 2 * by - 1 + (k >> 1), px = 2 * bx - 1 + (k & 1);
+      if (py < 0 || px < 0 || py > H + 1 || px > W + 1) continue;
+      float o[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        float r = 0.f;
+        if (win) {
+          // first maximum in scan order: element k wins if it is >= all later ones and > all earlier ones
+          bool is_max = true;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            if (m < k) is_max = is_max && (v[k][j] > v[m][j]);
+            if (m > k) is_max = is_max && (v[k][j] >= v[m][j]);
+          }
+          r = is_max ? g[j] : 0.f;
+        }
+        o[j] = r;
+      }
+      Vec<T, VEC>::st(dx + ((((long long)n * (H + 2) + py) * (W + 2) + px) * C + cv * VEC), o);
+    }
+  }
+}
+
 #define DISPATCH_T_VEC(t, ...)                                            \
   do {                                                                    \
     const bool vec8__ = ((t)->c % 8 == 0) && ((t)->c / 8 <= 256);         \
@@ -972,6 +1057,48 @@ extern "C" int srk_act_add(const srk_tensor* a, const srk_tensor* b, const srk_t
   else
     act_add_kernel<float><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((const float*)a->data, (const float*)b->data, (float*)out->data, total);
   SRK_CUDA_LAUNCH_CHECK("act_add");
+  return 0;
+}
+
+extern "C" int srk_maxpool2_fwd(const srk_tensor* x, const srk_tensor* out, void* stream) {
+  ACT_CHECK(x, "srk_maxpool2_fwd"); ACT_CHECK(out, "srk_maxpool2_fwd");
+  SRK_REQUIRE(out->n == x->n && out->c == x->c && out->h == x->h / 2 && out->w == x->w / 2 && out->dtype == x->dtype &&
+                  out->h >= 1 && out->w >= 1,
+              "srk_maxpool2_fwd: output must be [N, C, H/2, W/2] of the input dtype");
+  const long long total = (long long)out->n * (out->h + 2) * (out->w + 2) * (x->c % 8 == 0 ? x->c / 8 : x->c);
+  if (x->c % 8 == 0) {
+    if (x->dtype == SRK_BF16)
+      maxpool2_fwd_kernel<__nv_bfloat16, 8><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x->data, x->n, x->h, x->w, x->c, (__nv_bfloat16*)out->data);
+    else
+      maxpool2_fwd_kernel<float, 8><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((const float*)x->data, x->n, x->h, x->w, x->c, (float*)out->data);
+  } else {
+    if (x->dtype == SRK_BF16)
+      maxpool2_fwd_kernel<__nv_bfloat16, 1><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x->data, x->n, x->h, x->w, x->c, (__nv_bfloat16*)out->data);
+    else
+      maxpool2_fwd_kernel<float, 1><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((const float*)x->data, x->n, x->h, x->w, x->c, (float*)out->data);
+  }
+  SRK_CUDA_LAUNCH_CHECK("maxpool2_fwd");
+  return 0;
+}
+
+extern "C" int srk_maxpool2_bwd(const srk_tensor* x, const srk_tensor* dout, const srk_tensor* dx, void* stream) {
+  ACT_CHECK(x, "srk_maxpool2_bwd"); ACT_CHECK(dout, "srk_maxpool2_bwd"); ACT_CHECK(dx, "srk_maxpool2_bwd");
+  SRK_REQUIRE(same_geometry(x, dx) && x->dtype == dx->dtype && dout->dtype == x->dtype && dout->n == x->n &&
+                  dout->c == x->c && dout->h == x->h / 2 && dout->w == x->w / 2,
+              "srk_maxpool2_bwd: geometry mismatch");
+  const long long total = (long long)x->n * ((x->h + 4) / 2) * ((x->w + 4) / 2) * (x->c % 8 == 0 ? x->c / 8 : x->c);
+  if (x->c % 8 == 0) {
+    if (x->dtype == SRK_BF16)
+      maxpool2_bwd_kernel<__nv_bfloat16, 8><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x->data, (const __nv_bfloat16*)dout->data, x->n, x->h, x->w, x->c, (__nv_bfloat16*)dx->data);
+    else
+      maxpool2_bwd_kernel<float, 8><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((const float*)x->data, (const float*)dout->data, x->n, x->h, x->w, x->c, (float*)dx->data);
+  } else {
+    if (x->dtype == SRK_BF16)
+      maxpool2_bwd_kernel<__nv_bfloat16, 1><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x->data, (const __nv_bfloat16*)dout->data, x->n, x->h, x->w, x->c, (__nv_bfloat16*)dx->data);
+    else
+      maxpool2_bwd_kernel<float, 1><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>((const float*)x->data, (const float*)dout->data, x->n, x->h, x->w, x->c, (float*)dx->data);
+  }
+  SRK_CUDA_LAUNCH_CHECK("maxpool2_bwd");
   return 0;
 }
 

@@ -3,7 +3,7 @@ constructor arguments, registered buffers and get_loss_function() names (referen
 
   mae / mse   fused reduce kernels, forward and gradient          (reference loss.py:84,86)
   nlpd        Laplacian-pyramid loss, fused forward and backward  (reference loss.py:31-79)
-  perceptual  VGG19 feature MSE - needs downloaded weights; outside the accelerated path
+  perceptual  VGG19.features[:35] MSE on the tcgen05 convs + max-pool kernels    (reference loss.py:19-29)
 """
 import torch
 import torch.nn as nn
@@ -87,20 +87,51 @@ class TVLoss(nn.Module):
 
 
 class PerceptualLoss(nn.Module):
-    """MSE between VGG19.features[:35] activations (reference loss.py:19-29).  Needs the ImageNet VGG19
-    checkpoint, which cannot be fetched offline; constructing it without one raises.  Outside the
-    accelerated path for now (SURVEY 8a row a10 marks it second priority)."""
+    """MSE between VGG19.features[:35] activations of input and target (reference loss.py:19-29): sixteen 3x3
+    convs (ReLU after all but the last: index 34 is the bare conv5_4) and four 2x2 max-pools, weights frozen, no
+    ImageNet normalisation.  The module holds the torchvision layers under the reference's attribute name
+    (`vgg`, so state_dict keys match) and runs them on libsrk: tcgen05 convs with fused bias + ReLU in the compute
+    dtype (the 3 -> 64 first conv on the CUDA-core kernel), max-pool kernels, and the fused MSE reduction.
 
-    def __init__(self, device):
+    `weights` is what torchvision.models.vgg19 takes; the reference's "DEFAULT" needs the ImageNet checkpoint
+    (vgg19-dcbb9e9d.pth) in the torch hub cache - offline it raises, exactly like the reference does.  Pass
+    weights=None (random init, what the parity tests use) or a state-dict path to build it without a download."""
+
+    def __init__(self, device, weights="DEFAULT"):
         super().__init__()
         from torchvision.models import vgg19
-        self.vgg = vgg19(weights="DEFAULT").features[:35].eval().to(device)
+        if isinstance(weights, str) and weights != "DEFAULT" and weights.endswith((".pth", ".pt")):
+            net = vgg19(weights=None)
+            net.load_state_dict(torch.load(weights, map_location="cpu"))
+        else:
+            net = vgg19(weights=weights)
+        self.vgg = net.features[:35].eval().to(device)
         for p in self.vgg.parameters():
             p.requires_grad = False
-        self.loss = nn.MSELoss()
+        self.loss = MSELoss()
+
+    def features(self, img):
+        """NCHW fp32 image -> NCHW fp32 conv5_4 features, through libsrk."""
+        from srk import fn
+        ops.require_cuda(img, "PerceptualLoss")
+        layers = list(self.vgg)
+        x, x_img, i = img.contiguous().float(), True, 0
+        while i < len(layers):
+            layer = layers[i]
+            if isinstance(layer, nn.Conv2d):
+                relu = i + 1 < len(layers) and isinstance(layers[i + 1], nn.ReLU)
+                x = fn.conv_act(x, layer, act=L.ACT_RELU if relu else L.ACT_NONE, x_img=x_img)
+                x_img = False
+                i += 2 if relu else 1
+            elif isinstance(layer, nn.MaxPool2d):
+                x = fn.MaxPool2.apply(x)
+                i += 1
+            else:
+                raise RuntimeError("PerceptualLoss: unexpected layer %r in VGG19.features" % (layer,))
+        return fn.ActToImage.apply(x)
 
     def forward(self, input, target):
-        return self.loss(self.vgg(input), self.vgg(target))
+        return self.loss(self.features(input), self.features(target))
 
 
 class _NLPD(torch.autograd.Function):

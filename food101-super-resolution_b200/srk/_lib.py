@@ -58,6 +58,8 @@ SIGNATURES = {
     "srk_image_to_act": (c_int, [_T, _T, _P]),
     "srk_act_to_image": (c_int, [_T, _T, _P]),
     "srk_act_add": (c_int, [_T, _T, _T, _P]),
+    "srk_maxpool2_fwd": (c_int, [_T, _T, _P]),
+    "srk_maxpool2_bwd": (c_int, [_T, _T, _T, _P]),
     "srk_bicubic_upsample": (c_int, [_T, _T, _P]),
     "srk_pixel_loss_fwd": (c_int, [_P, _P, c_int64, c_int, _P, _P, _P]),
     "srk_pixel_loss_bwd": (c_int, [_P, _P, c_int64, c_int, _P, _P, _P]),

@@ -4,6 +4,7 @@
   ConvAct      conv + bias + ReLU/PReLU + PixelShuffle(2) [+ residual]         models.py:84-87,107-108,116-125
   ConvBN       conv + bias + BatchNorm2d [+ PReLU] [+ residual]                 models.py:55-60,113-114,140-141
   AttnBlock    conv + PReLU + conv + squeeze-excite gate + scaled skip          models.py:62-78
+  MaxPool2     2x2 / stride 2 max pooling (VGG19 features of the perceptual loss)  loss.py:23
   ImageToAct / ActToImage                                                       layout boundary
 
 Gradients w.r.t. parameters are returned as ordinary fp32 tensors in the state_dict layout (OIHW),
@@ -207,6 +208,22 @@ class SEGate(torch.autograd.Function):
         r, pool, hidden, gate, fc1, fc2 = ctx.saved_tensors
         dr, dfc1, dfc2 = ops.se_backward(dout.contiguous(), r, pool, hidden, gate, fc1, fc2, 1.0)
         return dr, dfc1, dfc2
+
+
+class MaxPool2(torch.autograd.Function):
+    """nn.MaxPool2d(kernel_size=2, stride=2) on an act tensor (VGG19.features inside PerceptualLoss, loss.py:23)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ops.require_cuda(x, "max pooling")
+        x = x.contiguous()
+        ctx.save_for_backward(x)
+        return ops.maxpool2_fwd(x)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x,) = ctx.saved_tensors
+        return ops.maxpool2_bwd(x, dout.contiguous())
 
 
 class ActAdd(torch.autograd.Function):

@@ -560,6 +560,22 @@ def act_add(a, b):
     return out
 
 
+def maxpool2_fwd(x):
+    """2x2 / stride 2 max pooling (floor mode) of an act tensor."""
+    n, c, h, w = geometry(x, False)
+    if h < 2 or w < 2:
+        raise ValueError("maxpool2: input %dx%d is smaller than the window" % (h, w))
+    out = new_act(n, c, h // 2, w // 2, x.dtype, x.device)
+    L.call("srk_maxpool2_fwd", act_desc(x), act_desc(out), stream_ptr())
+    return out
+
+
+def maxpool2_bwd(x, dout):
+    dx = torch.empty_like(x)
+    L.call("srk_maxpool2_bwd", act_desc(x), act_desc(dout), act_desc(dx), stream_ptr())
+    return dx
+
+
 def bicubic_upsample(img, oh, ow):
     n, c, h, w = img.shape
     out = new_image(n, c, oh, ow, img.device)

@@ -171,6 +171,12 @@ int srk_image_to_act(const srk_tensor* img, const srk_tensor* act, void* stream)
 int srk_act_to_image(const srk_tensor* act, const srk_tensor* img, void* stream);
 /* out = a + b on ACT tensors (residual sums models.py:60,141) ; out may alias a */
 int srk_act_add(const srk_tensor* a, const srk_tensor* b, const srk_tensor* out, void* stream);
+
+/* 2x2 / stride 2 max pooling, floor mode, on ACT tensors: nn.MaxPool2d(2, 2) of torchvision VGG19.features, which
+ * PerceptualLoss runs both images through (reference loss.py:23-28).  out: [N, C, H/2, W/2].  bwd: dx (same geometry
+ * as x, fully written) receives dout at the first maximum of each window in row-major order (ATen's index rule). */
+int srk_maxpool2_fwd(const srk_tensor* x, const srk_tensor* out, void* stream);
+int srk_maxpool2_bwd(const srk_tensor* x, const srk_tensor* dout, const srk_tensor* dx, void* stream);
 /* F.interpolate(mode='bicubic', align_corners=False) models.py:98 (A=-0.75, clamped taps) */
 int srk_bicubic_upsample(const srk_tensor* in, const srk_tensor* out, void* stream);
 

@@ -160,6 +160,30 @@ def nlpd_loss(sr, hr, n_levels=4, alpha=0.7):
     return alpha * l_mae + (1.0 - alpha) * l_pyr
 
 
+# VGG19.features[:35] (torchvision cfg "E"): conv widths, 'M' = MaxPool2d(2, 2); ReLU after every conv except the
+# last one (index 34 = conv5_4, the slice ends before its ReLU).  The integer keys are the Sequential indices.
+VGG19_35 = [(0, 64), (2, 64), "M", (5, 128), (7, 128), "M", (10, 256), (12, 256), (14, 256), (16, 256), "M",
+            (19, 512), (21, 512), (23, 512), (25, 512), "M", (28, 512), (30, 512), (32, 512), (34, 512)]
+
+
+def vgg19_features35(sd, x, prefix="vgg."):
+    """torchvision vgg19().features[:35] as loss.py:23-24 slices it; sd holds '<prefix><idx>.weight/.bias'."""
+    for item in VGG19_35:
+        if item == "M":
+            x = F.max_pool2d(x, 2, 2)
+            continue
+        idx, _ = item
+        x = F.conv2d(x, sd["%s%d.weight" % (prefix, idx)], sd["%s%d.bias" % (prefix, idx)], padding=1)
+        if idx != 34:
+            x = F.relu(x)
+    return x
+
+
+def perceptual_loss(sd, sr, hr, prefix="vgg."):
+    """PerceptualLoss.forward (loss.py:27-29): MSE between the VGG19 features of input and target."""
+    return F.mse_loss(vgg19_features35(sd, sr, prefix), vgg19_features35(sd, hr, prefix))
+
+
 def loss_fn(name):
     """get_loss_function (loss.py:81-92) for the names on the accelerated path."""
     name = name.lower()

@@ -94,3 +94,23 @@ def test_metrics_compute_clamps_first():
     m = O.metrics_compute(x, y)
     assert m["psnr"] == float("inf") and abs(m["ssim"] - 1.0) < 1e-9 and m["nlpd"] == 0.0
     assert math.isfinite(O.metrics_compute(x * 0.3, y * 0.5)["psnr"])
+
+
+def test_perceptual_oracle_matches_torchvision_vgg19_slice():
+    """The reference's PerceptualLoss wraps torchvision vgg19().features[:35] (loss.py:23-24); it cannot be built
+    offline (the constructor downloads the ImageNet checkpoint), so the oracle's restatement of that slice is pinned
+    against the torchvision module itself with seeded random weights, forward and input gradient."""
+    from torchvision.models import vgg19
+    torch.manual_seed(11)
+    net = vgg19(weights=None).features[:35].eval()
+    sd = {"vgg." + k: v for k, v in net.state_dict().items()}
+    sr = torch.rand(2, 3, 40, 36, requires_grad=True)
+    hr = torch.rand(2, 3, 40, 36)
+    ref = torch.nn.functional.mse_loss(net(sr), net(hr))
+    (g_ref,) = torch.autograd.grad(ref, sr)
+    sr2 = sr.detach().clone().requires_grad_(True)
+    got = O.perceptual_loss(sd, sr2, hr)
+    (g_got,) = torch.autograd.grad(got, sr2)
+    assert abs(got.item() - ref.item()) <= 1e-7 * max(1.0, abs(ref.item()))
+    assert max_abs(g_got, g_ref) <= 1e-9
+    assert len([k for k in sd if k.endswith(".weight")]) == 16
