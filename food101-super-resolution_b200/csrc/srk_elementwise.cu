@@ -231,12 +231,43 @@ __global__ void bn_eval_params_kernel(const float* rm, const float* rv, int C, f
   if (c < C) { mean[c] = rm[c]; invstd[c] = rsqrtf(rv[c] + eps); }
 }
 
+// Training-mode statistics folded into the apply pass (one launch less on the critical path of every BN layer):
+// when `fin.sum` is set, every block derives mean / invstd from the per-channel sums itself (double precision, as
+// bn_finalize_kernel does) and block 0 also publishes them and updates the running statistics.
+struct BnFinalize {
+  const float* sum; const float* sumsq;
+  double count; float eps, momentum;
+  float* running_mean; float* running_var; long long* nbt;
+  float* mean_out; float* invstd_out;
+};
+
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ y, Geo g, int ppb,
     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
     const float* __restrict__ beta, const float* __restrict__ alpha_p, const T* __restrict__ res,
-    T* __restrict__ out) {
+    T* __restrict__ out, const BnFinalize fin) {
+  extern __shared__ float bn_smem[];   // fused statistics: [C] mean, [C] invstd
   const float alpha = alpha_p ? alpha_p[0] : 1.f;
+  if (fin.sum) {
+    for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
+      const double m = (double)fin.sum[c] / fin.count;
+      double var = (double)fin.sumsq[c] / fin.count - m * m;
+      if (var < 0.0) var = 0.0;
+      const float mf = (float)m, isf = (float)(1.0 / sqrt(var + (double)fin.eps));
+      bn_smem[c] = mf; bn_smem[g.C + c] = isf;
+      if (blockIdx.x == 0) {
+        fin.mean_out[c] = mf; fin.invstd_out[c] = isf;
+        if (fin.running_mean != nullptr) {
+          const double unbiased = fin.count > 1.0 ? var * fin.count / (fin.count - 1.0) : var;
+          fin.running_mean[c] = (1.f - fin.momentum) * fin.running_mean[c] + fin.momentum * mf;
+          fin.running_var[c] = (1.f - fin.momentum) * fin.running_var[c] + fin.momentum * (float)unbiased;
+        }
+      }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && fin.nbt != nullptr) fin.nbt[0] += 1;
+    __syncthreads();
+    mean = bn_smem; invstd = bn_smem + g.C;
+  }
   // per-channel scale / shift of this thread's channel vector, hoisted out of the pixel loop
   float sc[VEC], sh[VEC];
   {
@@ -873,10 +904,33 @@ extern "C" int srk_bn_apply(const srk_tensor* y, const float* mean, const float*
   if (residual) SRK_REQUIRE(same_geometry(y, residual) && residual->dtype == y->dtype && residual->layout == SRK_LAYOUT_ACT, "srk_bn_apply: residual mismatch");
   SRK_REQUIRE(c_ok(y), "srk_bn_apply: unsupported channel count %d", y->c);
   Geo g = geo_of(y); int blocks, ppb; pixel_grid(g, blocks, ppb);
+  BnFinalize fin = {};
   DISPATCH_T_VEC(y, (bn_apply_kernel<T, VEC><<<blocks, 256, 0, (cudaStream_t)stream>>>(
                         (const T*)y->data, g, ppb, mean, invstd, gamma, beta, alpha,
-                        residual ? (const T*)residual->data : nullptr, (T*)out->data)));
+                        residual ? (const T*)residual->data : nullptr, (T*)out->data, fin)));
   SRK_CUDA_LAUNCH_CHECK("bn_apply");
+  return 0;
+}
+
+extern "C" int srk_bn_apply_train(const srk_tensor* y, const float* sum, const float* sumsq, int64_t count, float eps,
+                                  float momentum, float* running_mean, float* running_var,
+                                  int64_t* num_batches_tracked, float* mean, float* invstd, const float* gamma,
+                                  const float* beta, const float* alpha, const srk_tensor* residual,
+                                  const srk_tensor* out, void* stream) {
+  ACT_CHECK(y, "srk_bn_apply_train"); ACT_CHECK(out, "srk_bn_apply_train");
+  SRK_REQUIRE(same_geometry(y, out) && y->dtype == out->dtype, "srk_bn_apply_train: geometry mismatch");
+  if (residual) SRK_REQUIRE(same_geometry(y, residual) && residual->dtype == y->dtype && residual->layout == SRK_LAYOUT_ACT, "srk_bn_apply_train: residual mismatch");
+  SRK_REQUIRE(c_ok(y), "srk_bn_apply_train: unsupported channel count %d", y->c);
+  SRK_REQUIRE(sum && sumsq && mean && invstd && count > 0, "srk_bn_apply_train: statistics buffers required");
+  SRK_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "srk_bn_apply_train: running_mean / running_var go together");
+  Geo g = geo_of(y); int blocks, ppb; pixel_grid(g, blocks, ppb);
+  BnFinalize fin = {sum, sumsq, (double)count, eps, momentum, running_mean, running_var,
+                    (long long*)num_batches_tracked, mean, invstd};
+  const size_t smem = 2 * (size_t)y->c * sizeof(float);
+  DISPATCH_T_VEC(y, (bn_apply_kernel<T, VEC><<<blocks, 256, smem, (cudaStream_t)stream>>>(
+                        (const T*)y->data, g, ppb, nullptr, nullptr, gamma, beta, alpha,
+                        residual ? (const T*)residual->data : nullptr, (T*)out->data, fin)));
+  SRK_CUDA_LAUNCH_CHECK("bn_apply_train");
   return 0;
 }
 

@@ -47,6 +47,7 @@ SIGNATURES = {
     "srk_bn_finalize": (c_int, [_P, _P, c_int, c_int64, c_float, c_float, _P, _P, _P, _P, _P, _P]),
     "srk_bn_eval_params": (c_int, [_P, _P, c_int, c_float, _P, _P, _P]),
     "srk_bn_apply": (c_int, [_T, _P, _P, _P, _P, _P, _T, _T, _P]),
+    "srk_bn_apply_train": (c_int, [_T, _P, _P, c_int64, c_float, c_float, _P, _P, _P, _P, _P, _P, _P, _P, _T, _T, _P]),
     "srk_bn_bwd_reduce": (c_int, [_T, _T, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "srk_bn_bwd_apply": (c_int, [_T, _T, _P, _P, _P, _P, _P, _P, _P, c_int, _T, _P]),
     "srk_se_pool": (c_int, [_T, _P, _P]),

@@ -471,9 +471,13 @@ def bn_forward(y, gamma, beta, running_mean, running_var, nbt, training, eps, mo
             sums = zeros((2, c), dev)
             L.call("srk_bn_stats", act_desc(y), sums[0].data_ptr(), sums[1].data_ptr(), st)
         upd = training and running_mean is not None
-        L.call("srk_bn_finalize", sums[0].data_ptr(), sums[1].data_ptr(), c, n * h * w, eps, momentum,
+        # statistics -> mean / invstd (+ running-stat update) happen inside the apply kernel: one launch per layer
+        out = torch.empty_like(y)
+        L.call("srk_bn_apply_train", act_desc(y), sums[0].data_ptr(), sums[1].data_ptr(), n * h * w, eps, momentum,
                _ptr(running_mean) if upd else None, _ptr(running_var) if upd else None,
-               _ptr(nbt) if upd else None, mean.data_ptr(), invstd.data_ptr(), st)
+               _ptr(nbt) if upd else None, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+               _ptr(alpha), act_desc(residual) if residual is not None else None, act_desc(out), st)
+        return out, stats
     else:
         L.call("srk_bn_eval_params", running_mean.data_ptr(), running_var.data_ptr(), c, eps,
                mean.data_ptr(), invstd.data_ptr(), st)

@@ -136,6 +136,14 @@ int srk_bn_eval_params(const float* running_mean, const float* running_var, int 
 int srk_bn_apply(const srk_tensor* y, const float* mean, const float* invstd, const float* gamma,
                  const float* beta, const float* alpha, const srk_tensor* residual,
                  const srk_tensor* out, void* stream);
+/* training-mode BatchNorm in one pass after the statistics: srk_bn_finalize folded into srk_bn_apply (every block
+ * derives mean / invstd from (sum, sumsq) itself; block 0 publishes them to mean / invstd for the backward and updates
+ * the running statistics and num_batches_tracked when those pointers are non-NULL).  F.batch_norm(training=True) of
+ * models.py:56-57,140. */
+int srk_bn_apply_train(const srk_tensor* y, const float* sum, const float* sumsq, int64_t count, float eps,
+                       float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                       float* mean, float* invstd, const float* gamma, const float* beta, const float* alpha,
+                       const srk_tensor* residual, const srk_tensor* out, void* stream);
 /* backward pass 1: dgamma[C], dbeta[C], dalpha[1] (all fp32, accumulated) */
 int srk_bn_bwd_reduce(const srk_tensor* dout, const srk_tensor* y, const float* mean,
                       const float* invstd, const float* gamma, const float* beta,
