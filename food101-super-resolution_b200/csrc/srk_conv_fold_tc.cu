@@ -35,7 +35,8 @@ namespace fold {
 using namespace tc;
 
 constexpr int TM = 128;              // pixels per tile (UMMA M)
-constexpr int TMO = 126;             // output pixels per tile
+// output pixels per tile: 126 with the folded taps (rows 0 and 127 of the tile are halo rows), 128 per-tap
+template <bool kFold> struct Tile { static constexpr int TMO = kFold ? 126 : 128, ROW0 = kFold ? 1 : 0; };
 constexpr int NT = 64;               // output channels per pass (one accumulator slot)
 constexpr int KC = 64;               // contraction channels per pass: one 128-byte swizzle row
 constexpr int W_BYTES = 9 * NT * KC * 2;   // 72 KB: [r][s][co][ci]
@@ -96,11 +97,15 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // kFast: the common single-chunk 64 -> 64 pass (no partial sums, N = 3 x 64, four K steps, no PixelShuffle) with
 // those choices and the activation (kAct) compiled in; the general instantiation (kFast = false, kAct = ACT_RUNTIME)
 // covers 32-wide tails, chunked contractions and the PixelShuffle store.
-template <bool kFast, bool kStats, int kAct>
+// kFold = false: the same pipeline with one MMA group per tap (N = 64, 36 MMAs per tile, A operand re-read per tap
+// from the row-shifted slab) and a plain one-slot epilogue - the per-tap formulation of srk_conv_tc.cu on the
+// 16-warp epilogue of this file.
+template <bool kFold, bool kFast, bool kStats, int kAct>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                        const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
                        const Params p) {
+  constexpr int TMO = Tile<kFold>::TMO, ROW0 = Tile<kFold>::ROW0;
   const int n_cols = kFast ? NT : p.n_cols;
   const int ksteps = kFast ? KC / 16 : p.ksteps;
   const int shuffle = kFast ? 0 : p.shuffle;
@@ -172,7 +177,7 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           mbar_arrive(fb);
         } else {
           mbar_arrive_expect_tx(fb, p.slab_rows * KC * 2);
-          const int row0 = tile * TMO - 1 - p.Wp;
+          const int row0 = tile * TMO - p.Wp - 1;   // folded: pixel (tile*126 - 1) - Wp; per-tap: tile*128 - Wp - 1
           for (int j = 0; j < p.slab_rows / SLAB_BOX_ROWS; ++j)
             tma_load_2d(asm0 + s * p.stage_bytes + j * SLAB_BOX_ROWS * KC * 2, &tmA, fb, p.k_col0,
                         row0 + j * SLAB_BOX_ROWS);
@@ -184,7 +189,7 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    const uint32_t idesc = make_idesc_bf16(TM, 3 * n_cols, 0, 0);
+    const uint32_t idesc = make_idesc_bf16(TM, kFold ? 3 * n_cols : n_cols, 0, 0);
     const uint64_t desc_hi = make_smem_desc(0, 16, 1024, kLayoutSW128, 0) & 0xFFFFFFFF00000000ull;
     const uint32_t lo_base = (uint32_t)(make_smem_desc(0, 16, 1024, kLayoutSW128, 0) & 0xFFFFFFFFull);
     const uint32_t w_lo = lo_base + (wsm >> 4), a_lo0 = lo_base + (asm0 >> 4);
@@ -205,13 +210,25 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const uint32_t a_lo = a_lo0 + s * stage_units;
       if (elect_one()) {
         if (trace && blockIdx.x == 0 && it < 32) trace[1 * 32 + it] = clock64();
+        if (kFold) {
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+          for (int r = 0; r < 3; ++r)
 #pragma unroll
-          for (int ks = 0; ks < KC / 16; ++ks)
-            if (ks < ksteps && !(dbg & 2))
-              umma_bf16(d_tmem, desc_hi | (a_lo + r * row_units + 2 * ks), desc_hi | (w_lo + r * wrow_units + 2 * ks),
-                        idesc, (r | ks) != 0);
+            for (int ks = 0; ks < KC / 16; ++ks)
+              if (ks < ksteps && !(dbg & 2))
+                umma_bf16(d_tmem, desc_hi | (a_lo + r * row_units + 2 * ks), desc_hi | (w_lo + r * wrow_units + 2 * ks),
+                          idesc, (r | ks) != 0);
+        } else {
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+              for (int ks = 0; ks < KC / 16; ++ks)
+                if (ks < ksteps && !(dbg & 2))
+                  umma_bf16(d_tmem, desc_hi | (a_lo + r * row_units + c * (KC * 2 / 16) + 2 * ks),
+                            desc_hi | (w_lo + r * wrow_units + c * (wrow_units / 3) + 2 * ks), idesc, (r | c | ks) != 0);
+        }
         umma_commit(smem_u32(&bars->empty[s]));
         umma_commit(smem_u32(&bars->tfull[acc]));
         if (trace && blockIdx.x == 0 && it < 32) trace[2 * 32 + it] = clock64();
@@ -261,9 +278,9 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const bool active = c0 < n_cols;
     const bool staged = shuffle == 0 && partial_out == nullptr && !(dbg & 1);
     const int row = lg * 32 + lane;
-    const bool has_row = row >= 1 && row <= TMO;
+    const bool has_row = row >= ROW0 && row < ROW0 + TMO;
     const int src_up = (lane + 31) & 31, src_dn = (lane + 1) & 31;
-    // pixel walker: coordinates (wn, wy, wx) of padded pixel t = tile*TMO + row (= this thread's pixel + 1)
+    // pixel walker: coordinates (wn, wy, wx) of padded pixel t = tile*TMO + row (= this thread's pixel + ROW0)
     int wn, wy, wx;
     {
       const int t0 = blockIdx.x * TMO + row, img = p.Hp * p.Wp;
@@ -283,11 +300,11 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
-      const int pix = tile * TMO - 1 + row;
-      // this thread's pixel is t - 1: same row of the image unless wx == 0 (then it is a right-border pixel)
+      const int pix = tile * TMO - ROW0 + row;
+      // this thread's pixel is t - ROW0: same row of the image unless that underflows (then it is a border pixel)
       const bool is_out = has_row && pix < p.P;
-      const bool interior = is_out && wx >= 2 && wx <= p.Wp - 1 && wy >= 1 && wy <= p.Hp - 2;
-      const int cn = wn, cy = wy, cx = wx - 1;
+      const int cn = wn, cy = wy, cx = wx - ROW0;
+      const bool interior = is_out && cx >= 1 && cx <= p.Wp - 2 && wy >= 1 && wy <= p.Hp - 2;
       wx += p.step_x;
       if (wx >= p.Wp) { wx -= p.Wp; ++wy; }
       wy += p.step_y;
@@ -298,7 +315,7 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       if (ok) ok = mbar_wait(smem_u32(&bars->tfull[acc]), (it >> 1) & 1, p.err, 5);
       tc_fence_after();
       if (tr) trace[4 * 32 + it] = clock64();
-      uint8_t* orow = optr + acc * O_TILE_BYTES + (row - 1) * 128;
+      uint8_t* orow = optr + acc * O_TILE_BYTES + (row - ROW0) * 128;
       if (!active) {
         tc_fence_before();
         mbar_arrive(smem_u32(&bars->tempty[acc]));
@@ -310,6 +327,20 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         continue;
       }
       float f[CPT];
+      if (!kFold) {
+        uint32_t v1[CPT];
+        tmem_ld_32x16(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * ACC_COLS + c0, v1);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(smem_u32(&bars->tempty[acc]));   // the accumulator is in registers: MMA may refill it
+        if (tr) trace[5 * 32 + it] = clock64();
+#pragma unroll
+        for (int j = 0; j < CPT / 4; ++j) {
+          const float4 b4 = reinterpret_cast<const float4*>(bias_s + c0)[j];
+          f[4 * j] = __uint_as_float(v1[4 * j]) + b4.x; f[4 * j + 1] = __uint_as_float(v1[4 * j + 1]) + b4.y;
+          f[4 * j + 2] = __uint_as_float(v1[4 * j + 2]) + b4.z; f[4 * j + 3] = __uint_as_float(v1[4 * j + 3]) + b4.w;
+        }
+      } else
       {
         uint32_t v0[CPT], v1[CPT], v2[CPT];
         const uint32_t tbase = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * ACC_COLS + c0;
@@ -411,7 +442,7 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (has_row) {
 #pragma unroll
           for (int j = 0; j < CPT / 8; ++j) {
-            const uint4 rr = *reinterpret_cast<const uint4*>(orow + (((cq * (CPT / 8) + j) ^ ((row - 1) & 7)) << 4));
+            const uint4 rr = *reinterpret_cast<const uint4*>(orow + (((cq * (CPT / 8) + j) ^ ((row - ROW0) & 7)) << 4));
             const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rr);
 #pragma unroll
             for (int t = 0; t < 4; ++t) { float2 u = __bfloat1622float2(h[t]); f[8 * j + 2 * t] += u.x; f[8 * j + 2 * t + 1] += u.y; }
@@ -428,7 +459,7 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           if (interior)
             o = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
                            pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
-          *reinterpret_cast<uint4*>(orow + (((cq * (CPT / 8) + j) ^ ((row - 1) & 7)) << 4)) = o;
+          *reinterpret_cast<uint4*>(orow + (((cq * (CPT / 8) + j) ^ ((row - ROW0) & 7)) << 4)) = o;
         }
       }
       fence_proxy_async();
@@ -468,9 +499,33 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   }
 }
 
-template <bool kFast, bool kStats, int kAct>
+template <bool kFold, bool kFast, bool kStats, int kAct>
 static void set_smem(int smem_max) {
-  cudaFuncSetAttribute(conv3x3_fold_tc_kernel<kFast, kStats, kAct>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+  cudaFuncSetAttribute(conv3x3_fold_tc_kernel<kFold, kFast, kStats, kAct>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       smem_max);
+}
+template <bool kFold>
+static void set_smem_all(int smem_max) {
+  set_smem<kFold, true, false, SRK_ACT_NONE>(smem_max);
+  set_smem<kFold, true, true, SRK_ACT_NONE>(smem_max);
+  set_smem<kFold, true, false, SRK_ACT_RELU>(smem_max);
+  set_smem<kFold, true, false, SRK_ACT_PRELU>(smem_max);
+  set_smem<kFold, false, false, ACT_RUNTIME>(smem_max);
+}
+
+template <bool kFold>
+static void launch_pass(bool fast, bool stats, int act, int grid, int smem_bytes, cudaStream_t st, const CUtensorMap& tmA,
+                        const CUtensorMap& tmW, const CUtensorMap& tmY, const CUtensorMap& tmRes, const Params& p) {
+  if (fast && stats)
+    conv3x3_fold_tc_kernel<kFold, true, true, SRK_ACT_NONE><<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, tmRes, p);
+  else if (fast && act == SRK_ACT_NONE)
+    conv3x3_fold_tc_kernel<kFold, true, false, SRK_ACT_NONE><<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, tmRes, p);
+  else if (fast && act == SRK_ACT_RELU)
+    conv3x3_fold_tc_kernel<kFold, true, false, SRK_ACT_RELU><<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, tmRes, p);
+  else if (fast && act == SRK_ACT_PRELU)
+    conv3x3_fold_tc_kernel<kFold, true, false, SRK_ACT_PRELU><<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, tmRes, p);
+  else
+    conv3x3_fold_tc_kernel<kFold, false, false, ACT_RUNTIME><<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, tmRes, p);
 }
 
 }  // namespace fold
@@ -479,8 +534,9 @@ static void set_smem(int smem_max) {
 // per-tap kernel of srk_conv_tc.cu).
 int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout,
                            const float* bias, int act, const float* alpha, const srk_tensor* residual, int shuffle,
-                           float* stats_sum, float* stats_sumsq, void* workspace, cudaStream_t st) {
+                           float* stats_sum, float* stats_sumsq, void* workspace, int folded, cudaStream_t st) {
   using namespace fold;
+  const int TMO = folded ? Tile<true>::TMO : Tile<false>::TMO;
   const int cin = x->c;
   const int Hp = x->h + 2, Wp = x->w + 2;
   const long long P = (long long)x->n * Hp * Wp;
@@ -490,13 +546,10 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    set_smem<true, false, SRK_ACT_NONE>(smem_max);
-    set_smem<true, true, SRK_ACT_NONE>(smem_max);
-    set_smem<true, false, SRK_ACT_RELU>(smem_max);
-    set_smem<true, false, SRK_ACT_PRELU>(smem_max);
-    set_smem<false, false, ACT_RUNTIME>(smem_max);
+    set_smem_all<true>(smem_max);
+    set_smem_all<false>(smem_max);
   }
-  const int slab_rows = ((TM + 2 * Wp) + SLAB_BOX_ROWS - 1) / SLAB_BOX_ROWS * SLAB_BOX_ROWS;
+  const int slab_rows = ((TM + 2 * Wp + (folded ? 0 : 2)) + SLAB_BOX_ROWS - 1) / SLAB_BOX_ROWS * SLAB_BOX_ROWS;
   const int fixed = 1024 + W_BYTES + 2 * O_TILE_BYTES + XCH_BYTES + BIAS_BYTES + (int)sizeof(Barriers);
   const int stage_bytes = slab_rows * KC * 2;
   int stages = (smem_max - fixed) / stage_bytes;
@@ -569,16 +622,8 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
       const bool fast = kchunks == 1 && p.n_cols == NT && p.ksteps == KC / 16 && shuffle == 0 && p.dbg == 0 &&
                         p.trace == nullptr;
       SRK_REQUIRE(fast || stats_sum == nullptr, "conv_fold: fused BN statistics need the single-chunk 64 -> 64 pass");
-      if (fast && stats_sum)
-        conv3x3_fold_tc_kernel<true, true, SRK_ACT_NONE><<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, tmRes, p);
-      else if (fast && p.act == SRK_ACT_NONE)
-        conv3x3_fold_tc_kernel<true, false, SRK_ACT_NONE><<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, tmRes, p);
-      else if (fast && p.act == SRK_ACT_RELU)
-        conv3x3_fold_tc_kernel<true, false, SRK_ACT_RELU><<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, tmRes, p);
-      else if (fast && p.act == SRK_ACT_PRELU)
-        conv3x3_fold_tc_kernel<true, false, SRK_ACT_PRELU><<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, tmRes, p);
-      else
-        conv3x3_fold_tc_kernel<false, false, ACT_RUNTIME><<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, tmRes, p);
+      if (folded) launch_pass<true>(fast, stats_sum != nullptr, p.act, grid, smem_bytes, st, tmA, tmW, tmY, tmRes, p);
+      else launch_pass<false>(fast, stats_sum != nullptr, p.act, grid, smem_bytes, st, tmA, tmW, tmY, tmRes, p);
       SRK_CUDA_LAUNCH_CHECK("conv3x3_fold_tc");
     }
   }

@@ -215,9 +215,10 @@ def test_conv_forward_backward_vs_oracle(cin, cout, k, h, w, n, act, shuffle, dt
 
 
 @pytest.mark.parametrize("cin,cout,k,h,w,n,act,shuffle", [c for c in CONV_CASES if c[2] == 3 and c[0] >= 64])
-@pytest.mark.parametrize("fold", [0, 1])
+@pytest.mark.parametrize("fold", [0, 1, 2])
 def test_conv3x3_both_tc_kernels_vs_oracle(cin, cout, k, h, w, n, act, shuffle, fold):
-    """Two tcgen05 kernels serve the 3x3 convs: the per-tap kernel (srk_conv_tc.cu) and the folded-tap kernel
+    """Three tcgen05 variants serve the 3x3 convs (0: per-tap kernel of srk_conv_tc.cu, 2: per-tap on the 16-warp
+    pipeline of srk_conv_fold_tc.cu, 1: the folded-tap kernel
     (srk_conv_fold_tc.cu, three horizontal taps in the MMA N dimension).  Both must match the oracle whichever
     one is the default."""
     import ctypes
