@@ -100,13 +100,21 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // kFold = false: the same pipeline with one MMA group per tap (N = 64, 36 MMAs per tile, A operand re-read per tap
 // from the row-shifted slab) and a plain one-slot epilogue - the per-tap formulation of srk_conv_tc.cu on the
 // 16-warp epilogue of this file.
-template <bool kFold, bool kFast, bool kStats, int kAct>
+// kPair = true (per-tap only): the CTAs of a 2-CTA cluster process the two halves of a 256-pixel tile with
+// tcgen05.mma.cta_group::2 (M = 256).  Each CTA stages its own slab and only HALF of the weight rows of every tap, so
+// the weight operand costs half the shared-memory bandwidth per SM.  Rank 0 issues the MMAs; all TMA loads signal
+// rank 0's barriers; MMA completion is multicast to both CTAs; the accumulator-free arrivals of rank 1's epilogue go
+// to rank 0 through shared::cluster.
+template <bool kFold, bool kFast, bool kStats, int kAct, bool kPair = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                        const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
                        const Params p) {
+  static_assert(!(kPair && kFold), "the CTA-pair variant is per-tap");
   constexpr int TMO = Tile<kFold>::TMO, ROW0 = Tile<kFold>::ROW0;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
   const int n_cols = kFast ? NT : p.n_cols;
+  const int w_rows = kPair ? n_cols / 2 : n_cols;   // weight rows per tap held by this CTA
   const int ksteps = kFast ? KC / 16 : p.ksteps;
   const int shuffle = kFast ? 0 : p.shuffle;
   const int act = kAct == ACT_RUNTIME ? p.act : kAct;
@@ -135,7 +143,7 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     for (int i = 0; i < S; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
     mbar_init(smem_u32(&bars->wfull), 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&bars->tfull[i]), 1); mbar_init(smem_u32(&bars->tempty[i]), kEpiThreads);
+      mbar_init(smem_u32(&bars->tfull[i]), 1); mbar_init(smem_u32(&bars->tempty[i]), (kPair ? 2 : 1) * kEpiWarps);
       mbar_init(smem_u32(&bars->oready[i]), kEpiThreads); mbar_init(smem_u32(&bars->ofree[i]), 1);
       mbar_init(smem_u32(&bars->rfull[i]), 1);
     }
@@ -146,41 +154,51 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     bias_s[c] = (p.bias && c < n_cols) ? __ldg(p.bias + p.bias_off + c) : 0.f;
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(&bars->tmem_base), 512);
-    tmem_relinquish();
+    if (kPair) { tmem_alloc_pair(smem_u32(&bars->tmem_base), 512); tmem_relinquish_pair(); }
+    else { tmem_alloc(smem_u32(&bars->tmem_base), 512); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();   // barriers initialised in both CTAs before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  // a pair walks its tiles in lockstep: both CTAs run an iteration iff the pair's first tile exists
+  auto tile_ok = [&](int tile) { return (kPair ? tile - (int)rank : tile) < p.num_tiles; };
 
   if (warp == 0) {
     // ================= TMA producer =================
+    const uint32_t wbar = kPair ? mapa_shared(smem_u32(&bars->wfull), 0) : smem_u32(&bars->wfull);
     if (elect_one()) {
       prefetch_tmap(&tmA);
       prefetch_tmap(&tmW);
-      const uint32_t wbar = smem_u32(&bars->wfull);
-      mbar_arrive_expect_tx(wbar, 9 * n_cols * KC * 2);
-      for (int t = 0; t < 9; ++t)   // smem order [r][s][n_cols rows]: the three s of a row are one N = 3 n_cols tile
-        tma_load_2d(wsm + t * n_cols * KC * 2, &tmW, wbar, p.k_col0, t * p.w_row_per_tap + p.w_row0);
+      if (!kPair || rank == 0) mbar_arrive_expect_tx(smem_u32(&bars->wfull), 9 * n_cols * KC * 2);
+      for (int t = 0; t < 9; ++t) {   // smem order [r][s][rows]: the three s of a row are one N = 3 n_cols tile
+        const uint32_t dst = wsm + t * w_rows * KC * 2;
+        const int wrow = t * p.w_row_per_tap + p.w_row0 + (int)rank * w_rows;
+        if (kPair) tma_load_2d_pair(dst, &tmW, wbar, p.k_col0, wrow);
+        else tma_load_2d(dst, &tmW, wbar, p.k_col0, wrow);
+      }
     }
     __syncwarp();
     int s = 0;
     uint32_t ph = 0;
     bool ok = true;
-    for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile_ok(tile) && ok; tile += gridDim.x) {
       ok = mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1, p.err, 1);
       if (!ok) break;
       if (elect_one()) {
-        const uint32_t fb = smem_u32(&bars->full[s]);
+        const uint32_t fb_local = smem_u32(&bars->full[s]);
+        const uint32_t fb = kPair ? mapa_shared(fb_local, 0) : fb_local;
         if (dbg & 4) {
-          mbar_arrive(fb);
+          mbar_arrive(fb_local);
         } else {
-          mbar_arrive_expect_tx(fb, p.slab_rows * KC * 2);
+          // pair: rank 0 expects the bytes of both slabs on its barrier; rank 1 only issues its loads
+          if (!kPair || rank == 0) mbar_arrive_expect_tx(fb_local, (kPair ? 2 : 1) * p.slab_rows * KC * 2);
           const int row0 = tile * TMO - p.Wp - 1;   // folded: pixel (tile*126 - 1) - Wp; per-tap: tile*128 - Wp - 1
-          for (int j = 0; j < p.slab_rows / SLAB_BOX_ROWS; ++j)
-            tma_load_2d(asm0 + s * p.stage_bytes + j * SLAB_BOX_ROWS * KC * 2, &tmA, fb, p.k_col0,
-                        row0 + j * SLAB_BOX_ROWS);
+          for (int j = 0; j < p.slab_rows / SLAB_BOX_ROWS; ++j) {
+            const uint32_t dst = asm0 + s * p.stage_bytes + j * SLAB_BOX_ROWS * KC * 2;
+            if (kPair) tma_load_2d_pair(dst, &tmA, fb, p.k_col0, row0 + j * SLAB_BOX_ROWS);
+            else tma_load_2d(dst, &tmA, fb, p.k_col0, row0 + j * SLAB_BOX_ROWS);
+          }
         }
         if (trace && blockIdx.x == 0 && tile / (int)gridDim.x < 32) trace[0 * 32 + tile / gridDim.x] = clock64();
       }
@@ -188,18 +206,19 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       if (++s == S) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    const uint32_t idesc = make_idesc_bf16(TM, kFold ? 3 * n_cols : n_cols, 0, 0);
+    if (rank == 0) {   // rank 1 of a pair has no MMA work: its operands are consumed by rank 0's instructions
+    // ================= MMA issuer (rank 0 of a pair issues for both CTAs) =================
+    const uint32_t idesc = make_idesc_bf16(kPair ? 2 * TM : TM, kFold ? 3 * n_cols : n_cols, 0, 0);
     const uint64_t desc_hi = make_smem_desc(0, 16, 1024, kLayoutSW128, 0) & 0xFFFFFFFF00000000ull;
     const uint32_t lo_base = (uint32_t)(make_smem_desc(0, 16, 1024, kLayoutSW128, 0) & 0xFFFFFFFFull);
     const uint32_t w_lo = lo_base + (wsm >> 4), a_lo0 = lo_base + (asm0 >> 4);
     const uint32_t row_units = (uint32_t)p.Wp * (KC * 2 / 16);   // one image row of the slab, in 16-byte units
-    const uint32_t wrow_units = (uint32_t)(3 * n_cols) * (KC * 2 / 16);   // one kernel row of weights
+    const uint32_t wrow_units = (uint32_t)(3 * w_rows) * (KC * 2 / 16);   // one kernel row of weights (this CTA's rows)
     const uint32_t stage_units = (uint32_t)p.stage_bytes >> 4;
     bool ok = mbar_wait(smem_u32(&bars->wfull), 0, p.err, 2);
     int s = 0, it = 0;
     uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile_ok(tile) && ok; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       ok = mbar_wait(smem_u32(&bars->tempty[acc]), ((it >> 1) & 1) ^ 1, p.err, 3);
       if (!ok) break;
@@ -225,21 +244,31 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             for (int c = 0; c < 3; ++c)
 #pragma unroll
               for (int ks = 0; ks < KC / 16; ++ks)
-                if (ks < ksteps && !(dbg & 2))
-                  umma_bf16(d_tmem, desc_hi | (a_lo + r * row_units + c * (KC * 2 / 16) + 2 * ks),
-                            desc_hi | (w_lo + r * wrow_units + c * (wrow_units / 3) + 2 * ks), idesc, (r | c | ks) != 0);
+                if (ks < ksteps && !(dbg & 2)) {
+                  const uint64_t ad = desc_hi | (a_lo + r * row_units + c * (KC * 2 / 16) + 2 * ks);
+                  const uint64_t bd = desc_hi | (w_lo + r * wrow_units + c * (wrow_units / 3) + 2 * ks);
+                  if (kPair) umma_bf16_pair(d_tmem, ad, bd, idesc, (r | c | ks) != 0);
+                  else umma_bf16(d_tmem, ad, bd, idesc, (r | c | ks) != 0);
+                }
         }
-        umma_commit(smem_u32(&bars->empty[s]));
-        umma_commit(smem_u32(&bars->tfull[acc]));
+        if (kPair) {
+          umma_commit_pair(smem_u32(&bars->empty[s]));
+          umma_commit_pair(smem_u32(&bars->tfull[acc]));
+        } else {
+          umma_commit(smem_u32(&bars->empty[s]));
+          umma_commit(smem_u32(&bars->tfull[acc]));
+        }
         if (trace && blockIdx.x == 0 && it < 32) trace[2 * 32 + it] = clock64();
       }
       __syncwarp();
       if (++s == S) { s = 0; ph ^= 1; }
     }
+    }
   } else if (warp == 2) {
     // ================= output store / residual load warp (plain, non-PixelShuffle outputs) =================
     if (shuffle == 0 && partial_out == nullptr && !(dbg & 1)) {
-      const int my_tiles = blockIdx.x < p.num_tiles ? (p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+      const int first = kPair ? (int)blockIdx.x - (int)rank : (int)blockIdx.x;   // lockstep with the pair's first tile
+      const int my_tiles = first < p.num_tiles ? (p.num_tiles - first + gridDim.x - 1) / gridDim.x : 0;
       if (p.has_residual && elect_one()) {
         prefetch_tmap(&tmR);
         for (int it = 0; it < 2 && it < my_tiles; ++it) {
@@ -298,7 +327,18 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // the named barriers below stay matched (a hung bar.sync would hang the GPU)
     bool ok = true;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    const uint32_t te0 = kPair ? mapa_shared(smem_u32(&bars->tempty[0]), 0) : smem_u32(&bars->tempty[0]);
+    const uint32_t te1 = kPair ? mapa_shared(smem_u32(&bars->tempty[1]), 0) : smem_u32(&bars->tempty[1]);
+    // one arrival per warp on the accumulator-free barrier (rank 0's, also for rank 1's epilogue)
+    auto release_acc = [&](int acc) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (kPair) mbar_arrive_cluster(acc ? te1 : te0);
+        else mbar_arrive(acc ? te1 : te0);
+      }
+    };
+    for (int tile = blockIdx.x; tile_ok(tile); tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const int pix = tile * TMO - ROW0 + row;
       // this thread's pixel is t - ROW0: same row of the image unless that underflows (then it is a border pixel)
@@ -317,8 +357,7 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       if (tr) trace[4 * 32 + it] = clock64();
       uint8_t* orow = optr + acc * O_TILE_BYTES + (row - ROW0) * 128;
       if (!active) {
-        tc_fence_before();
-        mbar_arrive(smem_u32(&bars->tempty[acc]));
+        release_acc(acc);
         if (staged) {
           if (ok) ok = mbar_wait(smem_u32(&bars->ofree[acc]), ((it >> 1) & 1) ^ 1, p.err, 7);
           if (ok && p.has_residual) ok = mbar_wait(smem_u32(&bars->rfull[acc]), (it >> 1) & 1, p.err, 8);
@@ -331,8 +370,7 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         uint32_t v1[CPT];
         tmem_ld_32x16(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * ACC_COLS + c0, v1);
         tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(smem_u32(&bars->tempty[acc]));   // the accumulator is in registers: MMA may refill it
+        release_acc(acc);   // the accumulator is in registers: MMA may refill it
         if (tr) trace[5 * 32 + it] = clock64();
 #pragma unroll
         for (int j = 0; j < CPT / 4; ++j) {
@@ -349,8 +387,7 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         tmem_ld_32x16(tbase, v0);                 // slot 0: belongs to the pixel one lane up
         tmem_ld_32x16(tbase + 2 * n_cols, v2);    // slot 2: belongs to the pixel one lane down
         tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(smem_u32(&bars->tempty[acc]));   // the accumulator is in registers: MMA may refill it
+        release_acc(acc);   // the accumulator is in registers: MMA may refill it
         if (tr) trace[5 * 32 + it] = clock64();
         if (lane == 31) {
 #pragma unroll
@@ -492,40 +529,48 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();   // no CTA of a pair exits while its peer may still signal it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (kPair) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
-template <bool kFold, bool kFast, bool kStats, int kAct>
+template <bool kFold, bool kFast, bool kStats, int kAct, bool kPair>
 static void set_smem(int smem_max) {
-  cudaFuncSetAttribute(conv3x3_fold_tc_kernel<kFold, kFast, kStats, kAct>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       smem_max);
+  cudaFuncSetAttribute(conv3x3_fold_tc_kernel<kFold, kFast, kStats, kAct, kPair>,
+                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
 }
-template <bool kFold>
+template <bool kFold, bool kPair>
 static void set_smem_all(int smem_max) {
-  set_smem<kFold, true, false, SRK_ACT_NONE>(smem_max);
-  set_smem<kFold, true, true, SRK_ACT_NONE>(smem_max);
-  set_smem<kFold, true, false, SRK_ACT_RELU>(smem_max);
-  set_smem<kFold, true, false, SRK_ACT_PRELU>(smem_max);
-  set_smem<kFold, false, false, ACT_RUNTIME>(smem_max);
+  set_smem<kFold, true, false, SRK_ACT_NONE, kPair>(smem_max);
+  set_smem<kFold, true, true, SRK_ACT_NONE, kPair>(smem_max);
+  set_smem<kFold, true, false, SRK_ACT_RELU, kPair>(smem_max);
+  set_smem<kFold, true, false, SRK_ACT_PRELU, kPair>(smem_max);
+  set_smem<kFold, false, false, ACT_RUNTIME, kPair>(smem_max);
 }
 
-template <bool kFold>
-static void launch_pass(bool fast, bool stats, int act, int grid, int smem_bytes, cudaStream_t st, const CUtensorMap& tmA,
-                        const CUtensorMap& tmW, const CUtensorMap& tmY, const CUtensorMap& tmRes, const Params& p) {
-  if (fast && stats)
-    conv3x3_fold_tc_kernel<kFold, true, true, SRK_ACT_NONE><<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, tmRes, p);
-  else if (fast && act == SRK_ACT_NONE)
-    conv3x3_fold_tc_kernel<kFold, true, false, SRK_ACT_NONE><<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, tmRes, p);
-  else if (fast && act == SRK_ACT_RELU)
-    conv3x3_fold_tc_kernel<kFold, true, false, SRK_ACT_RELU><<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, tmRes, p);
-  else if (fast && act == SRK_ACT_PRELU)
-    conv3x3_fold_tc_kernel<kFold, true, false, SRK_ACT_PRELU><<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, tmRes, p);
-  else
-    conv3x3_fold_tc_kernel<kFold, false, false, ACT_RUNTIME><<<grid, kThreads, smem_bytes, st>>>(tmA, tmW, tmY, tmRes, p);
+template <bool kFold, bool kFast, bool kStats, int kAct, bool kPair>
+static cudaError_t launch_one(int grid, int smem_bytes, cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmW,
+                              const CUtensorMap& tmY, const CUtensorMap& tmRes, const Params& p) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kPair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, conv3x3_fold_tc_kernel<kFold, kFast, kStats, kAct, kPair>, tmA, tmW, tmY, tmRes, p);
+}
+
+template <bool kFold, bool kPair>
+static cudaError_t launch_pass(bool fast, bool stats, int act, int grid, int smem_bytes, cudaStream_t st,
+                               const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmY,
+                               const CUtensorMap& tmRes, const Params& p) {
+  if (fast && stats) return launch_one<kFold, true, true, SRK_ACT_NONE, kPair>(grid, smem_bytes, st, tmA, tmW, tmY, tmRes, p);
+  if (fast && act == SRK_ACT_NONE) return launch_one<kFold, true, false, SRK_ACT_NONE, kPair>(grid, smem_bytes, st, tmA, tmW, tmY, tmRes, p);
+  if (fast && act == SRK_ACT_RELU) return launch_one<kFold, true, false, SRK_ACT_RELU, kPair>(grid, smem_bytes, st, tmA, tmW, tmY, tmRes, p);
+  if (fast && act == SRK_ACT_PRELU) return launch_one<kFold, true, false, SRK_ACT_PRELU, kPair>(grid, smem_bytes, st, tmA, tmW, tmY, tmRes, p);
+  return launch_one<kFold, false, false, ACT_RUNTIME, kPair>(grid, smem_bytes, st, tmA, tmW, tmY, tmRes, p);
 }
 
 }  // namespace fold
@@ -534,8 +579,10 @@ static void launch_pass(bool fast, bool stats, int act, int grid, int smem_bytes
 // per-tap kernel of srk_conv_tc.cu).
 int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout,
                            const float* bias, int act, const float* alpha, const srk_tensor* residual, int shuffle,
-                           float* stats_sum, float* stats_sumsq, void* workspace, int folded, cudaStream_t st) {
+                           float* stats_sum, float* stats_sumsq, void* workspace, int variant, cudaStream_t st) {
   using namespace fold;
+  // variant: 0 per-tap, 1 folded taps, 2 per-tap on CTA pairs (cta_group::2)
+  const bool folded = variant == 1, pair = variant == 2;
   const int TMO = folded ? Tile<true>::TMO : Tile<false>::TMO;
   const int cin = x->c;
   const int Hp = x->h + 2, Wp = x->w + 2;
@@ -546,8 +593,9 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    set_smem_all<true>(smem_max);
-    set_smem_all<false>(smem_max);
+    set_smem_all<true, false>(smem_max);
+    set_smem_all<false, false>(smem_max);
+    set_smem_all<false, true>(smem_max);
   }
   const int slab_rows = ((TM + 2 * Wp + (folded ? 0 : 2)) + SLAB_BOX_ROWS - 1) / SLAB_BOX_ROWS * SLAB_BOX_ROWS;
   const int fixed = 1024 + W_BYTES + 2 * O_TILE_BYTES + XCH_BYTES + BIAS_BYTES + (int)sizeof(Barriers);
@@ -583,7 +631,8 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
   const int nchunks = (cout + NT - 1) / NT, kchunks = (cin + KC - 1) / KC;
   SRK_REQUIRE(stats_sum == nullptr || (kchunks == 1 && shuffle == 0 && act == SRK_ACT_NONE && residual == nullptr),
               "conv_fold: fused BN statistics need a plain Cin == 64 conv");
-  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  if (pair) grid = (grid + 1) / 2 * 2 <= kNumSMs ? (grid + 1) / 2 * 2 : kNumSMs / 2 * 2;   // whole pairs
   {
     const long long step = (long long)grid * TMO, img = (long long)Hp * Wp;
     p.step_n = (int)(step / img);
@@ -593,7 +642,9 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
   for (int nc = 0; nc < nchunks; ++nc) {
     const int n_cols = cout - nc * NT < NT ? cout - nc * NT : NT;
     CUtensorMap tmW;
-    if (make_tmap_2d_bf16(&tmW, w_packed, (uint64_t)9 * cout, (uint64_t)cin, (uint64_t)cin, n_cols, KC, 128)) return 1;
+    if (make_tmap_2d_bf16(&tmW, w_packed, (uint64_t)9 * cout, (uint64_t)cin, (uint64_t)cin, pair ? n_cols / 2 : n_cols, KC,
+                          128))
+      return 1;
     for (int kc = 0; kc < kchunks; ++kc) {
       const bool first = kc == 0, last = kc == kchunks - 1;
       p.k_col0 = kc * KC;
@@ -622,8 +673,11 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
       const bool fast = kchunks == 1 && p.n_cols == NT && p.ksteps == KC / 16 && shuffle == 0 && p.dbg == 0 &&
                         p.trace == nullptr;
       SRK_REQUIRE(fast || stats_sum == nullptr, "conv_fold: fused BN statistics need the single-chunk 64 -> 64 pass");
-      if (folded) launch_pass<true>(fast, stats_sum != nullptr, p.act, grid, smem_bytes, st, tmA, tmW, tmY, tmRes, p);
-      else launch_pass<false>(fast, stats_sum != nullptr, p.act, grid, smem_bytes, st, tmA, tmW, tmY, tmRes, p);
+      cudaError_t le;
+      if (folded) le = launch_pass<true, false>(fast, stats_sum != nullptr, p.act, grid, smem_bytes, st, tmA, tmW, tmY, tmRes, p);
+      else if (pair) le = launch_pass<false, true>(fast, stats_sum != nullptr, p.act, grid, smem_bytes, st, tmA, tmW, tmY, tmRes, p);
+      else le = launch_pass<false, false>(fast, stats_sum != nullptr, p.act, grid, smem_bytes, st, tmA, tmW, tmY, tmRes, p);
+      SRK_REQUIRE(le == cudaSuccess, "conv3x3_fold_tc: launch failed: %s", cudaGetErrorString(le));
       SRK_CUDA_LAUNCH_CHECK("conv3x3_fold_tc");
     }
   }

@@ -502,15 +502,15 @@ int tc_read_err_flag() {
 // srk_conv_fold_tc.cu: 3x3 kernel with the horizontal taps folded into N (the default for 3x3)
 int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout,
                            const float* bias, int act, const float* alpha, const srk_tensor* residual, int shuffle,
-                           float* stats_sum, float* stats_sumsq, void* workspace, int folded, cudaStream_t st);
+                           float* stats_sum, float* stats_sumsq, void* workspace, int variant, cudaStream_t st);
 // 3x3 kernel choice: 0 = per-tap kernel of this file (8 epilogue warps), 1 = folded taps, 2 = per-tap on the 16-warp
-// pipeline of srk_conv_fold_tc.cu
+// pipeline of srk_conv_fold_tc.cu, 3 = as 2 on CTA pairs (cta_group::2, M = 256)
 static int g_tc_fold = -1;
 int tc_fold() {
   if (g_tc_fold < 0) {
     const char* e = getenv("SRK_TC_FOLD");
     g_tc_fold = e ? atoi(e) : 2;   // measured (C2 layer): fprop 23.2 / 24.4, fprop+stats 24.8 / 27.8, dgrad+res 25.8 / 27.1 us (2 / 0)
-    if (g_tc_fold < 0 || g_tc_fold > 2) g_tc_fold = 2;
+    if (g_tc_fold < 0 || g_tc_fold > 3) g_tc_fold = 2;
   }
   return g_tc_fold;
 }
@@ -533,9 +533,9 @@ int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w
                          float* stats_sum, float* stats_sumsq, void* workspace, cudaStream_t st) {
   // PixelShuffle outputs stay on the 8-warp kernel below: its threads own 32 channels = 16-byte stores per sub-pixel,
   // the 16-warp pipeline would store 8 bytes at a time (measured 64->256 at 128^2: 424 vs 685 us)
-  if (r == 3 && tc_fold() && !(tc_fold() == 2 && shuffle != 0)) {
+  if (r == 3 && tc_fold() && !(tc_fold() >= 2 && shuffle != 0)) {
     const int rc = conv_fprop_fold_launch(x, y, w_packed, cout, bias, act, alpha, residual, shuffle, stats_sum,
-                                          stats_sumsq, workspace, tc_fold() == 1, st);
+                                          stats_sumsq, workspace, tc_fold() == 1 ? 1 : (tc_fold() == 3 ? 2 : 0), st);
     if (rc >= 0) return rc;   // -1: slab does not fit (very wide images) -> per-tap kernel below
   }
   const int cin = x->c;
@@ -657,7 +657,7 @@ int probe_ldtm_rate(int nwarps, int batch, float* out_host);
 // (0 = none; it is cleared by the call), out_host[1] = the mode now in effect.  Synchronises the device.
 extern "C" int srk_tc_probe(int variant, float* out_host, int out_len) {
   if (variant >= 0 && variant <= 2) srk::tc_set_mode(variant);
-  if (variant >= 10 && variant <= 12) { srk::tc_fold(); srk::g_tc_fold = variant - 10; }  // 3x3 kernel choice (see tc_fold)
+  if (variant >= 10 && variant <= 13) { srk::tc_fold(); srk::g_tc_fold = variant - 10; }  // 3x3 kernel choice (see tc_fold)
   if (variant == 20 && out_host && out_len >= 2) {   // query: out[1] = 1 when the folded-tap kernel is the default
     out_host[0] = 0.f;
     out_host[1] = (float)srk::tc_fold();

@@ -215,7 +215,7 @@ def test_conv_forward_backward_vs_oracle(cin, cout, k, h, w, n, act, shuffle, dt
 
 
 @pytest.mark.parametrize("cin,cout,k,h,w,n,act,shuffle", [c for c in CONV_CASES if c[2] == 3 and c[0] >= 64])
-@pytest.mark.parametrize("fold", [0, 1, 2])
+@pytest.mark.parametrize("fold", [0, 1, 2, 3])
 def test_conv3x3_both_tc_kernels_vs_oracle(cin, cout, k, h, w, n, act, shuffle, fold):
     """Three tcgen05 variants serve the 3x3 convs (0: per-tap kernel of srk_conv_tc.cu, 2: per-tap on the 16-warp
     pipeline of srk_conv_fold_tc.cu, 1: the folded-tap kernel
