@@ -28,6 +28,16 @@ int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w
                          const srk_tensor* residual, int shuffle, float* stats_sum, float* stats_sumsq,
                          void* workspace, cudaStream_t st);
 int64_t conv_fprop_tc_workspace(const srk_tensor* x);
+// srk_conv_fold_tc.cu
+struct BnRedArgs {
+  const srk_tensor* z;
+  const float *mean, *invstd, *gamma, *beta, *alpha;
+  float *sum_g, *sum_gz, *dalpha;
+};
+int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout,
+                           const float* bias, int act, const float* alpha, const srk_tensor* residual, int shuffle,
+                           float* stats_sum, float* stats_sumsq, void* workspace, int variant, cudaStream_t st,
+                           const BnRedArgs* br);
 bool conv_smalln_tc_ok(const srk_tensor* x, const srk_tensor* y, int cout, int r, int s);
 int conv_smalln_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout, int r,
                           const float* bias, cudaStream_t st);
@@ -126,6 +136,27 @@ extern "C" int srk_conv_fprop(const srk_tensor* x, const srk_tensor* y, const vo
                              pixel_shuffle, st))
     return 1;
   return bn_sum ? srk_bn_stats(y, bn_sum, bn_sumsq, stream) : 0;
+}
+
+// Data gradient of a 3x3 64 -> 64 conv with the BatchNorm-backward reduction of the layer BELOW fused into the
+// epilogue: dx = dgrad(dz), and over interior pixels  sum_g[c] += sum g,  sum_gz[c] += sum g * z,
+// dalpha += sum_{b<0} g * b, with z the saved pre-BN activation, b = BN(z) and g = dx masked by the PReLU that sits
+// between that BN and this conv (alpha != NULL) or dx itself.  Returns 2 (and launches nothing) when the shape is
+// outside the fused kernel: the caller then runs srk_conv_fprop + srk_bn_bwd_reduce.
+extern "C" int srk_conv_dgrad_bnred(const srk_tensor* dz, const srk_tensor* dx, const void* w_packed_dgrad,
+                                    const srk_tensor* z, const float* mean, const float* invstd, const float* gamma,
+                                    const float* beta, const float* alpha, float* sum_g, float* sum_gz, float* dalpha,
+                                    void* stream) {
+  SRK_REQUIRE(tensor_ok(dz) && tensor_ok(dx) && tensor_ok(z) && w_packed_dgrad, "srk_conv_dgrad_bnred: bad tensors");
+  SRK_REQUIRE(mean && invstd && gamma && beta && sum_g && sum_gz, "srk_conv_dgrad_bnred: null statistics");
+  SRK_REQUIRE(alpha == nullptr || dalpha != nullptr, "srk_conv_dgrad_bnred: dalpha is required with alpha");
+  if (!(dz->layout == SRK_LAYOUT_ACT && dx->layout == SRK_LAYOUT_ACT && dz->dtype == SRK_BF16 && dx->dtype == SRK_BF16 &&
+        dz->c == 64 && dx->c == 64 && same_geometry(dz, dx)))
+    return 2;
+  BnRedArgs br = {z, mean, invstd, gamma, beta, alpha, sum_g, sum_gz, dalpha};
+  const int rc = conv_fprop_fold_launch(dz, dx, w_packed_dgrad, 64, nullptr, SRK_ACT_NONE, nullptr, nullptr, 0, nullptr,
+                                        nullptr, nullptr, 0, (cudaStream_t)stream, &br);
+  return rc < 0 ? 2 : rc;
 }
 
 extern "C" int64_t srk_conv_wgrad_workspace_bytes(const srk_tensor* x, const srk_tensor* dy, int r, int s,

@@ -48,7 +48,7 @@ constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;   // 608
 constexpr int CPT = 16;              // accumulator columns (output channels) per epilogue thread
 constexpr int O_TILE_BYTES = TM * NT * 2;  // bf16 output tile staged for the TMA store (126 rows used)
 constexpr int XCH_BYTES = 2 * 4 * 4 * 2 * CPT * 4;  // [acc][column quarter][lane group][slot 0 / slot 2][16 floats]
-constexpr int BIAS_BYTES = 256;
+constexpr int BIAS_BYTES = 1024;      // bias[64] | BN scale[64] | BN shift[64]
 constexpr int MAX_STAGES = 4;
 constexpr int ACC_COLS = 256;        // TMEM column stride between the two accumulator buffers
 constexpr int ACT_RUNTIME = -1;
@@ -75,6 +75,13 @@ struct Params {
   int Hp2, Wp2;        // padded sizes of the pixel-shuffled output
   float* stats_sum;
   float* stats_sumsq;
+  // BatchNorm-backward reduction fused into a dgrad (stats instantiation, bn_red = 1): the tile that arrives through
+  // the residual path is Z, the saved pre-BN activation of the BN layer this gradient flows into; instead of being
+  // added it gives  stats_sum[c] += sum g,  stats_sumsq[c] += sum g * z,  bn_dalpha += sum_{b<0} g * b  with
+  // b = z * sc + sh the BN output and g the PReLU-masked gradient (bn_mask = 1) or the gradient itself.
+  int bn_red, bn_mask;
+  const float* bn_mean; const float* bn_invstd; const float* bn_gamma; const float* bn_beta;
+  float* bn_dalpha;
   int* err;
   long long* trace;    // bring-up: per-tile clock64 stamps of CTA 0 ([16][32]) or null (general instantiation)
   int dbg;             // bring-up knobs (general instantiation only): 1 no stores, 2 no MMAs, 4 no A loads
@@ -152,6 +159,11 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (threadIdx.x >= 96 && threadIdx.x < 160) {
     const int c = threadIdx.x - 96;
     bias_s[c] = (p.bias && c < n_cols) ? __ldg(p.bias + p.bias_off + c) : 0.f;
+    if (kStats && p.bn_red) {
+      const float sc = __ldg(p.bn_gamma + c) * __ldg(p.bn_invstd + c);
+      bias_s[64 + c] = sc;
+      bias_s[128 + c] = __ldg(p.bn_beta + c) - __ldg(p.bn_mean + c) * sc;
+    }
   }
   if (warp == 1) {
     if (kPair) { tmem_alloc_pair(smem_u32(&bars->tmem_base), 512); tmem_relinquish_pair(); }
@@ -318,6 +330,8 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       wy = q / p.Wp;
       wx = q - wy * p.Wp;
     }
+    float bn_da = 0.f;
+    const float bn_alpha = (kStats && p.bn_red && p.bn_mask) ? __ldg(p.alpha) : 1.f;
     float s1[CPT], s2[CPT];
     if (stats_sum) {
 #pragma unroll
@@ -469,12 +483,45 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
         continue;
       }
-      if (stats_sum && interior) {
+      const bool bn_red = kStats && p.bn_red;
+      if (stats_sum && !bn_red && interior) {
 #pragma unroll
         for (int j = 0; j < CPT; ++j) { s1[j] += f[j]; s2[j] = fmaf(f[j], f[j], s2[j]); }
       }
       if (ok) ok = mbar_wait(smem_u32(&bars->ofree[acc]), ((it >> 1) & 1) ^ 1, p.err, 7);
-      if (p.has_residual) {
+      if (bn_red) {
+        // the "residual" tile is Z: reduce, do not add
+        if (ok) ok = mbar_wait(smem_u32(&bars->rfull[acc]), (it >> 1) & 1, p.err, 8);
+        if (interior) {
+#pragma unroll
+          for (int j = 0; j < CPT / 8; ++j) {
+            const uint4 rr = *reinterpret_cast<const uint4*>(orow + (((cq * (CPT / 8) + j) ^ ((row - ROW0) & 7)) << 4));
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rr);
+            const float4 sc0 = reinterpret_cast<const float4*>(bias_s + 64 + c0 + 8 * j)[0];
+            const float4 sc1 = reinterpret_cast<const float4*>(bias_s + 64 + c0 + 8 * j)[1];
+            const float4 sh0 = reinterpret_cast<const float4*>(bias_s + 128 + c0 + 8 * j)[0];
+            const float4 sh1 = reinterpret_cast<const float4*>(bias_s + 128 + c0 + 8 * j)[1];
+            const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+            const float shv[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 u = __bfloat1622float2(h[t]);
+              const float zz[2] = {u.x, u.y};
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int k = 8 * j + 2 * t + e;
+                float gd = f[k];
+                if (p.bn_mask) {
+                  const float b = fmaf(zz[e], scv[2 * t + e], shv[2 * t + e]);
+                  if (b < 0.f) { bn_da = fmaf(gd, b, bn_da); gd *= bn_alpha; }
+                }
+                s1[k] += gd;
+                s2[k] = fmaf(gd, zz[e], s2[k]);
+              }
+            }
+          }
+        }
+      } else if (p.has_residual) {
         if (ok) ok = mbar_wait(smem_u32(&bars->rfull[acc]), (it >> 1) & 1, p.err, 8);
         if (has_row) {
 #pragma unroll
@@ -526,6 +573,10 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         atomicAdd(stats_sum + p.cout_off + c0 + lane, s1[0]);
         atomicAdd(stats_sumsq + p.cout_off + c0 + lane, s2[0]);
       }
+      if (kStats && p.bn_red && p.bn_mask && p.bn_dalpha) {
+        const float t = warp_sum(bn_da);
+        if (lane == 0) atomicAdd(p.bn_dalpha, t);
+      }
     }
   }
   tc_fence_before();
@@ -575,11 +626,19 @@ static cudaError_t launch_pass(bool fast, bool stats, int act, int grid, int sme
 
 }  // namespace fold
 
+// BatchNorm-backward reduction fused into a 64 -> 64 dgrad (see Params::bn_red)
+struct BnRedArgs {
+  const srk_tensor* z;
+  const float *mean, *invstd, *gamma, *beta, *alpha;   // alpha: PReLU slope between the BN and this conv, or null
+  float *sum_g, *sum_gz, *dalpha;
+};
+
 // Returns 0 ok, 1 error, -1 "not applicable" (image too wide for two slab stages: the caller uses the
 // per-tap kernel of srk_conv_tc.cu).
 int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout,
                            const float* bias, int act, const float* alpha, const srk_tensor* residual, int shuffle,
-                           float* stats_sum, float* stats_sumsq, void* workspace, int variant, cudaStream_t st) {
+                           float* stats_sum, float* stats_sumsq, void* workspace, int variant, cudaStream_t st,
+                           const BnRedArgs* br) {
   using namespace fold;
   // variant: 0 per-tap, 1 folded taps, 2 per-tap on CTA pairs (cta_group::2)
   const bool folded = variant == 1, pair = variant == 2;
@@ -628,6 +687,20 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
   { const char* e = getenv("SRK_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.trace = g_tc_trace;
   p.stats_sum = stats_sum; p.stats_sumsq = stats_sumsq;
+  p.bn_red = 0; p.bn_mask = 0;
+  p.bn_mean = p.bn_invstd = p.bn_gamma = p.bn_beta = nullptr; p.bn_dalpha = nullptr;
+  if (br) {
+    SRK_REQUIRE(cin == KC && cout == NT && shuffle == 0 && act == SRK_ACT_NONE && residual == nullptr &&
+                    stats_sum == nullptr && variant == 0,
+                "conv_fold: the fused BN-backward reduction covers the plain 64 -> 64 per-tap dgrad");
+    SRK_REQUIRE(same_geometry(br->z, y) && br->z->dtype == SRK_BF16 && br->z->layout == SRK_LAYOUT_ACT,
+                "conv_fold: Z must match the dgrad output geometry (bf16 ACT)");
+    if (make_tmap_2d_bf16(&tmR, br->z->data, (uint64_t)P, (uint64_t)cout, (uint64_t)cout, TMO, NT, 128)) return 1;
+    p.stats_sum = stats_sum = br->sum_g; p.stats_sumsq = stats_sumsq = br->sum_gz;
+    p.bn_red = 1; p.bn_mask = br->alpha != nullptr; p.alpha = br->alpha;
+    p.bn_mean = br->mean; p.bn_invstd = br->invstd; p.bn_gamma = br->gamma; p.bn_beta = br->beta;
+    p.bn_dalpha = br->dalpha;
+  }
   const int nchunks = (cout + NT - 1) / NT, kchunks = (cin + KC - 1) / KC;
   SRK_REQUIRE(stats_sum == nullptr || (kchunks == 1 && shuffle == 0 && act == SRK_ACT_NONE && residual == nullptr),
               "conv_fold: fused BN statistics need a plain Cin == 64 conv");
@@ -665,7 +738,7 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
         p.partial_in = first ? nullptr : (const float*)workspace;
         SRK_REQUIRE(workspace != nullptr, "conv_fold: Cin > 64 with an activation needs the fprop workspace");
       } else {
-        p.has_residual = first ? (residual ? 1 : 0) : 1;
+        p.has_residual = first ? ((residual || br) ? 1 : 0) : 1;
         p.partial_out = nullptr;
         p.partial_in = nullptr;
       }

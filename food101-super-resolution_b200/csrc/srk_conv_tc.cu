@@ -502,7 +502,8 @@ int tc_read_err_flag() {
 // srk_conv_fold_tc.cu: 3x3 kernel with the horizontal taps folded into N (the default for 3x3)
 int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout,
                            const float* bias, int act, const float* alpha, const srk_tensor* residual, int shuffle,
-                           float* stats_sum, float* stats_sumsq, void* workspace, int variant, cudaStream_t st);
+                           float* stats_sum, float* stats_sumsq, void* workspace, int variant, cudaStream_t st,
+                           const struct BnRedArgs* br);
 // 3x3 kernel choice: 0 = per-tap kernel of this file (8 epilogue warps), 1 = folded taps, 2 = per-tap on the 16-warp
 // pipeline of srk_conv_fold_tc.cu, 3 = as 2 on CTA pairs (cta_group::2, M = 256)
 static int g_tc_fold = -1;
@@ -535,7 +536,7 @@ int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w
   // the 16-warp pipeline would store 8 bytes at a time (measured 64->256 at 128^2: 424 vs 685 us)
   if (r == 3 && tc_fold() && !(tc_fold() >= 2 && shuffle != 0)) {
     const int rc = conv_fprop_fold_launch(x, y, w_packed, cout, bias, act, alpha, residual, shuffle, stats_sum,
-                                          stats_sumsq, workspace, tc_fold() == 1 ? 1 : (tc_fold() == 3 ? 2 : 0), st);
+                                          stats_sumsq, workspace, tc_fold() == 1 ? 1 : (tc_fold() == 3 ? 2 : 0), st, nullptr);
     if (rc >= 0) return rc;   // -1: slab does not fit (very wide images) -> per-tap kernel below
   }
   const int cin = x->c;

@@ -374,8 +374,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
     const T* __restrict__ y, Geo g, int ppb, const float* __restrict__ mean,
     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
     const float* __restrict__ alpha_p, const float* __restrict__ dgamma, const float* __restrict__ dbeta,
-    float inv_count, int batch_stats, T* __restrict__ dy) {
+    float inv_count, int batch_stats, T* __restrict__ dy, float* __restrict__ dgamma_out) {
   const float alpha = alpha_p ? alpha_p[0] : 1.f;
+  // raw mode (dgamma_out != null): the reduction came out of a conv epilogue as (sum g, sum g*z) in (dbeta, dgamma);
+  // sum g*xhat = invstd * (sum g*z - mean * sum g).  Block 0 publishes the finished dgamma.
+  if (dgamma_out != nullptr && blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < g.C; c += blockDim.x) dgamma_out[c] = invstd[c] * (dgamma[c] - mean[c] * dbeta[c]);
+  }
   // dy = a1 * g' + a2 * v + a3 with g' = PReLU-masked dout; mask from b = v * a1 + sh   (4 constants / channel)
   float a1[VEC], a2[VEC], a3[VEC], sh[VEC];
   {
@@ -383,8 +388,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       const float is = invstd[c0 + j], mu = mean[c0 + j], ga = gamma[c0 + j];
+      const float dg = dgamma_out != nullptr ? is * (dgamma[c0 + j] - mu * dbeta[c0 + j]) : dgamma[c0 + j];
       const float k1 = batch_stats ? dbeta[c0 + j] * inv_count : 0.f;
-      const float k2 = batch_stats ? dgamma[c0 + j] * inv_count : 0.f;
+      const float k2 = batch_stats ? dg * inv_count : 0.f;
       a1[j] = ga * is;
       a2[j] = -a1[j] * is * k2;
       a3[j] = -a1[j] * k1 - a2[j] * mu;
@@ -962,8 +968,26 @@ extern "C" int srk_bn_bwd_apply(const srk_tensor* dout, const srk_tensor* y, con
   float inv_count = 1.f / ((float)y->n * y->h * y->w);
   DISPATCH_T_VEC(y, (bn_bwd_apply_kernel<T, VEC><<<blocks, 256, 0, (cudaStream_t)stream>>>(
                         (const T*)dout->data, (const T*)y->data, g, ppb, mean, invstd, gamma, beta,
-                        alpha, dgamma_b, dbeta_b, inv_count, batch_stats, (T*)dy->data)));
+                        alpha, dgamma_b, dbeta_b, inv_count, batch_stats, (T*)dy->data, nullptr)));
   SRK_CUDA_LAUNCH_CHECK("bn_bwd_apply");
+  return 0;
+}
+
+extern "C" int srk_bn_bwd_apply_raw(const srk_tensor* dout, const srk_tensor* y, const float* mean,
+                                    const float* invstd, const float* gamma, const float* beta,
+                                    const float* alpha, const float* sum_g, const float* sum_gz,
+                                    int batch_stats, float* dgamma_out, const srk_tensor* dy, void* stream) {
+  ACT_CHECK(y, "srk_bn_bwd_apply_raw"); ACT_CHECK(dout, "srk_bn_bwd_apply_raw"); ACT_CHECK(dy, "srk_bn_bwd_apply_raw");
+  SRK_REQUIRE(same_geometry(y, dout) && same_geometry(y, dy) && y->dtype == dout->dtype && y->dtype == dy->dtype,
+              "srk_bn_bwd_apply_raw: geometry mismatch");
+  SRK_REQUIRE(c_ok(y), "srk_bn_bwd_apply_raw: unsupported channel count %d", y->c);
+  SRK_REQUIRE(sum_g && sum_gz && dgamma_out, "srk_bn_bwd_apply_raw: sums and dgamma_out are required");
+  Geo g = geo_of(y); int blocks, ppb; pixel_grid(g, blocks, ppb);
+  float inv_count = 1.f / ((float)y->n * y->h * y->w);
+  DISPATCH_T_VEC(y, (bn_bwd_apply_kernel<T, VEC><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)dout->data, (const T*)y->data, g, ppb, mean, invstd, gamma, beta,
+                        alpha, sum_gz, sum_g, inv_count, batch_stats, (T*)dy->data, dgamma_out)));
+  SRK_CUDA_LAUNCH_CHECK("bn_bwd_apply_raw");
   return 0;
 }
 

@@ -106,11 +106,21 @@ def _conv_bn_forward(x, w, b, bn_params, bn_buffers, training, eps, momentum, al
     return y, out, stats
 
 
-def _conv_bn_backward(dout, x, y, stats, w, has_bias, gamma, beta, alpha, batch_stats, dgrad_residual, need_dx):
-    dy, dgamma, dbeta, dalpha = ops.bn_backward(dout, y, stats, gamma, beta, alpha, batch_stats)
-    dx = ops.conv_dgrad(dy, False, w, dgrad_residual, x.dtype) if need_dx else None
+def _conv_bn_backward(dout, x, y, stats, w, has_bias, gamma, beta, alpha, batch_stats, dgrad_residual, need_dx,
+                      pre=None, below=None):
+    """Backward of out = [PReLU](BN(conv(x))).  pre: raw BN-backward sums of dout when the dgrad that produced dout
+    already reduced them (ops.conv_dgrad_bnred).  below = (z, stats, gamma, beta, alpha) of the BatchNorm layer that
+    produced x: its backward reduction is then fused into this conv's dgrad and returned as the last item."""
+    dy, dgamma, dbeta, dalpha = ops.bn_backward(dout, y, stats, gamma, beta, alpha, batch_stats, pre=pre)
+    dx = red = None
+    if need_dx:
+        fused = ops.conv_dgrad_bnred(dy, w, *below) if (below is not None and dgrad_residual is None) else None
+        if fused is not None:
+            dx, red = fused
+        else:
+            dx = ops.conv_dgrad(dy, False, w, dgrad_residual, x.dtype)
     dw, db = ops.conv_wgrad(x, False, dy, False, w, has_bias, side=True)   # overlaps the next BN backward
-    return dx, dw, db, dgamma, dbeta, dalpha
+    return dx, dw, db, dgamma, dbeta, dalpha, red
 
 
 class ConvBN(torch.autograd.Function):
@@ -131,7 +141,7 @@ class ConvBN(torch.autograd.Function):
         x, y, stats, w, gamma, beta, alpha = ctx.saved_tensors
         has_bias, has_res, batch_stats = ctx.cfg
         dout = dout.contiguous()
-        dx, dw, db, dgamma, dbeta, dalpha = _conv_bn_backward(
+        dx, dw, db, dgamma, dbeta, dalpha, _ = _conv_bn_backward(
             dout, x, y, stats, w, has_bias, gamma, beta, alpha, batch_stats, None, _needs(ctx, 0))
         return (dx, dw, db, dgamma, dbeta, dalpha, dout if has_res else None,
                 None, None, None, None, None, None)
@@ -155,11 +165,13 @@ class ResBlockBN(torch.autograd.Function):
         x, y1, st1, a1, y2, st2, w1, g1, be1, alpha, w2, g2, be2 = ctx.saved_tensors
         hb1, hb2, batch_stats = ctx.cfg
         dout = dout.contiguous()
-        da1, dw2, db2, dg2, dbe2, _ = _conv_bn_backward(dout, a1, y2, st2, w2, hb2, g2, be2, None,
-                                                        batch_stats, None, True)
+        # conv2's dgrad produces da1, the gradient BN1 (+ PReLU) receives: BN1's backward reduction rides in its epilogue
+        da1, dw2, db2, dg2, dbe2, _, red1 = _conv_bn_backward(dout, a1, y2, st2, w2, hb2, g2, be2, None,
+                                                              batch_stats, None, True,
+                                                              below=(y1, st1, g1, be1, alpha))
         # the skip connection's gradient rides in the dgrad epilogue: dx = dgrad(dy1) + dout
-        dx, dw1, db1, dg1, dbe1, dalpha = _conv_bn_backward(da1, x, y1, st1, w1, hb1, g1, be1, alpha,
-                                                            batch_stats, dout, True)
+        dx, dw1, db1, dg1, dbe1, dalpha, _ = _conv_bn_backward(da1, x, y1, st1, w1, hb1, g1, be1, alpha,
+                                                               batch_stats, dout, True, pre=red1)
         return (dx, dw1, db1, dg1, dbe1, dalpha, dw2, db2, dg2, dbe2,
                 None, None, None, None, None, None, None)
 

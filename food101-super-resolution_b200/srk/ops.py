@@ -25,6 +25,8 @@ class _Config:
     # weight-gradient kernels (tensor-core / shared-memory bound) run on a side stream so that they overlap the
     # HBM-bound BatchNorm / activation backward passes of the next layer (see run_on_side_stream)
     overlap_wgrad = os.environ.get("SRK_OVERLAP_WGRAD", "1") != "0"
+    # BatchNorm-backward reductions ride in the epilogue of the dgrad that produces their input gradient
+    fuse_bn_reduce = os.environ.get("SRK_FUSE_BN_REDUCE", "1") != "0"
 
 
 cfg = _Config()
@@ -396,6 +398,32 @@ def conv_dgrad(dz, dz_img, weight, residual, out_dtype, perm_tc=False):
     return dx
 
 
+def conv_dgrad_bnred(dz, weight, z, stats, gamma, beta, alpha):
+    """dx = dgrad(dz) with the backward reduction of the BatchNorm layer below fused into the epilogue
+    (srk_conv_dgrad_bnred).  z / stats / gamma / beta: that BN's saved input, (mean, invstd) and affine parameters;
+    alpha: slope of the PReLU between the BN and this conv, or None.
+    -> (dx, red) with red = [sum g | sum g*z | dalpha] (fp32, 2C+1), or None when the fused kernel does not cover
+    the shape (the caller then runs conv_dgrad and the stand-alone reduction)."""
+    cout, cin, r, s = weight.shape
+    if not (cfg.fuse_bn_reduce and cfg.conv_impl != "simt" and r == 3 and s == 3 and cin == 64 and cout == 64
+            and dz.dtype == torch.bfloat16 and z.dtype == torch.bfloat16 and dz.shape == z.shape):
+        return None
+    n, c, h, w = geometry(dz, False)
+    pk = packed_weight(weight, L.PACK_DGRAD_TC, 0)
+    dx = new_act(n, cin, h, w, torch.bfloat16, dz.device)
+    red = zeros((2 * cin + 1,), dz.device)
+    rc = L.cdll.srk_conv_dgrad_bnred(act_desc(dz), act_desc(dx), pk.data_ptr(), act_desc(z), stats[0].data_ptr(),
+                                     stats[1].data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(alpha),
+                                     red[:cin].data_ptr(), red[cin:2 * cin].data_ptr(),
+                                     red[2 * cin:].data_ptr() if alpha is not None else None, stream_ptr())
+    if rc == 2:
+        return None
+    if rc != 0:
+        raise RuntimeError("srk_conv_dgrad_bnred failed: %s" % L.last_error())
+    L.launch_calls += 1
+    return dx, red
+
+
 def conv_wgrad(x, x_img, dz, dz_img, weight, need_bias, perm_tc=False, side=False):
     """-> (dW fp32 OIHW, db fp32 [Cout] or None).  side=True: launch on the side stream (run_on_side_stream);
     the caller must not read the results before the backward pass has ended."""
@@ -487,10 +515,19 @@ def bn_forward(y, gamma, beta, running_mean, running_var, nbt, training, eps, mo
     return out, stats
 
 
-def bn_backward(dout, y, stats, gamma, beta, alpha, batch_stats):
-    """-> (dy, dgamma, dbeta, dalpha or None)"""
+def bn_backward(dout, y, stats, gamma, beta, alpha, batch_stats, pre=None):
+    """-> (dy, dgamma, dbeta, dalpha or None).  pre: the raw sums of conv_dgrad_bnred when the reduction already
+    happened in the epilogue of the dgrad that produced dout."""
     c = y.shape[3]
     dev = y.device
+    if pre is not None:
+        sum_g, sum_gz, dalpha = pre[:c], pre[c:2 * c], pre[2 * c:]
+        dgamma = torch.empty((c,), dtype=torch.float32, device=dev)
+        dy = torch.empty_like(y)
+        L.call("srk_bn_bwd_apply_raw", act_desc(dout), act_desc(y), stats[0].data_ptr(), stats[1].data_ptr(),
+               gamma.data_ptr(), beta.data_ptr(), _ptr(alpha), sum_g.data_ptr(), sum_gz.data_ptr(),
+               1 if batch_stats else 0, dgamma.data_ptr(), act_desc(dy), stream_ptr())
+        return dy, dgamma, sum_g, (dalpha if alpha is not None else None)
     red = zeros((2 * c + 1,), dev)
     dgamma, dbeta, dalpha = red[:c], red[c:2 * c], red[2 * c:]
     mean, invstd = stats[0], stats[1]

@@ -89,6 +89,16 @@ int srk_conv_wgrad(const srk_tensor* x, const srk_tensor* dy, float* dw, float* 
                    int impl, int accumulate, void* workspace, void* stream);
 int64_t srk_conv_wgrad_workspace_bytes(const srk_tensor* x, const srk_tensor* dy, int r, int s, int impl);
 
+/* dgrad of a 3x3 64 -> 64 conv (bf16 ACT, w_packed_dgrad = SRK_PACK_DGRAD_TC weights) with the BatchNorm-backward
+ * REDUCTION of the BN layer below it fused into the epilogue (native_batch_norm_backward's sums of
+ * ResidualBlock.backward, models.py:56-57): z = that BN's saved input, alpha = the PReLU slope between the BN and
+ * this conv (models.py:57) or NULL.  Accumulates sum_g[64], sum_gz[64] (raw sums; srk_bn_bwd_apply_raw turns them into
+ * dgamma / the dy constants) and dalpha[1].  Returns 0 ok, 1 error, 2 = shape outside the fused kernel (nothing
+ * launched; run srk_conv_fprop + srk_bn_bwd_reduce instead). */
+int srk_conv_dgrad_bnred(const srk_tensor* dz, const srk_tensor* dx, const void* w_packed_dgrad, const srk_tensor* z,
+                         const float* mean, const float* invstd, const float* gamma, const float* beta,
+                         const float* alpha, float* sum_g, float* sum_gz, float* dalpha, void* stream);
+
 /* ---- convolutions with an RGB side on tcgen05 (K = 9 or 5; im2col built in shared memory) ---------
  * input_conv / SRCNN conv1 (3 -> 64, models.py:84,107,150) and the backward of output_conv / SRCNN conv3
  * (64 -> 3, models.py:86,125,167).  img3: IMAGE fp32 [N,3,H,W]; y, t64, dx: bf16 ACT [N,64,H,W].
@@ -154,6 +164,11 @@ int srk_bn_bwd_apply(const srk_tensor* dout, const srk_tensor* y, const float* m
                      const float* invstd, const float* gamma, const float* beta, const float* alpha,
                      const float* dgamma_b, const float* dbeta_b, int batch_stats,
                      const srk_tensor* dy, void* stream);
+/* as srk_bn_bwd_apply, fed with the raw sums of srk_conv_dgrad_bnred: sum_g = sum g (= dbeta), sum_gz = sum g * z;
+ * dgamma_out[C] receives invstd * (sum_gz - mean * sum_g). */
+int srk_bn_bwd_apply_raw(const srk_tensor* dout, const srk_tensor* y, const float* mean, const float* invstd,
+                         const float* gamma, const float* beta, const float* alpha, const float* sum_g,
+                         const float* sum_gz, int batch_stats, float* dgamma_out, const srk_tensor* dy, void* stream);
 
 /* ---- squeeze-excite gate (models.py:26-41,76-78): mean / mm / sigmoid / mul / add ------------- */
 /* pool[N][C] = mean over H,W of r */

@@ -615,3 +615,44 @@ def test_perceptual_loss_vs_oracle(dtype, hw):
         assert rel_err(f_srk, f_ref) <= 2e-2
         cos = torch.nn.functional.cosine_similarity(sg.grad.cpu().flatten(), go.flatten(), dim=0).item()
         assert cos >= 0.9, cos
+
+
+@pytest.mark.parametrize("with_prelu", [True, False])
+def test_dgrad_with_fused_bn_backward_reduction(with_prelu):
+    """srk_conv_dgrad_bnred: the BatchNorm-backward sums taken in the dgrad epilogue (from the fp32 accumulators)
+    against the stand-alone reduction kernel (which re-reads the bf16-rounded gradient), and the raw-sum form of the
+    BN-backward apply against the plain one."""
+    import srk
+    from srk import ops
+    srk.set_compute_dtype("bf16")
+    g = torch.Generator().manual_seed(23)
+    n, c, h, w = 3, 64, 21, 30
+
+    def act(scale=1.0):
+        t = torch.zeros(n, h + 2, w + 2, c)
+        t[:, 1:-1, 1:-1] = torch.randn(n, h, w, c, generator=g) * scale
+        return t.to(DEV).bfloat16()
+
+    dz, z = act(), act(2.0)
+    wt = (torch.randn(64, 64, 3, 3, generator=g) / 24).to(DEV)
+    gamma = (torch.rand(c, generator=g) + 0.5).to(DEV)
+    beta = (torch.randn(c, generator=g) * 0.3).to(DEV)
+    alpha = torch.tensor([0.25], device=DEV) if with_prelu else None
+    _, stats = ops.bn_forward(z, gamma, beta, None, None, None, True, 1e-5, 0.1, alpha, None)
+    fused = ops.conv_dgrad_bnred(dz, wt, z, stats, gamma, beta, alpha)
+    assert fused is not None, "the fused kernel must cover the 64 -> 64 trunk shape"
+    dx_f, red = fused
+    dx_u = ops.conv_dgrad(dz, False, wt, None, torch.bfloat16)
+    assert torch.equal(dx_f, dx_u)
+    dy_u, dgamma_u, dbeta_u, dalpha_u = ops.bn_backward(dx_u, z, stats, gamma, beta, alpha, True)
+    dy_f, dgamma_f, dbeta_f, dalpha_f = ops.bn_backward(dx_f, z, stats, gamma, beta, alpha, True, pre=red)
+    assert rel_err(dbeta_f.cpu(), dbeta_u.cpu()) <= 3e-3
+    assert rel_err(dgamma_f.cpu(), dgamma_u.cpu()) <= 3e-3
+    if with_prelu:
+        # dalpha = sum over b < 0 of g * b is a heavily cancelling signed sum: the two paths differ by the bf16 rounding
+        # of g, so the yardstick is the sum of magnitudes, not the (small) signed total
+        b = (z.float() - stats[0]) * stats[1] * gamma + beta
+        scale = (dx_u.float().abs() * b.abs() * (b < 0)).sum().item()
+        assert abs(dalpha_f.item() - dalpha_u.item()) <= 1e-3 * scale
+    assert rel_err(dy_f.float().cpu(), dy_u.float().cpu()) <= 1e-2
+    assert float(dy_f[:, 0].abs().max()) == 0 and float(dy_f[:, :, -1].abs().max()) == 0
