@@ -164,8 +164,13 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     if (my_tiles > 0 && mbar_wait(smem_u32(&bars->done), 0, p.err, 14)) {
       tc_fence_after();
       const int lg = warp & 3;
-      const int row = lg * 32 + lane;          // accumulator lane = (half, ci)
-      const int half = row >> 6, ci = row & 63;
+      // Flush: a thread holds one accumulator row (64 fp32 = 256 B), so storing it directly would write 16-byte pieces
+      // at a 256-byte lane stride (32 L1 wavefronts per instruction).  Each warp transposes its 32 rows through a
+      // padded tile in the (now idle) operand ring instead - conflict-free 16-byte stores, then two full rows per
+      // coalesced 512-byte global store.  Rows (tap 2a, ci) and (tap 2a+1, ci) of accumulator a are 128
+      // consecutive rows of this CTA's partial block.
+      constexpr int ROW_PITCH = NT * 4 + 16;   // 272 B: consecutive rows start in different 16-byte bank groups
+      uint8_t* tbuf = smem_al + lg * 32 * ROW_PITCH;
 #pragma unroll 1
       for (int a = 0; a < NACC; ++a) {
         uint32_t v[NT];
@@ -173,15 +178,21 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         tmem_ld_32x32(taddr, v);
         tmem_ld_32x32(taddr + 32, v + 32);
         tmem_ld_wait();
-        if (a == NACC - 1 && half == 1) continue;
-        const int tap = 2 * a + half;
-        // this CTA's partial sum, stored plainly (148 CTAs hammering the same 147 KB with atomics cost ~20 us);
-        // wgrad_fold_kernel adds the partials up
-        float4* dst = reinterpret_cast<float4*>(p.ws + ((size_t)blockIdx.x * TAPS + tap) * KC * NT + (size_t)ci * NT);
+        __syncwarp();   // the previous accumulator's rows have been read back
 #pragma unroll
         for (int j = 0; j < NT / 4; ++j)
-          dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                               __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          *reinterpret_cast<uint4*>(tbuf + lane * ROW_PITCH + j * 16) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        if (a == NACC - 1 && lg >= 2) continue;   // the fifth accumulator holds tap 8 only (rows 0..63)
+        // this CTA's partial sum, stored plainly (148 CTAs hammering the same 147 KB with atomics cost ~20 us);
+        // wgrad_fold_kernel adds the partials up
+        float* dst = p.ws + ((size_t)blockIdx.x * TAPS + 2 * a) * KC * NT + (size_t)(lg * 32) * NT;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int r = 2 * j + (lane >> 4), c = lane & 15;
+          const uint4 q = *reinterpret_cast<const uint4*>(tbuf + r * ROW_PITCH + c * 16);
+          *reinterpret_cast<uint4*>(dst + (size_t)r * NT + c * 4) = q;
+        }
       }
     }
   }
