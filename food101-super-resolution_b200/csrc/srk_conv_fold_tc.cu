@@ -97,6 +97,11 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+template <int N>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* v) {
+  if (N == 32) tmem_ld_32x32(taddr, v);
+  else tmem_ld_32x16(taddr, v);
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -112,12 +117,17 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // the weight operand costs half the shared-memory bandwidth per SM.  Rank 0 issues the MMAs; all TMA loads signal
 // rank 0's barriers; MMA completion is multicast to both CTAs; the accumulator-free arrivals of rank 1's epilogue go
 // to rank 0 through shared::cluster.
-template <bool kFold, bool kFast, bool kStats, int kAct, bool kPair = false>
+// kCPT: accumulator columns per epilogue thread.  16 covers passes of up to 64 output channels; 32 (CTA pairs only:
+// each CTA then holds 64 of the 128 weight rows of a tap, the same 72 KB as a 64-channel pass) runs N = 128 MMAs at
+// the tensor floor - used for the 64 -> 256 PixelShuffle convs, whose threads then store 16 bytes per sub-pixel.
+template <bool kFold, bool kFast, bool kStats, int kAct, bool kPair = false, int kCPT = 16>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                        const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
                        const Params p) {
   static_assert(!(kPair && kFold), "the CTA-pair variant is per-tap");
+  static_assert(kCPT == 16 || (kCPT == 32 && kPair && !kFast && !kStats), "N = 128 passes run on CTA pairs");
+  constexpr int CPT = kCPT;
   constexpr int TMO = Tile<kFold>::TMO, ROW0 = Tile<kFold>::ROW0;
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;
   const int n_cols = kFast ? NT : p.n_cols;
@@ -156,13 +166,13 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
     fence_barrier_init();
   }
-  if (threadIdx.x >= 96 && threadIdx.x < 160) {
+  if (threadIdx.x >= 96 && threadIdx.x < 96 + 4 * CPT) {
     const int c = threadIdx.x - 96;
     bias_s[c] = (p.bias && c < n_cols) ? __ldg(p.bias + p.bias_off + c) : 0.f;
     if (kStats && p.bn_red) {
       const float sc = __ldg(p.bn_gamma + c) * __ldg(p.bn_invstd + c);
-      bias_s[64 + c] = sc;
-      bias_s[128 + c] = __ldg(p.bn_beta + c) - __ldg(p.bn_mean + c) * sc;
+      bias_s[128 + c] = sc;
+      bias_s[192 + c] = __ldg(p.bn_beta + c) - __ldg(p.bn_mean + c) * sc;
     }
   }
   if (warp == 1) {
@@ -382,7 +392,7 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       float f[CPT];
       if (!kFold) {
         uint32_t v1[CPT];
-        tmem_ld_32x16(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * ACC_COLS + c0, v1);
+        tmem_ld_cols<CPT>(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * ACC_COLS + c0, v1);
         tmem_ld_wait();
         release_acc(acc);   // the accumulator is in registers: MMA may refill it
         if (tr) trace[5 * 32 + it] = clock64();
@@ -392,7 +402,7 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           f[4 * j] = __uint_as_float(v1[4 * j]) + b4.x; f[4 * j + 1] = __uint_as_float(v1[4 * j + 1]) + b4.y;
           f[4 * j + 2] = __uint_as_float(v1[4 * j + 2]) + b4.z; f[4 * j + 3] = __uint_as_float(v1[4 * j + 3]) + b4.w;
         }
-      } else
+      } else if (CPT == 16)
       {
         uint32_t v0[CPT], v1[CPT], v2[CPT];
         const uint32_t tbase = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * ACC_COLS + c0;
@@ -478,8 +488,13 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         for (int sub = 0; sub < 4; ++sub) {
           const long long o2 =
               ((long long)cn * p.Hp2 + (2 * (cy - 1) + (sub >> 1) + 1)) * p.Wp2 + (2 * (cx - 1) + (sub & 1) + 1);
-          uint2* dst = reinterpret_cast<uint2*>(p.y + o2 * p.cout_total + (p.cout_off + c0) / 4);
-          dst[0] = make_uint2(pack_bf16x2(f[sub], f[4 + sub]), pack_bf16x2(f[8 + sub], f[12 + sub]));
+          __nv_bfloat16* dst = p.y + o2 * p.cout_total + (p.cout_off + c0) / 4;
+          if (CPT == 32)
+            *reinterpret_cast<uint4*>(dst) =
+                make_uint4(pack_bf16x2(f[sub], f[4 + sub]), pack_bf16x2(f[8 + sub], f[12 + sub]),
+                           pack_bf16x2(f[(16 + sub) % CPT], f[(20 + sub) % CPT]), pack_bf16x2(f[(24 + sub) % CPT], f[(28 + sub) % CPT]));
+          else
+            *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(f[sub], f[4 + sub]), pack_bf16x2(f[8 + sub], f[12 + sub]));
         }
         continue;
       }
@@ -497,10 +512,10 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           for (int j = 0; j < CPT / 8; ++j) {
             const uint4 rr = *reinterpret_cast<const uint4*>(orow + (((cq * (CPT / 8) + j) ^ ((row - ROW0) & 7)) << 4));
             const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rr);
-            const float4 sc0 = reinterpret_cast<const float4*>(bias_s + 64 + c0 + 8 * j)[0];
-            const float4 sc1 = reinterpret_cast<const float4*>(bias_s + 64 + c0 + 8 * j)[1];
-            const float4 sh0 = reinterpret_cast<const float4*>(bias_s + 128 + c0 + 8 * j)[0];
-            const float4 sh1 = reinterpret_cast<const float4*>(bias_s + 128 + c0 + 8 * j)[1];
+            const float4 sc0 = reinterpret_cast<const float4*>(bias_s + 128 + c0 + 8 * j)[0];
+            const float4 sc1 = reinterpret_cast<const float4*>(bias_s + 128 + c0 + 8 * j)[1];
+            const float4 sh0 = reinterpret_cast<const float4*>(bias_s + 192 + c0 + 8 * j)[0];
+            const float4 sh1 = reinterpret_cast<const float4*>(bias_s + 192 + c0 + 8 * j)[1];
             const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
             const float shv[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
 #pragma unroll
@@ -587,9 +602,9 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   }
 }
 
-template <bool kFold, bool kFast, bool kStats, int kAct, bool kPair>
+template <bool kFold, bool kFast, bool kStats, int kAct, bool kPair, int kCPT = 16>
 static void set_smem(int smem_max) {
-  cudaFuncSetAttribute(conv3x3_fold_tc_kernel<kFold, kFast, kStats, kAct, kPair>,
+  cudaFuncSetAttribute(conv3x3_fold_tc_kernel<kFold, kFast, kStats, kAct, kPair, kCPT>,
                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
 }
 template <bool kFold, bool kPair>
@@ -601,7 +616,7 @@ static void set_smem_all(int smem_max) {
   set_smem<kFold, false, false, ACT_RUNTIME, kPair>(smem_max);
 }
 
-template <bool kFold, bool kFast, bool kStats, int kAct, bool kPair>
+template <bool kFold, bool kFast, bool kStats, int kAct, bool kPair, int kCPT = 16>
 static cudaError_t launch_one(int grid, int smem_bytes, cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmW,
                               const CUtensorMap& tmY, const CUtensorMap& tmRes, const Params& p) {
   cudaLaunchConfig_t cfg = {};
@@ -610,7 +625,7 @@ static cudaError_t launch_one(int grid, int smem_bytes, cudaStream_t st, const C
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kPair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, conv3x3_fold_tc_kernel<kFold, kFast, kStats, kAct, kPair>, tmA, tmW, tmY, tmRes, p);
+  return cudaLaunchKernelEx(&cfg, conv3x3_fold_tc_kernel<kFold, kFast, kStats, kAct, kPair, kCPT>, tmA, tmW, tmY, tmRes, p);
 }
 
 template <bool kFold, bool kPair>
@@ -640,8 +655,12 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
                            float* stats_sum, float* stats_sumsq, void* workspace, int variant, cudaStream_t st,
                            const BnRedArgs* br) {
   using namespace fold;
-  // variant: 0 per-tap, 1 folded taps, 2 per-tap on CTA pairs (cta_group::2)
-  const bool folded = variant == 1, pair = variant == 2;
+  // variant: 0 per-tap, 1 folded taps, 2 per-tap on CTA pairs (cta_group::2), 3 = CTA pairs with 128 output
+  // channels per pass (PixelShuffle outputs of a single-chunk contraction: the 64 -> 256 upsample convs)
+  const bool folded = variant == 1, pair = variant == 2 || variant == 3;
+  const int pass_n = variant == 3 ? 2 * NT : NT;
+  SRK_REQUIRE(variant != 3 || (shuffle == 2 && x->c == KC && cout % pass_n == 0 && residual == nullptr && stats_sum == nullptr),
+              "conv_fold: 128-channel passes serve single-chunk PixelShuffle convs with Cout %% 128 == 0");
   const int TMO = folded ? Tile<true>::TMO : Tile<false>::TMO;
   const int cin = x->c;
   const int Hp = x->h + 2, Wp = x->w + 2;
@@ -655,6 +674,7 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
     set_smem_all<true, false>(smem_max);
     set_smem_all<false, false>(smem_max);
     set_smem_all<false, true>(smem_max);
+    set_smem<false, false, false, ACT_RUNTIME, true, 32>(smem_max);
   }
   const int slab_rows = ((TM + 2 * Wp + (folded ? 0 : 2)) + SLAB_BOX_ROWS - 1) / SLAB_BOX_ROWS * SLAB_BOX_ROWS;
   const int fixed = 1024 + W_BYTES + 2 * O_TILE_BYTES + XCH_BYTES + BIAS_BYTES + (int)sizeof(Barriers);
@@ -701,7 +721,7 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
     p.bn_mean = br->mean; p.bn_invstd = br->invstd; p.bn_gamma = br->gamma; p.bn_beta = br->beta;
     p.bn_dalpha = br->dalpha;
   }
-  const int nchunks = (cout + NT - 1) / NT, kchunks = (cin + KC - 1) / KC;
+  const int nchunks = (cout + pass_n - 1) / pass_n, kchunks = (cin + KC - 1) / KC;
   SRK_REQUIRE(stats_sum == nullptr || (kchunks == 1 && shuffle == 0 && act == SRK_ACT_NONE && residual == nullptr),
               "conv_fold: fused BN statistics need a plain Cin == 64 conv");
   int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
@@ -713,7 +733,7 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
     p.step_x = (int)((step % img) % Wp);
   }
   for (int nc = 0; nc < nchunks; ++nc) {
-    const int n_cols = cout - nc * NT < NT ? cout - nc * NT : NT;
+    const int n_cols = cout - nc * pass_n < pass_n ? cout - nc * pass_n : pass_n;
     CUtensorMap tmW;
     if (make_tmap_2d_bf16(&tmW, w_packed, (uint64_t)9 * cout, (uint64_t)cin, (uint64_t)cin, pair ? n_cols / 2 : n_cols, KC,
                           128))
@@ -721,10 +741,10 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
     for (int kc = 0; kc < kchunks; ++kc) {
       const bool first = kc == 0, last = kc == kchunks - 1;
       p.k_col0 = kc * KC;
-      p.w_row0 = nc * NT;
+      p.w_row0 = nc * pass_n;
       p.cout_total = y->c;
-      p.cout_off = nc * NT;
-      p.bias_off = nc * NT;
+      p.cout_off = nc * pass_n;
+      p.bias_off = nc * pass_n;
       p.n_cols = n_cols;
       p.ksteps = (cin - kc * KC < KC ? cin - kc * KC : KC) / 16;
       p.bias = first ? bias : nullptr;
@@ -747,7 +767,9 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
                         p.trace == nullptr;
       SRK_REQUIRE(fast || stats_sum == nullptr, "conv_fold: fused BN statistics need the single-chunk 64 -> 64 pass");
       cudaError_t le;
-      if (folded) le = launch_pass<true, false>(fast, stats_sum != nullptr, p.act, grid, smem_bytes, st, tmA, tmW, tmY, tmRes, p);
+      if (variant == 3)
+        le = launch_one<false, false, false, ACT_RUNTIME, true, 32>(grid, smem_bytes, st, tmA, tmW, tmY, tmRes, p);
+      else if (folded) le = launch_pass<true, false>(fast, stats_sum != nullptr, p.act, grid, smem_bytes, st, tmA, tmW, tmY, tmRes, p);
       else if (pair) le = launch_pass<false, true>(fast, stats_sum != nullptr, p.act, grid, smem_bytes, st, tmA, tmW, tmY, tmRes, p);
       else le = launch_pass<false, false>(fast, stats_sum != nullptr, p.act, grid, smem_bytes, st, tmA, tmW, tmY, tmRes, p);
       SRK_REQUIRE(le == cudaSuccess, "conv3x3_fold_tc: launch failed: %s", cudaGetErrorString(le));

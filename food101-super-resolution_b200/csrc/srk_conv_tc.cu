@@ -507,6 +507,7 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
 // 3x3 kernel choice: 0 = per-tap kernel of this file (8 epilogue warps), 1 = folded taps, 2 = per-tap on the 16-warp
 // pipeline of srk_conv_fold_tc.cu, 3 = as 2 on CTA pairs (cta_group::2, M = 256)
 static int g_tc_fold = -1;
+static int g_up_pair = -1;
 int tc_fold() {
   if (g_tc_fold < 0) {
     const char* e = getenv("SRK_TC_FOLD");
@@ -534,6 +535,15 @@ int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w
                          float* stats_sum, float* stats_sumsq, void* workspace, cudaStream_t st) {
   // PixelShuffle outputs stay on the 8-warp kernel below: its threads own 32 channels = 16-byte stores per sub-pixel,
   // the 16-warp pipeline would store 8 bytes at a time (measured 64->256 at 128^2: 424 vs 685 us)
+  // 64 -> 256 PixelShuffle convs on CTA pairs with N = 128 MMAs (SRK_TC_UP_PAIR=1): parity-green but slower (128^2:
+  // 513 vs 421 us) - these convs are bound by their scattered 16-byte PixelShuffle stores, not by the MMAs
+  if (g_up_pair < 0) { const char* e = getenv("SRK_TC_UP_PAIR"); g_up_pair = e ? atoi(e) != 0 : 0; }
+  if (r == 3 && g_up_pair && shuffle == 2 && x->c == 64 && cout % 128 == 0 && residual == nullptr &&
+      stats_sum == nullptr) {
+    const int rc = conv_fprop_fold_launch(x, y, w_packed, cout, bias, act, alpha, residual, shuffle, nullptr, nullptr,
+                                          workspace, 3, st, nullptr);
+    if (rc >= 0) return rc;
+  }
   if (r == 3 && tc_fold() && !(tc_fold() >= 2 && shuffle != 0)) {
     const int rc = conv_fprop_fold_launch(x, y, w_packed, cout, bias, act, alpha, residual, shuffle, stats_sum,
                                           stats_sumsq, workspace, tc_fold() == 1 ? 1 : (tc_fold() == 3 ? 2 : 0), st, nullptr);
@@ -659,6 +669,7 @@ int probe_ldtm_rate(int nwarps, int batch, float* out_host);
 extern "C" int srk_tc_probe(int variant, float* out_host, int out_len) {
   if (variant >= 0 && variant <= 2) srk::tc_set_mode(variant);
   if (variant >= 10 && variant <= 13) { srk::tc_fold(); srk::g_tc_fold = variant - 10; }  // 3x3 kernel choice (see tc_fold)
+  if (variant == 30 || variant == 31) srk::g_up_pair = variant - 30;   // N = 128 CTA-pair upsample convs off / on
   if (variant == 20 && out_host && out_len >= 2) {   // query: out[1] = 1 when the folded-tap kernel is the default
     out_host[0] = 0.f;
     out_host[1] = (float)srk::tc_fold();

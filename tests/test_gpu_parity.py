@@ -237,6 +237,20 @@ def test_conv3x3_both_tc_kernels_vs_oracle(cin, cout, k, h, w, n, act, shuffle, 
         assert out[0] == 0, "tcgen05 protocol error flag %r" % out[0]
 
 
+def test_upsample_conv_on_cta_pairs_vs_oracle():
+    """64 -> 256 + PixelShuffle on the CTA-pair kernel with N = 128 passes (cta_group::2, off by default)."""
+    import ctypes
+    from srk import _lib as L
+    out = (ctypes.c_float * 2)()
+    L.call("srk_tc_probe", 31, out, 2)
+    try:
+        test_conv_forward_backward_vs_oracle(64, 256, 3, 20, 20, 1, "prelu", 2, "bf16")
+        test_conv_forward_backward_vs_oracle(64, 256, 3, 8, 6, 2, "prelu", 2, "bf16")
+    finally:
+        L.call("srk_tc_probe", 30, out, 2)
+        assert out[0] == 0, "tcgen05 protocol error flag %r" % out[0]
+
+
 def test_image_in_image_out_convs_vs_oracle():
     """9x9 3->C read straight from NCHW fp32 and 9x9 C->3 written straight to NCHW fp32."""
     from srk import _lib as L
