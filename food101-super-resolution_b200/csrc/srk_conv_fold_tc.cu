@@ -168,7 +168,12 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   }
   if (threadIdx.x >= 96 && threadIdx.x < 96 + 4 * CPT) {
     const int c = threadIdx.x - 96;
-    bias_s[c] = (p.bias && c < n_cols) ? __ldg(p.bias + p.bias_off + c) : 0.f;
+    int bi = p.bias_off + c;
+    if (shuffle == 2) {   // sub-pixel-major rows: packed row cop = sub * C + ch  <->  reference channel 4 ch + sub
+      const int cop = p.cout_off + c, sub = cop / p.cout_total;
+      bi = 4 * (cop - sub * p.cout_total) + sub;
+    }
+    bias_s[c] = (p.bias && c < n_cols) ? __ldg(p.bias + bi) : 0.f;
     if (kStats && p.bn_red) {
       const float sc = __ldg(p.bn_gamma + c) * __ldg(p.bn_invstd + c);
       bias_s[128 + c] = sc;
@@ -481,21 +486,18 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         for (int j = 0; j < CPT; ++j) f[j] = fmaf(alpha, fminf(f[j], 0.f), fmaxf(f[j], 0.f));
       }
       if (shuffle == 2) {
-        // PixelShuffle(2) as a store remap (models.py:118,121): column j of this pass is reference channel
-        // co = cout_off + c0 + j = 4c + sub  ->  output pixel (2y + sub/2, 2x + sub%2), channel c.
+        // PixelShuffle(2) as a store remap (models.py:118,121) over sub-pixel-major weight rows: this thread's CPT
+        // columns are packed rows cop = sub * C + ch, i.e. CPT consecutive channels of output pixel
+        // (2y + sub/2, 2x + sub%2)
         if (!interior) continue;
+        const int cop0 = p.cout_off + c0, sub = cop0 / p.cout_total, ch = cop0 - sub * p.cout_total;
+        const long long o2 =
+            ((long long)cn * p.Hp2 + (2 * (cy - 1) + (sub >> 1) + 1)) * p.Wp2 + (2 * (cx - 1) + (sub & 1) + 1);
+        uint4* dst = reinterpret_cast<uint4*>(p.y + o2 * p.cout_total + ch);
 #pragma unroll
-        for (int sub = 0; sub < 4; ++sub) {
-          const long long o2 =
-              ((long long)cn * p.Hp2 + (2 * (cy - 1) + (sub >> 1) + 1)) * p.Wp2 + (2 * (cx - 1) + (sub & 1) + 1);
-          __nv_bfloat16* dst = p.y + o2 * p.cout_total + (p.cout_off + c0) / 4;
-          if (CPT == 32)
-            *reinterpret_cast<uint4*>(dst) =
-                make_uint4(pack_bf16x2(f[sub], f[4 + sub]), pack_bf16x2(f[8 + sub], f[12 + sub]),
-                           pack_bf16x2(f[(16 + sub) % CPT], f[(20 + sub) % CPT]), pack_bf16x2(f[(24 + sub) % CPT], f[(28 + sub) % CPT]));
-          else
-            *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(f[sub], f[4 + sub]), pack_bf16x2(f[8 + sub], f[12 + sub]));
-        }
+        for (int j = 0; j < CPT / 8; ++j)
+          dst[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                              pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
         continue;
       }
       const bool bn_red = kStats && p.bn_red;

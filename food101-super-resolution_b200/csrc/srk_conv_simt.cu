@@ -383,11 +383,12 @@ struct PackTable {
   const float* w[PACK_MT];
   void* out[PACK_MT];
   short cout[PACK_MT], cin[PACK_MT];
-  signed char r[PACK_MT], kind[PACK_MT];
+  signed char r[PACK_MT], kind[PACK_MT], shuffle[PACK_MT];
 };
 __global__ void pack_weights_multi_kernel(const PackTable tb) {
   const int t = blockIdx.y;
-  pack_weights_body(tb.w[t], tb.out[t], tb.cout[t], tb.cin[t], tb.r[t], tb.r[t], tb.kind[t], 0, blockIdx.x, gridDim.x);
+  pack_weights_body(tb.w[t], tb.out[t], tb.cout[t], tb.cin[t], tb.r[t], tb.r[t], tb.kind[t], tb.shuffle[t], blockIdx.x,
+                    gridDim.x);
 }
 
 }  // namespace srk
@@ -422,7 +423,8 @@ extern "C" int srk_weight_pack(const float* w_oihw, void* out, int cout, int cin
 }
 
 extern "C" int srk_weight_pack_multi(int count, const float* const* w_oihw, void* const* out, const int32_t* cout,
-                                     const int32_t* cin, const int32_t* r, const int32_t* kind, void* stream) {
+                                     const int32_t* cin, const int32_t* r, const int32_t* kind,
+                                     const int32_t* pixel_shuffle, void* stream) {
   SRK_REQUIRE(count >= 0, "srk_weight_pack_multi: negative count");
   for (int base = 0; base < count; base += PACK_MT) {
     PackTable tb;
@@ -434,6 +436,7 @@ extern "C" int srk_weight_pack_multi(int count, const float* const* w_oihw, void
                   "srk_weight_pack_multi: bad entry %d", j);
       tb.w[i] = w_oihw[j]; tb.out[i] = out[j];
       tb.cout[i] = (short)cout[j]; tb.cin[i] = (short)cin[j]; tb.r[i] = (signed char)r[j]; tb.kind[i] = (signed char)kind[j];
+      tb.shuffle[i] = (signed char)(pixel_shuffle ? pixel_shuffle[j] : 0);
     }
     pack_weights_multi_kernel<<<dim3(64, c), 256, 0, (cudaStream_t)stream>>>(tb);
     SRK_CUDA_LAUNCH_CHECK("pack_weights_multi");

@@ -320,9 +320,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const float alpha = (p.act == SRK_ACT_PRELU) ? __ldg(p.alpha) : 0.f;
     const int img = p.Hp * p.Wp;
     const bool active = c0 < n_cols;   // a 32-column pass leaves the second column half idle (it still signals)
+    // PixelShuffle passes run over sub-pixel-major weight rows (SRK_PACK_FPROP_TC with pixel_shuffle = 2): column j of
+    // this thread is packed row cop = cout_off + c0 + j = sub * C + c (C = channels of y), i.e. reference channel
+    // 4c + sub: one sub-pixel per thread and pass, 32 consecutive output channels
+    const int ps_cop0 = p.cout_off + c0, ps_sub = p.shuffle == 2 ? ps_cop0 / p.cout_total : 0;
+    const int ps_c = ps_cop0 - ps_sub * p.cout_total;
     float bias[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) bias[j] = (p.bias && active) ? __ldg(p.bias + p.bias_off + c0 + j) : 0.f;
+    for (int j = 0; j < 32; ++j) {
+      const int bi = p.shuffle == 2 ? 4 * (ps_c + j) + ps_sub : p.bias_off + c0 + j;
+      bias[j] = (p.bias && active) ? __ldg(p.bias + bi) : 0.f;
+    }
     float s1[32], s2[32];
     if (stats_sum) {
 #pragma unroll
@@ -389,17 +397,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         f[j] = a;
       }
       if (p.shuffle == 2) {
-        // PixelShuffle(2) as a store remap (models.py:118,121): column j of this pass is reference channel
-        // co = cout_off + c0 + j = 4c + sub  ->  output pixel (2y + sub/2, 2x + sub%2), channel c.
+        // PixelShuffle(2) as a store remap (models.py:118,121): this thread's 32 columns are channels ps_c .. ps_c+31
+        // of output pixel (2y + sub/2, 2x + sub%2): one 64-byte run
         if (!interior) continue;
+        const long long orow =
+            ((long long)n * p.Hp2 + (2 * (yy - 1) + (ps_sub >> 1) + 1)) * p.Wp2 + (2 * (xx - 1) + (ps_sub & 1) + 1);
+        uint4* dst = reinterpret_cast<uint4*>(p.y + orow * p.cout_total + ps_c);
 #pragma unroll
-        for (int sub = 0; sub < 4; ++sub) {
-          const long long orow =
-              ((long long)n * p.Hp2 + (2 * (yy - 1) + (sub >> 1) + 1)) * p.Wp2 + (2 * (xx - 1) + (sub & 1) + 1);
-          uint4* dst = reinterpret_cast<uint4*>(p.y + orow * p.cout_total + (p.cout_off + c0) / 4);
-          dst[0] = make_uint4(pack_bf16x2(f[sub], f[4 + sub]), pack_bf16x2(f[8 + sub], f[12 + sub]),
-                              pack_bf16x2(f[16 + sub], f[20 + sub]), pack_bf16x2(f[24 + sub], f[28 + sub]));
-        }
+        for (int j = 0; j < 4; ++j)
+          dst[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                              pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
         continue;
       }
       // stage the bf16 tile in shared memory ([128 rows][128 B], SWIZZLE_128B) for one coalesced TMA store;
@@ -526,7 +533,7 @@ bool conv_tc_shape_ok(int cin, int cout, int r, int s, int dtype, int shuffle) {
   if (dtype != SRK_BF16 || r != s || (r != 3 && r != 1)) return false;
   // channels are processed in chunks of 64 with a 32-wide tail (96 = 64 + 32 for AttentionSR)
   if (cin % 32 != 0 || cout % 32 != 0 || cin < 64 || cout < 64) return false;
-  if (shuffle != 0 && !(shuffle == 2 && cout % NT == 0)) return false;
+  if (shuffle != 0 && !(shuffle == 2 && cout == 4 * NT)) return false;   // one sub-pixel per 64-row pass
   return true;
 }
 

@@ -41,7 +41,7 @@ SIGNATURES = {
     "srk_conv_rgb_bwd": (c_int, [_T, _T, _P, _T, _P, _P, c_int, c_int, _P, _P]),
     "srk_weight_pack": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "srk_weight_pack_bytes": (c_int64, [c_int] * 5),
-    "srk_weight_pack_multi": (c_int, [c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "srk_weight_pack_multi": (c_int, [c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     "srk_act_bwd": (c_int, [_T, _T, _T, c_int, _P, _P, c_int, c_int, _P]),
     "srk_bn_stats": (c_int, [_T, _P, _P, _P]),
     "srk_bn_finalize": (c_int, [_P, _P, c_int, c_int64, c_float, c_float, _P, _P, _P, _P, _P, _P]),

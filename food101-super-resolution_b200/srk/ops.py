@@ -191,7 +191,7 @@ def repack_all():
     optimizer step (srk.optim.Adam bumps the epoch): the next forward / backward then finds all packs ready
     instead of launching ~70 small pack kernels on first use."""
     import ctypes
-    srcs, dsts, couts, cins, rs, kinds, ents = [], [], [], [], [], [], []
+    srcs, dsts, couts, cins, rs, kinds, shufs, ents = [], [], [], [], [], [], [], []
     for ent in list(_pack_cache.values()):
         ref = ent.get("ref")
         w = ref() if ref is not None else None
@@ -201,17 +201,16 @@ def repack_all():
         if r != s:
             continue
         for (kind, shuffle), pk in ent["packs"].items():
-            if shuffle != 0:
-                continue
             srcs.append(w.data_ptr()); dsts.append(pk.data_ptr())
-            couts.append(cout); cins.append(cin); rs.append(r); kinds.append(kind)
+            couts.append(cout); cins.append(cin); rs.append(r); kinds.append(kind); shufs.append(shuffle)
         ents.append((ent, w))
     n = len(srcs)
     if n == 0:
         return 0
     vp = lambda v: (ctypes.c_void_p * n)(*v)
     ip = lambda v: (ctypes.c_int32 * n)(*v)
-    L.call("srk_weight_pack_multi", n, vp(srcs), vp(dsts), ip(couts), ip(cins), ip(rs), ip(kinds), stream_ptr())
+    L.call("srk_weight_pack_multi", n, vp(srcs), vp(dsts), ip(couts), ip(cins), ip(rs), ip(kinds), ip(shufs),
+           stream_ptr())
     for ent, w in ents:
         ent["ver"] = (w._version, _weights_epoch)
     return n
@@ -361,7 +360,9 @@ def conv_fprop(x, x_img, weight, bias, act, alpha, residual, shuffle, out_img, o
     rgb_tc = tc == 2 and out_img and act == L.ACT_NONE and residual is None
     use_tc = rgb_tc or (tc == 1 and (not out_img) and out_dtype == torch.bfloat16)
     kind = L.PACK_FPROP_TC_N8 if rgb_tc else (L.PACK_FPROP_TC if use_tc else L.PACK_FPROP_SIMT)
-    pk = packed_weight(weight, kind, 0)
+    # tensor-core PixelShuffle convs take their weight rows sub-pixel-major (row = sub * Cout/4 + c): a pass of 64
+    # rows then produces all channels of ONE output pixel per input pixel and stores whole 64-byte runs
+    pk = packed_weight(weight, kind, 2 if (shuffle == 2 and kind == L.PACK_FPROP_TC) else 0)
     if shuffle == 2:
         oc, oh, ow = cout // 4, 2 * h, 2 * w
     else:

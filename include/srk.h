@@ -120,7 +120,8 @@ int srk_weight_pack(const float* w_oihw, void* out, int cout, int cin, int r, in
 int64_t srk_weight_pack_bytes(int cout, int cin, int r, int s, int kind);
 /* `count` packs (square kernels, pixel_shuffle = 0) in ceil(count / 64) launches; host arrays of device pointers */
 int srk_weight_pack_multi(int count, const float* const* w_oihw, void* const* out, const int32_t* cout,
-                          const int32_t* cin, const int32_t* r, const int32_t* kind, void* stream);
+                          const int32_t* cin, const int32_t* r, const int32_t* kind, const int32_t* pixel_shuffle,
+                          void* stream);
 
 /* ---- activation backward: _prelu_kernel_backward / threshold_backward (+ pixel_unshuffle) ----
  * out: saved post-activation tensor; dout: its gradient; dz: gradient of the pre-activation in
