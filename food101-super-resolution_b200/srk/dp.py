@@ -76,12 +76,11 @@ class GradAverager:
         """flat buckets -> .grad"""
         if self.world == 1:
             return
+        # .grad becomes a view of the averaged flat bucket: no copy kernels (one per parameter before), and the
+        # optimizer reads the same memory the collective wrote.  The views stay valid until the next pack().
         for bucket, views in zip(self.buckets, self._views):
             for p, v in zip(bucket, views):
-                if p.grad is None:
-                    p.grad = v.view_as(p).clone()
-                else:
-                    p.grad.copy_(v.view_as(p))
+                p.grad = v.view_as(p)
 
     def average(self):
         self.pack()
