@@ -2,19 +2,27 @@
 //   input_conv 9x9 3->64 (models.py:107,150), SRCNN conv1 9x9 3->64 (models.py:84)       : forward + wgrad
 //   output_conv 9x9 64->3 (models.py:125,167), SRCNN conv3 5x5 64->3 (models.py:86)       : dgrad + wgrad
 //
-// All of them contract over k = (tap, rgb channel): KK = K*K*3 (243 / 75), padded to KP = 256 / 128.  The
-// kernel materialises, per 16x8-pixel tile, the im2col matrix A[128 pixels][KP] of the 3-channel fp32
+// All of them contract over k = (kernel row r, column s, rgb channel c).  The K axis is laid out in SEGMENTS of
+// SEGW = 28 / 16 elements per kernel row: k = r * SEGW + s * 3 + c (the 27 / 15 real entries of a row, then zero-weight
+// padding), the ones column at k = K * SEGW, padded to KP = 256 / 128.  With the halo of the 3-channel image staged
+// pixel-interleaved in shared memory ([row][x][rgb] bf16), a segment of A is then 56 / 32 CONTIGUOUS bytes of the
+// halo (9 / 5 neighbouring pixels), so the im2col builders copy 32-bit words instead of gathering 2-byte elements
+// (a second copy of the halo, shifted by one element, serves the pixels whose segment starts on an odd element).
+// The kernel materialises, per 16x8-pixel tile, the im2col matrix A[128 pixels][KP] of the 3-channel fp32
 // NCHW image T3 in shared memory (bf16, four/two [128 x 128 B] SWIZZLE_128B sub-tiles) and feeds it to the
 // tensor cores twice:
 //   (y)  Y[pixel][n]  = sum_k A[pixel][k] * Wk[n][k]          A K-major,  Wk K-major  -> ACT bf16 output
 //   (g)  G[k][n]     += sum_pixel A[pixel][k] * T64[pixel][n] A MN-major, T64 MN-major -> fp32 weight gradient
 // with T64 the 64-channel activation-layout tensor at the same pixels (TMA 4-D box, zero outside the image).
-// Column k = KK of A is 1 for in-image pixels, so row KK of G is the column sum of T64 (a bias gradient for
+// The ones column of A is 1 for in-image pixels, so that row of G is the column sum of T64 (a bias gradient for
 // free).  G stays in TMEM for the CTA's whole tile range and is flushed once with vector fp32 reductions.
 //
 // 18 warps: 0 TMA, 1 MMA issue, 2-9 im2col builders (two threads per pixel row), 10-17 epilogue.
 #include "srk_common.cuh"
 #include "srk_tc_common.cuh"
+
+#include <cstdlib>
+#include <cstring>
 
 namespace srk {
 
@@ -41,6 +49,7 @@ struct Params {
   float* ws;             // [KP][64] fp32 (g), zero-filled by the caller
   float* db3;            // [3]: sum over pixels of T3 (accumulated) or null
   int* err;
+  int dbg;               // bring-up knobs: 1 builders skip the A rows, 2 no MMAs, 4 no T64 loads, 8 no y stores, 16 no halo
 };
 
 struct __align__(8) Barriers {
@@ -57,24 +66,35 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint
       : "memory");
 }
 
+__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(tmap), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
 template <int K>
 struct Geo {
   static constexpr int KK = K * K * 3;
-  static constexpr int KP = (KK + 1 + 63) / 64 * 64;   // + the ones column
+  static constexpr int SEGW = (K * 3 + 1) / 2 * 2;      // elements per kernel-row segment (even: whole 32-bit words)
+  static constexpr int KONE = K * SEGW;                 // the ones column
+  static constexpr int KP = (KONE + 1 + 63) / 64 * 64;
   static constexpr int KCH = KP / 64;
   static constexpr int HH = TY + K - 1, HW = TX + K - 1;
-  static constexpr int HALO = 3 * HH * HW;              // bf16 elements
-  static constexpr int HALO_BYTES = (2 * HALO * 2 + 1023) / 1024 * 1024;   // double buffered
+  static constexpr int HALO = 3 * HH * HW;              // bf16 elements of one pixel-interleaved halo copy
+  static constexpr int HALO_PITCH = (HALO * 2 + 8 + 15) / 16 * 16;   // bytes per copy (+ the over-read of the last segment)
+  static constexpr int HALO_BYTES = (2 * 2 * HALO_PITCH + 1023) / 1024 * 1024;   // 2 copies, double buffered
   static constexpr int A_BYTES = KCH * SUB_BYTES;
   static constexpr int W_BYTES = KCH * NT * 128;
   static constexpr int T_BYTES = TM * 128;
-  // smem: [A x2][W][T64 x2][halo][barriers]
-  static constexpr int SMEM = 1024 + 2 * A_BYTES + W_BYTES + 2 * T_BYTES + HALO_BYTES + (int)sizeof(Barriers);
+  static constexpr int Y_BYTES = TM * 128;   // bf16 output tile staged for the TMA store
+  // smem: [A x2][W][T64 x2][Y][halo][barriers]
+  static constexpr int SMEM = 1024 + 2 * A_BYTES + W_BYTES + 2 * T_BYTES + Y_BYTES + HALO_BYTES + (int)sizeof(Barriers);
 };
 
 template <int K>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmT, const Params p) {
+conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmT,
+                   const __grid_constant__ CUtensorMap tmY, const Params p) {
   using G = Geo<K>;
   constexpr int PAD = K / 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -82,8 +102,10 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t a_sm = smem_base, w_sm = a_sm + 2 * G::A_BYTES, t_sm = w_sm + G::W_BYTES;
   uint8_t* a_ptr = smem_al;
-  __nv_bfloat16* halo = reinterpret_cast<__nv_bfloat16*>(smem_al + 2 * G::A_BYTES + G::W_BYTES + 2 * G::T_BYTES);
-  Barriers* bars = reinterpret_cast<Barriers*>(smem_al + 2 * G::A_BYTES + G::W_BYTES + 2 * G::T_BYTES + G::HALO_BYTES);
+  uint8_t* ystage = smem_al + 2 * G::A_BYTES + G::W_BYTES + 2 * G::T_BYTES;
+  const uint32_t y_sm = t_sm + 2 * G::T_BYTES;
+  uint8_t* halo = ystage + G::Y_BYTES;
+  Barriers* bars = reinterpret_cast<Barriers*>(halo + G::HALO_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int NG = G::KP / 128;        // G accumulators (M = 128 each)
   constexpr int TMEM_COLS = 256;         // Y: 2 x 64, G: up to 2 x 64
@@ -134,8 +156,11 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         if (!mbar_wait(smem_u32(&bars->tempty[s]), ((i >> 1) & 1) ^ 1, p.err, 31)) break;
         if (elect_one()) {
           const uint32_t fb = smem_u32(&bars->tfull[s]);
-          mbar_arrive_expect_tx(fb, G::T_BYTES);
-          tma_load_4d(t_sm + s * G::T_BYTES, &tmT, fb, p.t_col0, x0, y0, n);
+          if (p.dbg & 4) mbar_arrive(fb);
+          else {
+            mbar_arrive_expect_tx(fb, G::T_BYTES);
+            tma_load_4d(t_sm + s * G::T_BYTES, &tmT, fb, p.t_col0, x0, y0, n);
+          }
         }
         __syncwarp();
       }
@@ -167,7 +192,7 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           for (int q = 0; q < G::KCH; ++q)
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              umma_bf16(d, hi_k | (lo_k + a0 + q * (SUB_BYTES / 16) + 2 * ks),
+              if (!(p.dbg & 2)) umma_bf16(d, hi_k | (lo_k + a0 + q * (SUB_BYTES / 16) + 2 * ks),
                         hi_k | (lo_k + (w_sm >> 4) + q * (NT * 128 / 16) + 2 * ks), idesc_y, (q | ks) != 0);
           umma_commit(smem_u32(&bars->yfull[buf]));
         }
@@ -183,7 +208,7 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           for (int mh = 0; mh < NG; ++mh)
 #pragma unroll
             for (int ks = 0; ks < TM / 16; ++ks)
-              umma_bf16(tmem_base + 2 * NT + mh * NT,
+              if (!(p.dbg & 2)) umma_bf16(tmem_base + 2 * NT + mh * NT,
                         hi_k | (lo_ga + a0 + (2 * mh) * (SUB_BYTES / 16) + ks * (16 * 128 / 16)),
                         hi_k | (lo_gb + t0 + ks * (16 * 128 / 16)), idesc_g, (i | ks) != 0);
           umma_commit(smem_u32(&bars->tempty[buf]));
@@ -200,7 +225,7 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     const int bt = threadIdx.x - 64, bi = bt & 127, half = bt >> 7, ty = bi >> 3, tx = bi & 7;
     constexpr int PER = (G::HALO + kBuilders - 1) / kBuilders;   // halo elements staged per thread
     float s3[3] = {0.f, 0.f, 0.f};
-    const __nv_bfloat16 one = __float2bfloat16_rn(1.f), zero = __float2bfloat16_rn(0.f);
+    const __nv_bfloat16 one = __float2bfloat16_rn(1.f);
     float pre[PER];
     auto fetch = [&](int i) {   // global -> registers for tile i (issued one tile ahead of its use)
       const int tile = blockIdx.x + i * gridDim.x;
@@ -220,6 +245,10 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         pre[u] = v;
       }
     };
+    // the padding element of a row's last segment is read from just behind the halo (and multiplied by a zero
+    // weight): it must never be a NaN / Inf bit pattern
+    for (int z = bt; z < G::HALO_BYTES / 16; z += kBuilders) reinterpret_cast<uint4*>(halo)[z] = make_uint4(0, 0, 0, 0);
+    asm volatile("bar.sync 2, 256;" ::: "memory");
     if (my_tiles > 0) fetch(0);
     for (int i = 0; i < my_tiles; ++i) {
       const int tile = blockIdx.x + i * gridDim.x;
@@ -227,50 +256,62 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       const int y0 = (t2 / p.tiles_x) * TY, x0 = (t2 % p.tiles_x) * TX;
       (void)n;
       const int buf = i & 1;
-      __nv_bfloat16* hbuf = halo + buf * G::HALO;
+      // two pixel-interleaved copies of the halo: copy 0 at element e -> byte 2e, copy 1 shifted down by one element
+      // (element e -> byte 2e - 2), so that a segment starting on an odd element is word-aligned in copy 1
+      uint8_t* h0 = halo + (buf * 2) * G::HALO_PITCH;
+      uint8_t* h1 = h0 + G::HALO_PITCH;
 #pragma unroll
       for (int u = 0; u < PER; ++u) {
         const int idx = bt + u * kBuilders;
-        if (idx < G::HALO) hbuf[idx] = __float2bfloat16_rn(pre[u]);
+        if (idx < G::HALO && !(p.dbg & 16)) {
+          const int c = idx / (G::HH * G::HW), rem = idx - c * (G::HH * G::HW);   // fetch order: channel planes
+          const int e = rem * 3 + c;                                               // interleaved element index
+          const __nv_bfloat16 v = __float2bfloat16_rn(pre[u]);
+          *reinterpret_cast<__nv_bfloat16*>(h0 + 2 * e) = v;
+          if (e > 0) *reinterpret_cast<__nv_bfloat16*>(h1 + 2 * e - 2) = v;
+        }
       }
       // one barrier per tile: the other halo buffer is only rewritten after everybody passed this point again
       asm volatile("bar.sync 2, 256;" ::: "memory");
       if (i + 1 < my_tiles) fetch(i + 1);
       if (!mbar_wait(smem_u32(&bars->aempty[buf]), ((i >> 1) & 1) ^ 1, p.err, 36)) break;
       const bool inside = (y0 + ty < p.H) && (x0 + tx < p.W);
-      const __nv_bfloat16* hb = hbuf + ty * G::HW + tx;
+      // segment r of this pixel = SEGW elements from element ((ty + r) * HW + tx) * 3
+      const int e0 = (ty * G::HW + tx) * 3;
+      const uint8_t* hsrc = (e0 & 1) ? h1 + 2 * e0 - 2 : h0 + 2 * e0;
+      constexpr int ROW_STEP = G::HW * 3 * 2;        // bytes between consecutive halo rows
+      constexpr int WSEG = G::SEGW / 2;              // words per segment
+      constexpr int WROW = G::KP / 2;                // words per A row
+      constexpr int WONE = G::KONE / 2;              // word holding the ones column (KONE is even)
       uint8_t* arow = a_ptr + buf * G::A_BYTES + bi * 128;
+      const uint32_t one_word = inside ? (uint32_t)__bfloat16_as_ushort(one) : 0u;
 #pragma unroll
-      for (int jh = 0; jh < G::KP / 16; ++jh) {
+      for (int hsel = 0; hsel < 2; ++hsel) {
+        if (hsel != half || (p.dbg & 1)) continue;
 #pragma unroll
-        for (int hsel = 0; hsel < 2; ++hsel) {
-          if (hsel != half) continue;
-          const int j = hsel * (G::KP / 16) + jh;
-          __nv_bfloat16 e[8];
+        for (int cj = 0; cj < WROW / 8; ++cj) {      // 16-byte chunks of this thread's half row
+          const int chunk = hsel * (WROW / 8) + cj;
+          uint32_t wv[4];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const int k = j * 8 + t;
-            if (k < G::KK) {
-              const int tap = k / 3, c = k - tap * 3, r = tap / K, s = tap - r * K;
-              e[t] = hb[(c * G::HH + r) * G::HW + s];
-            } else if (k == G::KK) {
-              e[t] = inside ? one : zero;
+          for (int t = 0; t < 4; ++t) {
+            const int w = chunk * 4 + t;             // word index inside the A row (compile-time)
+            if (w < K * WSEG) {
+              const int r = w / WSEG, j = w - r * WSEG;
+              wv[t] = *reinterpret_cast<const uint32_t*>(hsrc + r * ROW_STEP + 4 * j);
+            } else if (w == WONE) {
+              wv[t] = one_word;
             } else {
-              e[t] = zero;
+              wv[t] = 0u;
             }
           }
-          uint4 q;
-          q.x = (uint32_t)__bfloat16_as_ushort(e[0]) | ((uint32_t)__bfloat16_as_ushort(e[1]) << 16);
-          q.y = (uint32_t)__bfloat16_as_ushort(e[2]) | ((uint32_t)__bfloat16_as_ushort(e[3]) << 16);
-          q.z = (uint32_t)__bfloat16_as_ushort(e[4]) | ((uint32_t)__bfloat16_as_ushort(e[5]) << 16);
-          q.w = (uint32_t)__bfloat16_as_ushort(e[6]) | ((uint32_t)__bfloat16_as_ushort(e[7]) << 16);
-          const int sub = j >> 3, jj = j & 7;
-          *reinterpret_cast<uint4*>(arow + sub * SUB_BYTES + ((jj ^ (bi & 7)) << 4)) = q;
+          const int sub = chunk >> 3, jj = chunk & 7;
+          *reinterpret_cast<uint4*>(arow + sub * SUB_BYTES + ((jj ^ (bi & 7)) << 4)) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
         }
       }
       if (p.db3 && inside && half == 0) {
+        const __nv_bfloat16* hc = reinterpret_cast<const __nv_bfloat16*>(h0) + ((ty + PAD) * G::HW + tx + PAD) * 3;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) s3[c] += __bfloat162float(hb[(c * G::HH + PAD) * G::HW + PAD]);
+        for (int c = 0; c < 3; ++c) s3[c] += __bfloat162float(hc[c]);
       }
       fence_proxy_async();
       mbar_arrive(smem_u32(&bars->afull[buf]));
@@ -310,9 +351,7 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         mbar_arrive(smem_u32(&bars->yempty[buf]));
         const int tile = blockIdx.x + i * gridDim.x;
         const int n = tile / tiles_per_img, t2 = tile - n * tiles_per_img;
-        const int y = (t2 / p.tiles_x) * TY + ty, x = (t2 % p.tiles_x) * TX + tx;
-        if (y >= p.H || x >= p.W || c0 >= p.n_valid) continue;
-        uint4* dst = reinterpret_cast<uint4*>(p.y + (((size_t)n * Hp + y + 1) * Wp + x + 1) * p.y_stride + p.y_col0 + c0);
+        const int y0 = (t2 / p.tiles_x) * TY, x0 = (t2 % p.tiles_x) * TX;
         uint4 o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -329,10 +368,22 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           o[j] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
                             *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
         }
+        // The [16 x 8 pixels][64 ch] tile goes out as ONE 4-D TMA store from a swizzled staging tile (row = pixel):
+        // per-thread 16-byte stores at a 128-byte lane stride cost ~1000 L1 wavefronts per tile (measured 176 us of
+        // the 612 us output-conv backward).  Pixels / channels outside the tensor are clipped by the TMA unit.
+        if (threadIdx.x == 320) tma_store_wait_read0();      // the previous tile has left the staging buffer
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        uint8_t* orow = ystage + ei * 128;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (c0 + j * 8 < p.n_valid) dst[j] = o[j];
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(orow + (((ch * 4 + j) ^ (ei & 7)) << 4)) = o[j];
+        fence_proxy_async();
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        if (threadIdx.x == 320 && !(p.dbg & 8)) {
+          tma_store_4d(&tmY, y_sm, p.y_col0, x0, y0, n);
+          tma_store_commit();
+        }
       }
+      if (threadIdx.x == 320) tma_store_wait_all();
     }
     if (p.do_g && my_tiles > 0 && mbar_wait(smem_u32(&bars->done), 0, p.err, 38)) {
       tc_fence_after();
@@ -359,20 +410,21 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   }
 }
 
-// ws[k][n] -> OIHW gradient.  rgb_out = 0: dW[n][c][tap] (3 -> 64 conv), db[n] = ws[KK][n]
-//                               rgb_out = 1: dW[c][n][taps-1-tap] (64 -> 3 conv; im2col was taken over dY)
+// ws[k][n] -> OIHW gradient, k = r * SEGW + s * 3 + c.  rgb_out = 0: dW[n][c][tap] (3 -> 64 conv), db[n] = ws[KONE][n]
+//                                                       rgb_out = 1: dW[c][n][taps-1-tap] (64 -> 3 conv; im2col over dY)
 __global__ void fold_kernel(const float* __restrict__ ws, float* __restrict__ dw, float* __restrict__ db, int K,
                             int rgb_out, int n0, int n_total) {
-  const int taps = K * K, KK = taps * 3;
+  const int taps = K * K, segw = (K * 3 + 1) / 2 * 2, kone = K * segw;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < KK * NT) {
-    const int n = i % NT, k = i / NT, tap = k / 3, c = k - tap * 3;
-    if (n0 + n >= n_total) return;
+  if (i < kone * NT) {
+    const int n = i % NT, k = i / NT, r = k / segw, t = k - r * segw;
+    if (t >= K * 3 || n0 + n >= n_total) return;
+    const int sx = t / 3, c = t - sx * 3, tap = r * K + sx;
     const float v = ws[i];
     if (!rgb_out) dw[((size_t)(n0 + n) * 3 + c) * taps + tap] += v;
     else dw[((size_t)c * n_total + n0 + n) * taps + (taps - 1 - tap)] += v;
-  } else if (i < (KK + 1) * NT && db != nullptr && !rgb_out) {
-    const int n = i - KK * NT;
+  } else if (i < (kone + 1) * NT && db != nullptr && !rgb_out) {
+    const int n = i - kone * NT;
     if (n0 + n < n_total) db[n0 + n] += ws[i];
   }
 }
@@ -394,14 +446,15 @@ static int make_tmap_act_4d_tile(CUtensorMap* out, const srk_tensor* x) {
 }
 
 template <int K>
-static int launch(const CUtensorMap& tmW, const CUtensorMap& tmT, const Params& p, cudaStream_t st) {
+static int launch(const CUtensorMap& tmW, const CUtensorMap& tmT, const CUtensorMap& tmY, const Params& p,
+                  cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(conv_rgb_tc_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<K>::SMEM);
     attr = true;
   }
   const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
-  conv_rgb_tc_kernel<K><<<grid, kThreads, Geo<K>::SMEM, st>>>(tmW, tmT, p);
+  conv_rgb_tc_kernel<K><<<grid, kThreads, Geo<K>::SMEM, st>>>(tmW, tmT, tmY, p);
   SRK_CUDA_LAUNCH_CHECK("conv_rgb_tc");
   return 0;
 }
@@ -427,9 +480,10 @@ int conv_rgb_tc_run(const srk_tensor* t3, const srk_tensor* y, const void* w_pac
   p.t3 = (const float*)t3->data; p.bias = bias; p.alpha = alpha;
   p.y = y ? (__nv_bfloat16*)y->data : nullptr;
   p.ws = (float*)workspace; p.db3 = db3; p.err = tc_err_flag();
+  { const char* e = getenv("SRK_RGB_DBG"); p.dbg = e ? atoi(e) : 0; }
   const int KP = k == 9 ? rgb::Geo<9>::KP : rgb::Geo<5>::KP;
-  CUtensorMap tmW, tmT;
-  memset(&tmW, 0, sizeof(tmW)); memset(&tmT, 0, sizeof(tmT));
+  CUtensorMap tmW, tmT, tmY;
+  memset(&tmW, 0, sizeof(tmW)); memset(&tmT, 0, sizeof(tmT)); memset(&tmY, 0, sizeof(tmY));
   // the 64-channel side may have 64 or 96 channels: one pass per 64-channel chunk (tails are zero-filled by TMA)
   const int c64 = p.do_y ? y->c : t64->c;
   if (p.do_y) {
@@ -437,6 +491,7 @@ int conv_rgb_tc_run(const srk_tensor* t3, const srk_tensor* y, const void* w_pac
                     y->h == p.H && y->w == p.W,
                 "conv_rgb: y must be a bf16 ACT tensor with 64 or 96 channels");
     if (make_tmap_2d_bf16(&tmW, w_packed, (uint64_t)(rgb_out ? 64 : y->c), (uint64_t)KP, (uint64_t)KP, 64, 64, 128)) return 1;
+    if (rgb::make_tmap_act_4d_tile(&tmY, y)) return 1;   // output tiles leave through a 4-D TMA store
   }
   if (p.do_g) {
     SRK_REQUIRE(t64->layout == SRK_LAYOUT_ACT && t64->dtype == SRK_BF16 && t64->c % 32 == 0 && t64->c >= 64 &&
@@ -455,10 +510,10 @@ int conv_rgb_tc_run(const srk_tensor* t3, const srk_tensor* y, const void* w_pac
     p.t_col0 = n0;
     p.db3 = n0 == 0 ? db3 : nullptr;
     if (p.do_g) cudaMemsetAsync(workspace, 0, (size_t)KP * 64 * 4, st);
-    int rc = k == 9 ? rgb::launch<9>(tmW, tmT, p, st) : rgb::launch<5>(tmW, tmT, p, st);
+    int rc = k == 9 ? rgb::launch<9>(tmW, tmT, tmY, p, st) : rgb::launch<5>(tmW, tmT, tmY, p, st);
     if (rc) return rc;
     if (p.do_g) {
-      const int total = (k * k * 3 + 1) * 64;
+      const int total = (k * ((k * 3 + 1) / 2 * 2) + 1) * 64;
       rgb::fold_kernel<<<(total + 255) / 256, 256, 0, st>>>((const float*)workspace, dw, db, k, rgb_out, n0, c64);
       SRK_CUDA_LAUNCH_CHECK("conv_rgb_fold");
     }

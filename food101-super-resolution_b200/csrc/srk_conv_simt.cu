@@ -320,7 +320,8 @@ __device__ __forceinline__ void pack_weights_body(const float* __restrict__ w, v
   long long total = (long long)Cout * Cin * R * S;
   const int NPn8 = S * 3 > 16 ? 32 : 16;
   if (kind == SRK_PACK_FPROP_TC_N8) total = (long long)R * NPn8 * Cin;
-  const int KPr = (R * S * 3 + 1 + 63) / 64 * 64;
+  const int SEGr = (S * 3 + 1) / 2 * 2;                 // K layout of the RGB-side tcgen05 kernels: k = r * SEG + s * 3 + c
+  const int KPr = (R * SEGr + 1 + 63) / 64 * 64;
   if (kind == SRK_PACK_RGBOUT_DGRAD_TC) total = 64LL * KPr;
   if (kind == SRK_PACK_RGBIN_TC) total = (long long)Cout * KPr;
   for (long long i = bx * (long long)blockDim.x + threadIdx.x; i < total; i += gx * blockDim.x) {
@@ -328,8 +329,9 @@ __device__ __forceinline__ void pack_weights_body(const float* __restrict__ w, v
     if (kind == SRK_PACK_RGBIN_TC || kind == SRK_PACK_RGBOUT_DGRAD_TC) {  // bf16 [64][KP]
       int k = (int)(i % KPr), n = (int)(i / KPr);
       float v = 0.f;
-      if (k < R * S * 3) {
-        int tap = k / 3, c = k - tap * 3, r = tap / S, s = tap - r * S;
+      const int r = k / SEGr, tk = k - r * SEGr;
+      if (r < R && tk < S * 3) {
+        int s = tk / 3, c = tk - s * 3;
         if (kind == SRK_PACK_RGBIN_TC) {            // n = co (Cout == 64), c = ci (Cin == 3)
           if (n < Cout && c < Cin) v = w[(((long long)n * Cin + c) * R + r) * S + s];
         } else {                                      // n = ci (Cin == 64), c = co (Cout <= 3), rot180
@@ -398,8 +400,9 @@ using namespace srk;
 extern "C" int64_t srk_weight_pack_bytes(int cout, int cin, int r, int s, int kind) {
   int64_t n = (int64_t)cout * cin * r * s;
   if (kind == SRK_PACK_FPROP_TC_N8) return (int64_t)r * (s * 3 > 16 ? 32 : 16) * cin * 2;
-  if (kind == SRK_PACK_RGBOUT_DGRAD_TC) return 64LL * ((r * s * 3 + 1 + 63) / 64 * 64) * 2;
-  if (kind == SRK_PACK_RGBIN_TC) return (int64_t)cout * ((r * s * 3 + 1 + 63) / 64 * 64) * 2;
+  const int64_t kp_rgb = (r * ((s * 3 + 1) / 2 * 2) + 1 + 63) / 64 * 64;
+  if (kind == SRK_PACK_RGBOUT_DGRAD_TC) return 64LL * kp_rgb * 2;
+  if (kind == SRK_PACK_RGBIN_TC) return (int64_t)cout * kp_rgb * 2;
   return (kind == SRK_PACK_FPROP_SIMT || kind == SRK_PACK_DGRAD_SIMT) ? n * 4 : n * 2;
 }
 
@@ -413,8 +416,9 @@ extern "C" int srk_weight_pack(const float* w_oihw, void* out, int cout, int cin
   SRK_REQUIRE(pixel_shuffle == 0 || (pixel_shuffle == 2 && cout % 4 == 0), "srk_weight_pack: bad pixel_shuffle");
   long long total = (long long)cout * cin * r * s;
   if (kind == SRK_PACK_FPROP_TC_N8) total = (long long)r * (s * 3 > 16 ? 32 : 16) * cin;
-  if (kind == SRK_PACK_RGBOUT_DGRAD_TC) total = 64LL * ((r * s * 3 + 1 + 63) / 64 * 64);
-  if (kind == SRK_PACK_RGBIN_TC) total = (long long)cout * ((r * s * 3 + 1 + 63) / 64 * 64);
+  const long long kp_rgb = (r * ((s * 3 + 1) / 2 * 2) + 1 + 63) / 64 * 64;
+  if (kind == SRK_PACK_RGBOUT_DGRAD_TC) total = 64LL * kp_rgb;
+  if (kind == SRK_PACK_RGBIN_TC) total = (long long)cout * kp_rgb;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, out, cout, cin, r, s, kind, pixel_shuffle);

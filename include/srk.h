@@ -48,8 +48,8 @@ extern "C" {
 #define SRK_PACK_FPROP_TC 2   /* bf16 [R*S][Cout'][Cin]  (Cout' permuted when pixel_shuffle) */
 #define SRK_PACK_DGRAD_TC 3   /* bf16 [R*S rot180][Cin][Cout'] */
 #define SRK_PACK_FPROP_TC_N8 4 /* bf16 [R][NP][Cin], row n = s*3 + co, NP = 32 / 16: RGB-output convs on tcgen05 */
-#define SRK_PACK_RGBIN_TC 5    /* bf16 [64][KP], k = (r*S+s)*3 + c, zero padded: 3 -> 64 conv forward */
-#define SRK_PACK_RGBOUT_DGRAD_TC 6 /* bf16 [64 ci][KP], k = (r'*S+s')*3 + co, taps rotated: 64 -> 3 conv dgrad */
+#define SRK_PACK_RGBIN_TC 5    /* bf16 [64][KP], k = r*SEG + s*3 + c (SEG = 3S rounded up to even), zero padded: 3 -> 64 conv forward */
+#define SRK_PACK_RGBOUT_DGRAD_TC 6 /* bf16 [64 ci][KP], k = r'*SEG + s'*3 + co, taps rotated: 64 -> 3 conv dgrad */
 
 typedef struct srk_tensor {
   void* data;
