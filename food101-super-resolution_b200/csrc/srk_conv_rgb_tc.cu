@@ -226,8 +226,8 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     constexpr int PER = (G::HALO + kBuilders - 1) / kBuilders;   // halo elements staged per thread
     float s3[3] = {0.f, 0.f, 0.f};
     const __nv_bfloat16 one = __float2bfloat16_rn(1.f);
-    float pre[PER];
-    auto fetch = [&](int i) {   // global -> registers for tile i (issued one tile ahead of its use)
+    float preA[PER], preB[PER];
+    auto fetch = [&](int i, float (&pre)[PER]) {   // global -> registers for tile i (issued TWO tiles ahead of its use)
       const int tile = blockIdx.x + i * gridDim.x;
       const int n = tile / tiles_per_img, t2 = tile - n * tiles_per_img;
       const int y0 = (t2 / p.tiles_x) * TY, x0 = (t2 % p.tiles_x) * TX;
@@ -249,8 +249,11 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     // weight): it must never be a NaN / Inf bit pattern
     for (int z = bt; z < G::HALO_BYTES / 16; z += kBuilders) reinterpret_cast<uint4*>(halo)[z] = make_uint4(0, 0, 0, 0);
     asm volatile("bar.sync 2, 256;" ::: "memory");
-    if (my_tiles > 0) fetch(0);
-    for (int i = 0; i < my_tiles; ++i) {
+    if (my_tiles > 0) fetch(0, preA);
+    if (my_tiles > 1) fetch(1, preB);
+    // one tile: stage its halo (fetched two tiles earlier: a global load takes longer than one tile's build), refill
+    // the registers for tile i + 2, build the A rows
+    auto build_tile = [&](int i, float (&pre)[PER]) -> bool {
       const int tile = blockIdx.x + i * gridDim.x;
       const int n = tile / tiles_per_img, t2 = tile - n * tiles_per_img;
       const int y0 = (t2 / p.tiles_x) * TY, x0 = (t2 % p.tiles_x) * TX;
@@ -273,8 +276,8 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       }
       // one barrier per tile: the other halo buffer is only rewritten after everybody passed this point again
       asm volatile("bar.sync 2, 256;" ::: "memory");
-      if (i + 1 < my_tiles) fetch(i + 1);
-      if (!mbar_wait(smem_u32(&bars->aempty[buf]), ((i >> 1) & 1) ^ 1, p.err, 36)) break;
+      if (i + 2 < my_tiles) fetch(i + 2, pre);
+      if (!mbar_wait(smem_u32(&bars->aempty[buf]), ((i >> 1) & 1) ^ 1, p.err, 36)) return false;
       const bool inside = (y0 + ty < p.H) && (x0 + tx < p.W);
       // segment r of this pixel = SEGW elements from element ((ty + r) * HW + tx) * 3
       const int e0 = (ty * G::HW + tx) * 3;
@@ -315,6 +318,11 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       }
       fence_proxy_async();
       mbar_arrive(smem_u32(&bars->afull[buf]));
+      return true;
+    };
+    for (int i = 0; i < my_tiles; i += 2) {
+      if (!build_tile(i, preA)) break;
+      if (i + 1 < my_tiles && !build_tile(i + 1, preB)) break;
     }
     if (p.db3) {
 #pragma unroll
