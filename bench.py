@@ -389,6 +389,91 @@ def run_srk(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------------------
+def run_eval(args):
+    """BASELINE config C4 (secondary measurement, `--config C4`): ResNet-SR inference 128 -> 512 + PSNR / SSIM / NLPD
+    per batch over synthetic Food101-shaped images, batches sharded over the ranks (srk/evaluate.py), one all-reduce
+    of the per-batch metric sums at the end.  `value`: images/s with the batches resident in HBM; `e2e`: the same
+    from pinned host memory."""
+    import srk
+    from srk import evaluate as ev
+    from src.dataset import synthetic_pair
+    from src.metrics import MetricsCalculator
+    from src.models import get_model
+    import torch.distributed as dist
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    srk.set_compute_dtype(args.dtype)
+    torch.manual_seed(0)
+    model = get_model("RESNET", 4, dev).eval()
+    B = args.batch
+    per_rank = args.eval_images            # images per GPU (full C4: 10 000 / 8 = 1 250)
+    sizes = [B] * (per_rank // B) + ([per_rank % B] if per_rank % B else [])
+    # two distinct synthetic batches are cycled (generating 1 250 x 512^2 images on the host would take minutes)
+    base = [synthetic_pair(B, 128, 128, 4, seed=4321 + rank * 2 + k) for k in range(2)]
+    host = [(base[i % 2][0][:n].contiguous().pin_memory(), base[i % 2][1][:n].contiguous().pin_memory())
+            for i, n in enumerate(sizes)]
+    resident = [(lr.to(dev), hr.to(dev)) for lr, hr in host]
+    metrics_fn = MetricsCalculator(dev).compute
+
+    def run(batches):
+        # every rank evaluates ITS list (rank = 0, world = 1 inside evaluate); the cross-rank mean is one all-reduce
+        return ev.evaluate(model, batches, dev, 0, 1, metrics_fn)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        run(resident[:2])
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    times = {}
+    res = None
+    for name, batches in (("resident", resident), ("e2e", host)):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = run(batches)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        times[name] = ms
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        buf = torch.tensor([res["psnr"], res["ssim"], float(res["batches"])], dtype=torch.float64, device=dev)
+        buf[:2] *= res["batches"]
+        dist.all_reduce(buf)
+        res = {"psnr": float(buf[0] / buf[2]), "ssim": float(buf[1] / buf[2]), "batches": int(buf[2])}
+    if rank == 0:
+        total = world * per_rank
+        pk = peaks()
+        tf = total * 72.69 / (times["resident"] * 1e-3) / 1e3     # SURVEY 8d: 72.69 GFLOP per image forward at 128 -> 512
+        line = {"metric": "sr_eval_images_per_sec", "value": round(total / (times["resident"] * 1e-3), 2),
+                "unit": "images/s", "n_gpus": world, "steps": len(sizes), "warmup": args.warmup,
+                "ms_per_step": round(times["resident"] / len(sizes), 3), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16" if args.dtype == "bf16" else "f32", "data": "synthetic",
+                "config": {"workload": "C4: ResNet-SR 16x64ch x4 inference 128->512 + PSNR/SSIM/NLPD per batch, batch %d, "
+                                       "%d images per GPU, batches sharded over ranks" % (B, per_rank),
+                           "global_images": total, "parallelism": "dp%d" % world,
+                           "l2": "activations of one batch (2 GB at 512^2) exceed the 126 MB L2",
+                           "psnr": round(res["psnr"], 4), "ssim": round(res["ssim"], 5),
+                           "step_tflops": round(tf, 2), "step_frac_of_bf16_sustained": round(tf / (world * pk["tf_sustained"]), 4)},
+                "e2e": {"value": round(total / (times["e2e"] * 1e-3), 2), "unit": "images/s",
+                        "h2d_bytes_per_step": int(B * 3 * (128 * 128 + 512 * 512) * 4), "d2h_bytes_per_step": 32},
+                "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -397,11 +482,25 @@ def main():
     ap.add_argument("--impl", default="srk", choices=["srk", "reference"])
     ap.add_argument("--dtype", default=os.environ.get("SRK_BENCH_DTYPE", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the config's)")
-    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS), help="BASELINE.json config (headline: C2)")
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS) + ["C4"],
+                    help="BASELINE.json config (headline: C2; C4 = sharded inference + metrics)")
+    ap.add_argument("--eval-images", type=int, default=1250, help="--config C4: images per GPU (10 000 / 8)")
     ap.add_argument("--cpu-batch", type=int, default=4, help="--impl reference: images per CPU step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
+    if args.config == "C4":
+        if args.batch <= 0:
+            args.batch = 64
+        if not torch.cuda.is_available():
+            sys.exit("bench.py: no CUDA device; the SR hot path has no CPU fallback")
+        _, _, world = dist_env()
+        if world == 1 and args.gpus > 1:
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+                   "--master-addr", "127.0.0.1", "--master-port", "29511"] + sys.argv
+            sys.exit(subprocess.call(cmd))
+        run_eval(args)
+        return
     select_config(args.config)
     if args.batch <= 0:
         args.batch = BATCH_PER_GPU
