@@ -46,6 +46,42 @@ def _bn_args(bn):
     return (bn.running_mean, bn.running_var, bn.num_batches_tracked), bn.eps, momentum
 
 
+def _can_fold_bn(module, bn):
+    """Inference with running statistics and no autograd graph: BN is a per-channel affine map of the conv output."""
+    return (not module.training) and (not torch.is_grad_enabled()) and bn.track_running_stats \
+        and bn.running_mean is not None
+
+
+def _folded_conv_bn(conv, bn):
+    """eval-mode BN(conv(x)) = conv'(x):  w' = w * gamma / sqrt(var + eps),  b' = (b - mean) * gamma / sqrt(var + eps)
+    + beta  (F.batch_norm with training=False, models.py:56-57,140).  The whole residual block then is two conv
+    launches with fused PReLU / skip epilogues and no elementwise pass.  The folded tensors are cached on the BN
+    module and rebuilt when any source tensor changes (in-place versions; libsrk's raw-pointer writers - Adam, the
+    running-statistics update - are covered by the weights epoch and by dropping the cache in training mode)."""
+    srcs = (conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+    key = tuple(-1 if t is None else t._version for t in srcs) + tuple(0 if t is None else t.data_ptr() for t in srcs) \
+        + (ops._weights_epoch, bn.eps)
+    ent = getattr(bn, "_srk_fold", None)
+    if ent is None or ent[0] != key:
+        with torch.no_grad():
+            scale = bn.weight / torch.sqrt(bn.running_var + bn.eps) if bn.weight is not None \
+                else torch.rsqrt(bn.running_var + bn.eps)
+            w = (conv.weight * scale.view(-1, 1, 1, 1)).contiguous()
+            b0 = conv.bias if conv.bias is not None else torch.zeros_like(bn.running_mean)
+            b = (b0 - bn.running_mean) * scale
+            if bn.bias is not None:
+                b = b + bn.bias
+            ent = (key, w, b.contiguous())
+        bn._srk_fold = ent
+    return ent[1], ent[2]
+
+
+def _drop_fold(*bns):
+    for bn in bns:
+        if getattr(bn, "_srk_fold", None) is not None:
+            bn._srk_fold = None
+
+
 class SEBlock(nn.Module):
     """Squeeze-excite channel gate (reference models.py:26-41)."""
 
@@ -83,6 +119,13 @@ class ResidualBlock(nn.Module):
     def _forward_act(self, x):
         buf1, eps1, mom1 = _bn_args(self.bn1)
         buf2, eps2, mom2 = _bn_args(self.bn2)
+        if self.training:
+            _drop_fold(self.bn1, self.bn2)       # the running statistics are about to change under the cache
+        elif not self.use_se and _can_fold_bn(self, self.bn1) and _can_fold_bn(self, self.bn2):
+            w1, b1 = _folded_conv_bn(self.conv1, self.bn1)
+            w2, b2 = _folded_conv_bn(self.conv2, self.bn2)
+            a = fn.ConvAct.apply(x, w1, b1, self.prelu.weight, None, L.ACT_PRELU, 0, False, False, x.dtype)
+            return fn.ConvAct.apply(a, w2, b2, None, x, L.ACT_NONE, 0, False, False, x.dtype)
         if not self.use_se:
             return fn.ResBlockBN.apply(
                 x, self.conv1.weight, self.conv1.bias, self.bn1.weight, self.bn1.bias, self.prelu.weight,
@@ -201,6 +244,12 @@ class ResNetSR(nn.Module):
         for blk in self.res_blocks:
             r = blk._forward_act(r)
         buf, eps, mom = _bn_args(self.bn_mid)
+        if self.training:
+            _drop_fold(self.bn_mid)
+        elif _can_fold_bn(self, self.bn_mid):
+            wm, bm = _folded_conv_bn(self.mid_conv, self.bn_mid)
+            t = fn.ConvAct.apply(r, wm, bm, None, initial, L.ACT_NONE, 0, False, False, r.dtype)
+            return _upsample_tail(self, t)
         t = fn.ConvBN.apply(r, self.mid_conv.weight, self.mid_conv.bias, self.bn_mid.weight, self.bn_mid.bias,
                             None, initial, *buf, self.training, eps, mom)
         return _upsample_tail(self, t)

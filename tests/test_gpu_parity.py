@@ -673,3 +673,25 @@ def test_dgrad_with_fused_bn_backward_reduction(with_prelu):
         assert abs(dalpha_f.item() - dalpha_u.item()) <= 1e-3 * scale
     assert rel_err(dy_f.float().cpu(), dy_u.float().cpu()) <= 1e-2
     assert float(dy_f[:, 0].abs().max()) == 0 and float(dy_f[:, :, -1].abs().max()) == 0
+
+
+@pytest.mark.parametrize("dtype,tol", [("fp32", 2e-5), ("bf16", 3e-2)])   # bf16: two different roundings of the same
+def test_eval_bn_folding_matches_unfolded_path(dtype, tol):                # network, each <= 2e-2 from the fp32 oracle
+    """Inference folds the running-statistics BatchNorm into the conv weights (two launches per residual block);
+    with autograd enabled the same modules take the unfolded conv -> BN -> PReLU path.  Both must agree, also after
+    the statistics moved in a training step (the fold cache must not go stale)."""
+    import srk
+    from src import models as M
+    srk.set_compute_dtype(dtype)
+    torch.manual_seed(9)
+    model = M.ResNetSR(num_channels=64, num_residuals=2).to(DEV)
+    lr, _ = O.synthetic_pair(2, 20, 24, 4, seed=3)
+    lr = lr.to(DEV)
+    for round_ in range(2):
+        model.train()
+        model(lr).mean().backward()          # moves the running statistics through libsrk's raw-pointer update
+        model.eval()
+        with torch.no_grad():
+            folded = model(lr)
+        unfolded = model(lr).detach()        # grad mode on: conv -> BN(eval) -> PReLU kernels
+        assert rel_err(folded.cpu(), unfolded.cpu()) <= tol, (round_, rel_err(folded.cpu(), unfolded.cpu()))
