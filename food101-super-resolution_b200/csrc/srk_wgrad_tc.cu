@@ -12,8 +12,17 @@
 // (split-K over persistent CTAs); each CTA stores its partial [9][64 ci][64 co] block once and a small
 // kernel adds the partials into the OIHW fp32 gradient.  The bias gradient
 // (column sums of dZ) is accumulated from the staged dZ tiles by the otherwise idle epilogue warps.
+//
+// Folded variant (default, WgradTcParams::fold): the three HORIZONTAL taps go into the MMA N dimension.  With
+// p' = p + (s-1):  dW[(r,s)][ci][co] = sum_p' X[p' + (r-1)(W+2)][ci] * dZ[p' - (s-1)][co], so for one pixel block the
+// B operand is dZ at three pixel shifts - three 64-wide N blocks of the same [130 pixels][64 co] slab, one pixel
+// (128 B) apart through the descriptor's leading-byte-offset - and the A operand is X at the vertical taps only:
+// two MMAs of M128 x N192 per 16-pixel K step (rows r = 0,1 | r = 2 and a discarded half) instead of five of
+// M128 x N64: 18 KB of operand reads and 192 tensor cycles per K step instead of 30 KB and 240 port cycles.
 #include "srk_common.cuh"
 #include "srk_tc_common.cuh"
+
+#include <cstdlib>
 
 namespace srk {
 
@@ -27,7 +36,12 @@ constexpr int DZ_TILE_BYTES = TM * NT * 2;
 constexpr int kThreads = 192;
 constexpr int MAX_STAGES = 6;
 
+constexpr int DZ_FOLD_ROWS = TM + 2;                        // dZ slab of the folded variant: pixels m0-1 .. m0+128
+constexpr int DZ_FOLD_BYTES = (DZ_FOLD_ROWS * NT * 2 + 1023) / 1024 * 1024;
+constexpr int FOLD_N = 3 * NT;                              // 192 accumulator columns per MMA
+
 struct WgradTcParams {
+  int fold;                // 1: horizontal taps folded into N (see the header comment)
   int P, Wp, num_tiles;
   int x_col0, dz_col0;     // channel offsets of this (ci chunk, co chunk) pass
   int slab_rows, stages, stage_bytes;
@@ -83,11 +97,11 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       if (elect_one()) {
         const uint32_t fb = smem_u32(&bars->full[s]);
         const uint32_t st0 = smem_base + s * p.stage_bytes;
-        mbar_arrive_expect_tx(fb, slab_bytes + DZ_TILE_BYTES);
-        const int row0 = m0 - p.Wp - 1;
+        mbar_arrive_expect_tx(fb, slab_bytes + (p.fold ? DZ_FOLD_ROWS * NT * 2 : DZ_TILE_BYTES));
+        const int row0 = p.fold ? m0 - p.Wp : m0 - p.Wp - 1;   // folded: vertical shifts only on the X side
         for (int j = 0; j < p.slab_rows / SLAB_BOX_ROWS; ++j)
           tma_load_2d(st0 + j * SLAB_BOX_ROWS * KC * 2, &tmX, fb, p.x_col0, row0 + j * SLAB_BOX_ROWS);
-        tma_load_2d(st0 + slab_bytes, &tmDz, fb, p.dz_col0, m0);
+        tma_load_2d(st0 + slab_bytes, &tmDz, fb, p.dz_col0, p.fold ? m0 - 1 : m0);
       }
       __syncwarp();
       if (++s == S) { s = 0; ph ^= 1; }
@@ -112,12 +126,26 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       const uint32_t slab_lo = lo_base + ((smem_base + s * p.stage_bytes) >> 4);
       const uint32_t dz_lo = slab_lo + (slab_bytes >> 4);
       if (elect_one()) {
+        if (p.fold) {
+          constexpr uint32_t idesc_f = make_idesc_bf16(128, FOLD_N, 1, 1);
+          // A: rows (r = 0 | r = 1) and (r = 1 again, discarded | r = 2) - every read stays inside the slab;
+          // B: dZ slab rows j .. (N block j <-> s = 2 - j)
+          const uint32_t af[2] = {0u + (wp_u << 16), wp_u + (wp_u << 16)};
+          const uint32_t bf = dz_lo + (px_u << 16);
 #pragma unroll
-        for (int a = 0; a < NACC; ++a) {
+          for (int a = 0; a < 2; ++a)
 #pragma unroll
-          for (int ks = 0; ks < TM / 16; ++ks)
-            umma_bf16(tmem_base + a * NT, hi | (slab_lo + a_off[a] + ks * (16 * KC * 2 / 16)),
-                      hi | (dz_lo + ks * (16 * NT * 2 / 16)), idesc, (i | ks) != 0);
+            for (int ks = 0; ks < TM / 16; ++ks)
+              umma_bf16(tmem_base + a * FOLD_N, hi | (slab_lo + af[a] + ks * (16 * KC * 2 / 16)),
+                        hi | (bf + ks * (16 * NT * 2 / 16)), idesc_f, (i | ks) != 0);
+        } else {
+#pragma unroll
+          for (int a = 0; a < NACC; ++a) {
+#pragma unroll
+            for (int ks = 0; ks < TM / 16; ++ks)
+              umma_bf16(tmem_base + a * NT, hi | (slab_lo + a_off[a] + ks * (16 * KC * 2 / 16)),
+                        hi | (dz_lo + ks * (16 * NT * 2 / 16)), idesc, (i | ks) != 0);
+          }
         }
         umma_commit(smem_u32(&bars->empty[s]));
       }
@@ -139,9 +167,10 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       for (int i = 0; i < my_tiles; ++i) {
         if (!mbar_wait(smem_u32(&bars->full[s]), ph, p.err, 13)) break;
         const uint8_t* dz = smem_al + s * p.stage_bytes + slab_bytes;
+        const int roff = p.fold ? 1 : 0;      // the folded dZ slab starts one pixel before the tile
 #pragma unroll
         for (int rr = 0; rr < TM / 16; ++rr) {
-          const int r = r0 + rr * 16;
+          const int r = r0 + rr * 16 + roff;
           const uint4 q = *reinterpret_cast<const uint4*>(dz + r * 128 + ((c8 ^ (r & 7)) << 4));
           const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
 #pragma unroll
@@ -171,10 +200,13 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       // consecutive rows of this CTA's partial block.
       constexpr int ROW_PITCH = NT * 4 + 16;   // 272 B: consecutive rows start in different 16-byte bank groups
       uint8_t* tbuf = smem_al + lg * 32 * ROW_PITCH;
+      // blocks of 64 accumulator columns: per-tap  a = 0..4 (taps 2a, 2a+1 in the two 64-row halves);
+      // folded  b = 0..5: accumulator b / 3 (rows r = 0,1 | r = (1),2), N block j = b % 3 <-> horizontal tap s = 2 - j
+      const int nblocks = p.fold ? 6 : NACC;
 #pragma unroll 1
-      for (int a = 0; a < NACC; ++a) {
+      for (int a = 0; a < nblocks; ++a) {
         uint32_t v[NT];
-        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + a * NT;
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + a * NT;   // folded: (a / 3) * 192 + (a % 3) * 64
         tmem_ld_32x32(taddr, v);
         tmem_ld_32x32(taddr + 32, v + 32);
         tmem_ld_wait();
@@ -183,10 +215,18 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         for (int j = 0; j < NT / 4; ++j)
           *reinterpret_cast<uint4*>(tbuf + lane * ROW_PITCH + j * 16) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         __syncwarp();
-        if (a == NACC - 1 && lg >= 2) continue;   // the fifth accumulator holds tap 8 only (rows 0..63)
+        int tap0;            // tap of this warp's 64-row half; rows (lg & 1) * 32 .. of that tap's [ci][co] block
+        if (p.fold) {
+          const int acc = a / 3, sx = 2 - a % 3, r = acc == 0 ? (lg >> 1) : 2;
+          if (acc == 1 && lg < 2) continue;       // first half of the second accumulator is a discarded copy of r = 1
+          tap0 = r * 3 + sx;
+        } else {
+          if (a == NACC - 1 && lg >= 2) continue;   // the fifth accumulator holds tap 8 only (rows 0..63)
+          tap0 = 2 * a + (lg >> 1);
+        }
         // this CTA's partial sum, stored plainly (148 CTAs hammering the same 147 KB with atomics cost ~20 us);
         // wgrad_fold_kernel adds the partials up
-        float* dst = p.ws + ((size_t)blockIdx.x * TAPS + 2 * a) * KC * NT + (size_t)(lg * 32) * NT;
+        float* dst = p.ws + ((size_t)blockIdx.x * TAPS + tap0) * KC * NT + (size_t)((lg & 1) * 32) * NT;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int r = 2 * j + (lane >> 4), c = lane & 15;
@@ -256,7 +296,7 @@ bool conv_wgrad_tc_shape_ok(const srk_tensor* x, const srk_tensor* dy, int r, in
   if (x->c % 32 != 0 || dy->c % 32 != 0 || x->c < 64 || dy->c < 64) return false;
   const int Wp = x->w + 2;
   const int slab_rows = ((TM + 2 * Wp + 2) + SLAB_BOX_ROWS - 1) / SLAB_BOX_ROWS * SLAB_BOX_ROWS;
-  return 2 * (slab_rows * KC * 2 + DZ_TILE_BYTES) + 4096 <= 227 * 1024;
+  return 2 * (slab_rows * KC * 2 + DZ_FOLD_BYTES) + 8192 <= 227 * 1024;
 }
 
 int64_t conv_wgrad_tc_workspace(const srk_tensor* x, const srk_tensor* dy, int, int) {
@@ -276,11 +316,14 @@ int conv_wgrad_tc_launch(const srk_tensor* x, const srk_tensor* dy, float* dw, f
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaFuncSetAttribute(wgrad3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
   }
+  static int fold = -1;
+  if (fold < 0) { const char* e = getenv("SRK_WGRAD_FOLD"); fold = e ? atoi(e) != 0 : 1; }
   WgradTcParams p;
+  p.fold = fold;
   p.P = (int)P; p.Wp = Wp;
   p.num_tiles = (int)((P + TM - 1) / TM);
-  p.slab_rows = ((TM + 2 * Wp + 2) + SLAB_BOX_ROWS - 1) / SLAB_BOX_ROWS * SLAB_BOX_ROWS;
-  p.stage_bytes = p.slab_rows * KC * 2 + DZ_TILE_BYTES;
+  p.slab_rows = ((TM + 2 * Wp + (fold ? 0 : 2)) + SLAB_BOX_ROWS - 1) / SLAB_BOX_ROWS * SLAB_BOX_ROWS;
+  p.stage_bytes = p.slab_rows * KC * 2 + (fold ? DZ_FOLD_BYTES : DZ_TILE_BYTES);
   const int fixed = 1024 + (int)sizeof(WgradBarriers);
   p.stages = (smem_max - fixed) / p.stage_bytes;
   // Three stages hide the TMA latency (a stage is ~2000 cycles of MMA work) and leave ~60 KB of the SM's shared
@@ -292,7 +335,8 @@ int conv_wgrad_tc_launch(const srk_tensor* x, const srk_tensor* dy, float* dw, f
   const int smem_bytes = fixed + p.stages * p.stage_bytes;
   CUtensorMap tmX, tmDz;
   if (make_tmap_2d_bf16(&tmX, x->data, (uint64_t)P, (uint64_t)x->c, (uint64_t)x->c, SLAB_BOX_ROWS, KC, 128)) return 1;
-  if (make_tmap_2d_bf16(&tmDz, dy->data, (uint64_t)P, (uint64_t)dy->c, (uint64_t)dy->c, TM, NT, 128)) return 1;
+  if (make_tmap_2d_bf16(&tmDz, dy->data, (uint64_t)P, (uint64_t)dy->c, (uint64_t)dy->c, fold ? DZ_FOLD_ROWS : TM, NT, 128))
+    return 1;
   const int kchunks = (x->c + KC - 1) / KC, nchunks = (dy->c + NT - 1) / NT;
   const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
   for (int nc = 0; nc < nchunks; ++nc)
