@@ -1,6 +1,7 @@
 // C-ABI front door of libsrk: error channel, conv dispatch (CUDA-core fp32 path vs tcgen05 path),
 // version / capability queries.  Declarations: include/srk.h.
 #include "srk_common.cuh"
+#include "srk_tc_common.cuh"
 
 #include <cstring>
 
@@ -28,16 +29,6 @@ int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w
                          const srk_tensor* residual, int shuffle, float* stats_sum, float* stats_sumsq,
                          void* workspace, cudaStream_t st);
 int64_t conv_fprop_tc_workspace(const srk_tensor* x);
-// srk_conv_fold_tc.cu
-struct BnRedArgs {
-  const srk_tensor* z;
-  const float *mean, *invstd, *gamma, *beta, *alpha;
-  float *sum_g, *sum_gz, *dalpha;
-};
-int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout,
-                           const float* bias, int act, const float* alpha, const srk_tensor* residual, int shuffle,
-                           float* stats_sum, float* stats_sumsq, void* workspace, int variant, cudaStream_t st,
-                           const BnRedArgs* br);
 bool conv_smalln_tc_ok(const srk_tensor* x, const srk_tensor* y, int cout, int r, int s);
 int conv_smalln_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout, int r,
                           const float* bias, cudaStream_t st);

@@ -643,13 +643,6 @@ static cudaError_t launch_pass(bool fast, bool stats, int act, int grid, int sme
 
 }  // namespace fold
 
-// BatchNorm-backward reduction fused into a 64 -> 64 dgrad (see Params::bn_red)
-struct BnRedArgs {
-  const srk_tensor* z;
-  const float *mean, *invstd, *gamma, *beta, *alpha;   // alpha: PReLU slope between the BN and this conv, or null
-  float *sum_g, *sum_gz, *dalpha;
-};
-
 // Returns 0 ok, 1 error, -1 "not applicable" (image too wide for two slab stages: the caller uses the
 // per-tap kernel of srk_conv_tc.cu).
 int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout,

@@ -506,11 +506,6 @@ int tc_read_err_flag() {
   return v;
 }
 
-// srk_conv_fold_tc.cu: 3x3 kernel with the horizontal taps folded into N (the default for 3x3)
-int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout,
-                           const float* bias, int act, const float* alpha, const srk_tensor* residual, int shuffle,
-                           float* stats_sum, float* stats_sumsq, void* workspace, int variant, cudaStream_t st,
-                           const struct BnRedArgs* br);
 // 3x3 kernel choice: 0 = per-tap kernel of this file (8 epilogue warps), 1 = folded taps, 2 = per-tap on the 16-warp
 // pipeline of srk_conv_fold_tc.cu, 3 = as 2 on CTA pairs (cta_group::2, M = 256)
 static int g_tc_fold = -1;

@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/srk.h"
+
 namespace srk {
 namespace tc {
 
@@ -220,6 +222,20 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 }  // namespace tc
+
+// ---- host: launcher of the 3x3 trunk kernels (srk_conv_fold_tc.cu) ----------------------------------------------
+// BatchNorm-backward reduction fused into a 64 -> 64 dgrad (fold::Params::bn_red): z = saved input of the BN layer the
+// gradient flows into, alpha = slope of the PReLU between that BN and this conv (or null).
+struct BnRedArgs {
+  const srk_tensor* z;
+  const float *mean, *invstd, *gamma, *beta, *alpha;
+  float *sum_g, *sum_gz, *dalpha;
+};
+// variant: 0 per-tap, 1 folded taps, 2 per-tap on CTA pairs, 3 CTA pairs with 128-channel PixelShuffle passes.
+// Returns 0 ok, 1 error, -1 "slab does not fit" (the caller falls back to the per-tap kernel of srk_conv_tc.cu).
+int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout, const float* bias,
+                           int act, const float* alpha, const srk_tensor* residual, int shuffle, float* stats_sum,
+                           float* stats_sumsq, void* workspace, int variant, cudaStream_t st, const BnRedArgs* br);
 
 // ---- host: TMA descriptor encoding through the driver entry point (no link-time libcuda dependency) ----
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
