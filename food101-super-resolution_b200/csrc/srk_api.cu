@@ -35,12 +35,12 @@ int conv_smalln_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* 
 bool conv_wgrad_tc_shape_ok(const srk_tensor* x, const srk_tensor* dy, int r, int s);
 int64_t conv_wgrad_tc_workspace(const srk_tensor* x, const srk_tensor* dy, int r, int s);
 int conv_wgrad_tc_launch(const srk_tensor* x, const srk_tensor* dy, float* dw, float* db, int r, int s,
-                         void* workspace, int accumulate, cudaStream_t st);
+                         void* workspace, int accumulate, int perm_shuffle, cudaStream_t st);
 
 int64_t conv_rgb_workspace_bytes(int k);
 int conv_rgb_tc_run(const srk_tensor* t3, const srk_tensor* y, const void* w_packed, const float* bias, int act,
                     const float* alpha, const srk_tensor* t64, float* dw, float* db, float* db3, int rgb_out, int k,
-                    void* workspace, cudaStream_t st);
+                    void* workspace, cudaStream_t st, const srk_tensor* dz_ps, const float* ps_alpha, float* ps_dalpha);
 
 static bool tensor_ok(const srk_tensor* t) {
   if (t == nullptr || t->data == nullptr) return false;
@@ -159,7 +159,7 @@ extern "C" int64_t srk_conv_wgrad_workspace_bytes(const srk_tensor* x, const srk
 }
 
 extern "C" int srk_conv_wgrad(const srk_tensor* x, const srk_tensor* dy, float* dw, float* db, int r, int s,
-                              int impl, int accumulate, void* workspace, void* stream) {
+                              int impl, int accumulate, int perm_shuffle, void* workspace, void* stream) {
   SRK_REQUIRE(tensor_ok(x) && tensor_ok(dy), "srk_conv_wgrad: bad x / dy tensor");
   SRK_REQUIRE(dw != nullptr, "srk_conv_wgrad: null dw");
   SRK_REQUIRE(r == s && (r & 1) == 1 && r >= 1 && r <= 11, "srk_conv_wgrad: odd square kernels only");
@@ -169,8 +169,9 @@ extern "C" int srk_conv_wgrad(const srk_tensor* x, const srk_tensor* dy, float* 
   if (impl == SRK_IMPL_TC) {
     SRK_REQUIRE(conv_wgrad_tc_shape_ok(x, dy, r, s), "srk_conv_wgrad: shape not supported by the tcgen05 path");
     SRK_REQUIRE(workspace != nullptr || conv_wgrad_tc_workspace(x, dy, r, s) == 0, "srk_conv_wgrad: workspace required");
-    return conv_wgrad_tc_launch(x, dy, dw, db, r, s, workspace, accumulate, st);
+    return conv_wgrad_tc_launch(x, dy, dw, db, r, s, workspace, accumulate, perm_shuffle, st);
   }
+  SRK_REQUIRE(!perm_shuffle, "srk_conv_wgrad: sub-pixel-major dY is a tcgen05-path layout");
   if (!accumulate) {  // the CUDA-core kernel adds with atomics
     cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)dy->c * x->c * r * s, st);
     if (db) cudaMemsetAsync(db, 0, sizeof(float) * (size_t)dy->c, st);
@@ -185,7 +186,7 @@ extern "C" int srk_conv_rgb_fprop(const srk_tensor* img3, const srk_tensor* y, c
   SRK_REQUIRE(tensor_ok(img3) && tensor_ok(y) && w_packed != nullptr, "srk_conv_rgb_fprop: bad arguments");
   SRK_REQUIRE(act != SRK_ACT_PRELU || alpha != nullptr, "srk_conv_rgb_fprop: PReLU needs alpha");
   return conv_rgb_tc_run(img3, y, w_packed, bias, act, alpha, nullptr, nullptr, nullptr, nullptr, 0, k, nullptr,
-                         (cudaStream_t)stream);
+                         (cudaStream_t)stream, nullptr, nullptr, nullptr);
 }
 
 extern "C" int srk_conv_rgb_bwd(const srk_tensor* img3, const srk_tensor* t64, const void* w_packed,
@@ -195,5 +196,20 @@ extern "C" int srk_conv_rgb_bwd(const srk_tensor* img3, const srk_tensor* t64, c
   SRK_REQUIRE(dx == nullptr || (tensor_ok(dx) && w_packed != nullptr && rgb_out == 1),
               "srk_conv_rgb_bwd: dx needs rgb_out = 1 and SRK_PACK_RGBOUT_DGRAD_TC weights");
   return conv_rgb_tc_run(img3, dx, w_packed, nullptr, SRK_ACT_NONE, nullptr, t64, dw, rgb_out ? nullptr : db,
-                         rgb_out ? db : nullptr, rgb_out, k, workspace, (cudaStream_t)stream);
+                         rgb_out ? db : nullptr, rgb_out, k, workspace, (cudaStream_t)stream, nullptr, nullptr, nullptr);
+}
+
+// Backward of the 64 -> 3 output conv fused with the PReLU + PixelShuffle(2) backward of the upsample stage below it
+// (models.py:120-125): dY = gradient of the RGB image, t64 = the upsample stage's output (= the conv input), w_packed =
+// SRK_PACK_RGBOUT_DGRAD_TC weights.  Produces dw [3][64][K][K], db [3] (accumulated), dalpha (accumulated) and
+// dz_ps = gradient of the 64 -> 256 conv output, bf16 ACT [N, 256, H/2, W/2] with channels SUB-PIXEL-MAJOR
+// (sub * 64 + c instead of 4c + sub): feed it to srk_conv_fprop with SRK_PACK_DGRAD_TC weights packed with
+// pixel_shuffle = 2 and to srk_conv_wgrad with perm_shuffle = 1.
+extern "C" int srk_conv_rgbout_bwd_unshuffle(const srk_tensor* dy_img, const srk_tensor* t64, const void* w_packed,
+                                             const srk_tensor* dz_ps, float* dw, float* db, const float* alpha,
+                                             float* dalpha, int k, void* workspace, void* stream) {
+  SRK_REQUIRE(tensor_ok(dy_img) && tensor_ok(t64) && tensor_ok(dz_ps) && dw && workspace && w_packed && alpha,
+              "srk_conv_rgbout_bwd_unshuffle: bad arguments");
+  return conv_rgb_tc_run(dy_img, nullptr, w_packed, nullptr, SRK_ACT_NONE, nullptr, t64, dw, nullptr, db, 1, k, workspace,
+                         (cudaStream_t)stream, dz_ps, alpha, dalpha);
 }

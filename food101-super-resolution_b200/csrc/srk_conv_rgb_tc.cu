@@ -48,6 +48,12 @@ struct Params {
   __nv_bfloat16* y;      // ACT [N][H+2][W+2][64]
   float* ws;             // [KP][64] fp32 (g), zero-filled by the caller
   float* db3;            // [3]: sum over pixels of T3 (accumulated) or null
+  // rgb_out backward fused with the PReLU + PixelShuffle(2) backward of the layer below (models.py:120-122): T64 is that
+  // layer's output, the dgrad result is masked by its sign and stored through tmY as dz of the 64 -> 256 conv,
+  // channels sub-pixel-major (row (y/2, x/2), channel sub * 64 + c), the PReLU-slope gradient goes to ps_dalpha
+  int unshuffle;
+  const float* ps_alpha;
+  float* ps_dalpha;
   int* err;
   int dbg;               // bring-up knobs: 1 builders skip the A rows, 2 no MMAs, 4 no T64 loads, 8 no y stores, 16 no halo
 };
@@ -69,6 +75,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint
 __device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                ::"l"(tmap), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
+__device__ __forceinline__ void tma_store_5d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(tmap), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                : "memory");
 }
 
@@ -116,7 +128,7 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       mbar_init(smem_u32(&bars->afull[i]), kBuilders);
       mbar_init(smem_u32(&bars->aempty[i]), 1);
       mbar_init(smem_u32(&bars->tfull[i]), 1);
-      mbar_init(smem_u32(&bars->tempty[i]), 1);
+      mbar_init(smem_u32(&bars->tempty[i]), p.unshuffle ? 257 : 1);   // + the epilogue threads that read the T64 tile
       mbar_init(smem_u32(&bars->yfull[i]), 1);
       mbar_init(smem_u32(&bars->yempty[i]), 256);
     }
@@ -344,7 +356,9 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     const int ei = lg * 32 + lane, ty = ei >> 3, tx = ei & 7;
     if (p.do_y) {
       const float alpha = (p.act == SRK_ACT_PRELU) ? p.alpha[0] : 0.f;
-      const int Hp = p.H + 2, Wp = p.W + 2;
+      const float ps_alpha = p.unshuffle ? __ldg(p.ps_alpha) : 0.f;
+      const float ps_inv_alpha = (p.unshuffle && ps_alpha != 0.f) ? 1.f / ps_alpha : 0.f;
+      float ps_da = 0.f;
       float bias[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) bias[j] = (p.bias && c0 + j < p.n_valid) ? __ldg(p.bias + p.y_col0 + c0 + j) : 0.f;
@@ -360,6 +374,8 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         const int tile = blockIdx.x + i * gridDim.x;
         const int n = tile / tiles_per_img, t2 = tile - n * tiles_per_img;
         const int y0 = (t2 / p.tiles_x) * TY, x0 = (t2 % p.tiles_x) * TX;
+        if (p.unshuffle && !mbar_wait(smem_u32(&bars->tfull[buf]), (i >> 1) & 1, p.err, 39)) break;
+        const uint8_t* trow = smem_al + 2 * G::A_BYTES + G::W_BYTES + buf * G::T_BYTES + ei * 128;
         uint4 o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -371,25 +387,44 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
             else if (p.act == SRK_ACT_PRELU) a = a > 0.f ? a : alpha * a;
             f[e] = a;
           }
+          if (p.unshuffle) {   // PReLU backward of the layer below: mask by the sign of its OUTPUT (the T64 tile)
+            const uint4 tq = *reinterpret_cast<const uint4*>(trow + (((ch * 4 + j) ^ (ei & 7)) << 4));
+            const __nv_bfloat162* th = reinterpret_cast<const __nv_bfloat162*>(&tq);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 tv = __bfloat1622float2(th[e]);
+              if (!(tv.x > 0.f)) { ps_da = fmaf(f[2 * e], tv.x * ps_inv_alpha, ps_da); f[2 * e] *= ps_alpha; }
+              if (!(tv.y > 0.f)) { ps_da = fmaf(f[2 * e + 1], tv.y * ps_inv_alpha, ps_da); f[2 * e + 1] *= ps_alpha; }
+            }
+          }
           __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
           __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
           o[j] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
                             *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
         }
-        // The [16 x 8 pixels][64 ch] tile goes out as ONE 4-D TMA store from a swizzled staging tile (row = pixel):
+        if (p.unshuffle) mbar_arrive(smem_u32(&bars->tempty[buf]));   // the T64 tile has been read
+        // The [16 x 8 pixels][64 ch] tile goes out as ONE TMA store from a swizzled staging tile (row = pixel):
         // per-thread 16-byte stores at a 128-byte lane stride cost ~1000 L1 wavefronts per tile (measured 176 us of
         // the 612 us output-conv backward).  Pixels / channels outside the tensor are clipped by the TMA unit.
+        // unshuffle: staging row = (coarse pixel (ty/2, tx/2), sub-pixel (ty%2)*2 + tx%2) - the 5-D box
+        // [8 y2][4 x2][4 sub][64 ch] of the sub-pixel-major dz tensor
+        const int srow = p.unshuffle ? (((ty >> 1) * (TX / 2) + (tx >> 1)) * 4 + (ty & 1) * 2 + (tx & 1)) : ei;
         if (threadIdx.x == 320) tma_store_wait_read0();      // the previous tile has left the staging buffer
         asm volatile("bar.sync 3, 256;" ::: "memory");
-        uint8_t* orow = ystage + ei * 128;
+        uint8_t* orow = ystage + srow * 128;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(orow + (((ch * 4 + j) ^ (ei & 7)) << 4)) = o[j];
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(orow + (((ch * 4 + j) ^ (srow & 7)) << 4)) = o[j];
         fence_proxy_async();
         asm volatile("bar.sync 3, 256;" ::: "memory");
         if (threadIdx.x == 320 && !(p.dbg & 8)) {
-          tma_store_4d(&tmY, y_sm, p.y_col0, x0, y0, n);
+          if (p.unshuffle) tma_store_5d(&tmY, y_sm, 0, 0, x0 / 2, y0 / 2, n);
+          else tma_store_4d(&tmY, y_sm, p.y_col0, x0, y0, n);
           tma_store_commit();
         }
+      }
+      if (p.unshuffle && p.ps_dalpha) {
+        const float t = warp_sum(ps_da);
+        if (lane == 0) atomicAdd(p.ps_dalpha, t);
       }
       if (threadIdx.x == 320) tma_store_wait_all();
     }
@@ -453,6 +488,24 @@ static int make_tmap_act_4d_tile(CUtensorMap* out, const srk_tensor* x) {
   return 0;
 }
 
+// dz of the 64 -> 256 PixelShuffle conv below the output conv: bf16 ACT [N][256][H/2][W/2] with channels sub-pixel-major
+// (sub * 64 + c), viewed as (c = 64, sub = 4, x2, y2, n); a 16 x 8 tile of fine pixels is the box [8 y2][4 x2][4 sub][64 c]
+static int make_tmap_unshuffle_5d(CUtensorMap* out, const srk_tensor* dz) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  SRK_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  const uint64_t C = dz->c, Wp = dz->w + 2, Hp = dz->h + 2;
+  cuuint64_t dims[5] = {64, 4, (cuuint64_t)dz->w, (cuuint64_t)dz->h, (cuuint64_t)dz->n};
+  cuuint64_t strides[4] = {64 * 2, C * 2, Wp * C * 2, Hp * Wp * C * 2};
+  cuuint32_t box[5] = {64, 4, TX / 2, TY / 2, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  void* base = (char*)dz->data + (Wp + 1) * C * 2;
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SRK_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(5d unshuffle) failed (%d)", (int)r);
+  return 0;
+}
+
 template <int K>
 static int launch(const CUtensorMap& tmW, const CUtensorMap& tmT, const CUtensorMap& tmY, const Params& p,
                   cudaStream_t st) {
@@ -473,9 +526,12 @@ int64_t conv_rgb_workspace_bytes(int k) { return (int64_t)(k == 9 ? rgb::Geo<9>:
 
 // t3: IMAGE [N,3,H,W]; y (optional): ACT bf16 [N,64,H,W] = act(conv + bias) with Wk = w_packed (bf16 [64][KP]);
 // t64 (optional): ACT bf16 [N,64,H,W] -> dw (OIHW fp32, accumulated), db / db3 (accumulated).
+// dz_ps (optional, rgb_out only): instead of y = dgrad(dY) the kernel stores the gradient of the 64 -> 256 PixelShuffle +
+// PReLU layer below (see Params::unshuffle); ps_alpha / ps_dalpha: that PReLU's slope and its gradient (accumulated).
 int conv_rgb_tc_run(const srk_tensor* t3, const srk_tensor* y, const void* w_packed, const float* bias, int act,
                     const float* alpha, const srk_tensor* t64, float* dw, float* db, float* db3, int rgb_out, int k,
-                    void* workspace, cudaStream_t st) {
+                    void* workspace, cudaStream_t st, const srk_tensor* dz_ps, const float* ps_alpha,
+                    float* ps_dalpha) {
   SRK_REQUIRE(k == 9 || k == 5, "conv_rgb: kernel size must be 9 or 5");
   SRK_REQUIRE(t3 && t3->layout == SRK_LAYOUT_IMAGE && t3->c == 3, "conv_rgb: needs a 3-channel IMAGE tensor");
   rgb::Params p;
@@ -484,7 +540,15 @@ int conv_rgb_tc_run(const srk_tensor* t3, const srk_tensor* y, const void* w_pac
   const long long nt = (long long)p.N * p.tiles_x * p.tiles_y;
   SRK_REQUIRE(nt < (1LL << 31), "conv_rgb: too many tiles");
   p.num_tiles = (int)nt;
-  p.do_y = y != nullptr; p.do_g = t64 != nullptr; p.act = act;
+  p.do_y = y != nullptr || dz_ps != nullptr; p.do_g = t64 != nullptr; p.act = act;
+  p.unshuffle = dz_ps != nullptr; p.ps_alpha = ps_alpha; p.ps_dalpha = ps_dalpha;
+  if (dz_ps) {
+    SRK_REQUIRE(rgb_out && y == nullptr && t64 != nullptr && t64->c == 64 && ps_alpha != nullptr && w_packed != nullptr,
+                "conv_rgb: the fused unshuffle needs the 64 -> 3 backward with its 64-channel input");
+    SRK_REQUIRE(dz_ps->layout == SRK_LAYOUT_ACT && dz_ps->dtype == SRK_BF16 && dz_ps->c == 256 && dz_ps->n == t3->n &&
+                    2 * dz_ps->h == t3->h && 2 * dz_ps->w == t3->w,
+                "conv_rgb: dz must be a bf16 ACT tensor [N, 256, H/2, W/2]");
+  }
   p.t3 = (const float*)t3->data; p.bias = bias; p.alpha = alpha;
   p.y = y ? (__nv_bfloat16*)y->data : nullptr;
   p.ws = (float*)workspace; p.db3 = db3; p.err = tc_err_flag();
@@ -493,8 +557,11 @@ int conv_rgb_tc_run(const srk_tensor* t3, const srk_tensor* y, const void* w_pac
   CUtensorMap tmW, tmT, tmY;
   memset(&tmW, 0, sizeof(tmW)); memset(&tmT, 0, sizeof(tmT)); memset(&tmY, 0, sizeof(tmY));
   // the 64-channel side may have 64 or 96 channels: one pass per 64-channel chunk (tails are zero-filled by TMA)
-  const int c64 = p.do_y ? y->c : t64->c;
-  if (p.do_y) {
+  const int c64 = y ? y->c : t64->c;
+  if (dz_ps) {
+    if (make_tmap_2d_bf16(&tmW, w_packed, 64, (uint64_t)KP, (uint64_t)KP, 64, 64, 128)) return 1;
+    if (rgb::make_tmap_unshuffle_5d(&tmY, dz_ps)) return 1;
+  } else if (p.do_y) {
     SRK_REQUIRE(y->layout == SRK_LAYOUT_ACT && y->dtype == SRK_BF16 && y->c % 32 == 0 && y->c >= 64 && y->n == p.N &&
                     y->h == p.H && y->w == p.W,
                 "conv_rgb: y must be a bf16 ACT tensor with 64 or 96 channels");
@@ -506,12 +573,12 @@ int conv_rgb_tc_run(const srk_tensor* t3, const srk_tensor* y, const void* w_pac
                     t64->n == p.N && t64->h == p.H && t64->w == p.W,
                 "conv_rgb: t64 must be a bf16 ACT tensor with 64 or 96 channels");
     SRK_REQUIRE(workspace != nullptr && dw != nullptr, "conv_rgb: workspace / dw required");
-    SRK_REQUIRE(!(p.do_y && t64->c != y->c), "conv_rgb: y and t64 channel counts differ");
+    SRK_REQUIRE(!(y && t64->c != y->c), "conv_rgb: y and t64 channel counts differ");
     if (rgb::make_tmap_act_4d_tile(&tmT, t64)) return 1;
   }
   SRK_REQUIRE(!rgb_out || c64 == 64, "conv_rgb: the 64 -> 3 backward takes a 64-channel input");
   for (int n0 = 0; n0 < c64; n0 += 64) {
-    p.y_stride = p.do_y ? y->c : 64;
+    p.y_stride = y ? y->c : 64;
     p.y_col0 = n0;
     p.n_valid = c64 - n0 < 64 ? c64 - n0 : 64;
     p.w_row0 = rgb_out ? 0 : n0;
@@ -526,7 +593,8 @@ int conv_rgb_tc_run(const srk_tensor* t3, const srk_tensor* y, const void* w_pac
       SRK_CUDA_LAUNCH_CHECK("conv_rgb_fold");
     }
   }
-  if (p.do_y) return zero_border(y, st);
+  if (dz_ps) return zero_border(dz_ps, st);
+  if (y) return zero_border(y, st);
   return 0;
 }
 

@@ -251,7 +251,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 constexpr int FOLD_OUT = 32, FOLD_WARPS = 8, FOLD_MAX_PER_WARP = 24;   // up to 192 partials
 __global__ void __launch_bounds__(FOLD_OUT * FOLD_WARPS)
 wgrad_fold_kernel(const float* __restrict__ ws, int parts, float* __restrict__ dw, int cin_total,
-                  int cout_total, int ci0, int co0, float* __restrict__ db, int accumulate) {
+                  int cout_total, int ci0, int co0, float* __restrict__ db, int accumulate, int perm_c4) {
   __shared__ float red[FOLD_WARPS][FOLD_OUT];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int i = blockIdx.x * FOLD_OUT + lane;   // over [tap][ci][co], then the 64 bias columns
@@ -277,14 +277,19 @@ wgrad_fold_kernel(const float* __restrict__ ws, int parts, float* __restrict__ d
   if (w != 0) return;
 #pragma unroll
   for (int r = 1; r < FOLD_WARPS; ++r) s += red[r][lane];
+  // perm_c4 != 0: dZ arrived with its channels sub-pixel-major (cop = sub * C4 + c, C4 = Cout / 4): reference 4c + sub
+  auto ref_co = [&](int cop) { return perm_c4 ? 4 * (cop % perm_c4) + cop / perm_c4 : cop; };
   if (bias_part) {
     const int c = i - NT * KC * TAPS;
-    if (db != nullptr && co0 + c < cout_total) db[co0 + c] = accumulate ? db[co0 + c] + s : s;
+    if (db != nullptr && co0 + c < cout_total) {
+      const int cr = ref_co(co0 + c);
+      db[cr] = accumulate ? db[cr] + s : s;
+    }
     return;
   }
   const int co = i % NT, t = i / NT, ci = t % KC, tap = t / KC;
   if (ci0 + ci >= cin_total || co0 + co >= cout_total) return;  // zero-filled tail of a 96-channel tensor
-  float* o = &dw[((size_t)(co0 + co) * cin_total + (ci0 + ci)) * TAPS + tap];
+  float* o = &dw[((size_t)ref_co(co0 + co) * cin_total + (ci0 + ci)) * TAPS + tap];
   *o = accumulate ? *o + s : s;
 }
 
@@ -305,7 +310,8 @@ int64_t conv_wgrad_tc_workspace(const srk_tensor* x, const srk_tensor* dy, int, 
 }
 
 int conv_wgrad_tc_launch(const srk_tensor* x, const srk_tensor* dy, float* dw, float* db, int r, int s,
-                         void* workspace, int accumulate, cudaStream_t st) {
+                         void* workspace, int accumulate, int perm_shuffle, cudaStream_t st) {
+  SRK_REQUIRE(!perm_shuffle || dy->c % 4 == 0, "wgrad_tc: sub-pixel-major dZ needs Cout %% 4 == 0");
   const int Hp = x->h + 2, Wp = x->w + 2;
   const long long P = (long long)x->n * Hp * Wp;
   SRK_REQUIRE(P < (1LL << 31) - 4096, "wgrad_tc: too many pixels");
@@ -348,7 +354,8 @@ int conv_wgrad_tc_launch(const srk_tensor* x, const srk_tensor* dy, float* dw, f
       wgrad3x3_tc_kernel<<<grid, kThreads, smem_bytes, st>>>(tmX, tmDz, p);
       SRK_CUDA_LAUNCH_CHECK("wgrad3x3_tc");
       wgrad_fold_kernel<<<(NT * KC * TAPS + NT) / FOLD_OUT, FOLD_OUT * FOLD_WARPS, 0, st>>>(p.ws, grid, dw, x->c, dy->c, kc * KC, nc * NT,
-                                                                           p.db ? db : nullptr, accumulate);
+                                                                           p.db ? db : nullptr, accumulate,
+                                                                           perm_shuffle ? dy->c / 4 : 0);
       SRK_CUDA_LAUNCH_CHECK("wgrad_fold");
     }
   return 0;

@@ -194,8 +194,12 @@ class SRCNN(nn.Module):
 def _upsample_tail(model, x):
     up = model.upsample
     x = fn.conv_act(x, up[0], act=L.ACT_PRELU, alpha=up[2].weight, shuffle=2)
+    oc = model.output_conv
+    if torch.is_grad_enabled() and fn.UpShuffleThenRGB.supported(x, up[3].weight, oc.weight):
+        # second upsample stage + output conv as one autograd node (fused backward, see fn.UpShuffleThenRGB)
+        return fn.UpShuffleThenRGB.apply(x, up[3].weight, up[3].bias, up[5].weight, oc.weight, oc.bias)
     x = fn.conv_act(x, up[3], act=L.ACT_PRELU, alpha=up[5].weight, shuffle=2)
-    return fn.conv_act(x, model.output_conv, out_img=True)
+    return fn.conv_act(x, oc, out_img=True)
 
 
 def _make_upsample(num_channels):

@@ -34,7 +34,8 @@ SIGNATURES = {
     "srk_conv_tc_supported": (c_int, [c_int] * 6),
     "srk_conv_fprop": (c_int, [_T, _T, _P, c_int, c_int, c_int, c_int, _P, c_int, _P, _T, c_int, c_int, _P, _P, _P, _P]),
     "srk_conv_fprop_workspace_bytes": (c_int64, [_T, c_int]),
-    "srk_conv_wgrad": (c_int, [_T, _T, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "srk_conv_wgrad": (c_int, [_T, _T, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "srk_conv_rgbout_bwd_unshuffle": (c_int, [_T, _T, _P, _T, _P, _P, _P, _P, c_int, _P, _P]),
     "srk_conv_wgrad_workspace_bytes": (c_int64, [_T, _T, c_int, c_int, c_int]),
     "srk_conv_rgb_workspace_bytes": (c_int64, [c_int]),
     "srk_conv_rgb_fprop": (c_int, [_T, _T, _P, c_int, _P, c_int, _P, _P]),

@@ -88,6 +88,38 @@ class ConvAct(torch.autograd.Function):
         return dx, dw, db, (dalpha if _needs(ctx, 3) else None), dres, None, None, None, None, None
 
 
+class UpShuffleThenRGB(torch.autograd.Function):
+    """img = output_conv(PReLU(PixelShuffle2(up_conv(x))))  -  upsample[3..5] + output_conv (models.py:120-125) as ONE
+    node, so that the backward of the 64 -> 3 conv, of the PReLU and of the PixelShuffle are one kernel
+    (srk_conv_rgbout_bwd_unshuffle): the 64-channel gradient at the output resolution (545 MB at C2) is never written,
+    and dz of the up conv arrives with sub-pixel-major channels for its dgrad / wgrad."""
+
+    @staticmethod
+    def forward(ctx, x, w_up, b_up, alpha, w_out, b_out):
+        ops.require_cuda(x, "upsample tail")
+        x = x.contiguous()
+        y, _ = ops.conv_fprop(x, False, w_up, b_up, L.ACT_PRELU, alpha, None, 2, False, x.dtype)
+        img, _ = ops.conv_fprop(y, False, w_out, b_out, L.ACT_NONE, None, None, 0, True, torch.float32)
+        ctx.save_for_backward(x, y, w_up, alpha, w_out)
+        ctx.cfg = (b_up is not None, b_out is not None)
+        return img
+
+    @staticmethod
+    def backward(ctx, dimg):
+        x, y, w_up, alpha, w_out = ctx.saved_tensors
+        hb_up, hb_out = ctx.cfg
+        dz, dw_out, db_out, dalpha = ops.conv_rgbout_bwd_unshuffle(y, dimg.contiguous().float(), w_out, alpha, hb_out)
+        dx = ops.conv_dgrad(dz, False, w_up, None, x.dtype, perm_tc=True) if _needs(ctx, 0) else None
+        dw_up, db_up = ops.conv_wgrad(x, False, dz, False, w_up, hb_up, perm_tc=True, side=True)
+        return dx, dw_up, db_up, dalpha, dw_out, db_out
+
+    @staticmethod
+    def supported(x, w_up, w_out):
+        return (x.dtype == torch.bfloat16 and tuple(w_up.shape) == (256, 64, 3, 3) and tuple(w_out.shape[:2]) == (3, 64)
+                and w_out.shape[2] == w_out.shape[3] and ops._rgb_tc_ok(w_out.shape[2], w_out.shape[3])
+                and ops.tc_supported(64, 256, 3, 3, x.dtype, 2) == 1 and ops.tc_supported(256, 64, 3, 3, x.dtype, 0) == 1)
+
+
 def conv_act(x, conv, act=L.ACT_NONE, alpha=None, residual=None, shuffle=0, x_img=False, out_img=False,
              out_dtype=None):
     if out_dtype is None:

@@ -332,6 +332,25 @@ def conv_rgbout_bwd(x, dout, weight, need_dx, need_bias):
     return dx, dw, (db if need_bias else None)
 
 
+def conv_rgbout_bwd_unshuffle(t64, dout_img, weight, alpha, need_bias):
+    """Backward of the 64 -> 3 output conv fused with the PReLU + PixelShuffle(2) backward of the upsample stage that
+    produced its input t64 (srk_conv_rgbout_bwd_unshuffle).  -> (dz [N, H/2+2, W/2+2, 256] bf16 with sub-pixel-major
+    channels, dw, db or None, dalpha[1])"""
+    cout, cin, r, s = weight.shape
+    n, _, h, w = geometry(t64, False)
+    dw = torch.zeros_like(weight, memory_format=torch.contiguous_format)
+    db = zeros((cout,), weight.device)
+    dalpha = zeros((1,), weight.device)
+    dz = new_act(n, 4 * cin, h // 2, w // 2, torch.bfloat16, t64.device)
+    pk = packed_weight(weight, L.PACK_RGBOUT_DGRAD_TC, 0)
+    ws = _rgb_workspace(r, t64.device)
+    _timed(("conv_rgbout_bwd_unshuffle", cin, cout, r, 2, n, h, w, True),
+           lambda: L.call("srk_conv_rgbout_bwd_unshuffle", img_desc(dout_img), act_desc(t64), pk.data_ptr(),
+                          act_desc(dz), dw.data_ptr(), db.data_ptr(), alpha.data_ptr(), dalpha.data_ptr(), r,
+                          ws.data_ptr(), stream_ptr()))
+    return dz, dw, (db if need_bias else None), dalpha
+
+
 def rgbout_bwd_supported(x, x_img, dz_img, weight):
     cout, cin, r, s = weight.shape
     return (not x_img) and dz_img and cin == 64 and cout == 3 and x.dtype == torch.bfloat16 and _rgb_tc_ok(r, s)
@@ -388,7 +407,7 @@ def conv_dgrad(dz, dz_img, weight, residual, out_dtype, perm_tc=False):
     if perm_tc and not use_tc:
         raise RuntimeError("conv_dgrad: permuted dz requires the tcgen05 path")
     kind = L.PACK_DGRAD_TC if use_tc else L.PACK_DGRAD_SIMT
-    pk = packed_weight(weight, kind, 0)
+    pk = packed_weight(weight, kind, 2 if perm_tc else 0)   # perm: dz channels are sub-pixel-major
     dx = new_act(n, cin, h, w, out_dtype, dz.device)
     rd = act_desc(residual) if residual is not None else None
     dzd = desc(dz, dz_img)
@@ -433,8 +452,6 @@ def conv_wgrad(x, x_img, dz, dz_img, weight, need_bias, perm_tc=False, side=Fals
     # reference to dw / db - which is why `keep` below must not hold them); otherwise stay on the current stream.
     side = (side and cfg.overlap_wgrad and weight.grad is None and not weight._backward_hooks
             and not getattr(weight, "_post_accumulate_grad_hooks", None))
-    if perm_tc:
-        raise RuntimeError("conv_wgrad: sub-pixel-major dz is not supported yet")
     cout, cin, r, s = weight.shape
     if not (x_img and (not dz_img) and cin == 3 and cout in (64, 96) and dz.dtype == torch.bfloat16 and _rgb_tc_ok(r, s)):
         # general path: the kernels write (accumulate = 0), so no zero-fill launches are needed
@@ -447,7 +464,7 @@ def conv_wgrad(x, x_img, dz, dz_img, weight, need_bias, perm_tc=False, side=Fals
         n, _, h, w = geometry(x, x_img)
         launch = lambda: _timed(("conv_wgrad", cin, cout, r, 0, n, h, w, nbytes > 0),
                                 lambda: L.call("srk_conv_wgrad", xd, dd, dw.data_ptr(), _ptr(db), r, s, impl, 0,
-                                               _ptr(ws), stream_ptr()))
+                                               1 if perm_tc else 0, _ptr(ws), stream_ptr()))
         if side:
             run_on_side_stream(launch, (x, dz, ws))
         else:

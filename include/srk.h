@@ -84,9 +84,12 @@ int64_t srk_conv_fprop_workspace_bytes(const srk_tensor* x, int pack_kind);
 
 /* dW (fp32, OIHW) and db (fp32 [Cout], may be NULL): added into dw / db when accumulate != 0, written otherwise.
  * x: conv input, dy: gradient w.r.t. the conv output (pre-activation, conv-output geometry).
- * workspace: srk_conv_wgrad_workspace_bytes() bytes (may be NULL when that returns 0). */
+ * workspace: srk_conv_wgrad_workspace_bytes() bytes (may be NULL when that returns 0).
+ * perm_shuffle != 0 (tcgen05 path): dy's channels are sub-pixel-major (sub * Cout/4 + c, what
+ * srk_conv_rgbout_bwd_unshuffle and srk_act_bwd(perm_tc = 1) produce for a PixelShuffle conv); dw / db come out in the
+ * reference channel order 4c + sub all the same. */
 int srk_conv_wgrad(const srk_tensor* x, const srk_tensor* dy, float* dw, float* db, int r, int s,
-                   int impl, int accumulate, void* workspace, void* stream);
+                   int impl, int accumulate, int perm_shuffle, void* workspace, void* stream);
 int64_t srk_conv_wgrad_workspace_bytes(const srk_tensor* x, const srk_tensor* dy, int r, int s, int impl);
 
 /* dgrad of a 3x3 64 -> 64 conv (bf16 ACT, w_packed_dgrad = SRK_PACK_DGRAD_TC weights) with the BatchNorm-backward
@@ -113,6 +116,14 @@ int srk_conv_rgb_fprop(const srk_tensor* img3, const srk_tensor* y, const void* 
 int srk_conv_rgb_bwd(const srk_tensor* img3, const srk_tensor* t64, const void* w_packed,
                      const srk_tensor* dx, float* dw, float* db, int k, int rgb_out, void* workspace,
                      void* stream);
+/* srk_conv_rgb_bwd (rgb_out = 1) fused with the PReLU + PixelShuffle(2) backward of the upsample stage below the output
+ * conv (autograd of models.py:120-125): t64 = that stage's output, alpha / dalpha = its PReLU slope and slope gradient
+ * (accumulated).  Instead of dx it writes dz_ps = the gradient of the 64 -> 256 conv output, bf16 ACT [N,256,H/2,W/2],
+ * channels SUB-PIXEL-MAJOR (sub * 64 + c).  Consumers: srk_conv_fprop with SRK_PACK_DGRAD_TC weights packed with
+ * pixel_shuffle = 2, and srk_conv_wgrad with perm_shuffle = 1. */
+int srk_conv_rgbout_bwd_unshuffle(const srk_tensor* dy_img, const srk_tensor* t64, const void* w_packed,
+                                  const srk_tensor* dz_ps, float* dw, float* db, const float* alpha, float* dalpha, int k,
+                                  void* workspace, void* stream);
 
 /* OIHW fp32 master weights -> kernel operand layouts (see SRK_PACK_*). */
 int srk_weight_pack(const float* w_oihw, void* out, int cout, int cin, int r, int s, int kind,

@@ -695,3 +695,54 @@ def test_eval_bn_folding_matches_unfolded_path(dtype, tol):                # net
             folded = model(lr)
         unfolded = model(lr).detach()        # grad mode on: conv -> BN(eval) -> PReLU kernels
         assert rel_err(folded.cpu(), unfolded.cpu()) <= tol, (round_, rel_err(folded.cpu(), unfolded.cpu()))
+
+
+@pytest.mark.parametrize("n,h,w", [(2, 8, 4), (1, 10, 13), (2, 16, 24)])
+def test_fused_upsample_tail_backward_vs_unfused(n, h, w):
+    """fn.UpShuffleThenRGB (64 -> 256 conv + PixelShuffle + PReLU + 9x9 64 -> 3 conv as one node whose backward fuses the
+    output-conv dgrad, the PReLU mask and the un-shuffle, with sub-pixel-major dz for the up conv's dgrad / wgrad)
+    against the same stage built from two ConvAct nodes, and against the fp32 oracle."""
+    import srk
+    from srk import _lib as L
+    from srk import fn
+    srk.set_compute_dtype("bf16")
+    g = torch.Generator().manual_seed(31 + h)
+    up = torch.nn.Conv2d(64, 256, 3, padding=1)
+    oc = torch.nn.Conv2d(64, 3, 9, padding=4)
+    with torch.no_grad():
+        for m in (up, oc):
+            m.weight.copy_(m.weight.bfloat16().float())
+            m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+    alpha0 = torch.tensor([0.25])
+    x0 = torch.randn(n, 64, h, w, generator=g).bfloat16().float()
+    gimg = torch.randn(n, 3, 2 * h, 2 * w, generator=g)
+    # fp32 oracle
+    xo, ao = x0.clone().requires_grad_(True), alpha0.clone().requires_grad_(True)
+    yo = F.conv2d(F.prelu(F.pixel_shuffle(F.conv2d(xo, up.weight, up.bias, padding=1), 2), ao), oc.weight, oc.bias, padding=4)
+    grads_o = torch.autograd.grad(yo, [xo, up.weight, up.bias, ao, oc.weight, oc.bias], gimg)
+    up, oc = up.to(DEV), oc.to(DEV)
+    res = {}
+    for mode in ("fused", "unfused"):
+        al = alpha0.to(DEV).requires_grad_(True)
+        xg = x0.to(DEV).requires_grad_(True)
+        xa = fn.ImageToAct.apply(xg, torch.bfloat16)
+        for m in (up, oc):
+            m.weight.grad = m.bias.grad = None
+        if mode == "fused":
+            assert fn.UpShuffleThenRGB.supported(xa, up.weight, oc.weight)
+            img = fn.UpShuffleThenRGB.apply(xa, up.weight, up.bias, al, oc.weight, oc.bias)
+        else:
+            t = fn.conv_act(xa, up, act=L.ACT_PRELU, alpha=al, shuffle=2)
+            img = fn.conv_act(t, oc, out_img=True)
+        img.backward(gimg.to(DEV))
+        res[mode] = [img.detach().cpu(), xg.grad.cpu(), up.weight.grad.cpu(), up.bias.grad.cpu(), al.grad.cpu(),
+                     oc.weight.grad.cpu(), oc.bias.grad.cpu()]
+    names = ["img", "dx", "dw_up", "db_up", "dalpha", "dw_out", "db_out"]
+    assert torch.equal(res["fused"][0], res["unfused"][0])
+    for k in range(1, 7):
+        # the shared PReLU slope's gradient is ONE number summed over positive and negative contributions: its relative
+        # error is that of a cancelling sum (the whole-network tests give it 2.5e-1 for the same reason)
+        tol = 1.5e-1 if names[k] == "dalpha" else 1e-2
+        assert rel_err(res["fused"][k], res["unfused"][k]) <= tol, names[k]
+        assert rel_err(res["fused"][k], grads_o[k - 1]) <= (1.5e-1 if names[k] == "dalpha" else 1.5e-2), names[k]
+    assert rel_err(res["fused"][0], yo.detach()) <= 1e-2
