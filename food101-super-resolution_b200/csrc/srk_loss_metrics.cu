@@ -176,17 +176,30 @@ __global__ void __launch_bounds__(256) nlpd_bwd_down_kernel(const signed char* _
     float acc = 0.f;
     // an exact 2x level touches fine rows / columns 2y-1 .. 2y+2 only; other ratios get the wider safe window
     const int ry = (H == 2 * h2) ? 1 : 3, rx = (W == 2 * w2) ? 1 : 3;
+    // the column weights do not depend on the row: compute them once (up to 8 columns)
+    const int X0 = max(2 * x - rx, 0), X1 = min(2 * x + rx + 1, W - 1);
+    float wxs[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int X = X0 + k;
+      float wv = 0.f;
+      if (X <= X1) {
+        int x0, x1; float lx;
+        bilin_src(X, sx, w2, x0, x1, lx);
+        wv = (x0 == x ? 1.f - lx : 0.f) + (x1 == x ? lx : 0.f);
+      }
+      wxs[k] = wv;
+    }
     for (int Y = max(2 * y - ry, 0); Y <= min(2 * y + ry + 1, H - 1); ++Y) {
       int y0, y1; float ly;
       bilin_src(Y, sy, h2, y0, y1, ly);
       float wy = (y0 == y ? 1.f - ly : 0.f) + (y1 == y ? ly : 0.f);
       if (wy == 0.f) continue;
-      for (int X = max(2 * x - rx, 0); X <= min(2 * x + rx + 1, W - 1); ++X) {
-        int x0, x1; float lx;
-        bilin_src(X, sx, w2, x0, x1, lx);
-        float wx = (x0 == x ? 1.f - lx : 0.f) + (x1 == x ? lx : 0.f);
-        if (wx == 0.f) continue;
-        acc = fmaf(wy * wx, (float)sp[(long long)Y * W + X], acc);
+      const signed char* row = sp + (long long)Y * W + X0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (X0 + k > X1 || wxs[k] == 0.f) continue;
+        acc = fmaf(wy * wxs[k], (float)row[k], acc);
       }
     }
     g_down[i] = (g_next ? g_next[i] : 0.f) - c_l * acc;
@@ -224,6 +237,61 @@ __global__ void __launch_bounds__(256) nlpd_bwd_up_kernel(const signed char* __r
       acc *= go;
     }
     G[i] = acc;
+  NLPD_LOOP_END
+}
+
+// Exact-2x levels (H = 2 h2, W = 2 w2): one thread per COARSE pixel produces the 2x2 block of fine outputs from the
+// 3x3 neighbourhood of g_down it shares (9 loads for 4 outputs instead of ~6 per output), same tap order as the
+// generic kernel, so the results are bit-identical.
+__global__ void __launch_bounds__(256) nlpd_bwd_up_2x_kernel(const signed char* __restrict__ sign,
+    const float* __restrict__ g_down, int NC, int H, int W, int h2, int w2, const float* __restrict__ k25,
+    float c_l, const float* __restrict__ d0, float c_mae, const float* __restrict__ gout,
+    float* __restrict__ G) {
+  __shared__ float k[25];
+  if (threadIdx.x < 25) k[threadIdx.x] = k25[threadIdx.x];
+  __syncthreads();
+  const float go = gout ? gout[0] : 1.f;
+  NLPD_LOOP_BEGIN(NC, h2, w2)
+    (void)i;
+    const float* gp = g_down + (long long)nc * h2 * w2;
+    float gv[3][3];   // gv[a + 1][b + 1] = g_down[y + a][x + b], 0 outside
+#pragma unroll
+    for (int a = -1; a <= 1; ++a)
+#pragma unroll
+      for (int b = -1; b <= 1; ++b) {
+        const int yy = y + a, xx = x + b;
+        gv[a + 1][b + 1] = (yy >= 0 && yy < h2 && xx >= 0 && xx < w2) ? gp[(long long)yy * w2 + xx] : 0.f;
+      }
+    const bool ya[3] = {y - 1 >= 0, true, y + 1 < h2}, xa[3] = {x - 1 >= 0, true, x + 1 < w2};
+    const long long base = ((long long)nc * H + 2 * y) * W + 2 * x;
+#pragma unroll
+    for (int py = 0; py < 2; ++py) {
+      const char2 sg = *reinterpret_cast<const char2*>(sign + base + (long long)py * W);
+      float acc[2] = {c_l * (float)sg.x, c_l * (float)sg.y};
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        // generic order: ky = Y&1, +2, ... (i.e. a = +1 first), kx likewise
+#pragma unroll
+        for (int a = 1; a >= (py ? 0 : -1); --a) {
+          const int ky = (py ? 3 : 2) - 2 * a;
+          if (!ya[a + 1]) continue;
+#pragma unroll
+          for (int b = 1; b >= (px ? 0 : -1); --b) {
+            const int kx = (px ? 3 : 2) - 2 * b;
+            if (!xa[b + 1]) continue;
+            acc[px] = fmaf(k[ky * 5 + kx], gv[a + 1][b + 1], acc[px]);
+          }
+        }
+      }
+      const long long o = base + (long long)py * W;
+      if (d0) {
+        const float2 d = *reinterpret_cast<const float2*>(d0 + o);
+        acc[0] += d.x > 0.f ? c_mae : (d.x < 0.f ? -c_mae : 0.f);
+        acc[1] += d.y > 0.f ? c_mae : (d.y < 0.f ? -c_mae : 0.f);
+        acc[0] *= go; acc[1] *= go;
+      }
+      *reinterpret_cast<float2*>(G + o) = make_float2(acc[0], acc[1]);
+    }
   NLPD_LOOP_END
 }
 
@@ -466,10 +534,16 @@ extern "C" int srk_nlpd_bwd(int n, int c, int h, int w, int levels, float alpha,
     nlpd_bwd_down_kernel<<<red_blocks(nd, 1), 256, 0, st>>>(sbase + p.sign_off[l], g_next, NC, H, W, h2, w2, sy, sx, c_l, g_down);
     if (l == 0) {
       float c_mae = (float)((double)alpha / (double)nu);
-      nlpd_bwd_up_kernel<<<red_blocks(nu, 2), 256, 0, st>>>(sbase + p.sign_off[0], g_down, NC, H, W, h2, w2, kernel25, c_l, wsf + p.cur_off[0], c_mae, gout, grad_sr);
+      if (H == 2 * h2 && W == 2 * w2)
+        nlpd_bwd_up_2x_kernel<<<red_blocks(nd, 1), 256, 0, st>>>(sbase + p.sign_off[0], g_down, NC, H, W, h2, w2, kernel25, c_l, wsf + p.cur_off[0], c_mae, gout, grad_sr);
+      else
+        nlpd_bwd_up_kernel<<<red_blocks(nu, 2), 256, 0, st>>>(sbase + p.sign_off[0], g_down, NC, H, W, h2, w2, kernel25, c_l, wsf + p.cur_off[0], c_mae, gout, grad_sr);
     } else {
       float* G = wsf + p.g_off[l & 1];
-      nlpd_bwd_up_kernel<<<red_blocks(nu, 2), 256, 0, st>>>(sbase + p.sign_off[l], g_down, NC, H, W, h2, w2, kernel25, c_l, nullptr, 0.f, nullptr, G);
+      if (H == 2 * h2 && W == 2 * w2)
+        nlpd_bwd_up_2x_kernel<<<red_blocks(nd, 1), 256, 0, st>>>(sbase + p.sign_off[l], g_down, NC, H, W, h2, w2, kernel25, c_l, nullptr, 0.f, nullptr, G);
+      else
+        nlpd_bwd_up_kernel<<<red_blocks(nu, 2), 256, 0, st>>>(sbase + p.sign_off[l], g_down, NC, H, W, h2, w2, kernel25, c_l, nullptr, 0.f, nullptr, G);
       g_next = G;
     }
   }
