@@ -1,24 +1,24 @@
-// tcgen05 / TMEM / TMA implicit-GEMM 3x3 convolution with the three HORIZONTAL taps folded into the MMA N
-// dimension (fprop, and dgrad through rotated weights) on the zero-bordered channels-last bf16 layout.
+// The 3x3 trunk convolution on tcgen05 / TMEM / TMA (fprop, and dgrad through rotated weights) on the zero-bordered
+// channels-last bf16 layout: ONE pipeline, three formulations of the MMA loop (template parameters of the kernel).
 //
-// Why: with N = 64 a tcgen05.mma M128 K16 is bound by shared-memory operand delivery (A 4 KB + B 2 KB per MMA at
-// 128 B/cycle = 48 cycles against a 32-cycle tensor floor, measured, scratch/ldtm_rate.py).  Folding the taps
-// s = 0,1,2 of one kernel row into N (N = 3 x 64 = 192) reads the A operand once per kernel ROW instead of once
-// per tap: 12 MMAs of 96 cycles per tile (measured 96 = floor) instead of 36 of 48.
+// Pipeline - one persistent CTA per SM, 608 threads: warp 0 TMA producer (halo slab [128 + 2(W+2) (+2) rows][64 ch] per
+// tile, weights once), warp 1 MMA issuer, warp 2 output TMA store / residual TMA load, warps 3-18 epilogue (four per TMEM
+// lane group, 16 output channels each; activation compiled in, incremental pixel walker, one accumulator-free arrival
+// per warp), accumulators double buffered in TMEM.  Optional epilogue fusions: BatchNorm forward statistics
+// (kStats), BatchNorm BACKWARD reduction against a second input tile (Params::bn_red, srk_conv_dgrad_bnred).
 //
-// GEMM view (reference: nn.Conv2d 3x3 s1 p1 at models.py:46,49,65,67,113,117,120):
-//   D_s[q, co] = sum_{r, ci} X[q + (r-1)*(W+2), ci] * W[r][s][co][ci]          (accumulator slot s, TMEM columns)
-//   Y[p, co]   = D_0[p-1, co] + D_1[p, co] + D_2[p+1, co]                      (epilogue: shift across TMEM lanes)
-// q runs over ALL padded pixels (a vertical tap is a constant shift of the flat pixel index because the border is
-// zero).  A tile is 128 consecutive padded pixels q0..q0+127 and produces the 126 outputs q0+1..q0+126, so
-// consecutive tiles overlap by two pixels.  The +-1 lane shift is a rotating warp shuffle per slot; the value that
-// crosses a warp boundary is first swapped in through a 4 KB shared-memory exchange buffer (lane 31 / lane 0 load
-// their neighbour warp's edge value before the rotation), so the shuffled sum needs no masking.
-//
-// One persistent CTA per SM, 608 threads: warp 0 TMA producer (halo slab [128 + 2(W+2) rows][64 ch] per tile,
-// weights once), warp 1 MMA issuer, warp 2 output TMA store / residual TMA load, warps 3-18 epilogue (four per
-// TMEM lane group, 16 output channels each: the epilogue is instruction-issue bound).
-// Accumulators are double buffered in TMEM (2 x 192 columns).
+//   kFold = 0 (DEFAULT): one MMA group per tap, N = 64: Y[p, co] = sum_{tap, ci} X[p + d(tap), ci] W[tap][co][ci] with
+//     the 9 taps as row-shifted descriptors into the slab.  Bound by the shared-memory port.
+//   kFold = 1: the three HORIZONTAL taps folded into N (N = 192, 12 MMAs of 96 cycles = the tensor floor, the A operand
+//     read once per kernel ROW):
+//       D_s[q, co] = sum_{r, ci} X[q + (r-1)*(W+2), ci] * W[r][s][co][ci]        (accumulator slot s, TMEM columns)
+//       Y[p, co]   = D_0[p-1, co] + D_1[p, co] + D_2[p+1, co]                    (epilogue: shift across TMEM lanes)
+//     A tile is 128 consecutive padded pixels q0..q0+127 and produces the 126 outputs q0+1..q0+126.  The +-1 lane
+//     shift is a rotating warp shuffle per slot; the value that crosses a warp boundary is first swapped in through a
+//     4 KB shared-memory exchange buffer.  Parity-green, but the shuffles travel through the same shared-memory port
+//     the MMA operands use: slower than kFold = 0 (25.9 vs 23.2 us per C2 layer).
+//   kPair = 1: kFold = 0 on CTA pairs (cta_group::2, M = 256), optionally with 128 output channels per pass
+//     (kCPT = 32).  Parity-green, slower (the N = 64 MMA is bound by the A operand, which pairing does not reduce).
 #include "srk_common.cuh"
 #include "srk_tc_common.cuh"
 
