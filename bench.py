@@ -367,7 +367,9 @@ def run_srk(args):
         ach = flops / (avg_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "conv3x3_c64_fprop(%s)" % ("tcgen05" if key[8] else "cuda-core"),
                 "achieved": round(ach, 2), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": round(ach / pk["tf_sustained"], 4), "traffic": ncu_traffic(), "avg_ms": round(avg_ms, 4),
+                "frac": round(ach / pk["tf_sustained"], 4),
+                "traffic": (ncu_traffic() or {}).get("bytes"), "traffic_detail": ncu_traffic(),
+                "algorithmic_flops_per_launch": flops, "avg_ms": round(avg_ms, 4),
                 "launches_per_step": count, "peak_source": pk["src"] + " bf16 sustained"}
     step_tf = world * B * FWD_BWD_GFLOP_PER_IMG / (ms_step * 1e-3) / 1e3
     line = {"metric": "sr_train_images_per_sec", "value": round(value, 2), "unit": "images/s", "n_gpus": world,
