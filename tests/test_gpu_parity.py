@@ -154,6 +154,7 @@ CONV_CASES = [
     (96, 96, 3, 20, 17, 2, "prelu", 0),     # 64 + 32 channel chunks over several tiles
     (64, 256, 3, 20, 20, 1, "prelu", 2),
     (128, 64, 3, 12, 30, 2, "relu", 0),     # two full contraction chunks
+    (64, 64, 3, 3, 300, 1, "prelu", 0),     # too wide for two halo-slab stages: per-tap TMA loads, wgrad fallback
 ]
 
 
