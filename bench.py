@@ -198,6 +198,7 @@ def run_srk(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     srk.set_compute_dtype(args.dtype)
+    srk.set_overlap_wgrad(os.environ.get("SRK_OVERLAP_WGRAD", "1") != "0")   # weight gradients on the side stream
     torch.manual_seed(0)
     model = get_model(ARCH, SCALE, dev)
     dp.broadcast_parameters(model)

@@ -56,13 +56,13 @@ class ConvAct(torch.autograd.Function):
         # with pixel-shuffle the activation is applied by the conv epilogue before the store remap
         # (a single-alpha PReLU / ReLU commutes with the permutation, models.py:117-119)
         y, used_tc = ops.conv_fprop(x, x_img, weight, bias, act, alpha, residual, shuffle, out_img, out_dtype)
-        ctx.save_for_backward(x, weight, alpha, y if act != L.ACT_NONE else None)
+        ctx.save_for_backward(x, weight, alpha, y if act != L.ACT_NONE else None, bias)
         ctx.cfg = (act, shuffle, x_img, out_img, bias is not None, residual is not None, used_tc)
         return y
 
     @staticmethod
     def backward(ctx, dout):
-        x, weight, alpha, y = ctx.saved_tensors
+        x, weight, alpha, y, bias = ctx.saved_tensors
         act, shuffle, x_img, out_img, has_bias, has_res, used_tc = ctx.cfg
         dout = dout.contiguous()
         dalpha = None
@@ -83,7 +83,7 @@ class ConvAct(torch.autograd.Function):
             if x_img:
                 dx = ops.act_to_image(dx)
         if _needs(ctx, 1) or (has_bias and _needs(ctx, 2)):
-            dw, db = ops.conv_wgrad(x, x_img, dz, dz_img, weight, has_bias, perm, side=True)
+            dw, db = ops.conv_wgrad(x, x_img, dz, dz_img, weight, has_bias, perm, side=True, bias=bias)
         dres = dout if (has_res and _needs(ctx, 4)) else None
         return dx, dw, db, (dalpha if _needs(ctx, 3) else None), dres, None, None, None, None, None
 
@@ -100,17 +100,17 @@ class UpShuffleThenRGB(torch.autograd.Function):
         x = x.contiguous()
         y, _ = ops.conv_fprop(x, False, w_up, b_up, L.ACT_PRELU, alpha, None, 2, False, x.dtype)
         img, _ = ops.conv_fprop(y, False, w_out, b_out, L.ACT_NONE, None, None, 0, True, torch.float32)
-        ctx.save_for_backward(x, y, w_up, alpha, w_out)
+        ctx.save_for_backward(x, y, w_up, alpha, w_out, b_up)
         ctx.cfg = (b_up is not None, b_out is not None)
         return img
 
     @staticmethod
     def backward(ctx, dimg):
-        x, y, w_up, alpha, w_out = ctx.saved_tensors
+        x, y, w_up, alpha, w_out, b_up = ctx.saved_tensors
         hb_up, hb_out = ctx.cfg
         dz, dw_out, db_out, dalpha = ops.conv_rgbout_bwd_unshuffle(y, dimg.contiguous().float(), w_out, alpha, hb_out)
         dx = ops.conv_dgrad(dz, False, w_up, None, x.dtype, perm_tc=True) if _needs(ctx, 0) else None
-        dw_up, db_up = ops.conv_wgrad(x, False, dz, False, w_up, hb_up, perm_tc=True, side=True)
+        dw_up, db_up = ops.conv_wgrad(x, False, dz, False, w_up, hb_up, perm_tc=True, side=True, bias=b_up)
         return dx, dw_up, db_up, dalpha, dw_out, db_out
 
     @staticmethod
@@ -138,7 +138,7 @@ def _conv_bn_forward(x, w, b, bn_params, bn_buffers, training, eps, momentum, al
     return y, out, stats
 
 
-def _conv_bn_backward(dout, x, y, stats, w, has_bias, gamma, beta, alpha, batch_stats, dgrad_residual, need_dx,
+def _conv_bn_backward(dout, x, y, stats, w, bias, gamma, beta, alpha, batch_stats, dgrad_residual, need_dx,
                       pre=None, below=None):
     """Backward of out = [PReLU](BN(conv(x))).  pre: raw BN-backward sums of dout when the dgrad that produced dout
     already reduced them (ops.conv_dgrad_bnred).  below = (z, stats, gamma, beta, alpha) of the BatchNorm layer that
@@ -151,7 +151,7 @@ def _conv_bn_backward(dout, x, y, stats, w, has_bias, gamma, beta, alpha, batch_
             dx, red = fused
         else:
             dx = ops.conv_dgrad(dy, False, w, dgrad_residual, x.dtype)
-    dw, db = ops.conv_wgrad(x, False, dy, False, w, has_bias, side=True)   # overlaps the next BN backward
+    dw, db = ops.conv_wgrad(x, False, dy, False, w, bias is not None, side=True, bias=bias)   # overlaps the next BN backward
     return dx, dw, db, dgamma, dbeta, dalpha, red
 
 
@@ -164,17 +164,17 @@ class ConvBN(torch.autograd.Function):
         x = x.contiguous()
         y, out, stats = _conv_bn_forward(x, w, b, (gamma, beta), (rm, rv, nbt), training, eps, momentum,
                                          alpha, residual)
-        ctx.save_for_backward(x, y, stats, w, gamma, beta, alpha)
+        ctx.save_for_backward(x, y, stats, w, gamma, beta, alpha, b)
         ctx.cfg = (b is not None, residual is not None, training or rm is None)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, y, stats, w, gamma, beta, alpha = ctx.saved_tensors
+        x, y, stats, w, gamma, beta, alpha, b = ctx.saved_tensors
         has_bias, has_res, batch_stats = ctx.cfg
         dout = dout.contiguous()
         dx, dw, db, dgamma, dbeta, dalpha, _ = _conv_bn_backward(
-            dout, x, y, stats, w, has_bias, gamma, beta, alpha, batch_stats, None, _needs(ctx, 0))
+            dout, x, y, stats, w, b, gamma, beta, alpha, batch_stats, None, _needs(ctx, 0))
         return (dx, dw, db, dgamma, dbeta, dalpha, dout if has_res else None,
                 None, None, None, None, None, None)
 
@@ -188,21 +188,21 @@ class ResBlockBN(torch.autograd.Function):
         x = x.contiguous()
         y1, a1, st1 = _conv_bn_forward(x, w1, b1, (g1, be1), buf1, training, eps1, mom1, alpha, None)
         y2, out, st2 = _conv_bn_forward(a1, w2, b2, (g2, be2), buf2, training, eps2, mom2, None, x)
-        ctx.save_for_backward(x, y1, st1, a1, y2, st2, w1, g1, be1, alpha, w2, g2, be2)
+        ctx.save_for_backward(x, y1, st1, a1, y2, st2, w1, g1, be1, alpha, w2, g2, be2, b1, b2)
         ctx.cfg = (b1 is not None, b2 is not None, training or buf1[0] is None)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, y1, st1, a1, y2, st2, w1, g1, be1, alpha, w2, g2, be2 = ctx.saved_tensors
+        x, y1, st1, a1, y2, st2, w1, g1, be1, alpha, w2, g2, be2, b1, b2 = ctx.saved_tensors
         hb1, hb2, batch_stats = ctx.cfg
         dout = dout.contiguous()
         # conv2's dgrad produces da1, the gradient BN1 (+ PReLU) receives: BN1's backward reduction rides in its epilogue
-        da1, dw2, db2, dg2, dbe2, _, red1 = _conv_bn_backward(dout, a1, y2, st2, w2, hb2, g2, be2, None,
+        da1, dw2, db2, dg2, dbe2, _, red1 = _conv_bn_backward(dout, a1, y2, st2, w2, b2, g2, be2, None,
                                                               batch_stats, None, True,
                                                               below=(y1, st1, g1, be1, alpha))
         # the skip connection's gradient rides in the dgrad epilogue: dx = dgrad(dy1) + dout
-        dx, dw1, db1, dg1, dbe1, dalpha, _ = _conv_bn_backward(da1, x, y1, st1, w1, hb1, g1, be1, alpha,
+        dx, dw1, db1, dg1, dbe1, dalpha, _ = _conv_bn_backward(da1, x, y1, st1, w1, b1, g1, be1, alpha,
                                                                batch_stats, dout, True, pre=red1)
         return (dx, dw1, db1, dg1, dbe1, dalpha, dw2, db2, dg2, dbe2,
                 None, None, None, None, None, None, None)
@@ -218,21 +218,21 @@ class AttnBlock(torch.autograd.Function):
         a, _ = ops.conv_fprop(x, False, w1, b1, L.ACT_PRELU, alpha, None, 0, False, x.dtype)
         r, _ = ops.conv_fprop(a, False, w2, b2, L.ACT_NONE, None, None, 0, False, x.dtype)
         out, pool, hidden, gate = ops.se_forward(x, r, fc1, fc2, scale)
-        ctx.save_for_backward(x, a, r, pool, hidden, gate, w1, alpha, w2, fc1, fc2)
+        ctx.save_for_backward(x, a, r, pool, hidden, gate, w1, alpha, w2, fc1, fc2, b1, b2)
         ctx.cfg = (b1 is not None, b2 is not None, scale)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, a, r, pool, hidden, gate, w1, alpha, w2, fc1, fc2 = ctx.saved_tensors
+        x, a, r, pool, hidden, gate, w1, alpha, w2, fc1, fc2, b1, b2 = ctx.saved_tensors
         hb1, hb2, scale = ctx.cfg
         dout = dout.contiguous()
         dr, dfc1, dfc2 = ops.se_backward(dout, r, pool, hidden, gate, fc1, fc2, scale)
         da = ops.conv_dgrad(dr, False, w2, None, a.dtype)
-        dw2, db2 = ops.conv_wgrad(a, False, dr, False, w2, hb2, side=True)
+        dw2, db2 = ops.conv_wgrad(a, False, dr, False, w2, hb2, side=True, bias=b2)
         dz1, dalpha = ops.act_bwd(da, a, L.ACT_PRELU, alpha, 0)
         dx = ops.conv_dgrad(dz1, False, w1, dout, x.dtype)
-        dw1, db1 = ops.conv_wgrad(x, False, dz1, False, w1, hb1, side=True)
+        dw1, db1 = ops.conv_wgrad(x, False, dz1, False, w1, hb1, side=True, bias=b1)
         return dx, dw1, db1, dalpha, dw2, db2, dfc1, dfc2, None
 
 

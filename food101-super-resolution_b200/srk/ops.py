@@ -22,9 +22,14 @@ class _Config:
     conv_impl = "auto"
 
 
-    # weight-gradient kernels (tensor-core / shared-memory bound) run on a side stream so that they overlap the
-    # HBM-bound BatchNorm / activation backward passes of the next layer (see run_on_side_stream)
-    overlap_wgrad = os.environ.get("SRK_OVERLAP_WGRAD", "1") != "0"
+    # Opt-in (set_overlap_wgrad / SRK_OVERLAP_WGRAD=1; bench.py and train.py switch it on): weight-gradient kernels
+    # (tensor-core / shared-memory bound) run on a side stream so that they overlap the HBM-bound BatchNorm /
+    # activation backward passes of the next layer.  Their results are then NOT handed to autograd (AccumulateGrad
+    # would clone or add them on the main stream before the side stream has produced them): the backward nodes return
+    # None for those parameters and `.grad` is assigned once the streams have joined, at the end of the backward pass.
+    # Consequences: use loss.backward() (torch.autograd.grad(..., params) sees no gradient for conv weights), and
+    # parameter hooks do not fire for them (parameters with hooks stay on the ordinary path).
+    overlap_wgrad = os.environ.get("SRK_OVERLAP_WGRAD", "0") == "1"
     # BatchNorm-backward reductions ride in the epilogue of the dgrad that produces their input gradient
     fuse_bn_reduce = os.environ.get("SRK_FUSE_BN_REDUCE", "1") != "0"
 
@@ -39,6 +44,11 @@ def set_compute_dtype(dtype):
     if dtype not in (torch.float32, torch.bfloat16):
         raise ValueError("compute dtype must be float32 or bfloat16")
     cfg.compute_dtype = dtype
+
+
+def set_overlap_wgrad(on):
+    """See _Config.overlap_wgrad."""
+    cfg.overlap_wgrad = bool(on)
 
 
 def set_conv_impl(impl):
@@ -263,6 +273,7 @@ def _timed(key, launch):
 class _Side:
     streams = {}      # device index -> torch.cuda.Stream
     pending = []      # tensors the side stream still uses (kept alive until the join is enqueued)
+    deferred = []     # (parameter, gradient computed on the side stream): assigned to .grad after the join
 
 
 def _side_stream(device):
@@ -275,23 +286,32 @@ def _side_stream(device):
     return st
 
 
+@torch.no_grad()
 def join_side_stream():
-    """Make the current stream wait for everything launched through run_on_side_stream."""
-    if not _Side.pending:
+    """Make the current stream wait for everything launched through run_on_side_stream, then hand the deferred
+    parameter gradients over: .grad = g, or .grad += g when a gradient is already there (accumulation)."""
+    if not _Side.pending and not _Side.deferred:
         return
     main = torch.cuda.current_stream()
     main.wait_stream(_side_stream(main.device))
+    for p, g in _Side.deferred:
+        if p.grad is None:
+            p.grad = g
+        else:
+            p.grad.add_(g)
+    _Side.deferred.clear()
     _Side.pending.clear()   # frees happen after the join is enqueued: allocator reuse stays ordered
 
 
-def run_on_side_stream(launch, keep):
+def run_on_side_stream(launch, keep, grads=()):
     """Run `launch()` (libsrk launches that read the current stream through stream_ptr) on the side stream,
     ordered after everything already enqueued on the current stream.  The current stream joins again at the end
-    of the autograd backward pass (engine callback), so results must only be consumed after backward() returns;
-    outside a backward pass the join happens immediately.  `keep` holds every tensor the launch touches: all of
+    of the autograd backward pass (engine callback); outside a backward pass the join happens immediately.
+    `keep` holds every tensor the launch touches and `grads` the (parameter, gradient) pairs it produces: all of
     them were allocated on the current stream and stay referenced until the join is enqueued, so the caching
-    allocator cannot hand their memory to later kernels of the current stream.  Works under CUDA-graph capture
-    (event record / wait become graph edges; the join closes the fork before the capture ends)."""
+    allocator cannot hand their memory to later kernels of the current stream, and the gradients reach `.grad`
+    only after the join.  Works under CUDA-graph capture (event record / wait become graph edges; the join closes
+    the fork before the capture ends)."""
     main = torch.cuda.current_stream()
     side = _side_stream(main.device)
     ev = torch.cuda.Event()
@@ -300,6 +320,7 @@ def run_on_side_stream(launch, keep):
     with torch.cuda.stream(side):
         launch()
     _Side.pending.append(keep)
+    _Side.deferred.extend(grads)
     try:   # one callback per launch: after the first one has joined the others find nothing pending
         torch.autograd.Variable._execution_engine.queue_callback(join_side_stream)
     except RuntimeError:
@@ -444,15 +465,25 @@ def conv_dgrad_bnred(dz, weight, z, stats, gamma, beta, alpha):
     return dx, red
 
 
-def conv_wgrad(x, x_img, dz, dz_img, weight, need_bias, perm_tc=False, side=False):
-    """-> (dW fp32 OIHW, db fp32 [Cout] or None).  side=True: launch on the side stream (run_on_side_stream);
-    the caller must not read the results before the backward pass has ended."""
-    # The results are handed to autograd before the side stream has produced them.  That is safe only when
-    # AccumulateGrad takes the tensors over without touching them (no existing .grad to add to, no hooks, no other
-    # reference to dw / db - which is why `keep` below must not hold them); otherwise stay on the current stream.
-    side = (side and cfg.overlap_wgrad and weight.grad is None and not weight._backward_hooks
-            and not getattr(weight, "_post_accumulate_grad_hooks", None))
+def conv_wgrad(x, x_img, dz, dz_img, weight, need_bias, perm_tc=False, side=False, bias=None):
+    """-> (dW fp32 OIHW, db fp32 [Cout] or None).
+    side=True asks for the side-stream path (cfg.overlap_wgrad): the kernels then run beside the following layers'
+    backward passes, the gradients are assigned to weight.grad / bias.grad when the streams join at the end of the
+    backward pass, and (None, None) is returned - the caller hands exactly that to autograd.  `bias` is the bias
+    PARAMETER (needed to assign its gradient); parameters with hooks stay on the ordinary path."""
+    def _hooked(t):
+        return t is not None and (bool(t._backward_hooks) or bool(getattr(t, "_post_accumulate_grad_hooks", None)))
+    side = (side and cfg.overlap_wgrad and torch.is_tensor(weight) and weight.is_leaf and not _hooked(weight)
+            and (not need_bias or (bias is not None and bias.is_leaf and not _hooked(bias))))
     cout, cin, r, s = weight.shape
+
+    def finish(launch, keep, dw, db):
+        if not side:
+            launch()
+            return dw, db
+        run_on_side_stream(launch, keep, [(weight, dw)] + ([(bias, db)] if db is not None else []))
+        return None, None
+
     if not (x_img and (not dz_img) and cin == 3 and cout in (64, 96) and dz.dtype == torch.bfloat16 and _rgb_tc_ok(r, s)):
         # general path: the kernels write (accumulate = 0), so no zero-fill launches are needed
         dw = torch.empty_like(weight, memory_format=torch.contiguous_format)
@@ -465,25 +496,15 @@ def conv_wgrad(x, x_img, dz, dz_img, weight, need_bias, perm_tc=False, side=Fals
         launch = lambda: _timed(("conv_wgrad", cin, cout, r, 0, n, h, w, nbytes > 0),
                                 lambda: L.call("srk_conv_wgrad", xd, dd, dw.data_ptr(), _ptr(db), r, s, impl, 0,
                                                1 if perm_tc else 0, _ptr(ws), stream_ptr()))
-        if side:
-            run_on_side_stream(launch, (x, dz, ws))
-        else:
-            launch()
-        return dw, db
+        return finish(launch, (x, dz, ws), dw, db)
     dw = torch.zeros_like(weight, memory_format=torch.contiguous_format)
     db = torch.zeros((cout,), dtype=torch.float32, device=weight.device) if need_bias else None
-    if x_img and (not dz_img) and cin == 3 and cout in (64, 96) and dz.dtype == torch.bfloat16 and _rgb_tc_ok(r, s):
-        n, _, h, w = geometry(x, True)
-        ws = _rgb_workspace(r, x.device)
-        launch = lambda: _timed(("conv_rgbin_wgrad", cin, cout, r, 0, n, h, w, True),
-                                lambda: L.call("srk_conv_rgb_bwd", img_desc(x), act_desc(dz), None, None,
-                                               dw.data_ptr(), _ptr(db), r, 0, ws.data_ptr(), stream_ptr()))
-        if side:
-            run_on_side_stream(launch, (x, dz, ws))
-        else:
-            launch()
-        return dw, db
-    raise AssertionError("unreachable")
+    n, _, h, w = geometry(x, True)
+    ws = _rgb_workspace(r, x.device)
+    launch = lambda: _timed(("conv_rgbin_wgrad", cin, cout, r, 0, n, h, w, True),
+                            lambda: L.call("srk_conv_rgb_bwd", img_desc(x), act_desc(dz), None, None,
+                                           dw.data_ptr(), _ptr(db), r, 0, ws.data_ptr(), stream_ptr()))
+    return finish(launch, (x, dz, ws), dw, db)
 
 
 def act_bwd(dout, out, act, alpha, unshuffle, perm_tc=False):

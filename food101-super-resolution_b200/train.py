@@ -63,6 +63,8 @@ def train(config=None):
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=device)
     srk.set_compute_dtype(os.environ.get("SRK_DTYPE", "bf16"))
+    # this loop only ever calls loss.backward(): weight gradients may run on the side stream (srk/ops.py)
+    srk.set_overlap_wgrad(os.environ.get("SRK_OVERLAP_WGRAD", "1") != "0")
     with _init_run(config) as run:
         cfg = run.config
         if cfg.loss_function == "gan":
