@@ -166,6 +166,14 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
     fence_barrier_init();
   }
+  if (warp == 1) {
+    if (kPair) { tmem_alloc_pair(smem_u32(&bars->tmem_base), 512); tmem_relinquish_pair(); }
+    else { tmem_alloc(smem_u32(&bars->tmem_base), 512); tmem_relinquish(); }
+  }
+  // Everything above touches only this CTA's shared memory and TMEM: under programmatic dependent launch it overlaps
+  // the tail of the previous kernel.  From here on global memory is read (bias, BN constants, operands).
+  pdl_wait();
+  pdl_trigger();
   if (threadIdx.x >= 96 && threadIdx.x < 96 + 4 * CPT) {
     const int c = threadIdx.x - 96;
     int bi = p.bias_off + c;
@@ -179,10 +187,6 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       bias_s[128 + c] = sc;
       bias_s[192 + c] = __ldg(p.bn_beta + c) - __ldg(p.bn_mean + c) * sc;
     }
-  }
-  if (warp == 1) {
-    if (kPair) { tmem_alloc_pair(smem_u32(&bars->tmem_base), 512); tmem_relinquish_pair(); }
-    else { tmem_alloc(smem_u32(&bars->tmem_base), 512); tmem_relinquish(); }
   }
   tc_fence_before();
   if (kPair) cluster_sync_all(); else __syncthreads();   // barriers initialised in both CTAs before any remote signal
@@ -623,10 +627,12 @@ static cudaError_t launch_one(int grid, int smem_bytes, cudaStream_t st, const C
                               const CUtensorMap& tmY, const CUtensorMap& tmRes, const Params& p) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kPair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = (!kPair && pdl_enabled(PDL_CONV)) ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, conv3x3_fold_tc_kernel<kFold, kFast, kStats, kAct, kPair, kCPT>, tmA, tmW, tmY, tmRes, p);
 }
 

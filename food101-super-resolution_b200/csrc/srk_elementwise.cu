@@ -203,6 +203,8 @@ __device__ __forceinline__ void block_channel_atomic(float* part, float* smem, i
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ y, Geo g, int ppb,
                                                        float* __restrict__ sum, float* __restrict__ sumsq) {
+  pdl_wait();      // the inputs come from the previous kernel of the stream (see launch_dep)
+  pdl_trigger();
   extern __shared__ float smem[];
   float s1[VEC], s2[VEC];
 #pragma unroll
@@ -258,6 +260,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ y, 
     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
     const float* __restrict__ beta, const float* __restrict__ alpha_p, const T* __restrict__ res,
     T* __restrict__ out, const BnFinalize fin) {
+  pdl_wait();      // the inputs come from the previous kernel of the stream (see launch_dep)
+  pdl_trigger();
   extern __shared__ float bn_smem[];   // fused statistics: [C] mean, [C] invstd
   const float alpha = alpha_p ? alpha_p[0] : 1.f;
   if (fin.sum) {
@@ -322,6 +326,8 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const T* __restri
     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
     const float* __restrict__ alpha_p, float* __restrict__ dgamma, float* __restrict__ dbeta,
     float* __restrict__ dalpha) {
+  pdl_wait();      // the inputs come from the previous kernel of the stream (see launch_dep)
+  pdl_trigger();
   extern __shared__ float smem[];
   const float alpha = alpha_p ? alpha_p[0] : 1.f;
   float dg[VEC], db[VEC];
@@ -387,6 +393,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
     const float* __restrict__ alpha_p, const float* __restrict__ dgamma, const float* __restrict__ dbeta,
     float inv_count, int batch_stats, T* __restrict__ dy, float* __restrict__ dgamma_out) {
+  pdl_wait();      // the inputs come from the previous kernel of the stream (see launch_dep)
+  pdl_trigger();
   const float alpha = alpha_p ? alpha_p[0] : 1.f;
   // raw mode (dgamma_out != null): the reduction came out of a conv epilogue as (sum g, sum g*z) in (dbeta, dgamma);
   // sum g*xhat = invstd * (sum g*z - mean * sum g).  Block 0 publishes the finished dgamma.
@@ -890,7 +898,7 @@ extern "C" int srk_bn_stats(const srk_tensor* y, float* sum, float* sumsq, void*
   ACT_CHECK(y, "srk_bn_stats");
   SRK_REQUIRE(c_ok(y), "srk_bn_stats: unsupported channel count %d", y->c);
   Geo g = geo_of(y); int blocks, ppb; reduce_grid(g, blocks, ppb);
-  DISPATCH_T_VEC(y, (bn_stats_kernel<T, VEC><<<blocks, 256, red_smem(y), (cudaStream_t)stream>>>(
+  DISPATCH_T_VEC(y, (launch_dep(PDL_BN, bn_stats_kernel<T, VEC>, dim3(blocks), dim3(256), red_smem(y), (cudaStream_t)stream,
                         (const T*)y->data, g, ppb, sum, sumsq)));
   SRK_CUDA_LAUNCH_CHECK("bn_stats");
   return 0;
@@ -923,7 +931,7 @@ extern "C" int srk_bn_apply(const srk_tensor* y, const float* mean, const float*
   SRK_REQUIRE(c_ok(y), "srk_bn_apply: unsupported channel count %d", y->c);
   Geo g = geo_of(y); int blocks, ppb; bn_map_grid(g, blocks, ppb);
   BnFinalize fin = {};
-  DISPATCH_T_VEC(y, (bn_apply_kernel<T, VEC><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T_VEC(y, (launch_dep(PDL_BN, bn_apply_kernel<T, VEC>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream,
                         (const T*)y->data, g, ppb, mean, invstd, gamma, beta, alpha,
                         residual ? (const T*)residual->data : nullptr, (T*)out->data, fin)));
   SRK_CUDA_LAUNCH_CHECK("bn_apply");
@@ -945,7 +953,7 @@ extern "C" int srk_bn_apply_train(const srk_tensor* y, const float* sum, const f
   BnFinalize fin = {sum, sumsq, (double)count, eps, momentum, running_mean, running_var,
                     (long long*)num_batches_tracked, mean, invstd};
   const size_t smem = 2 * (size_t)y->c * sizeof(float);
-  DISPATCH_T_VEC(y, (bn_apply_kernel<T, VEC><<<blocks, 256, smem, (cudaStream_t)stream>>>(
+  DISPATCH_T_VEC(y, (launch_dep(PDL_BN, bn_apply_kernel<T, VEC>, dim3(blocks), dim3(256), smem, (cudaStream_t)stream,
                         (const T*)y->data, g, ppb, nullptr, nullptr, gamma, beta, alpha,
                         residual ? (const T*)residual->data : nullptr, (T*)out->data, fin)));
   SRK_CUDA_LAUNCH_CHECK("bn_apply_train");
@@ -961,7 +969,7 @@ extern "C" int srk_bn_bwd_reduce(const srk_tensor* dout, const srk_tensor* y, co
   SRK_REQUIRE(c_ok(y), "srk_bn_bwd_reduce: unsupported channel count %d", y->c);
   ew_carveout_once();
   Geo g = geo_of(y); int blocks, ppb; reduce_grid(g, blocks, ppb);
-  DISPATCH_T_VEC(y, (bn_bwd_reduce_kernel<T, VEC><<<blocks, 256, red_smem(y), (cudaStream_t)stream>>>(
+  DISPATCH_T_VEC(y, (launch_dep(PDL_BN, bn_bwd_reduce_kernel<T, VEC>, dim3(blocks), dim3(256), red_smem(y), (cudaStream_t)stream,
                         (const T*)dout->data, (const T*)y->data, g, ppb, mean, invstd, gamma, beta,
                         alpha, dgamma, dbeta, dalpha)));
   SRK_CUDA_LAUNCH_CHECK("bn_bwd_reduce");
@@ -978,7 +986,7 @@ extern "C" int srk_bn_bwd_apply(const srk_tensor* dout, const srk_tensor* y, con
   SRK_REQUIRE(c_ok(y), "srk_bn_bwd_apply: unsupported channel count %d", y->c);
   Geo g = geo_of(y); int blocks, ppb; bn_map_grid(g, blocks, ppb);
   float inv_count = 1.f / ((float)y->n * y->h * y->w);
-  DISPATCH_T_VEC(y, (bn_bwd_apply_kernel<T, VEC><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T_VEC(y, (launch_dep(PDL_BN, bn_bwd_apply_kernel<T, VEC>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream,
                         (const T*)dout->data, (const T*)y->data, g, ppb, mean, invstd, gamma, beta,
                         alpha, dgamma_b, dbeta_b, inv_count, batch_stats, (T*)dy->data, nullptr)));
   SRK_CUDA_LAUNCH_CHECK("bn_bwd_apply");
@@ -996,7 +1004,7 @@ extern "C" int srk_bn_bwd_apply_raw(const srk_tensor* dout, const srk_tensor* y,
   SRK_REQUIRE(sum_g && sum_gz && dgamma_out, "srk_bn_bwd_apply_raw: sums and dgamma_out are required");
   Geo g = geo_of(y); int blocks, ppb; bn_map_grid(g, blocks, ppb);
   float inv_count = 1.f / ((float)y->n * y->h * y->w);
-  DISPATCH_T_VEC(y, (bn_bwd_apply_kernel<T, VEC><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T_VEC(y, (launch_dep(PDL_BN, bn_bwd_apply_kernel<T, VEC>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream,
                         (const T*)dout->data, (const T*)y->data, g, ppb, mean, invstd, gamma, beta,
                         alpha, sum_gz, sum_g, inv_count, batch_stats, (T*)dy->data, dgamma_out)));
   SRK_CUDA_LAUNCH_CHECK("bn_bwd_apply_raw");

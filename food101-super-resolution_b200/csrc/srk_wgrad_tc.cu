@@ -82,6 +82,8 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();      // barrier init and the TMEM allocation above overlap the previous kernel's tail (launch_dep)
+  pdl_trigger();
   const uint32_t tmem_base = bars->tmem_base;
   const int my_tiles = blockIdx.x < p.num_tiles ? (p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
@@ -253,6 +255,8 @@ __global__ void __launch_bounds__(FOLD_OUT * FOLD_WARPS)
 wgrad_fold_kernel(const float* __restrict__ ws, int parts, float* __restrict__ dw, int cin_total,
                   int cout_total, int ci0, int co0, float* __restrict__ db, int accumulate, int perm_c4) {
   __shared__ float red[FOLD_WARPS][FOLD_OUT];
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int i = blockIdx.x * FOLD_OUT + lane;   // over [tap][ci][co], then the 64 bias columns
   const bool bias_part = i >= NT * KC * TAPS;
@@ -345,17 +349,17 @@ int conv_wgrad_tc_launch(const srk_tensor* x, const srk_tensor* dy, float* dw, f
     return 1;
   const int kchunks = (x->c + KC - 1) / KC, nchunks = (dy->c + NT - 1) / NT;
   const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  const int pdl_cls = kchunks * nchunks > 1 ? PDL_WGRAD : PDL_WGRAD_SINGLE;
   for (int nc = 0; nc < nchunks; ++nc)
     for (int kc = 0; kc < kchunks; ++kc) {
       p.x_col0 = kc * KC;
       p.dz_col0 = nc * NT;
       p.ws = (float*)workspace;  // reused by every (ci, co) chunk pass: the fold runs right behind on the stream
       p.db = (db != nullptr && kc == 0) ? db + nc * NT : nullptr;
-      wgrad3x3_tc_kernel<<<grid, kThreads, smem_bytes, st>>>(tmX, tmDz, p);
+      launch_dep(pdl_cls, wgrad3x3_tc_kernel, dim3(grid), dim3(kThreads), smem_bytes, st, tmX, tmDz, p);
       SRK_CUDA_LAUNCH_CHECK("wgrad3x3_tc");
-      wgrad_fold_kernel<<<(NT * KC * TAPS + NT) / FOLD_OUT, FOLD_OUT * FOLD_WARPS, 0, st>>>(p.ws, grid, dw, x->c, dy->c, kc * KC, nc * NT,
-                                                                           p.db ? db : nullptr, accumulate,
-                                                                           perm_shuffle ? dy->c / 4 : 0);
+      launch_dep(pdl_cls, wgrad_fold_kernel, dim3((NT * KC * TAPS + NT) / FOLD_OUT), dim3(FOLD_OUT * FOLD_WARPS), 0, st, p.ws, grid,
+                 dw, x->c, dy->c, kc * KC, nc * NT, p.db ? db : nullptr, accumulate, perm_shuffle ? dy->c / 4 : 0);
       SRK_CUDA_LAUNCH_CHECK("wgrad_fold");
     }
   return 0;
