@@ -794,3 +794,23 @@ def test_side_stream_weight_gradients_match_main_stream(arch):
         assert rel_err(b, a, floor=1e-6) <= 5e-2, k
         # the second pass ran on different BatchNorm running statistics only in eval mode: train-mode grads repeat
         assert rel_err(b2, 2 * a, floor=1e-6) <= 5e-2, k
+
+
+def test_programmatic_dependent_launch_every_kernel_class():
+    """SRK_PDL selects which kernel classes are launched with the programmatic-serialization attribute (DESIGN 4e);
+    the library reads it once per process, so the oracle comparisons of the conv / wgrad / BatchNorm kernels and a
+    bf16 network step are re-run in a child process with every class switched on (default: multi-pass wgrads only)."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("SRK_PDL_CHILD"):
+        pytest.skip("already inside the SRK_PDL=15 child run")
+    env = dict(os.environ, SRK_PDL="15", SRK_PDL_CHILD="1")
+    sel = ("test_conv_forward_backward_vs_oracle or test_dgrad_with_fused_bn_backward_reduction or "
+           "test_bf16_tiny_golden_forward or test_bf16_attention_step_realistic_size or "
+           "test_side_stream_weight_gradients_match_main_stream")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k", sel],
+                       env=env, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout
