@@ -59,12 +59,14 @@ static NlpdPlan nlpd_plan(int n, int c, int h, int w, int L) {
   NlpdPlan p; p.L = L;
   long long nc = (long long)n * c, off = 0;
   p.h[0] = h; p.w[0] = w;
+  // every region starts on a 16-byte boundary: the exact-2x kernels use float2 / char2 accesses on fine rows
+  auto pad4 = [](long long v) { return (v + 3) / 4 * 4; };
   for (int l = 0; l <= L; ++l) {
     if (l > 0) { p.h[l] = (p.h[l - 1] + 1) / 2; p.w[l] = (p.w[l - 1] + 1) / 2; }
-    p.cur_off[l] = off; off += nc * p.h[l] * p.w[l];
+    p.cur_off[l] = off; off += pad4(nc * p.h[l] * p.w[l]);
   }
-  p.g_off[0] = off; off += nc * p.h[0] * p.w[0];
-  p.g_off[1] = off; off += nc * p.h[1] * p.w[1];
+  p.g_off[0] = off; off += pad4(nc * p.h[0] * p.w[0]);
+  p.g_off[1] = off; off += pad4(nc * p.h[1] * p.w[1]);
   p.floats = off;
   long long sb = 0;
   for (int l = 0; l < L; ++l) { p.sign_off[l] = sb; sb += (nc * p.h[l] * p.w[l] + 15) / 16 * 16; }
@@ -139,6 +141,16 @@ __device__ __forceinline__ void bilin_src(int o, float scale, int in, int& i0, i
   lam = fminf(fmaxf(lam, 0.f), 1.f);
 }
 
+// The generic and the exact-2x kernels share these two expressions with explicit roundings, so that a level gives the
+// same bits on either path (the compiler is otherwise free to contract a*b + c*d either way).
+__device__ __forceinline__ float bilerp(float ly, float lx, float a00, float a01, float a10, float a11) {
+  const float top = __fmaf_rn(lx, a01, __fmul_rn(1.f - lx, a00));
+  const float bot = __fmaf_rn(lx, a11, __fmul_rn(1.f - lx, a10));
+  return __fmaf_rn(ly, bot, __fmul_rn(1.f - ly, top));
+}
+__device__ __forceinline__ float gdown_of(float g_next, float c_l, float acc) { return __fmaf_rn(-c_l, acc, g_next); }
+__device__ __forceinline__ signed char sign_of(float d) { return d > 0.f ? 1 : (d < 0.f ? -1 : 0); }
+
 // diff = cur - up(down); accumulates sum|diff|; optionally stores sign(diff) as int8
 __global__ void __launch_bounds__(256) nlpd_lap_abs_kernel(const float* __restrict__ cur,
     const float* __restrict__ down, int NC, int H, int W, int h2, int w2, float sy, float sx,
@@ -150,11 +162,46 @@ __global__ void __launch_bounds__(256) nlpd_lap_abs_kernel(const float* __restri
     bilin_src(y, sy, h2, y0, y1, ly);
     bilin_src(x, sx, w2, x0, x1, lx);
     const float* p = down + (long long)nc * h2 * w2;
-    float up = (1.f - ly) * ((1.f - lx) * p[y0 * w2 + x0] + lx * p[y0 * w2 + x1]) +
-               ly * ((1.f - lx) * p[y1 * w2 + x0] + lx * p[y1 * w2 + x1]);
+    float up = bilerp(ly, lx, p[y0 * w2 + x0], p[y0 * w2 + x1], p[y1 * w2 + x0], p[y1 * w2 + x1]);
     float d = cur[i] - up;
     s += fabsf(d);
-    if (sign) sign[i] = d > 0.f ? 1 : (d < 0.f ? -1 : 0);
+    if (sign) sign[i] = sign_of(d);
+  NLPD_LOOP_END
+  double t = block_sum_d((double)s, red);
+  if (threadIdx.x == 0) atomicAdd(acc, t);
+}
+
+// Exact-2x levels (H = 2 h2, W = 2 w2; every level of a power-of-two crop): one thread per COARSE pixel produces its
+// 2x2 block of fine outputs.  align_corners=False at scale 1/2 puts fine row 2y at coarse y - 0.25 (rows y-1, y with
+// lambda 0.75; row 0 alone when y = 0) and fine row 2y+1 at y + 0.25 (rows y, min(y+1, h2-1) with lambda 0.25): the
+// 3x3 coarse neighbourhood is loaded once (9 loads for 4 outputs instead of 16), bilin_src disappears, the fine row
+// goes out as float2 / char2.  Same bilerp() on the same operands as the generic kernel: identical signs.
+__global__ void __launch_bounds__(256) nlpd_lap_abs_2x_kernel(const float* __restrict__ cur,
+    const float* __restrict__ down, int NC, int H, int W, int h2, int w2, signed char* __restrict__ sign,
+    double* __restrict__ acc) {
+  __shared__ double red[32];
+  float s = 0.f;
+  NLPD_LOOP_BEGIN(NC, h2, w2)
+    (void)i;
+    const float* p = down + (long long)nc * h2 * w2;
+    const int yr[3] = {max(y - 1, 0), y, min(y + 1, h2 - 1)}, xr[3] = {max(x - 1, 0), x, min(x + 1, w2 - 1)};
+    float g[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) g[a][b] = p[yr[a] * w2 + xr[b]];
+    const float lys[2] = {y == 0 ? 0.f : 0.75f, 0.25f}, lxs[2] = {x == 0 ? 0.f : 0.75f, 0.25f};
+    const long long base = ((long long)nc * H + 2 * y) * W + 2 * x;
+#pragma unroll
+    for (int py = 0; py < 2; ++py) {
+      const long long o = base + (long long)py * W;
+      const float2 c = *reinterpret_cast<const float2*>(cur + o);
+      const float d0 = c.x - bilerp(lys[py], lxs[0], g[py][0], g[py][1], g[py + 1][0], g[py + 1][1]);
+      const float d1 = c.y - bilerp(lys[py], lxs[1], g[py][1], g[py][2], g[py + 1][1], g[py + 1][2]);
+      s += fabsf(d0);
+      s += fabsf(d1);
+      if (sign) *reinterpret_cast<char2*>(sign + o) = make_char2(sign_of(d0), sign_of(d1));
+    }
   NLPD_LOOP_END
   double t = block_sum_d((double)s, red);
   if (threadIdx.x == 0) atomicAdd(acc, t);
@@ -202,7 +249,34 @@ __global__ void __launch_bounds__(256) nlpd_bwd_down_kernel(const signed char* _
         acc = fmaf(wy * wxs[k], (float)row[k], acc);
       }
     }
-    g_down[i] = (g_next ? g_next[i] : 0.f) - c_l * acc;
+    g_down[i] = gdown_of(g_next ? g_next[i] : 0.f, c_l, acc);
+  NLPD_LOOP_END
+}
+
+// Exact-2x levels: coarse pixel (y, x) receives fine rows 2y-1 .. 2y+2 with weights 0.25, 0.75, 0.75, 0.25 - the
+// transposed rule of nlpd_lap_abs_2x_kernel; at the borders the missing outer row drops out and the outermost fine row
+// counts fully (weight 1: both of its bilinear taps are the border pixel) - and the same in x.  No bilin_src, a
+// char / char2 / char per fine row, same products in the same order as the generic kernel: identical bits.
+__global__ void __launch_bounds__(256) nlpd_bwd_down_2x_kernel(const signed char* __restrict__ sign,
+    const float* __restrict__ g_next, int NC, int H, int W, int h2, int w2, float c_l,
+    float* __restrict__ g_down) {
+  NLPD_LOOP_BEGIN(NC, h2, w2)
+    const signed char* sp = sign + ((long long)nc * H + 2 * y) * W + 2 * x;   // fine pixel (2y, 2x)
+    const float wys[4] = {0.25f, y == 0 ? 1.f : 0.75f, y == h2 - 1 ? 1.f : 0.75f, 0.25f};
+    const float wxs[4] = {0.25f, x == 0 ? 1.f : 0.75f, x == w2 - 1 ? 1.f : 0.75f, 0.25f};
+    const bool left = x > 0, right = x < w2 - 1;
+    float acc = 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if ((r == 0 && y == 0) || (r == 3 && y == h2 - 1)) continue;
+      const signed char* row = sp + (long long)(r - 1) * W;
+      const char2 mid = *reinterpret_cast<const char2*>(row);
+      if (left) acc = fmaf(wys[r] * wxs[0], (float)row[-1], acc);
+      acc = fmaf(wys[r] * wxs[1], (float)mid.x, acc);
+      acc = fmaf(wys[r] * wxs[2], (float)mid.y, acc);
+      if (right) acc = fmaf(wys[r] * wxs[3], (float)row[2], acc);
+    }
+    g_down[i] = gdown_of(g_next ? g_next[i] : 0.f, c_l, acc);
   NLPD_LOOP_END
 }
 
@@ -452,6 +526,12 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamTable tb, flo
 
 using namespace srk;
 
+// SRK_NLPD_2X=0 keeps exact-2x pyramid levels on the generic kernels (read per call: the tests compare both paths).
+static inline bool nlpd_2x() {
+  const char* e = getenv("SRK_NLPD_2X");
+  return e == nullptr || atoi(e) != 0;
+}
+
 static inline int red_blocks(long long n, int per_thread) {
   long long b = (n + 256LL * per_thread - 1) / (256LL * per_thread);
   if (b > 148 * 8) b = 148 * 8;
@@ -505,7 +585,10 @@ extern "C" int srk_nlpd_fwd(const float* sr, const float* hr, int n, int c, int 
     long long nd = (long long)NC * h2 * w2, nu = (long long)NC * H * W;
     nlpd_blur_down_kernel<<<red_blocks(nd, 2), 256, 0, st>>>(wsf + p.cur_off[l], NC, H, W, h2, w2, kernel25, wsf + p.cur_off[l + 1]);
     float sy = (float)((double)h2 / H), sx = (float)((double)w2 / W);
-    nlpd_lap_abs_kernel<<<red_blocks(nu, 4), 256, 0, st>>>(wsf + p.cur_off[l], wsf + p.cur_off[l + 1], NC, H, W, h2, w2, sy, sx, sbase + p.sign_off[l], acc + 1 + l);
+    if (nlpd_2x() && H == 2 * h2 && W == 2 * w2)
+      nlpd_lap_abs_2x_kernel<<<red_blocks(nd, 1), 256, 0, st>>>(wsf + p.cur_off[l], wsf + p.cur_off[l + 1], NC, H, W, h2, w2, sbase + p.sign_off[l], acc + 1 + l);
+    else
+      nlpd_lap_abs_kernel<<<red_blocks(nu, 4), 256, 0, st>>>(wsf + p.cur_off[l], wsf + p.cur_off[l + 1], NC, H, W, h2, w2, sy, sx, sbase + p.sign_off[l], acc + 1 + l);
     wt.w[1 + l] = (1.0 - (double)alpha) / (double)nu;
   }
   nlpd_combine_kernel<<<1, 1, 0, st>>>(acc, wt, loss);
@@ -531,7 +614,10 @@ extern "C" int srk_nlpd_bwd(int n, int c, int h, int w, int levels, float alpha,
     float c_l = (float)((1.0 - (double)alpha) / (double)nu);
     float sy = (float)((double)h2 / H), sx = (float)((double)w2 / W);
     float* g_down = wsf + p.cur_off[l + 1];
-    nlpd_bwd_down_kernel<<<red_blocks(nd, 1), 256, 0, st>>>(sbase + p.sign_off[l], g_next, NC, H, W, h2, w2, sy, sx, c_l, g_down);
+    if (nlpd_2x() && H == 2 * h2 && W == 2 * w2)
+      nlpd_bwd_down_2x_kernel<<<red_blocks(nd, 1), 256, 0, st>>>(sbase + p.sign_off[l], g_next, NC, H, W, h2, w2, c_l, g_down);
+    else
+      nlpd_bwd_down_kernel<<<red_blocks(nd, 1), 256, 0, st>>>(sbase + p.sign_off[l], g_next, NC, H, W, h2, w2, sy, sx, c_l, g_down);
     if (l == 0) {
       float c_mae = (float)((double)alpha / (double)nu);
       if (H == 2 * h2 && W == 2 * w2)

@@ -18,4 +18,7 @@ def t(f, n=10):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n * 1e3
-print("NLPD fwd+bwd at 64x3x256x256: %.1f us" % t(f))
+import os
+for mode in ("0", "1", "0", "1"):
+    os.environ["SRK_NLPD_2X"] = mode
+    print("NLPD fwd+bwd at 64x3x256x256, SRK_NLPD_2X=%s: %.1f us" % (mode, t(f)))

@@ -814,3 +814,40 @@ def test_programmatic_dependent_launch_every_kernel_class():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout and "failed" not in r.stdout
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 16, 16), (1, 3, 32, 48), (2, 1, 64, 40), (1, 3, 256, 256), (1, 2, 4, 4)])
+def test_nlpd_exact_2x_kernels_match_generic_kernels_and_oracle(shape):
+    """Pyramid levels with H = 2 h2, W = 2 w2 (every level of a power-of-two crop) run on one-thread-per-coarse-pixel
+    kernels (nlpd_lap_abs_2x / nlpd_bwd_down_2x / nlpd_bwd_up_2x); SRK_NLPD_2X=0 keeps them on the generic kernels.
+    Shapes go down to 1x1 levels (both borders in one pixel) and include a level chain that stops being exact
+    (40 -> 20 -> 10 -> 5 -> 3).  Same operands through the same rounded expressions: the gradient (sign maps and
+    their transposed filters) is bit-identical; the loss differs only by the fp32 summation order."""
+    import os
+    from src.loss import get_loss_function
+    g = torch.Generator().manual_seed(5)
+    sr_h, hr_h = torch.rand(shape, generator=g), torch.rand(shape, generator=g)
+    crit = get_loss_function("nlpd", DEV)
+    if shape[1] != 3:
+        from src.loss import NLPDLoss
+        crit = NLPDLoss(device=DEV, channels=shape[1]).to(DEV)
+    res = {}
+    try:
+        for mode in ("0", "1"):
+            os.environ["SRK_NLPD_2X"] = mode
+            sr = sr_h.to(DEV).requires_grad_(True)
+            loss = crit(sr, hr_h.to(DEV))
+            loss.backward()
+            res[mode] = (loss.item(), sr.grad.cpu())
+    finally:
+        os.environ.pop("SRK_NLPD_2X", None)
+    sro = sr_h.clone().requires_grad_(True)
+    lo = O.nlpd_loss(sro, hr_h)
+    lo.backward()
+    gtol = 2e-7 * max(1.0, 1e4 / sr_h.numel())   # gradients scale with 1 / numel
+    assert abs(res["0"][0] - lo.item()) <= 2e-6, "generic kernels vs oracle"
+    assert max_abs(res["0"][1], sro.grad) <= gtol, "generic kernels vs oracle"
+    assert abs(res["1"][0] - lo.item()) <= 2e-6, "2x kernels vs oracle"
+    assert max_abs(res["1"][1], sro.grad) <= gtol, "2x kernels vs oracle"
+    assert abs(res["0"][0] - res["1"][0]) <= 1e-6 * max(1.0, abs(res["0"][0]))
+    assert torch.equal(res["0"][1], res["1"][1])
