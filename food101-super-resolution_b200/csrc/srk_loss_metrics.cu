@@ -132,6 +132,49 @@ __global__ void __launch_bounds__(256) nlpd_blur_down_kernel(const float* __rest
   NLPD_LOOP_END
 }
 
+// Even fine width (W = 2 w2): one thread produces TWO horizontally adjacent outputs from the 5 x 7 fine window they
+// share, read as three float2 and one float per row (20 load instructions for two outputs instead of 50).  Taps that
+// fall outside the image contribute k * 0 (the generic kernel skips them): the same fmaf chain, identical bits.
+__global__ void __launch_bounds__(256) nlpd_blur_down_pair_kernel(const float* __restrict__ cur, int NC, int H,
+    int W, int h2, int w2, const float* __restrict__ k25, float* __restrict__ down) {
+  __shared__ float k[25];
+  if (threadIdx.x < 25) k[threadIdx.x] = k25[threadIdx.x];
+  __syncthreads();
+  const int pairs = (w2 + 1) / 2;
+  NLPD_LOOP_BEGIN(NC, h2, pairs)
+    (void)i;
+    const float* p = cur + (long long)nc * H * W;
+    const int c0 = 4 * x - 2;   // first fine column of the window; outputs 2x and 2x + 1
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky) {
+      const int yy = 2 * y + ky - 2;
+      if (yy < 0 || yy >= H) continue;
+      const float* row = p + (long long)yy * W + c0;
+      float v[7];
+      {
+        const float2 t0 = c0 >= 0 ? *reinterpret_cast<const float2*>(row) : make_float2(0.f, 0.f);
+        const float2 t1 = *reinterpret_cast<const float2*>(row + 2);   // columns 4x, 4x + 1 always exist
+        const float2 t2 = c0 + 4 < W ? *reinterpret_cast<const float2*>(row + 4) : make_float2(0.f, 0.f);
+        v[0] = t0.x; v[1] = t0.y; v[2] = t1.x; v[3] = t1.y; v[4] = t2.x; v[5] = t2.y;
+        v[6] = c0 + 6 < W ? row[6] : 0.f;
+      }
+#pragma unroll
+      for (int kx = 0; kx < 5; ++kx) {
+        a0 = fmaf(k[ky * 5 + kx], v[kx], a0);
+        a1 = fmaf(k[ky * 5 + kx], v[kx + 2], a1);
+      }
+    }
+    float* o = down + ((long long)nc * h2 + y) * w2 + 2 * x;
+    if ((w2 & 1) == 0) {
+      *reinterpret_cast<float2*>(o) = make_float2(a0, a1);
+    } else {
+      o[0] = a0;
+      if (2 * x + 1 < w2) o[1] = a1;
+    }
+  NLPD_LOOP_END
+}
+
 // bilinear, align_corners=False, explicit output size (loss.py:63): src = max(scale*(o+.5)-.5, 0)
 __device__ __forceinline__ void bilin_src(int o, float scale, int in, int& i0, int& i1, float& lam) {
   float src = fmaxf(scale * (o + 0.5f) - 0.5f, 0.f);
@@ -532,6 +575,16 @@ static inline bool nlpd_2x() {
   return e == nullptr || atoi(e) != 0;
 }
 
+// The NLPD kernels are row-stride loops: more blocks than fit on the GPU at once only add a partial second wave
+// (lap_abs_2x: 40 registers -> 6 blocks / SM, so 1184 blocks ran as 1.33 waves).  Cap the grid at what is resident.
+template <typename K>
+static int resident_cap(K kernel, int blocks) {
+  int occ = 0;   // queried per launch (microseconds, and nothing at all when a captured graph is replayed)
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, 0) != cudaSuccess || occ < 1) occ = 1;
+  const int cap = kNumSMs * occ;
+  return blocks < cap ? blocks : cap;
+}
+
 static inline int red_blocks(long long n, int per_thread) {
   long long b = (n + 256LL * per_thread - 1) / (256LL * per_thread);
   if (b > 148 * 8) b = 148 * 8;
@@ -576,19 +629,22 @@ extern "C" int srk_nlpd_fwd(const float* sr, const float* hr, int n, int c, int 
   const int NC = n * c;
   cudaMemsetAsync(acc, 0, 8 * sizeof(double), st);
   long long n0 = (long long)NC * h * w;
-  nlpd_diff_kernel<<<red_blocks(n0, 8), 256, 0, st>>>(sr, hr, n0, clamp01, wsf + p.cur_off[0], acc);
+  nlpd_diff_kernel<<<resident_cap(nlpd_diff_kernel, red_blocks(n0, 8)), 256, 0, st>>>(sr, hr, n0, clamp01, wsf + p.cur_off[0], acc);
   NlpdWeights wt;
   for (int i = 0; i < 8; ++i) wt.w[i] = 0.0;
   wt.w[0] = (double)alpha / (double)n0;
   for (int l = 0; l < levels; ++l) {
     int H = p.h[l], W = p.w[l], h2 = p.h[l + 1], w2 = p.w[l + 1];
     long long nd = (long long)NC * h2 * w2, nu = (long long)NC * H * W;
-    nlpd_blur_down_kernel<<<red_blocks(nd, 2), 256, 0, st>>>(wsf + p.cur_off[l], NC, H, W, h2, w2, kernel25, wsf + p.cur_off[l + 1]);
+    if (nlpd_2x() && W == 2 * w2)
+      nlpd_blur_down_pair_kernel<<<resident_cap(nlpd_blur_down_pair_kernel, red_blocks((long long)NC * h2 * ((w2 + 1) / 2), 1)), 256, 0, st>>>(wsf + p.cur_off[l], NC, H, W, h2, w2, kernel25, wsf + p.cur_off[l + 1]);
+    else
+      nlpd_blur_down_kernel<<<resident_cap(nlpd_blur_down_kernel, red_blocks(nd, 2)), 256, 0, st>>>(wsf + p.cur_off[l], NC, H, W, h2, w2, kernel25, wsf + p.cur_off[l + 1]);
     float sy = (float)((double)h2 / H), sx = (float)((double)w2 / W);
     if (nlpd_2x() && H == 2 * h2 && W == 2 * w2)
-      nlpd_lap_abs_2x_kernel<<<red_blocks(nd, 1), 256, 0, st>>>(wsf + p.cur_off[l], wsf + p.cur_off[l + 1], NC, H, W, h2, w2, sbase + p.sign_off[l], acc + 1 + l);
+      nlpd_lap_abs_2x_kernel<<<resident_cap(nlpd_lap_abs_2x_kernel, red_blocks(nd, 1)), 256, 0, st>>>(wsf + p.cur_off[l], wsf + p.cur_off[l + 1], NC, H, W, h2, w2, sbase + p.sign_off[l], acc + 1 + l);
     else
-      nlpd_lap_abs_kernel<<<red_blocks(nu, 4), 256, 0, st>>>(wsf + p.cur_off[l], wsf + p.cur_off[l + 1], NC, H, W, h2, w2, sy, sx, sbase + p.sign_off[l], acc + 1 + l);
+      nlpd_lap_abs_kernel<<<resident_cap(nlpd_lap_abs_kernel, red_blocks(nu, 4)), 256, 0, st>>>(wsf + p.cur_off[l], wsf + p.cur_off[l + 1], NC, H, W, h2, w2, sy, sx, sbase + p.sign_off[l], acc + 1 + l);
     wt.w[1 + l] = (1.0 - (double)alpha) / (double)nu;
   }
   nlpd_combine_kernel<<<1, 1, 0, st>>>(acc, wt, loss);
@@ -615,21 +671,21 @@ extern "C" int srk_nlpd_bwd(int n, int c, int h, int w, int levels, float alpha,
     float sy = (float)((double)h2 / H), sx = (float)((double)w2 / W);
     float* g_down = wsf + p.cur_off[l + 1];
     if (nlpd_2x() && H == 2 * h2 && W == 2 * w2)
-      nlpd_bwd_down_2x_kernel<<<red_blocks(nd, 1), 256, 0, st>>>(sbase + p.sign_off[l], g_next, NC, H, W, h2, w2, c_l, g_down);
+      nlpd_bwd_down_2x_kernel<<<resident_cap(nlpd_bwd_down_2x_kernel, red_blocks(nd, 1)), 256, 0, st>>>(sbase + p.sign_off[l], g_next, NC, H, W, h2, w2, c_l, g_down);
     else
-      nlpd_bwd_down_kernel<<<red_blocks(nd, 1), 256, 0, st>>>(sbase + p.sign_off[l], g_next, NC, H, W, h2, w2, sy, sx, c_l, g_down);
+      nlpd_bwd_down_kernel<<<resident_cap(nlpd_bwd_down_kernel, red_blocks(nd, 1)), 256, 0, st>>>(sbase + p.sign_off[l], g_next, NC, H, W, h2, w2, sy, sx, c_l, g_down);
     if (l == 0) {
       float c_mae = (float)((double)alpha / (double)nu);
       if (H == 2 * h2 && W == 2 * w2)
-        nlpd_bwd_up_2x_kernel<<<red_blocks(nd, 1), 256, 0, st>>>(sbase + p.sign_off[0], g_down, NC, H, W, h2, w2, kernel25, c_l, wsf + p.cur_off[0], c_mae, gout, grad_sr);
+        nlpd_bwd_up_2x_kernel<<<resident_cap(nlpd_bwd_up_2x_kernel, red_blocks(nd, 1)), 256, 0, st>>>(sbase + p.sign_off[0], g_down, NC, H, W, h2, w2, kernel25, c_l, wsf + p.cur_off[0], c_mae, gout, grad_sr);
       else
-        nlpd_bwd_up_kernel<<<red_blocks(nu, 2), 256, 0, st>>>(sbase + p.sign_off[0], g_down, NC, H, W, h2, w2, kernel25, c_l, wsf + p.cur_off[0], c_mae, gout, grad_sr);
+        nlpd_bwd_up_kernel<<<resident_cap(nlpd_bwd_up_kernel, red_blocks(nu, 2)), 256, 0, st>>>(sbase + p.sign_off[0], g_down, NC, H, W, h2, w2, kernel25, c_l, wsf + p.cur_off[0], c_mae, gout, grad_sr);
     } else {
       float* G = wsf + p.g_off[l & 1];
       if (H == 2 * h2 && W == 2 * w2)
-        nlpd_bwd_up_2x_kernel<<<red_blocks(nd, 1), 256, 0, st>>>(sbase + p.sign_off[l], g_down, NC, H, W, h2, w2, kernel25, c_l, nullptr, 0.f, nullptr, G);
+        nlpd_bwd_up_2x_kernel<<<resident_cap(nlpd_bwd_up_2x_kernel, red_blocks(nd, 1)), 256, 0, st>>>(sbase + p.sign_off[l], g_down, NC, H, W, h2, w2, kernel25, c_l, nullptr, 0.f, nullptr, G);
       else
-        nlpd_bwd_up_kernel<<<red_blocks(nu, 2), 256, 0, st>>>(sbase + p.sign_off[l], g_down, NC, H, W, h2, w2, kernel25, c_l, nullptr, 0.f, nullptr, G);
+        nlpd_bwd_up_kernel<<<resident_cap(nlpd_bwd_up_kernel, red_blocks(nu, 2)), 256, 0, st>>>(sbase + p.sign_off[l], g_down, NC, H, W, h2, w2, kernel25, c_l, nullptr, 0.f, nullptr, G);
       g_next = G;
     }
   }

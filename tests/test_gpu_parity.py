@@ -819,7 +819,8 @@ def test_programmatic_dependent_launch_every_kernel_class():
 @pytest.mark.parametrize("shape", [(2, 3, 16, 16), (1, 3, 32, 48), (2, 1, 64, 40), (1, 3, 256, 256), (1, 2, 4, 4)])
 def test_nlpd_exact_2x_kernels_match_generic_kernels_and_oracle(shape):
     """Pyramid levels with H = 2 h2, W = 2 w2 (every level of a power-of-two crop) run on one-thread-per-coarse-pixel
-    kernels (nlpd_lap_abs_2x / nlpd_bwd_down_2x / nlpd_bwd_up_2x); SRK_NLPD_2X=0 keeps them on the generic kernels.
+    kernels (nlpd_lap_abs_2x / nlpd_bwd_down_2x / nlpd_bwd_up_2x) and a two-outputs-per-thread blur (nlpd_blur_down_pair);
+    SRK_NLPD_2X=0 keeps them on the generic kernels.
     Shapes go down to 1x1 levels (both borders in one pixel) and include a level chain that stops being exact
     (40 -> 20 -> 10 -> 5 -> 3).  Same operands through the same rounded expressions: the gradient (sign maps and
     their transposed filters) is bit-identical; the loss differs only by the fp32 summation order."""
