@@ -97,3 +97,25 @@ def test_product_code_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "sr_oracle" not in src and "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_nlpd_workspace_plan_is_host_only_and_aligned():
+    """srk_nlpd_workspace_bytes is pure host arithmetic (no GPU needed): it rejects level counts outside [1, 6], grows
+    with every dimension, and holds at least the pyramid of the difference image (sum of the level sizes, fp32), the
+    int8 sign maps and the two gradient ping-pong buffers; every region is padded to 16 bytes (the exact-2x kernels use
+    float2 / char2 accesses), so odd sizes cost at most a few bytes per region."""
+    from srk import _lib
+    f = _lib.cdll.srk_nlpd_workspace_bytes
+    assert f(1, 3, 16, 16, 0) == -1 and f(1, 3, 16, 16, 7) == -1
+    for (n, c, h, w, L) in [(1, 3, 4, 4, 4), (2, 3, 25, 37, 4), (1, 1, 11, 11, 3), (64, 3, 256, 256, 4)]:
+        hs, ws = [h], [w]
+        for _ in range(L):
+            hs.append((hs[-1] + 1) // 2)
+            ws.append((ws[-1] + 1) // 2)
+        nc = n * c
+        floats = sum(nc * a * b for a, b in zip(hs, ws)) + nc * hs[0] * ws[0] + nc * hs[1] * ws[1]
+        signs = sum(nc * hs[l] * ws[l] for l in range(L))
+        need = 4 * floats + signs + 8 * 8
+        got = f(n, c, h, w, L)
+        assert got % 16 == 0 and need <= got <= need + 16 * (2 * L + 6), (n, c, h, w, L, got, need)
+        assert f(n + 1, c, h, w, L) > got and f(n, c, h + 2, w, L) > got
