@@ -125,7 +125,7 @@ def run_reference(args):
         return
     from oracle import sr_oracle as O
     torch.manual_seed(0)
-    threads = torch.get_num_threads()
+    threads = host_threads()
     sample_batch = args.cpu_batch
     sd = cpu_state_dict()
     lr, hr = O.synthetic_pair(sample_batch, LR_HW, LR_HW, SCALE)
@@ -167,11 +167,29 @@ def cpu_state_dict():
     return {k: v.clone() for k, v in get_model(ARCH, SCALE, "cpu").state_dict().items()}
 
 
+def host_threads():
+    """Threads of the CPU legs.  torch's own default (one per physical core) is kept; torchrun, however, exports
+    OMP_NUM_THREADS=1 to its workers, which would turn the reference arm of an N > 1 run into a single-threaded
+    measurement: in that case the physical cores this process may run on are used, as in the N = 1 run."""
+    if torch.get_num_threads() == 1 and "OMP_NUM_THREADS" in os.environ:
+        try:
+            n = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n = os.cpu_count() or 1
+        try:
+            import psutil
+            n = min(n, psutil.cpu_count(logical=False) or n)
+        except ImportError:
+            pass
+        torch.set_num_threads(max(n, 1))
+    return torch.get_num_threads()
+
+
 def cpu_baseline(budget_s=20.0, batch=2):
     from oracle import sr_oracle as O
     sd = cpu_state_dict()
     lr, hr = O.synthetic_pair(batch, LR_HW, LR_HW, SCALE)
-    threads = torch.get_num_threads()
+    threads = host_threads()
     times = []
     t_begin = time.perf_counter()
     while len(times) < 4 and (time.perf_counter() - t_begin) < budget_s:
