@@ -56,17 +56,6 @@ def peaks():
     return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
 
 
-def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    `ncu --set full` capture (profiles/r1_conv3x3_ncu.json); None when the summary is missing."""
-    p = os.path.join(ROOT, "profiles", "r1_conv3x3_ncu.json")
-    if not os.path.exists(p):
-        return None
-    d = json.load(open(p))
-    return {"bytes": d["dram_bytes_read"] + d["dram_bytes_write"], "algorithmic_bytes": d["algorithmic_bytes"],
-            "tensor_pipe_active_pct": d["tensor_pipe_active_pct"], "source": "profiles/r1_conv3x3_ncu.json"}
-
-
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -118,53 +107,84 @@ def dist_env():
 
 
 # --------------------------------------------------------------------------------------------------
+class _CpuReference:
+    """The reference's own CPU training step: its unmodified nn.Modules (oracle/_ref: byte copies of the reference's
+    src/models.py and src/loss.py, see oracle/build_ref.py) driven the way reference train.py:53-56,116-120 drives
+    them - get_model, get_loss_function, optim.Adam(betas=(0.5, 0.999)), zero_grad / forward / loss / backward / step.
+    Falls back to the pinned port (oracle/sr_oracle.py, the same ATen calls) when the copy is not in the tree."""
+
+    def __init__(self, batch):
+        from oracle import ref_modules
+        from oracle import sr_oracle as O
+        self.O, self.batch = O, batch
+        torch.manual_seed(0)
+        self.lr, self.hr = O.synthetic_pair(batch, LR_HW, LR_HW, SCALE)
+        if ref_modules.available():
+            ref = ref_modules.load()
+            self.kind = "reference"
+            self.model = ref.models.get_model(ARCH, scale_factor=SCALE, device="cpu").train()
+            self.crit = ref.loss.get_loss_function(LOSS, "cpu")
+            self.opt = torch.optim.Adam(self.model.parameters(), lr=4e-4, betas=(0.5, 0.999))
+        else:
+            self.kind = "port"
+            from src.models import get_model   # constructors only (seeded init); no libsrk kernel runs on CPU tensors
+            sd = {k: v.clone() for k, v in get_model(ARCH, SCALE, "cpu").state_dict().items()}
+            self.params = {k: v.clone().requires_grad_(True) for k, v in sd.items()
+                           if v.is_floating_point() and "running_" not in k}
+            self.work = dict(sd)
+            self.work.update(self.params)
+            self.opt = torch.optim.Adam(list(self.params.values()), lr=4e-4, betas=(0.5, 0.999))
+
+    def step(self):
+        self.opt.zero_grad()
+        if self.kind == "reference":
+            loss = self.crit(self.model(self.lr), self.hr)
+        else:
+            out = self.O.model_forward(ARCH, self.work, self.lr, training=True, scale_factor=SCALE)
+            loss = self.O.loss_fn(LOSS)(out, self.hr)
+        loss.backward()
+        self.opt.step()
+        return loss.item()
+
+
+def _cpu_probe_rate(threads):
+    """images/s of the CPU reference step at a small batch (one warm-up + one timed step)."""
+    ref = _CpuReference(min(4, BATCH_PER_GPU))
+    ref.step()
+    t0 = time.perf_counter()
+    ref.step()
+    return ref.batch / (time.perf_counter() - t0)
+
+
 def run_reference(args):
-    """CPU port of the reference path on the host cores (rank 0 only)."""
+    """`--impl reference`: the reference's CPU implementation on the host cores (rank 0 only), all threads, same
+    workload definition; the per-step batch is the config's own when (steps + warmup) of it fit ~150 s of CPU time,
+    else the largest batch that does (stated in `sample`)."""
     rank, _, world = dist_env()
     if rank != 0:
         return
-    from oracle import sr_oracle as O
-    torch.manual_seed(0)
     threads = host_threads()
-    sample_batch = args.cpu_batch
-    sd = cpu_state_dict()
-    lr, hr = O.synthetic_pair(sample_batch, LR_HW, LR_HW, SCALE)
-    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()
-              if v.is_floating_point() and "running_" not in k}
-    work = dict(sd)
-    work.update(params)
-    opt = torch.optim.Adam(list(params.values()), lr=4e-4, betas=(0.5, 0.999))
-
-    def step():
-        opt.zero_grad()
-        out = O.model_forward(ARCH, work, lr, training=True, scale_factor=SCALE)
-        loss = O.loss_fn(LOSS)(out, hr)
-        loss.backward()
-        opt.step()
-        return loss.item()
-
+    rate = _cpu_probe_rate(threads)
+    budget_s = float(os.environ.get("SRK_REF_BUDGET_S", "150"))
+    fit = int(rate * budget_s / max(args.steps + args.warmup, 1))
+    sample_batch = args.cpu_batch if args.cpu_batch > 0 else max(1, min(args.batch, fit))
+    ref = _CpuReference(sample_batch)
     for _ in range(args.warmup):
-        step()
+        ref.step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        ref.step()
     dt = (time.perf_counter() - t0) / args.steps
     v = sample_batch / dt
-    sample = "batch %d of the C2 workload per step (fp32, torch CPU ATen ops, %d threads)" % (sample_batch, threads)
+    what = "unmodified reference modules (oracle/_ref)" if ref.kind == "reference" else "port oracle/sr_oracle.py"
+    sample = "batch %d of %d per step, %s, fp32, torch CPU ATen ops, %d threads" % (sample_batch, args.batch, what, threads)
     line = {"impl": "reference", "metric": "sr_train_images_per_sec", "value": round(v, 3), "unit": "images/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": sample},
-            "cpu_baseline": {"value": round(v, 3), "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+            "config": {"workload": WORKLOAD, "sample": sample, "sample_batch": sample_batch},
+            "cpu_baseline": {"value": round(v, 3), "unit": "images/s", "cores": threads, "kind": ref.kind, "sample": sample},
             "e2e": {"value": round(v, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
-
-
-def cpu_state_dict():
-    """Seeded ResNet-SR weights built on the CPU through the drop-in constructors (no compute)."""
-    from src.models import get_model
-    torch.manual_seed(0)
-    return {k: v.clone() for k, v in get_model(ARCH, SCALE, "cpu").state_dict().items()}
 
 
 def host_threads():
@@ -185,27 +205,175 @@ def host_threads():
     return torch.get_num_threads()
 
 
-def cpu_baseline(budget_s=20.0, batch=2):
-    from oracle import sr_oracle as O
-    sd = cpu_state_dict()
-    lr, hr = O.synthetic_pair(batch, LR_HW, LR_HW, SCALE)
+def cpu_baseline(budget_s=20.0, batch=4):
+    """The same CPU reference step on a bounded sample (rank 0, N = 1 only): best of up to 3 steps after a warm-up."""
+    ref = _CpuReference(min(batch, BATCH_PER_GPU))
     threads = host_threads()
     times = []
     t_begin = time.perf_counter()
     while len(times) < 4 and (time.perf_counter() - t_begin) < budget_s:
         t0 = time.perf_counter()
-        O.train_step_grads(ARCH, sd, lr, hr, LOSS, scale_factor=SCALE)
+        ref.step()
         times.append(time.perf_counter() - t0)
     best = min(times[1:]) if len(times) > 1 else times[0]
-    return {"value": round(batch / best, 3), "unit": "images/s", "cores": threads, "kind": "port",
-            "sample": "%d x (fwd+loss+bwd of batch %d, C2 shapes, fp32), best step after 1 warm-up" % (len(times), batch)}
+    what = "unmodified reference modules (oracle/_ref)" if ref.kind == "reference" else "port oracle/sr_oracle.py"
+    return {"value": round(ref.batch / best, 3), "unit": "images/s", "cores": threads, "kind": ref.kind,
+            "sample": "%d x (zero_grad+fwd+loss+bwd+Adam of batch %d, %s, fp32), best step after 1 warm-up"
+                      % (len(times), ref.batch, what)}
 
 
 # --------------------------------------------------------------------------------------------------
+def _time_replayed(launch_sets, reps=5):
+    """Average duration (ms) of ONE launch: the launches of `launch_sets` (a list of callables, each bound to its own
+    set of seeded, non-zero buffers; together they exceed the 126 MB L2, so no launch finds its operands cached by the
+    previous one) are captured back to back in a CUDA graph - no host gaps inside the bracket - and the replay is timed
+    with CUDA events on the stream it runs on."""
+    for f in launch_sets:
+        f()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    rounds = max(1, 24 // len(launch_sets))
+    with torch.cuda.stream(side):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(rounds):
+                for f in launch_sets:
+                    f()
+        g.replay()
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(side)
+            g.replay()
+            e1.record(side)
+            torch.cuda.synchronize()
+            t = e0.elapsed_time(e1) / (rounds * len(launch_sets))
+            best = t if best is None else min(best, t)
+    return best
+
+
+def kernel_rooflines(B, dev, pk):
+    """Per-kernel rooflines of the C2 step's heaviest kernels, each timed ALONE (hence against the BURST tensor peak /
+    the measured copy bandwidth) at the step's own shapes, on four rotating sets of seeded random operands.
+    Algorithmic work per launch: convs 2 * N*H*W * Cin * Cout * 9 FLOP; HBM kernels: every distinct input read once and
+    every output written once at the storage dtype."""
+    from srk import ops
+    from srk import _lib as L
+    g = torch.Generator(device=dev).manual_seed(7)
+    NSET = 4
+
+    def act(n, h, w, c, scale=1.0):
+        t = torch.zeros((n, h + 2, w + 2, c), dtype=torch.bfloat16, device=dev)
+        t[:, 1:-1, 1:-1] = (torch.randn((n, h, w, c), generator=g, device=dev) * scale).bfloat16()
+        return t
+
+    H = LR_HW
+    w64 = torch.randn((64, 64, 3, 3), generator=g, device=dev) / 24
+    wup = torch.randn((256, 64, 3, 3), generator=g, device=dev) / 24
+    bias = torch.randn((64,), generator=g, device=dev) * 0.1
+    gamma, beta = torch.rand((64,), generator=g, device=dev) + 0.5, torch.randn((64,), generator=g, device=dev) * 0.1
+    alpha = torch.full((1,), 0.25, device=dev)
+    xs = [act(B, H, H, 64) for _ in range(NSET)]
+    ds = [act(B, H, H, 64, 1e-3) for _ in range(NSET)]
+    sums = [torch.empty((2, 64), dtype=torch.float32, device=dev) for _ in range(NSET)]
+    ys, stats = [], []
+    for x, sm in zip(xs, sums):
+        y, _ = ops.conv_fprop(x, False, w64, bias, L.ACT_NONE, None, None, 0, False, torch.bfloat16, bn_sums=sm)
+        _, st = ops.bn_forward(y, gamma, beta, None, None, None, True, 1e-5, 0.1, alpha, None, sums=sm)
+        ys.append(y)
+        stats.append(st)
+    P = B * H * H
+    conv_flop = 2.0 * P * 64 * 64 * 9
+    act_bytes = B * (H + 2) * (H + 2) * 64 * 2
+    out = []
+
+    def add(name, bound, work, launches, per_step, note=None):
+        ms = _time_replayed(launches)
+        if bound == "tensor":
+            ach, peak, unit = work / (ms * 1e-3) / 1e12, pk["tf_burst"], "TFLOP/s"
+        else:
+            ach, peak, unit = work / (ms * 1e-3) / 1e9, pk["hbm_gbs"], "GB/s"
+        rec = {"kernel": name, "bound": bound, "achieved": round(ach, 2), "peak": peak, "unit": unit,
+               "frac": round(ach / peak, 4), "avg_ms": round(ms, 4), "launches_per_step": per_step,
+               ("algorithmic_flops_per_launch" if bound == "tensor" else "algorithmic_bytes_per_launch"): work,
+               "traffic": ncu_traffic(name)}
+        if note:
+            rec["note"] = note
+        out.append(rec)
+
+    add("conv3x3_c64_fprop+bn_stats", "tensor", conv_flop,
+        [lambda x=x, sm=sm: ops.conv_fprop(x, False, w64, bias, L.ACT_NONE, None, None, 0, False, torch.bfloat16, bn_sums=sm)
+         for x, sm in zip(xs, sums)], 33, "fold::conv3x3_fold_tc_kernel<kStats>: the variant every trunk conv of the step runs")
+    add("conv3x3_c64_dgrad+bn_bwd_reduce", "tensor", conv_flop,
+        [lambda d=d, y=y, st=st: ops.conv_dgrad_bnred(d, w64, y, st, gamma, beta, alpha) for d, y, st in zip(ds, ys, stats)], 16)
+    add("conv3x3_c64_dgrad+residual", "tensor", conv_flop,
+        [lambda d=d, x=x: ops.conv_dgrad(d, False, w64, x, torch.bfloat16) for d, x in zip(ds, xs)], 17)
+    add("conv3x3_c64_wgrad", "tensor", conv_flop,
+        [lambda x=x, d=d: ops.conv_wgrad(x, False, d, False, w64, True) for x, d in zip(xs, ds)], 33,
+        "wgrad3x3_tc_kernel + wgrad_fold_kernel (two launches)")
+    x128 = [act(B, 2 * H, 2 * H, 64) for _ in range(2)]
+    add("conv3x3_64to256_pixelshuffle_prelu@%dx%d" % (2 * H, 2 * H), "tensor", 2.0 * B * 4 * H * H * 64 * 256 * 9,
+        [lambda x=x: ops.conv_fprop(x, False, wup, None, L.ACT_PRELU, alpha, None, 2, False, torch.bfloat16) for x in x128], 1)
+    del x128
+    add("bn_apply_train+prelu", "hbm", 2.0 * act_bytes,
+        [lambda y=y, sm=sm: ops.bn_forward(y, gamma, beta, None, None, None, True, 1e-5, 0.1, alpha, None, sums=sm)
+         for y, sm in zip(ys, sums)], 16)
+    add("bn_apply_train+residual", "hbm", 3.0 * act_bytes,
+        [lambda y=y, sm=sm, x=x: ops.bn_forward(y, gamma, beta, None, None, None, True, 1e-5, 0.1, None, x, sums=sm)
+         for y, sm, x in zip(ys, sums, xs)], 17)
+    add("bn_bwd_reduce+bn_bwd_apply", "hbm", 5.0 * act_bytes,
+        [lambda d=d, y=y, st=st: ops.bn_backward(d, y, st, gamma, beta, None, True) for d, y, st in zip(ds, ys, stats)], 17,
+        "two launches: reduce (2 reads) + apply (2 reads, 1 write)")
+    del xs, ds, ys
+    # loss / metric kernels on the step's image shapes
+    from src.loss import get_loss_function
+    from src.metrics import psnr_ssim_sums
+    HR = LR_HW * SCALE
+    imgs = [(torch.rand((B, 3, HR, HR), generator=g, device=dev), torch.rand((B, 3, HR, HR), generator=g, device=dev))
+            for _ in range(NSET)]
+    img_bytes = B * 3 * HR * HR * 4
+    crit = get_loss_function("nlpd", dev)
+
+    def nlpd_fb(sr, hr):
+        sr = sr.detach().requires_grad_(True)
+        crit(sr, hr).backward()
+    add("nlpd_fwd+bwd", "hbm", 3.0 * img_bytes, [lambda a=a, b=b: nlpd_fb(a, b) for a, b in imgs], 1,
+        "13 launches; algorithmic bytes = sr + hr read, grad written (the pyramid intermediates are extra traffic)")
+    mae = get_loss_function("mae", dev)
+
+    def mae_fb(sr, hr):
+        sr = sr.detach().requires_grad_(True)
+        mae(sr, hr).backward()
+    add("l1_fwd+bwd", "hbm", 5.0 * img_bytes, [lambda a=a, b=b: mae_fb(a, b) for a, b in imgs], 0,
+        "forward (2 reads) + backward (2 reads, 1 write); used by config C3")
+    sse = torch.empty((B,), dtype=torch.float64, device=dev)
+    st = ops.stream_ptr
+    add("psnr_sse", "hbm", 2.0 * img_bytes,
+        [lambda a=a, b=b: L.call("srk_psnr_sse", a.data_ptr(), b.data_ptr(), B, 3 * HR * HR, 1, sse.data_ptr(), st())
+         for a, b in imgs], 0, "evaluation path (config C4)")
+    add("ssim", "hbm", 2.0 * img_bytes,
+        [lambda a=a, b=b: L.call("srk_ssim", a.data_ptr(), b.data_ptr(), B, 3, HR, HR, 1, sse.data_ptr(), st())
+         for a, b in imgs], 0, "evaluation path; fp32-FMA bound (110 FMA per pixel-channel), HBM fraction for reference")
+    return out
+
+
+def ncu_traffic(kernel=None):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` summaries
+    (profiles/r2_ncu_kernels.json: {kernel name: {...}}); None when that kernel has no capture."""
+    p = os.path.join(ROOT, "profiles", "r2_ncu_kernels.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    rec = d.get(kernel) if kernel else None
+    return None if rec is None else rec.get("dram_bytes")
+
+
 def run_srk(args):
     import srk
     from srk import dp, ops
-    from srk import _lib as L
+    from srk.trainer import GraphStep
     from src.loss import get_loss_function
     from src.models import get_model
     import torch.distributed as dist
@@ -216,14 +384,17 @@ def run_srk(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     srk.set_compute_dtype(args.dtype)
-    srk.set_overlap_wgrad(os.environ.get("SRK_OVERLAP_WGRAD", "1") != "0")   # weight gradients on the side stream
     torch.manual_seed(0)
     model = get_model(ARCH, SCALE, dev)
     dp.broadcast_parameters(model)
     model.train()
     crit = get_loss_function(LOSS, dev)
-    opt = srk.optim.Adam(model.parameters(), lr=4e-4, betas=(0.5, 0.999))
     averager = dp.GradAverager(model.parameters()) if world > 1 else None
+    # the step object train.py uses: forward + loss + backward + all-reduce + Adam + weight re-pack, captured into ONE
+    # CUDA graph after the eager warm-up steps (NCCL all-reduce included) and replayed
+    trainer = GraphStep(model, crit, lr=4e-4, betas=(0.5, 0.999), averager=averager, use_graph=not args.no_graph,
+                        warmup=max(args.warmup - 1, 2),
+                        overlap_wgrad=os.environ.get("SRK_OVERLAP_WGRAD", "1") != "0")
 
     from src.dataset import synthetic_pair
     B = args.batch
@@ -231,53 +402,21 @@ def run_srk(args):
     lr_pin, hr_pin = lr_h.pin_memory(), hr_h.pin_memory()
     lr_d, hr_d = lr_pin.to(dev), hr_pin.to(dev)
 
-    def fwd_bwd(lr, hr):
-        ops.begin_step(device=dev)   # one memset serves every zero-initialised scratch tensor of the step
-        opt.zero_grad()
-        loss = crit(model(lr), hr)
-        loss.backward()
-        if averager is not None:
-            averager.pack()          # gradients -> flat fp32 buckets / world
-        return loss
-
-    def finish():
-        if averager is not None:
-            averager.unpack()
-        opt.step()
-        ops.repack_all()             # all weight packs of the next step in one launch
-
-    def step(lr, hr):
-        loss = fwd_bwd(lr, hr)
-        if averager is not None:
-            averager.all_reduce()    # NCCL over NVLink, one collective per bucket
-        finish()
-        return loss
-
-    # The step is captured once into two CUDA graphs (forward + loss + backward + weight re-pack | Adam) and
-    # replayed: same kernels, same work, no per-launch host overhead.  The NCCL all-reduce between them is
-    # launched eagerly.
-    use_graph = not args.no_graph
-    lr_s, hr_s = lr_d.clone(), hr_d.clone()
-    g1 = g2 = loss_s = None
-
-    def run_step():
-        if g1 is None:
-            return step(lr_s, hr_s)
-        g1.replay()
-        if averager is not None:
-            averager.all_reduce()
-        g2.replay()
-        return loss_s
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    for _ in range(max(args.warmup, 3)):      # eager steps, then the capture (inside the trainer), then one replay
+        trainer(lr_d, hr_d)
+    barrier()
+    trainer(lr_d, hr_d)
+    graphed = trainer.static_inputs(lr_d, hr_d) is not None
+
     # e2e: every step's LR/HR batch comes from pinned host memory.  The copy of step i+1 is issued on a copy stream
-    # while step i computes (staging buffers), so the step only pays a device-to-device hand-over.
+    # while step i computes (staging buffers); the step then takes it with a device-to-device hand-over.
     copy_stream = torch.cuda.Stream()
-    lr_n, hr_n = torch.empty_like(lr_s), torch.empty_like(hr_s)
+    lr_n, hr_n = torch.empty_like(lr_d), torch.empty_like(hr_d)
     ev_h2d, ev_taken = torch.cuda.Event(), torch.cuda.Event()
 
     def prefetch():
@@ -298,14 +437,25 @@ def run_srk(args):
         for i in range(nsteps):
             if e2e:
                 main.wait_event(ev_h2d)
-                lr_s.copy_(lr_n, non_blocking=True)
-                hr_s.copy_(hr_n, non_blocking=True)
-                ev_taken.record(main)
-                if i + 1 < nsteps:
-                    prefetch()
-                run_step().item()
+                if graphed:
+                    s_lr, s_hr = trainer.static_inputs(lr_d, hr_d)
+                    s_lr.copy_(lr_n, non_blocking=True)
+                    s_hr.copy_(hr_n, non_blocking=True)
+                    ev_taken.record(main)
+                    if i + 1 < nsteps:
+                        prefetch()
+                    trainer.replay(lr_d, hr_d).item()
+                else:
+                    lr_d.copy_(lr_n, non_blocking=True)
+                    hr_d.copy_(hr_n, non_blocking=True)
+                    ev_taken.record(main)
+                    if i + 1 < nsteps:
+                        prefetch()
+                    trainer(lr_d, hr_d).item()
+            elif graphed:
+                trainer.replay(lr_d, hr_d)
             else:
-                run_step()
+                trainer(lr_d, hr_d)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -315,61 +465,12 @@ def run_srk(args):
             ms = float(t.item())
         return ms / nsteps
 
-    c0 = L.launch_calls
-    step(lr_s, hr_s)                      # eager: also counts the libsrk launches of one step
-    launches = L.launch_calls - c0
-    for _ in range(max(args.warmup - 1, 2)):
-        step(lr_s, hr_s)
-    if use_graph:
-        barrier()
-        ops.repack_all()                  # packs are current; inside the graphs only finish() refreshes them
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            g1 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g1, stream=side, capture_error_mode="thread_local"):
-                loss_s = fwd_bwd(lr_s, hr_s)
-            g2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g2, stream=side, pool=g1.pool(), capture_error_mode="thread_local"):
-                finish()
-        torch.cuda.current_stream().wait_stream(side)
-        barrier()
-        run_step()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms_step = timed(args.steps, e2e=False)
     clocks = sampler.stop() if sampler else None
     ms_e2e = timed(max(2, min(args.steps, 20)), e2e=True)
-    loss_value = float(run_step().item())
-
-    # dominant kernel (3x3 64->64 conv forward at the step's own shape): its launches inside one eager step are
-    # counted, and its duration is measured with CUDA events on the launching stream around 20 back-to-back
-    # launches replayed from a CUDA graph (no host launch gaps inside the bracket)
-    ops.kernel_timer = ops.KernelTimer(lambda k: k[0] == "conv_fprop" and k[1:5] == (64, 64, 3, 0))
-    step(lr_s, hr_s)
-    torch.cuda.synchronize()
-    kt = ops.kernel_timer.summary()
-    ops.kernel_timer = None
-    kern_ms = None
-    if kt and ARCH == "RESNET":
-        blk = model.res_blocks[0]
-        xa = torch.zeros((B, LR_HW + 2, LR_HW + 2, 64), dtype=ops.cfg.compute_dtype, device=dev)
-        one = lambda: ops.conv_fprop(xa, False, blk.conv1.weight, blk.conv1.bias, 0, None, None, 0, False, xa.dtype)
-        one()
-        torch.cuda.synchronize()
-        side = torch.cuda.Stream()
-        with torch.cuda.stream(side):
-            kg = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(kg, stream=side):
-                for _ in range(20):
-                    one()
-            kg.replay()
-            torch.cuda.synchronize()
-            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            k0.record(side)
-            kg.replay()
-            k1.record(side)
-            torch.cuda.synchronize()
-            kern_ms = k0.elapsed_time(k1) / 20
+    loss_value = float((trainer.replay(lr_d, hr_d) if graphed else trainer(lr_d, hr_d)).item())
+    launches = trainer.launches_per_step or 0
 
     if rank != 0:
         if world > 1:
@@ -377,19 +478,19 @@ def run_srk(args):
         return
     pk = peaks()
     value = world * B / (ms_step * 1e-3)
+    roofs = None
+    if ARCH == "RESNET" and args.dtype == "bf16" and not args.no_rooflines:
+        del trainer
+        torch.cuda.empty_cache()
+        roofs = kernel_rooflines(B, dev, pk)
     roof = None
-    if kt and kern_ms is not None:
-        key, (_, count) = max(kt.items(), key=lambda kv: kv[1][0] * kv[1][1])
-        avg_ms = kern_ms
-        n, h, w = key[5:8]
-        flops = 2.0 * n * h * w * 64 * 64 * 9
-        ach = flops / (avg_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "conv3x3_c64_fprop(%s)" % ("tcgen05" if key[8] else "cuda-core"),
-                "achieved": round(ach, 2), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": round(ach / pk["tf_sustained"], 4),
-                "traffic": (ncu_traffic() or {}).get("bytes"), "traffic_detail": ncu_traffic(),
-                "algorithmic_flops_per_launch": flops, "avg_ms": round(avg_ms, 4),
-                "launches_per_step": count, "peak_source": pk["src"] + " bf16 sustained"}
+    if roofs:
+        r0 = roofs[0]
+        roof = {"bound": r0["bound"], "kernel": r0["kernel"], "achieved": r0["achieved"], "peak": r0["peak"],
+                "unit": r0["unit"], "frac": r0["frac"], "traffic": r0["traffic"], "avg_ms": r0["avg_ms"],
+                "launches_per_step": r0["launches_per_step"],
+                "algorithmic_flops_per_launch": r0["algorithmic_flops_per_launch"],
+                "peak_source": pk["src"] + " bf16 burst (kernel timed alone, 4 rotating operand sets > L2)"}
     step_tf = world * B * FWD_BWD_GFLOP_PER_IMG / (ms_step * 1e-3) / 1e3
     line = {"metric": "sr_train_images_per_sec", "value": round(value, 2), "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True,
@@ -397,12 +498,12 @@ def run_srk(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": "dp%d" % world,
                        "l2": "working set (>2 GB of activations per step) exceeds the 126 MB L2; no explicit flush",
-                       "cuda_graph": bool(g1 is not None), "final_loss": round(loss_value, 5),
-                       "step_tflops": round(step_tf, 2),
+                       "cuda_graph": bool(graphed), "nccl_in_graph": bool(graphed and world > 1),
+                       "final_loss": round(loss_value, 5), "step_tflops": round(step_tf, 2),
                        "step_frac_of_bf16_sustained": round(step_tf / (world * pk["tf_sustained"]), 4)},
             "e2e": {"value": round(world * B / (ms_e2e * 1e-3), 2), "unit": "images/s",
                     "h2d_bytes_per_step": int(lr_pin.numel() * 4 + hr_pin.numel() * 4), "d2h_bytes_per_step": 4},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "rooflines": roofs}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
     print(json.dumps(line), flush=True)
@@ -506,8 +607,10 @@ def main():
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS) + ["C4"],
                     help="BASELINE.json config (headline: C2; C4 = sharded inference + metrics)")
     ap.add_argument("--eval-images", type=int, default=1250, help="--config C4: images per GPU (10 000 / 8)")
-    ap.add_argument("--cpu-batch", type=int, default=4, help="--impl reference: images per CPU step")
+    ap.add_argument("--cpu-batch", type=int, default=0,
+                    help="--impl reference: images per CPU step (default: the config's batch when it fits the time budget)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-rooflines", action="store_true", help="skip the per-kernel roofline measurements")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.config == "C4":

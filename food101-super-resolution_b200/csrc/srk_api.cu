@@ -19,15 +19,16 @@ void set_error(const char* fmt, ...) {
 // srk_conv_simt.cu
 int conv_fprop_simt_launch(const srk_tensor* x, const srk_tensor* y, const float* w, int cout, int r,
                            int s, const float* bias, int act, const float* alpha,
-                           const srk_tensor* residual, int shuffle, cudaStream_t st);
+                           const srk_tensor* residual, int shuffle, cudaStream_t st, void* zsave);
 int conv_wgrad_simt_launch(const srk_tensor* x, const srk_tensor* dy, float* dw, float* db, int r,
-                           int s, cudaStream_t st);
+                           int s, void* workspace, int accumulate, cudaStream_t st);
+int64_t conv_wgrad_simt_workspace(const srk_tensor* x, const srk_tensor* dy, int r, int s);
 // srk_conv_tc.cu
 bool conv_tc_shape_ok(int cin, int cout, int r, int s, int dtype, int shuffle);
 int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout,
                          int r, int s, const float* bias, int act, const float* alpha,
                          const srk_tensor* residual, int shuffle, float* stats_sum, float* stats_sumsq,
-                         void* workspace, cudaStream_t st);
+                         void* workspace, cudaStream_t st, void* reduce_ws, void* zsave);
 int64_t conv_fprop_tc_workspace(const srk_tensor* x);
 bool conv_smalln_tc_ok(const srk_tensor* x, const srk_tensor* y, int cout, int r, int s);
 int conv_smalln_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout, int r,
@@ -40,7 +41,8 @@ int conv_wgrad_tc_launch(const srk_tensor* x, const srk_tensor* dy, float* dw, f
 int64_t conv_rgb_workspace_bytes(int k);
 int conv_rgb_tc_run(const srk_tensor* t3, const srk_tensor* y, const void* w_packed, const float* bias, int act,
                     const float* alpha, const srk_tensor* t64, float* dw, float* db, float* db3, int rgb_out, int k,
-                    void* workspace, cudaStream_t st, const srk_tensor* dz_ps, const float* ps_alpha, float* ps_dalpha);
+                    void* workspace, cudaStream_t st, const srk_tensor* dz_ps, const float* ps_alpha, float* ps_dalpha,
+                    void* zsave, const void* ps_zsave);
 
 static bool tensor_ok(const srk_tensor* t) {
   if (t == nullptr || t->data == nullptr) return false;
@@ -72,12 +74,15 @@ extern "C" int64_t srk_conv_fprop_workspace_bytes(const srk_tensor* x, int pack_
 extern "C" int srk_conv_fprop(const srk_tensor* x, const srk_tensor* y, const void* w_packed,
                               int pack_kind, int cout, int r, int s, const float* bias, int act,
                               const float* alpha, const srk_tensor* residual, int pixel_shuffle,
-                              int impl, float* bn_sum, float* bn_sumsq, void* workspace, void* stream) {
-  SRK_REQUIRE((bn_sum == nullptr) == (bn_sumsq == nullptr), "srk_conv_fprop: bn_sum and bn_sumsq go together");
+                              int impl, float* bn_sums, void* reduce_ws, const srk_tensor* prelu_z,
+                              void* workspace, void* stream) {
+  float* bn_sum = bn_sums;
+  float* bn_sumsq = bn_sums ? bn_sums + cout : nullptr;
+  SRK_REQUIRE(tensor_ok(x) && tensor_ok(y), "srk_conv_fprop: bad x / y tensor");
   SRK_REQUIRE(bn_sum == nullptr || (act == SRK_ACT_NONE && residual == nullptr && pixel_shuffle == 0 &&
                                     y->layout == SRK_LAYOUT_ACT),
               "srk_conv_fprop: BN statistics are taken of a plain conv output in the ACT layout");
-  SRK_REQUIRE(tensor_ok(x) && tensor_ok(y), "srk_conv_fprop: bad x / y tensor");
+  SRK_REQUIRE(bn_sum == nullptr || reduce_ws != nullptr, "srk_conv_fprop: bn_sums needs reduce_ws");
   SRK_REQUIRE(w_packed != nullptr, "srk_conv_fprop: null weights");
   SRK_REQUIRE(r == s && (r & 1) == 1 && r >= 1 && r <= 11, "srk_conv_fprop: odd square kernels only (got %dx%d)", r, s);
   SRK_REQUIRE(act == SRK_ACT_NONE || act == SRK_ACT_RELU || act == SRK_ACT_PRELU, "srk_conv_fprop: bad act %d", act);
@@ -93,6 +98,13 @@ extern "C" int srk_conv_fprop(const srk_tensor* x, const srk_tensor* y, const vo
   if (residual) {
     SRK_REQUIRE(tensor_ok(residual) && same_geometry(residual, y) && residual->layout == y->layout,
                 "srk_conv_fprop: residual must match the output geometry and layout");
+  }
+  void* zsave = nullptr;
+  if (prelu_z) {
+    SRK_REQUIRE(act == SRK_ACT_PRELU && tensor_ok(prelu_z) && same_geometry(prelu_z, y) && prelu_z->layout == y->layout &&
+                    prelu_z->dtype == y->dtype && y->layout == SRK_LAYOUT_ACT,
+                "srk_conv_fprop: prelu_z must match an ACT output of a PReLU conv");
+    zsave = prelu_z->data;
   }
   if (pack_kind == SRK_PACK_FPROP_TC_N8) {
     SRK_REQUIRE(conv_smalln_tc_ok(x, y, cout, r, s) && act == SRK_ACT_NONE && residual == nullptr && pixel_shuffle == 0 &&
@@ -113,20 +125,20 @@ extern "C" int srk_conv_fprop(const srk_tensor* x, const srk_tensor* y, const vo
                 "srk_conv_fprop: tcgen05 path needs bf16 ACT tensors");
     SRK_REQUIRE(conv_tc_shape_ok(x->c, cout, r, s, SRK_BF16, pixel_shuffle),
                 "srk_conv_fprop: shape Cin=%d Cout=%d %dx%d not supported by the tcgen05 path", x->c, cout, r, s);
-    if (bn_sum != nullptr && x->c != 64) {  // the fused statistics cover single-pass convs only
+    if (bn_sum != nullptr && (x->c != 64 || cout != 64)) {  // the fused statistics cover the single-pass 64 -> 64 conv only
       if (conv_fprop_tc_launch(x, y, w_packed, cout, r, s, bias, act, alpha, residual, pixel_shuffle, nullptr,
-                               nullptr, workspace, st))
+                               nullptr, workspace, st, nullptr, zsave))
         return 1;
-      return srk_bn_stats(y, bn_sum, bn_sumsq, stream);
+      return srk_bn_stats(y, bn_sums, reduce_ws, stream);
     }
     return conv_fprop_tc_launch(x, y, w_packed, cout, r, s, bias, act, alpha, residual, pixel_shuffle, bn_sum,
-                                bn_sumsq, workspace, st);
+                                bn_sumsq, workspace, st, reduce_ws, zsave);
   }
   SRK_REQUIRE(impl == SRK_IMPL_SIMT && simt_kind, "srk_conv_fprop: CUDA-core path needs SRK_PACK_*_SIMT weights");
   if (conv_fprop_simt_launch(x, y, (const float*)w_packed, cout, r, s, bias, act, alpha, residual,
-                             pixel_shuffle, st))
+                             pixel_shuffle, st, zsave))
     return 1;
-  return bn_sum ? srk_bn_stats(y, bn_sum, bn_sumsq, stream) : 0;
+  return bn_sum ? srk_bn_stats(y, bn_sums, reduce_ws, stream) : 0;
 }
 
 // Data gradient of a 3x3 64 -> 64 conv with the BatchNorm-backward reduction of the layer BELOW fused into the
@@ -137,8 +149,9 @@ extern "C" int srk_conv_fprop(const srk_tensor* x, const srk_tensor* y, const vo
 extern "C" int srk_conv_dgrad_bnred(const srk_tensor* dz, const srk_tensor* dx, const void* w_packed_dgrad,
                                     const srk_tensor* z, const float* mean, const float* invstd, const float* gamma,
                                     const float* beta, const float* alpha, float* sum_g, float* sum_gz, float* dalpha,
-                                    void* stream) {
+                                    void* reduce_ws, void* stream) {
   SRK_REQUIRE(tensor_ok(dz) && tensor_ok(dx) && tensor_ok(z) && w_packed_dgrad, "srk_conv_dgrad_bnred: bad tensors");
+  SRK_REQUIRE(reduce_ws != nullptr, "srk_conv_dgrad_bnred: reduce_ws is required");
   SRK_REQUIRE(mean && invstd && gamma && beta && sum_g && sum_gz, "srk_conv_dgrad_bnred: null statistics");
   SRK_REQUIRE(alpha == nullptr || dalpha != nullptr, "srk_conv_dgrad_bnred: dalpha is required with alpha");
   if (!(dz->layout == SRK_LAYOUT_ACT && dx->layout == SRK_LAYOUT_ACT && dz->dtype == SRK_BF16 && dx->dtype == SRK_BF16 &&
@@ -146,7 +159,7 @@ extern "C" int srk_conv_dgrad_bnred(const srk_tensor* dz, const srk_tensor* dx, 
     return 2;
   BnRedArgs br = {z, mean, invstd, gamma, beta, alpha, sum_g, sum_gz, dalpha};
   const int rc = conv_fprop_fold_launch(dz, dx, w_packed_dgrad, 64, nullptr, SRK_ACT_NONE, nullptr, nullptr, 0, nullptr,
-                                        nullptr, nullptr, 0, (cudaStream_t)stream, &br);
+                                        nullptr, nullptr, 0, (cudaStream_t)stream, &br, reduce_ws, nullptr);
   return rc < 0 ? 2 : rc;
 }
 
@@ -155,7 +168,7 @@ extern "C" int64_t srk_conv_wgrad_workspace_bytes(const srk_tensor* x, const srk
   if (x == nullptr || dy == nullptr) return -1;
   if (impl == SRK_IMPL_TC || (impl == SRK_IMPL_AUTO && conv_wgrad_tc_shape_ok(x, dy, r, s)))
     return conv_wgrad_tc_workspace(x, dy, r, s);
-  return 0;
+  return conv_wgrad_simt_workspace(x, dy, r, s);
 }
 
 extern "C" int srk_conv_wgrad(const srk_tensor* x, const srk_tensor* dy, float* dw, float* db, int r, int s,
@@ -172,21 +185,21 @@ extern "C" int srk_conv_wgrad(const srk_tensor* x, const srk_tensor* dy, float* 
     return conv_wgrad_tc_launch(x, dy, dw, db, r, s, workspace, accumulate, perm_shuffle, st);
   }
   SRK_REQUIRE(!perm_shuffle, "srk_conv_wgrad: sub-pixel-major dY is a tcgen05-path layout");
-  if (!accumulate) {  // the CUDA-core kernel adds with atomics
-    cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)dy->c * x->c * r * s, st);
-    if (db) cudaMemsetAsync(db, 0, sizeof(float) * (size_t)dy->c, st);
-  }
-  return conv_wgrad_simt_launch(x, dy, dw, db, r, s, st);
+  return conv_wgrad_simt_launch(x, dy, dw, db, r, s, workspace, accumulate, st);
 }
 
 extern "C" int64_t srk_conv_rgb_workspace_bytes(int k) { return (k == 9 || k == 5) ? conv_rgb_workspace_bytes(k) : -1; }
 
 extern "C" int srk_conv_rgb_fprop(const srk_tensor* img3, const srk_tensor* y, const void* w_packed, int k,
-                                  const float* bias, int act, const float* alpha, void* stream) {
+                                  const float* bias, int act, const float* alpha, const srk_tensor* prelu_z,
+                                  void* stream) {
   SRK_REQUIRE(tensor_ok(img3) && tensor_ok(y) && w_packed != nullptr, "srk_conv_rgb_fprop: bad arguments");
   SRK_REQUIRE(act != SRK_ACT_PRELU || alpha != nullptr, "srk_conv_rgb_fprop: PReLU needs alpha");
+  SRK_REQUIRE(prelu_z == nullptr || (act == SRK_ACT_PRELU && tensor_ok(prelu_z) && same_geometry(prelu_z, y) &&
+                                     prelu_z->layout == SRK_LAYOUT_ACT && prelu_z->dtype == SRK_BF16),
+              "srk_conv_rgb_fprop: prelu_z must match the bf16 ACT output of a PReLU conv");
   return conv_rgb_tc_run(img3, y, w_packed, bias, act, alpha, nullptr, nullptr, nullptr, nullptr, 0, k, nullptr,
-                         (cudaStream_t)stream, nullptr, nullptr, nullptr);
+                         (cudaStream_t)stream, nullptr, nullptr, nullptr, prelu_z ? prelu_z->data : nullptr, nullptr);
 }
 
 extern "C" int srk_conv_rgb_bwd(const srk_tensor* img3, const srk_tensor* t64, const void* w_packed,
@@ -196,7 +209,8 @@ extern "C" int srk_conv_rgb_bwd(const srk_tensor* img3, const srk_tensor* t64, c
   SRK_REQUIRE(dx == nullptr || (tensor_ok(dx) && w_packed != nullptr && rgb_out == 1),
               "srk_conv_rgb_bwd: dx needs rgb_out = 1 and SRK_PACK_RGBOUT_DGRAD_TC weights");
   return conv_rgb_tc_run(img3, dx, w_packed, nullptr, SRK_ACT_NONE, nullptr, t64, dw, rgb_out ? nullptr : db,
-                         rgb_out ? db : nullptr, rgb_out, k, workspace, (cudaStream_t)stream, nullptr, nullptr, nullptr);
+                         rgb_out ? db : nullptr, rgb_out, k, workspace, (cudaStream_t)stream, nullptr, nullptr, nullptr,
+                         nullptr, nullptr);
 }
 
 // Backward of the 64 -> 3 output conv fused with the PReLU + PixelShuffle(2) backward of the upsample stage below it
@@ -205,11 +219,14 @@ extern "C" int srk_conv_rgb_bwd(const srk_tensor* img3, const srk_tensor* t64, c
 // dz_ps = gradient of the 64 -> 256 conv output, bf16 ACT [N, 256, H/2, W/2] with channels SUB-PIXEL-MAJOR
 // (sub * 64 + c instead of 4c + sub): feed it to srk_conv_fprop with SRK_PACK_DGRAD_TC weights packed with
 // pixel_shuffle = 2 and to srk_conv_wgrad with perm_shuffle = 1.
-extern "C" int srk_conv_rgbout_bwd_unshuffle(const srk_tensor* dy_img, const srk_tensor* t64, const void* w_packed,
-                                             const srk_tensor* dz_ps, float* dw, float* db, const float* alpha,
-                                             float* dalpha, int k, void* workspace, void* stream) {
+extern "C" int srk_conv_rgbout_bwd_unshuffle(const srk_tensor* dy_img, const srk_tensor* t64, const srk_tensor* t64_z,
+                                             const void* w_packed, const srk_tensor* dz_ps, float* dw, float* db,
+                                             const float* alpha, float* dalpha, int k, void* workspace, void* stream) {
   SRK_REQUIRE(tensor_ok(dy_img) && tensor_ok(t64) && tensor_ok(dz_ps) && dw && workspace && w_packed && alpha,
               "srk_conv_rgbout_bwd_unshuffle: bad arguments");
+  SRK_REQUIRE(t64_z == nullptr || (tensor_ok(t64_z) && same_geometry(t64_z, t64) && t64_z->layout == SRK_LAYOUT_ACT &&
+                                   t64_z->dtype == SRK_BF16),
+              "srk_conv_rgbout_bwd_unshuffle: t64_z must match t64 (bf16 ACT)");
   return conv_rgb_tc_run(dy_img, nullptr, w_packed, nullptr, SRK_ACT_NONE, nullptr, t64, dw, nullptr, db, 1, k, workspace,
-                         (cudaStream_t)stream, dz_ps, alpha, dalpha);
+                         (cudaStream_t)stream, dz_ps, alpha, dalpha, nullptr, t64_z ? t64_z->data : nullptr);
 }

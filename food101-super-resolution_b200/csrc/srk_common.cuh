@@ -119,6 +119,92 @@ __device__ __forceinline__ double block_sum_d(double v, double* smem32) {
 
 constexpr int kNumSMs = 148;  // B200
 
+// ---- deterministic cross-block reductions ------------------------------------------------------------------
+// Float atomics make a sum depend on the order in which blocks happen to retire; two runs of the same training
+// step then differ in the last bits of every BatchNorm statistic and, amplified by bf16 rounding, by percents
+// on a gradient.  Every cross-block reduction of the library therefore goes through ordered_fold(): each block
+// stores its partial row, takes a ticket, and the block that draws the LAST ticket sums all rows in block-index
+// order (which block is last does not matter: the order of the additions is fixed by the code alone).
+//
+// Workspace (caller-owned, srk_reduce_workspace_bytes() bytes, zero-filled once when it is allocated, one per
+// stream on which libsrk kernels may run concurrently):  [kRedTickets x u32 tickets][float partial rows].
+// Tickets reset themselves, partial rows need no initialisation.
+constexpr int kRedTickets = 4096;
+constexpr size_t kRedWsBytes = (size_t)8 << 20;
+constexpr size_t kRedPartialFloats = (kRedWsBytes - kRedTickets * sizeof(unsigned)) / sizeof(float);
+inline unsigned* red_tickets(void* ws) { return reinterpret_cast<unsigned*>(ws); }
+inline float* red_partials(void* ws) { return reinterpret_cast<float*>(reinterpret_cast<unsigned*>(ws) + kRedTickets); }
+
+// Called by the T threads `tid` = 0..T-1 of a block (a whole block with sync = __syncthreads, or a warp-aligned
+// subset with a named barrier).  vals[NV]: this block's partial sums in shared memory, complete and visible to the
+// T threads.  part: rows of this reduction [nblk][4 * ceil(NV / 4)] floats; bidx in [0, nblk): this block's row.
+// scratch: T float4 of shared memory.  finish(i, sum) is called once per value by the last-arriving block.
+template <typename Sync, typename Finish>
+__device__ __forceinline__ void ordered_fold(const float* vals, int NV, unsigned* ticket, int nblk, int bidx,
+                                             float* part, float4* scratch, int tid, int T, Sync sync, Finish finish) {
+  const int NV4 = (NV + 3) >> 2;
+  float4* prow = reinterpret_cast<float4*>(part) + (size_t)bidx * NV4;
+  for (int i = tid; i < NV4; i += T) {
+    float4 v;
+    v.x = vals[4 * i];
+    v.y = 4 * i + 1 < NV ? vals[4 * i + 1] : 0.f;
+    v.z = 4 * i + 2 < NV ? vals[4 * i + 2] : 0.f;
+    v.w = 4 * i + 3 < NV ? vals[4 * i + 3] : 0.f;
+    __stcg(prow + i, v);
+  }
+  __threadfence();
+  sync();
+  int* flag = reinterpret_cast<int*>(scratch);
+  if (tid == 0) {
+    const unsigned k = atomicAdd(ticket, 1u);
+    const int last = (k == (unsigned)nblk - 1u);
+    if (last) *ticket = 0u;     // everybody has arrived: ready for the next launch that uses this ticket
+    flag[0] = last;
+  }
+  sync();
+  const bool last = flag[0] != 0;
+  sync();                       // flag[0] is about to be overwritten as scratch
+  if (!last) return;
+  __threadfence();
+  for (int c0 = 0; c0 < NV4; c0 += T) {
+    const int ncol = NV4 - c0 < T ? NV4 - c0 : T;
+    const int G = T / ncol;     // row groups: thread (g, col) sums rows g, g + G, ... in that order
+    const int col = tid % ncol, g = tid / ncol;
+    if (g < G) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* p = reinterpret_cast<const float4*>(part) + c0 + col;
+#pragma unroll 8
+      for (int b = g; b < nblk; b += G) {
+        const float4 v = __ldcg(p + (size_t)b * NV4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      scratch[g * ncol + col] = acc;
+    }
+    sync();
+    // fixed binary tree over the row groups
+    int top = 1;
+    while (top < G) top <<= 1;
+    for (int h = top >> 1; h >= 1; h >>= 1) {
+      if (g < h && g + h < G) {
+        float4 a = scratch[g * ncol + col];
+        const float4 b = scratch[(g + h) * ncol + col];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        scratch[g * ncol + col] = a;
+      }
+      sync();
+    }
+    if (tid < ncol) {
+      const float4 s = scratch[tid];
+      const int i = 4 * (c0 + tid);
+      finish(i, s.x);
+      if (i + 1 < NV) finish(i + 1, s.y);
+      if (i + 2 < NV) finish(i + 2, s.z);
+      if (i + 3 < NV) finish(i + 3, s.w);
+    }
+    sync();
+  }
+}
+
 // ---- programmatic dependent launch ---------------------------------------------------------------------
 // A training step is ~270 launches of 7-60 us each, so the gap between two kernels of a stream (launch latency,
 // the tail of the first, the prologue of the second: barrier init, TMEM allocation, descriptor prefetch) is a few

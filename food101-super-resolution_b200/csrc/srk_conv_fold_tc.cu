@@ -27,6 +27,7 @@
 namespace srk {
 
 int* tc_err_flag();
+int tc_dbg();
 extern long long* g_tc_trace;
 int zero_border(const srk_tensor* t, cudaStream_t st);
 
@@ -82,6 +83,11 @@ struct Params {
   int bn_red, bn_mask;
   const float* bn_mean; const float* bn_invstd; const float* bn_gamma; const float* bn_beta;
   float* bn_dalpha;
+  // cross-CTA stage of the statistics (ordered_fold, srk_common.cuh): ticket + partial rows [grid][132]
+  unsigned* red_ticket;
+  float* red_part;
+  // PReLU epilogues with a slope <= 0 also store the pre-activation (same geometry as y) for the backward pass
+  __nv_bfloat16* zsave;
   int* err;
   long long* trace;    // bring-up: per-tile clock64 stamps of CTA 0 ([16][32]) or null (general instantiation)
   int dbg;             // bring-up knobs (general instantiation only): 1 no stores, 2 no MMAs, 4 no A loads
@@ -482,10 +488,27 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
         continue;
       }
+      if (act == SRK_ACT_PRELU && p.zsave != nullptr && !(alpha > 0.f) && interior) {
+        // rare path (see act_bwd_kernel): the backward cannot recover sign(z) / z from the output
+        long long zo;
+        if (shuffle == 2) {
+          const int cop0 = p.cout_off + c0, sub = cop0 / p.cout_total, ch = cop0 - sub * p.cout_total;
+          zo = (((long long)cn * p.Hp2 + (2 * (cy - 1) + (sub >> 1) + 1)) * p.Wp2 + (2 * (cx - 1) + (sub & 1) + 1)) *
+                   p.cout_total + ch;
+        } else {
+          zo = (long long)pix * p.cout_total + p.cout_off + c0;
+        }
+        uint4* zd = reinterpret_cast<uint4*>(p.zsave + zo);
+#pragma unroll
+        for (int j = 0; j < CPT / 8; ++j)
+          zd[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                             pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+      }
       if (act == SRK_ACT_RELU) {
 #pragma unroll
         for (int j = 0; j < CPT; ++j) f[j] = fmaxf(f[j], 0.f);
       } else if (act == SRK_ACT_PRELU) {
+        // z > 0 ? z : alpha * z, written so that it also holds for alpha <= 0
 #pragma unroll
         for (int j = 0; j < CPT; ++j) f[j] = fmaf(alpha, fminf(f[j], 0.f), fmaxf(f[j], 0.f));
       }
@@ -590,13 +613,39 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           s2[j] = k2 + __shfl_xor_sync(0xffffffffu, o2, half);
         }
       }
-      if (active && lane < CPT && p.cout_off + c0 + lane < p.cout_total) {
-        atomicAdd(stats_sum + p.cout_off + c0 + lane, s1[0]);
-        atomicAdd(stats_sumsq + p.cout_off + c0 + lane, s2[0]);
+      // CTA partial in a fixed order: the four lane groups of a column through shared memory (the exchange buffer
+      // is free once every epilogue warp has left the tile loop), then one ordered fold over the CTAs of the grid
+      float* red = xch;                       // [4 lane groups][sum 64 | sumsq 64] | [16 warps] dalpha
+      float* vals = xch + 528;
+      const int et = threadIdx.x - kEpiWarp0 * 32;
+      named_bar_sync(7, kEpiThreads);
+      if (active && lane < CPT) {
+        red[lg * 128 + c0 + lane] = s1[0];
+        red[lg * 128 + 64 + c0 + lane] = s2[0];
       }
-      if (kStats && p.bn_red && p.bn_mask && p.bn_dalpha) {
+      {
         const float t = warp_sum(bn_da);
-        if (lane == 0) atomicAdd(p.bn_dalpha, t);
+        if (lane == 0) red[512 + (warp - kEpiWarp0)] = t;
+      }
+      named_bar_sync(7, kEpiThreads);
+      if (et < 128) {
+        vals[et] = ((red[et] + red[128 + et]) + red[256 + et]) + red[384 + et];
+      } else if (et == 128) {
+        float t = 0.f;
+        for (int w = 0; w < kEpiWarps; ++w) t += red[512 + w];
+        vals[128] = t;
+      }
+      named_bar_sync(7, kEpiThreads);
+      if (et < 256) {
+        const bool want_da = kStats && p.bn_red && p.bn_mask && p.bn_dalpha != nullptr;
+        const int n_ok = p.cout_total - p.cout_off;   // columns of this pass that exist in the tensor
+        ordered_fold(vals, 129, p.red_ticket, (int)gridDim.x, (int)blockIdx.x, p.red_part, reinterpret_cast<float4*>(xch),
+                     et, 256, [] { named_bar_sync(8, 256); },
+                     [&](int i, float v) {
+                       if (i < 64) { if (i < n_ok) stats_sum[p.cout_off + i] = v; }
+                       else if (i < 128) { if (i - 64 < n_ok) stats_sumsq[p.cout_off + i - 64] = v; }
+                       else if (want_da) p.bn_dalpha[0] = v;
+                     });
       }
     }
   }
@@ -654,8 +703,10 @@ static cudaError_t launch_pass(bool fast, bool stats, int act, int grid, int sme
 int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout,
                            const float* bias, int act, const float* alpha, const srk_tensor* residual, int shuffle,
                            float* stats_sum, float* stats_sumsq, void* workspace, int variant, cudaStream_t st,
-                           const BnRedArgs* br) {
+                           const BnRedArgs* br, void* reduce_ws, void* zsave) {
   using namespace fold;
+  SRK_REQUIRE((stats_sum == nullptr && br == nullptr) || reduce_ws != nullptr,
+              "conv_fold: fused statistics need the reduce workspace");
   // variant: 0 per-tap, 1 folded taps, 2 per-tap on CTA pairs (cta_group::2), 3 = CTA pairs with 128 output
   // channels per pass (PixelShuffle outputs of a single-chunk contraction: the 64 -> 256 upsample convs)
   const bool folded = variant == 1, pair = variant == 2 || variant == 3;
@@ -705,9 +756,12 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
   p.shuffle = shuffle;
   p.Hp2 = y->h + 2; p.Wp2 = y->w + 2;
   p.err = tc_err_flag();
-  { const char* e = getenv("SRK_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
+  p.dbg = tc_dbg();
   p.trace = g_tc_trace;
   p.stats_sum = stats_sum; p.stats_sumsq = stats_sumsq;
+  p.red_ticket = reduce_ws ? red_tickets(reduce_ws) : nullptr;
+  p.red_part = reduce_ws ? red_partials(reduce_ws) : nullptr;
+  p.zsave = (__nv_bfloat16*)zsave;
   p.bn_red = 0; p.bn_mask = 0;
   p.bn_mean = p.bn_invstd = p.bn_gamma = p.bn_beta = nullptr; p.bn_dalpha = nullptr;
   if (br) {

@@ -46,14 +46,17 @@ struct Params {
   const float* bias;     // [64] or null (y)
   const float* alpha;
   __nv_bfloat16* y;      // ACT [N][H+2][W+2][64]
-  float* ws;             // [KP][64] fp32 (g), zero-filled by the caller
-  float* db3;            // [3]: sum over pixels of T3 (accumulated) or null
+  float* ws;             // [grid][KP][64] fp32: one partial of G per CTA (summed in CTA order by fold_kernel)
+  float* ws_small;       // [grid][4] fp32: per-CTA partials of db3[0..2] and ps_dalpha
+  int want_db3;          // sum over pixels of T3 (bias gradient of the 64 -> 3 conv)
+  __nv_bfloat16* zsave;  // fprop with PReLU and a slope <= 0: copy of the pre-activation (y geometry), or null
+  const __nv_bfloat16* ps_zsave;   // unshuffle: pre-activation of the layer below (read when its slope is <= 0), or null
   // rgb_out backward fused with the PReLU + PixelShuffle(2) backward of the layer below (models.py:120-122): T64 is that
   // layer's output, the dgrad result is masked by its sign and stored through tmY as dz of the 64 -> 256 conv,
   // channels sub-pixel-major (row (y/2, x/2), channel sub * 64 + c), the PReLU-slope gradient goes to ps_dalpha
   int unshuffle;
   const float* ps_alpha;
-  float* ps_dalpha;
+  int want_dalpha;
   int* err;
   int dbg;               // bring-up knobs: 1 builders skip the A rows, 2 no MMAs, 4 no T64 loads, 8 no y stores, 16 no halo
 };
@@ -62,6 +65,7 @@ struct __align__(8) Barriers {
   uint64_t wfull, afull[2], aempty[2], tfull[2], tempty[2], yfull[2], yempty[2], done;
   uint32_t tmem_base;
   float red3[8][3];
+  float redda[8];
 };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2,
@@ -323,7 +327,7 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           *reinterpret_cast<uint4*>(arow + sub * SUB_BYTES + ((jj ^ (bi & 7)) << 4)) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
         }
       }
-      if (p.db3 && inside && half == 0) {
+      if (p.want_db3 && inside && half == 0) {
         const __nv_bfloat16* hc = reinterpret_cast<const __nv_bfloat16*>(h0) + ((ty + PAD) * G::HW + tx + PAD) * 3;
 #pragma unroll
         for (int c = 0; c < 3; ++c) s3[c] += __bfloat162float(hc[c]);
@@ -336,7 +340,7 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       if (!build_tile(i, preA)) break;
       if (i + 1 < my_tiles && !build_tile(i + 1, preB)) break;
     }
-    if (p.db3) {
+    if (p.want_db3) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         float t = warp_sum(s3[c]);
@@ -347,7 +351,7 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         float t = 0.f;
 #pragma unroll
         for (int w8 = 0; w8 < 8; ++w8) t += bars->red3[w8][bt];
-        atomicAdd(&p.db3[bt], t);
+        p.ws_small[blockIdx.x * 4 + bt] = t;     // CTA partial; fold_kernel sums the CTAs in order
       }
     }
   } else {
@@ -358,6 +362,9 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       const float alpha = (p.act == SRK_ACT_PRELU) ? p.alpha[0] : 0.f;
       const float ps_alpha = p.unshuffle ? __ldg(p.ps_alpha) : 0.f;
       const float ps_inv_alpha = (p.unshuffle && ps_alpha != 0.f) ? 1.f / ps_alpha : 0.f;
+      // slope <= 0: the sign / value of the pre-activation does not follow from the layer's output (see act_bwd_kernel)
+      const bool ps_use_z = p.unshuffle && p.ps_zsave != nullptr && !(ps_alpha > 0.f);
+      const bool save_z = p.act == SRK_ACT_PRELU && p.zsave != nullptr && !(alpha > 0.f);
       float ps_da = 0.f;
       float bias[32];
 #pragma unroll
@@ -381,20 +388,39 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         for (int j = 0; j < 4; ++j) {
           float f[8];
 #pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]) + bias[j * 8 + e];
+          if (save_z && y0 + ty < p.H && x0 + tx < p.W && c0 + j * 8 < p.n_valid) {
+            __nv_bfloat162 z0 = __floats2bfloat162_rn(f[0], f[1]), z1 = __floats2bfloat162_rn(f[2], f[3]);
+            __nv_bfloat162 z2 = __floats2bfloat162_rn(f[4], f[5]), z3 = __floats2bfloat162_rn(f[6], f[7]);
+            *reinterpret_cast<uint4*>(p.zsave + (((size_t)n * (p.H + 2) + y0 + ty + 1) * (p.W + 2) + x0 + tx + 1) * p.y_stride +
+                                      p.y_col0 + c0 + j * 8) =
+                make_uint4(*reinterpret_cast<uint32_t*>(&z0), *reinterpret_cast<uint32_t*>(&z1),
+                           *reinterpret_cast<uint32_t*>(&z2), *reinterpret_cast<uint32_t*>(&z3));
+          }
+#pragma unroll
           for (int e = 0; e < 8; ++e) {
-            float a = __uint_as_float(v[j * 8 + e]) + bias[j * 8 + e];
+            float a = f[e];
             if (p.act == SRK_ACT_RELU) a = fmaxf(a, 0.f);
             else if (p.act == SRK_ACT_PRELU) a = a > 0.f ? a : alpha * a;
             f[e] = a;
           }
           if (p.unshuffle) {   // PReLU backward of the layer below: mask by the sign of its OUTPUT (the T64 tile)
-            const uint4 tq = *reinterpret_cast<const uint4*>(trow + (((ch * 4 + j) ^ (ei & 7)) << 4));
+            uint4 tq = *reinterpret_cast<const uint4*>(trow + (((ch * 4 + j) ^ (ei & 7)) << 4));
+            float zsc = ps_inv_alpha;
+            if (ps_use_z) {      // ... or of its saved pre-activation
+              zsc = 1.f;
+              tq = make_uint4(0, 0, 0, 0);
+              if (y0 + ty < p.H && x0 + tx < p.W)
+                tq = *reinterpret_cast<const uint4*>(p.ps_zsave + (((size_t)n * (p.H + 2) + y0 + ty + 1) * (p.W + 2) + x0 + tx + 1) * 64 +
+                                                     c0 + j * 8);
+            }
             const __nv_bfloat162* th = reinterpret_cast<const __nv_bfloat162*>(&tq);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float2 tv = __bfloat1622float2(th[e]);
-              if (!(tv.x > 0.f)) { ps_da = fmaf(f[2 * e], tv.x * ps_inv_alpha, ps_da); f[2 * e] *= ps_alpha; }
-              if (!(tv.y > 0.f)) { ps_da = fmaf(f[2 * e + 1], tv.y * ps_inv_alpha, ps_da); f[2 * e + 1] *= ps_alpha; }
+              const bool nx = ps_use_z ? (tv.x < 0.f) : !(tv.x > 0.f), ny = ps_use_z ? (tv.y < 0.f) : !(tv.y > 0.f);
+              if (nx) { ps_da = fmaf(f[2 * e], tv.x * zsc, ps_da); f[2 * e] *= ps_alpha; }
+              if (ny) { ps_da = fmaf(f[2 * e + 1], tv.y * zsc, ps_da); f[2 * e + 1] *= ps_alpha; }
             }
           }
           __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
@@ -422,9 +448,16 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           tma_store_commit();
         }
       }
-      if (p.unshuffle && p.ps_dalpha) {
+      if (p.unshuffle && p.want_dalpha) {
         const float t = warp_sum(ps_da);
-        if (lane == 0) atomicAdd(p.ps_dalpha, t);
+        if (lane == 0) bars->redda[warp - 10] = t;
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        if (threadIdx.x == 320) {
+          float u = 0.f;
+#pragma unroll
+          for (int w8 = 0; w8 < 8; ++w8) u += bars->redda[w8];
+          p.ws_small[blockIdx.x * 4 + 3] = u;    // CTA partial; fold_kernel sums the CTAs in order
+        }
       }
       if (threadIdx.x == 320) tma_store_wait_all();
     }
@@ -435,13 +468,13 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + 2 * NT + mh * NT + c0, v);
         tmem_ld_wait();
-        float* dst = p.ws + (size_t)(mh * 128 + ei) * NT + c0;
+        // this CTA's partial of G: plain stores; fold_kernel adds the partials in CTA order (float atomics here
+        // would make the weight gradient depend on the order in which the CTAs retire)
+        float4* dst = reinterpret_cast<float4*>(p.ws + ((size_t)blockIdx.x * G::KP + mh * 128 + ei) * NT + c0);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j),
-                       "f"(__uint_as_float(v[4 * j])), "f"(__uint_as_float(v[4 * j + 1])),
-                       "f"(__uint_as_float(v[4 * j + 2])), "f"(__uint_as_float(v[4 * j + 3]))
-                       : "memory");
+          dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                               __uint_as_float(v[4 * j + 3]));
       }
     }
   }
@@ -453,22 +486,36 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   }
 }
 
-// ws[k][n] -> OIHW gradient, k = r * SEGW + s * 3 + c.  rgb_out = 0: dW[n][c][tap] (3 -> 64 conv), db[n] = ws[KONE][n]
-//                                                       rgb_out = 1: dW[c][n][taps-1-tap] (64 -> 3 conv; im2col over dY)
-__global__ void fold_kernel(const float* __restrict__ ws, float* __restrict__ dw, float* __restrict__ db, int K,
-                            int rgb_out, int n0, int n_total) {
+// sum over the CTA partials ws[b][k][n] (in CTA order) -> OIHW gradient, k = r * SEGW + s * 3 + c.
+//   rgb_out = 0: dW[n][c][tap] (3 -> 64 conv), db[n] = column sums (the ones row of G)
+//   rgb_out = 1: dW[c][n][taps-1-tap] (64 -> 3 conv; im2col over dY); db3 / dalpha from the per-CTA small partials
+// Every output element is WRITTEN exactly once over the 64-channel passes of a call.
+__global__ void fold_kernel(const float* __restrict__ ws, const float* __restrict__ ws_small, int nblk, int kp,
+                            float* __restrict__ dw, float* __restrict__ db, float* __restrict__ db3,
+                            float* __restrict__ dalpha, int K, int rgb_out, int n0, int n_total) {
   const int taps = K * K, segw = (K * 3 + 1) / 2 * 2, kone = K * segw;
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < kone * NT) {
-    const int n = i % NT, k = i / NT, r = k / segw, t = k - r * segw;
-    if (t >= K * 3 || n0 + n >= n_total) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)kp * NT;
+  if (i < (kone + 1) * NT) {
+    const int n = i % NT, k = i / NT;
+    if (n0 + n >= n_total) return;
+    int r = 0, t = 0;
+    if (k < kone) { r = k / segw; t = k - r * segw; if (t >= K * 3) return; }
+    else if (db == nullptr || rgb_out) return;
+    float v = 0.f;
+#pragma unroll 8
+    for (int b = 0; b < nblk; ++b) v += __ldg(ws + b * stride + i);
+    if (k == kone) { db[n0 + n] = v; return; }
     const int sx = t / 3, c = t - sx * 3, tap = r * K + sx;
-    const float v = ws[i];
-    if (!rgb_out) dw[((size_t)(n0 + n) * 3 + c) * taps + tap] += v;
-    else dw[((size_t)c * n_total + n0 + n) * taps + (taps - 1 - tap)] += v;
-  } else if (i < (kone + 1) * NT && db != nullptr && !rgb_out) {
-    const int n = i - kone * NT;
-    if (n0 + n < n_total) db[n0 + n] += ws[i];
+    if (!rgb_out) dw[((size_t)(n0 + n) * 3 + c) * taps + tap] = v;
+    else dw[((size_t)c * n_total + n0 + n) * taps + (taps - 1 - tap)] = v;
+  } else if (i < (kone + 1) * NT + 4) {
+    const int c = i - (kone + 1) * NT;
+    float* dst = c < 3 ? (db3 ? db3 + c : nullptr) : dalpha;
+    if (dst == nullptr) return;
+    float v = 0.f;
+    for (int b = 0; b < nblk; ++b) v += __ldg(ws_small + b * 4 + c);
+    *dst = v;
   }
 }
 
@@ -522,7 +569,10 @@ static int launch(const CUtensorMap& tmW, const CUtensorMap& tmT, const CUtensor
 
 }  // namespace rgb
 
-int64_t conv_rgb_workspace_bytes(int k) { return (int64_t)(k == 9 ? rgb::Geo<9>::KP : rgb::Geo<5>::KP) * 64 * 4; }
+// one partial of G ([KP][64] fp32) plus four small partials per CTA
+int64_t conv_rgb_workspace_bytes(int k) {
+  return (int64_t)kNumSMs * ((int64_t)(k == 9 ? rgb::Geo<9>::KP : rgb::Geo<5>::KP) * 64 + 4) * 4;
+}
 
 // t3: IMAGE [N,3,H,W]; y (optional): ACT bf16 [N,64,H,W] = act(conv + bias) with Wk = w_packed (bf16 [64][KP]);
 // t64 (optional): ACT bf16 [N,64,H,W] -> dw (OIHW fp32, accumulated), db / db3 (accumulated).
@@ -531,7 +581,7 @@ int64_t conv_rgb_workspace_bytes(int k) { return (int64_t)(k == 9 ? rgb::Geo<9>:
 int conv_rgb_tc_run(const srk_tensor* t3, const srk_tensor* y, const void* w_packed, const float* bias, int act,
                     const float* alpha, const srk_tensor* t64, float* dw, float* db, float* db3, int rgb_out, int k,
                     void* workspace, cudaStream_t st, const srk_tensor* dz_ps, const float* ps_alpha,
-                    float* ps_dalpha) {
+                    float* ps_dalpha, void* zsave, const void* ps_zsave) {
   SRK_REQUIRE(k == 9 || k == 5, "conv_rgb: kernel size must be 9 or 5");
   SRK_REQUIRE(t3 && t3->layout == SRK_LAYOUT_IMAGE && t3->c == 3, "conv_rgb: needs a 3-channel IMAGE tensor");
   rgb::Params p;
@@ -541,7 +591,8 @@ int conv_rgb_tc_run(const srk_tensor* t3, const srk_tensor* y, const void* w_pac
   SRK_REQUIRE(nt < (1LL << 31), "conv_rgb: too many tiles");
   p.num_tiles = (int)nt;
   p.do_y = y != nullptr || dz_ps != nullptr; p.do_g = t64 != nullptr; p.act = act;
-  p.unshuffle = dz_ps != nullptr; p.ps_alpha = ps_alpha; p.ps_dalpha = ps_dalpha;
+  p.unshuffle = dz_ps != nullptr; p.ps_alpha = ps_alpha; p.want_dalpha = ps_dalpha != nullptr;
+  p.zsave = (__nv_bfloat16*)zsave; p.ps_zsave = (const __nv_bfloat16*)ps_zsave;
   if (dz_ps) {
     SRK_REQUIRE(rgb_out && y == nullptr && t64 != nullptr && t64->c == 64 && ps_alpha != nullptr && w_packed != nullptr,
                 "conv_rgb: the fused unshuffle needs the 64 -> 3 backward with its 64-channel input");
@@ -551,9 +602,14 @@ int conv_rgb_tc_run(const srk_tensor* t3, const srk_tensor* y, const void* w_pac
   }
   p.t3 = (const float*)t3->data; p.bias = bias; p.alpha = alpha;
   p.y = y ? (__nv_bfloat16*)y->data : nullptr;
-  p.ws = (float*)workspace; p.db3 = db3; p.err = tc_err_flag();
-  { const char* e = getenv("SRK_RGB_DBG"); p.dbg = e ? atoi(e) : 0; }
   const int KP = k == 9 ? rgb::Geo<9>::KP : rgb::Geo<5>::KP;
+  p.ws = (float*)workspace; p.ws_small = p.ws ? p.ws + (size_t)kNumSMs * KP * 64 : nullptr;
+  p.want_db3 = db3 != nullptr; p.err = tc_err_flag();
+#ifdef SRK_DEBUG_KNOBS
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("SRK_RGB_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
+#else
+  p.dbg = 0;
+#endif
   CUtensorMap tmW, tmT, tmY;
   memset(&tmW, 0, sizeof(tmW)); memset(&tmT, 0, sizeof(tmT)); memset(&tmY, 0, sizeof(tmY));
   // the 64-channel side may have 64 or 96 channels: one pass per 64-channel chunk (tails are zero-filled by TMA)
@@ -583,13 +639,15 @@ int conv_rgb_tc_run(const srk_tensor* t3, const srk_tensor* y, const void* w_pac
     p.n_valid = c64 - n0 < 64 ? c64 - n0 : 64;
     p.w_row0 = rgb_out ? 0 : n0;
     p.t_col0 = n0;
-    p.db3 = n0 == 0 ? db3 : nullptr;
-    if (p.do_g) cudaMemsetAsync(workspace, 0, (size_t)KP * 64 * 4, st);
+    p.want_db3 = n0 == 0 && db3 != nullptr;
+    p.want_dalpha = n0 == 0 && ps_dalpha != nullptr;
     int rc = k == 9 ? rgb::launch<9>(tmW, tmT, tmY, p, st) : rgb::launch<5>(tmW, tmT, tmY, p, st);
     if (rc) return rc;
     if (p.do_g) {
-      const int total = (k * ((k * 3 + 1) / 2 * 2) + 1) * 64;
-      rgb::fold_kernel<<<(total + 255) / 256, 256, 0, st>>>((const float*)workspace, dw, db, k, rgb_out, n0, c64);
+      const int total = (k * ((k * 3 + 1) / 2 * 2) + 1) * 64 + 4;
+      const int nblk = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;   // = the grid of rgb::launch
+      rgb::fold_kernel<<<(total + 255) / 256, 256, 0, st>>>(p.ws, p.ws_small, nblk, KP, dw, db, p.want_db3 ? db3 : nullptr,
+                                                            p.want_dalpha ? ps_dalpha : nullptr, k, rgb_out, n0, c64);
       SRK_CUDA_LAUNCH_CHECK("conv_rgb_fold");
     }
   }

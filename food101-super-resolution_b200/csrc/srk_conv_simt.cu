@@ -22,6 +22,7 @@ struct FpropParams {
   const float* w;  // [R][S][Cin][Cout]
   const float* bias;
   const float* alpha;
+  void* zsave;      // PReLU with a slope <= 0: copy of the pre-activation in y's geometry / dtype, or null
   int Cin, Cout, R, S, pad;
   int act, shuffle, has_res;
   int K;            // R*S*Cin
@@ -112,11 +113,12 @@ __global__ void __launch_bounds__(256) conv_fprop_simt(FpropParams P) {
       int co = n0 + tx * 4 + j;
       if (co >= P.Cout) continue;
       float v = acc[i][j] + (P.bias ? P.bias[co] : 0.f);
-      if (P.act == SRK_ACT_RELU) v = fmaxf(v, 0.f);
-      else if (P.act == SRK_ACT_PRELU) v = v > 0.f ? v : alpha * v;
       int oc = co, oy = y, ox = x;
       if (P.shuffle == 2) { oc = co >> 2; oy = 2 * y + ((co >> 1) & 1); ox = 2 * x + (co & 1); }
       long long oidx = P.y.off + n * P.y.sn + oy * P.y.sh + ox * P.y.sw + oc * P.y.sc;
+      if (P.act == SRK_ACT_PRELU && P.zsave != nullptr && !(alpha > 0.f)) ((TO*)P.zsave)[oidx] = from_f<TO>(v);
+      if (P.act == SRK_ACT_RELU) v = fmaxf(v, 0.f);
+      else if (P.act == SRK_ACT_PRELU) v = v > 0.f ? v : alpha * v;
       if (P.has_res) {
         // residual shares the output geometry
         long long ridx = P.res.off + n * P.res.sn + oy * P.res.sh + ox * P.res.sw + oc * P.res.sc;
@@ -164,8 +166,9 @@ int zero_border(const srk_tensor* t, cudaStream_t st) {
 
 int conv_fprop_simt_launch(const srk_tensor* x, const srk_tensor* y, const float* w, int cout, int r,
                            int s, const float* bias, int act, const float* alpha,
-                           const srk_tensor* residual, int shuffle, cudaStream_t st) {
+                           const srk_tensor* residual, int shuffle, cudaStream_t st, void* zsave) {
   FpropParams P;
+  P.zsave = zsave;
   P.x = make_view(x); P.y = make_view(y);
   P.has_res = residual != nullptr;
   P.res = residual ? make_view(residual) : P.y;
@@ -190,12 +193,13 @@ int conv_fprop_simt_launch(const srk_tensor* x, const srk_tensor* y, const float
 }
 
 // ---------------------------------------------------------------------------------------------
-// wgrad: dW[k][co] += sum_p A[p][k] dY[p][co], written straight into the OIHW fp32 gradient with
-// atomics (split over pixel ranges); db[co] += sum_p dY[p][co].
+// wgrad: dW[k][co] = sum_p A[p][k] dY[p][co], db[co] = sum_p dY[p][co].  The pixel range is split over blockIdx.z;
+// every slice stores its partial [K][Cout] (+ [Cout]) into the workspace and conv_wgrad_simt_fold adds the slices in
+// slice order into the OIHW gradient (no float atomics: the result does not depend on block scheduling).
 struct WgradParams {
   View x, dy;
-  float* dw;  // OIHW
-  float* db;
+  float* part;      // [gz][K * Cout + Cout]
+  int has_bias;
   int Cin, Cout, R, S, pad, K;
   long long M;
   long long chunk;  // pixels per z-slice
@@ -226,6 +230,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_simt(WgradParams P) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   float bsum = 0.f;
+  float* slice = P.part + (long long)blockIdx.z * ((long long)P.K * P.Cout + P.Cout);
 
   for (long long p0 = p_begin; p0 < p_end; p0 += BK) {
 #pragma unroll
@@ -271,37 +276,71 @@ __global__ void __launch_bounds__(256) conv_wgrad_simt(WgradParams P) {
     for (int j = 0; j < 4; ++j) {
       int c2 = n0 + tx * 4 + j;
       if (c2 >= P.Cout) continue;
-      atomicAdd(&P.dw[((long long)c2 * P.Cin + cii) * (P.R * P.S) + tap], acc[i][j]);
+      (void)tap; (void)cii;
+      slice[(long long)kk * P.Cout + c2] = acc[i][j];
     }
   }
-  if (P.db != nullptr && blockIdx.x == 0) {
+  if (P.has_bias && blockIdx.x == 0) {
     // threads tid, tid+64, tid+128, tid+192 share a column: reduce through smem
     __shared__ float red[256];
     red[tid] = bsum;
     __syncthreads();
-    if (tid < 64 && covalid) atomicAdd(&P.db[co], red[tid] + red[tid + 64] + red[tid + 128] + red[tid + 192]);
+    if (tid < 64 && covalid) slice[(long long)P.K * P.Cout + co] = red[tid] + red[tid + 64] + red[tid + 128] + red[tid + 192];
   }
 }
 
-int conv_wgrad_simt_launch(const srk_tensor* x, const srk_tensor* dy, float* dw, float* db, int r,
-                           int s, cudaStream_t st) {
-  WgradParams P;
-  P.x = make_view(x); P.dy = make_view(dy);
-  P.dw = dw; P.db = db;
-  P.Cin = x->c; P.Cout = dy->c; P.R = r; P.S = s; P.pad = r / 2;
-  P.K = r * s * x->c;
-  P.M = (long long)x->n * x->h * x->w;
-  int gx = (P.K + BM - 1) / BM, gy = (P.Cout + BN - 1) / BN;
-  long long want = (148LL * 4 + (long long)gx * gy - 1) / ((long long)gx * gy);
-  long long max_splits = (P.M + 1023) / 1024;
+__global__ void conv_wgrad_simt_fold(const float* __restrict__ part, int gz, int K, int Cin, int Cout, int taps,
+                                     float* __restrict__ dw, float* __restrict__ db, int accumulate) {
+  const long long stride = (long long)K * Cout + Cout;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= stride || (i >= (long long)K * Cout && db == nullptr)) return;
+  float v = 0.f;
+  for (int z = 0; z < gz; ++z) v += part[z * stride + i];
+  if (i < (long long)K * Cout) {
+    const int kk = (int)(i / Cout), c2 = (int)(i - (long long)kk * Cout);
+    const int tap = kk / Cin, cii = kk - tap * Cin;
+    float* d = dw + ((long long)c2 * Cin + cii) * taps + tap;
+    *d = accumulate ? *d + v : v;
+  } else {
+    float* d = db + (i - (long long)K * Cout);
+    *d = accumulate ? *d + v : v;
+  }
+}
+
+struct WgradGrid { int gx, gy, gz; long long chunk; };
+static WgradGrid wgrad_simt_grid(const srk_tensor* x, const srk_tensor* dy, int r, int s) {
+  WgradGrid g;
+  const int K = r * s * x->c;
+  const long long M = (long long)x->n * x->h * x->w;
+  g.gx = (K + BM - 1) / BM; g.gy = (dy->c + BN - 1) / BN;
+  long long want = (148LL * 4 + (long long)g.gx * g.gy - 1) / ((long long)g.gx * g.gy);
+  long long max_splits = (M + 1023) / 1024;
   if (want > max_splits) want = max_splits;
   if (want < 1) want = 1;
   if (want > 65535) want = 65535;
-  long long chunk = (P.M + want - 1) / want;
+  long long chunk = (M + want - 1) / want;
   chunk = (chunk + BK - 1) / BK * BK;
-  int gz = (int)((P.M + chunk - 1) / chunk);
-  P.chunk = chunk;
-  dim3 grid(gx, gy, gz);
+  g.gz = (int)((M + chunk - 1) / chunk);
+  g.chunk = chunk;
+  return g;
+}
+int64_t conv_wgrad_simt_workspace(const srk_tensor* x, const srk_tensor* dy, int r, int s) {
+  const WgradGrid g = wgrad_simt_grid(x, dy, r, s);
+  return (int64_t)g.gz * ((int64_t)r * s * x->c * dy->c + dy->c) * (int64_t)sizeof(float);
+}
+
+int conv_wgrad_simt_launch(const srk_tensor* x, const srk_tensor* dy, float* dw, float* db, int r,
+                           int s, void* workspace, int accumulate, cudaStream_t st) {
+  SRK_REQUIRE(workspace != nullptr, "conv_wgrad_simt: workspace required (srk_conv_wgrad_workspace_bytes)");
+  WgradParams P;
+  P.x = make_view(x); P.dy = make_view(dy);
+  P.part = (float*)workspace; P.has_bias = db != nullptr;
+  P.Cin = x->c; P.Cout = dy->c; P.R = r; P.S = s; P.pad = r / 2;
+  P.K = r * s * x->c;
+  P.M = (long long)x->n * x->h * x->w;
+  const WgradGrid g = wgrad_simt_grid(x, dy, r, s);
+  P.chunk = g.chunk;
+  dim3 grid(g.gx, g.gy, g.gz);
   bool x_bf = x->layout == SRK_LAYOUT_ACT && x->dtype == SRK_BF16;
   bool g_bf = dy->layout == SRK_LAYOUT_ACT && dy->dtype == SRK_BF16;
   if (x_bf && g_bf) conv_wgrad_simt<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(P);
@@ -309,6 +348,10 @@ int conv_wgrad_simt_launch(const srk_tensor* x, const srk_tensor* dy, float* dw,
   else if (g_bf) conv_wgrad_simt<float, __nv_bfloat16><<<grid, 256, 0, st>>>(P);
   else conv_wgrad_simt<float, float><<<grid, 256, 0, st>>>(P);
   SRK_CUDA_LAUNCH_CHECK("conv_wgrad_simt");
+  const long long total = (long long)P.K * P.Cout + P.Cout;
+  conv_wgrad_simt_fold<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(P.part, g.gz, P.K, P.Cin, P.Cout, r * s, dw, db,
+                                                                        accumulate);
+  SRK_CUDA_LAUNCH_CHECK("conv_wgrad_simt_fold");
   return 0;
 }
 

@@ -72,6 +72,7 @@ constexpr int SLAB_BOX_ROWS = 32;
 constexpr int kThreads = 352;           // warps: 0 TMA, 1 MMA, 2-9 epilogue, 10 output store / residual load
 constexpr int O_TILE_BYTES = TM * NT * 2;  // bf16 output tile staged for the TMA store
 constexpr int MAX_STAGES = 8;
+constexpr int RED_BYTES = 4096;
 
 struct TcConvParams {
   int P, Hp, Wp, num_tiles;
@@ -95,7 +96,10 @@ struct TcConvParams {
   __nv_bfloat16* y;
   int Hp2, Wp2;        // padded sizes of the shuffled output
   float* stats_sum;    // fused BatchNorm statistics: per-channel sum / sum of squares of the fp32
-  float* stats_sumsq;  // outputs over interior pixels (accumulated), or null
+  float* stats_sumsq;  // outputs over interior pixels (written), or null
+  unsigned* red_ticket;   // cross-CTA stage of the statistics (ordered_fold, srk_common.cuh)
+  float* red_part;
+  __nv_bfloat16* zsave;   // PReLU with a slope <= 0: copy of the pre-activation (y geometry) for the backward pass
   int* err;
   int dbg;             // bring-up knobs: 1 skip stores, 2 skip MMAs, 4 skip A loads
   long long* trace;    // bring-up: per-tile clock64 stamps of CTA 0 ([6][32]) or null
@@ -137,7 +141,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t asm0 = smem_base + TAPS * W_TILE_BYTES;
   const uint32_t osm = asm0 + p.stages * p.stage_bytes;
   uint8_t* optr = smem_al + TAPS * W_TILE_BYTES + p.stages * p.stage_bytes;
-  TcBarriers* bars = reinterpret_cast<TcBarriers*>(optr + 2 * O_TILE_BYTES);
+  float* redp = reinterpret_cast<float*>(optr + 2 * O_TILE_BYTES);   // RED_BYTES: statistics fold scratch
+  TcBarriers* bars = reinterpret_cast<TcBarriers*>(optr + 2 * O_TILE_BYTES + RED_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
@@ -389,6 +394,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         continue;
       }
       if (p.shuffle == 0 && !mbar_wait(smem_u32(&bars->ofree[acc]), ((it >> 1) & 1) ^ 1, p.err, 7)) break;
+      if (p.act == SRK_ACT_PRELU && p.zsave != nullptr && !(alpha > 0.f) && interior) {
+        // rare path (see act_bwd_kernel): the backward cannot recover sign(z) / z from the output
+        long long zo;
+        if (p.shuffle == 2)
+          zo = (((long long)n * p.Hp2 + (2 * (yy - 1) + (ps_sub >> 1) + 1)) * p.Wp2 + (2 * (xx - 1) + (ps_sub & 1) + 1)) *
+                   p.cout_total + ps_c;
+        else
+          zo = (long long)pix * p.cout_total + p.cout_off + c0;
+        uint4* zd = reinterpret_cast<uint4*>(p.zsave + zo);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          zd[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                             pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+      }
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         float a = f[j];
@@ -452,11 +471,25 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           s2[j] = k2 + __shfl_xor_sync(0xffffffffu, o2, half);
         }
       }
-      // after the butterfly lane l holds the total of column bitrev-free index: col = sum over steps of (lane & half)
-      if (active && p.cout_off + c0 + lane < p.cout_total) {
-        atomicAdd(stats_sum + p.cout_off + c0 + lane, s1[0]);
-        atomicAdd(stats_sumsq + p.cout_off + c0 + lane, s2[0]);
+      // after the butterfly lane l holds the total of column c0 + l over this warp's rows.  CTA partial in a fixed
+      // order (the four lane groups of a column through shared memory), then one ordered fold over the grid.
+      float* red = redp;               // [4 lane groups][sum 64 | sumsq 64]
+      float* vals = redp + 512;
+      const int et = threadIdx.x - 64;
+      if (active) {
+        red[lg * 128 + c0 + lane] = s1[0];
+        red[lg * 128 + 64 + c0 + lane] = s2[0];
       }
+      asm volatile("bar.sync 7, 256;" ::: "memory");
+      if (et < 128) vals[et] = ((red[et] + red[128 + et]) + red[256 + et]) + red[384 + et];
+      asm volatile("bar.sync 7, 256;" ::: "memory");
+      const int n_ok = p.cout_total - p.cout_off;
+      ordered_fold(vals, 128, p.red_ticket, (int)gridDim.x, (int)blockIdx.x, p.red_part, reinterpret_cast<float4*>(redp),
+                   et, 256, [] { asm volatile("bar.sync 7, 256;" ::: "memory"); },
+                   [&](int i, float v) {
+                     if (i < 64) { if (i < n_ok) stats_sum[p.cout_off + i] = v; }
+                     else if (i - 64 < n_ok) stats_sumsq[p.cout_off + i - 64] = v;
+                   });
     }
   }
   tc_fence_before();
@@ -480,6 +513,18 @@ int tc_mode() {
   return g_tc_mode;
 }
 void tc_set_mode(int m) { g_tc_mode = m; }
+
+// Bring-up knobs of the general kernel instantiations (skip stores / MMAs / loads: results are wrong by design).
+// Compiled out of release builds; with -DSRK_DEBUG_KNOBS the environment variable SRK_TC_DBG is read once.
+int tc_dbg() {
+#ifdef SRK_DEBUG_KNOBS
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SRK_TC_DBG"); v = e ? atoi(e) : 0; }
+  return v;
+#else
+  return 0;
+#endif
+}
 
 int* tc_err_flag() {
   // one device int per process per device; checked lazily by the probe (never synchronises the hot path)
@@ -534,7 +579,9 @@ bool conv_tc_shape_ok(int cin, int cout, int r, int s, int dtype, int shuffle) {
 
 int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout, int r, int s,
                          const float* bias, int act, const float* alpha, const srk_tensor* residual, int shuffle,
-                         float* stats_sum, float* stats_sumsq, void* workspace, cudaStream_t st) {
+                         float* stats_sum, float* stats_sumsq, void* workspace, cudaStream_t st, void* reduce_ws,
+                         void* zsave) {
+  SRK_REQUIRE(stats_sum == nullptr || reduce_ws != nullptr, "conv_tc: fused statistics need the reduce workspace");
   // PixelShuffle outputs stay on the 8-warp kernel below: its threads own 32 channels = 16-byte stores per sub-pixel,
   // the 16-warp pipeline would store 8 bytes at a time (measured 64->256 at 128^2: 424 vs 685 us)
   // 64 -> 256 PixelShuffle convs on CTA pairs with N = 128 MMAs (SRK_TC_UP_PAIR=1): parity-green but slower (128^2:
@@ -543,12 +590,13 @@ int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w
   if (r == 3 && g_up_pair && shuffle == 2 && x->c == 64 && cout % 128 == 0 && residual == nullptr &&
       stats_sum == nullptr) {
     const int rc = conv_fprop_fold_launch(x, y, w_packed, cout, bias, act, alpha, residual, shuffle, nullptr, nullptr,
-                                          workspace, 3, st, nullptr);
+                                          workspace, 3, st, nullptr, nullptr, zsave);
     if (rc >= 0) return rc;
   }
   if (r == 3 && tc_fold() && !(tc_fold() >= 2 && shuffle != 0)) {
     const int rc = conv_fprop_fold_launch(x, y, w_packed, cout, bias, act, alpha, residual, shuffle, stats_sum,
-                                          stats_sumsq, workspace, tc_fold() == 1 ? 1 : (tc_fold() == 3 ? 2 : 0), st, nullptr);
+                                          stats_sumsq, workspace, tc_fold() == 1 ? 1 : (tc_fold() == 3 ? 2 : 0), st, nullptr,
+                                          reduce_ws, zsave);
     if (rc >= 0) return rc;   // -1: slab does not fit (very wide images) -> per-tap kernel below
   }
   const int cin = x->c;
@@ -566,7 +614,7 @@ int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w
   }
   int mode = r == 1 ? 0 : tc_mode();
   int slab_rows = ((TM + 2 * Wp + 2) + SLAB_BOX_ROWS - 1) / SLAB_BOX_ROWS * SLAB_BOX_ROWS;
-  const int fixed = 1024 + TAPS * W_TILE_BYTES + 2 * O_TILE_BYTES + (int)sizeof(TcBarriers);
+  const int fixed = 1024 + TAPS * W_TILE_BYTES + 2 * O_TILE_BYTES + RED_BYTES + (int)sizeof(TcBarriers);
   int stage_bytes, stages;
   if (mode != 0) {
     stage_bytes = slab_rows * KC * 2;
@@ -605,9 +653,12 @@ int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w
   p.shuffle = shuffle;
   p.Hp2 = y->h + 2; p.Wp2 = y->w + 2;
   p.err = tc_err_flag();
-  { const char* e = getenv("SRK_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
+  p.dbg = tc_dbg();
   p.trace = g_tc_trace;
   p.stats_sum = stats_sum; p.stats_sumsq = stats_sumsq;
+  p.red_ticket = reduce_ws ? red_tickets(reduce_ws) : nullptr;
+  p.red_part = reduce_ws ? red_partials(reduce_ws) : nullptr;
+  p.zsave = (__nv_bfloat16*)zsave;
   const int nchunks = (cout + NT - 1) / NT, kchunks = (cin + KC - 1) / KC;
   SRK_REQUIRE(stats_sum == nullptr || (kchunks == 1 && shuffle == 0 && act == SRK_ACT_NONE && residual == nullptr),
               "conv_tc: fused BN statistics need a plain Cin == 64 conv");

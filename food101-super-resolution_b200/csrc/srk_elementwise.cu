@@ -160,12 +160,13 @@ inline void pixel_grid(const Geo& g, int& blocks, int& ppb) {
   blocks = (int)((g.pixels + ppb - 1) / ppb);
 }
 
-// Reduce per-thread VEC partials across the rows of a block, then one atomic per channel.
+// Reduce per-thread VEC partials across the rows of a block into dst[C] (shared memory), in a fixed order.
 // When the channel-vector count divides the warp size the lanes that share a channel vector are first folded
-// with shuffles, so only one row per warp goes through shared memory.
+// with shuffles, so only one row per warp goes through shared memory.  Ends with a __syncthreads(): dst is
+// complete and visible, `smem` may be reused.
 template <int VEC>
-__device__ __forceinline__ void block_channel_atomic(float* part, float* smem, int CV, int rows,
-                                                     int cv, int prow, float* gdst) {
+__device__ __forceinline__ void block_channel_sum(float* part, float* smem, int CV, int rows,
+                                                  int cv, int prow, float* dst) {
   const int C = CV * VEC;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   __syncthreads();
@@ -182,8 +183,9 @@ __device__ __forceinline__ void block_channel_atomic(float* part, float* smem, i
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       float s = 0.f;
       for (int r = 0; r < nwarps; ++r) s += smem[r * C + c];
-      atomicAdd(&gdst[c], s);
+      dst[c] = s;
     }
+    __syncthreads();
     return;
   }
   // smem: [rows][CV*VEC]
@@ -195,17 +197,29 @@ __device__ __forceinline__ void block_channel_atomic(float* part, float* smem, i
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = 0.f;
     for (int r = 0; r < rows; ++r) s += smem[r * C + c];
-    atomicAdd(&gdst[c], s);
+    dst[c] = s;
   }
+  __syncthreads();
 }
+
+// Dynamic shared memory of the reducing kernels: [row scratch: red_rows_floats][vals: NV (padded to 4)][fold
+// scratch: blockDim float4].  Cross-block stage: ordered_fold (srk_common.cuh).
+struct RedArgs {
+  unsigned* tickets;   // ticket base of this launch (one per reduction slot)
+  float* partials;     // partial rows of this launch
+};
+__device__ __forceinline__ void sync_block() { __syncthreads(); }
 
 // ---- BatchNorm ---------------------------------------------------------------------------------
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ y, Geo g, int ppb,
-                                                       float* __restrict__ sum, float* __restrict__ sumsq) {
+                                                       float* __restrict__ sums /* [2][C]: sum | sum of squares */,
+                                                       RedArgs ra, int row_floats) {
   pdl_wait();      // the inputs come from the previous kernel of the stream (see launch_dep)
   pdl_trigger();
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
+  float* vals = smem + row_floats;
+  float4* scratch = reinterpret_cast<float4*>(vals + ((2 * g.C + 3) & ~3));
   float s1[VEC], s2[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
@@ -216,8 +230,10 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ y, 
 #pragma unroll
     for (int j = 0; j < VEC; ++j) { s1[j] += v[j]; s2[j] = fmaf(v[j], v[j], s2[j]); }
   }
-  block_channel_atomic<VEC>(s1, smem, CV, rows, cv, prow, sum);
-  block_channel_atomic<VEC>(s2, smem, CV, rows, cv, prow, sumsq);
+  block_channel_sum<VEC>(s1, smem, CV, rows, cv, prow, vals);
+  block_channel_sum<VEC>(s2, smem, CV, rows, cv, prow, vals + g.C);
+  ordered_fold(vals, 2 * g.C, ra.tickets, gridDim.x, blockIdx.x, ra.partials, scratch, threadIdx.x, blockDim.x,
+               sync_block, [&](int i, float v) { sums[i] = v; });
 }
 
 __global__ void bn_finalize_kernel(const float* sum, const float* sumsq, int C, double count, float eps,
@@ -325,10 +341,12 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const T* __restri
     const T* __restrict__ y, Geo g, int ppb, const float* __restrict__ mean,
     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
     const float* __restrict__ alpha_p, float* __restrict__ dgamma, float* __restrict__ dbeta,
-    float* __restrict__ dalpha) {
+    float* __restrict__ dalpha, RedArgs ra, int row_floats) {
   pdl_wait();      // the inputs come from the previous kernel of the stream (see launch_dep)
   pdl_trigger();
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
+  float* vals = smem + row_floats;
+  float4* scratch = reinterpret_cast<float4*>(vals + ((2 * g.C + 1 + 3) & ~3));
   const float alpha = alpha_p ? alpha_p[0] : 1.f;
   float dg[VEC], db[VEC];
   float da = 0.f;
@@ -378,13 +396,21 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const T* __restri
       }
     }
   }
-  block_channel_atomic<VEC>(dg, smem, CV, rows, cv, prow, dgamma);
-  block_channel_atomic<VEC>(db, smem, CV, rows, cv, prow, dbeta);
-  if (alpha_p && dalpha) {
+  block_channel_sum<VEC>(dg, smem, CV, rows, cv, prow, vals);
+  block_channel_sum<VEC>(db, smem, CV, rows, cv, prow, vals + g.C);
+  {
     __shared__ float red[32];
-    float t = block_sum(da, red);
-    if (threadIdx.x == 0) atomicAdd(dalpha, t);
+    const float t = block_sum(da, red);
+    if (threadIdx.x == 0) vals[2 * g.C] = t;
+    __syncthreads();
   }
+  const int C = g.C;
+  ordered_fold(vals, 2 * C + 1, ra.tickets, gridDim.x, blockIdx.x, ra.partials, scratch, threadIdx.x, blockDim.x,
+               sync_block, [&](int i, float v) {
+                 if (i < C) dgamma[i] = v;
+                 else if (i < 2 * C) dbeta[i - C] = v;
+                 else if (alpha_p && dalpha) dalpha[0] = v;
+               });
 }
 
 template <typename T, int VEC>
@@ -436,12 +462,20 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
 }
 
 // ---- activation backward -------------------------------------------------------------------------
+// PReLU backward needs the sign (and, for the slope gradient, the value) of the PRE-activation z.  For alpha > 0
+// both follow from the saved output (sign(out) = sign(z), z = out / alpha on the negative side).  For alpha <= 0
+// they do not (alpha < 0 maps negative z to positive outputs, alpha = 0 maps them to 0): the forward epilogues then
+// store z itself into `zsave` (same geometry as out) and this kernel reads it instead - a uniform branch on the
+// device-resident slope, so the common case costs nothing and no host decision depends on a parameter value.
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) act_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ out,
-    Geo g, int ppb, int act, const float* __restrict__ alpha_p, float* __restrict__ dalpha,
-    T* __restrict__ dz) {
+    const T* __restrict__ zsave, Geo g, int ppb, int act, const float* __restrict__ alpha_p,
+    float* __restrict__ dalpha, RedArgs ra, T* __restrict__ dz) {
   const float alpha = (act == SRK_ACT_PRELU) ? alpha_p[0] : 0.f;
+  const bool use_z = act == SRK_ACT_PRELU && zsave != nullptr && !(alpha > 0.f);
   const float inv_alpha = (act == SRK_ACT_PRELU && alpha != 0.f) ? 1.f / alpha : 0.f;
+  const T* __restrict__ src = use_z ? zsave : out;
+  const float zscale = use_z ? 1.f : inv_alpha;     // z = src * zscale on the negative side
   float da = 0.f;
   SRK_PIXEL_LOOP(g, VEC) {
     const long long q = pw.q;
@@ -452,30 +486,39 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const T* __restrict__ dout
       for (int j = 0; j < VEC; ++j) o[j] = 0.f;
     } else {
       float v[VEC], d[VEC];
-      Vec<T, VEC>::ld(out + e, v);
+      Vec<T, VEC>::ld(src + e, v);
       Vec<T, VEC>::ld(dout + e, d);
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
-        if (v[j] > 0.f) o[j] = d[j];
-        else { o[j] = alpha * d[j]; da = fmaf(d[j], v[j] * inv_alpha, da); }
+        const bool pos = use_z ? !(v[j] < 0.f) : (v[j] > 0.f);
+        if (pos) o[j] = d[j];
+        else { o[j] = alpha * d[j]; da = fmaf(d[j], v[j] * zscale, da); }
       }
     }
     Vec<T, VEC>::st(dz + e, o);
   }
   if (act == SRK_ACT_PRELU && dalpha) {
     __shared__ float red[32];
-    float t = block_sum(da, red);
-    if (threadIdx.x == 0) atomicAdd(dalpha, t);
+    __shared__ __align__(16) float vals[4];
+    __shared__ float4 scratch[256];
+    const float t = block_sum(da, red);
+    if (threadIdx.x == 0) vals[0] = t;
+    __syncthreads();
+    ordered_fold(vals, 1, ra.tickets, gridDim.x, blockIdx.x, ra.partials, scratch, threadIdx.x, blockDim.x,
+                 sync_block, [&](int, float v) { dalpha[0] = v; });
   }
 }
 
 // dout/out: [N][2H+2][2W+2][C]; dz: [N][H+2][W+2][4C].  Iterates over dz.
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) act_bwd_unshuffle_kernel(const T* __restrict__ dout,
-    const T* __restrict__ out, Geo gz, int ppb, int C, int act, const float* __restrict__ alpha_p,
-    float* __restrict__ dalpha, int perm_tc, T* __restrict__ dz) {
+    const T* __restrict__ out_, const T* __restrict__ zsave, Geo gz, int ppb, int C, int act,
+    const float* __restrict__ alpha_p, float* __restrict__ dalpha, RedArgs ra, int perm_tc, T* __restrict__ dz) {
   const float alpha = (act == SRK_ACT_PRELU) ? alpha_p[0] : 0.f;
+  const bool use_z = act == SRK_ACT_PRELU && zsave != nullptr && !(alpha > 0.f);   // see act_bwd_kernel
   const float inv_alpha = (act == SRK_ACT_PRELU && alpha != 0.f) ? 1.f / alpha : 0.f;
+  const T* __restrict__ out = use_z ? zsave : out_;
+  const float zscale = use_z ? 1.f : inv_alpha;
   const int Wp2 = 2 * (gz.Wp - 2) + 2, Hp2 = 2 * (gz.Hp - 2) + 2;
   float da = 0.f;
   SRK_PIXEL_LOOP(gz, VEC) {
@@ -521,16 +564,22 @@ __global__ void __launch_bounds__(256) act_bwd_unshuffle_kernel(const T* __restr
       }
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
-        if (act == SRK_ACT_NONE || v[j] > 0.f) o[j] = d[j];
-        else { o[j] = alpha * d[j]; da = fmaf(d[j], v[j] * inv_alpha, da); }
+        const bool pos = act == SRK_ACT_NONE || (use_z ? !(v[j] < 0.f) : (v[j] > 0.f));
+        if (pos) o[j] = d[j];
+        else { o[j] = alpha * d[j]; da = fmaf(d[j], v[j] * zscale, da); }
       }
     }
     Vec<T, VEC>::st(dz + e, o);
   }
   if (act == SRK_ACT_PRELU && dalpha) {
     __shared__ float red[32];
-    float t = block_sum(da, red);
-    if (threadIdx.x == 0) atomicAdd(dalpha, t);
+    __shared__ __align__(16) float vals[4];
+    __shared__ float4 scratch[256];
+    const float t = block_sum(da, red);
+    if (threadIdx.x == 0) vals[0] = t;
+    __syncthreads();
+    ordered_fold(vals, 1, ra.tickets, gridDim.x, blockIdx.x, ra.partials, scratch, threadIdx.x, blockDim.x,
+                 sync_block, [&](int, float v) { dalpha[0] = v; });
   }
 }
 
@@ -538,8 +587,10 @@ __global__ void __launch_bounds__(256) act_bwd_unshuffle_kernel(const T* __restr
 // per-image channel sums of a (optionally times b): grid = (blocks_per_image, N)
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) image_channel_sum_kernel(const T* __restrict__ a,
-    const T* __restrict__ b, Geo g, int ppb, float scale, float* __restrict__ out) {
-  extern __shared__ float smem[];
+    const T* __restrict__ b, Geo g, int ppb, float scale, float* __restrict__ out, RedArgs ra, int row_floats) {
+  extern __shared__ __align__(16) float smem[];
+  float* vals = smem + row_floats;
+  float4* scratch = reinterpret_cast<float4*>(vals + ((g.C + 3) & ~3));
   const int n = blockIdx.y;
   const long long img_pixels = (long long)g.Hp * g.Wp;
   const int CV = g.C / VEC, rows = blockDim.x / CV, cv = threadIdx.x % CV, prow = threadIdx.x / CV;
@@ -564,9 +615,12 @@ __global__ void __launch_bounds__(256) image_channel_sum_kernel(const T* __restr
         for (int j = 0; j < VEC; ++j) s[j] += v[j];
       }
     }
-#pragma unroll
-  for (int j = 0; j < VEC; ++j) s[j] *= scale;
-  block_channel_atomic<VEC>(s, smem, CV, rows, cv, prow, out + (long long)n * g.C);
+  block_channel_sum<VEC>(s, smem, CV, rows, cv, prow, vals);
+  // one reduction slot per image: ticket n, partial rows [n][gridDim.x][C]
+  float* dst = out + (long long)n * g.C;
+  const int C4 = (g.C + 3) & ~3;
+  ordered_fold(vals, g.C, ra.tickets + n, gridDim.x, blockIdx.x, ra.partials + (size_t)n * gridDim.x * C4, scratch,
+               threadIdx.x, blockDim.x, sync_block, [&](int i, float v) { dst[i] = v * scale; });
 }
 
 __global__ void se_fc_kernel(const float* __restrict__ pool, const float* __restrict__ w1,
@@ -619,7 +673,7 @@ __global__ void __launch_bounds__(256) se_apply_kernel(const T* __restrict__ x, 
   }
 }
 
-// single block; accumulates dw1/dw2 over the batch and writes dpool
+// single block; writes dw1 / dw2 (sums over the batch) and dpool
 __global__ void se_fc_bwd_kernel(const float* __restrict__ dgate_raw, const float* __restrict__ gate,
     const float* __restrict__ hidden, const float* __restrict__ pool, const float* __restrict__ w1,
     const float* __restrict__ w2, int N, int C, int Cr, float scale, float* __restrict__ dw1,
@@ -643,13 +697,13 @@ __global__ void se_fc_bwd_kernel(const float* __restrict__ dgate_raw, const floa
     int c = i / Cr, j = i - c * Cr;
     float s = 0.f;
     for (int n = 0; n < N; ++n) s = fmaf(dz2_ws[n * C + c], hidden[n * Cr + j], s);
-    dw2[i] += s;
+    dw2[i] = s;
   }
   for (int i = threadIdx.x; i < Cr * C; i += blockDim.x) {
     int j = i / C, c = i - j * C;
     float s = 0.f;
     for (int n = 0; n < N; ++n) s = fmaf(dh_ws[n * Cr + j], pool[n * C + c], s);
-    dw1[i] += s;
+    dw1[i] = s;
   }
   for (int i = threadIdx.x; i < N * C; i += blockDim.x) {
     int n = i / C, c = i - n * C;
@@ -889,17 +943,37 @@ static inline size_t red_smem(const srk_tensor* t) {
   int rows = 256 / cv; if (rows < 1) rows = 1;
   return (size_t)rows * t->c * sizeof(float);
 }
+// dynamic shared memory of a reducing kernel with NV values per block (layout: see RedArgs)
+static inline int red_row_floats(const srk_tensor* t) { return (int)((red_smem(t) / sizeof(float) + 3) & ~(size_t)3); }
+static inline size_t red_total_smem(const srk_tensor* t, int nv) {
+  return ((size_t)red_row_floats(t) + (size_t)((nv + 3) & ~3) + 4 * 256) * sizeof(float);
+}
 static inline bool c_ok(const srk_tensor* t) {
   int vec = (t->c % 8 == 0 && t->c / 8 <= 256) ? 8 : 1;
-  return t->c / vec <= 256 && red_smem(t) <= 48 * 1024;
+  return t->c / vec <= 256 && red_total_smem(t, 2 * t->c + 1) <= 48 * 1024;
 }
+// partial rows of `slots` reductions with `nblk` blocks and `nv` values each must fit the reduce workspace
+static inline bool red_fits(long long slots, long long nblk, int nv) {
+  return slots <= kRedTickets && slots * nblk * ((nv + 3) & ~3) <= (long long)kRedPartialFloats;
+}
+#define RED_WS_CHECK(ws, slots, nblk, nv, name)                                                              \
+  do {                                                                                                       \
+    SRK_REQUIRE((ws) != nullptr, "%s: reduce_ws is required (srk_reduce_workspace_bytes() bytes, zero-filled once)", name); \
+    SRK_REQUIRE(red_fits(slots, nblk, nv), "%s: reduction of %lld x %lld rows x %d values exceeds the reduce workspace", \
+                name, (long long)(slots), (long long)(nblk), (int)(nv));                                      \
+  } while (0)
 
-extern "C" int srk_bn_stats(const srk_tensor* y, float* sum, float* sumsq, void* stream) {
+extern "C" int64_t srk_reduce_workspace_bytes(void) { return (int64_t)kRedWsBytes; }
+
+extern "C" int srk_bn_stats(const srk_tensor* y, float* sums, void* reduce_ws, void* stream) {
   ACT_CHECK(y, "srk_bn_stats");
   SRK_REQUIRE(c_ok(y), "srk_bn_stats: unsupported channel count %d", y->c);
+  SRK_REQUIRE(sums != nullptr, "srk_bn_stats: null output");
   Geo g = geo_of(y); int blocks, ppb; reduce_grid(g, blocks, ppb);
-  DISPATCH_T_VEC(y, (launch_dep(PDL_BN, bn_stats_kernel<T, VEC>, dim3(blocks), dim3(256), red_smem(y), (cudaStream_t)stream,
-                        (const T*)y->data, g, ppb, sum, sumsq)));
+  RED_WS_CHECK(reduce_ws, 1, blocks, 2 * y->c, "srk_bn_stats");
+  const RedArgs ra = {red_tickets(reduce_ws), red_partials(reduce_ws)};
+  DISPATCH_T_VEC(y, (launch_dep(PDL_BN, bn_stats_kernel<T, VEC>, dim3(blocks), dim3(256), red_total_smem(y, 2 * y->c),
+                        (cudaStream_t)stream, (const T*)y->data, g, ppb, sums, ra, red_row_floats(y))));
   SRK_CUDA_LAUNCH_CHECK("bn_stats");
   return 0;
 }
@@ -963,15 +1037,18 @@ extern "C" int srk_bn_apply_train(const srk_tensor* y, const float* sum, const f
 extern "C" int srk_bn_bwd_reduce(const srk_tensor* dout, const srk_tensor* y, const float* mean,
                                  const float* invstd, const float* gamma, const float* beta,
                                  const float* alpha, float* dgamma, float* dbeta, float* dalpha,
-                                 void* stream) {
+                                 void* reduce_ws, void* stream) {
   ACT_CHECK(y, "srk_bn_bwd_reduce"); ACT_CHECK(dout, "srk_bn_bwd_reduce");
   SRK_REQUIRE(same_geometry(y, dout) && y->dtype == dout->dtype, "srk_bn_bwd_reduce: geometry mismatch");
   SRK_REQUIRE(c_ok(y), "srk_bn_bwd_reduce: unsupported channel count %d", y->c);
   ew_carveout_once();
   Geo g = geo_of(y); int blocks, ppb; reduce_grid(g, blocks, ppb);
-  DISPATCH_T_VEC(y, (launch_dep(PDL_BN, bn_bwd_reduce_kernel<T, VEC>, dim3(blocks), dim3(256), red_smem(y), (cudaStream_t)stream,
+  RED_WS_CHECK(reduce_ws, 1, blocks, 2 * y->c + 1, "srk_bn_bwd_reduce");
+  const RedArgs ra = {red_tickets(reduce_ws), red_partials(reduce_ws)};
+  DISPATCH_T_VEC(y, (launch_dep(PDL_BN, bn_bwd_reduce_kernel<T, VEC>, dim3(blocks), dim3(256),
+                        red_total_smem(y, 2 * y->c + 1), (cudaStream_t)stream,
                         (const T*)dout->data, (const T*)y->data, g, ppb, mean, invstd, gamma, beta,
-                        alpha, dgamma, dbeta, dalpha)));
+                        alpha, dgamma, dbeta, dalpha, ra, red_row_floats(y))));
   SRK_CUDA_LAUNCH_CHECK("bn_bwd_reduce");
   return 0;
 }
@@ -1011,32 +1088,41 @@ extern "C" int srk_bn_bwd_apply_raw(const srk_tensor* dout, const srk_tensor* y,
   return 0;
 }
 
-extern "C" int srk_act_bwd(const srk_tensor* dout, const srk_tensor* out, const srk_tensor* dz, int act,
-                           const float* alpha, float* dalpha, int pixel_unshuffle, int perm_tc,
-                           void* stream) {
+extern "C" int srk_act_bwd(const srk_tensor* dout, const srk_tensor* out, const srk_tensor* zsave,
+                           const srk_tensor* dz, int act, const float* alpha, float* dalpha, int pixel_unshuffle,
+                           int perm_tc, void* reduce_ws, void* stream) {
   ACT_CHECK(dout, "srk_act_bwd"); ACT_CHECK(out, "srk_act_bwd"); ACT_CHECK(dz, "srk_act_bwd");
   SRK_REQUIRE(same_geometry(dout, out) && dout->dtype == out->dtype && dz->dtype == out->dtype, "srk_act_bwd: geometry mismatch");
   SRK_REQUIRE(act != SRK_ACT_PRELU || alpha != nullptr, "srk_act_bwd: PReLU needs alpha");
   SRK_REQUIRE(c_ok(dz), "srk_act_bwd: unsupported channel count %d", dz->c);
+  if (zsave) {
+    ACT_CHECK(zsave, "srk_act_bwd");
+    SRK_REQUIRE(same_geometry(zsave, out) && zsave->dtype == out->dtype, "srk_act_bwd: zsave must match out");
+  }
   Geo g = geo_of(dz); int blocks, ppb; pixel_grid(g, blocks, ppb);
+  RedArgs ra = {nullptr, nullptr};
+  if (act == SRK_ACT_PRELU && dalpha) {
+    RED_WS_CHECK(reduce_ws, 1, blocks, 1, "srk_act_bwd");
+    ra.tickets = red_tickets(reduce_ws); ra.partials = red_partials(reduce_ws);
+  }
   if (pixel_unshuffle == 2) {
     SRK_REQUIRE(dz->c == 4 * out->c && out->h == 2 * dz->h && out->w == 2 * dz->w && dz->n == out->n,
                 "srk_act_bwd: unshuffle geometry mismatch");
     SRK_REQUIRE(!perm_tc || out->c % 8 == 0, "srk_act_bwd: perm_tc needs C %% 8 == 0");
     DISPATCH_T_VEC(dz, (act_bwd_unshuffle_kernel<T, VEC><<<blocks, 256, 0, (cudaStream_t)stream>>>(
-                           (const T*)dout->data, (const T*)out->data, g, ppb, out->c, act, alpha, dalpha,
-                           perm_tc, (T*)dz->data)));
+                           (const T*)dout->data, (const T*)out->data, zsave ? (const T*)zsave->data : nullptr, g, ppb,
+                           out->c, act, alpha, dalpha, ra, perm_tc, (T*)dz->data)));
   } else {
     SRK_REQUIRE(pixel_unshuffle == 0 && same_geometry(dz, out), "srk_act_bwd: geometry mismatch");
     DISPATCH_T_VEC(dz, (act_bwd_kernel<T, VEC><<<blocks, 256, 0, (cudaStream_t)stream>>>(
-                           (const T*)dout->data, (const T*)out->data, g, ppb, act, alpha, dalpha,
-                           (T*)dz->data)));
+                           (const T*)dout->data, (const T*)out->data, zsave ? (const T*)zsave->data : nullptr, g, ppb,
+                           act, alpha, dalpha, ra, (T*)dz->data)));
   }
   SRK_CUDA_LAUNCH_CHECK("act_bwd");
   return 0;
 }
 
-static int image_sum_launch(const srk_tensor* a, const srk_tensor* b, float scale, float* out,
+static int image_sum_launch(const srk_tensor* a, const srk_tensor* b, float scale, float* out, void* reduce_ws,
                             cudaStream_t st, const char* name) {
   Geo g = geo_of(a);
   long long img_pixels = (long long)g.Hp * g.Wp;
@@ -1047,17 +1133,18 @@ static int image_sum_launch(const srk_tensor* a, const srk_tensor* b, float scal
   int ppb = (int)((img_pixels + bpi - 1) / bpi);
   bpi = (int)((img_pixels + ppb - 1) / ppb);
   dim3 grid(bpi, g.N);
-  DISPATCH_T_VEC(a, (image_channel_sum_kernel<T, VEC><<<grid, 256, red_smem(a), st>>>(
-                        (const T*)a->data, b ? (const T*)b->data : nullptr, g, ppb, scale, out)));
+  RED_WS_CHECK(reduce_ws, g.N, bpi, a->c, name);
+  const RedArgs ra = {red_tickets(reduce_ws), red_partials(reduce_ws)};
+  DISPATCH_T_VEC(a, (image_channel_sum_kernel<T, VEC><<<grid, 256, red_total_smem(a, a->c), st>>>(
+                        (const T*)a->data, b ? (const T*)b->data : nullptr, g, ppb, scale, out, ra, red_row_floats(a))));
   SRK_CUDA_LAUNCH_CHECK(name);
   return 0;
 }
 
-extern "C" int srk_se_pool(const srk_tensor* r, float* pool, void* stream) {
+extern "C" int srk_se_pool(const srk_tensor* r, float* pool, void* reduce_ws, void* stream) {
   ACT_CHECK(r, "srk_se_pool");
   SRK_REQUIRE(c_ok(r), "srk_se_pool: unsupported channel count %d", r->c);
-  cudaMemsetAsync(pool, 0, sizeof(float) * (size_t)r->n * r->c, (cudaStream_t)stream);
-  return image_sum_launch(r, nullptr, 1.f / ((float)r->h * r->w), pool, (cudaStream_t)stream, "se_pool");
+  return image_sum_launch(r, nullptr, 1.f / ((float)r->h * r->w), pool, reduce_ws, (cudaStream_t)stream, "srk_se_pool");
 }
 
 extern "C" int srk_se_fc(const float* pool, const float* w1, const float* w2, int n, int c, int cr,
@@ -1081,11 +1168,12 @@ extern "C" int srk_se_apply(const srk_tensor* x, const srk_tensor* r, const floa
   return 0;
 }
 
-extern "C" int srk_se_bwd_reduce(const srk_tensor* dout, const srk_tensor* r, float* dgate_raw, void* stream) {
+extern "C" int srk_se_bwd_reduce(const srk_tensor* dout, const srk_tensor* r, float* dgate_raw, void* reduce_ws,
+                                 void* stream) {
   ACT_CHECK(r, "srk_se_bwd_reduce"); ACT_CHECK(dout, "srk_se_bwd_reduce");
   SRK_REQUIRE(same_geometry(r, dout) && r->dtype == dout->dtype, "srk_se_bwd_reduce: geometry mismatch");
   SRK_REQUIRE(c_ok(r), "srk_se_bwd_reduce: unsupported channel count %d", r->c);
-  return image_sum_launch(dout, r, 1.f, dgate_raw, (cudaStream_t)stream, "se_bwd_reduce");
+  return image_sum_launch(dout, r, 1.f, dgate_raw, reduce_ws, (cudaStream_t)stream, "srk_se_bwd_reduce");
 }
 
 extern "C" int srk_se_fc_bwd(const float* dgate_raw, const float* gate, const float* hidden,

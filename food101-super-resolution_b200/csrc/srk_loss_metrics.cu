@@ -6,6 +6,8 @@
 
 namespace srk {
 
+constexpr int kLossPartials = 148 * 8;    // upper bound of every reducing grid in this file (red_blocks)
+
 // ---- L1 / MSE -------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pixel_loss_fwd_kernel(const float* __restrict__ a,
     const float* __restrict__ b, long long n, int mode, double* __restrict__ acc) {
@@ -26,9 +28,20 @@ __global__ void __launch_bounds__(256) pixel_loss_fwd_kernel(const float* __rest
     for (int j = 0; j < 4; ++j) s += mode == 0 ? fabsf(d[j]) : d[j] * d[j];
   }
   double t = block_sum_d((double)s, red);
-  if (threadIdx.x == 0) atomicAdd(acc, t);
+  if (threadIdx.x == 0) acc[blockIdx.x] = t;      // per-block partial: summed in block order by the finishing kernel
 }
-__global__ void scale_to_float_kernel(const double* acc, double scale, float* out) { out[0] = (float)(acc[0] * scale); }
+// Fixed-order sum of `n` per-block partials by one 256-thread block (thread t takes partials t, t + 256, ...; then the
+// block tree of block_sum_d): the loss value does not depend on the order in which blocks retire.
+__device__ __forceinline__ double ordered_partial_sum(const double* part, int n, double* red) {
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += part[i];
+  return block_sum_d(s, red);
+}
+__global__ void __launch_bounds__(256) scale_to_float_kernel(const double* part, int n, double scale, float* out) {
+  __shared__ double red[32];
+  const double t = ordered_partial_sum(part, n, red);
+  if (threadIdx.x == 0) out[0] = (float)(t * scale);
+}
 
 __global__ void __launch_bounds__(256) pixel_loss_bwd_kernel(const float* __restrict__ a,
     const float* __restrict__ b, long long n, int mode, const float* __restrict__ gout,
@@ -53,7 +66,7 @@ struct NlpdPlan {
   long long sign_off[8];  // byte offsets from sign base
   long long g_off[2];     // float offsets
   long long floats, sign_bytes, total_bytes;
-  long long acc_off;      // byte offset of double acc[8]
+  long long acc_off;      // byte offset of double acc[8][kLossPartials] (per-block partial sums)
 };
 static NlpdPlan nlpd_plan(int n, int c, int h, int w, int L) {
   NlpdPlan p; p.L = L;
@@ -72,7 +85,7 @@ static NlpdPlan nlpd_plan(int n, int c, int h, int w, int L) {
   for (int l = 0; l < L; ++l) { p.sign_off[l] = sb; sb += (nc * p.h[l] * p.w[l] + 15) / 16 * 16; }
   p.sign_bytes = sb;
   p.acc_off = (p.floats * 4 + 15) / 16 * 16 + sb;
-  p.total_bytes = p.acc_off + 8 * sizeof(double);
+  p.total_bytes = p.acc_off + 8 * (long long)kLossPartials * sizeof(double);
   return p;
 }
 
@@ -88,7 +101,7 @@ __global__ void __launch_bounds__(256) nlpd_diff_kernel(const float* __restrict_
     d[i] = v; s += fabsf(v);
   }
   double t = block_sum_d((double)s, red);
-  if (threadIdx.x == 0) atomicAdd(acc, t);
+  if (threadIdx.x == 0) acc[blockIdx.x] = t;
 }
 
 // Row-wise iteration over an [NC][H][W] image stack: a block walks whole rows (several per pass when W is
@@ -211,7 +224,7 @@ __global__ void __launch_bounds__(256) nlpd_lap_abs_kernel(const float* __restri
     if (sign) sign[i] = sign_of(d);
   NLPD_LOOP_END
   double t = block_sum_d((double)s, red);
-  if (threadIdx.x == 0) atomicAdd(acc, t);
+  if (threadIdx.x == 0) acc[blockIdx.x] = t;
 }
 
 // Exact-2x levels (H = 2 h2, W = 2 w2; every level of a power-of-two crop): one thread per COARSE pixel produces its
@@ -247,14 +260,21 @@ __global__ void __launch_bounds__(256) nlpd_lap_abs_2x_kernel(const float* __res
     }
   NLPD_LOOP_END
   double t = block_sum_d((double)s, red);
-  if (threadIdx.x == 0) atomicAdd(acc, t);
+  if (threadIdx.x == 0) acc[blockIdx.x] = t;
 }
 
-struct NlpdWeights { double w[8]; };
-__global__ void nlpd_combine_kernel(const double* acc, NlpdWeights wt, float* loss) {
+struct NlpdWeights { double w[8]; int nblk[8]; };
+// acc: [8][kLossPartials] per-block partials of the L1 term (row 0) and of the pyramid levels (rows 1..)
+__global__ void __launch_bounds__(256) nlpd_combine_kernel(const double* acc, NlpdWeights wt, float* loss) {
+  __shared__ double red[32];
   double v = 0.0;
-  for (int i = 0; i < 8; ++i) v += acc[i] * wt.w[i];
-  loss[0] = (float)v;
+  for (int i = 0; i < 8; ++i) {
+    if (wt.nblk[i] == 0) continue;
+    const double t = ordered_partial_sum(acc + (size_t)i * kLossPartials, wt.nblk[i], red);
+    v += t * wt.w[i];     // valid in thread 0
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss[0] = (float)v;
 }
 
 // g_down[y][x] = G_next[y][x] - c_l * sum_{Y,X} Uy[Y][y] Ux[X][x] sign_l[Y][X]    (bilinear^T)
@@ -413,6 +433,10 @@ __global__ void __launch_bounds__(256) nlpd_bwd_up_2x_kernel(const signed char* 
 }
 
 // ---- PSNR / SSIM ------------------------------------------------------------------------------------
+// Per-image sum of squared errors: 16-byte loads (four pixels of both images per thread and step, two steps in
+// flight), fp32 partial per thread, fp64 from the warp level up.  The per-image totals are accumulated with fp64
+// atomics (a handful of blocks per image): order-dependent only at the 1e-16 relative level, far inside the
+// 0.01 dB the metric is specified to.
 __global__ void __launch_bounds__(256) psnr_sse_kernel(const float* __restrict__ a, const float* __restrict__ b,
     long long per_image, int clamp01, double* __restrict__ sse) {
   __shared__ double red[32];
@@ -420,12 +444,30 @@ __global__ void __launch_bounds__(256) psnr_sse_kernel(const float* __restrict__
   const float* pa = a + (long long)n * per_image;
   const float* pb = b + (long long)n * per_image;
   float s = 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_image;
-       i += (long long)gridDim.x * blockDim.x) {
-    float x = pa[i], y = pb[i];
+  auto term = [&](float x, float y) {
     if (clamp01) { x = fminf(fmaxf(x, 0.f), 1.f); y = fminf(fmaxf(y, 0.f), 1.f); }
-    float d = x - y;
+    const float d = x - y;
     s = fmaf(d, d, s);
+  };
+  const bool vec = (per_image & 3) == 0 && ((((uintptr_t)pa) | ((uintptr_t)pb)) & 15) == 0;
+  if (vec) {
+    const long long n4 = per_image >> 2, stride = (long long)gridDim.x * blockDim.x;
+    const float4* qa = reinterpret_cast<const float4*>(pa);
+    const float4* qb = reinterpret_cast<const float4*>(pb);
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    for (; i + stride < n4; i += 2 * stride) {
+      const float4 x0 = __ldg(qa + i), y0 = __ldg(qb + i), x1 = __ldg(qa + i + stride), y1 = __ldg(qb + i + stride);
+      term(x0.x, y0.x); term(x0.y, y0.y); term(x0.z, y0.z); term(x0.w, y0.w);
+      term(x1.x, y1.x); term(x1.y, y1.y); term(x1.z, y1.z); term(x1.w, y1.w);
+    }
+    if (i < n4) {
+      const float4 x0 = __ldg(qa + i), y0 = __ldg(qb + i);
+      term(x0.x, y0.x); term(x0.y, y0.y); term(x0.z, y0.z); term(x0.w, y0.w);
+    }
+  } else {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_image;
+         i += (long long)gridDim.x * blockDim.x)
+      term(pa[i], pb[i]);
   }
   double t = block_sum_d((double)s, red);
   if (threadIdx.x == 0) atomicAdd(&sse[n], t);
@@ -539,7 +581,12 @@ struct AdamTable {
   int n[ADAM_MT];
 };
 __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamTable tb, float lr, float b1, float b2, float eps,
-    const long long* __restrict__ step, float grad_scale) {
+    const long long* __restrict__ step, float grad_scale, const float* __restrict__ lr_dev,
+    const float* __restrict__ scale_dev) {
+  // device-resident learning rate / gradient scale: a captured graph keeps working when a scheduler changes the
+  // rate, and a gradient-norm clip can feed its factor without a host round trip
+  if (lr_dev) lr = lr_dev[0];
+  if (scale_dev) grad_scale *= scale_dev[0];
   const int t = blockIdx.y;
   const int n = tb.n[t];
   const int i0 = blockIdx.x * 1024;
@@ -592,13 +639,15 @@ static inline int red_blocks(long long n, int per_thread) {
   return (int)b;
 }
 
+extern "C" int64_t srk_pixel_loss_scratch_bytes(void) { return (int64_t)kLossPartials * sizeof(double); }
+
 extern "C" int srk_pixel_loss_fwd(const float* sr, const float* hr, int64_t numel, int mode, float* loss,
                                   double* scratch, void* stream) {
   SRK_REQUIRE(numel > 0 && (mode == 0 || mode == 1), "srk_pixel_loss_fwd: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  cudaMemsetAsync(scratch, 0, sizeof(double), st);
-  pixel_loss_fwd_kernel<<<red_blocks(numel, 16), 256, 0, st>>>(sr, hr, numel, mode, scratch);
-  scale_to_float_kernel<<<1, 1, 0, st>>>(scratch, 1.0 / (double)numel, loss);
+  const int blocks = red_blocks(numel, 16);   // <= kLossPartials: scratch holds one double per block
+  pixel_loss_fwd_kernel<<<blocks, 256, 0, st>>>(sr, hr, numel, mode, scratch);
+  scale_to_float_kernel<<<1, 256, 0, st>>>(scratch, blocks, 1.0 / (double)numel, loss);
   SRK_CUDA_LAUNCH_CHECK("pixel_loss_fwd");
   return 0;
 }
@@ -627,11 +676,11 @@ extern "C" int srk_nlpd_fwd(const float* sr, const float* hr, int n, int c, int 
   signed char* sbase = (signed char*)workspace + (p.floats * 4 + 15) / 16 * 16;
   double* acc = (double*)((char*)workspace + p.acc_off);
   const int NC = n * c;
-  cudaMemsetAsync(acc, 0, 8 * sizeof(double), st);
   long long n0 = (long long)NC * h * w;
-  nlpd_diff_kernel<<<resident_cap(nlpd_diff_kernel, red_blocks(n0, 8)), 256, 0, st>>>(sr, hr, n0, clamp01, wsf + p.cur_off[0], acc);
   NlpdWeights wt;
-  for (int i = 0; i < 8; ++i) wt.w[i] = 0.0;
+  for (int i = 0; i < 8; ++i) { wt.w[i] = 0.0; wt.nblk[i] = 0; }
+  wt.nblk[0] = resident_cap(nlpd_diff_kernel, red_blocks(n0, 8));
+  nlpd_diff_kernel<<<wt.nblk[0], 256, 0, st>>>(sr, hr, n0, clamp01, wsf + p.cur_off[0], acc);
   wt.w[0] = (double)alpha / (double)n0;
   for (int l = 0; l < levels; ++l) {
     int H = p.h[l], W = p.w[l], h2 = p.h[l + 1], w2 = p.w[l + 1];
@@ -641,13 +690,17 @@ extern "C" int srk_nlpd_fwd(const float* sr, const float* hr, int n, int c, int 
     else
       nlpd_blur_down_kernel<<<resident_cap(nlpd_blur_down_kernel, red_blocks(nd, 2)), 256, 0, st>>>(wsf + p.cur_off[l], NC, H, W, h2, w2, kernel25, wsf + p.cur_off[l + 1]);
     float sy = (float)((double)h2 / H), sx = (float)((double)w2 / W);
-    if (nlpd_2x() && H == 2 * h2 && W == 2 * w2)
-      nlpd_lap_abs_2x_kernel<<<resident_cap(nlpd_lap_abs_2x_kernel, red_blocks(nd, 1)), 256, 0, st>>>(wsf + p.cur_off[l], wsf + p.cur_off[l + 1], NC, H, W, h2, w2, sbase + p.sign_off[l], acc + 1 + l);
-    else
-      nlpd_lap_abs_kernel<<<resident_cap(nlpd_lap_abs_kernel, red_blocks(nu, 4)), 256, 0, st>>>(wsf + p.cur_off[l], wsf + p.cur_off[l + 1], NC, H, W, h2, w2, sy, sx, sbase + p.sign_off[l], acc + 1 + l);
+    double* acc_l = acc + (size_t)(1 + l) * kLossPartials;
+    if (nlpd_2x() && H == 2 * h2 && W == 2 * w2) {
+      wt.nblk[1 + l] = resident_cap(nlpd_lap_abs_2x_kernel, red_blocks(nd, 1));
+      nlpd_lap_abs_2x_kernel<<<wt.nblk[1 + l], 256, 0, st>>>(wsf + p.cur_off[l], wsf + p.cur_off[l + 1], NC, H, W, h2, w2, sbase + p.sign_off[l], acc_l);
+    } else {
+      wt.nblk[1 + l] = resident_cap(nlpd_lap_abs_kernel, red_blocks(nu, 4));
+      nlpd_lap_abs_kernel<<<wt.nblk[1 + l], 256, 0, st>>>(wsf + p.cur_off[l], wsf + p.cur_off[l + 1], NC, H, W, h2, w2, sy, sx, sbase + p.sign_off[l], acc_l);
+    }
     wt.w[1 + l] = (1.0 - (double)alpha) / (double)nu;
   }
-  nlpd_combine_kernel<<<1, 1, 0, st>>>(acc, wt, loss);
+  nlpd_combine_kernel<<<1, 256, 0, st>>>(acc, wt, loss);
   SRK_CUDA_LAUNCH_CHECK("nlpd_fwd");
   return 0;
 }
@@ -731,7 +784,8 @@ extern "C" int srk_adam_step(float* param, const float* grad, float* exp_avg, fl
 
 extern "C" int srk_adam_multi(int count, float* const* params, const float* const* grads, float* const* exp_avg,
                               float* const* exp_avg_sq, const int64_t* numel, float lr, float beta1, float beta2,
-                              float eps, const int64_t* step_count, float grad_scale, void* stream) {
+                              float eps, const int64_t* step_count, float grad_scale, const float* lr_dev,
+                              const float* grad_scale_dev, void* stream) {
   SRK_REQUIRE(count >= 0, "srk_adam_multi: negative count");
   for (int base = 0; base < count; base += ADAM_MT) {
     AdamTable tb;
@@ -749,7 +803,7 @@ extern "C" int srk_adam_multi(int count, float* const* params, const float* cons
     }
     dim3 grid((unsigned)((mx + 1023) / 1024), (unsigned)c);
     adam_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tb, lr, beta1, beta2, eps, (const long long*)step_count,
-                                                              grad_scale);
+                                                              grad_scale, lr_dev, grad_scale_dev);
     SRK_CUDA_LAUNCH_CHECK("adam_multi");
   }
   return 0;

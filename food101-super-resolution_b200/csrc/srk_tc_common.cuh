@@ -233,9 +233,11 @@ struct BnRedArgs {
 };
 // variant: 0 per-tap, 1 folded taps, 2 per-tap on CTA pairs, 3 CTA pairs with 128-channel PixelShuffle passes.
 // Returns 0 ok, 1 error, -1 "slab does not fit" (the caller falls back to the per-tap kernel of srk_conv_tc.cu).
+// reduce_ws: reduce workspace (required with stats_sum / br); zsave: optional pre-activation copy for PReLU (bf16, y geometry).
 int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout, const float* bias,
                            int act, const float* alpha, const srk_tensor* residual, int shuffle, float* stats_sum,
-                           float* stats_sumsq, void* workspace, int variant, cudaStream_t st, const BnRedArgs* br);
+                           float* stats_sumsq, void* workspace, int variant, cudaStream_t st, const BnRedArgs* br,
+                           void* reduce_ws, void* zsave);
 
 // ---- host: TMA descriptor encoding through the driver entry point (no link-time libcuda dependency) ----
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -29,7 +29,7 @@ class _PixelLoss(torch.autograd.Function):
         sr = sr.contiguous().float()
         hr = hr.contiguous().float()
         loss = torch.empty((), dtype=torch.float32, device=sr.device)
-        scratch = torch.empty((1,), dtype=torch.float64, device=sr.device)
+        scratch = torch.empty((L.cdll.srk_pixel_loss_scratch_bytes() // 8,), dtype=torch.float64, device=sr.device)
         L.call("srk_pixel_loss_fwd", sr.data_ptr(), hr.data_ptr(), sr.numel(), mode, loss.data_ptr(),
                scratch.data_ptr(), ops.stream_ptr())
         ctx.save_for_backward(sr, hr)
@@ -202,7 +202,11 @@ def get_loss_function(name, device):
     if name == "mse":
         return MSELoss()
     if name == "perceptual":
-        return PerceptualLoss(device)
+        # the reference always loads the ImageNet checkpoint (loss.py:23); SRK_VGG_WEIGHTS=none|<state-dict path> builds the
+        # same module without a download (offline boxes, tests)
+        import os
+        w = os.environ.get("SRK_VGG_WEIGHTS", "DEFAULT")
+        return PerceptualLoss(device, weights=None if w.lower() == "none" else w)
     if name == "nlpd":
         return NLPDLoss(device=device).to(device)
     raise ValueError(f"Unknown loss function: {name}")

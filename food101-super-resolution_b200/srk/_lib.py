@@ -32,31 +32,33 @@ SIGNATURES = {
     "srk_last_error": (c_char_p, []),
     "srk_version": (c_int, []),
     "srk_conv_tc_supported": (c_int, [c_int] * 6),
-    "srk_conv_fprop": (c_int, [_T, _T, _P, c_int, c_int, c_int, c_int, _P, c_int, _P, _T, c_int, c_int, _P, _P, _P, _P]),
+    "srk_conv_fprop": (c_int, [_T, _T, _P, c_int, c_int, c_int, c_int, _P, c_int, _P, _T, c_int, c_int, _P, _P, _T, _P, _P]),
+    "srk_reduce_workspace_bytes": (c_int64, []),
+    "srk_pixel_loss_scratch_bytes": (c_int64, []),
     "srk_conv_fprop_workspace_bytes": (c_int64, [_T, c_int]),
     "srk_conv_wgrad": (c_int, [_T, _T, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
-    "srk_conv_rgbout_bwd_unshuffle": (c_int, [_T, _T, _P, _T, _P, _P, _P, _P, c_int, _P, _P]),
+    "srk_conv_rgbout_bwd_unshuffle": (c_int, [_T, _T, _T, _P, _T, _P, _P, _P, _P, c_int, _P, _P]),
     "srk_conv_wgrad_workspace_bytes": (c_int64, [_T, _T, c_int, c_int, c_int]),
     "srk_conv_rgb_workspace_bytes": (c_int64, [c_int]),
-    "srk_conv_rgb_fprop": (c_int, [_T, _T, _P, c_int, _P, c_int, _P, _P]),
+    "srk_conv_rgb_fprop": (c_int, [_T, _T, _P, c_int, _P, c_int, _P, _T, _P]),
     "srk_conv_rgb_bwd": (c_int, [_T, _T, _P, _T, _P, _P, c_int, c_int, _P, _P]),
     "srk_weight_pack": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "srk_weight_pack_bytes": (c_int64, [c_int] * 5),
     "srk_weight_pack_multi": (c_int, [c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "srk_act_bwd": (c_int, [_T, _T, _T, c_int, _P, _P, c_int, c_int, _P]),
+    "srk_act_bwd": (c_int, [_T, _T, _T, _T, c_int, _P, _P, c_int, c_int, _P, _P]),
     "srk_bn_stats": (c_int, [_T, _P, _P, _P]),
     "srk_bn_finalize": (c_int, [_P, _P, c_int, c_int64, c_float, c_float, _P, _P, _P, _P, _P, _P]),
     "srk_bn_eval_params": (c_int, [_P, _P, c_int, c_float, _P, _P, _P]),
     "srk_bn_apply": (c_int, [_T, _P, _P, _P, _P, _P, _T, _T, _P]),
     "srk_bn_apply_train": (c_int, [_T, _P, _P, c_int64, c_float, c_float, _P, _P, _P, _P, _P, _P, _P, _P, _T, _T, _P]),
-    "srk_bn_bwd_reduce": (c_int, [_T, _T, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "srk_bn_bwd_reduce": (c_int, [_T, _T, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "srk_bn_bwd_apply": (c_int, [_T, _T, _P, _P, _P, _P, _P, _P, _P, c_int, _T, _P]),
     "srk_bn_bwd_apply_raw": (c_int, [_T, _T, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _T, _P]),
-    "srk_conv_dgrad_bnred": (c_int, [_T, _T, _P, _T, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "srk_se_pool": (c_int, [_T, _P, _P]),
+    "srk_conv_dgrad_bnred": (c_int, [_T, _T, _P, _T, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "srk_se_pool": (c_int, [_T, _P, _P, _P]),
     "srk_se_fc": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P]),
     "srk_se_apply": (c_int, [_T, _T, _P, c_float, _T, _P]),
-    "srk_se_bwd_reduce": (c_int, [_T, _T, _P, _P]),
+    "srk_se_bwd_reduce": (c_int, [_T, _T, _P, _P, _P]),
     "srk_se_fc_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P, _P, _P, _P]),
     "srk_se_bwd_apply": (c_int, [_T, _P, _P, c_float, _T, _P]),
     "srk_image_to_act": (c_int, [_T, _T, _P]),
@@ -73,7 +75,7 @@ SIGNATURES = {
     "srk_psnr_sse": (c_int, [_P, _P, c_int, c_int64, c_int, _P, _P]),
     "srk_ssim": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "srk_adam_step": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, _P, c_float, _P]),
-    "srk_adam_multi": (c_int, [c_int, _P, _P, _P, _P, _P, c_float, c_float, c_float, c_float, _P, c_float, _P]),
+    "srk_adam_multi": (c_int, [c_int, _P, _P, _P, _P, _P, c_float, c_float, c_float, c_float, _P, c_float, _P, _P, _P]),
     "srk_tc_probe": (c_int, [c_int, POINTER(c_float), c_int]),
 }
 
@@ -92,7 +94,7 @@ for _name, (_res, _args) in SIGNATURES.items():
 launch_calls = 0
 _NO_COUNT = {"srk_last_error", "srk_version", "srk_conv_tc_supported", "srk_weight_pack_bytes",
              "srk_conv_wgrad_workspace_bytes", "srk_nlpd_workspace_bytes", "srk_conv_rgb_workspace_bytes",
-             "srk_conv_fprop_workspace_bytes"}
+             "srk_conv_fprop_workspace_bytes", "srk_reduce_workspace_bytes", "srk_pixel_loss_scratch_bytes"}
 
 
 def last_error():

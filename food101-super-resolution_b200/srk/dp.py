@@ -94,3 +94,12 @@ def broadcast_parameters(module, src=0, group=None):
         return
     for t in list(module.parameters()) + list(module.buffers()):
         dist.broadcast(t.data, src=src, group=group)
+
+
+def broadcast_buffers(module, src=0, group=None):
+    """BatchNorm running statistics are per rank during training (DDP semantics): before an evaluation whose
+    result steers control flow, and before a checkpoint, every rank takes rank `src`'s buffers."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    for t in module.buffers():
+        dist.broadcast(t.data, src=src, group=group)

@@ -19,22 +19,32 @@ def my_batches(n_batches, rank, world):
 
 
 @torch.no_grad()
-def evaluate(model, batches, device, rank=0, world=1, metrics_fn=None, group=None):
-    """batches: sequence of (lr, hr) NCHW fp32 tensors (host or device).  Returns {"psnr","ssim","nlpd","lpips",
-    "batches"} averaged over all batches of all ranks.  Infinite PSNR (identical images) propagates as inf."""
+def evaluate(model, batches, device, rank=0, world=1, metrics_fn=None, group=None, criterion=None):
+    """batches: sequence or iterable (e.g. a DataLoader - identical on every rank) of (lr, hr) NCHW fp32 tensors (host or
+    device).  Returns {"psnr","ssim","nlpd","lpips","batches"} averaged over all batches of all ranks - the same numbers
+    on every rank, so that schedulers and early stopping driven by them stay in lockstep.  criterion: optional loss
+    module; adds "loss" (mean of the per-batch values, reference train.py:155-162).  Infinite PSNR (identical images)
+    propagates as inf."""
     if metrics_fn is None:
         from src.metrics import MetricsCalculator
         metrics_fn = MetricsCalculator(device).compute
     was_training = getattr(model, "training", False)
     if hasattr(model, "eval"):
         model.eval()
-    sums = [0.0] * len(KEYS)
+    keys = KEYS + (("loss",) if criterion is not None else ())
+    sums = [0.0] * len(keys)
     count = 0
-    for i in my_batches(len(batches), rank, world):
-        lr, hr = batches[i]
+    if hasattr(batches, "__getitem__"):
+        mine = (batches[i] for i in my_batches(len(batches), rank, world))
+    else:
+        mine = (b for i, b in enumerate(batches) if i % world == rank)
+    for lr, hr in mine:
         lr, hr = lr.to(device, non_blocking=True), hr.to(device, non_blocking=True)
-        res = metrics_fn(model(lr), hr)
-        for k, key in enumerate(KEYS):
+        sr = model(lr)
+        res = dict(metrics_fn(sr, hr))
+        if criterion is not None:
+            res["loss"] = float(criterion(sr, hr))
+        for k, key in enumerate(keys):
             v = res.get(key, float("nan"))
             sums[k] += v
         count += 1
@@ -48,10 +58,10 @@ def evaluate(model, batches, device, rank=0, world=1, metrics_fn=None, group=Non
     if world > 1:
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     buf = buf.cpu().tolist()
-    n = len(KEYS)
+    n = len(keys)
     total = buf[2 * n]
     out = {"batches": int(total)}
-    for k, key in enumerate(KEYS):
+    for k, key in enumerate(keys):
         if buf[n + k] >= 1000.0:
             out[key] = float("nan")
         elif buf[n + k] >= 1.0:

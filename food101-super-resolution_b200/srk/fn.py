@@ -55,20 +55,22 @@ class ConvAct(torch.autograd.Function):
         assert not (out_img and act != L.ACT_NONE), "activated outputs are kept in the act layout"
         # with pixel-shuffle the activation is applied by the conv epilogue before the store remap
         # (a single-alpha PReLU / ReLU commutes with the permutation, models.py:117-119)
-        y, used_tc = ops.conv_fprop(x, x_img, weight, bias, act, alpha, residual, shuffle, out_img, out_dtype)
-        ctx.save_for_backward(x, weight, alpha, y if act != L.ACT_NONE else None, bias)
+        # z: pre-activation copy the epilogue fills in only while the PReLU slope is <= 0 (ops.prelu_z_like)
+        y, used_tc, z = ops.conv_fprop(x, x_img, weight, bias, act, alpha, residual, shuffle, out_img, out_dtype,
+                                       zsave=True)
+        ctx.save_for_backward(x, weight, alpha, y if act != L.ACT_NONE else None, bias, z)
         ctx.cfg = (act, shuffle, x_img, out_img, bias is not None, residual is not None, used_tc)
         return y
 
     @staticmethod
     def backward(ctx, dout):
-        x, weight, alpha, y, bias = ctx.saved_tensors
+        x, weight, alpha, y, bias, z = ctx.saved_tensors
         act, shuffle, x_img, out_img, has_bias, has_res, used_tc = ctx.cfg
         dout = dout.contiguous()
         dalpha = None
         perm = False  # the tcgen05 path keeps the reference channel order
         if act != L.ACT_NONE or shuffle == 2:
-            dz, dalpha = ops.act_bwd(dout, y if y is not None else dout, act, alpha, shuffle, perm)
+            dz, dalpha = ops.act_bwd(dout, y if y is not None else dout, act, alpha, shuffle, perm, zsave=z)
             dz_img = False
         else:
             dz, dz_img = dout, out_img
@@ -98,17 +100,18 @@ class UpShuffleThenRGB(torch.autograd.Function):
     def forward(ctx, x, w_up, b_up, alpha, w_out, b_out):
         ops.require_cuda(x, "upsample tail")
         x = x.contiguous()
-        y, _ = ops.conv_fprop(x, False, w_up, b_up, L.ACT_PRELU, alpha, None, 2, False, x.dtype)
+        y, _, z = ops.conv_fprop(x, False, w_up, b_up, L.ACT_PRELU, alpha, None, 2, False, x.dtype, zsave=True)
         img, _ = ops.conv_fprop(y, False, w_out, b_out, L.ACT_NONE, None, None, 0, True, torch.float32)
-        ctx.save_for_backward(x, y, w_up, alpha, w_out, b_up)
+        ctx.save_for_backward(x, y, w_up, alpha, w_out, b_up, z)
         ctx.cfg = (b_up is not None, b_out is not None)
         return img
 
     @staticmethod
     def backward(ctx, dimg):
-        x, y, w_up, alpha, w_out, b_up = ctx.saved_tensors
+        x, y, w_up, alpha, w_out, b_up, z = ctx.saved_tensors
         hb_up, hb_out = ctx.cfg
-        dz, dw_out, db_out, dalpha = ops.conv_rgbout_bwd_unshuffle(y, dimg.contiguous().float(), w_out, alpha, hb_out)
+        dz, dw_out, db_out, dalpha = ops.conv_rgbout_bwd_unshuffle(y, dimg.contiguous().float(), w_out, alpha, hb_out,
+                                                                   zsave=z)
         dx = ops.conv_dgrad(dz, False, w_up, None, x.dtype, perm_tc=True) if _needs(ctx, 0) else None
         dw_up, db_up = ops.conv_wgrad(x, False, dz, False, w_up, hb_up, perm_tc=True, side=True, bias=b_up)
         return dx, dw_up, db_up, dalpha, dw_out, db_out
@@ -132,7 +135,7 @@ def _conv_bn_forward(x, w, b, bn_params, bn_buffers, training, eps, momentum, al
     rm, rv, nbt = bn_buffers
     sums = None
     if ops.bn_needs_batch_stats(rm, training):  # the conv epilogue accumulates the batch statistics
-        sums = ops.zeros((2, w.shape[0]), x.device)
+        sums = torch.empty((2, w.shape[0]), dtype=torch.float32, device=x.device)
     y, used_tc = ops.conv_fprop(x, False, w, b, L.ACT_NONE, None, None, 0, False, x.dtype, bn_sums=sums)
     out, stats = ops.bn_forward(y, gamma, beta, rm, rv, nbt, training, eps, momentum, alpha, residual, sums=sums)
     return y, out, stats
@@ -215,22 +218,22 @@ class AttnBlock(torch.autograd.Function):
     def forward(ctx, x, w1, b1, alpha, w2, b2, fc1, fc2, scale):
         ops.require_cuda(x, "attention residual block")
         x = x.contiguous()
-        a, _ = ops.conv_fprop(x, False, w1, b1, L.ACT_PRELU, alpha, None, 0, False, x.dtype)
+        a, _, za = ops.conv_fprop(x, False, w1, b1, L.ACT_PRELU, alpha, None, 0, False, x.dtype, zsave=True)
         r, _ = ops.conv_fprop(a, False, w2, b2, L.ACT_NONE, None, None, 0, False, x.dtype)
         out, pool, hidden, gate = ops.se_forward(x, r, fc1, fc2, scale)
-        ctx.save_for_backward(x, a, r, pool, hidden, gate, w1, alpha, w2, fc1, fc2, b1, b2)
+        ctx.save_for_backward(x, a, r, pool, hidden, gate, w1, alpha, w2, fc1, fc2, b1, b2, za)
         ctx.cfg = (b1 is not None, b2 is not None, scale)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, a, r, pool, hidden, gate, w1, alpha, w2, fc1, fc2, b1, b2 = ctx.saved_tensors
+        x, a, r, pool, hidden, gate, w1, alpha, w2, fc1, fc2, b1, b2, za = ctx.saved_tensors
         hb1, hb2, scale = ctx.cfg
         dout = dout.contiguous()
         dr, dfc1, dfc2 = ops.se_backward(dout, r, pool, hidden, gate, fc1, fc2, scale)
         da = ops.conv_dgrad(dr, False, w2, None, a.dtype)
         dw2, db2 = ops.conv_wgrad(a, False, dr, False, w2, hb2, side=True, bias=b2)
-        dz1, dalpha = ops.act_bwd(da, a, L.ACT_PRELU, alpha, 0)
+        dz1, dalpha = ops.act_bwd(da, a, L.ACT_PRELU, alpha, 0, zsave=za)
         dx = ops.conv_dgrad(dz1, False, w1, dout, x.dtype)
         dw1, db1 = ops.conv_wgrad(x, False, dz1, False, w1, hb1, side=True, bias=b1)
         return dx, dw1, db1, dalpha, dw2, db2, dfc1, dfc2, None

@@ -114,11 +114,27 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+# ---- reduce workspace ----------------------------------------------------------------------------------
+# Cross-block reductions are deterministic (per-block partial rows folded in block order, include/srk.h
+# "deterministic reductions"): the reducing entry points take a workspace that is zero-filled once and must not be
+# shared by kernels that may run concurrently - one per (device, stream).
+_reduce_ws = {}
+
+
+def reduce_ws(device=None):
+    st = torch.cuda.current_stream(device)
+    key = (st.device.index, st.cuda_stream)
+    t = _reduce_ws.get(key)
+    if t is None:
+        t = torch.zeros((L.cdll.srk_reduce_workspace_bytes(),), dtype=torch.uint8, device=st.device)
+        _reduce_ws[key] = t
+    return t.data_ptr()
+
+
 # ---- zero-initialised scratch ------------------------------------------------------------------------
-# Many kernels accumulate small results with atomics (BN sums, PReLU-slope gradients, SE reductions) and need
-# zero-filled outputs.  Opt-in: a trainer calls begin_step() once per step; zeros() then hands out slices of one
-# buffer cleared by a single memset instead of launching a fill kernel per tensor.  Tensors obtained this way are
-# only valid until the next begin_step() (gradients must have been consumed by the optimizer by then).
+# No libsrk kernel needs zero-filled outputs any more (reductions write their results); begin_step() / zeros() stay
+# for callers that want many small zero tensors from one memset.  Tensors obtained this way are only valid until the
+# next begin_step().
 class _ZeroArena:
     buf = None
     off = 0
@@ -341,8 +357,8 @@ def conv_rgbout_bwd(x, dout, weight, need_dx, need_bias):
     one tcgen05 kernel produces dx (bf16 act), dW and db.  -> (dx or None, dw, db or None)"""
     cout, cin, r, s = weight.shape
     n, _, h, w = geometry(x, False)
-    dw = torch.zeros_like(weight, memory_format=torch.contiguous_format)
-    db = zeros((cout,), weight.device)
+    dw = torch.empty_like(weight, memory_format=torch.contiguous_format)    # written, not accumulated
+    db = torch.empty((cout,), dtype=torch.float32, device=weight.device)
     dx = new_act(n, cin, h, w, torch.bfloat16, x.device) if need_dx else None
     pk = packed_weight(weight, L.PACK_RGBOUT_DGRAD_TC, 0) if need_dx else None
     ws = _rgb_workspace(r, x.device)
@@ -353,20 +369,21 @@ def conv_rgbout_bwd(x, dout, weight, need_dx, need_bias):
     return dx, dw, (db if need_bias else None)
 
 
-def conv_rgbout_bwd_unshuffle(t64, dout_img, weight, alpha, need_bias):
+def conv_rgbout_bwd_unshuffle(t64, dout_img, weight, alpha, need_bias, zsave=None):
     """Backward of the 64 -> 3 output conv fused with the PReLU + PixelShuffle(2) backward of the upsample stage that
-    produced its input t64 (srk_conv_rgbout_bwd_unshuffle).  -> (dz [N, H/2+2, W/2+2, 256] bf16 with sub-pixel-major
-    channels, dw, db or None, dalpha[1])"""
+    produced its input t64 (srk_conv_rgbout_bwd_unshuffle); zsave: that stage's prelu_z copy.
+    -> (dz [N, H/2+2, W/2+2, 256] bf16 with sub-pixel-major channels, dw, db or None, dalpha[1])"""
     cout, cin, r, s = weight.shape
     n, _, h, w = geometry(t64, False)
-    dw = torch.zeros_like(weight, memory_format=torch.contiguous_format)
-    db = zeros((cout,), weight.device)
-    dalpha = zeros((1,), weight.device)
+    dw = torch.empty_like(weight, memory_format=torch.contiguous_format)
+    db = torch.empty((cout,), dtype=torch.float32, device=weight.device)
+    dalpha = torch.empty((1,), dtype=torch.float32, device=weight.device)
     dz = new_act(n, 4 * cin, h // 2, w // 2, torch.bfloat16, t64.device)
     pk = packed_weight(weight, L.PACK_RGBOUT_DGRAD_TC, 0)
     ws = _rgb_workspace(r, t64.device)
     _timed(("conv_rgbout_bwd_unshuffle", cin, cout, r, 2, n, h, w, True),
-           lambda: L.call("srk_conv_rgbout_bwd_unshuffle", img_desc(dout_img), act_desc(t64), pk.data_ptr(),
+           lambda: L.call("srk_conv_rgbout_bwd_unshuffle", img_desc(dout_img), act_desc(t64),
+                          act_desc(zsave) if zsave is not None else None, pk.data_ptr(),
                           act_desc(dz), dw.data_ptr(), db.data_ptr(), alpha.data_ptr(), dalpha.data_ptr(), r,
                           ws.data_ptr(), stream_ptr()))
     return dz, dw, (db if need_bias else None), dalpha
@@ -382,9 +399,16 @@ def _fprop_workspace(xd, kind, device):
     return torch.empty((nbytes,), dtype=torch.uint8, device=device) if nbytes > 0 else None
 
 
-def conv_fprop(x, x_img, weight, bias, act, alpha, residual, shuffle, out_img, out_dtype, bn_sums=None):
+def prelu_z_like(y):
+    """Buffer for the pre-activation copy a PReLU conv epilogue writes when its slope is <= 0 (include/srk.h, prelu_z).
+    Allocation only: while the slope is > 0 - the usual case - nothing ever touches it."""
+    return torch.empty_like(y)
+
+
+def conv_fprop(x, x_img, weight, bias, act, alpha, residual, shuffle, out_img, out_dtype, bn_sums=None, zsave=False):
     """y = [shuffle](act(conv(x, weight) + bias)) [+ residual]; stride 1, pad R//2.
-    bn_sums: optional zero-filled fp32 [2, Cout] that receives the per-channel sum / sum of squares of y."""
+    bn_sums: optional fp32 [2, Cout] that receives the per-channel sum / sum of squares of y.
+    zsave=True (PReLU, ACT output): also returns the prelu_z buffer -> (y, used_tc, z)."""
     n, cin, h, w = geometry(x, x_img)
     cout, wcin, r, s = weight.shape
     assert wcin == cin, "conv: input has %d channels, weight expects %d" % (cin, wcin)
@@ -392,10 +416,11 @@ def conv_fprop(x, x_img, weight, bias, act, alpha, residual, shuffle, out_img, o
             and shuffle == 0 and _rgb_tc_ok(r, s)):
         pk = packed_weight(weight, L.PACK_RGBIN_TC, 0)
         y = new_act(n, cout, h, w, out_dtype, x.device)
+        z = prelu_z_like(y) if (zsave and act == L.ACT_PRELU) else None
         _timed(("conv_rgbin_fprop", cin, cout, r, 0, n, h, w, True),
                lambda: L.call("srk_conv_rgb_fprop", img_desc(x), act_desc(y), pk.data_ptr(), r, _ptr(bias), act,
-                              _ptr(alpha), stream_ptr()))
-        return y, True
+                              _ptr(alpha), act_desc(z) if z is not None else None, stream_ptr()))
+        return (y, True, z) if zsave else (y, True)
     tc = 0 if x_img else tc_supported(cin, cout, r, s, x.dtype, shuffle)
     rgb_tc = tc == 2 and out_img and act == L.ACT_NONE and residual is None
     use_tc = rgb_tc or (tc == 1 and (not out_img) and out_dtype == torch.bfloat16)
@@ -411,12 +436,13 @@ def conv_fprop(x, x_img, weight, bias, act, alpha, residual, shuffle, out_img, o
     xd, yd = desc(x, x_img), desc(y, out_img)
     rd = desc(residual, out_img) if residual is not None else None
     ws = _fprop_workspace(xd, kind, x.device)
+    z = prelu_z_like(y) if (zsave and act == L.ACT_PRELU and not out_img) else None
     _timed(("conv_fprop", cin, cout, r, shuffle, n, h, w, use_tc),
            lambda: L.call("srk_conv_fprop", xd, yd, pk.data_ptr(), kind, cout, r, s, _ptr(bias), act,
-                          _ptr(alpha), rd, shuffle, L.IMPL_AUTO,
-                          bn_sums[0].data_ptr() if bn_sums is not None else None,
-                          bn_sums[1].data_ptr() if bn_sums is not None else None, _ptr(ws), stream_ptr()))
-    return y, use_tc
+                          _ptr(alpha), rd, shuffle, L.IMPL_AUTO, _ptr(bn_sums),
+                          reduce_ws(x.device) if bn_sums is not None else None,
+                          act_desc(z) if z is not None else None, _ptr(ws), stream_ptr()))
+    return (y, use_tc, z) if zsave else (y, use_tc)
 
 
 def conv_dgrad(dz, dz_img, weight, residual, out_dtype, perm_tc=False):
@@ -435,7 +461,7 @@ def conv_dgrad(dz, dz_img, weight, residual, out_dtype, perm_tc=False):
     ws = _fprop_workspace(dzd, kind, dz.device)
     _timed(("conv_dgrad", cout, cin, r, 0, n, h, w, use_tc),
            lambda: L.call("srk_conv_fprop", dzd, act_desc(dx), pk.data_ptr(), kind, cin, r, s,
-                          None, L.ACT_NONE, None, rd, 0, L.IMPL_AUTO, None, None, _ptr(ws), stream_ptr()))
+                          None, L.ACT_NONE, None, rd, 0, L.IMPL_AUTO, None, None, None, _ptr(ws), stream_ptr()))
     return dx
 
 
@@ -452,11 +478,12 @@ def conv_dgrad_bnred(dz, weight, z, stats, gamma, beta, alpha):
     n, c, h, w = geometry(dz, False)
     pk = packed_weight(weight, L.PACK_DGRAD_TC, 0)
     dx = new_act(n, cin, h, w, torch.bfloat16, dz.device)
-    red = zeros((2 * cin + 1,), dz.device)
+    red = torch.empty((2 * cin + 1,), dtype=torch.float32, device=dz.device)
     rc = L.cdll.srk_conv_dgrad_bnred(act_desc(dz), act_desc(dx), pk.data_ptr(), act_desc(z), stats[0].data_ptr(),
                                      stats[1].data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(alpha),
                                      red[:cin].data_ptr(), red[cin:2 * cin].data_ptr(),
-                                     red[2 * cin:].data_ptr() if alpha is not None else None, stream_ptr())
+                                     red[2 * cin:].data_ptr() if alpha is not None else None,
+                                     reduce_ws(dz.device), stream_ptr())
     if rc == 2:
         return None
     if rc != 0:
@@ -493,12 +520,13 @@ def conv_wgrad(x, x_img, dz, dz_img, weight, need_bias, perm_tc=False, side=Fals
         nbytes = L.cdll.srk_conv_wgrad_workspace_bytes(xd, dd, r, s, impl)
         ws = torch.empty((nbytes,), dtype=torch.uint8, device=weight.device) if nbytes > 0 else None
         n, _, h, w = geometry(x, x_img)
-        launch = lambda: _timed(("conv_wgrad", cin, cout, r, 0, n, h, w, nbytes > 0),
+        on_tc = impl != L.IMPL_SIMT and not x_img and not dz_img and x.dtype == torch.bfloat16 and r == 3
+        launch = lambda: _timed(("conv_wgrad", cin, cout, r, 0, n, h, w, on_tc),
                                 lambda: L.call("srk_conv_wgrad", xd, dd, dw.data_ptr(), _ptr(db), r, s, impl, 0,
                                                1 if perm_tc else 0, _ptr(ws), stream_ptr()))
         return finish(launch, (x, dz, ws), dw, db)
-    dw = torch.zeros_like(weight, memory_format=torch.contiguous_format)
-    db = torch.zeros((cout,), dtype=torch.float32, device=weight.device) if need_bias else None
+    dw = torch.empty_like(weight, memory_format=torch.contiguous_format)     # written, not accumulated
+    db = torch.empty((cout,), dtype=torch.float32, device=weight.device) if need_bias else None
     n, _, h, w = geometry(x, True)
     ws = _rgb_workspace(r, x.device)
     launch = lambda: _timed(("conv_rgbin_wgrad", cin, cout, r, 0, n, h, w, True),
@@ -507,16 +535,18 @@ def conv_wgrad(x, x_img, dz, dz_img, weight, need_bias, perm_tc=False, side=Fals
     return finish(launch, (x, dz, ws), dw, db)
 
 
-def act_bwd(dout, out, act, alpha, unshuffle, perm_tc=False):
-    """gradient of the pre-activation (conv-output geometry) from the saved post-activation tensor"""
+def act_bwd(dout, out, act, alpha, unshuffle, perm_tc=False, zsave=None):
+    """gradient of the pre-activation (conv-output geometry) from the saved post-activation tensor (and, for a PReLU
+    whose slope is <= 0, from the pre-activation copy `zsave` the forward epilogue wrote)"""
     n, c, h, w = geometry(out, False)
     if unshuffle == 2:
         dz = new_act(n, 4 * c, h // 2, w // 2, out.dtype, out.device)
     else:
         dz = torch.empty_like(out)
-    dalpha = zeros((1,), out.device) if act == L.ACT_PRELU else None
-    L.call("srk_act_bwd", act_desc(dout), act_desc(out), act_desc(dz), act, _ptr(alpha), _ptr(dalpha),
-           unshuffle, 1 if perm_tc else 0, stream_ptr())
+    dalpha = torch.empty((1,), dtype=torch.float32, device=out.device) if act == L.ACT_PRELU else None
+    L.call("srk_act_bwd", act_desc(dout), act_desc(out), act_desc(zsave) if zsave is not None else None, act_desc(dz),
+           act, _ptr(alpha), _ptr(dalpha), unshuffle, 1 if perm_tc else 0,
+           reduce_ws(out.device) if dalpha is not None else None, stream_ptr())
     return dz, dalpha
 
 
@@ -535,8 +565,8 @@ def bn_forward(y, gamma, beta, running_mean, running_var, nbt, training, eps, mo
     st = stream_ptr()
     if training or running_mean is None:
         if sums is None:
-            sums = zeros((2, c), dev)
-            L.call("srk_bn_stats", act_desc(y), sums[0].data_ptr(), sums[1].data_ptr(), st)
+            sums = torch.empty((2, c), dtype=torch.float32, device=dev)
+            L.call("srk_bn_stats", act_desc(y), sums.data_ptr(), reduce_ws(dev), st)
         upd = training and running_mean is not None
         # statistics -> mean / invstd (+ running-stat update) happen inside the apply kernel: one launch per layer
         out = torch.empty_like(y)
@@ -567,13 +597,13 @@ def bn_backward(dout, y, stats, gamma, beta, alpha, batch_stats, pre=None):
                gamma.data_ptr(), beta.data_ptr(), _ptr(alpha), sum_g.data_ptr(), sum_gz.data_ptr(),
                1 if batch_stats else 0, dgamma.data_ptr(), act_desc(dy), stream_ptr())
         return dy, dgamma, sum_g, (dalpha if alpha is not None else None)
-    red = zeros((2 * c + 1,), dev)
+    red = torch.empty((2 * c + 1,), dtype=torch.float32, device=dev)
     dgamma, dbeta, dalpha = red[:c], red[c:2 * c], red[2 * c:]
     mean, invstd = stats[0], stats[1]
     st = stream_ptr()
     L.call("srk_bn_bwd_reduce", act_desc(dout), act_desc(y), mean.data_ptr(), invstd.data_ptr(),
            gamma.data_ptr(), beta.data_ptr(), _ptr(alpha), dgamma.data_ptr(), dbeta.data_ptr(),
-           dalpha.data_ptr() if alpha is not None else None, st)
+           dalpha.data_ptr() if alpha is not None else None, reduce_ws(dev), st)
     dy = torch.empty_like(y)
     L.call("srk_bn_bwd_apply", act_desc(dout), act_desc(y), mean.data_ptr(), invstd.data_ptr(),
            gamma.data_ptr(), beta.data_ptr(), _ptr(alpha), dgamma.data_ptr(), dbeta.data_ptr(),
@@ -591,7 +621,7 @@ def se_forward(x, r, w1, w2, scale):
     hidden = torch.empty((n, cr), dtype=torch.float32, device=dev)
     gate = torch.empty((n, c), dtype=torch.float32, device=dev)
     st = stream_ptr()
-    L.call("srk_se_pool", act_desc(r), pool.data_ptr(), st)
+    L.call("srk_se_pool", act_desc(r), pool.data_ptr(), reduce_ws(dev), st)
     L.call("srk_se_fc", pool.data_ptr(), w1.data_ptr(), w2.data_ptr(), n, c, cr, hidden.data_ptr(),
            gate.data_ptr(), st)
     out = torch.empty_like(r)
@@ -606,10 +636,10 @@ def se_backward(dout, r, pool, hidden, gate, w1, w2, scale):
     cr = w1.shape[0]
     dev = r.device
     st = stream_ptr()
-    dgate_raw = zeros((n, c), dev)
-    L.call("srk_se_bwd_reduce", act_desc(dout), act_desc(r), dgate_raw.data_ptr(), st)
-    dw1 = torch.zeros_like(w1, memory_format=torch.contiguous_format)
-    dw2 = torch.zeros_like(w2, memory_format=torch.contiguous_format)
+    dgate_raw = torch.empty((n, c), dtype=torch.float32, device=dev)
+    L.call("srk_se_bwd_reduce", act_desc(dout), act_desc(r), dgate_raw.data_ptr(), reduce_ws(dev), st)
+    dw1 = torch.empty_like(w1, memory_format=torch.contiguous_format)     # written by the kernel
+    dw2 = torch.empty_like(w2, memory_format=torch.contiguous_format)
     # dpool [n][c] followed by the kernel's scratch (dz2 [n][c], dh [n][cr])
     dpool = torch.empty((2 * n * c + n * cr,), dtype=torch.float32, device=dev)
     L.call("srk_se_fc_bwd", dgate_raw.data_ptr(), gate.data_ptr(), hidden.data_ptr(), pool.data_ptr(),

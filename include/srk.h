@@ -70,14 +70,27 @@ int srk_conv_tc_supported(int cin, int cout, int r, int s, int dtype, int pixel_
  * +residual (models.py:185), PixelShuffle(2) store remap (models.py:118,121,160,163).
  * stride 1, "same" padding (pad = R/2), as every conv on the path.
  * `y` holds the output geometry; with pixel_shuffle=2, y is [N][Cout/4][2H][2W].
- * bn_sum / bn_sumsq (fp32 [Cout], accumulated, both NULL or both set): per-channel sum and sum of squares of
- * the conv output over interior pixels - the statistics native_batch_norm needs (models.py:47,50,114) -
- * produced by the conv epilogue from the fp32 accumulators on the tcgen05 path.
+ * bn_sums (fp32 [2][Cout], WRITTEN, or NULL): per-channel sum and sum of squares of the conv output over interior
+ * pixels - the statistics native_batch_norm needs (models.py:47,50,114) - produced by the conv epilogue from the
+ * fp32 accumulators on the tcgen05 path, summed in a fixed order (needs reduce_ws, see srk_reduce_workspace_bytes).
+ * prelu_z (or NULL; act = PReLU, ACT outputs): a tensor of y's geometry / dtype that receives the PRE-activation
+ * when - and only when - the slope is <= 0 (decided on the device).  nn.PReLU places no constraint on its slope
+ * (models.py:48,66,108,119,122); for a slope <= 0 the backward cannot recover sign(z) / z from the output and reads
+ * this copy instead (srk_act_bwd, srk_conv_rgbout_bwd_unshuffle).  Contents are undefined while the slope is > 0.
  */
 int srk_conv_fprop(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int pack_kind,
                    int cout, int r, int s, const float* bias, int act, const float* alpha,
-                   const srk_tensor* residual, int pixel_shuffle, int impl, float* bn_sum,
-                   float* bn_sumsq, void* workspace, void* stream);
+                   const srk_tensor* residual, int pixel_shuffle, int impl, float* bn_sums,
+                   void* reduce_ws, const srk_tensor* prelu_z, void* workspace, void* stream);
+
+/* ---- deterministic reductions -------------------------------------------------------------------
+ * No kernel of the training step accumulates floating-point values with atomics: every cross-block sum (BatchNorm
+ * statistics and their backward reductions, PReLU-slope and SE gradients, weight / bias gradients, loss values) is
+ * per-block partial rows + ONE fold in block-index order, so a step is bit-reproducible run to run.  The entry
+ * points that reduce take `reduce_ws`: a caller-owned buffer of srk_reduce_workspace_bytes() bytes, zero-filled ONCE
+ * when it is allocated (its tickets reset themselves), and not shared between streams whose kernels may run
+ * concurrently (one per stream). */
+int64_t srk_reduce_workspace_bytes(void);
 /* bytes of `workspace` srk_conv_fprop needs for this input and pack kind (0 = may pass NULL): the tcgen05 path
  * carries the fp32 partial sums of a contraction over more than 64 input channels through it. */
 int64_t srk_conv_fprop_workspace_bytes(const srk_tensor* x, int pack_kind);
@@ -95,35 +108,36 @@ int64_t srk_conv_wgrad_workspace_bytes(const srk_tensor* x, const srk_tensor* dy
 /* dgrad of a 3x3 64 -> 64 conv (bf16 ACT, w_packed_dgrad = SRK_PACK_DGRAD_TC weights) with the BatchNorm-backward
  * REDUCTION of the BN layer below it fused into the epilogue (native_batch_norm_backward's sums of
  * ResidualBlock.backward, models.py:56-57): z = that BN's saved input, alpha = the PReLU slope between the BN and
- * this conv (models.py:57) or NULL.  Accumulates sum_g[64], sum_gz[64] (raw sums; srk_bn_bwd_apply_raw turns them into
+ * this conv (models.py:57) or NULL.  Writes sum_g[64], sum_gz[64] (raw sums; srk_bn_bwd_apply_raw turns them into
  * dgamma / the dy constants) and dalpha[1].  Returns 0 ok, 1 error, 2 = shape outside the fused kernel (nothing
  * launched; run srk_conv_fprop + srk_bn_bwd_reduce instead). */
 int srk_conv_dgrad_bnred(const srk_tensor* dz, const srk_tensor* dx, const void* w_packed_dgrad, const srk_tensor* z,
                          const float* mean, const float* invstd, const float* gamma, const float* beta,
-                         const float* alpha, float* sum_g, float* sum_gz, float* dalpha, void* stream);
+                         const float* alpha, float* sum_g, float* sum_gz, float* dalpha, void* reduce_ws,
+                         void* stream);
 
 /* ---- convolutions with an RGB side on tcgen05 (K = 9 or 5; im2col built in shared memory) ---------
  * input_conv / SRCNN conv1 (3 -> 64, models.py:84,107,150) and the backward of output_conv / SRCNN conv3
  * (64 -> 3, models.py:86,125,167).  img3: IMAGE fp32 [N,3,H,W]; y, t64, dx: bf16 ACT [N,64,H,W].
- *   fprop:  y = act(conv(img3, W) + bias), W packed SRK_PACK_RGBIN_TC.
- *   bwd, rgb_out = 0 (3 -> 64 conv): img3 = the conv input, t64 = dZ; dw [64][3][K][K], db [64] accumulated.
- *   bwd, rgb_out = 1 (64 -> 3 conv): img3 = dY, t64 = the conv input; dw [3][64][K][K], db [3] accumulated;
+ *   fprop:  y = act(conv(img3, W) + bias), W packed SRK_PACK_RGBIN_TC; prelu_z as in srk_conv_fprop.
+ *   bwd, rgb_out = 0 (3 -> 64 conv): img3 = the conv input, t64 = dZ; dw [64][3][K][K], db [64] WRITTEN.
+ *   bwd, rgb_out = 1 (64 -> 3 conv): img3 = dY, t64 = the conv input; dw [3][64][K][K], db [3] WRITTEN;
  *        when dx != NULL also dx = dgrad(dY) with w_packed = SRK_PACK_RGBOUT_DGRAD_TC weights.
- * workspace: srk_conv_rgb_workspace_bytes(k) bytes. */
+ * workspace: srk_conv_rgb_workspace_bytes(k) bytes (one partial gradient per CTA, summed in CTA order). */
 int64_t srk_conv_rgb_workspace_bytes(int k);
 int srk_conv_rgb_fprop(const srk_tensor* img3, const srk_tensor* y, const void* w_packed, int k,
-                       const float* bias, int act, const float* alpha, void* stream);
+                       const float* bias, int act, const float* alpha, const srk_tensor* prelu_z, void* stream);
 int srk_conv_rgb_bwd(const srk_tensor* img3, const srk_tensor* t64, const void* w_packed,
                      const srk_tensor* dx, float* dw, float* db, int k, int rgb_out, void* workspace,
                      void* stream);
 /* srk_conv_rgb_bwd (rgb_out = 1) fused with the PReLU + PixelShuffle(2) backward of the upsample stage below the output
- * conv (autograd of models.py:120-125): t64 = that stage's output, alpha / dalpha = its PReLU slope and slope gradient
- * (accumulated).  Instead of dx it writes dz_ps = the gradient of the 64 -> 256 conv output, bf16 ACT [N,256,H/2,W/2],
+ * conv (autograd of models.py:120-125): t64 = that stage's output, t64_z = its saved pre-activation (prelu_z of the
+ * forward call, or NULL), alpha / dalpha = its PReLU slope and slope gradient (written).  Instead of dx it writes dz_ps = the gradient of the 64 -> 256 conv output, bf16 ACT [N,256,H/2,W/2],
  * channels SUB-PIXEL-MAJOR (sub * 64 + c).  Consumers: srk_conv_fprop with SRK_PACK_DGRAD_TC weights packed with
  * pixel_shuffle = 2, and srk_conv_wgrad with perm_shuffle = 1. */
-int srk_conv_rgbout_bwd_unshuffle(const srk_tensor* dy_img, const srk_tensor* t64, const void* w_packed,
-                                  const srk_tensor* dz_ps, float* dw, float* db, const float* alpha, float* dalpha, int k,
-                                  void* workspace, void* stream);
+int srk_conv_rgbout_bwd_unshuffle(const srk_tensor* dy_img, const srk_tensor* t64, const srk_tensor* t64_z,
+                                  const void* w_packed, const srk_tensor* dz_ps, float* dw, float* db, const float* alpha,
+                                  float* dalpha, int k, void* workspace, void* stream);
 
 /* OIHW fp32 master weights -> kernel operand layouts (see SRK_PACK_*). */
 int srk_weight_pack(const float* w_oihw, void* out, int cout, int cin, int r, int s, int kind,
@@ -138,14 +152,15 @@ int srk_weight_pack_multi(int count, const float* const* w_oihw, void* const* ou
  * out: saved post-activation tensor; dout: its gradient; dz: gradient of the pre-activation in
  * conv-output geometry ([N][4C][H/2][W/2] when pixel_unshuffle=2; channel order matches `perm_tc`:
  * 0 = reference order co=4c+2i+j, 1 = sub-pixel-major co'=(2i+j)*C+c used by the TC conv path).
- * dalpha (fp32[1], accumulated) only for PReLU.  PReLU backward reconstructs the pre-activation
- * from `out`, exact for alpha > 0 (reference init 0.25, models.py:48). */
-int srk_act_bwd(const srk_tensor* dout, const srk_tensor* out, const srk_tensor* dz, int act,
-                const float* alpha, float* dalpha, int pixel_unshuffle, int perm_tc, void* stream);
+ * dalpha (fp32[1], written; needs reduce_ws) only for PReLU.  For a slope > 0 the pre-activation follows from `out`
+ * (sign(out) = sign(z), z = out / alpha on the negative side); for a slope <= 0 the kernel reads `zsave`, the
+ * prelu_z copy the forward epilogue wrote (NULL: the slope must be > 0). */
+int srk_act_bwd(const srk_tensor* dout, const srk_tensor* out, const srk_tensor* zsave, const srk_tensor* dz, int act,
+                const float* alpha, float* dalpha, int pixel_unshuffle, int perm_tc, void* reduce_ws, void* stream);
 
 /* ---- BatchNorm2d (models.py:47,50,56-57,114,140): native_batch_norm / _backward ----------------*/
-/* per-channel sum and sum of squares over interior pixels (fp32[C] each, accumulated) */
-int srk_bn_stats(const srk_tensor* y, float* sum, float* sumsq, void* stream);
+/* per-channel sum and sum of squares over interior pixels: sums = fp32 [2][C], written */
+int srk_bn_stats(const srk_tensor* y, float* sums, void* reduce_ws, void* stream);
 /* training: batch mean / invstd from (sum,sumsq); updates running stats (momentum, unbiased var)
  * and num_batches_tracked (int64) when those pointers are non-NULL. */
 int srk_bn_finalize(const float* sum, const float* sumsq, int c, int64_t count, float eps,
@@ -166,12 +181,13 @@ int srk_bn_apply_train(const srk_tensor* y, const float* sum, const float* sumsq
                        float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
                        float* mean, float* invstd, const float* gamma, const float* beta, const float* alpha,
                        const srk_tensor* residual, const srk_tensor* out, void* stream);
-/* backward pass 1: dgamma[C], dbeta[C], dalpha[1] (all fp32, accumulated) */
+/* backward pass 1: dgamma[C], dbeta[C], dalpha[1] (all fp32, written) */
 int srk_bn_bwd_reduce(const srk_tensor* dout, const srk_tensor* y, const float* mean,
                       const float* invstd, const float* gamma, const float* beta,
-                      const float* alpha, float* dgamma, float* dbeta, float* dalpha, void* stream);
-/* backward pass 2: dy.  dgamma_b/dbeta_b are THIS batch's reductions (pass-1 outputs into zeroed
- * buffers); batch_stats=0 gives the eval-mode backward (dy = gamma*invstd*g). */
+                      const float* alpha, float* dgamma, float* dbeta, float* dalpha, void* reduce_ws,
+                      void* stream);
+/* backward pass 2: dy.  dgamma_b/dbeta_b are THIS batch's reductions (pass-1 outputs);
+ * batch_stats=0 gives the eval-mode backward (dy = gamma*invstd*g). */
 int srk_bn_bwd_apply(const srk_tensor* dout, const srk_tensor* y, const float* mean,
                      const float* invstd, const float* gamma, const float* beta, const float* alpha,
                      const float* dgamma_b, const float* dbeta_b, int batch_stats,
@@ -184,16 +200,16 @@ int srk_bn_bwd_apply_raw(const srk_tensor* dout, const srk_tensor* y, const floa
 
 /* ---- squeeze-excite gate (models.py:26-41,76-78): mean / mm / sigmoid / mul / add ------------- */
 /* pool[N][C] = mean over H,W of r */
-int srk_se_pool(const srk_tensor* r, float* pool, void* stream);
+int srk_se_pool(const srk_tensor* r, float* pool, void* reduce_ws, void* stream);
 /* hidden[N][Cr] = relu(pool @ w1^T), gate[N][C] = sigmoid(hidden @ w2^T); w1 [Cr][C], w2 [C][Cr] */
 int srk_se_fc(const float* pool, const float* w1, const float* w2, int n, int c, int cr,
               float* hidden, float* gate, void* stream);
 /* out = (x ? x : 0) + scale * r * gate[n][c] */
 int srk_se_apply(const srk_tensor* x, const srk_tensor* r, const float* gate, float scale,
                  const srk_tensor* out, void* stream);
-/* dgate_raw[N][C] = sum_hw dout * r   (accumulated) */
-int srk_se_bwd_reduce(const srk_tensor* dout, const srk_tensor* r, float* dgate_raw, void* stream);
-/* tiny FC backward: dw1 [Cr][C], dw2 [C][Cr] (accumulated), dpool [N][C] (overwritten) */
+/* dgate_raw[N][C] = sum_hw dout * r   (written) */
+int srk_se_bwd_reduce(const srk_tensor* dout, const srk_tensor* r, float* dgate_raw, void* reduce_ws, void* stream);
+/* tiny FC backward: dw1 [Cr][C], dw2 [C][Cr], dpool [N][C] (all written) */
 int srk_se_fc_bwd(const float* dgate_raw, const float* gate, const float* hidden, const float* pool,
                   const float* w1, const float* w2, int n, int c, int cr, float scale, float* dw1,
                   float* dw2, float* dpool, void* stream);
@@ -216,7 +232,9 @@ int srk_maxpool2_bwd(const srk_tensor* x, const srk_tensor* dout, const srk_tens
 int srk_bicubic_upsample(const srk_tensor* in, const srk_tensor* out, void* stream);
 
 /* ---- losses (loss.py:81-86 nn.L1Loss / nn.MSELoss; loss.py:31-79 NLPDLoss) --------------------- */
-/* mode 0 = L1, 1 = MSE.  loss[1] fp32 overwritten. */
+/* mode 0 = L1, 1 = MSE.  loss[1] fp32 overwritten.  scratch: srk_pixel_loss_scratch_bytes() bytes (per-block fp64
+ * partial sums, added in block order). */
+int64_t srk_pixel_loss_scratch_bytes(void);
 int srk_pixel_loss_fwd(const float* sr, const float* hr, int64_t numel, int mode, float* loss,
                        double* scratch, void* stream);
 /* grad_sr = gout[0] * dLoss/dsr */
@@ -247,10 +265,14 @@ int srk_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   float lr, float beta1, float beta2, float eps, const int64_t* step_count,
                   float grad_scale, void* stream);
 
-/* the same update for `count` tensors in ceil(count / 48) launches (host arrays of device pointers) */
+/* the same update for `count` tensors in ceil(count / 48) launches (host arrays of device pointers).
+ * lr_dev (device float[1] or NULL): when set it REPLACES lr - a captured CUDA graph then follows a scheduler
+ * (train.py:56,164 ReduceLROnPlateau) without being re-captured.  grad_scale_dev (device float[1] or NULL): extra
+ * factor on the gradients, e.g. the clip coefficient of clip_grad_norm_ (train.py:113) computed on the device. */
 int srk_adam_multi(int count, float* const* params, const float* const* grads, float* const* exp_avg,
                    float* const* exp_avg_sq, const int64_t* numel, float lr, float beta1, float beta2,
-                   float eps, const int64_t* step_count, float grad_scale, void* stream);
+                   float eps, const int64_t* step_count, float grad_scale, const float* lr_dev,
+                   const float* grad_scale_dev, void* stream);
 
 /* ---- bring-up / self-test hooks (tests only) --------------------------------------------------- */
 /* Runs the tcgen05 descriptor probe (see csrc/srk_probe.cu); results into out[] (host memory). */

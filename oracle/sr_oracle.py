@@ -12,10 +12,14 @@ Pinning
   * models + mae/mse/nlpd: PINNED.  tests/golden/*.npz hold inputs, state_dicts, outputs, losses and
     gradients produced by the reference modules themselves (oracle/make_golden.py, run where
     /root/reference exists); tests/test_oracle_golden.py checks this file against them.
-  * PSNR / SSIM: PARITY UNPINNED.  The reference calls torchmetrics==1.8.2 (requirements.txt:4,
-    metrics.py:2,9-10,19-20), which is neither vendored in the reference nor installable here, and the
-    reference has no test or golden value for it.  psnr()/ssim() restate torchmetrics' published
-    algorithm (functional/image/psnr.py, ssim.py) and are checked against analytic known answers only.
+  * PSNR / SSIM: PARITY UNPINNED against torchmetrics.  The reference calls torchmetrics==1.8.2
+    (requirements.txt:4, metrics.py:2,9-10,19-20), which is neither vendored in the reference nor installable
+    here, and the reference has no test or golden value for it.  psnr()/ssim() restate torchmetrics' published
+    algorithm (functional/image/psnr.py, ssim.py); they are checked against analytic known answers and against
+    oracle/metrics_fp64.py, an independent numpy/scipy fp64 implementation written from the SSIM paper's
+    formulas (tests/test_oracle_golden.py) - a second opinion, not a torchmetrics fixture.
+  * the unmodified reference modules themselves are available as oracle/_ref (oracle/build_ref.py,
+    oracle/ref_modules.py) wherever __graft_entry__.build() ran with /root/reference present.
 """
 import math
 
@@ -152,7 +156,7 @@ def laplacian_pyramid(img, kernel, n_levels=4):
 
 def nlpd_loss(sr, hr, n_levels=4, alpha=0.7):
     """NLPDLoss.forward (loss.py:69-79)."""
-    k = gaussian_kernel_5x5(sr.shape[1], sr.dtype)
+    k = gaussian_kernel_5x5(sr.shape[1], sr.dtype).to(sr.device)
     l_mae = (sr - hr).abs().mean()
     l_pyr = 0
     for a, b in zip(laplacian_pyramid(sr, k, n_levels), laplacian_pyramid(hr, k, n_levels)):

@@ -102,8 +102,9 @@ def test_product_code_does_not_import_the_oracle():
 def test_nlpd_workspace_plan_is_host_only_and_aligned():
     """srk_nlpd_workspace_bytes is pure host arithmetic (no GPU needed): it rejects level counts outside [1, 6], grows
     with every dimension, and holds at least the pyramid of the difference image (sum of the level sizes, fp32), the
-    int8 sign maps and the two gradient ping-pong buffers; every region is padded to 16 bytes (the exact-2x kernels use
-    float2 / char2 accesses), so odd sizes cost at most a few bytes per region."""
+    int8 sign maps, the two gradient ping-pong buffers and the per-block fp64 partial sums of the loss terms
+    (8 terms x 148 * 8 blocks: the loss value is a fixed-order sum, not an atomic accumulation); every region is padded to
+    16 bytes (the exact-2x kernels use float2 / char2 accesses), so odd sizes cost at most a few bytes per region."""
     from srk import _lib
     f = _lib.cdll.srk_nlpd_workspace_bytes
     assert f(1, 3, 16, 16, 0) == -1 and f(1, 3, 16, 16, 7) == -1
@@ -115,7 +116,36 @@ def test_nlpd_workspace_plan_is_host_only_and_aligned():
         nc = n * c
         floats = sum(nc * a * b for a, b in zip(hs, ws)) + nc * hs[0] * ws[0] + nc * hs[1] * ws[1]
         signs = sum(nc * hs[l] * ws[l] for l in range(L))
-        need = 4 * floats + signs + 8 * 8
+        need = 4 * floats + signs + 8 * 8 * (148 * 8)
         got = f(n, c, h, w, L)
         assert got % 16 == 0 and need <= got <= need + 16 * (2 * L + 6), (n, c, h, w, L, got, need)
         assert f(n + 1, c, h, w, L) > got and f(n, c, h + 2, w, L) > got
+
+
+SWEEP_SHA256 = {   # sha256 of /root/reference/configs/* (taken where the reference exists)
+    "sweep_attentionSR.yaml": "a3b23415136e75d8d328fb9e32eb546c00d889a5838872486aab8d81e2883de2",
+    "sweep_resnet.yaml": "52dfb82a12c41095c46110a2f856ce353e82d42c48cc3b347a9a3a6da3040eb7",
+    "sweep_srcnn.yaml": "b35af37966fe55b398b4a9e13bb91ffa55887acd22bc808ad7612a0b20d4d046",
+    "sweep_tuning.yaml": "b9e4dfcd451cc3c135a4bc84f68820447b1e470d28e1a0584d79344f7637d5e1",
+    "sweep_winners.txt": "c8a059ae4d9437976f23d65db5502305799d2d5d833ce66507d41e2e42258b5f",
+}
+
+
+def test_sweep_configs_are_the_reference_files():
+    """The sweep entry points (reference configs/sweep_*.yaml, sweep_winners.txt) ship next to train.py, byte for byte
+    (wandb sweeps name `program: train.py` and the flags train.py parses)."""
+    import hashlib
+    want = SWEEP_SHA256
+    cfg_dir = os.path.join(ROOT, "food101-super-resolution_b200", "configs")
+    for name in want:
+        path = os.path.join(cfg_dir, name)
+        assert os.path.exists(path), name
+        digest = hashlib.sha256(open(path, "rb").read()).hexdigest()
+        assert digest == SWEEP_SHA256[name], (name, digest)
+    import yaml
+    for name in want:
+        if name.endswith(".yaml"):
+            doc = yaml.safe_load(open(os.path.join(cfg_dir, name)))
+            assert doc["program"] == "train.py" and doc["metric"]["name"] == "val_psnr"
+            assert set(doc["parameters"]) <= {"architecture", "loss_function", "lr", "batch_size", "subset", "epochs",
+                                              "patience", "pretrained_weights", "save_name"}

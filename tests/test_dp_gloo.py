@@ -85,3 +85,76 @@ def test_sharded_evaluation_reproduces_batch_mean_semantics():
         assert len(out) == world
         for nb, err, lp_nan in out.values():
             assert nb == 7 and err < 1e-12 and lp_nan
+
+
+def _fit_worker(rank, world, port, out):
+    """train.fit (the epoch loop of train.py) on two ranks whose LOCAL validation numbers differ: the loop must run
+    the same number of epochs on both, stop early on the same epoch, and never leave a rank waiting in a collective."""
+    sys.path.insert(0, os.path.join(ROOT, "food101-super-resolution_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world, timeout=__import__("datetime").timedelta(seconds=60))
+    import argparse
+    import train as T
+    from srk import dp
+    from srk import evaluate as ev
+    cfg = argparse.Namespace(epochs=12, patience=2)
+    net = torch.nn.Linear(4, 4)
+    dp.broadcast_parameters(net)
+    averager = dp.GradAverager(net.parameters())
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    sched = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, mode="max", factor=0.5, patience=2)
+    # identical batches on every rank (seeded loader), last batch smaller than the world size -> skipped everywhere
+    g = torch.Generator().manual_seed(5)
+    data = [(torch.randn(n, 4, generator=g), torch.randn(n, 4, generator=g)) for n in (6, 5, 3, 1)]
+    steps, weights = [0], []
+
+    def step_fn(x, y, weight):
+        opt.zero_grad()
+        loss = ((net(x) - y) ** 2).mean() * weight
+        loss.backward()
+        averager.average()          # the collective every rank must reach the same number of times
+        opt.step()
+        steps[0] += 1
+        weights.append(weight)
+        return loss.detach()
+
+    epoch = [0]
+    # per-rank "validation PSNR" that would make the ranks disagree if it steered control flow directly: rank 0 keeps
+    # improving, rank 1 gets worse; the all-reduced mean peaks at epoch 2, so both ranks stop after epoch 4
+    local_psnr = {0: [10, 12, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23], 1: [10, 12, 14, 9, 6, 3, 1, 0, 0, 0, 0, 0]}
+    val_batches = [(torch.full((2, 1), float(i)), torch.zeros(2, 1)) for i in range(4)]
+
+    def eval_fn():
+        e = epoch[0]
+        epoch[0] += 1
+        fake = lambda sr, hr: {"psnr": float(local_psnr[rank][e]), "ssim": 0.0, "nlpd": 0.0, "lpips": 0.0}
+        return ev.evaluate(lambda x: x, val_batches, "cpu", rank, world, metrics_fn=fake,
+                           criterion=lambda sr, hr: (sr - hr).abs().mean())
+
+    saved = []
+    best, epochs_run = T.fit(cfg, train_loader=data, step_fn=step_fn, eval_fn=eval_fn, scheduler=sched,
+                             get_lr=lambda: opt.param_groups[0]["lr"], save_best=lambda ep: saved.append(ep), rank=rank,
+                             world=world, log=lambda d: None, shard=lambda t: t)
+    dist.barrier()
+    w = torch.cat([p.detach().flatten() for p in net.parameters()])
+    ws = [torch.zeros_like(w) for _ in range(world)]
+    dist.all_gather(ws, w)
+    out[rank] = (epochs_run, steps[0], best, saved, opt.param_groups[0]["lr"], float((ws[0] - ws[1]).abs().max()),
+                 sorted(set(round(x, 6) for x in weights)))
+    dist.destroy_process_group()
+
+
+def test_training_loop_early_stops_in_lockstep_on_two_ranks():
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_fit_worker, args=(world, 29547, out), nprocs=world, join=True)
+        assert len(out) == world
+        a, b = out[0], out[1]
+        assert a[:5] == b[:5], (a, b)                      # epochs, steps, best PSNR, saved epochs, learning rate
+        assert a[0] == 5 and a[1] == 5 * 3 and a[3] == [0, 1, 2]   # stopped after 2 epochs without improvement; 1-sample batch skipped
+        assert abs(a[2] - 14.0) < 1e-12
+        assert a[5] == 0.0 and b[5] == 0.0                 # weights stayed identical on both ranks
+        # uneven shards (5 -> 3 + 2, 3 -> 2 + 1) carry weights n_local * world / n_global
+        assert a[6] == [1.0, 1.2, round(4 / 3, 6)] and b[6] == [round(2 / 3, 6), 0.8, 1.0]

@@ -173,7 +173,7 @@ def _oracle_conv(x, w, b, alpha, act, shuffle):
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 @pytest.mark.parametrize("cin,cout,k,h,w,n,act,shuffle", CONV_CASES)
-def test_conv_forward_backward_vs_oracle(cin, cout, k, h, w, n, act, shuffle, dtype):
+def test_conv_forward_backward_vs_oracle(cin, cout, k, h, w, n, act, shuffle, dtype, slope=0.25):
     import srk
     from srk import _lib as L
     from srk import fn
@@ -183,7 +183,7 @@ def test_conv_forward_backward_vs_oracle(cin, cout, k, h, w, n, act, shuffle, dt
     x = torch.randn(n, cin, h, w, generator=g)
     wt = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
     b = torch.randn(cout, generator=g) * 0.1
-    alpha = torch.tensor([0.25])
+    alpha = torch.tensor([slope])
     if dtype == "bf16":  # compare like with like: the oracle sees the bf16-rounded operands
         x = x.bfloat16().float()
         wt = wt.bfloat16().float()
@@ -220,6 +220,17 @@ def test_conv_forward_backward_vs_oracle(cin, cout, k, h, w, n, act, shuffle, dt
     assert float(ya[:, :, 0].abs().max()) == 0 and float(ya[:, :, -1].abs().max()) == 0
 
 
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("slope", [-0.1, 0.0])
+@pytest.mark.parametrize("cin,cout,k,h,w,n,act,shuffle", [c for c in CONV_CASES if c[6] == "prelu"])
+def test_prelu_epilogues_with_nonpositive_slope(cin, cout, k, h, w, n, act, shuffle, slope, dtype):
+    """nn.PReLU puts no constraint on its slope (reference models.py:48,66,108,119,122).  For a slope <= 0 the sign of
+    the pre-activation is not the sign of the output (and for 0 its value is gone), so every PReLU conv epilogue -
+    RGB-input kernel, 16-warp and 8-warp tcgen05 kernels incl. the chunked 96-channel and PixelShuffle passes, the
+    CUDA-core kernel - then also stores the pre-activation and srk_act_bwd reads that copy (include/srk.h, prelu_z)."""
+    test_conv_forward_backward_vs_oracle(cin, cout, k, h, w, n, act, shuffle, dtype, slope=slope)
+
+
 @pytest.mark.parametrize("cin,cout,k,h,w,n,act,shuffle", [c for c in CONV_CASES if c[2] == 3 and c[0] >= 64])
 @pytest.mark.parametrize("fold", [0, 1, 2, 3])
 def test_conv3x3_both_tc_kernels_vs_oracle(cin, cout, k, h, w, n, act, shuffle, fold):
@@ -235,6 +246,8 @@ def test_conv3x3_both_tc_kernels_vs_oracle(cin, cout, k, h, w, n, act, shuffle, 
     L.call("srk_tc_probe", 10 + fold, out, 2)
     try:
         test_conv_forward_backward_vs_oracle(cin, cout, k, h, w, n, act, shuffle, "bf16")
+        if act == "prelu":
+            test_conv_forward_backward_vs_oracle(cin, cout, k, h, w, n, act, shuffle, "bf16", slope=-0.1)
     finally:
         L.call("srk_tc_probe", 10 + default, out, 2)
         assert out[0] == 0, "tcgen05 protocol error flag %r" % out[0]

@@ -88,6 +88,24 @@ def test_ssim_equals_valid_window_mean():
     assert abs(m.mean().item() - O.ssim(p, t)) < 1e-12
 
 
+@pytest.mark.parametrize("shape", [(2, 3, 24, 20), (3, 1, 37, 53), (1, 3, 64, 64), (2, 3, 11 + 1, 11 + 6)])
+def test_psnr_ssim_agree_with_independent_fp64_implementation(shape):
+    """oracle/metrics_fp64.py shares no code with sr_oracle.py (numpy + scipy.ndimage.correlate1d, written from the
+    SSIM paper's formulas): both must give the same PSNR and per-image SSIM, on smooth and on noisy image pairs."""
+    from oracle import metrics_fp64 as M64
+    g = torch.Generator().manual_seed(shape[2] * 7 + shape[3])
+    hr = torch.rand(shape, generator=g)
+    for noise in (0.02, 0.3):
+        sr = (hr + noise * torch.randn(shape, generator=g)).clamp(0, 1)
+        assert abs(O.psnr(sr, hr) - M64.psnr(sr.numpy(), hr.numpy())) <= 1e-9
+        a, b = O.ssim_per_image(sr, hr).numpy(), M64.ssim_per_image(sr.numpy(), hr.numpy())
+        assert abs(a - b).max() <= 1e-12, (a, b)
+    # smooth content (what SR images look like): low-passed noise
+    lp = torch.nn.functional.avg_pool2d(hr, 3, 1, 1)
+    assert abs(O.ssim(lp, hr) - M64.ssim(lp.numpy(), hr.numpy())) <= 1e-12
+    assert M64.psnr(hr.numpy(), hr.numpy()) == float("inf") and abs(M64.ssim(hr.numpy(), hr.numpy()) - 1.0) <= 1e-12
+
+
 def test_metrics_compute_clamps_first():
     x = torch.full((1, 3, 16, 16), 1.5)
     y = torch.full((1, 3, 16, 16), 1.0)
