@@ -135,15 +135,28 @@ constexpr size_t kRedPartialFloats = (kRedWsBytes - kRedTickets * sizeof(unsigne
 inline unsigned* red_tickets(void* ws) { return reinterpret_cast<unsigned*>(ws); }
 inline float* red_partials(void* ws) { return reinterpret_cast<float*>(reinterpret_cast<unsigned*>(ws) + kRedTickets); }
 
+// Two levels keep the serial tail short: blocks are grouped by kRedGroup consecutive indices; the last block of a
+// group to arrive folds the group's rows (a few KB) into one group row, and the last GROUP to finish folds the group
+// rows.  One SM pulling all rows of a 296-block reduction (150 KB) at the end of the kernel measured +14 us; the two
+// small folds cost about two L2 round trips.  Tickets of a reduction: [0] level 2, [1 + g] group g.
+constexpr int kRedGroup = 8;
+__host__ __device__ inline int red_groups(int nblk) { return (nblk + kRedGroup - 1) / kRedGroup; }
+__host__ __device__ inline int red_tickets_needed(int nblk) { return 1 + red_groups(nblk); }
+// partial floats of one reduction: block rows followed by group rows
+__host__ __device__ inline long long red_partial_floats(int nblk, int nv) {
+  return (long long)(nblk + red_groups(nblk)) * ((nv + 3) & ~3);
+}
+
 // Called by the T threads `tid` = 0..T-1 of a block (a whole block with sync = __syncthreads, or a warp-aligned
 // subset with a named barrier).  vals[NV]: this block's partial sums in shared memory, complete and visible to the
-// T threads.  part: rows of this reduction [nblk][4 * ceil(NV / 4)] floats; bidx in [0, nblk): this block's row.
-// scratch: T float4 of shared memory.  finish(i, sum) is called once per value by the last-arriving block.
+// T threads.  part: red_partial_floats(nblk, NV) floats of this reduction; bidx in [0, nblk): this block's row.
+// scratch: T float4 of shared memory (may alias vals).  finish(i, sum) is called once per value, by one block.
 template <typename Sync, typename Finish>
 __device__ __forceinline__ void ordered_fold(const float* vals, int NV, unsigned* ticket, int nblk, int bidx,
                                              float* part, float4* scratch, int tid, int T, Sync sync, Finish finish) {
   const int NV4 = (NV + 3) >> 2;
-  float4* prow = reinterpret_cast<float4*>(part) + (size_t)bidx * NV4;
+  float4* rows = reinterpret_cast<float4*>(part);
+  float4* prow = rows + (size_t)bidx * NV4;
   for (int i = tid; i < NV4; i += T) {
     float4 v;
     v.x = vals[4 * i];
@@ -155,33 +168,63 @@ __device__ __forceinline__ void ordered_fold(const float* vals, int NV, unsigned
   __threadfence();
   sync();
   int* flag = reinterpret_cast<int*>(scratch);
+  const int grp = bidx / kRedGroup, ngrp = red_groups(nblk);
+  const int g0 = grp * kRedGroup, gsize = nblk - g0 < kRedGroup ? nblk - g0 : kRedGroup;
   if (tid == 0) {
-    const unsigned k = atomicAdd(ticket, 1u);
-    const int last = (k == (unsigned)nblk - 1u);
-    if (last) *ticket = 0u;     // everybody has arrived: ready for the next launch that uses this ticket
+    const unsigned k = atomicAdd(ticket + 1 + grp, 1u);
+    const int last = (k == (unsigned)gsize - 1u);
+    if (last) ticket[1 + grp] = 0u;     // the whole group has arrived: ready for the next launch
     flag[0] = last;
   }
   sync();
-  const bool last = flag[0] != 0;
-  sync();                       // flag[0] is about to be overwritten as scratch
+  bool last = flag[0] != 0;
+  sync();                       // flag[0] is about to be overwritten
   if (!last) return;
   __threadfence();
+  // level 1: this group's rows, in block order, into the group row
+  float4* grow = rows + (size_t)(nblk + grp) * NV4;
+  for (int i = tid; i < NV4; i += T) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int b = 0; b < kRedGroup; ++b) {
+      if (b < gsize) {
+        const float4 v = __ldcg(rows + (size_t)(g0 + b) * NV4 + i);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    __stcg(grow + i, acc);
+  }
+  __threadfence();
+  sync();
+  if (tid == 0) {
+    const unsigned k = atomicAdd(ticket, 1u);
+    const int l2 = (k == (unsigned)ngrp - 1u);
+    if (l2) ticket[0] = 0u;
+    flag[0] = l2;
+  }
+  sync();
+  last = flag[0] != 0;
+  sync();
+  if (!last) return;
+  __threadfence();
+  // level 2: the group rows, in group order
+  const float4* gro = rows + (size_t)nblk * NV4;
   for (int c0 = 0; c0 < NV4; c0 += T) {
     const int ncol = NV4 - c0 < T ? NV4 - c0 : T;
-    const int G = T / ncol;     // row groups: thread (g, col) sums rows g, g + G, ... in that order
+    const int G = T / ncol;     // row sets: thread (g, col) sums rows g, g + G, ... in that order
     const int col = tid % ncol, g = tid / ncol;
     if (g < G) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4* p = reinterpret_cast<const float4*>(part) + c0 + col;
-#pragma unroll 8
-      for (int b = g; b < nblk; b += G) {
+      const float4* p = gro + c0 + col;
+#pragma unroll 4
+      for (int b = g; b < ngrp; b += G) {
         const float4 v = __ldcg(p + (size_t)b * NV4);
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
       }
       scratch[g * ncol + col] = acc;
     }
     sync();
-    // fixed binary tree over the row groups
+    // fixed binary tree over the row sets
     int top = 1;
     while (top < G) top <<= 1;
     for (int h = top >> 1; h >= 1; h >>= 1) {

@@ -383,44 +383,52 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         const int y0 = (t2 / p.tiles_x) * TY, x0 = (t2 % p.tiles_x) * TX;
         if (p.unshuffle && !mbar_wait(smem_u32(&bars->tfull[buf]), (i >> 1) & 1, p.err, 39)) break;
         const uint8_t* trow = smem_al + 2 * G::A_BYTES + G::W_BYTES + buf * G::T_BYTES + ei * 128;
+        if (save_z && y0 + ty < p.H && x0 + tx < p.W) {   // rare: PReLU slope <= 0 (see act_bwd_kernel)
+          __nv_bfloat16* zrow = p.zsave + (((size_t)n * (p.H + 2) + y0 + ty + 1) * (p.W + 2) + x0 + tx + 1) * p.y_stride +
+                                p.y_col0 + c0;
+          for (int j = 0; j < 4; ++j) {
+            if (c0 + j * 8 >= p.n_valid) break;
+            uint32_t w4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat162 z = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 2 * e]) + bias[j * 8 + 2 * e],
+                                                       __uint_as_float(v[j * 8 + 2 * e + 1]) + bias[j * 8 + 2 * e + 1]);
+              w4[e] = *reinterpret_cast<uint32_t*>(&z);
+            }
+            *reinterpret_cast<uint4*>(zrow + j * 8) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+          }
+        }
         uint4 o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float f[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]) + bias[j * 8 + e];
-          if (save_z && y0 + ty < p.H && x0 + tx < p.W && c0 + j * 8 < p.n_valid) {
-            __nv_bfloat162 z0 = __floats2bfloat162_rn(f[0], f[1]), z1 = __floats2bfloat162_rn(f[2], f[3]);
-            __nv_bfloat162 z2 = __floats2bfloat162_rn(f[4], f[5]), z3 = __floats2bfloat162_rn(f[6], f[7]);
-            *reinterpret_cast<uint4*>(p.zsave + (((size_t)n * (p.H + 2) + y0 + ty + 1) * (p.W + 2) + x0 + tx + 1) * p.y_stride +
-                                      p.y_col0 + c0 + j * 8) =
-                make_uint4(*reinterpret_cast<uint32_t*>(&z0), *reinterpret_cast<uint32_t*>(&z1),
-                           *reinterpret_cast<uint32_t*>(&z2), *reinterpret_cast<uint32_t*>(&z3));
-          }
-#pragma unroll
           for (int e = 0; e < 8; ++e) {
-            float a = f[e];
+            float a = __uint_as_float(v[j * 8 + e]) + bias[j * 8 + e];
             if (p.act == SRK_ACT_RELU) a = fmaxf(a, 0.f);
             else if (p.act == SRK_ACT_PRELU) a = a > 0.f ? a : alpha * a;
             f[e] = a;
           }
-          if (p.unshuffle) {   // PReLU backward of the layer below: mask by the sign of its OUTPUT (the T64 tile)
-            uint4 tq = *reinterpret_cast<const uint4*>(trow + (((ch * 4 + j) ^ (ei & 7)) << 4));
-            float zsc = ps_inv_alpha;
-            if (ps_use_z) {      // ... or of its saved pre-activation
-              zsc = 1.f;
-              tq = make_uint4(0, 0, 0, 0);
-              if (y0 + ty < p.H && x0 + tx < p.W)
-                tq = *reinterpret_cast<const uint4*>(p.ps_zsave + (((size_t)n * (p.H + 2) + y0 + ty + 1) * (p.W + 2) + x0 + tx + 1) * 64 +
-                                                     c0 + j * 8);
-            }
+          if (p.unshuffle && !ps_use_z) {   // PReLU backward of the layer below: mask by the sign of its OUTPUT (the T64 tile)
+            const uint4 tq = *reinterpret_cast<const uint4*>(trow + (((ch * 4 + j) ^ (ei & 7)) << 4));
             const __nv_bfloat162* th = reinterpret_cast<const __nv_bfloat162*>(&tq);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float2 tv = __bfloat1622float2(th[e]);
-              const bool nx = ps_use_z ? (tv.x < 0.f) : !(tv.x > 0.f), ny = ps_use_z ? (tv.y < 0.f) : !(tv.y > 0.f);
-              if (nx) { ps_da = fmaf(f[2 * e], tv.x * zsc, ps_da); f[2 * e] *= ps_alpha; }
-              if (ny) { ps_da = fmaf(f[2 * e + 1], tv.y * zsc, ps_da); f[2 * e + 1] *= ps_alpha; }
+              if (!(tv.x > 0.f)) { ps_da = fmaf(f[2 * e], tv.x * ps_inv_alpha, ps_da); f[2 * e] *= ps_alpha; }
+              if (!(tv.y > 0.f)) { ps_da = fmaf(f[2 * e + 1], tv.y * ps_inv_alpha, ps_da); f[2 * e + 1] *= ps_alpha; }
+            }
+          } else if (p.unshuffle) {         // slope <= 0: mask by the sign of its saved PRE-activation (global memory)
+            uint4 tq = make_uint4(0, 0, 0, 0);
+            if (y0 + ty < p.H && x0 + tx < p.W)
+              tq = *reinterpret_cast<const uint4*>(p.ps_zsave + (((size_t)n * (p.H + 2) + y0 + ty + 1) * (p.W + 2) + x0 + tx + 1) * 64 +
+                                                   c0 + j * 8);
+            const __nv_bfloat162* th = reinterpret_cast<const __nv_bfloat162*>(&tq);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 tv = __bfloat1622float2(th[e]);
+              if (tv.x < 0.f) { ps_da = fmaf(f[2 * e], tv.x, ps_da); f[2 * e] *= ps_alpha; }
+              if (tv.y < 0.f) { ps_da = fmaf(f[2 * e + 1], tv.y, ps_da); f[2 * e + 1] *= ps_alpha; }
             }
           }
           __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
@@ -490,33 +498,46 @@ conv_rgb_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 //   rgb_out = 0: dW[n][c][tap] (3 -> 64 conv), db[n] = column sums (the ones row of G)
 //   rgb_out = 1: dW[c][n][taps-1-tap] (64 -> 3 conv; im2col over dY); db3 / dalpha from the per-CTA small partials
 // Every output element is WRITTEN exactly once over the 64-channel passes of a call.
-__global__ void fold_kernel(const float* __restrict__ ws, const float* __restrict__ ws_small, int nblk, int kp,
-                            float* __restrict__ dw, float* __restrict__ db, float* __restrict__ db3,
-                            float* __restrict__ dalpha, int K, int rgb_out, int n0, int n_total) {
+// Block = 32 consecutive outputs x 8 row sets: row set g adds partials g, g + 8, ... (148 dependent-free loads per
+// output were latency-bound on 64 blocks: 30 us), then the 8 sets are added in set order.
+__global__ void __launch_bounds__(256) fold_kernel(const float* __restrict__ ws, const float* __restrict__ ws_small,
+                                                   int nblk, int kp, float* __restrict__ dw, float* __restrict__ db,
+                                                   float* __restrict__ db3, float* __restrict__ dalpha, int K, int rgb_out,
+                                                   int n0, int n_total) {
+  __shared__ float part[8][33];
   const int taps = K * K, segw = (K * 3 + 1) / 2 * 2, kone = K * segw;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int il = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + il;
   const size_t stride = (size_t)kp * NT;
-  if (i < (kone + 1) * NT) {
-    const int n = i % NT, k = i / NT;
-    if (n0 + n >= n_total) return;
-    int r = 0, t = 0;
-    if (k < kone) { r = k / segw; t = k - r * segw; if (t >= K * 3) return; }
-    else if (db == nullptr || rgb_out) return;
-    float v = 0.f;
-#pragma unroll 8
-    for (int b = 0; b < nblk; ++b) v += __ldg(ws + b * stride + i);
-    if (k == kone) { db[n0 + n] = v; return; }
-    const int sx = t / 3, c = t - sx * 3, tap = r * K + sx;
-    if (!rgb_out) dw[((size_t)(n0 + n) * 3 + c) * taps + tap] = v;
-    else dw[((size_t)c * n_total + n0 + n) * taps + (taps - 1 - tap)] = v;
-  } else if (i < (kone + 1) * NT + 4) {
-    const int c = i - (kone + 1) * NT;
-    float* dst = c < 3 ? (db3 ? db3 + c : nullptr) : dalpha;
-    if (dst == nullptr) return;
-    float v = 0.f;
-    for (int b = 0; b < nblk; ++b) v += __ldg(ws_small + b * 4 + c);
-    *dst = v;
+  const int total = (kone + 1) * NT;
+  float v = 0.f;
+  if (i < total) {
+#pragma unroll 4
+    for (int b = g; b < nblk; b += 8) v += __ldg(ws + b * stride + i);
+  } else if (i < total + 4) {
+    for (int b = g; b < nblk; b += 8) v += __ldg(ws_small + b * 4 + (i - total));
   }
+  part[g][il] = v;
+  __syncthreads();
+  if (g != 0 || i >= total + 4) return;
+  v = ((part[0][il] + part[1][il]) + (part[2][il] + part[3][il])) + ((part[4][il] + part[5][il]) + (part[6][il] + part[7][il]));
+  if (i >= total) {
+    const int c = i - total;
+    float* dst = c < 3 ? (db3 ? db3 + c : nullptr) : dalpha;
+    if (dst != nullptr) *dst = v;
+    return;
+  }
+  const int n = i % NT, k = i / NT;
+  if (n0 + n >= n_total) return;
+  if (k == kone) {
+    if (db != nullptr && !rgb_out) db[n0 + n] = v;
+    return;
+  }
+  const int r = k / segw, t = k - r * segw;
+  if (t >= K * 3) return;
+  const int sx = t / 3, c = t - sx * 3, tap = r * K + sx;
+  if (!rgb_out) dw[((size_t)(n0 + n) * 3 + c) * taps + tap] = v;
+  else dw[((size_t)c * n_total + n0 + n) * taps + (taps - 1 - tap)] = v;
 }
 
 static int make_tmap_act_4d_tile(CUtensorMap* out, const srk_tensor* x) {
@@ -646,7 +667,7 @@ int conv_rgb_tc_run(const srk_tensor* t3, const srk_tensor* y, const void* w_pac
     if (p.do_g) {
       const int total = (k * ((k * 3 + 1) / 2 * 2) + 1) * 64 + 4;
       const int nblk = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;   // = the grid of rgb::launch
-      rgb::fold_kernel<<<(total + 255) / 256, 256, 0, st>>>(p.ws, p.ws_small, nblk, KP, dw, db, p.want_db3 ? db3 : nullptr,
+      rgb::fold_kernel<<<(total + 31) / 32, 256, 0, st>>>(p.ws, p.ws_small, nblk, KP, dw, db, p.want_db3 ? db3 : nullptr,
                                                             p.want_dalpha ? ps_dalpha : nullptr, k, rgb_out, n0, c64);
       SRK_CUDA_LAUNCH_CHECK("conv_rgb_fold");
     }

@@ -618,9 +618,9 @@ __global__ void __launch_bounds__(256) image_channel_sum_kernel(const T* __restr
   block_channel_sum<VEC>(s, smem, CV, rows, cv, prow, vals);
   // one reduction slot per image: ticket n, partial rows [n][gridDim.x][C]
   float* dst = out + (long long)n * g.C;
-  const int C4 = (g.C + 3) & ~3;
-  ordered_fold(vals, g.C, ra.tickets + n, gridDim.x, blockIdx.x, ra.partials + (size_t)n * gridDim.x * C4, scratch,
-               threadIdx.x, blockDim.x, sync_block, [&](int i, float v) { dst[i] = v * scale; });
+  ordered_fold(vals, g.C, ra.tickets + (size_t)n * red_tickets_needed(gridDim.x), gridDim.x, blockIdx.x,
+               ra.partials + (size_t)n * red_partial_floats(gridDim.x, g.C), scratch, threadIdx.x, blockDim.x, sync_block,
+               [&](int i, float v) { dst[i] = v * scale; });
 }
 
 __global__ void se_fc_kernel(const float* __restrict__ pool, const float* __restrict__ w1,
@@ -954,7 +954,8 @@ static inline bool c_ok(const srk_tensor* t) {
 }
 // partial rows of `slots` reductions with `nblk` blocks and `nv` values each must fit the reduce workspace
 static inline bool red_fits(long long slots, long long nblk, int nv) {
-  return slots <= kRedTickets && slots * nblk * ((nv + 3) & ~3) <= (long long)kRedPartialFloats;
+  return slots * red_tickets_needed((int)nblk) <= kRedTickets &&
+         slots * red_partial_floats((int)nblk, nv) <= (long long)kRedPartialFloats;
 }
 #define RED_WS_CHECK(ws, slots, nblk, nv, name)                                                              \
   do {                                                                                                       \
