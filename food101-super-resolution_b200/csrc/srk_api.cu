@@ -158,6 +158,11 @@ extern "C" int srk_conv_dgrad_bnred(const srk_tensor* dz, const srk_tensor* dx, 
         dz->c == 64 && dx->c == 64 && same_geometry(dz, dx)))
     return 2;
   BnRedArgs br = {z, mean, invstd, gamma, beta, alpha, sum_g, sum_gz, dalpha};
+  if (tc_fold() == 4) {
+    const int rs = conv_fprop_strip_launch(dz, dx, w_packed_dgrad, 64, nullptr, SRK_ACT_NONE, nullptr, nullptr, 0, nullptr,
+                                           nullptr, (cudaStream_t)stream, &br, reduce_ws, nullptr);
+    if (rs >= 0) return rs;
+  }
   const int rc = conv_fprop_fold_launch(dz, dx, w_packed_dgrad, 64, nullptr, SRK_ACT_NONE, nullptr, nullptr, 0, nullptr,
                                         nullptr, nullptr, 0, (cudaStream_t)stream, &br, reduce_ws, nullptr);
   return rc < 0 ? 2 : rc;

@@ -559,7 +559,7 @@ int tc_fold() {
   if (g_tc_fold < 0) {
     const char* e = getenv("SRK_TC_FOLD");
     g_tc_fold = e ? atoi(e) : 2;   // measured (C2 layer): fprop 23.2 / 24.4, fprop+stats 24.8 / 27.8, dgrad+res 25.8 / 27.1 us (2 / 0)
-    if (g_tc_fold < 0 || g_tc_fold > 3) g_tc_fold = 2;
+    if (g_tc_fold < 0 || g_tc_fold > 4) g_tc_fold = 2;
   }
   return g_tc_fold;
 }
@@ -592,6 +592,11 @@ int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w
     const int rc = conv_fprop_fold_launch(x, y, w_packed, cout, bias, act, alpha, residual, shuffle, nullptr, nullptr,
                                           workspace, 3, st, nullptr, nullptr, zsave);
     if (rc >= 0) return rc;
+  }
+  if (r == 3 && tc_fold() == 4) {
+    const int rc = conv_fprop_strip_launch(x, y, w_packed, cout, bias, act, alpha, residual, shuffle, stats_sum,
+                                           stats_sumsq, st, nullptr, reduce_ws, zsave);
+    if (rc >= 0) return rc;   // -1: not a plain 64 -> 64 pass -> the halo-slab kernels below
   }
   if (r == 3 && tc_fold() && !(tc_fold() >= 2 && shuffle != 0)) {
     const int rc = conv_fprop_fold_launch(x, y, w_packed, cout, bias, act, alpha, residual, shuffle, stats_sum,
@@ -721,7 +726,7 @@ int probe_ldtm_rate(int nwarps, int batch, float* out_host);
 // (0 = none; it is cleared by the call), out_host[1] = the mode now in effect.  Synchronises the device.
 extern "C" int srk_tc_probe(int variant, float* out_host, int out_len) {
   if (variant >= 0 && variant <= 2) srk::tc_set_mode(variant);
-  if (variant >= 10 && variant <= 13) { srk::tc_fold(); srk::g_tc_fold = variant - 10; }  // 3x3 kernel choice (see tc_fold)
+  if (variant >= 10 && variant <= 14) { srk::tc_fold(); srk::g_tc_fold = variant - 10; }  // 3x3 kernel choice (see tc_fold)
   if (variant == 30 || variant == 31) srk::g_up_pair = variant - 30;   // N = 128 CTA-pair upsample convs off / on
   if (variant == 20 && out_host && out_len >= 2) {   // query: out[1] = 1 when the folded-tap kernel is the default
     out_host[0] = 0.f;

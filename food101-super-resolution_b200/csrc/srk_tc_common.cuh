@@ -239,6 +239,14 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
                            float* stats_sumsq, void* workspace, int variant, cudaStream_t st, const BnRedArgs* br,
                            void* reduce_ws, void* zsave);
 
+// Column-strip formulation of the 3x3 64 -> 64 conv (srk_conv_strip_tc.cu).  Returns 0 ok, 1 error, -1 not applicable.
+int conv_fprop_strip_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout, const float* bias,
+                            int act, const float* alpha, const srk_tensor* residual, int shuffle, float* stats_sum,
+                            float* stats_sumsq, cudaStream_t st, const BnRedArgs* br, void* reduce_ws, void* zsave);
+// 3x3 kernel choice (SRK_TC_FOLD / srk_tc_probe 10 + v): 0 per-tap 8-warp kernel, 1 folded taps, 2 per-tap on the
+// 16-warp pipeline, 3 per-tap on CTA pairs, 4 column strips for the 64 -> 64 passes (others as 2)
+int tc_fold();
+
 // ---- host: TMA descriptor encoding through the driver entry point (no link-time libcuda dependency) ----
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

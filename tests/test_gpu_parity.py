@@ -232,12 +232,12 @@ def test_prelu_epilogues_with_nonpositive_slope(cin, cout, k, h, w, n, act, shuf
 
 
 @pytest.mark.parametrize("cin,cout,k,h,w,n,act,shuffle", [c for c in CONV_CASES if c[2] == 3 and c[0] >= 64])
-@pytest.mark.parametrize("fold", [0, 1, 2, 3])
+@pytest.mark.parametrize("fold", [0, 1, 2, 3, 4])
 def test_conv3x3_both_tc_kernels_vs_oracle(cin, cout, k, h, w, n, act, shuffle, fold):
-    """Three tcgen05 variants serve the 3x3 convs (0: per-tap kernel of srk_conv_tc.cu, 2: per-tap on the 16-warp
-    pipeline of srk_conv_fold_tc.cu, 1: the folded-tap kernel
-    (srk_conv_fold_tc.cu, three horizontal taps in the MMA N dimension).  Both must match the oracle whichever
-    one is the default."""
+    """Five tcgen05 variants serve the 3x3 convs (0: per-tap kernel of srk_conv_tc.cu, 2: per-tap on the 16-warp
+    pipeline of srk_conv_fold_tc.cu, 1: the folded-tap kernel (three horizontal taps in the MMA N dimension, shifted
+    across TMEM lanes), 3: per-tap on CTA pairs, 4: column strips for the 64 -> 64 passes (srk_conv_strip_tc.cu: the
+    horizontal taps in N, shifted across TMEM COLUMN blocks).  All must match the oracle whichever one is the default."""
     import ctypes
     from srk import _lib as L
     out = (ctypes.c_float * 2)()
@@ -648,6 +648,64 @@ def test_perceptual_loss_vs_oracle(dtype, hw):
         assert rel_err(f_srk, f_ref) <= 2e-2
         cos = torch.nn.functional.cosine_similarity(sg.grad.cpu().flatten(), go.flatten(), dim=0).item()
         assert cos >= 0.9, cos
+
+
+@pytest.mark.parametrize("n,h,w", [(1, 5, 1), (2, 7, 2), (3, 64, 64), (1, 130, 3), (5, 30, 37)])
+@pytest.mark.parametrize("mode", ["plain", "stats", "residual", "prelu"])
+def test_column_strip_conv_edge_geometries(n, h, w, mode):
+    """srk_conv_strip_tc.cu on geometries that stress its bookkeeping: a single column, runs shorter than the halo,
+    strips that span image borders, more strips than CTAs have runs, ragged last strip - plain, with BN statistics,
+    with a residual and with a PReLU epilogue - against the per-tap kernel (bit-identical accumulation order is not
+    expected: fp32 sums of the same products in a different order) and against the fp32 oracle."""
+    import ctypes
+    import srk
+    from srk import _lib as L
+    from srk import ops
+    srk.set_compute_dtype("bf16")
+    g = torch.Generator().manual_seed(n * 100 + h + w)
+
+    def act(c, scale=1.0):
+        t = torch.zeros(n, h + 2, w + 2, c)
+        t[:, 1:-1, 1:-1] = torch.randn(n, h, w, c, generator=g) * scale
+        return t.to(DEV).bfloat16()
+
+    x, res = act(64), act(64)
+    wt = (torch.randn(64, 64, 3, 3, generator=g) / 24).bfloat16().float().to(DEV)
+    bias = (torch.randn(64, generator=g) * 0.1).to(DEV)
+    alpha = torch.tensor([0.25], device=DEV)
+    out = (ctypes.c_float * 2)()
+    L.call("srk_tc_probe", 20, out, 2)
+    default = int(out[1])
+    got = {}
+    try:
+        for fold in (2, 4):
+            L.call("srk_tc_probe", 10 + fold, out, 2)
+            sums = torch.empty((2, 64), dtype=torch.float32, device=DEV) if mode == "stats" else None
+            y, used = ops.conv_fprop(x, False, wt, bias, L.ACT_PRELU if mode == "prelu" else L.ACT_NONE,
+                                     alpha if mode == "prelu" else None, res if mode == "residual" else None, 0, False,
+                                     torch.bfloat16, bn_sums=sums)
+            assert used
+            got[fold] = (y.float().cpu(), None if sums is None else sums.cpu())
+    finally:
+        L.call("srk_tc_probe", 10 + default, out, 2)
+        assert out[0] == 0, "tcgen05 protocol error flag %r" % out[0]
+    xi = x[:, 1:-1, 1:-1].float().permute(0, 3, 1, 2).cpu()
+    want = F.conv2d(xi, wt.cpu(), bias.cpu(), padding=1)
+    if mode == "prelu":
+        want = F.prelu(want, alpha.cpu())
+    if mode == "residual":
+        want = want + res[:, 1:-1, 1:-1].float().permute(0, 3, 1, 2).cpu()
+    for fold in (2, 4):
+        y = got[fold][0]
+        assert rel_err(y[:, 1:-1, 1:-1].permute(0, 3, 1, 2), want) <= 1e-2, fold
+        assert float(y[:, 0].abs().max()) == 0 and float(y[:, -1].abs().max()) == 0, fold
+        assert float(y[:, :, 0].abs().max()) == 0 and float(y[:, :, -1].abs().max()) == 0, fold
+    assert rel_err(got[4][0], got[2][0]) <= 1e-2
+    if mode == "stats":
+        pre = F.conv2d(xi, wt.cpu(), bias.cpu(), padding=1)
+        want_s = torch.stack([pre.sum(dim=(0, 2, 3)), (pre * pre).sum(dim=(0, 2, 3))])
+        for fold in (2, 4):
+            assert rel_err(got[fold][1], want_s) <= 2e-3, fold
 
 
 @pytest.mark.parametrize("with_prelu", [True, False])
