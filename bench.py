@@ -254,7 +254,7 @@ def _time_replayed(launch_sets, reps=5):
     return best
 
 
-def kernel_rooflines(B, dev, pk):
+def kernel_rooflines(B, dev, pk, timer=None):
     """Per-kernel rooflines of the C2 step's heaviest kernels, each timed ALONE (hence against the BURST tensor peak /
     the measured copy bandwidth) at the step's own shapes, on four rotating sets of seeded random operands.
     Algorithmic work per launch: convs 2 * N*H*W * Cin * Cout * 9 FLOP; HBM kernels: every distinct input read once and
@@ -290,7 +290,7 @@ def kernel_rooflines(B, dev, pk):
     out = []
 
     def add(name, bound, work, launches, per_step, note=None):
-        ms = _time_replayed(launches)
+        ms = (timer or _time_replayed)(launches)
         if bound == "tensor":
             ach, peak, unit = work / (ms * 1e-3) / 1e12, pk["tf_burst"], "TFLOP/s"
         else:

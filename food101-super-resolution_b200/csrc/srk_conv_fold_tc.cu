@@ -167,7 +167,7 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     mbar_init(smem_u32(&bars->wfull), 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bars->tfull[i]), 1); mbar_init(smem_u32(&bars->tempty[i]), (kPair ? 2 : 1) * kEpiWarps);
-      mbar_init(smem_u32(&bars->oready[i]), kEpiThreads); mbar_init(smem_u32(&bars->ofree[i]), 1);
+      mbar_init(smem_u32(&bars->oready[i]), kEpiWarps); mbar_init(smem_u32(&bars->ofree[i]), 1);
       mbar_init(smem_u32(&bars->rfull[i]), 1);
     }
     fence_barrier_init();
@@ -400,7 +400,8 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (staged) {
           if (ok) ok = mbar_wait(smem_u32(&bars->ofree[acc]), ((it >> 1) & 1) ^ 1, p.err, 7);
           if (ok && p.has_residual) ok = mbar_wait(smem_u32(&bars->rfull[acc]), (it >> 1) & 1, p.err, 8);
-          mbar_arrive(smem_u32(&bars->oready[acc]));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->oready[acc]));
         }
         continue;
       }
@@ -590,8 +591,10 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           *reinterpret_cast<uint4*>(orow + (((cq * (CPT / 8) + j) ^ ((row - ROW0) & 7)) << 4)) = o;
         }
       }
+      // every writer fences its own stores towards the async proxy; one arrival per warp
       fence_proxy_async();
-      mbar_arrive(smem_u32(&bars->oready[acc]));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars->oready[acc]));
       if (tr) trace[11 * 32 + it] = clock64();
     }
     if (stats_sum) {

@@ -28,11 +28,12 @@
 #include "srk_tc_common.cuh"
 
 #include <cstring>
+#include <type_traits>
 
 namespace srk {
 
 int* tc_err_flag();
-int zero_border(const srk_tensor* t, cudaStream_t st);
+extern long long* g_tc_trace;
 
 namespace strip {
 
@@ -72,6 +73,7 @@ struct Params {
   float* red_part;
   __nv_bfloat16* zsave;    // PReLU with a slope <= 0: copy of the pre-activation (y geometry) or null
   int* err;
+  long long* trace;        // bring-up: clock64 stamps of CTA 0 ([16 roles][32 tiles], srk_tc_probe 100 / 102) or null
 };
 
 struct __align__(8) Barriers {
@@ -144,7 +146,7 @@ conv3x3_strip_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     mbar_init(smem_u32(&bars->wfull), 1);
     for (int i = 0; i < RING; ++i) { mbar_init(smem_u32(&bars->tfull[i]), 1); mbar_init(smem_u32(&bars->tempty[i]), kEpiWarps); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&bars->oready[i]), kEpiThreads); mbar_init(smem_u32(&bars->ofree[i]), 1);
+      mbar_init(smem_u32(&bars->oready[i]), kEpiWarps); mbar_init(smem_u32(&bars->ofree[i]), 1);
       mbar_init(smem_u32(&bars->rfull[i]), 1);
     }
     fence_barrier_init();
@@ -181,25 +183,30 @@ conv3x3_strip_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         tma_load_2d(wsm + r * 3 * NT * KC * 2, &tmW, smem_u32(&bars->wfull), 0, r * 3 * NT);
     }
     __syncwarp();
-    int s = 0;
+    int s = 0, ntile = 0;
     uint32_t ph = 0;
     bool ok = true;
     Run run;
     for (int t = t0; ok && next_run(t, t1, p.W, run);) {
       for (int i = 0; i < run.nin && ok; ++i) {
-        ok = mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1, p.err, 1);
+        ok = mbar_wait_relaxed(smem_u32(&bars->empty[s]), ph ^ 1, p.err, 1);
         if (!ok) break;
         if (elect_one()) {
           const uint32_t fb = smem_u32(&bars->full[s]);
           mbar_arrive_expect_tx(fb, SLAB_USED * KC * 2);
           tma_load_3d(asm0 + s * STAGE_BYTES, &tmA, fb, 0, run.xlo + i, run.k * TM - 1);
+          if (p.trace && blockIdx.x == 0 && ntile < 32) p.trace[0 * 32 + ntile] = clock64();
         }
+        ++ntile;
         __syncwarp();
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
+    // tcgen05.mma issue blocks once the tensor queue is full, so the issuing thread cannot run ahead of the pipe: every
+    // cycle it spends between two columns (barrier waits, commits) is a cycle the pipe idles.  The waits for column
+    // i + 1 are therefore taken in the MIDDLE of column i's MMAs, while the queued ones execute.
     const uint32_t idesc64 = make_idesc_bf16(TM, 64, 0, 0), idesc128 = make_idesc_bf16(TM, 128, 0, 0),
                    idesc192 = make_idesc_bf16(TM, 192, 0, 0);
     const uint64_t desc_hi = make_smem_desc(0, 16, 1024, kLayoutSW128, 0) & 0xFFFFFFFF00000000ull;
@@ -207,59 +214,102 @@ conv3x3_strip_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     const uint32_t w_lo = lo_base + (wsm >> 4), a_lo0 = lo_base + (asm0 >> 4);
     constexpr uint32_t kRow = KC * 2 / 16;              // 16-byte units per operand row
     constexpr uint32_t kWr = 3 * NT * kRow, kWs = NT * kRow;   // one kernel row / one horizontal tap of weights
-    bool ok = mbar_wait(smem_u32(&bars->wfull), 0, p.err, 2);
-    int s = 0;
+    // Control flow of this warp depends on kernel parameters and blockIdx only (a timed-out wait raises the error
+    // flag but steers nothing), so the compiler keeps the stage / ring bookkeeping and the descriptor words in uniform
+    // registers: with per-thread loop state every tcgen05.mma cost ~8 R2UR / UMOV instructions (60 - 75 cycles of
+    // issue per MMA), which made the ISSUING THREAD, not the tensor pipe, the bottleneck of the tile.
+    auto wait_hot = [&](uint32_t bar, uint32_t parity, int code) {
+      if (mbar_try_wait(bar, parity)) return;
+      const long long tw = clock64();
+      while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - tw > 8000000000LL) { if (p.err) atomicExch(p.err, code); return; }
+      }
+    };
+    wait_hot(smem_u32(&bars->wfull), 0, 2);
+    struct Col { int t; Run run; int i, base; bool valid; };
+    auto advance = [&](Col& c) {
+      if (++c.i >= c.run.nin) { c.base += c.run.nin + 2; c.i = 0; c.valid = next_run(c.t, t1, p.W, c.run); }
+    };
+    // blocks a column opens must have been drained by the epilogue (their previous use, 8 blocks ago); its slab landed
+    auto wait_col = [&](const Col& c, int s, uint32_t ph) {
+      const int g0 = c.base + c.i;
+      if (c.i == 0) {
+        wait_hot(smem_u32(&bars->tempty[g0 & 7]), ((g0 >> 3) & 1) ^ 1, 3);
+        wait_hot(smem_u32(&bars->tempty[(g0 + 1) & 7]), (((g0 + 1) >> 3) & 1) ^ 1, 3);
+      }
+      wait_hot(smem_u32(&bars->tempty[(g0 + 2) & 7]), (((g0 + 2) >> 3) & 1) ^ 1, 3);
+      wait_hot(smem_u32(&bars->full[s]), ph, 4);
+    };
+    Col cur;
+    cur.t = t0; cur.i = 0; cur.base = 0;
+    cur.valid = next_run(cur.t, t1, p.W, cur.run);
+    int s = 0, ntile = 0;
     uint32_t ph = 0;
-    int base = 0;          // ring position of the run's block 0 (running block counter of this CTA)
-    Run run;
-    for (int t = t0; ok && next_run(t, t1, p.W, run);) {
-      for (int i = 0; i < run.nin && ok; ++i) {
-        const int g0 = base + i;          // blocks g0 (s = 2), g0 + 1 (s = 1), g0 + 2 (s = 0)
-        // blocks this column opens must have been drained by the epilogue (their previous use, 8 blocks ago)
-        for (int g = (i == 0 ? g0 : g0 + 2); g <= g0 + 2 && ok; ++g)
-          ok = mbar_wait(smem_u32(&bars->tempty[g & 7]), ((g >> 3) & 1) ^ 1, p.err, 3);
-        if (!ok) break;
-        ok = mbar_wait(smem_u32(&bars->full[s]), ph, p.err, 4);
-        if (!ok) break;
-        tc_fence_after();
-        const int p0 = g0 & 7, p1 = (g0 + 1) & 7, p2 = (g0 + 2) & 7;
-        const uint32_t c0 = tmem_base + (uint32_t)(7 - p0) * NT, c1 = tmem_base + (uint32_t)(7 - p1) * NT,
-                       c2 = tmem_base + (uint32_t)(7 - p2) * NT;
-        const uint32_t a_lo = a_lo0 + s * (STAGE_BYTES >> 4);
-        const uint32_t live = i == 0 ? 0u : 1u;   // blocks g0, g0 + 1 hold earlier columns' contributions
-        if (elect_one()) {
+    if (cur.valid) wait_col(cur, s, ph);
+    while (cur.valid) {
+      Col nxt = cur;
+      advance(nxt);
+      const int s2 = s + 1 == STAGES ? 0 : s + 1;
+      const uint32_t ph2 = s2 == 0 ? ph ^ 1 : ph;
+      const bool tr = p.trace && blockIdx.x == 0 && ntile < 32;
+      tc_fence_after();
+      const int g0 = cur.base + cur.i;          // blocks g0 (s = 2), g0 + 1 (s = 1), g0 + 2 (s = 0)
+      const int p0 = g0 & 7, p1 = (g0 + 1) & 7, p2 = (g0 + 2) & 7;
+      const uint32_t c0 = tmem_base + (uint32_t)(7 - p0) * NT, c1 = tmem_base + (uint32_t)(7 - p1) * NT,
+                     c2 = tmem_base + (uint32_t)(7 - p2) * NT;
+      const uint32_t a_lo = a_lo0 + s * (STAGE_BYTES >> 4);
+      const uint32_t live = cur.i == 0 ? 0u : 1u;   // blocks g0, g0 + 1 hold earlier columns' contributions
+      // kWrap 0: blocks p0+2, p0+1, p0 contiguous (descending columns) -> one N = 192 MMA per (r, ks);
+      //       1: ring wrap between s = 0 and s = 1 (p0 == 6);  2: between s = 1 and s = 2 (p0 == 7)
+      auto issue_rows = [&](auto wrap_tag, int r_begin, int r_end) {
+        constexpr int kWrap = decltype(wrap_tag)::value;
 #pragma unroll
-          for (int r = 0; r < 3; ++r)
+        for (int r = 0; r < 3; ++r) {
+          if (r < r_begin || r >= r_end) continue;
 #pragma unroll
-            for (int ks = 0; ks < KC / 16; ++ks) {
-              const uint64_t ad = desc_hi | (a_lo + r * kRow + 2 * ks);
-              const uint32_t b0 = w_lo + r * kWr + 2 * ks;
-              if (r == 0 && ks == 0) {
-                // the block of output column x + 1 is opened here (overwrite); the other two accumulate
-                umma_bf16(c2, ad, desc_hi | b0, idesc64, 0u);
-                umma_bf16(c1, ad, desc_hi | (b0 + kWs), idesc64, live);
-                umma_bf16(c0, ad, desc_hi | (b0 + 2 * kWs), idesc64, live);
-              } else if (p0 <= 5) {           // blocks p0+2, p0+1, p0 are contiguous (descending columns): one N = 192 MMA
-                umma_bf16(c2, ad, desc_hi | b0, idesc192, 1u);
-              } else if (p0 == 6) {           // ring wrap between s = 0 and s = 1
-                umma_bf16(c2, ad, desc_hi | b0, idesc64, 1u);
-                umma_bf16(c1, ad, desc_hi | (b0 + kWs), idesc128, 1u);
-              } else {                        // ring wrap between s = 1 and s = 2
-                umma_bf16(c2, ad, desc_hi | b0, idesc128, 1u);
-                umma_bf16(c0, ad, desc_hi | (b0 + 2 * kWs), idesc64, 1u);
-              }
+          for (int ks = 0; ks < KC / 16; ++ks) {
+            const uint64_t ad = desc_hi | (a_lo + r * kRow + 2 * ks);
+            const uint32_t b0 = w_lo + r * kWr + 2 * ks;
+            if (r == 0 && ks == 0) {
+              // the block of output column x + 1 is opened here (overwrite); the other two accumulate
+              umma_bf16(c2, ad, desc_hi | b0, idesc64, 0u);
+              umma_bf16(c1, ad, desc_hi | (b0 + kWs), idesc64, live);
+              umma_bf16(c0, ad, desc_hi | (b0 + 2 * kWs), idesc64, live);
+            } else if (kWrap == 0) {
+              umma_bf16(c2, ad, desc_hi | b0, idesc192, 1u);
+            } else if (kWrap == 1) {
+              umma_bf16(c2, ad, desc_hi | b0, idesc64, 1u);
+              umma_bf16(c1, ad, desc_hi | (b0 + kWs), idesc128, 1u);
+            } else {
+              umma_bf16(c2, ad, desc_hi | b0, idesc128, 1u);
+              umma_bf16(c0, ad, desc_hi | (b0 + 2 * kWs), idesc64, 1u);
             }
-          umma_commit(smem_u32(&bars->empty[s]));
-          umma_commit(smem_u32(&bars->tfull[p0]));          // output column x - 1 is complete
-          if (i == run.nin - 1) {                           // end of the run: the two blocks no later column feeds
-            umma_commit(smem_u32(&bars->tfull[p1]));
-            umma_commit(smem_u32(&bars->tfull[p2]));
           }
         }
-        __syncwarp();
-        if (++s == STAGES) { s = 0; ph ^= 1; }
+      };
+      auto issue = [&](int r_begin, int r_end) {
+        if (p0 <= 5) issue_rows(std::integral_constant<int, 0>{}, r_begin, r_end);
+        else if (p0 == 6) issue_rows(std::integral_constant<int, 1>{}, r_begin, r_end);
+        else issue_rows(std::integral_constant<int, 2>{}, r_begin, r_end);
+      };
+      if (tr && lane == 0) p.trace[1 * 32 + ntile] = clock64();
+      if (elect_one()) issue(0, 2);
+      __syncwarp();
+      if (tr && lane == 0) p.trace[2 * 32 + ntile] = clock64();
+      if (nxt.valid) wait_col(nxt, s2, ph2);     // overlaps the queued MMAs
+      if (tr && lane == 0) p.trace[3 * 32 + ntile] = clock64();
+      if (elect_one()) {
+        issue(2, 3);
+        umma_commit(smem_u32(&bars->empty[s]));
+        umma_commit(smem_u32(&bars->tfull[p0]));          // output column x - 1 is complete
+        if (cur.i == cur.run.nin - 1) {                   // end of the run: the two blocks no later column feeds
+          umma_commit(smem_u32(&bars->tfull[p1]));
+          umma_commit(smem_u32(&bars->tfull[p2]));
+        }
+        if (tr) p.trace[4 * 32 + ntile] = clock64();
       }
-      base += run.nin + 2;
+      __syncwarp();
+      cur = nxt; s = s2; ph = ph2; ++ntile;
     }
   } else if (warp == 2) {
     // ================= output store / residual load warp: stored output `it` <-> work item t0 + it =================
@@ -276,15 +326,17 @@ conv3x3_strip_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     __syncwarp();
     for (int it = 0; it < n_out; ++it) {
       const int b = it & 1;
-      if (!mbar_wait(smem_u32(&bars->oready[b]), (it >> 1) & 1, p.err, 6)) break;
+      if (!mbar_wait_relaxed(smem_u32(&bars->oready[b]), (it >> 1) & 1, p.err, 6)) break;
       if (elect_one()) {
         const int t = t0 + it, k = t / p.W, xo = t - k * p.W + 1;
+        if (p.trace && blockIdx.x == 0 && it < 32) p.trace[8 * 32 + it] = clock64();
         tma_store_3d(&tmY, osm + b * O_TILE_BYTES, 0, xo, k * TM);
         // the zero border columns of y (layout invariant) ride along with their interior neighbours
         if (xo == 1) tma_store_3d(&tmY, zsm, 0, 0, k * TM);
         if (xo == p.W) tma_store_3d(&tmY, zsm, 0, p.W + 1, k * TM);
         tma_store_commit();
         tma_store_wait_read0();
+        if (p.trace && blockIdx.x == 0 && it < 32) p.trace[9 * 32 + it] = clock64();
         if (p.has_residual && it + 2 < n_out) {
           const int t2 = t + 2, k2 = t2 / p.W, xo2 = t2 - k2 * p.W + 1;
           const uint32_t rb = smem_u32(&bars->rfull[b]);
@@ -324,8 +376,11 @@ conv3x3_strip_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const int g = base + j, slot = g & 7;
         const int xo = run.xlo - 1 + j;
         const bool stored = xo >= run.oa && xo <= run.ob;
-        if (ok) ok = mbar_wait(smem_u32(&bars->tfull[slot]), (g >> 3) & 1, p.err, 5);
+        const bool tr = p.trace && blockIdx.x == 0 && it < 32 && threadIdx.x == kEpiWarp0 * 32 && stored;
+        if (tr) p.trace[5 * 32 + it] = clock64();
+        if (ok) ok = mbar_wait_relaxed(smem_u32(&bars->tfull[slot]), (g >> 3) & 1, p.err, 5);
         tc_fence_after();
+        if (tr) p.trace[6 * 32 + it] = clock64();
         uint32_t v1[CPT];
         if (stored) {
           tmem_ld_32x16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(7 - slot) * NT + c0, v1);
@@ -363,10 +418,10 @@ conv3x3_strip_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 #pragma unroll
           for (int q = 0; q < CPT; ++q) { s1[q] += f[q]; s2[q] = fmaf(f[q], f[q], s2[q]); }
         }
-        if (ok) ok = mbar_wait(smem_u32(&bars->ofree[acc]), ((it >> 1) & 1) ^ 1, p.err, 7);
+        if (ok) ok = mbar_wait_relaxed(smem_u32(&bars->ofree[acc]), ((it >> 1) & 1) ^ 1, p.err, 7);
         if (bn_red) {
           // the "residual" tile is Z, the saved input of the BatchNorm layer below: reduce against it, do not add
-          if (ok) ok = mbar_wait(smem_u32(&bars->rfull[acc]), (it >> 1) & 1, p.err, 8);
+          if (ok) ok = mbar_wait_relaxed(smem_u32(&bars->rfull[acc]), (it >> 1) & 1, p.err, 8);
           if (interior) {
 #pragma unroll
             for (int q = 0; q < CPT / 8; ++q) {
@@ -397,7 +452,7 @@ conv3x3_strip_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             }
           }
         } else if (p.has_residual) {
-          if (ok) ok = mbar_wait(smem_u32(&bars->rfull[acc]), (it >> 1) & 1, p.err, 8);
+          if (ok) ok = mbar_wait_relaxed(smem_u32(&bars->rfull[acc]), (it >> 1) & 1, p.err, 8);
 #pragma unroll
           for (int q = 0; q < CPT / 8; ++q) {
             const uint4 rr = *reinterpret_cast<const uint4*>(orow + (((cq * (CPT / 8) + q) ^ (row & 7)) << 4));
@@ -416,8 +471,12 @@ conv3x3_strip_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                            pack_bf16x2(f[8 * q + 4], f[8 * q + 5]), pack_bf16x2(f[8 * q + 6], f[8 * q + 7]));
           *reinterpret_cast<uint4*>(orow + (((cq * (CPT / 8) + q) ^ (row & 7)) << 4)) = o;
         }
+        // every writer fences its own stores towards the async proxy; one arrival per warp (512 per-thread arrivals
+        // on one shared-memory barrier cost more than the tile's MMAs)
         fence_proxy_async();
-        mbar_arrive(smem_u32(&bars->oready[acc]));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->oready[acc]));
+        if (tr) p.trace[7 * 32 + it] = clock64();
         ++it;
       }
       base += run.nin + 2;
@@ -552,6 +611,7 @@ int conv_fprop_strip_launch(const srk_tensor* x, const srk_tensor* y, const void
   p.red_part = reduce_ws ? red_partials(reduce_ws) : nullptr;
   p.zsave = (__nv_bfloat16*)zsave;
   p.err = tc_err_flag();
+  p.trace = g_tc_trace;
   if (br) {
     SRK_REQUIRE(act == SRK_ACT_NONE && residual == nullptr && stats_sum == nullptr,
                 "conv_strip: the fused BN-backward reduction covers the plain dgrad");

@@ -55,6 +55,24 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* er
   }
   return true;
 }
+// The same for the warps that WAIT most of the time (epilogue, TMA producer, store warp): a hot polling loop of ~18 warps
+// takes the issue slots the single MMA-issuing warp needs - its ~15 instructions per tcgen05.mma then take longer than
+// the MMA itself (measured: 77 cycles per N = 192 MMA issue).  Sleeping between polls leaves the scheduler to the
+// warps that have work; the added wake-up latency is far inside these roles' slack.
+__device__ __forceinline__ bool mbar_wait_relaxed(uint32_t bar, uint32_t parity, int* err_flag, int code) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  unsigned ns = 32;
+  while (true) {
+    __nanosleep(ns);
+    if (mbar_try_wait(bar, parity)) return true;
+    if (ns < 256) ns <<= 1;
+    if (clock64() - t0 > 8000000000LL) {
+      if (err_flag) atomicExch(err_flag, code);
+      return false;
+    }
+  }
+}
 
 // ---- TMA ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const void* tmap) {
