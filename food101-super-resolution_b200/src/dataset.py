@@ -24,14 +24,27 @@ def synthetic_pair(n, h_lr, w_lr, scale, seed=1234):
     return lr.contiguous(), hr.contiguous()
 
 
+def synthetic_image_u8(h, w, seed):
+    """A decoded-photo stand-in: uint8 [h, w, 3] (what np.asarray(PIL image) gives), low-passed 8-bit noise."""
+    g = torch.Generator().manual_seed(seed)
+    img = torch.randint(0, 256, (1, 3, h, w), generator=g).float()
+    img = F.conv2d(img, _lowpass_kernel(), padding=2, groups=3)
+    return img[0].round().clamp(0, 255).to(torch.uint8).permute(1, 2, 0).contiguous()
+
+
 class SyntheticSRDataset(torch.utils.data.Dataset):
-    def __init__(self, length=1024, crop_size=200, scale_factor=4, seed=1234):
-        self.length, self.crop, self.scale, self.seed = length, crop_size, scale_factor, seed
+    """raw=False: (lr, hr) float pairs made on the host; raw=True: uint8 [h, w, 3] source images a little larger than
+    the crop - crop / flip / downsample then happen on the GPU (srk.data)."""
+
+    def __init__(self, length=1024, crop_size=200, scale_factor=4, seed=1234, raw=False):
+        self.length, self.crop, self.scale, self.seed, self.raw = length, crop_size, scale_factor, seed, raw
 
     def __len__(self):
         return self.length
 
     def __getitem__(self, idx):
+        if self.raw:
+            return synthetic_image_u8(self.crop + 24 + (idx % 3) * 8, self.crop + 40 - (idx % 2) * 16, self.seed + idx)
         lr, hr = synthetic_pair(1, self.crop // self.scale, self.crop // self.scale, self.scale, self.seed + idx)
         return lr[0], hr[0]
 
@@ -41,11 +54,14 @@ class FoodSRDataset(torch.utils.data.Dataset):
     when the archive is already under ./data (download needs a network); with SR_SYNTHETIC_DATA=<n> it
     serves <n> synthetic crops instead."""
 
-    def __init__(self, split="train", crop_size=200, scale_factor=4):
-        self.crop_size, self.scale_factor = crop_size, scale_factor
+    def __init__(self, split="train", crop_size=200, scale_factor=4, raw=False):
+        """raw=True (an addition; the reference has no such flag): __getitem__ returns the decoded image as a uint8
+        [h, w, 3] tensor (up-scaled first when smaller than the crop, reference dataset.py:31-32) and the crop / flip /
+        ToTensor / bicubic down-sampling run on the GPU (srk.data.GpuBatches)."""
+        self.crop_size, self.scale_factor, self.raw, self.split = crop_size, scale_factor, raw, split
         n_syn = int(os.environ.get("SR_SYNTHETIC_DATA", "0"))
         if n_syn > 0:
-            self.inner = SyntheticSRDataset(n_syn, crop_size, scale_factor, seed=1234 if split == "train" else 4321)
+            self.inner = SyntheticSRDataset(n_syn, crop_size, scale_factor, seed=1234 if split == "train" else 4321, raw=raw)
             self.food = None
             return
         from torchvision import transforms
@@ -69,5 +85,8 @@ class FoodSRDataset(torch.utils.data.Dataset):
         img, _ = self.food[idx]
         if min(img.size) < self.crop_size:
             img = self.grow(img)
+        if self.raw:
+            import numpy as np
+            return torch.from_numpy(np.asarray(img.convert("RGB")).copy())
         hr = self.to_hr(img)
         return self.down(hr), hr

@@ -6,4 +6,4 @@ from .ops import cfg, set_compute_dtype, set_conv_impl, set_overlap_wgrad  # noq
 
 __all__ = ["fn", "ops", "cfg", "set_compute_dtype", "set_conv_impl", "set_overlap_wgrad"]
 from . import optim  # noqa: F401,E402
-from . import dp, evaluate  # noqa: F401,E402
+from . import data, dp, evaluate, trainer  # noqa: F401,E402

@@ -76,6 +76,7 @@ SIGNATURES = {
     "srk_ssim": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "srk_adam_step": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, _P, c_float, _P]),
     "srk_adam_multi": (c_int, [c_int, _P, _P, _P, _P, _P, c_float, c_float, c_float, c_float, _P, c_float, _P, _P, _P]),
+    "srk_sr_make_batch": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, _P, _P, _P]),
     "srk_tc_probe": (c_int, [c_int, POINTER(c_float), c_int]),
 }
 

@@ -9,6 +9,8 @@ Additions that do not change the reference surface (all via environment variable
   SR_CROP=<pixels>        HR crop size (default 200, as reference train.py:27)
   SRK_DTYPE=bf16|fp32     arithmetic of the conv stacks (default bf16 on the tensor cores)
   SRK_GRAPH=0             launch every kernel from Python instead of replaying the captured step
+  SRK_GPU_PIPELINE=0      make the (lr, hr) pairs on the host like the reference; default 1: the loaders ship decoded
+                          uint8 images and srk.data crops / flips / converts / down-samples on the GPU
   WANDB_MODE=disabled     wandb is optional; without the package a no-op logger is used
 
 Data parallelism (torchrun, WORLD_SIZE > 1; the reference has none): every rank draws the SAME seeded split and the
@@ -133,22 +135,31 @@ def train(config=None):
         cfg = run.config
         print(f"Running on {device} | Arch: {cfg.architecture} | ranks: {world}")
         split_gen = torch.Generator().manual_seed(SPLIT_SEED)
-        full_train_ds = FoodSRDataset(split="train", crop_size=crop, scale_factor=4)
+        gpu_pipe = os.environ.get("SRK_GPU_PIPELINE", "1") != "0"
+        full_train_ds = FoodSRDataset(split="train", crop_size=crop, scale_factor=4, raw=gpu_pipe)
         if cfg.subset < 1.0:
             total = len(full_train_ds)
             keep = int(total * cfg.subset)
             full_train_ds, _ = random_split(full_train_ds, [keep, total - keep], generator=split_gen)
         train_len = int(0.9 * len(full_train_ds))
         train_ds, val_ds = random_split(full_train_ds, [train_len, len(full_train_ds) - train_len], generator=split_gen)
-        test_ds = FoodSRDataset(split="test", crop_size=crop, scale_factor=4)
+        test_ds = FoodSRDataset(split="test", crop_size=crop, scale_factor=4, raw=gpu_pipe)
         if cfg.subset < 1.0:
             keep = int(len(test_ds) * cfg.subset)
             test_ds, _ = random_split(test_ds, [keep, len(test_ds) - keep], generator=split_gen)
         if rank == 0:
             print(f"Dataset: Train={len(train_ds)} | Val={len(val_ds)} | Test={len(test_ds)}")
-        mk = lambda ds, sh: DataLoader(ds, batch_size=cfg.batch_size, shuffle=sh, num_workers=0, pin_memory=True,
+        mk = lambda ds, sh: DataLoader(ds, batch_size=cfg.batch_size, shuffle=sh, num_workers=0, pin_memory=not gpu_pipe,
+                                       collate_fn=srk.data.collate_raw if gpu_pipe else None,
                                        generator=torch.Generator().manual_seed(SPLIT_SEED + 1) if sh else None)
         train_loader, val_loader, test_loader = mk(train_ds, True), mk(val_ds, False), mk(test_ds, False)
+        if gpu_pipe:
+            # crop offsets / flips come from one seeded generator shared by all ranks (every rank sees the same batch);
+            # NOTE the validation split of the reference is cut from the TRAIN dataset, so it keeps random crops
+            aug_gen = torch.Generator().manual_seed(SPLIT_SEED + 2)
+            train_loader = srk.data.GpuBatches(train_loader, crop, 4, True, device, aug_gen)
+            val_loader = srk.data.GpuBatches(val_loader, crop, 4, True, device, aug_gen)
+            test_loader = srk.data.GpuBatches(test_loader, crop, 4, False, device)
 
         model = get_model(cfg.architecture, scale_factor=4, device=device)
         if cfg.pretrained_weights:

@@ -274,6 +274,15 @@ int srk_adam_multi(int count, float* const* params, const float* const* grads, f
                    float eps, const int64_t* step_count, float grad_scale, const float* lr_dev,
                    const float* grad_scale_dev, void* stream);
 
+/* ---- training-sample pipeline (dataset.py:14-41: RandomCrop / CenterCrop + RandomHorizontalFlip + ToTensor, then
+ * transforms.Resize((crop/s, crop/s), BICUBIC) on the HR tensor = antialiased bicubic, ATen _upsample_bicubic2d_aa) ----
+ * src_u8: decoded images, uint8, [N][Hs][Ws][3] (hwc != 0) or [N][3][Hs][Ws]; offsets int32 [N][2] = (top, left) of
+ * each crop, flips uint8 [N] (drawn by the host with torch's generator, as torchvision draws them);
+ * hr: fp32 [N][3][crop][crop] = crop (flipped) / 255; lr: fp32 [N][3][crop/scale][crop/scale], not clamped.
+ * scale in {2, 3, 4}, crop % scale == 0. */
+int srk_sr_make_batch(const void* src_u8, int hwc, int n, int hs, int ws, const int32_t* offsets, const uint8_t* flips,
+                      int crop, int scale, float* hr, float* lr, void* stream);
+
 /* ---- bring-up / self-test hooks (tests only) --------------------------------------------------- */
 /* Runs the tcgen05 descriptor probe (see csrc/srk_probe.cu); results into out[] (host memory). */
 int srk_tc_probe(int variant, float* out_host, int out_len);

@@ -77,3 +77,38 @@ def test_gan_branch_runs(synthetic_env):
     import train
     metrics = train.train(_config(architecture="SRCNN", loss_function="gan", epochs=1, batch_size=4))
     assert math.isfinite(metrics["psnr"]) and math.isfinite(metrics["nlpd"])
+
+
+@pytest.mark.parametrize("scale,crop", [(4, 200), (4, 64), (2, 48), (3, 45)])
+def test_gpu_sample_pipeline_matches_torchvision(scale, crop):
+    """srk.data (crop + flip + ToTensor + antialiased bicubic on the GPU) against the reference's own transforms
+    (reference dataset.py:17-39: RandomCrop, RandomHorizontalFlip, ToTensor, Resize(BICUBIC) on the tensor) applied on
+    the CPU to the same uint8 images with the same torch seed - identical crops / flips, HR bit-identical, LR within
+    1e-5 - and the CenterCrop (test split) variant."""
+    import numpy as np
+    from PIL import Image
+    from torchvision import transforms
+    from srk import data as D
+    from src.dataset import synthetic_image_u8
+    imgs = [synthetic_image_u8(crop + 13 + 7 * k, crop + 40 - 9 * k, seed=100 + k) for k in range(5)]
+    imgs.append(synthetic_image_u8(crop, crop, seed=9))            # exactly the crop size: RandomCrop draws nothing
+    src, sizes = D.collate_raw(imgs)
+    lr_size = crop // scale
+    down = transforms.Resize((lr_size, lr_size), interpolation=transforms.InterpolationMode.BICUBIC)
+    for train in (True, False):
+        tf = transforms.Compose(([transforms.RandomCrop(crop), transforms.RandomHorizontalFlip()] if train
+                                 else [transforms.CenterCrop(crop)]) + [transforms.ToTensor()])
+        torch.manual_seed(77)
+        want_hr = torch.stack([tf(Image.fromarray(im.numpy())) for im in imgs])
+        want_lr = torch.stack([down(h) for h in want_hr])
+        torch.manual_seed(77)
+        offs, flips = D.draw_crop_params(sizes, crop, train)
+        lr, hr = D.make_batch(src.to("cuda:0"), offs, flips, crop, scale)
+        assert hr.shape == want_hr.shape and lr.shape == want_lr.shape
+        assert torch.equal(hr.cpu(), want_hr), "HR crop / flip / ToTensor"
+        assert float((lr.cpu() - want_lr).abs().max()) <= 1e-5, float((lr.cpu() - want_lr).abs().max())
+        if train:
+            assert int(flips.sum()) not in (0, len(imgs))            # both orientations exercised
+    # channels-first uint8 input gives the same result
+    lr2, hr2 = D.make_batch(src.permute(0, 3, 1, 2).contiguous().to("cuda:0"), offs, flips, crop, scale)
+    assert torch.equal(hr2, hr) and torch.equal(lr2, lr)
