@@ -365,7 +365,7 @@ def ncu_traffic(kernel=None):
     p = os.path.join(ROOT, "profiles", "r2_ncu_kernels.json")
     if not os.path.exists(p):
         return None
-    d = json.load(open(p))
+    d = json.load(open(p)).get("kernels", {})
     rec = d.get(kernel) if kernel else None
     return None if rec is None else rec.get("dram_bytes")
 

@@ -716,10 +716,12 @@ int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w
 
 }  // namespace srk
 
+#ifdef SRK_WITH_PROBES   // micro-benchmarks (csrc/srk_probe_mma.cu): `python build.py --probes`, not part of the product library
 namespace srk {
 int probe_mma_rate(int n, int a_row_off, int mn_major, float* out_host);
 int probe_ldtm_rate(int nwarps, int batch, float* out_host);
 }
+#endif
 
 // Test / bring-up hook: variant 0..2 selects the A-staging mode of the tcgen05 conv (see the header
 // comment); any other value leaves it unchanged.  out_host[0] = the device-side protocol-error flag
@@ -733,6 +735,7 @@ extern "C" int srk_tc_probe(int variant, float* out_host, int out_len) {
     out_host[1] = (float)srk::tc_fold();
     return 0;
   }
+#ifdef SRK_WITH_PROBES
   if (variant >= 2000 && variant < 3000 && out_host && out_len >= 2)   // 2000 + nwarps + 100 * batch: TMEM read rate
     return srk::probe_ldtm_rate((variant - 2000) % 100, (variant - 2000) / 100, out_host);
   if (variant >= 1000 && out_host && out_len >= 2) {
@@ -740,6 +743,9 @@ extern "C" int srk_tc_probe(int variant, float* out_host, int out_len) {
     int v = variant - 1000;
     return srk::probe_mma_rate((v % 100) * 8, (v / 100) % 100, v / 10000, out_host);
   }
+#else
+  if (variant >= 1000) SRK_FAIL("srk_tc_probe: the micro-benchmarks are compiled in with `build.py --probes` only");
+#endif
   static long long* trace = nullptr;
   if (variant == 100) {
     if (!trace) cudaMalloc(&trace, 16 * 32 * sizeof(long long));

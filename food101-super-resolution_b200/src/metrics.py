@@ -6,6 +6,7 @@ data_range=1) and lpips 0.1.4.  PSNR and SSIM are restated as CUDA reductions wi
 sums (srk_psnr_sse / srk_ssim); LPIPS needs downloaded AlexNet weights and is reported as NaN unless
 an `lpips_fn` callable is supplied."""
 import math
+import os
 
 import torch
 
@@ -43,6 +44,11 @@ def psnr_from_sse(sse_total, numel, data_range=1.0):
 class MetricsCalculator:
     def __init__(self, device, lpips_fn=None):
         self.device = device
+        if lpips_fn is None and os.environ.get("SRK_LPIPS_WEIGHTS"):
+            # lpips.LPIPS(net='alex') (metrics.py:11) from a supplied state dict (src/lpips_alex.py); the package and its
+            # weights are not available offline, in which case the key stays NaN
+            from src.lpips_alex import LpipsAlex
+            lpips_fn = LpipsAlex.from_file(os.environ["SRK_LPIPS_WEIGHTS"], device)
         self.lpips_fn = lpips_fn
         self.nlpd = NLPDLoss(device=device, channels=3).to(device)
 

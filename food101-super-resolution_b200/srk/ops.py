@@ -498,6 +498,12 @@ def conv_wgrad(x, x_img, dz, dz_img, weight, need_bias, perm_tc=False, side=Fals
     backward passes, the gradients are assigned to weight.grad / bias.grad when the streams join at the end of the
     backward pass, and (None, None) is returned - the caller hands exactly that to autograd.  `bias` is the bias
     PARAMETER (needed to assign its gradient); parameters with hooks stay on the ordinary path."""
+    # frozen layer (requires_grad = False on the weight and on the bias): no gradient is wanted - and none must appear
+    # in .grad through the side-stream path, where a later optimizer over model.parameters() would pick it up
+    if torch.is_tensor(weight) and weight.is_leaf and not weight.requires_grad and \
+            (bias is None or not (torch.is_tensor(bias) and bias.requires_grad)):
+        return None, None
+
     def _hooked(t):
         return t is not None and (bool(t._backward_hooks) or bool(getattr(t, "_post_accumulate_grad_hooks", None)))
     side = (side and cfg.overlap_wgrad and torch.is_tensor(weight) and weight.is_leaf and not _hooked(weight)

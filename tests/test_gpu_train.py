@@ -112,3 +112,50 @@ def test_gpu_sample_pipeline_matches_torchvision(scale, crop):
     # channels-first uint8 input gives the same result
     lr2, hr2 = D.make_batch(src.permute(0, 3, 1, 2).contiguous().to("cuda:0"), offs, flips, crop, scale)
     assert torch.equal(hr2, hr) and torch.equal(lr2, lr)
+
+
+def test_visualize_tool_runs_on_reference_checkpoints(synthetic_env, monkeypatch):
+    """visualize.py (reference visualize.py:24-61,63-122): uint8 PSNR helper, get_prediction timing with a checkpoint
+    in the reference's state_dict layout, PNG outputs."""
+    import importlib
+    monkeypatch.setenv("NUM_EXAMPLES", "2")
+    monkeypatch.setenv("SR_SYNTHETIC_DATA", "3")
+    monkeypatch.setenv("OUTPUT_DIR", str(synthetic_env / "report"))
+    import visualize
+    importlib.reload(visualize)
+    from src.models import get_model
+    os.makedirs(synthetic_env / "weights", exist_ok=True)
+    torch.manual_seed(0)
+    torch.save(get_model("SRCNN", 4, "cpu").state_dict(), synthetic_env / "weights" / "srcnn_nlpd_best.pth")
+    times = visualize.run_comparison()
+    assert set(times) == {"SRCNN"} and times["SRCNN"] > 0           # the other checkpoints are missing: skipped, as upstream
+    files = sorted(os.listdir(next((synthetic_env / "report").iterdir())))
+    assert files == ["bicubic.png", "ground_truth.png", "input_lr_resized.png", "srcnn.png"]
+    a = torch.randint(0, 256, (8, 8, 3), dtype=torch.uint8).numpy()
+    assert visualize.calculate_psnr(a, a) == 100
+    assert abs(visualize.calculate_psnr(a.astype("float32") + 1, a) - 20 * math.log10(255.0)) < 1e-4
+
+
+def test_lpips_alex_module_properties():
+    """src/lpips_alex.py restates lpips.LPIPS(net='alex') (parity unpinned: neither the package nor its weights exist
+    offline): on random weights in the package's state_dict layout it must be 0 on identical inputs, symmetric,
+    positive otherwise, and MetricsCalculator must report it."""
+    from src.lpips_alex import LpipsAlex
+    from src.metrics import MetricsCalculator
+    torch.manual_seed(3)
+    ref = LpipsAlex()
+    idx = {1: 0, 2: 3, 3: 6, 4: 8, 5: 10}
+    sd = {}
+    for k, conv in enumerate(ref.convs):
+        sd["net.slice%d.%d.weight" % (k + 1, idx[k + 1])] = conv.weight.detach().clone()
+        sd["net.slice%d.%d.bias" % (k + 1, idx[k + 1])] = conv.bias.detach().clone()
+    for k in range(5):
+        sd["lin%d.model.1.weight" % k] = ref.lins[k].detach().clone()
+    m = LpipsAlex.from_state_dict(sd, "cuda:0")
+    x = torch.rand(2, 3, 64, 64, device="cuda:0") * 2 - 1
+    y = torch.rand(2, 3, 64, 64, device="cuda:0") * 2 - 1
+    assert m(x, y).shape == (2, 1, 1, 1)
+    assert float(m(x, x).abs().max()) == 0.0
+    assert torch.allclose(m(x, y), m(y, x)) and float(m(x, y).min()) > 0
+    got = MetricsCalculator("cuda:0", lpips_fn=m).compute((x + 1) / 2, (y + 1) / 2)
+    assert abs(got["lpips"] - float(m(x, y).mean())) < 1e-6
