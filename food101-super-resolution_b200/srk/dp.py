@@ -16,7 +16,7 @@ def shard_range(total, rank, world):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
-def make_buckets(params, bucket_bytes=8 << 20):
+def make_buckets(params, bucket_bytes=2 << 20):
     """Groups parameters in reverse registration order (the order backward produces gradients) into
     buckets of about `bucket_bytes`."""
     buckets, cur, size = [], [], 0
@@ -34,7 +34,7 @@ def make_buckets(params, bucket_bytes=8 << 20):
 class GradAverager:
     """Averages .grad of `params` across the process group through flat fp32 buckets."""
 
-    def __init__(self, params, bucket_bytes=8 << 20, group=None):
+    def __init__(self, params, bucket_bytes=2 << 20, group=None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.buckets = make_buckets(list(params), bucket_bytes)
@@ -86,6 +86,85 @@ class GradAverager:
         self.pack()
         self.all_reduce()
         self.unpack()
+
+    # ---- overlapped mode: buckets are reduced while backward is still running ------------------------------------
+    # begin_backward() before loss.backward(), finish_backward() after it.  A bucket (reverse registration order =
+    # the order backward produces gradients) is launched as soon as every one of its parameters has its gradient
+    # ENQUEUED: on the main stream (autograd's AccumulateGrad, seen through a post-accumulate hook) or on the
+    # weight-gradient side stream (ops.run_on_side_stream hands its (parameter, gradient) pairs over through
+    # ops.set_side_grad_listener).  The pack + NCCL all-reduce of the bucket then run on a communication stream
+    # ordered after both; finish_backward() joins that stream and points .grad at the averaged flat buckets.  All of
+    # it is stream-ordered device work, so it is captured into the trainer's CUDA graph like everything else.
+    def begin_backward(self):
+        from . import ops
+        if self.world == 1:
+            return
+        dev = self.buckets[0][0].device
+        if getattr(self, "_comm", None) is None:
+            self._comm = torch.cuda.Stream(device=dev)
+            self._owner = {}
+            for i, bucket in enumerate(self.buckets):
+                for p in bucket:
+                    self._owner[p] = i
+                    p.register_post_accumulate_grad_hook(self._on_autograd_grad)
+                    p._srk_dp_hooked = True
+        self._ready = [0] * len(self.buckets)
+        self._side = {}
+        self._launched = [False] * len(self.buckets)
+        self._views = [None] * len(self.buckets)
+        self._active = True
+        ops.set_side_grad_listener(self._on_side_grad)
+
+    def _on_autograd_grad(self, p):
+        if getattr(self, "_active", False) and p in self._owner:
+            self._count(p)
+
+    def _on_side_grad(self, p, g):
+        if getattr(self, "_active", False) and p in self._owner:
+            self._side[p] = g
+            self._count(p)
+
+    def _count(self, p):
+        i = self._owner[p]
+        self._ready[i] += 1
+        if self._ready[i] == len(self.buckets[i]) and not self._launched[i]:
+            self._launch(i)
+
+    @torch.no_grad()
+    def _launch(self, i):
+        from . import ops
+        self._launched[i] = True
+        bucket = self.buckets[i]
+        main = torch.cuda.current_stream()
+        self._comm.wait_stream(main)
+        self._comm.wait_stream(ops._side_stream(main.device))
+        grads = [self._side[p] if p in self._side else (p.grad if p.grad is not None else torch.zeros_like(p)) for p in bucket]
+        flat = self._flat(i, grads[0])
+        with torch.cuda.stream(self._comm):
+            views = list(flat.split([g.numel() for g in grads]))
+            torch._foreach_copy_(views, [g.reshape(-1) for g in grads])
+            flat.div_(self.world)
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        for g in grads:
+            g.record_stream(self._comm)
+        self._views[i] = views
+
+    @torch.no_grad()
+    def finish_backward(self):
+        """After loss.backward() (the side stream has been joined): launch what is left, join the communication
+        stream, point .grad at the averaged buckets."""
+        from . import ops
+        if self.world == 1:
+            return
+        ops.set_side_grad_listener(None)
+        self._active = False
+        for i in range(len(self.buckets)):
+            if not self._launched[i]:
+                self._launch(i)
+        torch.cuda.current_stream().wait_stream(self._comm)
+        for bucket, views in zip(self.buckets, self._views):
+            for p, v in zip(bucket, views):
+                p.grad = v.view_as(p)
 
 
 def broadcast_parameters(module, src=0, group=None):

@@ -290,6 +290,13 @@ class _Side:
     streams = {}      # device index -> torch.cuda.Stream
     pending = []      # tensors the side stream still uses (kept alive until the join is enqueued)
     deferred = []     # (parameter, gradient computed on the side stream): assigned to .grad after the join
+    listener = None   # callable(parameter, gradient): told about every side-stream gradient as it is enqueued
+
+
+def set_side_grad_listener(fn):
+    """srk.dp.GradAverager's overlapped mode: learn about side-stream gradients when they are ENQUEUED (they reach
+    .grad only at the join), so that a gradient bucket can be all-reduced while backward is still running."""
+    _Side.listener = fn
 
 
 def _side_stream(device):
@@ -337,6 +344,9 @@ def run_on_side_stream(launch, keep, grads=()):
         launch()
     _Side.pending.append(keep)
     _Side.deferred.extend(grads)
+    if _Side.listener is not None:
+        for prm, g in grads:
+            _Side.listener(prm, g)
     try:   # one callback per launch: after the first one has joined the others find nothing pending
         torch.autograd.Variable._execution_engine.queue_callback(join_side_stream)
     except RuntimeError:
@@ -500,12 +510,18 @@ def conv_wgrad(x, x_img, dz, dz_img, weight, need_bias, perm_tc=False, side=Fals
     PARAMETER (needed to assign its gradient); parameters with hooks stay on the ordinary path."""
     # frozen layer (requires_grad = False on the weight and on the bias): no gradient is wanted - and none must appear
     # in .grad through the side-stream path, where a later optimizer over model.parameters() would pick it up
-    if torch.is_tensor(weight) and weight.is_leaf and not weight.requires_grad and \
+    if isinstance(weight, torch.nn.Parameter) and not weight.requires_grad and \
             (bias is None or not (torch.is_tensor(bias) and bias.requires_grad)):
         return None, None
 
     def _hooked(t):
-        return t is not None and (bool(t._backward_hooks) or bool(getattr(t, "_post_accumulate_grad_hooks", None)))
+        # user hooks would not fire for a gradient that bypasses autograd; the one hook srk.dp.GradAverager registers is
+        # served through set_side_grad_listener instead and does not count
+        if t is None:
+            return False
+        post = getattr(t, "_post_accumulate_grad_hooks", None)
+        n_post = len(post) if post else 0
+        return bool(t._backward_hooks) or n_post > (1 if getattr(t, "_srk_dp_hooked", False) else 0)
     side = (side and cfg.overlap_wgrad and torch.is_tensor(weight) and weight.is_leaf and not _hooked(weight)
             and (not need_bias or (bias is not None and bias.is_leaf and not _hooked(bias))))
     cout, cin, r, s = weight.shape

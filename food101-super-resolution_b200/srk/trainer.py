@@ -24,11 +24,12 @@ from . import optim as srk_optim
 
 class GraphStep:
     def __init__(self, model, criterion, lr=4e-4, betas=(0.5, 0.999), eps=1e-8, optimizer=None, averager=None,
-                 use_graph=True, warmup=3, overlap_wgrad=True, extra_backward=None):
+                 use_graph=True, warmup=3, overlap_wgrad=True, extra_backward=None, overlap_comm=True):
         self.model, self.criterion = model, criterion
         self.optimizer = optimizer if optimizer is not None else srk_optim.Adam(model.parameters(), lr=lr, betas=betas,
                                                                               eps=eps)
         self.averager = averager
+        self.overlap_comm = bool(overlap_comm)
         self.use_graph = bool(use_graph)
         self.warmup = max(int(warmup), 1)
         self.extra_backward = extra_backward       # optional callable(out, hr) -> extra loss term (GAN generator step)
@@ -45,9 +46,14 @@ class GraphStep:
         loss = self.criterion(out, hr_imgs)
         if self.extra_backward is not None:
             loss = loss + self.extra_backward(out, hr_imgs)
-        loss.backward()
-        if self.averager is not None:
-            self.averager.average()
+        if self.averager is not None and self.overlap_comm:
+            self.averager.begin_backward()      # buckets are all-reduced on a communication stream DURING backward
+            loss.backward()
+            self.averager.finish_backward()
+        else:
+            loss.backward()
+            if self.averager is not None:
+                self.averager.average()
         self.optimizer.step()
         if isinstance(self.optimizer, srk_optim.Adam):
             ops.repack_all()   # the weights changed through raw pointers: refresh every cached operand pack in one launch
