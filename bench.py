@@ -102,6 +102,26 @@ class ClockSampler:
         return out
 
 
+def shutdown_distributed(*holders):
+    """Captured CUDA graphs that contain NCCL kernels keep the communicator busy: destroy_process_group() then waits
+    for ever (observed with torch 2.11 / NCCL 2.28).  Drop the graphs first, and never let the teardown outlive the
+    measurement: after 20 s the process exits on its own (the JSON line has been printed by then)."""
+    import gc
+    import threading
+    import torch.distributed as dist
+    for h in holders:
+        if h is not None and hasattr(h, "_graphs"):
+            h._graphs.clear()
+    gc.collect()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    t = threading.Timer(20.0, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
+    dist.destroy_process_group()
+    t.cancel()
+
+
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -474,13 +494,16 @@ def run_srk(args):
 
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            shutdown_distributed(trainer)
         return
     pk = peaks()
     value = world * B / (ms_step * 1e-3)
     roofs = None
+    if world > 1:
+        trainer._graphs.clear()
     if ARCH == "RESNET" and args.dtype == "bf16" and not args.no_rooflines:
         del trainer
+        trainer = None
         torch.cuda.empty_cache()
         roofs = kernel_rooflines(B, dev, pk)
     roof = None
@@ -508,7 +531,7 @@ def run_srk(args):
         line["cpu_baseline"] = cpu_baseline()
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        shutdown_distributed(trainer)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -593,7 +616,7 @@ def run_eval(args):
                 "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        shutdown_distributed()
 
 
 def main():

@@ -100,8 +100,8 @@ class GradAverager:
         if self.world == 1:
             return
         dev = self.buckets[0][0].device
-        if getattr(self, "_comm", None) is None:
-            self._comm = torch.cuda.Stream(device=dev)
+        if getattr(self, "_owner", None) is None:
+            self._comm = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None   # CPU (gloo tests): no streams
             self._owner = {}
             for i, bucket in enumerate(self.buckets):
                 for p in bucket:
@@ -135,19 +135,26 @@ class GradAverager:
         from . import ops
         self._launched[i] = True
         bucket = self.buckets[i]
-        main = torch.cuda.current_stream()
-        self._comm.wait_stream(main)
-        self._comm.wait_stream(ops._side_stream(main.device))
         grads = [self._side[p] if p in self._side else (p.grad if p.grad is not None else torch.zeros_like(p)) for p in bucket]
         flat = self._flat(i, grads[0])
-        with torch.cuda.stream(self._comm):
+
+        def reduce_bucket():
             views = list(flat.split([g.numel() for g in grads]))
             torch._foreach_copy_(views, [g.reshape(-1) for g in grads])
             flat.div_(self.world)
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            return views
+
+        if self._comm is None:
+            self._views[i] = reduce_bucket()
+            return
+        main = torch.cuda.current_stream()
+        self._comm.wait_stream(main)
+        self._comm.wait_stream(ops._side_stream(main.device))
+        with torch.cuda.stream(self._comm):
+            self._views[i] = reduce_bucket()
         for g in grads:
             g.record_stream(self._comm)
-        self._views[i] = views
 
     @torch.no_grad()
     def finish_backward(self):
@@ -161,7 +168,8 @@ class GradAverager:
         for i in range(len(self.buckets)):
             if not self._launched[i]:
                 self._launch(i)
-        torch.cuda.current_stream().wait_stream(self._comm)
+        if self._comm is not None:
+            torch.cuda.current_stream().wait_stream(self._comm)
         for bucket, views in zip(self.buckets, self._views):
             for p, v in zip(bucket, views):
                 p.grad = v.view_as(p)

@@ -216,6 +216,8 @@ def train(config=None):
 
         if world > 1:
             dist.barrier()
+            if not is_gan:
+                trainer._graphs.clear()     # captured NCCL kernels would keep the communicator busy at teardown
         if os.path.exists(best_path):
             model.load_state_dict(torch.load(best_path, map_location=device))
         test_metrics = ev.evaluate(model, test_loader, device, rank, world, metrics_calc.compute)

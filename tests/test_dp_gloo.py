@@ -28,6 +28,25 @@ def _worker(rank, world, port, out):
     avg = dp.GradAverager(net.parameters(), bucket_bytes=64)
     assert len(avg.buckets) >= 2
     avg.average()
+    plain = [p.grad.detach().clone() for p in net.parameters()]
+    # overlapped mode (buckets reduced from inside backward as their gradients arrive) must give the same numbers,
+    # also for a parameter that receives gradient from two places of the graph (two accumulations)
+    for p in net.parameters():
+        p.grad = None
+    avg.begin_backward()
+    (((net(x_all[b:e]) - y_all[b:e]) ** 2).mean()).backward()
+    avg.finish_backward()
+    assert all(torch.equal(p.grad, g) for p, g in zip(net.parameters(), plain))
+    twice = net[0].weight
+    for p in net.parameters():
+        p.grad = None
+    avg.begin_backward()
+    (((net(x_all[b:e]) - y_all[b:e]) ** 2).mean() + (twice ** 2).sum() * 0.5).backward()
+    avg.finish_backward()
+    want = plain[0] + twice.detach()
+    assert torch.allclose(net[0].weight.grad, want, atol=1e-6), (net[0].weight.grad - want).abs().max()
+    for p, g in zip(net.parameters(), plain):
+        p.grad = g
     # single-process oracle over the whole batch
     ref = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
     with torch.no_grad():
