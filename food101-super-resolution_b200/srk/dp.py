@@ -5,6 +5,8 @@ torch.distributed backend works - the gloo backend is what the CPU tests use).
 The reference has no distributed path at all; semantics follow SURVEY 8e: losses are
 batch means, so equal shards + gradient averaging reproduce the single-process gradient for
 AttentionSR / SRCNN exactly, and ResNet-SR BatchNorm keeps per-rank batch statistics (DDP semantics)."""
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -108,7 +110,7 @@ class GradAverager:
                     self._owner[p] = i
                     p.register_post_accumulate_grad_hook(self._on_autograd_grad)
                     p._srk_dp_hooked = True
-        self._ready = [0] * len(self.buckets)
+        self._counted = set()
         self._side = {}
         self._launched = [False] * len(self.buckets)
         self._views = [None] * len(self.buckets)
@@ -116,7 +118,9 @@ class GradAverager:
         ops.set_side_grad_listener(self._on_side_grad)
 
     def _on_autograd_grad(self, p):
-        if getattr(self, "_active", False) and p in self._owner:
+        # the hook also fires when the backward node handed autograd an undefined gradient (what the side-stream path
+        # returns for its parameters): those are announced by the listener, not here
+        if getattr(self, "_active", False) and p in self._owner and p.grad is not None and p not in self._side:
             self._count(p)
 
     def _on_side_grad(self, p, g):
@@ -126,8 +130,14 @@ class GradAverager:
 
     def _count(self, p):
         i = self._owner[p]
-        self._ready[i] += 1
-        if self._ready[i] == len(self.buckets[i]) and not self._launched[i]:
+        if self._launched[i]:
+            # a gradient contribution that arrives after its bucket went out would be lost silently
+            raise RuntimeError("srk.dp: a parameter %s received gradient after its bucket was all-reduced (parameter "
+                               "used in two places of the graph?); use GraphStep(overlap_comm=False)"
+                               % (tuple(p.shape),))
+        self._counted.add(p)
+        # launch on availability, not on a count: every parameter of the bucket has its gradient enqueued
+        if all((q in self._side) or (q.grad is not None) for q in self.buckets[i]):
             self._launch(i)
 
     @torch.no_grad()
