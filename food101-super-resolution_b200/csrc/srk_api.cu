@@ -144,12 +144,12 @@ extern "C" int srk_conv_fprop(const srk_tensor* x, const srk_tensor* y, const vo
 // Data gradient of a 3x3 64 -> 64 conv with the BatchNorm-backward reduction of the layer BELOW fused into the
 // epilogue: dx = dgrad(dz), and over interior pixels  sum_g[c] += sum g,  sum_gz[c] += sum g * z,
 // dalpha += sum_{b<0} g * b, with z the saved pre-BN activation, b = BN(z) and g = dx masked by the PReLU that sits
-// between that BN and this conv (alpha != NULL) or dx itself.  Returns 2 (and launches nothing) when the shape is
+// between that BN and this conv (alpha != NULL) or dx itself; with a residual, dx = dgrad(dz) + residual.  Returns 2 (and launches nothing) when the shape is
 // outside the fused kernel: the caller then runs srk_conv_fprop + srk_bn_bwd_reduce.
 extern "C" int srk_conv_dgrad_bnred(const srk_tensor* dz, const srk_tensor* dx, const void* w_packed_dgrad,
                                     const srk_tensor* z, const float* mean, const float* invstd, const float* gamma,
                                     const float* beta, const float* alpha, float* sum_g, float* sum_gz, float* dalpha,
-                                    void* reduce_ws, void* stream) {
+                                    const srk_tensor* residual, void* reduce_ws, void* stream) {
   SRK_REQUIRE(tensor_ok(dz) && tensor_ok(dx) && tensor_ok(z) && w_packed_dgrad, "srk_conv_dgrad_bnred: bad tensors");
   SRK_REQUIRE(reduce_ws != nullptr, "srk_conv_dgrad_bnred: reduce_ws is required");
   SRK_REQUIRE(mean && invstd && gamma && beta && sum_g && sum_gz, "srk_conv_dgrad_bnred: null statistics");
@@ -157,13 +157,16 @@ extern "C" int srk_conv_dgrad_bnred(const srk_tensor* dz, const srk_tensor* dx, 
   if (!(dz->layout == SRK_LAYOUT_ACT && dx->layout == SRK_LAYOUT_ACT && dz->dtype == SRK_BF16 && dx->dtype == SRK_BF16 &&
         dz->c == 64 && dx->c == 64 && same_geometry(dz, dx)))
     return 2;
+  if (residual && !(tensor_ok(residual) && same_geometry(residual, dx) && residual->layout == SRK_LAYOUT_ACT &&
+                    residual->dtype == SRK_BF16))
+    return 2;
   BnRedArgs br = {z, mean, invstd, gamma, beta, alpha, sum_g, sum_gz, dalpha};
-  if (tc_fold() == 4) {
+  if (tc_fold() == 4 && residual == nullptr) {
     const int rs = conv_fprop_strip_launch(dz, dx, w_packed_dgrad, 64, nullptr, SRK_ACT_NONE, nullptr, nullptr, 0, nullptr,
                                            nullptr, (cudaStream_t)stream, &br, reduce_ws, nullptr);
     if (rs >= 0) return rs;
   }
-  const int rc = conv_fprop_fold_launch(dz, dx, w_packed_dgrad, 64, nullptr, SRK_ACT_NONE, nullptr, nullptr, 0, nullptr,
+  const int rc = conv_fprop_fold_launch(dz, dx, w_packed_dgrad, 64, nullptr, SRK_ACT_NONE, nullptr, residual, 0, nullptr,
                                         nullptr, nullptr, 0, (cudaStream_t)stream, &br, reduce_ws, nullptr);
   return rc < 0 ? 2 : rc;
 }

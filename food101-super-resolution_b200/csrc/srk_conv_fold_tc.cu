@@ -80,6 +80,8 @@ struct Params {
   // the residual path is Z, the saved pre-BN activation of the BN layer this gradient flows into; instead of being
   // added it gives  stats_sum[c] += sum g,  stats_sumsq[c] += sum g * z,  bn_dalpha += sum_{b<0} g * b  with
   // b = z * sc + sh the BN output and g the PReLU-masked gradient (bn_mask = 1) or the gradient itself.
+  // bn_red = 2: the dgrad also carries a true residual (the skip gradient, added first: the sums are taken of the
+  // total) and Z arrives through its own pair of staging tiles (tmZ) - srk_conv_dgrad_bnred with a residual.
   int bn_red, bn_mask;
   const float* bn_mean; const float* bn_invstd; const float* bn_gamma; const float* bn_beta;
   float* bn_dalpha;
@@ -130,7 +132,7 @@ template <bool kFold, bool kFast, bool kStats, int kAct, bool kPair = false, int
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                        const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
-                       const Params p) {
+                       const __grid_constant__ CUtensorMap tmZ, const Params p) {
   static_assert(!(kPair && kFold), "the CTA-pair variant is per-tap");
   static_assert(kCPT == 16 || (kCPT == 32 && kPair && !kFast && !kStats), "N = 128 passes run on CTA pairs");
   constexpr int CPT = kCPT;
@@ -148,16 +150,19 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const int dbg = kFast ? 0 : p.dbg;
   long long* const trace = kFast ? nullptr : p.trace;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // dynamic smem: [weights 72 KB][A ring][2 output tiles][exchange][bias][barriers]
+  // dynamic smem: [weights 72 KB][A ring][2 output tiles][2 Z tiles iff bn_red == 2][exchange][bias][barriers]
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t wsm = smem_base;
   const uint32_t asm0 = smem_base + W_BYTES;
   const uint32_t osm = asm0 + p.stages * p.stage_bytes;
   uint8_t* optr = smem_al + W_BYTES + p.stages * p.stage_bytes;
-  float* xch = reinterpret_cast<float*>(optr + 2 * O_TILE_BYTES);
-  float* bias_s = reinterpret_cast<float*>(optr + 2 * O_TILE_BYTES + XCH_BYTES);
-  Barriers* bars = reinterpret_cast<Barriers*>(optr + 2 * O_TILE_BYTES + XCH_BYTES + BIAS_BYTES);
+  const bool two_in = kStats && p.bn_red == 2;   // residual tile AND Z tile per output tile
+  const int z_bytes = two_in ? 2 * O_TILE_BYTES : 0;
+  const uint32_t zsm = osm + 2 * O_TILE_BYTES;
+  float* xch = reinterpret_cast<float*>(optr + 2 * O_TILE_BYTES + z_bytes);
+  float* bias_s = reinterpret_cast<float*>(optr + 2 * O_TILE_BYTES + z_bytes + XCH_BYTES);
+  Barriers* bars = reinterpret_cast<Barriers*>(optr + 2 * O_TILE_BYTES + z_bytes + XCH_BYTES + BIAS_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
@@ -308,10 +313,12 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const int my_tiles = first < p.num_tiles ? (p.num_tiles - first + gridDim.x - 1) / gridDim.x : 0;
       if (p.has_residual && elect_one()) {
         prefetch_tmap(&tmR);
+        if (two_in) prefetch_tmap(&tmZ);
         for (int it = 0; it < 2 && it < my_tiles; ++it) {
           const uint32_t rb = smem_u32(&bars->rfull[it]);
-          mbar_arrive_expect_tx(rb, TMO * NT * 2);
+          mbar_arrive_expect_tx(rb, (two_in ? 2 : 1) * TMO * NT * 2);
           tma_load_2d(osm + it * O_TILE_BYTES, &tmR, rb, p.cout_off, (blockIdx.x + it * gridDim.x) * TMO);
+          if (two_in) tma_load_2d(zsm + it * O_TILE_BYTES, &tmZ, rb, p.cout_off, (blockIdx.x + it * gridDim.x) * TMO);
         }
       }
       __syncwarp();
@@ -325,9 +332,11 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           tma_store_wait_read0();
           if (trace && blockIdx.x == 0 && it < 32) trace[13 * 32 + it] = clock64();
           if (p.has_residual && it + 2 < my_tiles) {
+            // (the Z tile of this buffer is free as well: every epilogue warp read it before arriving on oready)
             const uint32_t rb = smem_u32(&bars->rfull[b]);
-            mbar_arrive_expect_tx(rb, TMO * NT * 2);
+            mbar_arrive_expect_tx(rb, (two_in ? 2 : 1) * TMO * NT * 2);
             tma_load_2d(osm + b * O_TILE_BYTES, &tmR, rb, p.cout_off, (blockIdx.x + (it + 2) * gridDim.x) * TMO);
+            if (two_in) tma_load_2d(zsm + b * O_TILE_BYTES, &tmZ, rb, p.cout_off, (blockIdx.x + (it + 2) * gridDim.x) * TMO);
           }
           mbar_arrive(smem_u32(&bars->ofree[b]));
         }
@@ -528,19 +537,29 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                               pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
         continue;
       }
-      const bool bn_red = kStats && p.bn_red;
+      const int bn_red = kStats ? p.bn_red : 0;
       if (stats_sum && !bn_red && interior) {
 #pragma unroll
         for (int j = 0; j < CPT; ++j) { s1[j] += f[j]; s2[j] = fmaf(f[j], f[j], s2[j]); }
       }
       if (ok) ok = mbar_wait(smem_u32(&bars->ofree[acc]), ((it >> 1) & 1) ^ 1, p.err, 7);
+      if (p.has_residual && ok) ok = mbar_wait(smem_u32(&bars->rfull[acc]), (it >> 1) & 1, p.err, 8);
+      if (p.has_residual && bn_red != 1 && has_row) {
+#pragma unroll
+        for (int j = 0; j < CPT / 8; ++j) {
+          const uint4 rr = *reinterpret_cast<const uint4*>(orow + (((cq * (CPT / 8) + j) ^ ((row - ROW0) & 7)) << 4));
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) { float2 u = __bfloat1622float2(h[t]); f[8 * j + 2 * t] += u.x; f[8 * j + 2 * t + 1] += u.y; }
+        }
+      }
       if (bn_red) {
-        // the "residual" tile is Z: reduce, do not add
-        if (ok) ok = mbar_wait(smem_u32(&bars->rfull[acc]), (it >> 1) & 1, p.err, 8);
+        // bn_red = 1: the "residual" tile is Z (reduce, do not add); 2: Z has its own tile, the residual is already in f
         if (interior) {
+          const uint8_t* zrow = bn_red == 2 ? orow + 2 * O_TILE_BYTES : orow;
 #pragma unroll
           for (int j = 0; j < CPT / 8; ++j) {
-            const uint4 rr = *reinterpret_cast<const uint4*>(orow + (((cq * (CPT / 8) + j) ^ ((row - ROW0) & 7)) << 4));
+            const uint4 rr = *reinterpret_cast<const uint4*>(zrow + (((cq * (CPT / 8) + j) ^ ((row - ROW0) & 7)) << 4));
             const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rr);
             const float4 sc0 = reinterpret_cast<const float4*>(bias_s + 128 + c0 + 8 * j)[0];
             const float4 sc1 = reinterpret_cast<const float4*>(bias_s + 128 + c0 + 8 * j)[1];
@@ -564,17 +583,6 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 s2[k] = fmaf(gd, zz[e], s2[k]);
               }
             }
-          }
-        }
-      } else if (p.has_residual) {
-        if (ok) ok = mbar_wait(smem_u32(&bars->rfull[acc]), (it >> 1) & 1, p.err, 8);
-        if (has_row) {
-#pragma unroll
-          for (int j = 0; j < CPT / 8; ++j) {
-            const uint4 rr = *reinterpret_cast<const uint4*>(orow + (((cq * (CPT / 8) + j) ^ ((row - ROW0) & 7)) << 4));
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rr);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) { float2 u = __bfloat1622float2(h[t]); f[8 * j + 2 * t] += u.x; f[8 * j + 2 * t + 1] += u.y; }
           }
         }
       }
@@ -676,7 +684,7 @@ static void set_smem_all(int smem_max) {
 
 template <bool kFold, bool kFast, bool kStats, int kAct, bool kPair, int kCPT = 16>
 static cudaError_t launch_one(int grid, int smem_bytes, cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmW,
-                              const CUtensorMap& tmY, const CUtensorMap& tmRes, const Params& p) {
+                              const CUtensorMap& tmY, const CUtensorMap& tmRes, const CUtensorMap& tmZ, const Params& p) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
   cudaLaunchAttribute attr[2];
@@ -685,18 +693,18 @@ static cudaError_t launch_one(int grid, int smem_bytes, cudaStream_t st, const C
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = (!kPair && pdl_enabled(PDL_CONV)) ? 2 : 1;
-  return cudaLaunchKernelEx(&cfg, conv3x3_fold_tc_kernel<kFold, kFast, kStats, kAct, kPair, kCPT>, tmA, tmW, tmY, tmRes, p);
+  return cudaLaunchKernelEx(&cfg, conv3x3_fold_tc_kernel<kFold, kFast, kStats, kAct, kPair, kCPT>, tmA, tmW, tmY, tmRes, tmZ, p);
 }
 
 template <bool kFold, bool kPair>
 static cudaError_t launch_pass(bool fast, bool stats, int act, int grid, int smem_bytes, cudaStream_t st,
                                const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmY,
-                               const CUtensorMap& tmRes, const Params& p) {
-  if (fast && stats) return launch_one<kFold, true, true, SRK_ACT_NONE, kPair>(grid, smem_bytes, st, tmA, tmW, tmY, tmRes, p);
-  if (fast && act == SRK_ACT_NONE) return launch_one<kFold, true, false, SRK_ACT_NONE, kPair>(grid, smem_bytes, st, tmA, tmW, tmY, tmRes, p);
-  if (fast && act == SRK_ACT_RELU) return launch_one<kFold, true, false, SRK_ACT_RELU, kPair>(grid, smem_bytes, st, tmA, tmW, tmY, tmRes, p);
-  if (fast && act == SRK_ACT_PRELU) return launch_one<kFold, true, false, SRK_ACT_PRELU, kPair>(grid, smem_bytes, st, tmA, tmW, tmY, tmRes, p);
-  return launch_one<kFold, false, false, ACT_RUNTIME, kPair>(grid, smem_bytes, st, tmA, tmW, tmY, tmRes, p);
+                               const CUtensorMap& tmRes, const CUtensorMap& tmZ, const Params& p) {
+  if (fast && stats) return launch_one<kFold, true, true, SRK_ACT_NONE, kPair>(grid, smem_bytes, st, tmA, tmW, tmY, tmRes, tmZ, p);
+  if (fast && act == SRK_ACT_NONE) return launch_one<kFold, true, false, SRK_ACT_NONE, kPair>(grid, smem_bytes, st, tmA, tmW, tmY, tmRes, tmZ, p);
+  if (fast && act == SRK_ACT_RELU) return launch_one<kFold, true, false, SRK_ACT_RELU, kPair>(grid, smem_bytes, st, tmA, tmW, tmY, tmRes, tmZ, p);
+  if (fast && act == SRK_ACT_PRELU) return launch_one<kFold, true, false, SRK_ACT_PRELU, kPair>(grid, smem_bytes, st, tmA, tmW, tmY, tmRes, tmZ, p);
+  return launch_one<kFold, false, false, ACT_RUNTIME, kPair>(grid, smem_bytes, st, tmA, tmW, tmY, tmRes, tmZ, p);
 }
 
 }  // namespace fold
@@ -732,7 +740,8 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
     set_smem<false, false, false, ACT_RUNTIME, true, 32>(smem_max);
   }
   const int slab_rows = ((TM + 2 * Wp + (folded ? 0 : 2)) + SLAB_BOX_ROWS - 1) / SLAB_BOX_ROWS * SLAB_BOX_ROWS;
-  const int fixed = 1024 + W_BYTES + 2 * O_TILE_BYTES + XCH_BYTES + BIAS_BYTES + (int)sizeof(Barriers);
+  const int fixed = 1024 + W_BYTES + 2 * O_TILE_BYTES + ((br && residual) ? 2 * O_TILE_BYTES : 0) + XCH_BYTES + BIAS_BYTES +
+                    (int)sizeof(Barriers);
   const int stage_bytes = slab_rows * KC * 2;
   int stages = (smem_max - fixed) / stage_bytes;
   if (stages < 2) return -1;
@@ -741,7 +750,7 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
 
   CUtensorMap tmA;
   if (make_tmap_2d_bf16(&tmA, x->data, (uint64_t)P, (uint64_t)cin, (uint64_t)cin, SLAB_BOX_ROWS, KC, 128)) return 1;
-  CUtensorMap tmY = tmA, tmR = tmA;  // output store / residual load maps (plain outputs only)
+  CUtensorMap tmY = tmA, tmR = tmA, tmZ = tmA;  // output store / residual load / Z load maps (plain outputs only)
   if (shuffle == 0) {
     if (make_tmap_2d_bf16(&tmY, y->data, (uint64_t)P, (uint64_t)cout, (uint64_t)cout, TMO, NT, 128)) return 1;
     tmR = tmY;
@@ -768,19 +777,20 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
   p.bn_red = 0; p.bn_mask = 0;
   p.bn_mean = p.bn_invstd = p.bn_gamma = p.bn_beta = nullptr; p.bn_dalpha = nullptr;
   if (br) {
-    SRK_REQUIRE(cin == KC && cout == NT && shuffle == 0 && act == SRK_ACT_NONE && residual == nullptr &&
-                    stats_sum == nullptr && variant == 0,
+    SRK_REQUIRE(cin == KC && cout == NT && shuffle == 0 && act == SRK_ACT_NONE && stats_sum == nullptr && variant == 0,
                 "conv_fold: the fused BN-backward reduction covers the plain 64 -> 64 per-tap dgrad");
     SRK_REQUIRE(same_geometry(br->z, y) && br->z->dtype == SRK_BF16 && br->z->layout == SRK_LAYOUT_ACT,
                 "conv_fold: Z must match the dgrad output geometry (bf16 ACT)");
-    if (make_tmap_2d_bf16(&tmR, br->z->data, (uint64_t)P, (uint64_t)cout, (uint64_t)cout, TMO, NT, 128)) return 1;
+    // without a residual Z travels in the residual slot; with one it gets its own map and staging tiles
+    if (make_tmap_2d_bf16(residual ? &tmZ : &tmR, br->z->data, (uint64_t)P, (uint64_t)cout, (uint64_t)cout, TMO, NT, 128))
+      return 1;
     p.stats_sum = stats_sum = br->sum_g; p.stats_sumsq = stats_sumsq = br->sum_gz;
-    p.bn_red = 1; p.bn_mask = br->alpha != nullptr; p.alpha = br->alpha;
+    p.bn_red = residual ? 2 : 1; p.bn_mask = br->alpha != nullptr; p.alpha = br->alpha;
     p.bn_mean = br->mean; p.bn_invstd = br->invstd; p.bn_gamma = br->gamma; p.bn_beta = br->beta;
     p.bn_dalpha = br->dalpha;
   }
   const int nchunks = (cout + pass_n - 1) / pass_n, kchunks = (cin + KC - 1) / KC;
-  SRK_REQUIRE(stats_sum == nullptr || (kchunks == 1 && shuffle == 0 && act == SRK_ACT_NONE && residual == nullptr),
+  SRK_REQUIRE(stats_sum == nullptr || (kchunks == 1 && shuffle == 0 && act == SRK_ACT_NONE && (residual == nullptr || br)),
               "conv_fold: fused BN statistics need a plain Cin == 64 conv");
   int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
   if (pair) grid = (grid + 1) / 2 * 2 <= kNumSMs ? (grid + 1) / 2 * 2 : kNumSMs / 2 * 2;   // whole pairs
@@ -826,10 +836,10 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
       SRK_REQUIRE(fast || stats_sum == nullptr, "conv_fold: fused BN statistics need the single-chunk 64 -> 64 pass");
       cudaError_t le;
       if (variant == 3)
-        le = launch_one<false, false, false, ACT_RUNTIME, true, 32>(grid, smem_bytes, st, tmA, tmW, tmY, tmRes, p);
-      else if (folded) le = launch_pass<true, false>(fast, stats_sum != nullptr, p.act, grid, smem_bytes, st, tmA, tmW, tmY, tmRes, p);
-      else if (pair) le = launch_pass<false, true>(fast, stats_sum != nullptr, p.act, grid, smem_bytes, st, tmA, tmW, tmY, tmRes, p);
-      else le = launch_pass<false, false>(fast, stats_sum != nullptr, p.act, grid, smem_bytes, st, tmA, tmW, tmY, tmRes, p);
+        le = launch_one<false, false, false, ACT_RUNTIME, true, 32>(grid, smem_bytes, st, tmA, tmW, tmY, tmRes, tmZ, p);
+      else if (folded) le = launch_pass<true, false>(fast, stats_sum != nullptr, p.act, grid, smem_bytes, st, tmA, tmW, tmY, tmRes, tmZ, p);
+      else if (pair) le = launch_pass<false, true>(fast, stats_sum != nullptr, p.act, grid, smem_bytes, st, tmA, tmW, tmY, tmRes, tmZ, p);
+      else le = launch_pass<false, false>(fast, stats_sum != nullptr, p.act, grid, smem_bytes, st, tmA, tmW, tmY, tmRes, tmZ, p);
       SRK_REQUIRE(le == cudaSuccess, "conv3x3_fold_tc: launch failed: %s", cudaGetErrorString(le));
       SRK_CUDA_LAUNCH_CHECK("conv3x3_fold_tc");
     }

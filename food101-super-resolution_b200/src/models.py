@@ -116,7 +116,8 @@ class ResidualBlock(nn.Module):
         if use_se:
             self.se = SEBlock(channels)
 
-    def _forward_act(self, x):
+    def _forward_act(self, x, link_in=None, link_out=None):
+        """link_in / link_out (fn.BnLink): set by the owner of a sequential chain of blocks (ResNetSR.forward)."""
         buf1, eps1, mom1 = _bn_args(self.bn1)
         buf2, eps2, mom2 = _bn_args(self.bn2)
         if self.training:
@@ -130,7 +131,7 @@ class ResidualBlock(nn.Module):
             return fn.ResBlockBN.apply(
                 x, self.conv1.weight, self.conv1.bias, self.bn1.weight, self.bn1.bias, self.prelu.weight,
                 self.conv2.weight, self.conv2.bias, self.bn2.weight, self.bn2.bias,
-                buf1, buf2, self.training, eps1, mom1, eps2, mom2)
+                buf1, buf2, self.training, eps1, mom1, eps2, mom2, link_in, link_out)
         a = fn.ConvBN.apply(x, self.conv1.weight, self.conv1.bias, self.bn1.weight, self.bn1.bias,
                             self.prelu.weight, None, *buf1, self.training, eps1, mom1)
         r = fn.ConvBN.apply(a, self.conv2.weight, self.conv2.bias, self.bn2.weight, self.bn2.bias,
@@ -245,8 +246,14 @@ class ResNetSR(nn.Module):
         ops.require_cuda(x, "ResNetSR input")
         initial = fn.conv_act(x, self.input_conv, act=L.ACT_PRELU, alpha=self.prelu.weight, x_img=True)
         r = initial
-        for blk in self.res_blocks:
-            r = blk._forward_act(r)
+        # every block output has exactly one consumer (the next block): the bn2 backward reduction of block k rides in
+        # the last dgrad of block k+1 (fn.BnLink)
+        link = None
+        chain = self.training and torch.is_grad_enabled()
+        for i, blk in enumerate(self.res_blocks):
+            nxt = fn.BnLink() if (chain and i + 1 < len(self.res_blocks)) else None
+            r = blk._forward_act(r, link, nxt)
+            link = nxt
         buf, eps, mom = _bn_args(self.bn_mid)
         if self.training:
             _drop_fold(self.bn_mid)

@@ -54,7 +54,7 @@ SIGNATURES = {
     "srk_bn_bwd_reduce": (c_int, [_T, _T, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "srk_bn_bwd_apply": (c_int, [_T, _T, _P, _P, _P, _P, _P, _P, _P, c_int, _T, _P]),
     "srk_bn_bwd_apply_raw": (c_int, [_T, _T, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _T, _P]),
-    "srk_conv_dgrad_bnred": (c_int, [_T, _T, _P, _T, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "srk_conv_dgrad_bnred": (c_int, [_T, _T, _P, _T, _P, _P, _P, _P, _P, _P, _P, _P, _T, _P, _P]),
     "srk_se_pool": (c_int, [_T, _P, _P, _P]),
     "srk_se_fc": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P]),
     "srk_se_apply": (c_int, [_T, _T, _P, c_float, _T, _P]),

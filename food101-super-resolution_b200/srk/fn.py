@@ -141,15 +141,40 @@ def _conv_bn_forward(x, w, b, bn_params, bn_buffers, training, eps, momentum, al
     return y, out, stats
 
 
+class BnLink:
+    """What a residual block tells the block ABOVE it about its bn2, so that the dgrad which produces this block's
+    incoming gradient (dx = dgrad(dy1) + dout of the block above, models.py:55-60) can take bn2's backward reduction
+    in its epilogue (ops.conv_dgrad_bnred with a residual) - one pass over (dout, y2) less per block.  Only the owner
+    of the chain (ResNetSR.forward) creates links: it knows that the block's output has exactly one consumer.
+    forward fills z / stats / gamma / beta; the consumer's backward fills red (+ the identity of the gradient tensor
+    the sums belong to); the producer's backward takes them if it is handed that very tensor."""
+    __slots__ = ("z", "stats", "gamma", "beta", "red", "grad_ptr", "grad_version")
+
+    def __init__(self):
+        self.z = self.stats = self.gamma = self.beta = self.red = None
+        self.grad_ptr = self.grad_version = None
+
+    def offer(self, red, grad):
+        self.red, self.grad_ptr, self.grad_version = red, grad.data_ptr(), grad._version
+
+    def take(self, grad):
+        red, self.red = self.red, None
+        self.z = self.stats = self.gamma = self.beta = None
+        if red is not None and grad.data_ptr() == self.grad_ptr and grad._version == self.grad_version:
+            return red
+        return None
+
+
 def _conv_bn_backward(dout, x, y, stats, w, bias, gamma, beta, alpha, batch_stats, dgrad_residual, need_dx,
                       pre=None, below=None):
     """Backward of out = [PReLU](BN(conv(x))).  pre: raw BN-backward sums of dout when the dgrad that produced dout
     already reduced them (ops.conv_dgrad_bnred).  below = (z, stats, gamma, beta, alpha) of the BatchNorm layer that
-    produced x: its backward reduction is then fused into this conv's dgrad and returned as the last item."""
+    produced x: its backward reduction is then fused into this conv's dgrad (after the skip gradient dgrad_residual, if
+    any, has been added) and returned as the last item."""
     dy, dgamma, dbeta, dalpha = ops.bn_backward(dout, y, stats, gamma, beta, alpha, batch_stats, pre=pre)
     dx = red = None
     if need_dx:
-        fused = ops.conv_dgrad_bnred(dy, w, *below) if (below is not None and dgrad_residual is None) else None
+        fused = ops.conv_dgrad_bnred(dy, w, *below, residual=dgrad_residual) if below is not None else None
         if fused is not None:
             dx, red = fused
         else:
@@ -186,13 +211,19 @@ class ResBlockBN(torch.autograd.Function):
     """out = x + BN2(conv2(PReLU(BN1(conv1(x)))))   (ResidualBlock.forward, models.py:55-60, use_se=False)"""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, g1, be1, alpha, w2, b2, g2, be2, buf1, buf2, training, eps1, mom1, eps2, mom2):
+    def forward(ctx, x, w1, b1, g1, be1, alpha, w2, b2, g2, be2, buf1, buf2, training, eps1, mom1, eps2, mom2,
+                link_in=None, link_out=None):
+        """link_in: BnLink of the block that produced x (its bn2 reduction rides in this block's last dgrad);
+        link_out: BnLink this block fills in for the block that consumes its output."""
         ops.require_cuda(x, "residual block")
         x = x.contiguous()
         y1, a1, st1 = _conv_bn_forward(x, w1, b1, (g1, be1), buf1, training, eps1, mom1, alpha, None)
         y2, out, st2 = _conv_bn_forward(a1, w2, b2, (g2, be2), buf2, training, eps2, mom2, None, x)
         ctx.save_for_backward(x, y1, st1, a1, y2, st2, w1, g1, be1, alpha, w2, g2, be2, b1, b2)
         ctx.cfg = (b1 is not None, b2 is not None, training or buf1[0] is None)
+        ctx.link_in, ctx.link_out = link_in, link_out
+        if link_out is not None:
+            link_out.z, link_out.stats, link_out.gamma, link_out.beta = y2, st2, g2, be2
         return out
 
     @staticmethod
@@ -200,15 +231,22 @@ class ResBlockBN(torch.autograd.Function):
         x, y1, st1, a1, y2, st2, w1, g1, be1, alpha, w2, g2, be2, b1, b2 = ctx.saved_tensors
         hb1, hb2, batch_stats = ctx.cfg
         dout = dout.contiguous()
+        # bn2's reduction was taken by the dgrad of the block above if that dgrad produced this very gradient tensor
+        pre2 = ctx.link_out.take(dout) if ctx.link_out is not None else None
         # conv2's dgrad produces da1, the gradient BN1 (+ PReLU) receives: BN1's backward reduction rides in its epilogue
         da1, dw2, db2, dg2, dbe2, _, red1 = _conv_bn_backward(dout, a1, y2, st2, w2, b2, g2, be2, None,
-                                                              batch_stats, None, True,
+                                                              batch_stats, None, True, pre=pre2,
                                                               below=(y1, st1, g1, be1, alpha))
-        # the skip connection's gradient rides in the dgrad epilogue: dx = dgrad(dy1) + dout
-        dx, dw1, db1, dg1, dbe1, dalpha, _ = _conv_bn_backward(da1, x, y1, st1, w1, b1, g1, be1, alpha,
-                                                               batch_stats, dout, True, pre=red1)
+        # the skip connection's gradient rides in the dgrad epilogue: dx = dgrad(dy1) + dout - and so does the bn2
+        # reduction of the block below, which dx is the incoming gradient of
+        lk = ctx.link_in
+        below = (lk.z, lk.stats, lk.gamma, lk.beta, None) if (lk is not None and lk.z is not None) else None
+        dx, dw1, db1, dg1, dbe1, dalpha, red_below = _conv_bn_backward(da1, x, y1, st1, w1, b1, g1, be1, alpha,
+                                                                       batch_stats, dout, True, pre=red1, below=below)
+        if red_below is not None:
+            lk.offer(red_below, dx)
         return (dx, dw1, db1, dg1, dbe1, dalpha, dw2, db2, dg2, dbe2,
-                None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None)
 
 
 class AttnBlock(torch.autograd.Function):

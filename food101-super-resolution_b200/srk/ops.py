@@ -475,15 +475,18 @@ def conv_dgrad(dz, dz_img, weight, residual, out_dtype, perm_tc=False):
     return dx
 
 
-def conv_dgrad_bnred(dz, weight, z, stats, gamma, beta, alpha):
+def conv_dgrad_bnred(dz, weight, z, stats, gamma, beta, alpha, residual=None):
     """dx = dgrad(dz) with the backward reduction of the BatchNorm layer below fused into the epilogue
     (srk_conv_dgrad_bnred).  z / stats / gamma / beta: that BN's saved input, (mean, invstd) and affine parameters;
-    alpha: slope of the PReLU between the BN and this conv, or None.
+    alpha: slope of the PReLU between the BN and this conv, or None.  residual: added to the dgrad before the
+    reduction (dx = dgrad(dz) + residual: the whole gradient of a residual block's input, reduced against the bn2 of
+    the block below).
     -> (dx, red) with red = [sum g | sum g*z | dalpha] (fp32, 2C+1), or None when the fused kernel does not cover
     the shape (the caller then runs conv_dgrad and the stand-alone reduction)."""
     cout, cin, r, s = weight.shape
     if not (cfg.fuse_bn_reduce and cfg.conv_impl != "simt" and r == 3 and s == 3 and cin == 64 and cout == 64
-            and dz.dtype == torch.bfloat16 and z.dtype == torch.bfloat16 and dz.shape == z.shape):
+            and dz.dtype == torch.bfloat16 and z.dtype == torch.bfloat16 and dz.shape == z.shape
+            and (residual is None or (residual.dtype == torch.bfloat16 and residual.shape == dz.shape))):
         return None
     n, c, h, w = geometry(dz, False)
     pk = packed_weight(weight, L.PACK_DGRAD_TC, 0)
@@ -493,6 +496,7 @@ def conv_dgrad_bnred(dz, weight, z, stats, gamma, beta, alpha):
                                      stats[1].data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(alpha),
                                      red[:cin].data_ptr(), red[cin:2 * cin].data_ptr(),
                                      red[2 * cin:].data_ptr() if alpha is not None else None,
+                                     act_desc(residual) if residual is not None else None,
                                      reduce_ws(dz.device), stream_ptr())
     if rc == 2:
         return None

@@ -109,12 +109,14 @@ int64_t srk_conv_wgrad_workspace_bytes(const srk_tensor* x, const srk_tensor* dy
  * REDUCTION of the BN layer below it fused into the epilogue (native_batch_norm_backward's sums of
  * ResidualBlock.backward, models.py:56-57): z = that BN's saved input, alpha = the PReLU slope between the BN and
  * this conv (models.py:57) or NULL.  Writes sum_g[64], sum_gz[64] (raw sums; srk_bn_bwd_apply_raw turns them into
- * dgamma / the dy constants) and dalpha[1].  Returns 0 ok, 1 error, 2 = shape outside the fused kernel (nothing
- * launched; run srk_conv_fprop + srk_bn_bwd_reduce instead). */
+ * dgamma / the dy constants) and dalpha[1].  residual (or NULL): the skip connection's gradient, added to the
+ * dgrad BEFORE the reduction - dx = dgrad(dz) + residual is then the whole gradient of a ResidualBlock's input
+ * (models.py:60) and z the bn2 input of the block below it.  Returns 0 ok, 1 error, 2 = shape outside the fused
+ * kernel (nothing launched; run srk_conv_fprop + srk_bn_bwd_reduce instead). */
 int srk_conv_dgrad_bnred(const srk_tensor* dz, const srk_tensor* dx, const void* w_packed_dgrad, const srk_tensor* z,
                          const float* mean, const float* invstd, const float* gamma, const float* beta,
-                         const float* alpha, float* sum_g, float* sum_gz, float* dalpha, void* reduce_ws,
-                         void* stream);
+                         const float* alpha, float* sum_g, float* sum_gz, float* dalpha, const srk_tensor* residual,
+                         void* reduce_ws, void* stream);
 
 /* ---- convolutions with an RGB side on tcgen05 (K = 9 or 5; im2col built in shared memory) ---------
  * input_conv / SRCNN conv1 (3 -> 64, models.py:84,107,150) and the backward of output_conv / SRCNN conv3

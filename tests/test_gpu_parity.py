@@ -749,6 +749,84 @@ def test_dgrad_with_fused_bn_backward_reduction(with_prelu):
     assert float(dy_f[:, 0].abs().max()) == 0 and float(dy_f[:, :, -1].abs().max()) == 0
 
 
+def test_dgrad_with_residual_and_fused_bn_backward_reduction():
+    """srk_conv_dgrad_bnred with a residual: dx = dgrad(dz) + residual is the whole gradient of a residual block's
+    input; the sums of the bn2 of the block below are taken of that total (no PReLU between them, models.py:55-60)."""
+    import srk
+    from srk import ops
+    srk.set_compute_dtype("bf16")
+    g = torch.Generator().manual_seed(29)
+    n, c, h, w = 3, 64, 19, 34
+
+    def act(scale=1.0):
+        t = torch.zeros(n, h + 2, w + 2, c)
+        t[:, 1:-1, 1:-1] = torch.randn(n, h, w, c, generator=g) * scale
+        return t.to(DEV).bfloat16()
+
+    dz, z, res = act(), act(2.0), act(0.7)
+    wt = (torch.randn(64, 64, 3, 3, generator=g) / 24).to(DEV)
+    gamma = (torch.rand(c, generator=g) + 0.5).to(DEV)
+    beta = (torch.randn(c, generator=g) * 0.3).to(DEV)
+    _, stats = ops.bn_forward(z, gamma, beta, None, None, None, True, 1e-5, 0.1, None, None)
+    fused = ops.conv_dgrad_bnred(dz, wt, z, stats, gamma, beta, None, residual=res)
+    assert fused is not None, "the fused kernel must cover the 64 -> 64 trunk shape"
+    dx_f, red = fused
+    dx_u = ops.conv_dgrad(dz, False, wt, res, torch.bfloat16)
+    assert torch.equal(dx_f, dx_u)
+    want = F.conv_transpose2d(dz[:, 1:-1, 1:-1].permute(0, 3, 1, 2).float().cpu(), wt.cpu(), padding=1) \
+        + res[:, 1:-1, 1:-1].permute(0, 3, 1, 2).float().cpu()
+    assert rel_err(dx_f[:, 1:-1, 1:-1].permute(0, 3, 1, 2).cpu(), want) <= 1e-2
+    zi = z[:, 1:-1, 1:-1].permute(0, 3, 1, 2).float().cpu()
+    assert rel_err(red[:c].cpu(), want.sum(dim=(0, 2, 3))) <= 2e-3
+    assert rel_err(red[c:2 * c].cpu(), (want * zi).sum(dim=(0, 2, 3))) <= 2e-3
+    dy_u, dgamma_u, dbeta_u, _ = ops.bn_backward(dx_u, z, stats, gamma, beta, None, True)
+    dy_f, dgamma_f, dbeta_f, _ = ops.bn_backward(dx_f, z, stats, gamma, beta, None, True, pre=red)
+    assert rel_err(dbeta_f.cpu(), dbeta_u.cpu()) <= 3e-3
+    assert rel_err(dgamma_f.cpu(), dgamma_u.cpu()) <= 3e-3
+    assert rel_err(dy_f.float().cpu(), dy_u.float().cpu()) <= 1e-2
+    assert float(dx_f[:, 0].abs().max()) == 0 and float(dx_f[:, :, -1].abs().max()) == 0
+
+
+def test_resnet_block_chain_reduction_matches_unfused_backward():
+    """ResNetSR hands the bn2 backward reduction of block k to the last dgrad of block k+1 (fn.BnLink).  Same step
+    with every fused BN-backward reduction switched off: gradients agree to the rounding of the sums."""
+    import srk
+    from srk import ops
+    from src import models as M
+    srk.set_compute_dtype("bf16")
+    torch.manual_seed(11)
+    model = M.ResNetSR(num_channels=64, num_residuals=3).to(DEV).train()
+    lr, hr = O.synthetic_pair(2, 20, 24, 4, seed=6)
+    lr, hr = lr.to(DEV), hr.to(DEV)
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+
+    def step(fuse):
+        model.load_state_dict(state)
+        model.zero_grad(set_to_none=True)
+        old = ops.cfg.fuse_bn_reduce
+        ops.cfg.fuse_bn_reduce = fuse
+        try:
+            c0 = L_calls()
+            (model(lr) - hr).abs().mean().backward()
+            torch.cuda.synchronize()
+            return {k: p.grad.detach().clone() for k, p in model.named_parameters()}, L_calls() - c0
+        finally:
+            ops.cfg.fuse_bn_reduce = old
+
+    def L_calls():
+        from srk import _lib
+        return _lib.launch_calls
+
+    g_f, n_f = step(True)
+    g_u, n_u = step(False)
+    # per block: bn1's reduction rides in conv2's dgrad; bn2's (all but the top block's) in the dgrad of the block above
+    assert n_u - n_f == 3 + 2, (n_u, n_f)
+    for k in g_u:
+        if g_u[k].numel() == 1 or ("conv" in k and k.endswith("bias") and "res_blocks" in k):
+            continue   # cancelling sums / analytically zero gradients (bias before a training-mode BatchNorm)
+        assert rel_err(g_f[k].cpu(), g_u[k].cpu()) <= 2e-2, (k, rel_err(g_f[k].cpu(), g_u[k].cpu()))
+
+
 @pytest.mark.parametrize("dtype,tol", [("fp32", 2e-5), ("bf16", 3e-2)])   # bf16: two different roundings of the same
 def test_eval_bn_folding_matches_unfolded_path(dtype, tol):                # network, each <= 2e-2 from the fp32 oracle
     """Inference folds the running-statistics BatchNorm into the conv weights (two launches per residual block);

@@ -51,6 +51,9 @@ for fold in (2, 4):
         "dgrad+bnred": [lambda d=d, y=y, st=st: ops.conv_dgrad_bnred(d, w, y, st, gamma, beta, alpha)
                         for d, y, st in zip(ds, ys, stats)],
     }
+    if fold == 2:
+        cases["dgrad+res+bnred"] = [lambda d=d, y=y, st=st, x=x: ops.conv_dgrad_bnred(d, w, y, st, gamma, beta, None, residual=x)
+                                    for d, y, st, x in zip(ds, ys, stats, xs)]
     for name, fs in cases.items():
         ms = bench._time_replayed(fs)
         print("fold %d  %-12s %7.2f us  %7.1f TFLOP/s" % (fold, name, ms * 1e3, flop / (ms * 1e-3) / 1e12), flush=True)
