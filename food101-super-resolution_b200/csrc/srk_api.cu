@@ -28,7 +28,7 @@ bool conv_tc_shape_ok(int cin, int cout, int r, int s, int dtype, int shuffle);
 int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout,
                          int r, int s, const float* bias, int act, const float* alpha,
                          const srk_tensor* residual, int shuffle, float* stats_sum, float* stats_sumsq,
-                         void* workspace, cudaStream_t st, void* reduce_ws, void* zsave);
+                         void* workspace, cudaStream_t st, void* reduce_ws, void* zsave, void* acc = nullptr);
 int64_t conv_fprop_tc_workspace(const srk_tensor* x);
 bool conv_smalln_tc_ok(const srk_tensor* x, const srk_tensor* y, int cout, int r, int s);
 int conv_smalln_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout, int r,
@@ -74,8 +74,18 @@ extern "C" int64_t srk_conv_fprop_workspace_bytes(const srk_tensor* x, int pack_
 extern "C" int srk_conv_fprop(const srk_tensor* x, const srk_tensor* y, const void* w_packed,
                               int pack_kind, int cout, int r, int s, const float* bias, int act,
                               const float* alpha, const srk_tensor* residual, int pixel_shuffle,
-                              int impl, float* bn_sums, void* reduce_ws, const srk_tensor* prelu_z,
+                              int impl, float* bn_sums, void* reduce_ws, void* bn_acc, const srk_tensor* prelu_z,
                               void* workspace, void* stream) {
+  if (bn_acc != nullptr) {   // 2 = the accumulator path does not cover this conv: nothing launched
+    SRK_REQUIRE(bn_sums == nullptr, "srk_conv_fprop: bn_sums and bn_acc exclude each other");
+    if (!(tensor_ok(x) && tensor_ok(y) && w_packed && pack_kind == SRK_PACK_FPROP_TC && (impl == SRK_IMPL_AUTO || impl == SRK_IMPL_TC) &&
+          x->layout == SRK_LAYOUT_ACT && y->layout == SRK_LAYOUT_ACT && x->dtype == SRK_BF16 && y->dtype == SRK_BF16 &&
+          r == 3 && s == 3 && x->c == 64 && cout == 64 && same_geometry(x, y) && act == SRK_ACT_NONE && residual == nullptr &&
+          pixel_shuffle == 0 && prelu_z == nullptr))
+      return 2;
+    return conv_fprop_tc_launch(x, y, w_packed, cout, r, s, bias, act, alpha, nullptr, 0, nullptr, nullptr, workspace,
+                                (cudaStream_t)stream, nullptr, nullptr, bn_acc);
+  }
   float* bn_sum = bn_sums;
   float* bn_sumsq = bn_sums ? bn_sums + cout : nullptr;
   SRK_REQUIRE(tensor_ok(x) && tensor_ok(y), "srk_conv_fprop: bad x / y tensor");
@@ -149,11 +159,12 @@ extern "C" int srk_conv_fprop(const srk_tensor* x, const srk_tensor* y, const vo
 extern "C" int srk_conv_dgrad_bnred(const srk_tensor* dz, const srk_tensor* dx, const void* w_packed_dgrad,
                                     const srk_tensor* z, const float* mean, const float* invstd, const float* gamma,
                                     const float* beta, const float* alpha, float* sum_g, float* sum_gz, float* dalpha,
-                                    const srk_tensor* residual, void* reduce_ws, void* stream) {
+                                    const srk_tensor* residual, void* reduce_ws, void* acc, void* stream) {
   SRK_REQUIRE(tensor_ok(dz) && tensor_ok(dx) && tensor_ok(z) && w_packed_dgrad, "srk_conv_dgrad_bnred: bad tensors");
-  SRK_REQUIRE(reduce_ws != nullptr, "srk_conv_dgrad_bnred: reduce_ws is required");
-  SRK_REQUIRE(mean && invstd && gamma && beta && sum_g && sum_gz, "srk_conv_dgrad_bnred: null statistics");
-  SRK_REQUIRE(alpha == nullptr || dalpha != nullptr, "srk_conv_dgrad_bnred: dalpha is required with alpha");
+  SRK_REQUIRE(reduce_ws != nullptr || acc != nullptr, "srk_conv_dgrad_bnred: reduce_ws (or acc) is required");
+  SRK_REQUIRE(mean && invstd && gamma && beta && ((sum_g && sum_gz) || acc), "srk_conv_dgrad_bnred: null statistics");
+  SRK_REQUIRE(alpha == nullptr || dalpha != nullptr || acc != nullptr, "srk_conv_dgrad_bnred: dalpha is required with alpha");
+  if (acc != nullptr && !(tc_fold() >= 1 && tc_fold() <= 3)) return 2;
   if (!(dz->layout == SRK_LAYOUT_ACT && dx->layout == SRK_LAYOUT_ACT && dz->dtype == SRK_BF16 && dx->dtype == SRK_BF16 &&
         dz->c == 64 && dx->c == 64 && same_geometry(dz, dx)))
     return 2;
@@ -161,13 +172,13 @@ extern "C" int srk_conv_dgrad_bnred(const srk_tensor* dz, const srk_tensor* dx, 
                     residual->dtype == SRK_BF16))
     return 2;
   BnRedArgs br = {z, mean, invstd, gamma, beta, alpha, sum_g, sum_gz, dalpha};
-  if (tc_fold() == 4 && residual == nullptr) {
+  if (tc_fold() == 4 && residual == nullptr && acc == nullptr) {
     const int rs = conv_fprop_strip_launch(dz, dx, w_packed_dgrad, 64, nullptr, SRK_ACT_NONE, nullptr, nullptr, 0, nullptr,
                                            nullptr, (cudaStream_t)stream, &br, reduce_ws, nullptr);
     if (rs >= 0) return rs;
   }
   const int rc = conv_fprop_fold_launch(dz, dx, w_packed_dgrad, 64, nullptr, SRK_ACT_NONE, nullptr, residual, 0, nullptr,
-                                        nullptr, nullptr, 0, (cudaStream_t)stream, &br, reduce_ws, nullptr);
+                                        nullptr, nullptr, 0, (cudaStream_t)stream, &br, reduce_ws, nullptr, acc);
   return rc < 0 ? 2 : rc;
 }
 

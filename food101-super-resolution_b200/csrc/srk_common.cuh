@@ -248,6 +248,54 @@ __device__ __forceinline__ void ordered_fold(const float* vals, int NV, unsigned
   }
 }
 
+// ---- exact cross-block sums: accumulators ("acc") ---------------------------------------------------------
+// ordered_fold() ends a kernel with a chain of dependent global-memory steps (row store, fence, ticket, row loads,
+// second level): measured at the end of the C2 trunk conv each step costs 1.2-2 us - 5 us on a 23 us kernel, on 65
+// launches of a training step.  The convs therefore hand their per-CTA partial sums over as INTEGERS instead: a float
+// is split exactly into radix-2^40 digits at 2^-94, 2^-54, 2^-14, 2^26, 2^66 (a 24-bit mantissa touches at most two
+// of them; what lies below 2^-94 is dropped) and each non-zero digit is added to a 64-bit counter with a fire-and-
+// forget red.global.add.u64.  Integer addition is associative, so the total does not depend on the order in which
+// the CTAs arrive - bit-reproducible like ordered_fold, and exact - and nothing waits for a reply.  A sixth counter
+// counts non-finite contributions (the sum then reads as NaN).  The CONSUMER kernel (bn_apply_train /
+// bn_bwd_apply_raw / acc_read) converts the digits back in its prologue, and the consumer block that draws the last
+// ticket - taken right after the prologue, its latency hidden behind the block's main loop - zero-fills the
+// accumulator for its next use.  Contract: zero-filled once by the caller, then producer and consumer alternate.
+// Layout (kAccBytes): u64 [6][kAccNV] digits (value-minor) | u32 consumer ticket.
+constexpr int kAccNV = 132, kAccLimbs = 5;
+constexpr size_t kAccBytes = 8192;
+__device__ __forceinline__ double acc_unit(int k) {   // 2^(-94 + 40 k)
+  return __longlong_as_double((long long)(1023 - 94 + 40 * k) << 52);
+}
+__device__ __forceinline__ void acc_add(unsigned long long* acc, int i, float p) {
+  if (!(fabsf(p) <= 3.402823466e38f)) { atomicAdd(acc + kAccLimbs * kAccNV + i, 1ull); return; }
+  double r = (double)p;
+#pragma unroll
+  for (int k = kAccLimbs - 1; k >= 0; --k) {
+    const long long d = __double2ll_rz(r * __longlong_as_double((long long)(1023 + 94 - 40 * k) << 52));   // r / unit
+    r -= (double)d * acc_unit(k);   // exact: d has at most 24 significant bits
+    if (d != 0) atomicAdd(acc + k * kAccNV + i, (unsigned long long)d);
+  }
+}
+__device__ __forceinline__ double acc_read(const unsigned long long* acc, int i) {
+  if (__ldcg(acc + kAccLimbs * kAccNV + i) != 0ull) return __longlong_as_double(0x7ff8000000000000ll);
+  double s = 0.0;
+#pragma unroll
+  for (int k = kAccLimbs - 1; k >= 0; --k) s += (double)(long long)__ldcg(acc + k * kAccNV + i) * acc_unit(k);
+  return s;
+}
+// Consumer side, called by thread 0 of EVERY block after the values of the block's acc_read()s have been USED (stored
+// to shared memory, a __syncthreads() behind them): returns true in the block that must zero-fill the accumulator
+// (acc_clear, at the end of that block).  No fence: the loads have returned their values before the ticket is issued,
+// and the zero-fill is issued after the last ticket has been observed, so it cannot reach a load that is still in
+// flight; the next producer is ordered behind the zero-fill by the kernel boundary.
+__device__ __forceinline__ bool acc_ticket(unsigned long long* acc, int nblk) {
+  unsigned* ticket = reinterpret_cast<unsigned*>(acc + (kAccLimbs + 1) * kAccNV);
+  return atomicAdd(ticket, 1u) == (unsigned)nblk - 1u;
+}
+__device__ __forceinline__ void acc_clear(unsigned long long* acc, int tid, int T) {
+  for (int i = tid; i < (kAccLimbs + 1) * kAccNV + 1; i += T) acc[i] = 0ull;   // digits, flags and the ticket word
+}
+
 // ---- programmatic dependent launch ---------------------------------------------------------------------
 // A training step is ~270 launches of 7-60 us each, so the gap between two kernels of a stream (launch latency,
 // the tail of the first, the prologue of the second: barrier init, TMEM allocation, descriptor prefetch) is a few

@@ -88,6 +88,9 @@ struct Params {
   // cross-CTA stage of the statistics (ordered_fold, srk_common.cuh): ticket + partial rows [grid][132]
   unsigned* red_ticket;
   float* red_part;
+  // ... or, when set, the exact integer accumulator (srk_common.cuh "acc"): value i of [sum 64 | sumsq 64 | dalpha]
+  // is added to acc slot i with fire-and-forget reductions and the kernel ends without a serial tail
+  unsigned long long* acc;
   // PReLU epilogues with a slope <= 0 also store the pre-activation (same geometry as y) for the backward pass
   __nv_bfloat16* zsave;
   int* err;
@@ -647,7 +650,9 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         vals[128] = t;
       }
       named_bar_sync(7, kEpiThreads);
-      if (et < 256) {
+      if (p.acc != nullptr) {
+        if (et < 128 || (et == 128 && kStats && p.bn_red && p.bn_mask)) acc_add(p.acc, et, vals[et]);
+      } else if (et < 256) {
         const bool want_da = kStats && p.bn_red && p.bn_mask && p.bn_dalpha != nullptr;
         const int n_ok = p.cout_total - p.cout_off;   // columns of this pass that exist in the tensor
         ordered_fold(vals, 129, p.red_ticket, (int)gridDim.x, (int)blockIdx.x, p.red_part, reinterpret_cast<float4*>(xch),
@@ -714,10 +719,12 @@ static cudaError_t launch_pass(bool fast, bool stats, int act, int grid, int sme
 int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout,
                            const float* bias, int act, const float* alpha, const srk_tensor* residual, int shuffle,
                            float* stats_sum, float* stats_sumsq, void* workspace, int variant, cudaStream_t st,
-                           const BnRedArgs* br, void* reduce_ws, void* zsave) {
+                           const BnRedArgs* br, void* reduce_ws, void* zsave, void* acc) {
   using namespace fold;
-  SRK_REQUIRE((stats_sum == nullptr && br == nullptr) || reduce_ws != nullptr,
-              "conv_fold: fused statistics need the reduce workspace");
+  SRK_REQUIRE((stats_sum == nullptr && br == nullptr) || reduce_ws != nullptr || acc != nullptr,
+              "conv_fold: fused statistics need the reduce workspace or an accumulator");
+  // accumulator mode: the kernel's "statistics on" switch is a non-null stats_sum
+  if (acc != nullptr && br == nullptr && stats_sum == nullptr) { stats_sum = (float*)acc; stats_sumsq = (float*)acc; }
   // variant: 0 per-tap, 1 folded taps, 2 per-tap on CTA pairs (cta_group::2), 3 = CTA pairs with 128 output
   // channels per pass (PixelShuffle outputs of a single-chunk contraction: the 64 -> 256 upsample convs)
   const bool folded = variant == 1, pair = variant == 2 || variant == 3;
@@ -773,6 +780,7 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
   p.stats_sum = stats_sum; p.stats_sumsq = stats_sumsq;
   p.red_ticket = reduce_ws ? red_tickets(reduce_ws) : nullptr;
   p.red_part = reduce_ws ? red_partials(reduce_ws) : nullptr;
+  p.acc = (unsigned long long*)acc;
   p.zsave = (__nv_bfloat16*)zsave;
   p.bn_red = 0; p.bn_mask = 0;
   p.bn_mean = p.bn_invstd = p.bn_gamma = p.bn_beta = nullptr; p.bn_dalpha = nullptr;
@@ -784,7 +792,7 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
     // without a residual Z travels in the residual slot; with one it gets its own map and staging tiles
     if (make_tmap_2d_bf16(residual ? &tmZ : &tmR, br->z->data, (uint64_t)P, (uint64_t)cout, (uint64_t)cout, TMO, NT, 128))
       return 1;
-    p.stats_sum = stats_sum = br->sum_g; p.stats_sumsq = stats_sumsq = br->sum_gz;
+    p.stats_sum = stats_sum = acc ? (float*)acc : br->sum_g; p.stats_sumsq = stats_sumsq = acc ? (float*)acc : br->sum_gz;
     p.bn_red = residual ? 2 : 1; p.bn_mask = br->alpha != nullptr; p.alpha = br->alpha;
     p.bn_mean = br->mean; p.bn_invstd = br->invstd; p.bn_gamma = br->gamma; p.bn_beta = br->beta;
     p.bn_dalpha = br->dalpha;

@@ -580,8 +580,19 @@ bool conv_tc_shape_ok(int cin, int cout, int r, int s, int dtype, int shuffle) {
 int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout, int r, int s,
                          const float* bias, int act, const float* alpha, const srk_tensor* residual, int shuffle,
                          float* stats_sum, float* stats_sumsq, void* workspace, cudaStream_t st, void* reduce_ws,
-                         void* zsave) {
+                         void* zsave, void* acc) {
   SRK_REQUIRE(stats_sum == nullptr || reduce_ws != nullptr, "conv_tc: fused statistics need the reduce workspace");
+  if (acc != nullptr) {
+    // statistics into an exact integer accumulator: the 16-warp halo-slab kernel's single-pass 64 -> 64 conv only;
+    // 2 = not covered, nothing launched (the caller uses the float path)
+    if (!(r == 3 && tc_fold() >= 1 && tc_fold() <= 3 && shuffle == 0 && x->c == 64 && cout == 64 && act == SRK_ACT_NONE &&
+          residual == nullptr && stats_sum == nullptr))
+      return 2;
+    const int rc = conv_fprop_fold_launch(x, y, w_packed, cout, bias, act, alpha, residual, shuffle, nullptr, nullptr,
+                                          workspace, tc_fold() == 1 ? 1 : (tc_fold() == 3 ? 2 : 0), st, nullptr, nullptr,
+                                          zsave, acc);
+    return rc < 0 ? 2 : rc;
+  }
   // PixelShuffle outputs stay on the 8-warp kernel below: its threads own 32 channels = 16-byte stores per sub-pixel,
   // the 16-warp pipeline would store 8 bytes at a time (measured 64->256 at 128^2: 424 vs 685 us)
   // 64 -> 256 PixelShuffle convs on CTA pairs with N = 128 MMAs (SRK_TC_UP_PAIR=1): parity-green but slower (128^2:

@@ -269,6 +269,7 @@ struct BnFinalize {
   double count; float eps, momentum;
   float* running_mean; float* running_var; long long* nbt;
   float* mean_out; float* invstd_out;
+  unsigned long long* acc;   // the sums as an exact integer accumulator (srk_common.cuh) instead of sum / sumsq
 };
 
 template <typename T, int VEC>
@@ -280,10 +281,11 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ y, 
   pdl_trigger();
   extern __shared__ float bn_smem[];   // fused statistics: [C] mean, [C] invstd
   const float alpha = alpha_p ? alpha_p[0] : 1.f;
-  if (fin.sum) {
+  bool clear_acc = false;
+  if (fin.sum || fin.acc) {
     for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
-      const double m = (double)fin.sum[c] / fin.count;
-      double var = (double)fin.sumsq[c] / fin.count - m * m;
+      const double m = (fin.acc ? acc_read(fin.acc, c) : (double)fin.sum[c]) / fin.count;
+      double var = (fin.acc ? acc_read(fin.acc, g.C + c) : (double)fin.sumsq[c]) / fin.count - m * m;
       if (var < 0.0) var = 0.0;
       const float mf = (float)m, isf = (float)(1.0 / sqrt(var + (double)fin.eps));
       bn_smem[c] = mf; bn_smem[g.C + c] = isf;
@@ -299,6 +301,9 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ y, 
     if (blockIdx.x == 0 && threadIdx.x == 0 && fin.nbt != nullptr) fin.nbt[0] += 1;
     __syncthreads();
     mean = bn_smem; invstd = bn_smem + g.C;
+    // every block has its statistics (the loads have returned: their values are in shared memory): take the ticket
+    // now, look at it after the pixel loop - the block that drew the last one resets the accumulator
+    if (fin.acc && threadIdx.x == 0) clear_acc = acc_ticket(fin.acc, gridDim.x);
   }
   // per-channel scale / shift of this thread's channel vector, hoisted out of the pixel loop
   float sc[VEC], sh[VEC];
@@ -333,6 +338,9 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ y, 
       }
     }
     Vec<T, VEC>::st(out + e, o);
+  }
+  if (fin.acc) {
+    if (__syncthreads_or(clear_acc)) acc_clear(fin.acc, threadIdx.x, blockDim.x);
   }
 }
 
@@ -418,12 +426,27 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
     const T* __restrict__ y, Geo g, int ppb, const float* __restrict__ mean,
     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
     const float* __restrict__ alpha_p, const float* __restrict__ dgamma, const float* __restrict__ dbeta,
-    float inv_count, int batch_stats, T* __restrict__ dy, float* __restrict__ dgamma_out) {
+    float inv_count, int batch_stats, T* __restrict__ dy, float* __restrict__ dgamma_out,
+    unsigned long long* acc, float* __restrict__ dbeta_out, float* __restrict__ dalpha_out) {
   pdl_wait();      // the inputs come from the previous kernel of the stream (see launch_dep)
   pdl_trigger();
   const float alpha = alpha_p ? alpha_p[0] : 1.f;
   // raw mode (dgamma_out != null): the reduction came out of a conv epilogue as (sum g, sum g*z) in (dbeta, dgamma);
   // sum g*xhat = invstd * (sum g*z - mean * sum g).  Block 0 publishes the finished dgamma.
+  // With `acc` the raw sums arrive as an exact integer accumulator [sum g C | sum g*z C | dalpha] (srk_common.cuh):
+  // converted once per block through shared memory; block 0 also publishes dbeta = sum g and dalpha.
+  __shared__ float racc[kAccNV];
+  bool clear_acc = false;
+  if (acc != nullptr) {
+    for (int i = threadIdx.x; i < 2 * g.C + 1; i += blockDim.x) racc[i] = (float)acc_read(acc, i);
+    __syncthreads();
+    if (threadIdx.x == 0) clear_acc = acc_ticket(acc, gridDim.x);   // looked at after the pixel loop
+    dbeta = racc; dgamma = racc + g.C;
+    if (blockIdx.x == 0) {
+      for (int c = threadIdx.x; c < g.C; c += blockDim.x) dbeta_out[c] = racc[c];
+      if (threadIdx.x == 0 && dalpha_out != nullptr) dalpha_out[0] = racc[2 * g.C];
+    }
+  }
   if (dgamma_out != nullptr && blockIdx.x == 0) {
     for (int c = threadIdx.x; c < g.C; c += blockDim.x) dgamma_out[c] = invstd[c] * (dgamma[c] - mean[c] * dbeta[c]);
   }
@@ -459,6 +482,16 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
     }
     Vec<T, VEC>::st(dy + e, o);
   }
+  if (acc != nullptr) {
+    if (__syncthreads_or(clear_acc)) acc_clear(acc, threadIdx.x, blockDim.x);
+  }
+}
+
+// generic consumer of an accumulator: out[i] = value i (i < nv), then the accumulator is reset
+__global__ void acc_read_kernel(unsigned long long* acc, int nv, float* __restrict__ out) {
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) out[i] = (float)acc_read(acc, i);
+  __syncthreads();
+  acc_clear(acc, threadIdx.x, blockDim.x);
 }
 
 // ---- activation backward -------------------------------------------------------------------------
@@ -1017,16 +1050,17 @@ extern "C" int srk_bn_apply_train(const srk_tensor* y, const float* sum, const f
                                   float momentum, float* running_mean, float* running_var,
                                   int64_t* num_batches_tracked, float* mean, float* invstd, const float* gamma,
                                   const float* beta, const float* alpha, const srk_tensor* residual,
-                                  const srk_tensor* out, void* stream) {
+                                  const srk_tensor* out, void* acc, void* stream) {
   ACT_CHECK(y, "srk_bn_apply_train"); ACT_CHECK(out, "srk_bn_apply_train");
   SRK_REQUIRE(same_geometry(y, out) && y->dtype == out->dtype, "srk_bn_apply_train: geometry mismatch");
   if (residual) SRK_REQUIRE(same_geometry(y, residual) && residual->dtype == y->dtype && residual->layout == SRK_LAYOUT_ACT, "srk_bn_apply_train: residual mismatch");
   SRK_REQUIRE(c_ok(y), "srk_bn_apply_train: unsupported channel count %d", y->c);
-  SRK_REQUIRE(sum && sumsq && mean && invstd && count > 0, "srk_bn_apply_train: statistics buffers required");
+  SRK_REQUIRE(((sum && sumsq) || acc) && mean && invstd && count > 0, "srk_bn_apply_train: statistics buffers required");
+  SRK_REQUIRE(acc == nullptr || 2 * y->c + 1 <= kAccNV, "srk_bn_apply_train: an accumulator holds at most %d values", kAccNV);
   SRK_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "srk_bn_apply_train: running_mean / running_var go together");
   Geo g = geo_of(y); int blocks, ppb; bn_map_grid(g, blocks, ppb);
   BnFinalize fin = {sum, sumsq, (double)count, eps, momentum, running_mean, running_var,
-                    (long long*)num_batches_tracked, mean, invstd};
+                    (long long*)num_batches_tracked, mean, invstd, (unsigned long long*)acc};
   const size_t smem = 2 * (size_t)y->c * sizeof(float);
   DISPATCH_T_VEC(y, (launch_dep(PDL_BN, bn_apply_kernel<T, VEC>, dim3(blocks), dim3(256), smem, (cudaStream_t)stream,
                         (const T*)y->data, g, ppb, nullptr, nullptr, gamma, beta, alpha,
@@ -1066,7 +1100,7 @@ extern "C" int srk_bn_bwd_apply(const srk_tensor* dout, const srk_tensor* y, con
   float inv_count = 1.f / ((float)y->n * y->h * y->w);
   DISPATCH_T_VEC(y, (launch_dep(PDL_BN, bn_bwd_apply_kernel<T, VEC>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream,
                         (const T*)dout->data, (const T*)y->data, g, ppb, mean, invstd, gamma, beta,
-                        alpha, dgamma_b, dbeta_b, inv_count, batch_stats, (T*)dy->data, nullptr)));
+                        alpha, dgamma_b, dbeta_b, inv_count, batch_stats, (T*)dy->data, nullptr, nullptr, nullptr, nullptr)));
   SRK_CUDA_LAUNCH_CHECK("bn_bwd_apply");
   return 0;
 }
@@ -1074,18 +1108,31 @@ extern "C" int srk_bn_bwd_apply(const srk_tensor* dout, const srk_tensor* y, con
 extern "C" int srk_bn_bwd_apply_raw(const srk_tensor* dout, const srk_tensor* y, const float* mean,
                                     const float* invstd, const float* gamma, const float* beta,
                                     const float* alpha, const float* sum_g, const float* sum_gz,
-                                    int batch_stats, float* dgamma_out, const srk_tensor* dy, void* stream) {
+                                    int batch_stats, float* dgamma_out, const srk_tensor* dy, void* acc,
+                                    float* dbeta_out, float* dalpha_out, void* stream) {
   ACT_CHECK(y, "srk_bn_bwd_apply_raw"); ACT_CHECK(dout, "srk_bn_bwd_apply_raw"); ACT_CHECK(dy, "srk_bn_bwd_apply_raw");
   SRK_REQUIRE(same_geometry(y, dout) && same_geometry(y, dy) && y->dtype == dout->dtype && y->dtype == dy->dtype,
               "srk_bn_bwd_apply_raw: geometry mismatch");
   SRK_REQUIRE(c_ok(y), "srk_bn_bwd_apply_raw: unsupported channel count %d", y->c);
-  SRK_REQUIRE(sum_g && sum_gz && dgamma_out, "srk_bn_bwd_apply_raw: sums and dgamma_out are required");
+  SRK_REQUIRE(((sum_g && sum_gz) || (acc && dbeta_out)) && dgamma_out,
+              "srk_bn_bwd_apply_raw: sums (or an accumulator and dbeta_out) and dgamma_out are required");
+  SRK_REQUIRE(acc == nullptr || 2 * y->c + 1 <= kAccNV, "srk_bn_bwd_apply_raw: an accumulator holds at most %d values", kAccNV);
   Geo g = geo_of(y); int blocks, ppb; bn_map_grid(g, blocks, ppb);
   float inv_count = 1.f / ((float)y->n * y->h * y->w);
   DISPATCH_T_VEC(y, (launch_dep(PDL_BN, bn_bwd_apply_kernel<T, VEC>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream,
                         (const T*)dout->data, (const T*)y->data, g, ppb, mean, invstd, gamma, beta,
-                        alpha, sum_gz, sum_g, inv_count, batch_stats, (T*)dy->data, dgamma_out)));
+                        alpha, sum_gz, sum_g, inv_count, batch_stats, (T*)dy->data, dgamma_out,
+                        (unsigned long long*)acc, dbeta_out, dalpha_out)));
   SRK_CUDA_LAUNCH_CHECK("bn_bwd_apply_raw");
+  return 0;
+}
+
+extern "C" int64_t srk_acc_bytes(void) { return (int64_t)kAccBytes; }
+
+extern "C" int srk_acc_read(void* acc, int nv, float* out, void* stream) {
+  SRK_REQUIRE(acc && out && nv >= 1 && nv <= kAccNV, "srk_acc_read: bad arguments");
+  acc_read_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((unsigned long long*)acc, nv, out);
+  SRK_CUDA_LAUNCH_CHECK("acc_read");
   return 0;
 }
 

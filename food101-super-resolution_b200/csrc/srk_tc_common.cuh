@@ -252,10 +252,12 @@ struct BnRedArgs {
 // variant: 0 per-tap, 1 folded taps, 2 per-tap on CTA pairs, 3 CTA pairs with 128-channel PixelShuffle passes.
 // Returns 0 ok, 1 error, -1 "slab does not fit" (the caller falls back to the per-tap kernel of srk_conv_tc.cu).
 // reduce_ws: reduce workspace (required with stats_sum / br); zsave: optional pre-activation copy for PReLU (bf16, y geometry).
+// acc: exact integer accumulator (srk_common.cuh) that receives [sum | sumsq] / [sum g | sum g z | dalpha] INSTEAD of
+// the float outputs (which may then be null, like reduce_ws).
 int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout, const float* bias,
                            int act, const float* alpha, const srk_tensor* residual, int shuffle, float* stats_sum,
                            float* stats_sumsq, void* workspace, int variant, cudaStream_t st, const BnRedArgs* br,
-                           void* reduce_ws, void* zsave);
+                           void* reduce_ws, void* zsave, void* acc = nullptr);
 
 // Column-strip formulation of the 3x3 64 -> 64 conv (srk_conv_strip_tc.cu).  Returns 0 ok, 1 error, -1 not applicable.
 int conv_fprop_strip_launch(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int cout, const float* bias,

@@ -32,8 +32,10 @@ SIGNATURES = {
     "srk_last_error": (c_char_p, []),
     "srk_version": (c_int, []),
     "srk_conv_tc_supported": (c_int, [c_int] * 6),
-    "srk_conv_fprop": (c_int, [_T, _T, _P, c_int, c_int, c_int, c_int, _P, c_int, _P, _T, c_int, c_int, _P, _P, _T, _P, _P]),
+    "srk_conv_fprop": (c_int, [_T, _T, _P, c_int, c_int, c_int, c_int, _P, c_int, _P, _T, c_int, c_int, _P, _P, _P, _T, _P, _P]),
     "srk_reduce_workspace_bytes": (c_int64, []),
+    "srk_acc_bytes": (c_int64, []),
+    "srk_acc_read": (c_int, [_P, c_int, _P, _P]),
     "srk_pixel_loss_scratch_bytes": (c_int64, []),
     "srk_conv_fprop_workspace_bytes": (c_int64, [_T, c_int]),
     "srk_conv_wgrad": (c_int, [_T, _T, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
@@ -50,11 +52,11 @@ SIGNATURES = {
     "srk_bn_finalize": (c_int, [_P, _P, c_int, c_int64, c_float, c_float, _P, _P, _P, _P, _P, _P]),
     "srk_bn_eval_params": (c_int, [_P, _P, c_int, c_float, _P, _P, _P]),
     "srk_bn_apply": (c_int, [_T, _P, _P, _P, _P, _P, _T, _T, _P]),
-    "srk_bn_apply_train": (c_int, [_T, _P, _P, c_int64, c_float, c_float, _P, _P, _P, _P, _P, _P, _P, _P, _T, _T, _P]),
+    "srk_bn_apply_train": (c_int, [_T, _P, _P, c_int64, c_float, c_float, _P, _P, _P, _P, _P, _P, _P, _P, _T, _T, _P, _P]),
     "srk_bn_bwd_reduce": (c_int, [_T, _T, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "srk_bn_bwd_apply": (c_int, [_T, _T, _P, _P, _P, _P, _P, _P, _P, c_int, _T, _P]),
-    "srk_bn_bwd_apply_raw": (c_int, [_T, _T, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _T, _P]),
-    "srk_conv_dgrad_bnred": (c_int, [_T, _T, _P, _T, _P, _P, _P, _P, _P, _P, _P, _P, _T, _P, _P]),
+    "srk_bn_bwd_apply_raw": (c_int, [_T, _T, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _T, _P, _P, _P, _P]),
+    "srk_conv_dgrad_bnred": (c_int, [_T, _T, _P, _T, _P, _P, _P, _P, _P, _P, _P, _P, _T, _P, _P, _P]),
     "srk_se_pool": (c_int, [_T, _P, _P, _P]),
     "srk_se_fc": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P]),
     "srk_se_apply": (c_int, [_T, _T, _P, c_float, _T, _P]),
@@ -95,7 +97,8 @@ for _name, (_res, _args) in SIGNATURES.items():
 launch_calls = 0
 _NO_COUNT = {"srk_last_error", "srk_version", "srk_conv_tc_supported", "srk_weight_pack_bytes",
              "srk_conv_wgrad_workspace_bytes", "srk_nlpd_workspace_bytes", "srk_conv_rgb_workspace_bytes",
-             "srk_conv_fprop_workspace_bytes", "srk_reduce_workspace_bytes", "srk_pixel_loss_scratch_bytes"}
+             "srk_conv_fprop_workspace_bytes", "srk_reduce_workspace_bytes", "srk_pixel_loss_scratch_bytes",
+             "srk_acc_bytes"}
 
 
 def last_error():

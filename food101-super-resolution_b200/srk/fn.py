@@ -135,8 +135,9 @@ def _conv_bn_forward(x, w, b, bn_params, bn_buffers, training, eps, momentum, al
     rm, rv, nbt = bn_buffers
     sums = None
     if ops.bn_needs_batch_stats(rm, training):  # the conv epilogue accumulates the batch statistics
-        sums = torch.empty((2, w.shape[0]), dtype=torch.float32, device=x.device)
-    y, used_tc = ops.conv_fprop(x, False, w, b, L.ACT_NONE, None, None, 0, False, x.dtype, bn_sums=sums)
+        y, used_tc, sums = ops.conv_fprop_stats(x, w, b)
+    else:
+        y, used_tc = ops.conv_fprop(x, False, w, b, L.ACT_NONE, None, None, 0, False, x.dtype)
     out, stats = ops.bn_forward(y, gamma, beta, rm, rv, nbt, training, eps, momentum, alpha, residual, sums=sums)
     return y, out, stats
 
@@ -162,6 +163,8 @@ class BnLink:
         self.z = self.stats = self.gamma = self.beta = None
         if red is not None and grad.data_ptr() == self.grad_ptr and grad._version == self.grad_version:
             return red
+        if isinstance(red, ops.Acc):
+            ops.acc_discard(red)     # sums of a gradient nobody will ask about: the accumulator goes back clean
         return None
 
 

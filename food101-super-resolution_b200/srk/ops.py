@@ -32,6 +32,9 @@ class _Config:
     overlap_wgrad = os.environ.get("SRK_OVERLAP_WGRAD", "0") == "1"
     # BatchNorm-backward reductions ride in the epilogue of the dgrad that produces their input gradient
     fuse_bn_reduce = os.environ.get("SRK_FUSE_BN_REDUCE", "1") != "0"
+    # BatchNorm sums of the trunk convs through exact integer accumulators (include/srk.h "exact sums") instead of the
+    # ordered float fold
+    use_acc = os.environ.get("SRK_ACC", "1") != "0"
 
 
 cfg = _Config()
@@ -129,6 +132,61 @@ def reduce_ws(device=None):
         t = torch.zeros((L.cdll.srk_reduce_workspace_bytes(),), dtype=torch.uint8, device=st.device)
         _reduce_ws[key] = t
     return t.data_ptr()
+
+
+# ---- accumulators (include/srk.h "exact sums") ------------------------------------------------------------
+# A small ring of accumulator slots per device, zero-filled once.  A producer (conv_fprop bn_sums=Acc,
+# conv_dgrad_bnred) marks its slot dirty, the consumer (bn_forward / bn_backward / acc_read), which leaves the device
+# buffer zero-filled again, marks it clean.  A slot that comes round still dirty (its consumer never ran: a partial
+# backward, an exception) is zero-filled before reuse.  Within a training step at most two slots are outstanding.
+class Acc:
+    __slots__ = ("t", "dirty")
+
+    def __init__(self, t):
+        self.t, self.dirty = t, False
+
+    def data_ptr(self):
+        return self.t.data_ptr()
+
+
+_acc_pool = {}
+_ACC_SLOTS = 16
+
+
+def acc_acquire(device):
+    idx = torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    pool = _acc_pool.get(idx)
+    if pool is None:
+        nb = int(L.cdll.srk_acc_bytes())
+        buf = torch.zeros((_ACC_SLOTS, nb), dtype=torch.uint8, device=torch.device("cuda", idx))
+        pool = _acc_pool[idx] = {"slots": [Acc(buf[i]) for i in range(_ACC_SLOTS)], "next": 0}
+    a = pool["slots"][pool["next"]]
+    pool["next"] = (pool["next"] + 1) % _ACC_SLOTS
+    if a.dirty:
+        a.t.zero_()
+    a.dirty = True
+    return a
+
+
+def acc_discard(a):
+    """An accumulator whose consumer will not run: reset it now."""
+    if a.dirty:
+        a.t.zero_()
+        a.dirty = False
+
+
+def acc_read(a, nv):
+    """Generic consumer -> fp32 [nv]; the accumulator is reset."""
+    out = torch.empty((nv,), dtype=torch.float32, device=a.t.device)
+    L.call("srk_acc_read", a.data_ptr(), nv, out.data_ptr(), stream_ptr())
+    a.dirty = False
+    return out
+
+
+def _acc_conv_ok(x, weight):
+    return (cfg.use_acc and cfg.conv_impl != "simt" and x.dtype == torch.bfloat16 and tuple(weight.shape) == (64, 64, 3, 3))
 
 
 # ---- zero-initialised scratch ------------------------------------------------------------------------
@@ -415,6 +473,32 @@ def prelu_z_like(y):
     return torch.empty_like(y)
 
 
+def conv_fprop_stats(x, weight, bias):
+    """y = conv(x, weight) + bias with the per-channel (sum, sum of squares) of y taken in the conv epilogue.
+    -> (y, used_tc, sums): sums is an Acc (single-pass 64 -> 64 tensor-core conv) or an fp32 [2, Cout] tensor; both
+    are what bn_forward(sums=...) takes."""
+    if not x.is_contiguous():
+        x = x.contiguous()
+    if _acc_conv_ok(x, weight):
+        n, cin, h, w = geometry(x, False)
+        pk = packed_weight(weight, L.PACK_FPROP_TC, 0)
+        y = new_act(n, 64, h, w, x.dtype, x.device)
+        a = acc_acquire(x.device)
+        rc = _timed(("conv_fprop", cin, 64, 3, 0, n, h, w, True),
+                    lambda: L.cdll.srk_conv_fprop(act_desc(x), act_desc(y), pk.data_ptr(), L.PACK_FPROP_TC, 64, 3, 3, _ptr(bias),
+                                                  L.ACT_NONE, None, None, 0, L.IMPL_AUTO, None, None, a.data_ptr(), None,
+                                                  None, stream_ptr()))
+        if rc == 0:
+            L.launch_calls += 1
+            return y, True, a
+        a.dirty = False          # nothing was launched (rc 2: another kernel variant is selected) or the call failed
+        if rc != 2:
+            raise RuntimeError("srk_conv_fprop failed: %s" % L.last_error())
+    sums = torch.empty((2, weight.shape[0]), dtype=torch.float32, device=x.device)
+    y, used_tc = conv_fprop(x, False, weight, bias, L.ACT_NONE, None, None, 0, False, x.dtype, bn_sums=sums)
+    return y, used_tc, sums
+
+
 def conv_fprop(x, x_img, weight, bias, act, alpha, residual, shuffle, out_img, out_dtype, bn_sums=None, zsave=False):
     """y = [shuffle](act(conv(x, weight) + bias)) [+ residual]; stride 1, pad R//2.
     bn_sums: optional fp32 [2, Cout] that receives the per-channel sum / sum of squares of y.
@@ -450,7 +534,7 @@ def conv_fprop(x, x_img, weight, bias, act, alpha, residual, shuffle, out_img, o
     _timed(("conv_fprop", cin, cout, r, shuffle, n, h, w, use_tc),
            lambda: L.call("srk_conv_fprop", xd, yd, pk.data_ptr(), kind, cout, r, s, _ptr(bias), act,
                           _ptr(alpha), rd, shuffle, L.IMPL_AUTO, _ptr(bn_sums),
-                          reduce_ws(x.device) if bn_sums is not None else None,
+                          reduce_ws(x.device) if bn_sums is not None else None, None,
                           act_desc(z) if z is not None else None, _ptr(ws), stream_ptr()))
     return (y, use_tc, z) if zsave else (y, use_tc)
 
@@ -471,7 +555,7 @@ def conv_dgrad(dz, dz_img, weight, residual, out_dtype, perm_tc=False):
     ws = _fprop_workspace(dzd, kind, dz.device)
     _timed(("conv_dgrad", cout, cin, r, 0, n, h, w, use_tc),
            lambda: L.call("srk_conv_fprop", dzd, act_desc(dx), pk.data_ptr(), kind, cin, r, s,
-                          None, L.ACT_NONE, None, rd, 0, L.IMPL_AUTO, None, None, None, _ptr(ws), stream_ptr()))
+                          None, L.ACT_NONE, None, rd, 0, L.IMPL_AUTO, None, None, None, None, _ptr(ws), stream_ptr()))
     return dx
 
 
@@ -481,8 +565,8 @@ def conv_dgrad_bnred(dz, weight, z, stats, gamma, beta, alpha, residual=None):
     alpha: slope of the PReLU between the BN and this conv, or None.  residual: added to the dgrad before the
     reduction (dx = dgrad(dz) + residual: the whole gradient of a residual block's input, reduced against the bn2 of
     the block below).
-    -> (dx, red) with red = [sum g | sum g*z | dalpha] (fp32, 2C+1), or None when the fused kernel does not cover
-    the shape (the caller then runs conv_dgrad and the stand-alone reduction)."""
+    -> (dx, red) with red = [sum g | sum g*z | dalpha] (an Acc, or fp32 [2C+1] with SRK_ACC=0), or None when the
+    fused kernel does not cover the shape (the caller then runs conv_dgrad and the stand-alone reduction)."""
     cout, cin, r, s = weight.shape
     if not (cfg.fuse_bn_reduce and cfg.conv_impl != "simt" and r == 3 and s == 3 and cin == 64 and cout == 64
             and dz.dtype == torch.bfloat16 and z.dtype == torch.bfloat16 and dz.shape == z.shape
@@ -491,13 +575,22 @@ def conv_dgrad_bnred(dz, weight, z, stats, gamma, beta, alpha, residual=None):
     n, c, h, w = geometry(dz, False)
     pk = packed_weight(weight, L.PACK_DGRAD_TC, 0)
     dx = new_act(n, cin, h, w, torch.bfloat16, dz.device)
-    red = torch.empty((2 * cin + 1,), dtype=torch.float32, device=dz.device)
-    rc = L.cdll.srk_conv_dgrad_bnred(act_desc(dz), act_desc(dx), pk.data_ptr(), act_desc(z), stats[0].data_ptr(),
-                                     stats[1].data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(alpha),
-                                     red[:cin].data_ptr(), red[cin:2 * cin].data_ptr(),
-                                     red[2 * cin:].data_ptr() if alpha is not None else None,
-                                     act_desc(residual) if residual is not None else None,
-                                     reduce_ws(dz.device), stream_ptr())
+    rd = act_desc(residual) if residual is not None else None
+    rc = 2
+    if cfg.use_acc:
+        red = acc_acquire(dz.device)
+        rc = L.cdll.srk_conv_dgrad_bnred(act_desc(dz), act_desc(dx), pk.data_ptr(), act_desc(z), stats[0].data_ptr(),
+                                         stats[1].data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(alpha),
+                                         None, None, None, rd, None, red.data_ptr(), stream_ptr())
+        if rc != 0:
+            red.dirty = False
+    if rc == 2:
+        red = torch.empty((2 * cin + 1,), dtype=torch.float32, device=dz.device)
+        rc = L.cdll.srk_conv_dgrad_bnred(act_desc(dz), act_desc(dx), pk.data_ptr(), act_desc(z), stats[0].data_ptr(),
+                                         stats[1].data_ptr(), gamma.data_ptr(), beta.data_ptr(), _ptr(alpha),
+                                         red[:cin].data_ptr(), red[cin:2 * cin].data_ptr(),
+                                         red[2 * cin:].data_ptr() if alpha is not None else None, rd,
+                                         reduce_ws(dz.device), None, stream_ptr())
     if rc == 2:
         return None
     if rc != 0:
@@ -596,12 +689,19 @@ def bn_forward(y, gamma, beta, running_mean, running_var, nbt, training, eps, mo
         upd = training and running_mean is not None
         # statistics -> mean / invstd (+ running-stat update) happen inside the apply kernel: one launch per layer
         out = torch.empty_like(y)
-        L.call("srk_bn_apply_train", act_desc(y), sums[0].data_ptr(), sums[1].data_ptr(), n * h * w, eps, momentum,
+        is_acc = isinstance(sums, Acc)
+        L.call("srk_bn_apply_train", act_desc(y), None if is_acc else sums[0].data_ptr(),
+               None if is_acc else sums[1].data_ptr(), n * h * w, eps, momentum,
                _ptr(running_mean) if upd else None, _ptr(running_var) if upd else None,
                _ptr(nbt) if upd else None, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-               _ptr(alpha), act_desc(residual) if residual is not None else None, act_desc(out), st)
+               _ptr(alpha), act_desc(residual) if residual is not None else None, act_desc(out),
+               sums.data_ptr() if is_acc else None, st)
+        if is_acc:
+            sums.dirty = False
         return out, stats
     else:
+        if isinstance(sums, Acc):
+            acc_discard(sums)
         L.call("srk_bn_eval_params", running_mean.data_ptr(), running_var.data_ptr(), c, eps,
                mean.data_ptr(), invstd.data_ptr(), st)
     out = torch.empty_like(y)
@@ -615,13 +715,23 @@ def bn_backward(dout, y, stats, gamma, beta, alpha, batch_stats, pre=None):
     happened in the epilogue of the dgrad that produced dout."""
     c = y.shape[3]
     dev = y.device
+    if isinstance(pre, Acc):
+        out = torch.empty((2 * c + 1,), dtype=torch.float32, device=dev)
+        dgamma, dbeta, dalpha = out[:c], out[c:2 * c], out[2 * c:]
+        dy = torch.empty_like(y)
+        L.call("srk_bn_bwd_apply_raw", act_desc(dout), act_desc(y), stats[0].data_ptr(), stats[1].data_ptr(),
+               gamma.data_ptr(), beta.data_ptr(), _ptr(alpha), None, None, 1 if batch_stats else 0, dgamma.data_ptr(),
+               act_desc(dy), pre.data_ptr(), dbeta.data_ptr(), dalpha.data_ptr() if alpha is not None else None,
+               stream_ptr())
+        pre.dirty = False
+        return dy, dgamma, dbeta, (dalpha if alpha is not None else None)
     if pre is not None:
         sum_g, sum_gz, dalpha = pre[:c], pre[c:2 * c], pre[2 * c:]
         dgamma = torch.empty((c,), dtype=torch.float32, device=dev)
         dy = torch.empty_like(y)
         L.call("srk_bn_bwd_apply_raw", act_desc(dout), act_desc(y), stats[0].data_ptr(), stats[1].data_ptr(),
                gamma.data_ptr(), beta.data_ptr(), _ptr(alpha), sum_g.data_ptr(), sum_gz.data_ptr(),
-               1 if batch_stats else 0, dgamma.data_ptr(), act_desc(dy), stream_ptr())
+               1 if batch_stats else 0, dgamma.data_ptr(), act_desc(dy), None, None, None, stream_ptr())
         return dy, dgamma, sum_g, (dalpha if alpha is not None else None)
     red = torch.empty((2 * c + 1,), dtype=torch.float32, device=dev)
     dgamma, dbeta, dalpha = red[:c], red[c:2 * c], red[2 * c:]

@@ -73,6 +73,9 @@ int srk_conv_tc_supported(int cin, int cout, int r, int s, int dtype, int pixel_
  * bn_sums (fp32 [2][Cout], WRITTEN, or NULL): per-channel sum and sum of squares of the conv output over interior
  * pixels - the statistics native_batch_norm needs (models.py:47,50,114) - produced by the conv epilogue from the
  * fp32 accumulators on the tcgen05 path, summed in a fixed order (needs reduce_ws, see srk_reduce_workspace_bytes).
+ * bn_acc (or NULL; excludes bn_sums): the same statistics delivered into an ACCUMULATOR ("exact sums" below) that
+ * srk_bn_apply_train consumes - the conv then ends without the serial tail of the ordered fold.  Returns 2, and
+ * launches nothing, when the conv is not the single-pass 3x3 64 -> 64 bf16 ACT conv that path covers.
  * prelu_z (or NULL; act = PReLU, ACT outputs): a tensor of y's geometry / dtype that receives the PRE-activation
  * when - and only when - the slope is <= 0 (decided on the device).  nn.PReLU places no constraint on its slope
  * (models.py:48,66,108,119,122); for a slope <= 0 the backward cannot recover sign(z) / z from the output and reads
@@ -81,7 +84,7 @@ int srk_conv_tc_supported(int cin, int cout, int r, int s, int dtype, int pixel_
 int srk_conv_fprop(const srk_tensor* x, const srk_tensor* y, const void* w_packed, int pack_kind,
                    int cout, int r, int s, const float* bias, int act, const float* alpha,
                    const srk_tensor* residual, int pixel_shuffle, int impl, float* bn_sums,
-                   void* reduce_ws, const srk_tensor* prelu_z, void* workspace, void* stream);
+                   void* reduce_ws, void* bn_acc, const srk_tensor* prelu_z, void* workspace, void* stream);
 
 /* ---- deterministic reductions -------------------------------------------------------------------
  * No kernel of the training step accumulates floating-point values with atomics: every cross-block sum (BatchNorm
@@ -91,6 +94,17 @@ int srk_conv_fprop(const srk_tensor* x, const srk_tensor* y, const void* w_packe
  * when it is allocated (its tickets reset themselves), and not shared between streams whose kernels may run
  * concurrently (one per stream). */
 int64_t srk_reduce_workspace_bytes(void);
+/* Exact sums ("accumulators").  The ordered fold ends a kernel with a chain of dependent global-memory steps (5 us on
+ * the 23 us trunk conv).  The trunk convs can instead add their per-CTA partial sums into an accumulator: each fp32
+ * partial is split EXACTLY into radix-2^40 integer digits that are added with 64-bit integer reductions - associative,
+ * so the total is bit-reproducible whatever the arrival order, and exact; non-finite partials make the value read as
+ * NaN.  An accumulator is srk_acc_bytes() bytes of device memory, zero-filled ONCE by the caller; after that a
+ * producer (srk_conv_fprop bn_acc, srk_conv_dgrad_bnred acc) and a consumer (srk_bn_apply_train acc,
+ * srk_bn_bwd_apply_raw acc, srk_acc_read) must alternate on it, in stream order: the consumer converts the digits and
+ * leaves the accumulator zero-filled again.  Values: [sum C | sum of squares C] or [sum g C | sum g*z C | dalpha], C = 64. */
+int64_t srk_acc_bytes(void);
+/* generic consumer: out[i] = value i for i < nv (fp32), accumulator reset */
+int srk_acc_read(void* acc, int nv, float* out, void* stream);
 /* bytes of `workspace` srk_conv_fprop needs for this input and pack kind (0 = may pass NULL): the tcgen05 path
  * carries the fp32 partial sums of a contraction over more than 64 input channels through it. */
 int64_t srk_conv_fprop_workspace_bytes(const srk_tensor* x, int pack_kind);
@@ -111,12 +125,14 @@ int64_t srk_conv_wgrad_workspace_bytes(const srk_tensor* x, const srk_tensor* dy
  * this conv (models.py:57) or NULL.  Writes sum_g[64], sum_gz[64] (raw sums; srk_bn_bwd_apply_raw turns them into
  * dgamma / the dy constants) and dalpha[1].  residual (or NULL): the skip connection's gradient, added to the
  * dgrad BEFORE the reduction - dx = dgrad(dz) + residual is then the whole gradient of a ResidualBlock's input
- * (models.py:60) and z the bn2 input of the block below it.  Returns 0 ok, 1 error, 2 = shape outside the fused
+ * (models.py:60) and z the bn2 input of the block below it.  acc (or NULL): an accumulator that receives the three
+ * sums instead of sum_g / sum_gz / dalpha (which may then be NULL, like reduce_ws); srk_bn_bwd_apply_raw consumes
+ * it.  Returns 0 ok, 1 error, 2 = shape outside the fused
  * kernel (nothing launched; run srk_conv_fprop + srk_bn_bwd_reduce instead). */
 int srk_conv_dgrad_bnred(const srk_tensor* dz, const srk_tensor* dx, const void* w_packed_dgrad, const srk_tensor* z,
                          const float* mean, const float* invstd, const float* gamma, const float* beta,
                          const float* alpha, float* sum_g, float* sum_gz, float* dalpha, const srk_tensor* residual,
-                         void* reduce_ws, void* stream);
+                         void* reduce_ws, void* acc, void* stream);
 
 /* ---- convolutions with an RGB side on tcgen05 (K = 9 or 5; im2col built in shared memory) ---------
  * input_conv / SRCNN conv1 (3 -> 64, models.py:84,107,150) and the backward of output_conv / SRCNN conv3
@@ -178,11 +194,11 @@ int srk_bn_apply(const srk_tensor* y, const float* mean, const float* invstd, co
 /* training-mode BatchNorm in one pass after the statistics: srk_bn_finalize folded into srk_bn_apply (every block
  * derives mean / invstd from (sum, sumsq) itself; block 0 publishes them to mean / invstd for the backward and updates
  * the running statistics and num_batches_tracked when those pointers are non-NULL).  F.batch_norm(training=True) of
- * models.py:56-57,140. */
+ * models.py:56-57,140.  acc (or NULL): the statistics as an accumulator (consumed) instead of sum / sumsq. */
 int srk_bn_apply_train(const srk_tensor* y, const float* sum, const float* sumsq, int64_t count, float eps,
                        float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
                        float* mean, float* invstd, const float* gamma, const float* beta, const float* alpha,
-                       const srk_tensor* residual, const srk_tensor* out, void* stream);
+                       const srk_tensor* residual, const srk_tensor* out, void* acc, void* stream);
 /* backward pass 1: dgamma[C], dbeta[C], dalpha[1] (all fp32, written) */
 int srk_bn_bwd_reduce(const srk_tensor* dout, const srk_tensor* y, const float* mean,
                       const float* invstd, const float* gamma, const float* beta,
@@ -195,10 +211,12 @@ int srk_bn_bwd_apply(const srk_tensor* dout, const srk_tensor* y, const float* m
                      const float* dgamma_b, const float* dbeta_b, int batch_stats,
                      const srk_tensor* dy, void* stream);
 /* as srk_bn_bwd_apply, fed with the raw sums of srk_conv_dgrad_bnred: sum_g = sum g (= dbeta), sum_gz = sum g * z;
- * dgamma_out[C] receives invstd * (sum_gz - mean * sum_g). */
+ * dgamma_out[C] receives invstd * (sum_gz - mean * sum_g).  acc (or NULL): the raw sums as an accumulator (consumed)
+ * instead of sum_g / sum_gz; dbeta_out[C] (= sum g) and dalpha_out[1] (may be NULL) are then written as well. */
 int srk_bn_bwd_apply_raw(const srk_tensor* dout, const srk_tensor* y, const float* mean, const float* invstd,
                          const float* gamma, const float* beta, const float* alpha, const float* sum_g,
-                         const float* sum_gz, int batch_stats, float* dgamma_out, const srk_tensor* dy, void* stream);
+                         const float* sum_gz, int batch_stats, float* dgamma_out, const srk_tensor* dy, void* acc,
+                         float* dbeta_out, float* dalpha_out, void* stream);
 
 /* ---- squeeze-excite gate (models.py:26-41,76-78): mean / mm / sigmoid / mul / add ------------- */
 /* pool[N][C] = mean over H,W of r */

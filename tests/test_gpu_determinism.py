@@ -229,7 +229,12 @@ def test_kernels_do_not_write_outside_their_outputs():
             ops.conv_rgbout_bwd(up, gimg, wout, True, True)
             gamma, beta = torch.ones(64, device=DEV), torch.zeros(64, device=DEV)
             _, stats = ops.bn_forward(y, gamma, beta, None, None, None, True, 1e-5, 0.1, alpha, x64, sums=sums)
-            ops.conv_dgrad_bnred(g64, w64, y, stats, gamma, beta, alpha)
+            fused = ops.conv_dgrad_bnred(g64, w64, y, stats, gamma, beta, alpha)
+            ops.bn_backward(fused[0], y, stats, gamma, beta, alpha, True, pre=fused[1])
+            fused = ops.conv_dgrad_bnred(g64, w64, y, stats, gamma, beta, None, residual=x64)
+            ops.bn_backward(fused[0], y, stats, gamma, beta, None, True, pre=fused[1])
+            ya, _, acc = ops.conv_fprop_stats(x64, w64, None)       # statistics through the integer accumulator
+            ops.bn_forward(ya, gamma, beta, None, None, None, True, 1e-5, 0.1, alpha, x64, sums=acc)
             ops.bn_backward(g64, y, stats, gamma, beta, alpha, True)
             ops.act_bwd(g64, yin, L.ACT_PRELU, alpha, 0)
         torch.cuda.synchronize()

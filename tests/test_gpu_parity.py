@@ -708,8 +708,66 @@ def test_column_strip_conv_edge_geometries(n, h, w, mode):
             assert rel_err(got[fold][1], want_s) <= 2e-3, fold
 
 
+@pytest.fixture(params=[True, False], ids=["acc", "ordered_fold"])
+def sums_mode(request):
+    """BatchNorm sums out of the conv epilogues: exact integer accumulators (default) or the ordered float fold."""
+    from srk import ops
+    old = ops.cfg.use_acc
+    ops.cfg.use_acc = request.param
+    yield request.param
+    ops.cfg.use_acc = old
+
+
+def test_conv_statistics_through_accumulator_are_exact_sums_of_the_cta_partials():
+    """srk_conv_fprop bn_acc -> srk_acc_read: the integer accumulator carries the per-channel (sum, sum of squares) of
+    the conv output; against the ordered float fold of the same per-CTA partials (same kernel, float outputs) and a
+    float64 reference; consumed accumulators are left zero-filled (a second read gives zeros)."""
+    import srk
+    from srk import ops
+    srk.set_compute_dtype("bf16")
+    g = torch.Generator().manual_seed(5)
+    n, c, h, w = 4, 64, 40, 36
+    x = torch.zeros(n, h + 2, w + 2, c)
+    x[:, 1:-1, 1:-1] = torch.randn(n, h, w, c, generator=g)
+    x = x.to(DEV).bfloat16()
+    wt = (torch.randn(64, 64, 3, 3, generator=g) / 24).to(DEV)
+    bias = (torch.randn(64, generator=g) * 0.1).to(DEV)
+    y, used_tc, a = ops.conv_fprop_stats(x, wt, bias)
+    assert used_tc and isinstance(a, ops.Acc)
+    got = ops.acc_read(a, 128).cpu()
+    again = ops.acc_read(a, 128).cpu()
+    assert float(again.abs().max()) == 0.0
+    sums = torch.empty((2, 64), dtype=torch.float32, device=DEV)
+    y2, _ = ops.conv_fprop(x, False, wt, bias, 0, None, None, 0, False, torch.bfloat16, bn_sums=sums)
+    assert torch.equal(y, y2)
+    assert rel_err(got, sums.flatten().cpu()) <= 2e-6
+    pre = F.conv2d(x[:, 1:-1, 1:-1].permute(0, 3, 1, 2).double().cpu(), wt.bfloat16().double().cpu(), bias.double().cpu(),
+                   padding=1)
+    want = torch.cat([pre.sum(dim=(0, 2, 3)), (pre * pre).sum(dim=(0, 2, 3))])
+    assert rel_err(got, want) <= 1e-4
+    # two runs: bit-identical totals whatever the CTA arrival order
+    _, _, a2 = ops.conv_fprop_stats(x, wt, bias)
+    assert torch.equal(ops.acc_read(a2, 128).cpu(), got)
+
+
+def test_accumulator_flags_non_finite_sums():
+    import srk
+    from srk import ops
+    srk.set_compute_dtype("bf16")
+    x = torch.zeros(1, 18, 18, 64)
+    x[0, 5, 5, 3] = float("inf")
+    x = x.to(DEV).bfloat16()
+    wt = torch.ones(64, 64, 3, 3, device=DEV) / 64
+    _, _, a = ops.conv_fprop_stats(x, wt, None)
+    got = ops.acc_read(a, 128).cpu()
+    assert torch.isnan(got).any()
+    x2 = torch.zeros(1, 18, 18, 64).to(DEV).bfloat16()
+    _, _, a = ops.conv_fprop_stats(x2, wt, None)
+    assert float(ops.acc_read(a, 128).abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("with_prelu", [True, False])
-def test_dgrad_with_fused_bn_backward_reduction(with_prelu):
+def test_dgrad_with_fused_bn_backward_reduction(with_prelu, sums_mode):
     """srk_conv_dgrad_bnred: the BatchNorm-backward sums taken in the dgrad epilogue (from the fp32 accumulators)
     against the stand-alone reduction kernel (which re-reads the bf16-rounded gradient), and the raw-sum form of the
     BN-backward apply against the plain one."""
@@ -749,7 +807,7 @@ def test_dgrad_with_fused_bn_backward_reduction(with_prelu):
     assert float(dy_f[:, 0].abs().max()) == 0 and float(dy_f[:, :, -1].abs().max()) == 0
 
 
-def test_dgrad_with_residual_and_fused_bn_backward_reduction():
+def test_dgrad_with_residual_and_fused_bn_backward_reduction(sums_mode):
     """srk_conv_dgrad_bnred with a residual: dx = dgrad(dz) + residual is the whole gradient of a residual block's
     input; the sums of the bn2 of the block below are taken of that total (no PReLU between them, models.py:55-60)."""
     import srk
@@ -776,9 +834,11 @@ def test_dgrad_with_residual_and_fused_bn_backward_reduction():
     want = F.conv_transpose2d(dz[:, 1:-1, 1:-1].permute(0, 3, 1, 2).float().cpu(), wt.cpu(), padding=1) \
         + res[:, 1:-1, 1:-1].permute(0, 3, 1, 2).float().cpu()
     assert rel_err(dx_f[:, 1:-1, 1:-1].permute(0, 3, 1, 2).cpu(), want) <= 1e-2
-    zi = z[:, 1:-1, 1:-1].permute(0, 3, 1, 2).float().cpu()
-    assert rel_err(red[:c].cpu(), want.sum(dim=(0, 2, 3))) <= 2e-3
-    assert rel_err(red[c:2 * c].cpu(), (want * zi).sum(dim=(0, 2, 3))) <= 2e-3
+    assert isinstance(red, ops.Acc) == sums_mode
+    if not sums_mode:
+        zi = z[:, 1:-1, 1:-1].permute(0, 3, 1, 2).float().cpu()
+        assert rel_err(red[:c].cpu(), want.sum(dim=(0, 2, 3))) <= 2e-3
+        assert rel_err(red[c:2 * c].cpu(), (want * zi).sum(dim=(0, 2, 3))) <= 2e-3
     dy_u, dgamma_u, dbeta_u, _ = ops.bn_backward(dx_u, z, stats, gamma, beta, None, True)
     dy_f, dgamma_f, dbeta_f, _ = ops.bn_backward(dx_f, z, stats, gamma, beta, None, True, pre=red)
     assert rel_err(dbeta_f.cpu(), dbeta_u.cpu()) <= 3e-3
@@ -787,7 +847,7 @@ def test_dgrad_with_residual_and_fused_bn_backward_reduction():
     assert float(dx_f[:, 0].abs().max()) == 0 and float(dx_f[:, :, -1].abs().max()) == 0
 
 
-def test_resnet_block_chain_reduction_matches_unfused_backward():
+def test_resnet_block_chain_reduction_matches_unfused_backward(sums_mode):
     """ResNetSR hands the bn2 backward reduction of block k to the last dgrad of block k+1 (fn.BnLink).  Same step
     with every fused BN-backward reduction switched off: gradients agree to the rounding of the sums."""
     import srk

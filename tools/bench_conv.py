@@ -39,6 +39,14 @@ for x, sm in zip(xs, sums):
     _, st = ops.bn_forward(y, gamma, beta, None, None, None, True, 1e-5, 0.1, alpha, None, sums=sm)
     ys.append(y)
     stats.append(st)
+
+
+def unconsumed(a):
+    """timing only: the accumulator keeps accumulating (integer wrap-around is harmless here); no zero-fill launches"""
+    if isinstance(a, ops.Acc):
+        a.dirty = False
+
+
 out = (ctypes.c_float * 2)()
 flop = 2.0 * B * H * H * 64 * 64 * 9
 for fold in (2, 4):
@@ -47,12 +55,13 @@ for fold in (2, 4):
         "fprop": [lambda x=x: ops.conv_fprop(x, False, w, bias, 0, None, None, 0, False, torch.bfloat16) for x in xs],
         "fprop+stats": [lambda x=x, sm=sm: ops.conv_fprop(x, False, w, bias, 0, None, None, 0, False, torch.bfloat16, bn_sums=sm)
                         for x, sm in zip(xs, sums)],
+        "fprop+stats(acc)": [lambda x=x: unconsumed(ops.conv_fprop_stats(x, w, bias)[2]) for x in xs],
         "dgrad+res": [lambda d=d, x=x: ops.conv_dgrad(d, False, w, x, torch.bfloat16) for d, x in zip(ds, xs)],
-        "dgrad+bnred": [lambda d=d, y=y, st=st: ops.conv_dgrad_bnred(d, w, y, st, gamma, beta, alpha)
+        "dgrad+bnred": [lambda d=d, y=y, st=st: unconsumed(ops.conv_dgrad_bnred(d, w, y, st, gamma, beta, alpha)[1])
                         for d, y, st in zip(ds, ys, stats)],
     }
     if fold == 2:
-        cases["dgrad+res+bnred"] = [lambda d=d, y=y, st=st, x=x: ops.conv_dgrad_bnred(d, w, y, st, gamma, beta, None, residual=x)
+        cases["dgrad+res+bnred"] = [lambda d=d, y=y, st=st, x=x: unconsumed(ops.conv_dgrad_bnred(d, w, y, st, gamma, beta, None, residual=x)[1])
                                     for d, y, st, x in zip(ds, ys, stats, xs)]
     for name, fs in cases.items():
         ms = bench._time_replayed(fs)
