@@ -297,13 +297,27 @@ def kernel_rooflines(B, dev, pk, timer=None):
     alpha = torch.full((1,), 0.25, device=dev)
     xs = [act(B, H, H, 64) for _ in range(NSET)]
     ds = [act(B, H, H, 64, 1e-3) for _ in range(NSET)]
-    sums = [torch.empty((2, 64), dtype=torch.float32, device=dev) for _ in range(NSET)]
     ys, stats = [], []
-    for x, sm in zip(xs, sums):
-        y, _ = ops.conv_fprop(x, False, w64, bias, L.ACT_NONE, None, None, 0, False, torch.bfloat16, bn_sums=sm)
+    for x in xs:
+        y, _, sm = ops.conv_fprop_stats(x, w64, bias)
         _, st = ops.bn_forward(y, gamma, beta, None, None, None, True, 1e-5, 0.1, alpha, None, sums=sm)
         ys.append(y)
         stats.append(st)
+    # The BatchNorm sums travel from the conv epilogues to the BatchNorm passes in integer accumulators (include/srk.h
+    # "exact sums"): producer and consumer alternate in the step.  Timed alone, a producer's accumulator is simply left
+    # unconsumed (it keeps accumulating; integer wrap-around is harmless) and a consumer reads a consumed one (zeros):
+    # neither changes the work of the kernel under test, and no zero-fill launch enters the timed region.
+    acc = ops.acc_acquire(dev)
+
+    def produced(a):
+        if isinstance(a, ops.Acc):
+            a.dirty = False
+
+    def consuming(f):
+        def run():
+            acc.dirty = True
+            f(acc)
+        return run
     P = B * H * H
     conv_flop = 2.0 * P * 64 * 64 * 9
     act_bytes = B * (H + 2) * (H + 2) * 64 * 2
@@ -324,12 +338,17 @@ def kernel_rooflines(B, dev, pk, timer=None):
         out.append(rec)
 
     add("conv3x3_c64_fprop+bn_stats", "tensor", conv_flop,
-        [lambda x=x, sm=sm: ops.conv_fprop(x, False, w64, bias, L.ACT_NONE, None, None, 0, False, torch.bfloat16, bn_sums=sm)
-         for x, sm in zip(xs, sums)], 33, "fold::conv3x3_fold_tc_kernel<kStats>: the variant every trunk conv of the step runs")
+        [lambda x=x: produced(ops.conv_fprop_stats(x, w64, bias)[2]) for x in xs], 33,
+        "fold::conv3x3_fold_tc_kernel<kStats>: the variant every trunk conv of the forward pass runs (sums into an accumulator)")
     add("conv3x3_c64_dgrad+bn_bwd_reduce", "tensor", conv_flop,
-        [lambda d=d, y=y, st=st: ops.conv_dgrad_bnred(d, w64, y, st, gamma, beta, alpha) for d, y, st in zip(ds, ys, stats)], 16)
+        [lambda d=d, y=y, st=st: produced(ops.conv_dgrad_bnred(d, w64, y, st, gamma, beta, alpha)[1])
+         for d, y, st in zip(ds, ys, stats)], 16, "conv2 dgrad of a residual block + the bn1 backward sums")
+    add("conv3x3_c64_dgrad+residual+bn_bwd_reduce", "tensor", conv_flop,
+        [lambda d=d, y=y, st=st, x=x: produced(ops.conv_dgrad_bnred(d, w64, y, st, gamma, beta, None, residual=x)[1])
+         for d, y, st, x in zip(ds, ys, stats, xs)], 15,
+        "conv1 dgrad of a residual block + skip gradient + the bn2 backward sums of the block below")
     add("conv3x3_c64_dgrad+residual", "tensor", conv_flop,
-        [lambda d=d, x=x: ops.conv_dgrad(d, False, w64, x, torch.bfloat16) for d, x in zip(ds, xs)], 17)
+        [lambda d=d, x=x: ops.conv_dgrad(d, False, w64, x, torch.bfloat16) for d, x in zip(ds, xs)], 2)
     add("conv3x3_c64_wgrad", "tensor", conv_flop,
         [lambda x=x, d=d: ops.conv_wgrad(x, False, d, False, w64, True) for x, d in zip(xs, ds)], 33,
         "wgrad3x3_tc_kernel + wgrad_fold_kernel (two launches)")
@@ -338,14 +357,19 @@ def kernel_rooflines(B, dev, pk, timer=None):
         [lambda x=x: ops.conv_fprop(x, False, wup, None, L.ACT_PRELU, alpha, None, 2, False, torch.bfloat16) for x in x128], 1)
     del x128
     add("bn_apply_train+prelu", "hbm", 2.0 * act_bytes,
-        [lambda y=y, sm=sm: ops.bn_forward(y, gamma, beta, None, None, None, True, 1e-5, 0.1, alpha, None, sums=sm)
-         for y, sm in zip(ys, sums)], 16)
+        [consuming(lambda a, y=y: ops.bn_forward(y, gamma, beta, None, None, None, True, 1e-5, 0.1, alpha, None, sums=a))
+         for y in ys], 16)
     add("bn_apply_train+residual", "hbm", 3.0 * act_bytes,
-        [lambda y=y, sm=sm, x=x: ops.bn_forward(y, gamma, beta, None, None, None, True, 1e-5, 0.1, None, x, sums=sm)
-         for y, sm, x in zip(ys, sums, xs)], 17)
+        [consuming(lambda a, y=y, x=x: ops.bn_forward(y, gamma, beta, None, None, None, True, 1e-5, 0.1, None, x, sums=a))
+         for y, x in zip(ys, xs)], 17)
+    add("bn_bwd_apply", "hbm", 3.0 * act_bytes,
+        [consuming(lambda a, d=d, y=y, st=st: ops.bn_backward(d, y, st, gamma, beta, alpha, True, pre=a))
+         for d, y, st in zip(ds, ys, stats)], 31,
+        "srk_bn_bwd_apply_raw: 2 reads, 1 write; the sums come out of the dgrad epilogue above it")
     add("bn_bwd_reduce+bn_bwd_apply", "hbm", 5.0 * act_bytes,
-        [lambda d=d, y=y, st=st: ops.bn_backward(d, y, st, gamma, beta, None, True) for d, y, st in zip(ds, ys, stats)], 17,
-        "two launches: reduce (2 reads) + apply (2 reads, 1 write)")
+        [lambda d=d, y=y, st=st: ops.bn_backward(d, y, st, gamma, beta, None, True) for d, y, st in zip(ds, ys, stats)], 2,
+        "two launches: reduce (2 reads) + apply (2 reads, 1 write): the two BatchNorms whose gradient does not come "
+        "out of a 64 -> 64 dgrad (top block, bn_mid)")
     del xs, ds, ys
     # loss / metric kernels on the step's image shapes
     from src.loss import get_loss_function

@@ -140,6 +140,7 @@ inline float* red_partials(void* ws) { return reinterpret_cast<float*>(reinterpr
 // rows.  One SM pulling all rows of a 296-block reduction (150 KB) at the end of the kernel measured +14 us; the two
 // small folds cost about two L2 round trips.  Tickets of a reduction: [0] level 2, [1 + g] group g.
 constexpr int kRedGroup = 8;
+constexpr int kRedFlat = 32;   // grids up to this size fold in one level
 __host__ __device__ inline int red_groups(int nblk) { return (nblk + kRedGroup - 1) / kRedGroup; }
 __host__ __device__ inline int red_tickets_needed(int nblk) { return 1 + red_groups(nblk); }
 // partial floats of one reduction: block rows followed by group rows
@@ -168,8 +169,11 @@ __device__ __forceinline__ void ordered_fold(const float* vals, int NV, unsigned
   __threadfence();
   sync();
   int* flag = reinterpret_cast<int*>(scratch);
-  const int grp = bidx / kRedGroup, ngrp = red_groups(nblk);
-  const int g0 = grp * kRedGroup, gsize = nblk - g0 < kRedGroup ? nblk - g0 : kRedGroup;
+  // grids of up to kRedFlat blocks (the per-image reductions of the squeeze-excite gate, small layers) are ONE group:
+  // the last block to arrive folds every row in block order and finishes - one ticket and one round of loads
+  const int gs = nblk <= kRedFlat ? nblk : kRedGroup;
+  const int grp = bidx / gs, ngrp = (nblk + gs - 1) / gs;
+  const int g0 = grp * gs, gsize = nblk - g0 < gs ? nblk - g0 : gs;
   if (tid == 0) {
     const unsigned k = atomicAdd(ticket + 1 + grp, 1u);
     const int last = (k == (unsigned)gsize - 1u);
@@ -185,15 +189,22 @@ __device__ __forceinline__ void ordered_fold(const float* vals, int NV, unsigned
   float4* grow = rows + (size_t)(nblk + grp) * NV4;
   for (int i = tid; i < NV4; i += T) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int b = 0; b < kRedGroup; ++b) {
-      if (b < gsize) {
-        const float4 v = __ldcg(rows + (size_t)(g0 + b) * NV4 + i);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-      }
+#pragma unroll 4
+    for (int b = 0; b < gsize; ++b) {
+      const float4 v = __ldcg(rows + (size_t)(g0 + b) * NV4 + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    __stcg(grow + i, acc);
+    if (ngrp == 1) {      // single group: these are the totals
+      const int k = 4 * i;
+      finish(k, acc.x);
+      if (k + 1 < NV) finish(k + 1, acc.y);
+      if (k + 2 < NV) finish(k + 2, acc.z);
+      if (k + 3 < NV) finish(k + 3, acc.w);
+    } else {
+      __stcg(grow + i, acc);
+    }
   }
+  if (ngrp == 1) return;
   __threadfence();
   sync();
   if (tid == 0) {
