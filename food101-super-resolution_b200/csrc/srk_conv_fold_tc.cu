@@ -91,6 +91,13 @@ struct Params {
   // ... or, when set, the exact integer accumulator (srk_common.cuh "acc"): value i of [sum 64 | sumsq 64 | dalpha]
   // is added to acc slot i with fire-and-forget reductions and the kernel ends without a serial tail
   unsigned long long* acc;
+  // wide passes (kCPT = 32 on single CTAs, up to 128 output channels per pass: the 96-channel convs of AttentionSR in
+  // ONE output-channel pass): w_bytes of resident weights instead of 72 KB, no staging tiles and no store warp - the
+  // epilogue threads store their 64 bytes of y themselves (direct_out) and read the residual row (res) the same way
+  int w_bytes;
+  int direct_out;
+  int part_stride;     // floats per pixel of partial_out / partial_in
+  const __nv_bfloat16* res;
   // PReLU epilogues with a slope <= 0 also store the pre-activation (same geometry as y) for the backward pass
   __nv_bfloat16* zsave;
   int* err;
@@ -137,7 +144,7 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                        const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
                        const __grid_constant__ CUtensorMap tmZ, const Params p) {
   static_assert(!(kPair && kFold), "the CTA-pair variant is per-tap");
-  static_assert(kCPT == 16 || (kCPT == 32 && kPair && !kFast && !kStats), "N = 128 passes run on CTA pairs");
+  static_assert(kCPT == 16 || (kCPT == 32 && !kFast && !kStats), "32 columns per thread: general instantiation only");
   constexpr int CPT = kCPT;
   constexpr int TMO = Tile<kFold>::TMO, ROW0 = Tile<kFold>::ROW0;
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;
@@ -156,16 +163,19 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   // dynamic smem: [weights 72 KB][A ring][2 output tiles][2 Z tiles iff bn_red == 2][exchange][bias][barriers]
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const bool direct_out = !kFast && p.direct_out != 0;
+  const int w_bytes = kFast ? W_BYTES : p.w_bytes;
   const uint32_t wsm = smem_base;
-  const uint32_t asm0 = smem_base + W_BYTES;
+  const uint32_t asm0 = smem_base + w_bytes;
   const uint32_t osm = asm0 + p.stages * p.stage_bytes;
-  uint8_t* optr = smem_al + W_BYTES + p.stages * p.stage_bytes;
+  uint8_t* optr = smem_al + w_bytes + p.stages * p.stage_bytes;
   const bool two_in = kStats && p.bn_red == 2;   // residual tile AND Z tile per output tile
+  const int o_bytes = direct_out ? 0 : 2 * O_TILE_BYTES;
   const int z_bytes = two_in ? 2 * O_TILE_BYTES : 0;
   const uint32_t zsm = osm + 2 * O_TILE_BYTES;
-  float* xch = reinterpret_cast<float*>(optr + 2 * O_TILE_BYTES + z_bytes);
-  float* bias_s = reinterpret_cast<float*>(optr + 2 * O_TILE_BYTES + z_bytes + XCH_BYTES);
-  Barriers* bars = reinterpret_cast<Barriers*>(optr + 2 * O_TILE_BYTES + z_bytes + XCH_BYTES + BIAS_BYTES);
+  float* xch = reinterpret_cast<float*>(optr + o_bytes + z_bytes);
+  float* bias_s = reinterpret_cast<float*>(optr + o_bytes + z_bytes + XCH_BYTES);
+  Barriers* bars = reinterpret_cast<Barriers*>(optr + o_bytes + z_bytes + XCH_BYTES + BIAS_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
@@ -311,7 +321,7 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
   } else if (warp == 2) {
     // ================= output store / residual load warp (plain, non-PixelShuffle outputs) =================
-    if (shuffle == 0 && partial_out == nullptr && !(dbg & 1)) {
+    if (shuffle == 0 && partial_out == nullptr && !direct_out && !(dbg & 1)) {
       const int first = kPair ? (int)blockIdx.x - (int)rank : (int)blockIdx.x;   // lockstep with the pair's first tile
       const int my_tiles = first < p.num_tiles ? (p.num_tiles - first + gridDim.x - 1) / gridDim.x : 0;
       if (p.has_residual && elect_one()) {
@@ -354,7 +364,8 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const int c0 = cq * CPT;
     const float alpha = (act == SRK_ACT_PRELU) ? __ldg(p.alpha) : 0.f;
     const bool active = c0 < n_cols;
-    const bool staged = shuffle == 0 && partial_out == nullptr && !(dbg & 1);
+    const bool staged = shuffle == 0 && partial_out == nullptr && !direct_out && !(dbg & 1);
+    const int part_stride = kFast ? NT : p.part_stride;
     const int row = lg * 32 + lane;
     const bool has_row = row >= ROW0 && row < ROW0 + TMO;
     const int src_up = (lane + 31) & 31, src_dn = (lane + 1) & 31;
@@ -486,7 +497,7 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       if (tr) trace[7 * 32 + it] = clock64();
       if (dbg & 1) continue;
       if (partial_in && is_out) {   // fp32 partial sums of the earlier contraction chunks
-        const float4* pin = reinterpret_cast<const float4*>(partial_in + (long long)pix * NT + c0);
+        const float4* pin = reinterpret_cast<const float4*>(partial_in + (long long)pix * part_stride + c0);
 #pragma unroll
         for (int j = 0; j < CPT / 4; ++j) {
           const float4 q4 = __ldg(pin + j);
@@ -495,7 +506,7 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
       if (partial_out) {              // not the last chunk: keep fp32, no activation, nothing goes to y
         if (is_out) {
-          float4* po = reinterpret_cast<float4*>(partial_out + (long long)pix * NT + c0);
+          float4* po = reinterpret_cast<float4*>(partial_out + (long long)pix * part_stride + c0);
 #pragma unroll
           for (int j = 0; j < CPT / 4; ++j) po[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
         }
@@ -538,6 +549,32 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         for (int j = 0; j < CPT / 8; ++j)
           dst[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
                               pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+        continue;
+      }
+      if (direct_out) {
+        // wide pass: this thread's CPT channels of its pixel, straight from registers (border pixels as zeros)
+        if (is_out) {
+          const long long go = (long long)pix * p.cout_total + p.cout_off + c0;
+          if (p.has_residual && interior) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res + go);
+#pragma unroll
+            for (int j = 0; j < CPT / 8; ++j) {
+              const uint4 rr = __ldg(rp + j);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) { const float2 u = __bfloat1622float2(h[t]); f[8 * j + 2 * t] += u.x; f[8 * j + 2 * t + 1] += u.y; }
+            }
+          }
+          uint4* dst = reinterpret_cast<uint4*>(p.y + go);
+#pragma unroll
+          for (int j = 0; j < CPT / 8; ++j) {
+            uint4 o = make_uint4(0, 0, 0, 0);
+            if (interior)
+              o = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                             pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+            dst[j] = o;
+          }
+        }
         continue;
       }
       const int bn_red = kStats ? p.bn_red : 0;
@@ -727,8 +764,11 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
   if (acc != nullptr && br == nullptr && stats_sum == nullptr) { stats_sum = (float*)acc; stats_sumsq = (float*)acc; }
   // variant: 0 per-tap, 1 folded taps, 2 per-tap on CTA pairs (cta_group::2), 3 = CTA pairs with 128 output
   // channels per pass (PixelShuffle outputs of a single-chunk contraction: the 64 -> 256 upsample convs)
-  const bool folded = variant == 1, pair = variant == 2 || variant == 3;
-  const int pass_n = variant == 3 ? 2 * NT : NT;
+  // 4 = wide single-CTA passes: all output channels (64 < Cout <= 128, Cout % 32 == 0) in ONE pass per contraction chunk
+  const bool folded = variant == 1, pair = variant == 2 || variant == 3, wide = variant == 4;
+  const int pass_n = variant == 3 ? 2 * NT : (wide ? cout : NT);
+  SRK_REQUIRE(!wide || (shuffle == 0 && cout > NT && cout <= 2 * NT && cout % 32 == 0 && stats_sum == nullptr && br == nullptr),
+              "conv_fold: wide passes serve plain convs with 64 < Cout <= 128 output channels");
   SRK_REQUIRE(variant != 3 || (shuffle == 2 && x->c == KC && cout % pass_n == 0 && residual == nullptr && stats_sum == nullptr),
               "conv_fold: 128-channel passes serve single-chunk PixelShuffle convs with Cout %% 128 == 0");
   const int TMO = folded ? Tile<true>::TMO : Tile<false>::TMO;
@@ -745,10 +785,12 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
     set_smem_all<false, false>(smem_max);
     set_smem_all<false, true>(smem_max);
     set_smem<false, false, false, ACT_RUNTIME, true, 32>(smem_max);
+    set_smem<false, false, false, ACT_RUNTIME, false, 32>(smem_max);
   }
   const int slab_rows = ((TM + 2 * Wp + (folded ? 0 : 2)) + SLAB_BOX_ROWS - 1) / SLAB_BOX_ROWS * SLAB_BOX_ROWS;
-  const int fixed = 1024 + W_BYTES + 2 * O_TILE_BYTES + ((br && residual) ? 2 * O_TILE_BYTES : 0) + XCH_BYTES + BIAS_BYTES +
-                    (int)sizeof(Barriers);
+  const int w_bytes = wide ? 9 * cout * KC * 2 : W_BYTES;
+  const int fixed = 1024 + w_bytes + (wide ? 0 : 2 * O_TILE_BYTES) + ((br && residual) ? 2 * O_TILE_BYTES : 0) + XCH_BYTES +
+                    BIAS_BYTES + (int)sizeof(Barriers);
   const int stage_bytes = slab_rows * KC * 2;
   int stages = (smem_max - fixed) / stage_bytes;
   if (stages < 2) return -1;
@@ -781,6 +823,8 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
   p.red_ticket = reduce_ws ? red_tickets(reduce_ws) : nullptr;
   p.red_part = reduce_ws ? red_partials(reduce_ws) : nullptr;
   p.acc = (unsigned long long*)acc;
+  p.w_bytes = w_bytes; p.direct_out = wide ? 1 : 0; p.part_stride = wide ? cout : NT;
+  p.res = residual ? (const __nv_bfloat16*)residual->data : nullptr;
   p.zsave = (__nv_bfloat16*)zsave;
   p.bn_red = 0; p.bn_mask = 0;
   p.bn_mean = p.bn_invstd = p.bn_gamma = p.bn_beta = nullptr; p.bn_dalpha = nullptr;
@@ -827,7 +871,8 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
       p.act = last ? act : SRK_ACT_NONE;
       // chunked contractions: see srk_conv_tc.cu (bf16 partial sums through y without an activation, fp32 partial
       // sums through the workspace when an activation / PixelShuffle follows)
-      const bool fp32_partials = kchunks > 1 && (act != SRK_ACT_NONE || shuffle != 0);
+      // (wide passes have no staged tile to carry a bf16 partial sum: always fp32 through the workspace)
+      const bool fp32_partials = kchunks > 1 && (act != SRK_ACT_NONE || shuffle != 0 || wide);
       if (fp32_partials) {
         p.has_residual = (last && residual) ? 1 : 0;
         p.partial_out = last ? nullptr : (float*)workspace;
@@ -845,6 +890,8 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
       cudaError_t le;
       if (variant == 3)
         le = launch_one<false, false, false, ACT_RUNTIME, true, 32>(grid, smem_bytes, st, tmA, tmW, tmY, tmRes, tmZ, p);
+      else if (wide)
+        le = launch_one<false, false, false, ACT_RUNTIME, false, 32>(grid, smem_bytes, st, tmA, tmW, tmY, tmRes, tmZ, p);
       else if (folded) le = launch_pass<true, false>(fast, stats_sum != nullptr, p.act, grid, smem_bytes, st, tmA, tmW, tmY, tmRes, tmZ, p);
       else if (pair) le = launch_pass<false, true>(fast, stats_sum != nullptr, p.act, grid, smem_bytes, st, tmA, tmW, tmY, tmRes, tmZ, p);
       else le = launch_pass<false, false>(fast, stats_sum != nullptr, p.act, grid, smem_bytes, st, tmA, tmW, tmY, tmRes, tmZ, p);

@@ -555,6 +555,7 @@ int tc_read_err_flag() {
 // pipeline of srk_conv_fold_tc.cu, 3 = as 2 on CTA pairs (cta_group::2, M = 256)
 static int g_tc_fold = -1;
 static int g_up_pair = -1;
+static int g_tc_wide = -1;   // 64 < Cout <= 128 in one output-channel pass (SRK_TC_WIDE, srk_tc_probe 40 / 41)
 int tc_fold() {
   if (g_tc_fold < 0) {
     const char* e = getenv("SRK_TC_FOLD");
@@ -566,7 +567,8 @@ int tc_fold() {
 
 int64_t conv_fprop_tc_workspace(const srk_tensor* x) {
   if (x->c <= KC) return 0;  // (needed when an activation or PixelShuffle follows a chunked contraction)
-  return (int64_t)x->n * (x->h + 2) * (x->w + 2) * NT * (int64_t)sizeof(float);
+  // up to 128 columns per pixel: the wide passes of srk_conv_fold_tc.cu keep all output channels of a <= 128-channel conv
+  return (int64_t)x->n * (x->h + 2) * (x->w + 2) * 2 * NT * (int64_t)sizeof(float);
 }
 
 bool conv_tc_shape_ok(int cin, int cout, int r, int s, int dtype, int shuffle) {
@@ -603,6 +605,18 @@ int conv_fprop_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* w
     const int rc = conv_fprop_fold_launch(x, y, w_packed, cout, bias, act, alpha, residual, shuffle, nullptr, nullptr,
                                           workspace, 3, st, nullptr, nullptr, zsave);
     if (rc >= 0) return rc;
+  }
+  // 64 < Cout <= 128 (the 96-channel trunk of AttentionSR): every output channel in ONE pass per contraction chunk -
+  // two launches per conv instead of four.  Parity-green but OFF by default (SRK_TC_WIDE=1 selects it): measured on
+  // config C3 17.5 vs 16.2 ms per step - its epilogue threads store 64-byte rows and read fp32 partial sums / residual
+  // rows themselves (no room for staging tiles next to 110 KB of weights), and that costs more than the two launches
+  // and the narrower MMAs of the 64 + 32 column passes save.
+  if (g_tc_wide < 0) { const char* e = getenv("SRK_TC_WIDE"); g_tc_wide = e ? atoi(e) != 0 : 0; }
+  if (r == 3 && g_tc_wide && tc_fold() >= 2 && shuffle == 0 && cout > NT && cout <= 2 * NT && cout % 32 == 0 &&
+      stats_sum == nullptr && (x->c <= KC || workspace != nullptr)) {
+    const int rc = conv_fprop_fold_launch(x, y, w_packed, cout, bias, act, alpha, residual, shuffle, nullptr, nullptr,
+                                          workspace, 4, st, nullptr, nullptr, zsave);
+    if (rc >= 0) return rc;   // -1: slab does not fit
   }
   if (r == 3 && tc_fold() == 4) {
     const int rc = conv_fprop_strip_launch(x, y, w_packed, cout, bias, act, alpha, residual, shuffle, stats_sum,
@@ -741,6 +755,7 @@ extern "C" int srk_tc_probe(int variant, float* out_host, int out_len) {
   if (variant >= 0 && variant <= 2) srk::tc_set_mode(variant);
   if (variant >= 10 && variant <= 14) { srk::tc_fold(); srk::g_tc_fold = variant - 10; }  // 3x3 kernel choice (see tc_fold)
   if (variant == 30 || variant == 31) srk::g_up_pair = variant - 30;   // N = 128 CTA-pair upsample convs off / on
+  if (variant == 40 || variant == 41) srk::g_tc_wide = variant - 40;   // wide (64 < Cout <= 128) single-pass convs off / on
   if (variant == 20 && out_host && out_len >= 2) {   // query: out[1] = 1 when the folded-tap kernel is the default
     out_host[0] = 0.f;
     out_host[1] = (float)srk::tc_fold();

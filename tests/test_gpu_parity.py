@@ -157,7 +157,11 @@ CONV_CASES = [
     (64, 256, 3, 20, 20, 1, "prelu", 2),
     (128, 64, 3, 12, 30, 2, "relu", 0),     # two full contraction chunks
     (64, 64, 3, 3, 300, 1, "prelu", 0),     # too wide for two halo-slab stages: per-tap TMA loads, wgrad fallback
+    (96, 96, 3, 20, 17, 2, "none", 0),      # 64 + 32 chunks without an activation (bf16 partial sums through y)
+    (64, 128, 3, 12, 14, 2, "relu", 0),     # VGG-like: two output passes, single chunk
+    (256, 96, 3, 9, 11, 1, "none", 0),      # four contraction chunks (the upsample dgrad shape of AttentionSR)
 ]
+WIDE_CASES = [c for c in CONV_CASES if c[2] == 3 and 64 < c[1] <= 128]
 
 
 def _oracle_conv(x, w, b, alpha, act, shuffle):
@@ -251,6 +255,65 @@ def test_conv3x3_both_tc_kernels_vs_oracle(cin, cout, k, h, w, n, act, shuffle, 
     finally:
         L.call("srk_tc_probe", 10 + default, out, 2)
         assert out[0] == 0, "tcgen05 protocol error flag %r" % out[0]
+
+
+def _with_wide(wide, body):
+    import ctypes
+    from srk import _lib as L
+    out = (ctypes.c_float * 2)()
+    L.call("srk_tc_probe", 40 + wide, out, 2)
+    try:
+        body()
+    finally:
+        L.call("srk_tc_probe", 40, out, 2)
+        assert out[0] == 0, "tcgen05 protocol error flag %r" % out[0]
+
+
+@pytest.mark.parametrize("cin,cout,k,h,w,n,act,shuffle", WIDE_CASES)
+def test_wide_single_pass_convs_vs_oracle(cin, cout, k, h, w, n, act, shuffle):
+    """SRK_TC_WIDE=1 (off by default): 64 < Cout <= 128 output channels in ONE pass per contraction chunk on the 16-warp
+    pipeline - 32 accumulator columns per epilogue thread, outputs / partial sums / residual rows moved by the epilogue
+    threads themselves."""
+    def body():
+        test_conv_forward_backward_vs_oracle(cin, cout, k, h, w, n, act, shuffle, "bf16")
+        if act == "prelu":
+            test_conv_forward_backward_vs_oracle(cin, cout, k, h, w, n, act, shuffle, "bf16", slope=-0.1)
+    _with_wide(1, body)
+
+
+@pytest.mark.parametrize("wide", [0, 1])
+def test_96_channel_conv_with_residual_vs_oracle(wide):
+    """96 -> 96 with a skip connection (AttentionSR mid_conv + `initial`, models.py:185) and its data gradient, on the
+    64 + 32 column passes (default) and on the one-pass wide kernel."""
+    import srk
+    from srk import fn
+    srk.set_compute_dtype("bf16")
+
+    def body():
+        g = torch.Generator().manual_seed(77)
+        n, c, h, w = 2, 96, 19, 23
+        x = torch.randn(n, c, h, w, generator=g).bfloat16().float()
+        res = torch.randn(n, c, h, w, generator=g).bfloat16().float()
+        wt = (torch.randn(c, c, 3, 3, generator=g) / math.sqrt(c * 9)).bfloat16().float()
+        b = torch.randn(c, generator=g) * 0.1
+        go = torch.randn(n, c, h, w, generator=g).bfloat16().float()
+        xo, ro, wo = [t.clone().requires_grad_(True) for t in (x, res, wt)]
+        yo = F.conv2d(xo, wo, b, padding=1) + ro
+        yo.backward(go)
+        conv = torch.nn.Conv2d(c, c, 3, padding=1).to(DEV)
+        with torch.no_grad():
+            conv.weight.copy_(wt)
+            conv.bias.copy_(b)
+        xg, rg = x.to(DEV).requires_grad_(True), res.to(DEV).requires_grad_(True)
+        ya = fn.conv_act(fn.ImageToAct.apply(xg, torch.bfloat16), conv, residual=fn.ImageToAct.apply(rg, torch.bfloat16))
+        y = fn.ActToImage.apply(ya)
+        y.backward(go.to(DEV))
+        assert rel_err(y.cpu(), yo) <= 1e-2
+        assert rel_err(xg.grad.cpu(), xo.grad) <= 1e-2
+        assert rel_err(rg.grad.cpu(), ro.grad) <= 1e-2
+        assert rel_err(conv.weight.grad.cpu(), wo.grad) <= 1e-2
+        assert float(ya[:, 0].abs().max()) == 0 and float(ya[:, :, -1].abs().max()) == 0
+    _with_wide(wide, body)
 
 
 def test_upsample_conv_on_cta_pairs_vs_oracle():
@@ -446,8 +509,8 @@ def test_rgb_input_conv_tcgen05_vs_oracle(k, n, h, w, act, cout):
         conv.weight.copy_(conv.weight.bfloat16().float())
     alpha = torch.tensor([0.25])
     ao = alpha.clone().requires_grad_(True)
-    yo = conv(x)
-    yo = F.prelu(yo, ao) if act == "prelu" else (F.relu(yo) if act == "relu" else yo)
+    pre = conv(x)
+    yo = F.prelu(pre, ao) if act == "prelu" else (F.relu(pre) if act == "relu" else pre)
     go = torch.randn(yo.shape, generator=g).bfloat16().float()
     yo.backward(go)
     ref_w, ref_b = conv.weight.grad.clone(), conv.bias.grad.clone()
@@ -462,7 +525,10 @@ def test_rgb_input_conv_tcgen05_vs_oracle(k, n, h, w, act, cout):
     assert rel_err(conv.weight.grad.cpu(), ref_w) <= 1e-2
     assert rel_err(conv.bias.grad.cpu(), ref_b) <= 1e-2
     if act == "prelu":
-        assert rel_err(al.grad.cpu(), ao.grad) <= 1e-2
+        # dalpha = sum over z < 0 of g * z is a signed, heavily cancelling sum (the conv weights come from the global
+        # RNG, so its size relative to its terms varies with the test order): the yardstick is the sum of magnitudes
+        scale = float((go.abs() * pre.detach().abs() * (pre.detach() < 0)).sum())
+        assert abs(float(al.grad) - float(ao.grad)) <= 2e-3 * scale, (float(al.grad), float(ao.grad), scale)
     assert float(ya[:, 0].abs().max()) == 0 and float(ya[:, :, -1].abs().max()) == 0
 
 
