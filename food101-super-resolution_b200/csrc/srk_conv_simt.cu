@@ -149,9 +149,38 @@ __global__ void zero_border_kernel(T* p, int N, int Hp, int Wp, int C) {
   }
 }
 
+// the same with 16-byte stores: one thread per 16-byte chunk of a ring pixel (CB = chunks per pixel)
+__global__ void zero_border_vec_kernel(uint4* p, int N, int Hp, int Wp, int CB) {
+  const int ring = 2 * Wp + 2 * (Hp - 2);
+  const long long total = (long long)N * ring * CB;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int per_img = ring * CB;
+    const int n = (int)(i / per_img);
+    const int t = (int)(i - (long long)n * per_img);
+    const int rp = t / CB, cb = t - rp * CB;
+    int y, x;
+    if (rp < Wp) { y = 0; x = rp; }
+    else if (rp < 2 * Wp) { y = Hp - 1; x = rp - Wp; }
+    else { const int q = rp - 2 * Wp; y = 1 + (q >> 1); x = (q & 1) ? Wp - 1 : 0; }
+    p[(((long long)n * Hp + y) * Wp + x) * CB + cb] = make_uint4(0, 0, 0, 0);
+  }
+}
+
 int zero_border(const srk_tensor* t, cudaStream_t st) {
   if (t->layout != SRK_LAYOUT_ACT) return 0;
   int Hp = t->h + 2, Wp = t->w + 2;
+  const int pixel_bytes = t->c * (t->dtype == SRK_BF16 ? 2 : 4);
+  if (pixel_bytes % 16 == 0 && ((uintptr_t)t->data & 15) == 0) {
+    const int CB = pixel_bytes / 16;
+    const long long chunks = (long long)t->n * (2 * Wp + 2 * (Hp - 2)) * CB;
+    int blocks = (int)((chunks + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    zero_border_vec_kernel<<<blocks, 256, 0, st>>>((uint4*)t->data, t->n, Hp, Wp, CB);
+    SRK_CUDA_LAUNCH_CHECK("zero_border");
+    return 0;
+  }
   long long total = (long long)t->n * (2 * Wp + 2 * (Hp - 2)) * t->c;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
