@@ -13,8 +13,12 @@
 // descriptors instead of K*K), the horizontal tap shift to the OUTPUT (a shifted sum across neighbouring
 // pixels = neighbouring TMEM lanes, done with warp shuffles in the epilogue).  M tile = 8 rows x 16 pixels;
 // the 16 - (K-1) centre columns of a tile are complete, tiles overlap horizontally by K-1 pixels.
-// One 4-D TMA box brings the (4 + K-1) x 32 pixel halo (zero outside the image) as [rows][32 px][128 B]
+// One 4-D TMA box brings the (TY + K-1) x 32 pixel halo (zero outside the image) as [rows][32 px][128 B]
 // SWIZZLE_128B, so every row shift is a whole number of 1024-byte swizzle atoms.
+// A CTA tile is TG = 3 such M tiles stacked vertically (12 rows x 32 pixels, three accumulators) on ONE halo of
+// 12 + K-1 rows: with a single 4-row M tile the 9x9 conv fetched 12 halo rows per 4 output rows - 512 bytes of
+// L2 -> shared-memory traffic per output pixel, 2.2 GB per launch at config C2, which bounded the kernel (336 us);
+// three stacked tiles share the vertical halo (284 bytes per output pixel).
 #include "srk_common.cuh"
 #include "srk_tc_common.cuh"
 
@@ -24,6 +28,9 @@ using namespace tc;
 int* tc_err_flag();
 
 constexpr int TY = 4, TXW = 32, KC = 64;   // M tile = 4 rows x 32 pixels: 32 - (K-1) of 32 columns are complete
+constexpr int TG = 3;                      // M tiles per CTA tile (stacked vertically, one accumulator each)
+constexpr int ACC_STRIDE = 32 * TG;        // TMEM columns of one accumulator buffer
+constexpr int TMEM_COLS = 256;             // 2 buffers x TG x 32 columns, rounded up to a power of two
 constexpr int kThreads = 192;
 constexpr int MAX_STAGES = 4;
 
@@ -69,7 +76,7 @@ conv_smalln_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(&bars->tmem_base), 64);
+    tmem_alloc(smem_u32(&bars->tmem_base), TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -92,7 +99,7 @@ conv_smalln_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int n = tile / tiles_per_img, t2 = tile - n * tiles_per_img;
-      const int y0 = (t2 / p.tiles_x) * TY, x0 = (t2 % p.tiles_x) * p.xv;
+      const int y0 = (t2 / p.tiles_x) * (TY * TG), x0 = (t2 % p.tiles_x) * p.xv;
       if (!mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1, p.err, 21)) break;
       if (elect_one()) {
         const uint32_t fb = smem_u32(&bars->full[s]);
@@ -118,14 +125,16 @@ conv_smalln_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       ok = mbar_wait(smem_u32(&bars->full[s]), ph, p.err, 24);
       if (!ok) break;
       tc_fence_after();
-      const uint32_t halo_lo = lo_base + ((hsm + s * p.stage_bytes) >> 4), d_tmem = tmem_base + acc * 32;
+      const uint32_t halo_lo = lo_base + ((hsm + s * p.stage_bytes) >> 4), d_tmem = tmem_base + acc * ACC_STRIDE;
       if (elect_one()) {
 #pragma unroll
-        for (int r = 0; r < K; ++r)
+        for (int g = 0; g < TG; ++g)   // M tile g: output rows 4g .. 4g+3 of the CTA tile = halo rows 4g + r ..
 #pragma unroll
-          for (int ks = 0; ks < KC / 16; ++ks)
-            umma_bf16(d_tmem, hi | (halo_lo + r * (TXW * 128 / 16) + 2 * ks), hi | (w_lo + r * (NP * 128 / 16) + 2 * ks),
-                      idesc, (r | ks) != 0);
+          for (int r = 0; r < K; ++r)
+#pragma unroll
+            for (int ks = 0; ks < KC / 16; ++ks)
+              umma_bf16(d_tmem + g * 32, hi | (halo_lo + (g * TY + r) * (TXW * 128 / 16) + 2 * ks),
+                        hi | (w_lo + r * (NP * 128 / 16) + 2 * ks), idesc, (r | ks) != 0);
         umma_commit(smem_u32(&bars->empty[s]));
         umma_commit(smem_u32(&bars->tfull[acc]));
       }
@@ -144,29 +153,35 @@ conv_smalln_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       const int acc = it & 1;
       if (!mbar_wait(smem_u32(&bars->tfull[acc]), (it >> 1) & 1, p.err, 25)) break;
       tc_fence_after();
-      uint32_t v[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * 32;
-      tmem_ld_32x16(taddr, v);
-      if (NP == 32) tmem_ld_32x16(taddr + 16, v + 16);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(smem_u32(&bars->tempty[acc]));
-      // out[q][co] = sum_s Z[q + (s - PAD)][(s, co)]: the neighbour's value comes by shuffle
-      float o[3] = {b[0], b[1], b[2]};
-#pragma unroll
-      for (int s = 0; s < K; ++s) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float z = __shfl_sync(0xffffffffu, __uint_as_float(v[s * 3 + c]), (lane + s - PAD) & 31);
-          o[c] += z;
-        }
-      }
       const int n = tile / tiles_per_img, t2 = tile - n * tiles_per_img;
-      const int y = (t2 / p.tiles_x) * TY + ty, x = (t2 % p.tiles_x) * p.xv + tx - PAD;
-      if (tx >= PAD && tx < TXW - PAD && y < p.H && x < p.W) {
+      const int x = (t2 % p.tiles_x) * p.xv + tx - PAD;
+#pragma unroll 1
+      for (int g = 0; g < TG; ++g) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * ACC_STRIDE + g * 32;
+        tmem_ld_32x16(taddr, v);
+        if (NP == 32) tmem_ld_32x16(taddr + 16, v + 16);
+        tmem_ld_wait();
+        if (g == TG - 1) {   // the whole buffer is in registers (or stored): MMA may refill it
+          tc_fence_before();
+          mbar_arrive(smem_u32(&bars->tempty[acc]));
+        }
+        // out[q][co] = sum_s Z[q + (s - PAD)][(s, co)]: the neighbour's value comes by shuffle
+        float o[3] = {b[0], b[1], b[2]};
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
-          if (c < p.cout) p.out[(((size_t)n * p.cout + c) * p.H + y) * p.W + x] = o[c];
+        for (int s = 0; s < K; ++s) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float z = __shfl_sync(0xffffffffu, __uint_as_float(v[s * 3 + c]), (lane + s - PAD) & 31);
+            o[c] += z;
+          }
+        }
+        const int y = (t2 / p.tiles_x) * (TY * TG) + g * TY + ty;
+        if (tx >= PAD && tx < TXW - PAD && y < p.H && x < p.W) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            if (c < p.cout) p.out[(((size_t)n * p.cout + c) * p.H + y) * p.W + x] = o[c];
+        }
       }
     }
   }
@@ -174,7 +189,7 @@ conv_smalln_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 64);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -216,11 +231,11 @@ int conv_smalln_tc_launch(const srk_tensor* x, const srk_tensor* y, const void* 
   p.N = x->n; p.H = x->h; p.W = x->w; p.K = r; p.pad = r / 2; p.cout = cout;
   p.npad = r * 3 > 16 ? 32 : 16;
   p.xv = TXW - (r - 1);
-  p.tiles_x = (p.W + p.xv - 1) / p.xv; p.tiles_y = (p.H + TY - 1) / TY;
+  p.tiles_x = (p.W + p.xv - 1) / p.xv; p.tiles_y = (p.H + TY * TG - 1) / (TY * TG);
   const long long nt = (long long)p.N * p.tiles_x * p.tiles_y;
   SRK_REQUIRE(nt < (1LL << 31), "conv_smalln: too many tiles");
   p.num_tiles = (int)nt;
-  p.halo_rows = TY + r - 1;
+  p.halo_rows = TY * TG + r - 1;
   p.stage_bytes = p.halo_rows * TXW * 128;                 // multiple of 2048
   p.w_bytes = (r * p.npad * 128 + 1023) / 1024 * 1024;
   const int fixed = 1024 + p.w_bytes + (int)sizeof(SmallNBarriers);
