@@ -1,8 +1,9 @@
 // The 3x3 trunk convolution on tcgen05 / TMEM / TMA (fprop, and dgrad through rotated weights) on the zero-bordered
 // channels-last bf16 layout: ONE pipeline, three formulations of the MMA loop (template parameters of the kernel).
 //
-// Pipeline - one persistent CTA per SM, 608 threads: warp 0 TMA producer (halo slab [128 + 2(W+2) (+2) rows][64 ch] per
-// tile, weights once), warp 1 MMA issuer, warp 2 output TMA store / residual TMA load, warps 3-18 epilogue (four per TMEM
+// Pipeline - one persistent CTA per SM, 640 threads: warp 0 TMA producer (halo slab [128 + 2(W+2) (+2) rows][64 ch] per
+// tile, weights once), warps 1 and 19 MMA issuers (even / odd tiles), warp 2 output TMA store / residual TMA load,
+// warps 3-18 epilogue (four per TMEM
 // lane group, 16 output channels each; activation compiled in, incremental pixel walker, one accumulator-free arrival
 // per warp), accumulators double buffered in TMEM.  Optional epilogue fusions: BatchNorm forward statistics
 // (kStats), BatchNorm BACKWARD reduction against a second input tile (Params::bn_red, srk_conv_dgrad_bnred).
@@ -45,7 +46,8 @@ constexpr int SLAB_BOX_ROWS = 32;
 constexpr int kEpiWarp0 = 3;         // first epilogue warp
 constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;   // 608
+constexpr int kMma2Warp = kEpiWarp0 + kEpiWarps;         // second MMA issuer (odd tiles), behind the epilogue warps
+constexpr int kThreads = (kMma2Warp + 1) * 32;           // 640
 constexpr int CPT = 16;              // accumulator columns (output channels) per epilogue thread
 constexpr int O_TILE_BYTES = TM * NT * 2;  // bf16 output tile staged for the TMA store (126 rows used)
 constexpr int XCH_BYTES = 2 * 4 * 4 * 2 * CPT * 4;  // [acc][column quarter][lane group][slot 0 / slot 2][16 floats]
@@ -94,6 +96,7 @@ struct Params {
   // wide passes (kCPT = 32 on single CTAs, up to 128 output channels per pass: the 96-channel convs of AttentionSR in
   // ONE output-channel pass): w_bytes of resident weights instead of 72 KB, no staging tiles and no store warp - the
   // epilogue threads store their 64 bytes of y themselves (direct_out) and read the residual row (res) the same way
+  int mma_warps;       // 2: warps 1 and kMma2Warp issue alternate tiles; 1: warp 1 issues every tile
   int w_bytes;
   int direct_out;
   int part_stride;     // floats per pixel of partial_out / partial_in
@@ -260,9 +263,14 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       __syncwarp();
       if (++s == S) { s = 0; ph ^= 1; }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == kMma2Warp) {
     if (rank == 0) {   // rank 1 of a pair has no MMA work: its operands are consumed by rank 0's instructions
-    // ================= MMA issuer (rank 0 of a pair issues for both CTAs) =================
+    // ================= MMA issuers (rank 0 of a pair issues for both CTAs) =================
+    // TWO issuing warps, one per accumulator buffer: warp 1 takes the even tiles of this CTA, warp kMma2Warp the odd
+    // ones.  Between two tiles an issuer commits and waits on two mbarriers - ~480 cycles in which at most two queued
+    // MMAs (~100 cycles) keep the tensor pipe busy (per-tile trace, profiles/r2_trace_pertap_kernel_*.txt: 36 MMAs
+    // issued in ~1 820 cycles, next tile's first MMA ~480 cycles later).  Tiles are independent (different accumulator,
+    // read-only operands, per-thread tcgen05.commit), so the second issuer's MMAs fill the first one's gap.
     const uint32_t idesc = make_idesc_bf16(kPair ? 2 * TM : TM, kFold ? 3 * n_cols : n_cols, 0, 0);
     const uint64_t desc_hi = make_smem_desc(0, 16, 1024, kLayoutSW128, 0) & 0xFFFFFFFF00000000ull;
     const uint32_t lo_base = (uint32_t)(make_smem_desc(0, 16, 1024, kLayoutSW128, 0) & 0xFFFFFFFFull);
@@ -271,10 +279,15 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const uint32_t wrow_units = (uint32_t)(3 * w_rows) * (KC * 2 / 16);   // one kernel row of weights (this CTA's rows)
     const uint32_t stage_units = (uint32_t)p.stage_bytes >> 4;
     bool ok = mbar_wait(smem_u32(&bars->wfull), 0, p.err, 2);
-    int s = 0, it = 0;
-    uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile_ok(tile) && ok; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
+    // (with fewer than three slab stages both in-flight tiles would hold every stage and the producer could not run
+    // ahead: dgrad + residual + BN-reduce measured 32.5 us with two issuers against 29.6 us with one)
+    const int nmw = p.mma_warps;
+    const int mw = warp == 1 ? 0 : 1;
+    if (mw >= nmw) ok = false;
+    for (int tile = blockIdx.x + mw * gridDim.x, it = mw; tile_ok(tile) && ok; tile += nmw * gridDim.x, it += nmw) {
+      const int acc = it & 1;                       // = mw
+      const int s = it % S;                         // slab stage and its phase follow the CTA's tile counter
+      const uint32_t ph = (uint32_t)(it / S) & 1u;
       ok = mbar_wait(smem_u32(&bars->tempty[acc]), ((it >> 1) & 1) ^ 1, p.err, 3);
       if (!ok) break;
       ok = mbar_wait(smem_u32(&bars->full[s]), ph, p.err, 4);
@@ -316,7 +329,6 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (trace && blockIdx.x == 0 && it < 32) trace[2 * 32 + it] = clock64();
       }
       __syncwarp();
-      if (++s == S) { s = 0; ph ^= 1; }
     }
     }
   } else if (warp == 2) {
@@ -824,6 +836,11 @@ int conv_fprop_fold_launch(const srk_tensor* x, const srk_tensor* y, const void*
   p.red_part = reduce_ws ? red_partials(reduce_ws) : nullptr;
   p.acc = (unsigned long long*)acc;
   p.w_bytes = w_bytes; p.direct_out = wide ? 1 : 0; p.part_stride = wide ? cout : NT;
+  {
+    static int two = -1;   // SRK_TC_MMA2=0: a single MMA-issuing warp (A/B measurements)
+    if (two < 0) { const char* e = getenv("SRK_TC_MMA2"); two = e ? atoi(e) != 0 : 1; }
+    p.mma_warps = (two && stages >= 3) ? 2 : 1;
+  }
   p.res = residual ? (const __nv_bfloat16*)residual->data : nullptr;
   p.zsave = (__nv_bfloat16*)zsave;
   p.bn_red = 0; p.bn_mask = 0;

@@ -139,9 +139,12 @@ inline void reduce_grid(const Geo& g, int& blocks, int& ppb) {
 
 // The BatchNorm apply passes (forward and backward) read two tensors and write one: 4 blocks / SM measured best
 // (bn_apply + residual 20.6 vs 21.7 us, bn_bwd_apply 21.0 vs 23.7 us at 4 vs 8 blocks / SM, C2 layer shape).
-inline void bn_map_grid(const Geo& g, int& blocks, int& ppb) {
-  static int per_sm = 0;
-  if (!per_sm) { const char* e = getenv("SRK_EW_BN_PER_SM"); per_sm = e ? atoi(e) : 4; if (per_sm < 1) per_sm = 4; }
+// resident: blocks of the kernel that fit on an SM (0 = not queried): a grid of 4 blocks / SM whose blocks only fit three
+// at a time runs as 1.33 waves (bn_bwd_apply at 79 registers: 33.5 us; sized to what is resident: 25.4 us).
+inline void bn_map_grid(const Geo& g, int& blocks, int& ppb, int resident = 0) {
+  static int per_sm_env = 0;
+  if (!per_sm_env) { const char* e = getenv("SRK_EW_BN_PER_SM"); per_sm_env = e ? atoi(e) : 4; if (per_sm_env < 1) per_sm_env = 4; }
+  const int per_sm = (resident > 0 && resident < per_sm_env) ? resident : per_sm_env;
   long long target = 148LL * per_sm;
   long long p = (g.pixels + target - 1) / target;
   if (p < 64) p = 64;
@@ -1006,6 +1009,13 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const T* __restrict__
   }
 }
 
+template <typename K>
+static int resident_blocks(K kernel, int smem = 0) {
+  int occ = 0;   // queried per launch (microseconds, and nothing at all when a captured graph is replayed)
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, smem) != cudaSuccess || occ < 1) occ = 1;
+  return occ;
+}
+
 #define DISPATCH_T_VEC(t, ...)                                            \
   do {                                                                    \
     const bool vec8__ = ((t)->c % 8 == 0) && ((t)->c / 8 <= 256);         \
@@ -1101,9 +1111,10 @@ extern "C" int srk_bn_apply(const srk_tensor* y, const float* mean, const float*
   SRK_REQUIRE(same_geometry(y, out) && y->dtype == out->dtype, "srk_bn_apply: geometry mismatch");
   if (residual) SRK_REQUIRE(same_geometry(y, residual) && residual->dtype == y->dtype && residual->layout == SRK_LAYOUT_ACT, "srk_bn_apply: residual mismatch");
   SRK_REQUIRE(c_ok(y), "srk_bn_apply: unsupported channel count %d", y->c);
-  Geo g = geo_of(y); int blocks, ppb; bn_map_grid(g, blocks, ppb);
+  Geo g = geo_of(y); int blocks = 0, ppb = 0;
   BnFinalize fin = {};
-  DISPATCH_T_VEC(y, (launch_dep(PDL_BN, bn_apply_kernel<T, VEC>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream,
+  DISPATCH_T_VEC(y, (bn_map_grid(g, blocks, ppb, resident_blocks(bn_apply_kernel<T, VEC>)),
+                     launch_dep(PDL_BN, bn_apply_kernel<T, VEC>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream,
                         (const T*)y->data, g, ppb, mean, invstd, gamma, beta, alpha,
                         residual ? (const T*)residual->data : nullptr, (T*)out->data, fin)));
   SRK_CUDA_LAUNCH_CHECK("bn_apply");
@@ -1122,11 +1133,12 @@ extern "C" int srk_bn_apply_train(const srk_tensor* y, const float* sum, const f
   SRK_REQUIRE(((sum && sumsq) || acc) && mean && invstd && count > 0, "srk_bn_apply_train: statistics buffers required");
   SRK_REQUIRE(acc == nullptr || 2 * y->c + 1 <= kAccNV, "srk_bn_apply_train: an accumulator holds at most %d values", kAccNV);
   SRK_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "srk_bn_apply_train: running_mean / running_var go together");
-  Geo g = geo_of(y); int blocks, ppb; bn_map_grid(g, blocks, ppb);
+  Geo g = geo_of(y); int blocks = 0, ppb = 0;
   BnFinalize fin = {sum, sumsq, (double)count, eps, momentum, running_mean, running_var,
                     (long long*)num_batches_tracked, mean, invstd, (unsigned long long*)acc};
   const size_t smem = 2 * (size_t)y->c * sizeof(float);
-  DISPATCH_T_VEC(y, (launch_dep(PDL_BN, bn_apply_kernel<T, VEC>, dim3(blocks), dim3(256), smem, (cudaStream_t)stream,
+  DISPATCH_T_VEC(y, (bn_map_grid(g, blocks, ppb, resident_blocks(bn_apply_kernel<T, VEC>, (int)smem)),
+                     launch_dep(PDL_BN, bn_apply_kernel<T, VEC>, dim3(blocks), dim3(256), smem, (cudaStream_t)stream,
                         (const T*)y->data, g, ppb, nullptr, nullptr, gamma, beta, alpha,
                         residual ? (const T*)residual->data : nullptr, (T*)out->data, fin)));
   SRK_CUDA_LAUNCH_CHECK("bn_apply_train");
@@ -1160,9 +1172,10 @@ extern "C" int srk_bn_bwd_apply(const srk_tensor* dout, const srk_tensor* y, con
   SRK_REQUIRE(same_geometry(y, dout) && same_geometry(y, dy) && y->dtype == dout->dtype && y->dtype == dy->dtype,
               "srk_bn_bwd_apply: geometry mismatch");
   SRK_REQUIRE(c_ok(y), "srk_bn_bwd_apply: unsupported channel count %d", y->c);
-  Geo g = geo_of(y); int blocks, ppb; bn_map_grid(g, blocks, ppb);
+  Geo g = geo_of(y); int blocks = 0, ppb = 0;
   float inv_count = 1.f / ((float)y->n * y->h * y->w);
-  DISPATCH_T_VEC(y, (launch_dep(PDL_BN, bn_bwd_apply_kernel<T, VEC>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream,
+  DISPATCH_T_VEC(y, (bn_map_grid(g, blocks, ppb, resident_blocks(bn_bwd_apply_kernel<T, VEC>)),
+                     launch_dep(PDL_BN, bn_bwd_apply_kernel<T, VEC>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream,
                         (const T*)dout->data, (const T*)y->data, g, ppb, mean, invstd, gamma, beta,
                         alpha, dgamma_b, dbeta_b, inv_count, batch_stats, (T*)dy->data, nullptr, nullptr, nullptr, nullptr)));
   SRK_CUDA_LAUNCH_CHECK("bn_bwd_apply");
@@ -1181,9 +1194,10 @@ extern "C" int srk_bn_bwd_apply_raw(const srk_tensor* dout, const srk_tensor* y,
   SRK_REQUIRE(((sum_g && sum_gz) || (acc && dbeta_out)) && dgamma_out,
               "srk_bn_bwd_apply_raw: sums (or an accumulator and dbeta_out) and dgamma_out are required");
   SRK_REQUIRE(acc == nullptr || 2 * y->c + 1 <= kAccNV, "srk_bn_bwd_apply_raw: an accumulator holds at most %d values", kAccNV);
-  Geo g = geo_of(y); int blocks, ppb; bn_map_grid(g, blocks, ppb);
+  Geo g = geo_of(y); int blocks = 0, ppb = 0;
   float inv_count = 1.f / ((float)y->n * y->h * y->w);
-  DISPATCH_T_VEC(y, (launch_dep(PDL_BN, bn_bwd_apply_kernel<T, VEC>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream,
+  DISPATCH_T_VEC(y, (bn_map_grid(g, blocks, ppb, resident_blocks(bn_bwd_apply_kernel<T, VEC>)),
+                     launch_dep(PDL_BN, bn_bwd_apply_kernel<T, VEC>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream,
                         (const T*)dout->data, (const T*)y->data, g, ppb, mean, invstd, gamma, beta,
                         alpha, sum_gz, sum_g, inv_count, batch_stats, (T*)dy->data, dgamma_out,
                         (unsigned long long*)acc, dbeta_out, dalpha_out)));
