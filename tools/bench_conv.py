@@ -49,7 +49,7 @@ def unconsumed(a):
 
 out = (ctypes.c_float * 2)()
 flop = 2.0 * B * H * H * 64 * 64 * 9
-for fold in (2, 4):
+for fold in [int(v) for v in os.environ.get("FOLDS", "2,4").split(",")]:
     L.call("srk_tc_probe", 10 + fold, out, 2)
     cases = {
         "fprop": [lambda x=x: ops.conv_fprop(x, False, w, bias, 0, None, None, 0, False, torch.bfloat16) for x in xs],
