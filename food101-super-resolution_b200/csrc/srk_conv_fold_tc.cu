@@ -594,7 +594,9 @@ conv3x3_fold_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 #pragma unroll
         for (int j = 0; j < CPT; ++j) { s1[j] += f[j]; s2[j] = fmaf(f[j], f[j], s2[j]); }
       }
+      if (tr) trace[8 * 32 + it] = clock64();
       if (ok) ok = mbar_wait(smem_u32(&bars->ofree[acc]), ((it >> 1) & 1) ^ 1, p.err, 7);
+      if (tr) trace[10 * 32 + it] = clock64();
       if (p.has_residual && ok) ok = mbar_wait(smem_u32(&bars->rfull[acc]), (it >> 1) & 1, p.err, 8);
       if (p.has_residual && bn_red != 1 && has_row) {
 #pragma unroll

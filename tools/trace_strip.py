@@ -28,7 +28,8 @@ names = {0: "tma issue", 1: "mma: loop top", 2: "mma: slot free", 3: "mma: slab 
          6: "epi: tfull", 7: "epi: staged", 8: "store: oready", 9: "store: read out"}
 if FOLD != 4:   # stamps of fold::conv3x3_fold_tc_kernel
     names = {0: "tma: slab issued", 1: "mma: slab full", 2: "mma: tile issued", 3: "epi: wait acc", 4: "epi: acc full",
-             5: "epi: acc in regs", 7: "epi: values done", 9: "epi: residual in", 11: "epi: tile staged",
+             5: "epi: acc in regs", 7: "epi: values done", 8: "epi: wait ofree", 10: "epi: ofree", 9: "epi: residual in",
+             11: "epi: tile staged",
              12: "store: tile ready", 13: "store: smem read"}
 print("FOLD=%d  B=%d  clock cycles since the first stamp, CTA 0, first 20 tiles" % (FOLD, B))
 for r, nm in names.items():
