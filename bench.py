@@ -457,18 +457,49 @@ def run_srk(args):
     trainer(lr_d, hr_d)
     graphed = trainer.static_inputs(lr_d, hr_d) is not None
 
-    # e2e: every step's LR/HR batch comes from pinned host memory.  The copy of step i+1 is issued on a copy stream
-    # while step i computes (staging buffers); the step then takes it with a device-to-device hand-over.
+    # e2e: every step's batch comes from pinned host memory.  The copy of step i+1 is issued on a copy stream while
+    # step i computes (staging buffers); the step then takes it with a device-to-device hand-over.
+    #   --e2e-input u8 (default): what train.py ships with its GPU sample pipeline (SRK_GPU_PIPELINE=1, srk/data.py) -
+    #     decoded uint8 HR crops [B, H, W, 3] + crop offsets / flip flags; srk_sr_make_batch (ToTensor + antialiased
+    #     bicubic, reference dataset.py:27-41) runs inside the timed region on the device;
+    #   --e2e-input fp32: the finished fp32 (lr, hr) pair, as a host-side torchvision pipeline would deliver it.
+    from srk import data as srk_data
     copy_stream = torch.cuda.Stream()
     lr_n, hr_n = torch.empty_like(lr_d), torch.empty_like(hr_d)
     ev_h2d, ev_taken = torch.cuda.Event(), torch.cuda.Event()
+    u8 = args.e2e_input == "u8" and SCALE in (2, 4)
+    if u8:
+        HRS = LR_HW * SCALE
+        src_pin = torch.randint(0, 256, (B, HRS, HRS, 3), dtype=torch.uint8,
+                                generator=torch.Generator().manual_seed(99 + rank)).pin_memory()
+        offs_pin = torch.zeros((B, 2), dtype=torch.int32).pin_memory()
+        flips_pin = (torch.arange(B) % 2).to(torch.uint8).pin_memory()
+        src_n = torch.empty(src_pin.shape, dtype=torch.uint8, device=dev)
+        offs_n = torch.empty(offs_pin.shape, dtype=torch.int32, device=dev)
+        flips_n = torch.empty(flips_pin.shape, dtype=torch.uint8, device=dev)
+        h2d_bytes = src_pin.numel() + offs_pin.numel() * 4 + flips_pin.numel()
+    else:
+        h2d_bytes = lr_pin.numel() * 4 + hr_pin.numel() * 4
 
     def prefetch():
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(ev_taken)
-            lr_n.copy_(lr_pin, non_blocking=True)
-            hr_n.copy_(hr_pin, non_blocking=True)
+            if u8:
+                src_n.copy_(src_pin, non_blocking=True)
+                offs_n.copy_(offs_pin, non_blocking=True)
+                flips_n.copy_(flips_pin, non_blocking=True)
+            else:
+                lr_n.copy_(lr_pin, non_blocking=True)
+                hr_n.copy_(hr_pin, non_blocking=True)
             ev_h2d.record(copy_stream)
+
+    def take_batch(lr_dst, hr_dst):
+        """this step's (lr, hr) from the staging buffers the copy stream has filled, into the step's input tensors"""
+        if u8:
+            srk_data.make_batch_into(src_n, offs_n, flips_n, LR_HW * SCALE, SCALE, lr_dst, hr_dst)
+        else:
+            lr_dst.copy_(lr_n, non_blocking=True)
+            hr_dst.copy_(hr_n, non_blocking=True)
 
     def timed(nsteps, e2e):
         barrier()
@@ -481,21 +512,20 @@ def run_srk(args):
         for i in range(nsteps):
             if e2e:
                 main.wait_event(ev_h2d)
+                # the step is enqueued before the next copy is (host time between two steps is GPU idle time: the loss
+                # read below drains the device every step)
                 if graphed:
                     s_lr, s_hr = trainer.static_inputs(lr_d, hr_d)
-                    s_lr.copy_(lr_n, non_blocking=True)
-                    s_hr.copy_(hr_n, non_blocking=True)
+                    take_batch(s_lr, s_hr)
                     ev_taken.record(main)
-                    if i + 1 < nsteps:
-                        prefetch()
-                    trainer.replay(lr_d, hr_d).item()
+                    loss = trainer.replay(lr_d, hr_d)
                 else:
-                    lr_d.copy_(lr_n, non_blocking=True)
-                    hr_d.copy_(hr_n, non_blocking=True)
+                    take_batch(lr_d, hr_d)
                     ev_taken.record(main)
-                    if i + 1 < nsteps:
-                        prefetch()
-                    trainer(lr_d, hr_d).item()
+                    loss = trainer(lr_d, hr_d)
+                if i + 1 < nsteps:
+                    prefetch()
+                loss.item()
             elif graphed:
                 trainer.replay(lr_d, hr_d)
             else:
@@ -549,7 +579,9 @@ def run_srk(args):
                        "final_loss": round(loss_value, 5), "step_tflops": round(step_tf, 2),
                        "step_frac_of_bf16_sustained": round(step_tf / (world * pk["tf_sustained"]), 4)},
             "e2e": {"value": round(world * B / (ms_e2e * 1e-3), 2), "unit": "images/s",
-                    "h2d_bytes_per_step": int(lr_pin.numel() * 4 + hr_pin.numel() * 4), "d2h_bytes_per_step": 4},
+                    "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
+                    "input": ("uint8 HR crops + crop offsets / flips; ToTensor + antialiased bicubic on the GPU inside the "
+                              "timed region (train.py's default pipeline)") if u8 else "fp32 (lr, hr) pair"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "rooflines": roofs}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
@@ -656,6 +688,8 @@ def main():
     ap.add_argument("--eval-images", type=int, default=1250, help="--config C4: images per GPU (10 000 / 8)")
     ap.add_argument("--cpu-batch", type=int, default=0,
                     help="--impl reference: images per CPU step (default: the config's batch when it fits the time budget)")
+    ap.add_argument("--e2e-input", default="u8", choices=["u8", "fp32"],
+                    help="what the e2e leg ships per step: decoded uint8 crops (GPU sample pipeline) or the fp32 pair")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-rooflines", action="store_true", help="skip the per-kernel roofline measurements")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")

@@ -57,6 +57,22 @@ def make_batch(src_u8, offsets, flips, crop, scale):
     return lr, hr
 
 
+def make_batch_into(src_u8, offsets, flips, crop, scale, lr_out, hr_out):
+    """make_batch writing into caller-owned float32 tensors (e.g. the static inputs of a captured training step):
+    no allocation, no extra device-to-device copy.  offsets int32 [N, 2] / flips uint8 [N] must be on the device."""
+    ops.require_cuda(src_u8, "make_batch")
+    assert src_u8.dtype == torch.uint8 and src_u8.dim() == 4 and src_u8.is_contiguous()
+    hwc = src_u8.shape[3] == 3
+    n = src_u8.shape[0]
+    hs, ws = (src_u8.shape[1], src_u8.shape[2]) if hwc else (src_u8.shape[2], src_u8.shape[3])
+    assert tuple(hr_out.shape) == (n, 3, crop, crop) and tuple(lr_out.shape) == (n, 3, crop // scale, crop // scale)
+    assert hr_out.dtype == torch.float32 and lr_out.dtype == torch.float32 and hr_out.is_contiguous() and lr_out.is_contiguous()
+    assert offsets.is_cuda and flips.is_cuda and offsets.dtype == torch.int32 and flips.dtype == torch.uint8
+    L.call("srk_sr_make_batch", src_u8.data_ptr(), 1 if hwc else 0, n, hs, ws, offsets.data_ptr(), flips.data_ptr(), crop,
+           scale, hr_out.data_ptr(), lr_out.data_ptr(), ops.stream_ptr())
+    return lr_out, hr_out
+
+
 def collate_raw(samples):
     """DataLoader collate_fn for raw samples (uint8 [h, w, 3] tensors): pads to the largest image of the batch
     -> (uint8 [N, Hmax, Wmax, 3], sizes [(h, w), ...])."""
