@@ -1009,10 +1009,18 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const T* __restrict__
   }
 }
 
+// blocks of 256 threads of `kernel` that fit on an SM; queried once per (kernel, dynamic shared memory)
 template <typename K>
 static int resident_blocks(K kernel, int smem = 0) {
-  int occ = 0;   // queried per launch (microseconds, and nothing at all when a captured graph is replayed)
+  struct Entry { const void* k; int smem, occ; };
+  static Entry cache[32];
+  static int n = 0;
+  const void* key = reinterpret_cast<const void*>(kernel);
+  for (int i = 0; i < n; ++i)
+    if (cache[i].k == key && cache[i].smem == smem) return cache[i].occ;
+  int occ = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, smem) != cudaSuccess || occ < 1) occ = 1;
+  if (n < 32) cache[n++] = {key, smem, occ};   // (a race between two host threads at worst repeats the query)
   return occ;
 }
 

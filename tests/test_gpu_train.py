@@ -112,6 +112,10 @@ def test_gpu_sample_pipeline_matches_torchvision(scale, crop):
     # channels-first uint8 input gives the same result
     lr2, hr2 = D.make_batch(src.permute(0, 3, 1, 2).contiguous().to("cuda:0"), offs, flips, crop, scale)
     assert torch.equal(hr2, hr) and torch.equal(lr2, lr)
+    # the in-place form (bench.py's e2e leg writes the batch straight into the captured step's input tensors)
+    lr3, hr3 = torch.full_like(lr, -1.0), torch.full_like(hr, -1.0)
+    D.make_batch_into(src.to("cuda:0"), offs.to("cuda:0"), flips.to("cuda:0"), crop, scale, lr3, hr3)
+    assert torch.equal(hr3, hr) and torch.equal(lr3, lr)
 
 
 def test_visualize_tool_runs_on_reference_checkpoints(synthetic_env, monkeypatch):
