@@ -2,11 +2,14 @@
 // channels-last bf16 layout: ONE pipeline, three formulations of the MMA loop (template parameters of the kernel).
 //
 // Pipeline - one persistent CTA per SM, 640 threads: warp 0 TMA producer (halo slab [128 + 2(W+2) (+2) rows][64 ch] per
-// tile, weights once), warps 1 and 19 MMA issuers (even / odd tiles), warp 2 output TMA store / residual TMA load,
-// warps 3-18 epilogue (four per TMEM
-// lane group, 16 output channels each; activation compiled in, incremental pixel walker, one accumulator-free arrival
-// per warp), accumulators double buffered in TMEM.  Optional epilogue fusions: BatchNorm forward statistics
-// (kStats), BatchNorm BACKWARD reduction against a second input tile (Params::bn_red, srk_conv_dgrad_bnred).
+// tile, weights once), warps 1 and 19 MMA issuers (even / odd tiles, one accumulator buffer each), warp 2 output TMA
+// store / residual (+ Z) TMA loads, warps 3-18 epilogue (four per TMEM lane group, 16 output channels each; activation
+// compiled in, incremental pixel walker, one accumulator-free arrival per warp), accumulators double buffered in TMEM.
+// Optional epilogue fusions: BatchNorm forward statistics (kStats), BatchNorm BACKWARD reduction against a second
+// input tile, with or without a residual added first (Params::bn_red, srk_conv_dgrad_bnred); the per-CTA sums leave
+// through the ordered fold or, without a serial tail, as integer digits into an accumulator (Params::acc).
+//   kCPT = 32 on single CTAs (Params::direct_out, SRK_TC_WIDE=1): 64 < Cout <= 128 in one pass, epilogue threads move
+//     their own rows (no staging tiles next to 110-147 KB of weights).  Parity-green, slower on config C3: off by default.
 //
 //   kFold = 0 (DEFAULT): one MMA group per tap, N = 64: Y[p, co] = sum_{tap, ci} X[p + d(tap), ci] W[tap][co][ci] with
 //     the 9 taps as row-shifted descriptors into the slab.  Bound by the shared-memory port.
