@@ -267,7 +267,8 @@ __device__ __forceinline__ void ordered_fold(const float* vals, int NV, unsigned
 // of them; what lies below 2^-94 is dropped) and each non-zero digit is added to a 64-bit counter with a fire-and-
 // forget red.global.add.u64.  Integer addition is associative, so the total does not depend on the order in which
 // the CTAs arrive - bit-reproducible like ordered_fold, and exact - and nothing waits for a reply.  A sixth counter
-// counts non-finite contributions (the sum then reads as NaN).  The CONSUMER kernel (bn_apply_train /
+// counts non-finite contributions and partial sums >= 2^120 (the sum then reads as NaN; below that bound 2^9
+// contributors cannot overflow a counter: tests/test_acc_model.py checks the arithmetic on the host).  The CONSUMER kernel (bn_apply_train /
 // bn_bwd_apply_raw / acc_read) converts the digits back in its prologue, and the consumer block that draws the last
 // ticket - taken right after the prologue, its latency hidden behind the block's main loop - zero-fills the
 // accumulator for its next use.  Contract: zero-filled once by the caller, then producer and consumer alternate.
@@ -278,7 +279,9 @@ __device__ __forceinline__ double acc_unit(int k) {   // 2^(-94 + 40 k)
   return __longlong_as_double((long long)(1023 - 94 + 40 * k) << 52);
 }
 __device__ __forceinline__ void acc_add(unsigned long long* acc, int i, float p) {
-  if (!(fabsf(p) <= 3.402823466e38f)) { atomicAdd(acc + kAccLimbs * kAccNV + i, 1ull); return; }
+  // NaN, Inf and partial sums of 2^120 and more (148 of them would overflow the top counter - and the float32 total
+  // anyway) count as non-finite
+  if (!(fabsf(p) < 1.329227995784916e36f)) { atomicAdd(acc + kAccLimbs * kAccNV + i, 1ull); return; }
   double r = (double)p;
 #pragma unroll
   for (int k = kAccLimbs - 1; k >= 0; --k) {

@@ -97,8 +97,8 @@ int64_t srk_reduce_workspace_bytes(void);
 /* Exact sums ("accumulators").  The ordered fold ends a kernel with a chain of dependent global-memory steps (5 us on
  * the 23 us trunk conv).  The trunk convs can instead add their per-CTA partial sums into an accumulator: each fp32
  * partial is split EXACTLY into radix-2^40 integer digits that are added with 64-bit integer reductions - associative,
- * so the total is bit-reproducible whatever the arrival order, and exact; non-finite partials make the value read as
- * NaN.  An accumulator is srk_acc_bytes() bytes of device memory, zero-filled ONCE by the caller; after that a
+ * so the total is bit-reproducible whatever the arrival order, and exact; non-finite partials (and partials of
+ * 2^120 and more, which could overflow a counter) make the value read as NaN.  An accumulator is srk_acc_bytes() bytes of device memory, zero-filled ONCE by the caller; after that a
  * producer (srk_conv_fprop bn_acc, srk_conv_dgrad_bnred acc) and a consumer (srk_bn_apply_train acc,
  * srk_bn_bwd_apply_raw acc, srk_acc_read) must alternate on it, in stream order: the consumer converts the digits and
  * leaves the accumulator zero-filled again.  Values: [sum C | sum of squares C] or [sum g C | sum g*z C | dalpha], C = 64. */
